@@ -1,0 +1,89 @@
+"""Oracle (test infrastructure): HEALPix pixel centres, ring and nested ordering.
+
+Stands in for ``astropy_healpix.HEALPix(nside, order, frame).healpix_to_skycoord(hpx_inds)`` at the
+reference call site ``src/pyradiosky/skymodel.py:1664-1667`` (``get_lon_lat`` healpix branch).
+astropy-healpix (>=1.0.2, reference pyproject.toml:43) is a third-party dependency absent from this
+image, so the published HEALPix pix2ang formulas (Gorski et al. 2005) are restated.  PARITY UNPINNED
+against astropy-healpix itself; pinned by invariants (ring/nested give the same centre set, equal
+areas => sum of unit vectors ~ 0, z non-increasing in ring order, pixel 357 @ nside 8 of
+reference test_skymodel.py:2094).
+"""
+
+import numpy as np
+
+_JRLL = np.array([2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4], dtype=np.int64)
+_JPLL = np.array([1, 3, 5, 7, 0, 2, 4, 6, 1, 3, 5, 7], dtype=np.int64)
+
+
+def _isqrt(v):
+    r = np.floor(np.sqrt(v.astype(np.float64))).astype(np.int64)
+    r = np.where(r * r > v, r - 1, r)
+    r = np.where((r + 1) * (r + 1) <= v, r + 1, r)
+    return r
+
+
+def _compact_bits(v):
+    """Keep the even bits of v and pack them (inverse of bit interleaving)."""
+    v = v & 0x5555555555555555
+    v = (v | (v >> 1)) & 0x3333333333333333
+    v = (v | (v >> 2)) & 0x0F0F0F0F0F0F0F0F
+    v = (v | (v >> 4)) & 0x00FF00FF00FF00FF
+    v = (v | (v >> 8)) & 0x0000FFFF0000FFFF
+    v = (v | (v >> 16)) & 0x00000000FFFFFFFF
+    return v
+
+
+def pix2zphi(nside, pix, nested=False):
+    """Return (z, one_minus_abs_z, phi) of pixel centres; the exact 1-|z| is kept for the caps."""
+    nside = int(nside)
+    pix = np.asarray(pix, dtype=np.int64)
+    npix = 12 * nside * nside
+    ncap = 2 * nside * (nside - 1)
+    nl4 = 4 * nside
+    if nested:
+        npface = nside * nside
+        face = pix // npface
+        ipf = pix % npface
+        ix = _compact_bits(ipf)
+        iy = _compact_bits(ipf >> 1)
+        jr = _JRLL[face] * nside - ix - iy - 1
+        north = jr < nside
+        south = jr > 3 * nside
+        nr = np.where(north, jr, np.where(south, nl4 - jr, nside))
+        kshift = np.where(north | south, 0, (jr - nside) & 1)
+        jp = (_JPLL[face] * nr + ix - iy + 1 + kshift) // 2
+        jp = np.where(jp > nl4, jp - nl4, jp)
+        jp = np.where(jp < 1, jp + nl4, jp)
+        iring_eq = jr
+    else:
+        north = pix < ncap
+        south = pix >= npix - ncap
+        # north cap
+        irn = (1 + _isqrt(1 + 2 * np.where(north, pix, 0))) >> 1
+        ipn = pix + 1 - 2 * irn * (irn - 1)
+        # south cap
+        ips = npix - pix
+        irs = (1 + _isqrt(2 * np.where(south, ips, 1) - 1)) >> 1
+        ipsn = 4 * irs + 1 - (ips - 2 * irs * (irs - 1))
+        # equatorial belt
+        ipe = pix - ncap
+        ire = ipe // nl4 + nside
+        ipen = ipe % nl4 + 1
+        nr = np.where(north, irn, np.where(south, irs, nside))
+        jp = np.where(north, ipn, np.where(south, ipsn, ipen))
+        kshift = np.where(north | south, 0, (ire - nside) & 1)
+        iring_eq = ire
+    nrf = nr.astype(np.float64)
+    omz_cap = nrf * nrf / (3.0 * nside * nside)
+    z_eq = (2 * nside - iring_eq).astype(np.float64) * (2.0 / (3.0 * nside))
+    z = np.where(north, 1.0 - omz_cap, np.where(south, omz_cap - 1.0, z_eq))
+    omz = np.where(north | south, omz_cap, 1.0 - np.abs(z_eq))
+    phi = (jp.astype(np.float64) - (kshift + 1) * 0.5) * ((np.pi / 2.0) / nrf)
+    return z, omz, phi
+
+
+def healpix_to_lonlat(nside, pix, nested=False):
+    """Pixel-centre (lon, lat) in radians; lon in [0, 2pi)."""
+    z, omz, phi = pix2zphi(nside, pix, nested=nested)
+    st = np.sqrt(omz * (2.0 - omz))  # sqrt((1-|z|)(1+|z|)) without cancellation near the poles
+    return phi, np.arctan2(z, st)
