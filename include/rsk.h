@@ -1,0 +1,213 @@
+/*
+ * rsk.h -- C ABI of librsk, the B200 (sm_100a) implementation of pyradiosky's per-component
+ * evaluation hot path.
+ *
+ * The reference (RadioAstronomySoftwareGroup/pyradiosky) is pure Python and has no FFI; its boundary
+ * for this path is the method surface of ``SkyModel`` (src/pyradiosky/skymodel.py) and two functions
+ * of src/pyradiosky/utils.py.  Each entry point below names the reference code it replaces; the
+ * ctypes stub a pyradiosky maintainer would add is shown in INTEGRATION.md and shipped as
+ * pyradiosky_b200/_lib.py.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes only.  Unless marked HOST, every pointer is a DEVICE pointer
+ *    on the current CUDA device (the caller selects the device, e.g. with torch.cuda.device).
+ *  - The caller owns every buffer.  The library never allocates or frees device memory and keeps no
+ *    global state.  Workspaces are caller-provided and sized by rsk_workspace_bytes().
+ *  - All functions that launch work are asynchronous on ``stream`` (a cudaStream_t passed as void*;
+ *    NULL = the legacy default stream) and never synchronise.
+ *  - Return value: 0 = success; negative = argument error (RSK_ERR_*); positive = the cudaError_t of
+ *    the failed launch.  No exceptions, no abort().
+ *  - Angles are radians, frequencies Hz, all floating point is IEEE double.  Complex outputs are
+ *    interleaved (re, im) doubles, i.e. numpy complex128.
+ *  - Array layouts are the reference's: Stokes (4, Nfreqs, Ncomponents) and coherency
+ *    (2, 2, Nfreqs, Ncomponents), C order, component axis fastest (skymodel.py:614-619, :2664-2667).
+ */
+#ifndef RSK_H
+#define RSK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSK_VERSION 100 /* 0.1.0 */
+
+/* Length of the astrometry context: exactly ERFA's eraASTROM / erfa.dt_eraASTROM, as doubles:
+ * pmt, eb[3], eh[3], em, v[3], bm1, bpn[3][3] (row-major), along, phi, xpl, ypl, sphi, cphi, diurab,
+ * eral, refa, refb  ->  1+3+3+1+3+1+9+10 = 31.  A host with astropy can pass
+ * ``erfa_astrom.get().apco(AltAz(obstime=..., location=...))`` bytes straight through. */
+#define RSK_ASTROM_LEN 31
+/* Length of the device-ready context produced by rsk_pack_context(). */
+#define RSK_CTX_LEN 34
+
+/* error codes */
+#define RSK_OK 0
+#define RSK_ERR_NULL (-1)        /* a required pointer is NULL */
+#define RSK_ERR_SIZE (-2)        /* negative or inconsistent size */
+#define RSK_ERR_MODE (-3)        /* unknown spectral mode / bad enum value */
+#define RSK_ERR_LD (-4)          /* ld_out < col0 + ncols */
+#define RSK_ERR_WORKSPACE (-5)   /* workspace missing or too small */
+#define RSK_ERR_UNSUPPORTED (-6) /* e.g. spline degree > 3 */
+#define RSK_ERR_NSIDE (-7)       /* nside not a positive power of two (nested) / not positive (ring) */
+
+/* spectral modes = SkyModel.spectral_type (skymodel.py:560-577) */
+#define RSK_FLAT 0
+#define RSK_SPECTRAL_INDEX 1
+#define RSK_SUBBAND 2
+#define RSK_FULL 3
+
+/* catalogue frames understood by rsk_frame_to_icrs() */
+#define RSK_FRAME_ICRS 0
+#define RSK_FRAME_FK5 1      /* equinox given as a Julian epoch, e.g. 2000.0 */
+#define RSK_FRAME_GALACTIC 2
+
+/* workspace selectors for rsk_workspace_bytes() */
+#define RSK_OP_COMPACT 1
+
+/* Where component coordinates come from.
+ * Point catalogues: lon/lat arrays in the catalogue frame (SkyModel.skycoord, skymodel.py:2449).
+ * HEALPix maps (nside > 0): pixel centres are generated on device, replacing
+ * astropy_healpix.HEALPix(nside, order, frame).healpix_to_skycoord(hpx_inds) (skymodel.py:1656-1669);
+ * hpx_inds == NULL means component i is pixel hpx_first + i (full map or a contiguous shard). */
+typedef struct RskCoords {
+  const double* lon;       /* [n] or NULL when nside > 0 */
+  const double* lat;       /* [n] or NULL when nside > 0 */
+  int64_t nside;           /* 0 = point catalogue */
+  int32_t nested;          /* hpx_order: 0 = ring, 1 = nested (skymodel.py:545-552) */
+  int32_t reserved;
+  const int64_t* hpx_inds; /* [n] or NULL */
+  int64_t hpx_first;
+} RskCoords;
+
+/* The spectral model of the catalogue = what SkyModel.at_frequencies (skymodel.py:2084-2389) reads. */
+typedef struct RskSpectrum {
+  int32_t mode;                 /* RSK_FLAT | RSK_SPECTRAL_INDEX | RSK_SUBBAND | RSK_FULL */
+  int32_t degree;               /* SUBBAND: degree (0..3) of the piecewise-polynomial operator */
+  const double* stokes;         /* [4][nf_in][n] */
+  int64_t nf_in;                /* stored channels; 1 for FLAT / SPECTRAL_INDEX */
+  int64_t n;                    /* components in the model (leading dimension of stokes) */
+  const double* spectral_index; /* SPECTRAL_INDEX: [n] */
+  const double* ref_freq;       /* SPECTRAL_INDEX: [n] Hz (SkyModel.reference_frequency) */
+  /* SUBBAND: scipy.interpolate.interp1d(freq_array, stokes, axis=1, kind) (skymodel.py:2362-2368) is
+   * linear in the data with knots shared by all components, so the host converts it once into a
+   * piecewise-polynomial operator: on break interval b, with u = (f - breaks[b]) / (breaks[b+1] -
+   * breaks[b]), value = sum_p u^p * sum_j ppoly[b][p][j] * stokes[s][j][comp]. */
+  const double* breaks;         /* [nb + 1] ascending Hz */
+  const double* ppoly;          /* [nb][degree + 1][nf_in] */
+  int64_t nb;
+  /* FULL: channel f of the request reads stored channel freq_map[f] (subset selection of
+   * skymodel.py:2165-2181); NULL = identity (requires nf == nf_in). */
+  const int32_t* freq_map;      /* [nf] or NULL */
+  /* polarised flag per component = membership of SkyModel._polarized (skymodel.py:1037-1042, frozen
+   * at construction upstream); NULL = nothing is rotated.  Build it with rsk_polarized_mask(). */
+  const uint8_t* polarized;     /* [n] or NULL */
+} RskSpectrum;
+
+/* ---- host-side helpers (no GPU work) -------------------------------------------------------- */
+
+int rsk_version(void);
+const char* rsk_strerror(int code);
+
+/* Astrometry context for a terrestrial observer = what astropy's ErfaAstrom.apco(AltAz(obstime,
+ * location)) feeds erfa.apco at the reference call site skymodel.py:2451-2454.  Medium-accuracy
+ * inputs (truncated CIP series, low-precision solar ephemeris); callers with astropy
+ * should pass the real eraASTROM instead.  All pointers HOST.
+ * jd_utc1 + jd_utc2 = UTC Julian date; dut1 = UT1-UTC (s); elong/phi = WGS84 geodetic east longitude
+ * and latitude (rad); height (m); xp, yp = polar motion (rad). */
+int rsk_astrom_context(double jd_utc1, double jd_utc2, double dut1, double elong, double phi,
+                       double height, double xp, double yp, double* astrom /* HOST [31] */);
+
+/* Geodetic WGS84 -> geocentric metres (astropy EarthLocation.geocentric; tutorial.rst:1231-1233). */
+int rsk_geodetic_to_geocentric(double elong, double phi, double height, double* xyz /* HOST [3] */);
+
+/* 3x3 row-major matrix taking catalogue-frame unit vectors to ICRS (the first leg of astropy's
+ * frame -> ICRS -> AltAz graph for non-ICRS catalogues, e.g. GLEAM's FK5, skymodel.py:4182). HOST. */
+int rsk_frame_to_icrs(int frame, double equinox_jyear, double* m /* HOST [9] */);
+
+/* SkyModel._calc_average_rotation_matrix (skymodel.py:2499-2555): the orthogonal polar factor of the
+ * AltAz images of the three ICRS axes, row-major, ICRS -> AltAz.  HOST pointers; runs the same
+ * per-source chain as the kernels on the CPU for the three axes. */
+int rsk_ravg(const double* astrom /* HOST [31] */, double* ravg /* HOST [9] */);
+
+/* Pre-digest an eraASTROM into the RSK_CTX_LEN doubles the sweep kernel reads from device memory
+ * (the single-time entry points do this internally and pass it by value).  HOST pointers. */
+int rsk_pack_context(const double* astrom /* HOST [31] */, const double* frame2icrs /* HOST [9] or NULL */,
+                     double* ctx /* HOST [RSK_CTX_LEN] */);
+
+size_t rsk_workspace_bytes(int op, int64_t n, int64_t nf);
+
+/* ---- K1: positions --------------------------------------------------------------------------- */
+
+/* SkyModel.update_positions (skymodel.py:2413-2479) for one time: catalogue lon/lat (or HEALPix pixel
+ * centres) -> alt_az [2][n] = (alt; az), pos_lmn [3][n] (optional) and above_horizon [n] = alt > 0.
+ * The per-source arithmetic is astropy's atciqz (light deflection eraLd, aberration eraAb, BPN eraRxp)
+ * followed by erfa.atioq (Earth rotation, polar motion, diurnal aberration, latitude rotation,
+ * A/B refraction); alt = pi/2 - zd as astropy does. */
+int rsk_positions(const RskCoords* coords, int64_t n,
+                  const double* frame2icrs /* HOST [9] row-major, NULL = identity */,
+                  const double* astrom /* HOST [31] */,
+                  double* alt_az /* [2][n] */, double* pos_lmn /* [3][n] or NULL */,
+                  uint8_t* above /* [n] or NULL */, void* stream);
+
+/* LST sweep: the same for T contexts in one launch (BASELINE config 5; the loop of
+ * tests/test_skymodel.py:2661-2740).  ctx = T packed contexts from rsk_pack_context(), uploaded by
+ * the caller.  Outputs are time-major: alt_az [T][2][n], pos_lmn [T][3][n] or NULL, above [T][n] or NULL. */
+int rsk_positions_sweep(const RskCoords* coords, int64_t n, const double* ctx /* [T][RSK_CTX_LEN] */,
+                        int64_t T, double* alt_az, double* pos_lmn, uint8_t* above, void* stream);
+
+/* SkyModel.get_lon_lat, healpix branch (skymodel.py:1656-1669): pixel-centre lon/lat arrays. */
+int rsk_healpix_lonlat(int64_t nside, int nested, const int64_t* hpx_inds /* [n] or NULL */,
+                       int64_t hpx_first, int64_t n, double* lon, double* lat, void* stream);
+
+/* ---- K1b: horizon compaction ------------------------------------------------------------------ */
+
+/* Order-preserving compaction of the horizon mask = the boolean fancy index of skymodel.py:2685 and
+ * the np.isin / list-comprehension bookkeeping of :2693-2699.  idx[k] = index of the k-th component
+ * with above != 0; *n_above (device int64) = their number.  work: rsk_workspace_bytes(RSK_OP_COMPACT, n, 0). */
+int rsk_compact_index(const uint8_t* above, int64_t n, int64_t* idx /* [n] */,
+                      int64_t* n_above /* device [1] */, void* work, size_t work_bytes, void* stream);
+
+/* SkyModel._polarized (skymodel.py:1037-1042): pol[c] = any over stored channels of (Q+U+V != 0). */
+int rsk_polarized_mask(const double* stokes /* [4][nf_in][n] */, int64_t nf_in, int64_t n,
+                       uint8_t* pol /* [n] */, void* stream);
+
+/* ---- K2: fused spectrum + rotation + coherency ----------------------------------------------- */
+
+/* SkyModel.coherency_calc (skymodel.py:2648-2712) fused with at_frequencies (:2084-2389),
+ * stokes_to_coherency (utils.py:17-61), _calc_rotation_matrix (:2557-2601, with sct.vecs2rot
+ * spherical_coords_transforms.py:259-310) and _calc_coherency_rotation (:2603-2646, with
+ * sct.spherical_basis_vector_rotation_matrix :140-186).  One thread per output column.
+ * Column k (0 <= k < ncols) is component idx[k] (idx NULL = identity); its 2x2xnf block is written to
+ * out[(a*2+b)*nf*ld_out + f*ld_out + col0 + k] as (re, im).  ld_out/col0 let several shards write
+ * disjoint column ranges of one gathered array.  alt_az is the [2][n] output of rsk_positions. */
+int rsk_coherency(const RskSpectrum* spec, const RskCoords* coords, const double* alt_az /* [2][n] */,
+                  const double* ravg /* HOST [9] */, const int64_t* idx /* [ncols] or NULL */,
+                  int64_t ncols, const double* freqs /* [nf] Hz */, int64_t nf,
+                  double* out /* complex [2][2][nf][ld_out] */, int64_t ld_out, int64_t col0,
+                  void* stream);
+
+/* ---- K3 / K4: unfused API-parity kernels ------------------------------------------------------- */
+
+/* SkyModel.at_frequencies (skymodel.py:2084-2389): evaluate the spectral model on ``freqs`` for all n
+ * components -> stokes_out [4][nf][n]. */
+int rsk_at_frequencies(const RskSpectrum* spec, const double* freqs /* [nf] */, int64_t nf,
+                       double* stokes_out, void* stream);
+
+/* utils.stokes_to_coherency / SkyModel.calc_frame_coherency (utils.py:17-61, skymodel.py:2481-2497):
+ * stokes [4][nf][n] -> out complex [2][2][nf][n]. */
+int rsk_stokes_to_coherency(const double* stokes, int64_t nf, int64_t n, double* out, void* stream);
+
+/* SkyModel.jansky_to_kelvin / kelvin_to_jansky (skymodel.py:1593-1635, :1541-1591) with
+ * utils.jy_to_ksr (utils.py:105-126): in-place stokes[s][f][c] *= k(nu) where k = 1e-26 c^2 / (2 k_B nu^2)
+ * (or 1/k when to_jansky != 0); nu = freq_per_comp[c] if that pointer is non-NULL (spectral_index /
+ * flat-with-reference-frequency branch), else freq_per_chan[f]. */
+int rsk_convert_units(double* stokes /* [4][nf][n] */, int64_t nf, int64_t n,
+                      const double* freq_per_chan /* [nf] or NULL */,
+                      const double* freq_per_comp /* [n] or NULL */, int to_jansky, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSK_H */

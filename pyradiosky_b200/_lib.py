@@ -1,0 +1,161 @@
+"""ctypes binding of librsk.so -- the thin layer between host Python and the sm_100a kernels.
+
+This file is exactly the stub a pyradiosky maintainer would add to call the C ABI declared in
+``include/rsk.h``.  There is no fallback: if the shared library has not been
+built (``python -c "import __graft_entry__ as g; g.build()"``) importing it raises.
+"""
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "librsk.so")
+
+ASTROM_LEN = 31
+CTX_LEN = 34
+
+FLAT, SPECTRAL_INDEX, SUBBAND, FULL = 0, 1, 2, 3
+SPECTRAL_MODES = {"flat": FLAT, "spectral_index": SPECTRAL_INDEX, "subband": SUBBAND, "full": FULL}
+FRAME_ICRS, FRAME_FK5, FRAME_GALACTIC = 0, 1, 2
+OP_COMPACT = 1
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+
+
+class RskCoords(ctypes.Structure):
+    _fields_ = [
+        ("lon", ctypes.c_void_p),
+        ("lat", ctypes.c_void_p),
+        ("nside", ctypes.c_int64),
+        ("nested", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("hpx_inds", ctypes.c_void_p),
+        ("hpx_first", ctypes.c_int64),
+    ]
+
+
+class RskSpectrum(ctypes.Structure):
+    _fields_ = [
+        ("mode", ctypes.c_int32),
+        ("degree", ctypes.c_int32),
+        ("stokes", ctypes.c_void_p),
+        ("nf_in", ctypes.c_int64),
+        ("n", ctypes.c_int64),
+        ("spectral_index", ctypes.c_void_p),
+        ("ref_freq", ctypes.c_void_p),
+        ("breaks", ctypes.c_void_p),
+        ("ppoly", ctypes.c_void_p),
+        ("nb", ctypes.c_int64),
+        ("freq_map", ctypes.c_void_p),
+        ("polarized", ctypes.c_void_p),
+    ]
+
+
+_SIGNATURES = {
+    "rsk_version": (ctypes.c_int, []),
+    "rsk_strerror": (ctypes.c_char_p, [ctypes.c_int]),
+    "rsk_astrom_context": (ctypes.c_int, [ctypes.c_double] * 8 + [c_double_p]),
+    "rsk_geodetic_to_geocentric": (ctypes.c_int, [ctypes.c_double] * 3 + [c_double_p]),
+    "rsk_frame_to_icrs": (ctypes.c_int, [ctypes.c_int, ctypes.c_double, c_double_p]),
+    "rsk_ravg": (ctypes.c_int, [c_double_p, c_double_p]),
+    "rsk_pack_context": (ctypes.c_int, [c_double_p, c_double_p, c_double_p]),
+    "rsk_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int64, ctypes.c_int64]),
+    "rsk_positions": (
+        ctypes.c_int,
+        [ctypes.POINTER(RskCoords), ctypes.c_int64, c_double_p, c_double_p, ctypes.c_void_p,
+         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p],
+    ),
+    "rsk_positions_sweep": (
+        ctypes.c_int,
+        [ctypes.POINTER(RskCoords), ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p],
+    ),
+    "rsk_healpix_lonlat": (
+        ctypes.c_int,
+        [ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p],
+    ),
+    "rsk_compact_index": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+         ctypes.c_size_t, ctypes.c_void_p],
+    ),
+    "rsk_polarized_mask": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p],
+    ),
+    "rsk_coherency": (
+        ctypes.c_int,
+        [ctypes.POINTER(RskSpectrum), ctypes.POINTER(RskCoords), ctypes.c_void_p, c_double_p,
+         ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+         ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p],
+    ),
+    "rsk_at_frequencies": (
+        ctypes.c_int,
+        [ctypes.POINTER(RskSpectrum), ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p],
+    ),
+    "rsk_stokes_to_coherency": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p],
+    ),
+    "rsk_convert_units": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+         ctypes.c_int, ctypes.c_void_p],
+    ),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+class RskError(RuntimeError):
+    """A librsk call returned a non-zero status."""
+
+    def __init__(self, func, code, message):
+        super().__init__(f"{func} failed with status {code}: {message}")
+        self.func = func
+        self.code = code
+
+
+def load():
+    """Load librsk.so (once) and declare every signature.  Raises if the library is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA extension has not been built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` from the repository root. "
+            "pyradiosky_b200 has no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(func, code):
+    """Raise RskError for a non-zero status."""
+    if code != 0:
+        msg = load().rsk_strerror(code).decode()
+        raise RskError(func, code, msg)
+
+
+def host_array(values, n=None):
+    """ctypes double array from a sequence (or zeros of length n)."""
+    if values is None:
+        return (ctypes.c_double * n)()
+    vals = [float(v) for v in values]
+    return (ctypes.c_double * len(vals))(*vals)
+
+
+def ptr(tensor):
+    """Device (or host) address of a torch tensor, or None."""
+    if tensor is None:
+        return None
+    return ctypes.c_void_p(tensor.data_ptr())

@@ -1,0 +1,249 @@
+// rsk_device.cuh -- per-component fp64 math shared by the kernels (and, through RSK_HD, by the host
+// helper rsk_ravg that pushes the three ICRS axes through the very same chain).
+//
+// What each piece replaces in the reference (RadioAstronomySoftwareGroup/pyradiosky):
+//   rsk_chain()          astropy ICRS->AltAz as called at src/pyradiosky/skymodel.py:2451-2454
+//                        (builtin_frames.utils.atciqz = eraLd + eraAb + eraRxp, then erfa.atioq) and
+//                        the lmn / horizon lines :2464-2479
+//   rsk_hpx_center()     astropy_healpix pixel centres, skymodel.py:1656-1669
+//   rsk_basis_rotation() skymodel.py:2557-2646 + spherical_coords_transforms.py:140-186, :259-310
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define RSK_HD __host__ __device__ __forceinline__
+#else
+#define RSK_HD inline
+#endif
+
+#define RSK_D2PI 6.283185307179586476925287
+#define RSK_DPI 3.141592653589793238462643
+#define RSK_HALFPI 1.5707963267948966192313216916398
+#define RSK_SRS 1.97412574336e-8 /* ERFA_SRS: Schwarzschild radius of the Sun, au */
+#define RSK_CELMIN 1e-6          /* eraAtioq */
+#define RSK_SELMIN 0.05          /* eraAtioq */
+
+// Device-ready astrometry context (RSK_CTX_LEN doubles): eraASTROM with the orthogonal steps between
+// aberration and the latitude rotation pre-multiplied on the host.
+struct RskCtx {
+  double eh[3];   // Sun -> observer unit vector
+  double em;      // Sun-observer distance, au
+  double v[3];    // observer barycentric velocity / c
+  double bm1;     // sqrt(1 - |v|^2)
+  double a1[9];   // polar-motion(xpl, ypl) . Rz(eral) . bpn : GCRS proper direction -> (-HA, Dec) frame
+  double sphi, cphi;
+  double diurab;
+  double refa, refb;
+  double w2;      // SRS / em
+  double m_ident; // != 0: frame matrix is the identity, skip it
+  double pad;
+  double m[9];    // catalogue frame -> ICRS
+};
+static_assert(sizeof(RskCtx) == 34 * sizeof(double), "RskCtx layout");
+
+struct RskAltAz {
+  double alt, az;   // radians
+  double l, m, n;   // direction cosines: east, north, up
+};
+
+// (px,py,pz): unit vector of the component in the catalogue frame.
+RSK_HD RskAltAz rsk_chain(const RskCtx& c, double px, double py, double pz) {
+  if (c.m_ident == 0.0) {
+    const double x = c.m[0] * px + c.m[1] * py + c.m[2] * pz;
+    const double y = c.m[3] * px + c.m[4] * py + c.m[5] * pz;
+    const double z = c.m[6] * px + c.m[7] * py + c.m[8] * pz;
+    px = x; py = y; pz = z;
+  }
+  // eraLd(bm=1, p, q=p, e=eh, em, dlim=1e-6): light deflection by the Sun (astropy atciqz sets q = p
+  // for coordinates without distance, which is every SkyModel component).
+  const double qdqpe = px * (px + c.eh[0]) + py * (py + c.eh[1]) + pz * (pz + c.eh[2]);
+  const double w = RSK_SRS / c.em / fmax(qdqpe, 1e-6);
+  const double eqx = c.eh[1] * pz - c.eh[2] * py;
+  const double eqy = c.eh[2] * px - c.eh[0] * pz;
+  const double eqz = c.eh[0] * py - c.eh[1] * px;
+  const double nx = px + w * (py * eqz - pz * eqy);
+  const double ny = py + w * (pz * eqx - px * eqz);
+  const double nz = pz + w * (px * eqy - py * eqx);
+  // eraAb(pnat, v, s=em, bm1): annual (+ observer) aberration
+  const double pdv = nx * c.v[0] + ny * c.v[1] + nz * c.v[2];
+  const double w1 = 1.0 + pdv / (1.0 + c.bm1);
+  double ax = nx * c.bm1 + w1 * c.v[0] + c.w2 * (c.v[0] - pdv * nx);
+  double ay = ny * c.bm1 + w1 * c.v[1] + c.w2 * (c.v[1] - pdv * ny);
+  double az_ = nz * c.bm1 + w1 * c.v[2] + c.w2 * (c.v[2] - pdv * nz);
+  const double rinv = 1.0 / sqrt(ax * ax + ay * ay + az_ * az_);
+  ax *= rinv; ay *= rinv; az_ *= rinv;
+  // eraRxp(bpn) + eraAtioq up to the polar-motion step, as one host-built rotation.  (ERFA goes
+  // through c2s -> anp -> s2c(ri - eral, di); rotating the vector directly is the same to ~1e-16.)
+  const double xhd = c.a1[0] * ax + c.a1[1] * ay + c.a1[2] * az_;
+  const double yhd = c.a1[3] * ax + c.a1[4] * ay + c.a1[5] * az_;
+  const double zhd = c.a1[6] * ax + c.a1[7] * ay + c.a1[8] * az_;
+  // diurnal aberration (0 in contexts made by eraApco, kept for generality)
+  const double f = 1.0 - c.diurab * yhd;
+  const double xhdt = f * xhd;
+  const double yhdt = f * (yhd + c.diurab);
+  const double zhdt = f * zhd;
+  // (-HA, Dec) -> Az/El cartesian (S=0, E=90)
+  const double xaet = c.sphi * xhdt - c.cphi * zhdt;
+  const double yaet = yhdt;
+  const double zaet = c.cphi * xhdt + c.sphi * zhdt;
+  double azobs = (xaet != 0.0 || yaet != 0.0) ? atan2(yaet, -xaet) : 0.0;
+  // A tan z + B tan^3 z refraction (identity for refa = refb = 0, which is what AltAz(obstime,
+  // location) with its default zero pressure gives at skymodel.py:2453)
+  double xaeo = xaet, yaeo = yaet, zaeo = zaet;
+  if (c.refa != 0.0 || c.refb != 0.0) {
+    const double r = fmax(sqrt(xaet * xaet + yaet * yaet), RSK_CELMIN);
+    const double z = fmax(zaet, RSK_SELMIN);
+    const double tz = r / z;
+    const double wr = c.refb * tz * tz;
+    const double del = (c.refa + wr) * tz / (1.0 + (c.refa + 3.0 * wr) / (z * z));
+    const double cosdel = 1.0 - del * del / 2.0;
+    const double fr = cosdel - del * z / r;
+    xaeo = xaet * fr;
+    yaeo = yaet * fr;
+    zaeo = cosdel * zaet + del * r;
+  }
+  const double rxy = sqrt(xaeo * xaeo + yaeo * yaeo);
+  const double zdobs = atan2(rxy, zaeo);
+  RskAltAz o;
+  o.alt = RSK_HALFPI - zdobs;                       // astropy: lat = PIOVER2 - zen
+  o.az = azobs < 0.0 ? azobs + RSK_D2PI : azobs;    // eraAnp
+  // skymodel.py:2468-2470: l = sin(az) cos(alt), m = cos(az) cos(alt), n = sin(alt); taken from the
+  // cartesian vector instead of four more trig calls.
+  const double ninv = 1.0 / sqrt(rxy * rxy + zaeo * zaeo);
+  o.l = yaeo * ninv;
+  o.m = -xaeo * ninv;
+  o.n = zaeo * ninv;
+  return o;
+}
+
+// ---- HEALPix pixel centres -----------------------------------------------------------------------
+
+RSK_HD int64_t rsk_isqrt(int64_t v) {
+  int64_t r = (int64_t)sqrt((double)v);
+  if (r * r > v) --r;
+  else if ((r + 1) * (r + 1) <= v) ++r;
+  return r;
+}
+
+RSK_HD int64_t rsk_compact_bits(uint64_t v) {
+  v &= 0x5555555555555555ull;
+  v = (v | (v >> 1)) & 0x3333333333333333ull;
+  v = (v | (v >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+  v = (v | (v >> 4)) & 0x00FF00FF00FF00FFull;
+  v = (v | (v >> 8)) & 0x0000FFFF0000FFFFull;
+  v = (v | (v >> 16)) & 0x00000000FFFFFFFFull;
+  return (int64_t)v;
+}
+
+// Pixel centre as (z = sin lat, st = cos lat, phi = lon).  st is formed from the exact 1-|z| in the
+// polar caps so there is no cancellation near the poles.
+RSK_HD void rsk_hpx_center(int64_t nside, int nested, int64_t pix, double& z, double& st, double& phi) {
+  const int64_t nl4 = 4 * nside;
+  const int64_t npix = 12 * nside * nside;
+  const int64_t ncap = 2 * nside * (nside - 1);
+  int64_t nr, jp, kshift, jr_eq;
+  int region;  // +1 north cap, 0 belt, -1 south cap
+  if (nested) {
+    const int64_t npface = nside * nside;
+    const int64_t face = pix / npface;
+    const uint64_t ipf = (uint64_t)(pix - face * npface);
+    const int64_t ix = rsk_compact_bits(ipf);
+    const int64_t iy = rsk_compact_bits(ipf >> 1);
+    const int64_t jrll = 2 + (face >> 2);
+    const int64_t fm = face & 3;
+    const int64_t jpll = (face >> 2) == 1 ? 2 * fm : 2 * fm + 1;
+    const int64_t jr = jrll * nside - ix - iy - 1;
+    if (jr < nside) { region = 1; nr = jr; kshift = 0; }
+    else if (jr > 3 * nside) { region = -1; nr = nl4 - jr; kshift = 0; }
+    else { region = 0; nr = nside; kshift = (jr - nside) & 1; }
+    jp = (jpll * nr + ix - iy + 1 + kshift) / 2;
+    if (jp > nl4) jp -= nl4;
+    if (jp < 1) jp += nl4;
+    jr_eq = jr;
+  } else if (pix < ncap) {
+    region = 1;
+    nr = (1 + rsk_isqrt(1 + 2 * pix)) >> 1;
+    jp = pix + 1 - 2 * nr * (nr - 1);
+    kshift = 0; jr_eq = 0;
+  } else if (pix < npix - ncap) {
+    region = 0;
+    const int64_t ip = pix - ncap;
+    jr_eq = ip / nl4 + nside;
+    jp = ip - (jr_eq - nside) * nl4 + 1;
+    nr = nside;
+    kshift = (jr_eq - nside) & 1;
+  } else {
+    region = -1;
+    const int64_t ip = npix - pix;
+    nr = (1 + rsk_isqrt(2 * ip - 1)) >> 1;
+    jp = 4 * nr + 1 - (ip - 2 * nr * (nr - 1));
+    kshift = 0; jr_eq = 0;
+  }
+  const double nrf = (double)nr;
+  double omz;
+  if (region != 0) {
+    omz = nrf * nrf / (3.0 * (double)nside * (double)nside);
+    z = region > 0 ? 1.0 - omz : omz - 1.0;
+  } else {
+    z = (double)(2 * nside - jr_eq) * (2.0 / (3.0 * (double)nside));
+    omz = 1.0 - fabs(z);
+  }
+  st = sqrt(omz * (2.0 - omz));
+  phi = ((double)jp - (double)(kshift + 1) * 0.5) * (RSK_HALFPI / nrf);
+}
+
+// ---- polarisation basis rotation -------------------------------------------------------------------
+
+// Per-component coefficients of the 2x2 rotation R^T C R of skymodel.py:2704-2710 with
+// R = [[cosX, sinX], [-sinX, cosX]]: in Stokes terms
+//   I' = n2 I,  V' = n2 V,  Q' = c2 Q - s2 U,  U' = s2 Q + c2 U
+// with n2 = cosX^2 + sinX^2 (1 to rounding, kept because the reference's einsum carries it),
+// c2 = cosX^2 - sinX^2, s2 = 2 sinX cosX.  The angle is NOT small (it is near pi at the HERA site).
+struct RskRot {
+  double n2, c2, s2;
+};
+
+// (sl, cl, sb, cb): sin/cos of catalogue-frame lon and lat.  (sa, ca, se, ce): sin/cos of az and alt.
+// ravg: row-major ICRS->AltAz average rotation (rsk_ravg).
+RSK_HD RskRot rsk_basis_rotation(const double* ravg, double sl, double cl, double sb, double cb,
+                                 double sa, double ca, double se, double ce) {
+  // r_hat(pi/2 - lat, lon) and r_hat(pi/2 - alt, az)   [sct.r_hat, spherical_coords_transforms.py:8-31]
+  const double fx = cl * cb, fy = sl * cb, fz = sb;
+  const double tx = ca * ce, ty = sa * ce, tz = se;
+  // intermediate_vec = R_avg . frame_vec   [skymodel.py:2595]
+  const double ix = ravg[0] * fx + ravg[1] * fy + ravg[2] * fz;
+  const double iy = ravg[3] * fx + ravg[4] * fy + ravg[5] * fz;
+  const double iz = ravg[6] * fx + ravg[7] * fy + ravg[8] * fz;
+  // vecs2rot(i, t): Rodrigues about n = i x t.  With K = [n_hat]x, sin(psi) K = [n]x and
+  // (1 - cos psi) K^2 = [n]x^2 / (1 + cos psi): no normalisation, no atan2, finite at psi = 0
+  // (where upstream divides by zero and raises, spherical_coords_transforms.py:300-303).
+  const double nx = iy * tz - iz * ty;
+  const double ny = iz * tx - ix * tz;
+  const double nz = ix * ty - iy * tx;
+  const double k = 1.0 / (1.0 + (ix * tx + iy * ty + iz * tz));
+  // theta_hat(beta, alpha) at the AltAz point, beta = pi/2 - alt: (cos az sin alt, sin az sin alt, -cos alt)
+  const double wx = ca * se, wy = sa * se, wz = -ce;
+  // R_perturb^T w = w - n x w + n x (n x w) / (1 + c)
+  const double c1x = ny * wz - nz * wy;
+  const double c1y = nz * wx - nx * wz;
+  const double c1z = nx * wy - ny * wx;
+  const double c2x = ny * c1z - nz * c1y;
+  const double c2y = nz * c1x - nx * c1z;
+  const double c2z = nx * c1y - ny * c1x;
+  const double ux = wx - c1x + k * c2x;
+  const double uy = wy - c1y + k * c2y;
+  const double uz = wz - c1z + k * c2z;
+  // bh = R_exact^T w = R_avg^T (R_perturb^T w)   [sct :180]
+  const double bx = ravg[0] * ux + ravg[3] * uy + ravg[6] * uz;
+  const double by = ravg[1] * ux + ravg[4] * uy + ravg[7] * uz;
+  const double bz = ravg[2] * ux + ravg[5] * uy + ravg[8] * uz;
+  // cosX = bh . theta_hat(theta, phi), sinX = bh . phi_hat(theta, phi)   [sct :182-183]
+  const double cosx = bx * (cl * sb) + by * (sl * sb) - bz * cb;
+  const double sinx = by * cl - bx * sl;
+  RskRot r;
+  r.n2 = cosx * cosx + sinx * sinx;
+  r.c2 = cosx * cosx - sinx * sinx;
+  r.s2 = 2.0 * sinx * cosx;
+  return r;
+}

@@ -1,0 +1,645 @@
+// rsk_kernels.cu -- sm_100a kernels and the C-ABI entry points that launch them (see include/rsk.h).
+//
+// Everything here is fp64 streaming work bounded by HBM bandwidth (nothing is a dense contraction, so
+// tensor cores are not used).  Layout rules: structure-of-arrays with the component axis fastest,
+// one thread per component, 128-bit streaming stores for the complex128 output, the frequency axis
+// (log-frequencies, spline interval + local coordinate, or channel map) staged in shared memory once
+// per block, and grids linearised so that blocks that share a component tile run back to back and
+// re-read its few hundred input bytes from L2 instead of HBM.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rsk.h"
+#include "rsk_device.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;       // threads per block for the component-parallel kernels
+constexpr int kMaxFChunk = 256;     // frequencies staged in shared memory per block
+constexpr int kTargetBlocks = 148 * 16;  // B200: 148 SMs; aim for >= 16 blocks per SM in the grid
+constexpr int kCompactItems = 8;    // mask bytes per thread in the compaction kernels
+constexpr int kCompactTile = kThreads * kCompactItems;  // 2048, see rsk_workspace_bytes
+constexpr int kSweepTimes = 16;     // time steps per block in the sweep kernel
+
+struct CoordSrc {
+  const double* lon;
+  const double* lat;
+  int64_t nside;
+  int nested;
+  const int64_t* hpx_inds;
+  int64_t hpx_first;
+};
+
+// sin/cos of the catalogue-frame longitude and latitude of component i
+__device__ __forceinline__ void frame_trig(const CoordSrc& c, int64_t i, double& sl, double& cl, double& sb,
+                                           double& cb) {
+  if (c.nside > 0) {
+    const int64_t pix = c.hpx_inds ? __ldg(c.hpx_inds + i) : c.hpx_first + i;
+    double z, st, phi;
+    rsk_hpx_center(c.nside, c.nested, pix, z, st, phi);
+    sincos(phi, &sl, &cl);
+    sb = z;
+    cb = st;
+  } else {
+    sincos(__ldg(c.lon + i), &sl, &cl);
+    sincos(__ldg(c.lat + i), &sb, &cb);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1: positions (one time step)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_positions(const CoordSrc cs, const int64_t n,
+                                                        const __grid_constant__ RskCtx ctx,
+                                                        double* __restrict__ alt_az, double* __restrict__ lmn,
+                                                        uint8_t* __restrict__ above) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  double sl, cl, sb, cb;
+  frame_trig(cs, i, sl, cl, sb, cb);
+  const RskAltAz o = rsk_chain(ctx, cl * cb, sl * cb, sb);
+  __stcs(alt_az + i, o.alt);
+  __stcs(alt_az + n + i, o.az);
+  if (lmn) {
+    __stcs(lmn + i, o.l);
+    __stcs(lmn + n + i, o.m);
+    __stcs(lmn + 2 * n + i, o.n);
+  }
+  if (above) above[i] = o.alt > 0.0 ? 1 : 0;  // skymodel.py:2479
+}
+
+// K1 sweep: T contexts per launch.  Block = kThreads components x kSweepTimes time steps; contexts are
+// staged in shared memory; per-component trigonometry is hoisted out of the time loop.
+__global__ void __launch_bounds__(kThreads) k_positions_sweep(const CoordSrc cs, const int64_t n,
+                                                              const double* __restrict__ ctx_g, const int64_t nt,
+                                                              const int ntchunks, double* __restrict__ alt_az,
+                                                              double* __restrict__ lmn, uint8_t* __restrict__ above) {
+  __shared__ RskCtx s_ctx[kSweepTimes];
+  const int64_t tile = blockIdx.x / ntchunks;
+  const int tchunk = (int)(blockIdx.x - tile * ntchunks);
+  const int64_t t0 = (int64_t)tchunk * kSweepTimes;
+  const int ntc = (int)min((int64_t)kSweepTimes, nt - t0);
+  {
+    double* dst = reinterpret_cast<double*>(s_ctx);
+    const double* src = ctx_g + t0 * RSK_CTX_LEN;
+    for (int k = threadIdx.x; k < ntc * RSK_CTX_LEN; k += kThreads) dst[k] = __ldg(src + k);
+  }
+  __syncthreads();
+  const int64_t i = tile * kThreads + threadIdx.x;
+  if (i >= n) return;
+  double sl, cl, sb, cb;
+  frame_trig(cs, i, sl, cl, sb, cb);
+  const double px = cl * cb, py = sl * cb, pz = sb;
+  for (int k = 0; k < ntc; ++k) {
+    const RskAltAz o = rsk_chain(s_ctx[k], px, py, pz);
+    const int64_t t = t0 + k;
+    __stcs(alt_az + (2 * t) * n + i, o.alt);
+    __stcs(alt_az + (2 * t + 1) * n + i, o.az);
+    if (lmn) {
+      __stcs(lmn + (3 * t) * n + i, o.l);
+      __stcs(lmn + (3 * t + 1) * n + i, o.m);
+      __stcs(lmn + (3 * t + 2) * n + i, o.n);
+    }
+    if (above) above[t * n + i] = o.alt > 0.0 ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_healpix_lonlat(const int64_t nside, const int nested,
+                                                             const int64_t* __restrict__ inds, const int64_t first,
+                                                             const int64_t n, double* __restrict__ lon,
+                                                             double* __restrict__ lat) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  const int64_t pix = inds ? __ldg(inds + i) : first + i;
+  double z, st, phi;
+  rsk_hpx_center(nside, nested, pix, z, st, phi);
+  lon[i] = phi;
+  lat[i] = atan2(z, st);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1b: order-preserving compaction of the horizon mask (count -> scan of tile counts -> scatter)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t load_mask8(const uint8_t* __restrict__ m, int64_t base, int64_t n, bool aligned) {
+  // bit k set <=> m[base + k] != 0
+  uint32_t bits = 0;
+  if (aligned && base + kCompactItems <= n) {
+    const uint64_t w = __ldg(reinterpret_cast<const uint64_t*>(m + base));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bits |= (((w >> (8 * k)) & 0xffull) != 0 ? 1u : 0u) << k;
+  } else {
+#pragma unroll
+    for (int k = 0; k < kCompactItems; ++k)
+      if (base + k < n && m[base + k]) bits |= 1u << k;
+  }
+  return bits;
+}
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
+  // kThreads = 256 = 8 warps
+  __shared__ int s_warp[kThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int woff = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    const int c = s_warp[w];
+    if (w < warp) woff += c;
+    tot += c;
+  }
+  __syncthreads();
+  *total = tot;
+  return woff + incl - v;
+}
+
+__global__ void __launch_bounds__(kThreads) k_compact_count(const uint8_t* __restrict__ mask, const int64_t n,
+                                                            const bool aligned, int64_t* __restrict__ tile_counts) {
+  const int64_t base = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * kCompactItems;
+  const int c = base < n ? __popc(load_mask8(mask, base, n, aligned)) : 0;
+  int total;
+  block_exclusive_scan(c, &total);
+  if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of the tile counts in place; grand total to tile_counts[ntiles] and *n_above
+__global__ void __launch_bounds__(kThreads) k_compact_scan(int64_t* __restrict__ tile_counts, const int64_t ntiles,
+                                                           int64_t* __restrict__ n_above) {
+  __shared__ int64_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int64_t b0 = 0; b0 < ntiles; b0 += kThreads) {
+    const int64_t j = b0 + threadIdx.x;
+    const int v = j < ntiles ? (int)tile_counts[j] : 0;  // a tile holds <= 2048 items
+    int total;
+    const int ex = block_exclusive_scan(v, &total);
+    const int64_t carry = s_carry;
+    if (j < ntiles) tile_counts[j] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    tile_counts[ntiles] = s_carry;
+    *n_above = s_carry;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_compact_scatter(const uint8_t* __restrict__ mask, const int64_t n,
+                                                              const bool aligned,
+                                                              const int64_t* __restrict__ tile_offsets,
+                                                              int64_t* __restrict__ idx) {
+  const int64_t base = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * kCompactItems;
+  const uint32_t bits = base < n ? load_mask8(mask, base, n, aligned) : 0u;
+  int total;
+  const int ex = block_exclusive_scan(__popc(bits), &total);
+  int64_t o = tile_offsets[blockIdx.x] + ex;
+#pragma unroll
+  for (int k = 0; k < kCompactItems; ++k)
+    if (bits & (1u << k)) idx[o++] = base + k;
+}
+
+// SkyModel._polarized predicate, skymodel.py:1039-1041: any_f ((Q + U) + V != 0)
+__global__ void __launch_bounds__(kThreads) k_polarized(const double* __restrict__ stokes, const int64_t nf,
+                                                        const int64_t n, uint8_t* __restrict__ pol) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  bool any = false;
+  for (int64_t f = 0; f < nf; ++f) {
+    const double q = __ldg(stokes + (1 * nf + f) * n + i);
+    const double u = __ldg(stokes + (2 * nf + f) * n + i);
+    const double v = __ldg(stokes + (3 * nf + f) * n + i);
+    any = any || (__dadd_rn(__dadd_rn(q, u), v) != 0.0);
+  }
+  pol[i] = any ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2 / K3: spectral evaluation fused with (optionally) the polarisation rotation + coherency epilogue
+// ---------------------------------------------------------------------------------------------------
+struct EvalParams {
+  // spectrum
+  const double* stokes;
+  int64_t nf_in, n;
+  const double* alpha;
+  const double* ref_freq;
+  const double* breaks;
+  const double* ppoly;
+  int nb, degree;
+  const int32_t* freq_map;
+  const uint8_t* polarized;
+  // geometry (coherency epilogue only)
+  CoordSrc cs;
+  const double* alt_az;
+  double ravg[9];
+  // columns
+  const int64_t* idx;
+  int64_t ncols;
+  // frequency axis
+  const double* freqs;
+  int nf, fchunk, nfchunks;
+  // output
+  double* out;
+  int64_t ld_out, col0;
+};
+
+template <bool COH>
+__device__ __forceinline__ void xform(const RskRot& r, double si, double sq, double su, double sv, double* o) {
+  if (COH) {
+    // R^T C R of skymodel.py:2704-2710 in Stokes terms, then utils.py:42-57 halves
+    const double qr = r.c2 * sq - r.s2 * su;
+    const double ur = r.s2 * sq + r.c2 * su;
+    const double ir = r.n2 * si;
+    o[0] = 0.5 * (ir + qr);  // C[0,0]
+    o[1] = 0.5 * (ir - qr);  // C[1,1]
+    o[2] = 0.5 * ur;         // Re C[0,1] = Re C[1,0]
+    o[3] = 0.5 * (r.n2 * sv);  // Im C[1,0] = -Im C[0,1]
+  } else {
+    o[0] = si; o[1] = sq; o[2] = su; o[3] = sv;
+  }
+}
+
+template <bool COH>
+__device__ __forceinline__ void emit(const EvalParams& p, int f, int64_t col, const double* o) {
+  if (COH) {
+    const int64_t plane = (int64_t)p.nf * p.ld_out;
+    double2* d = reinterpret_cast<double2*>(p.out) + (int64_t)f * p.ld_out + p.col0 + col;
+    __stcs(d, make_double2(o[0], 0.0));
+    __stcs(d + plane, make_double2(o[2], -o[3]));
+    __stcs(d + 2 * plane, make_double2(o[2], o[3]));
+    __stcs(d + 3 * plane, make_double2(o[1], 0.0));
+  } else {
+    const int64_t plane = (int64_t)p.nf * p.ld_out;
+    double* d = p.out + (int64_t)f * p.ld_out + p.col0 + col;
+    __stcs(d, o[0]);
+    __stcs(d + plane, o[1]);
+    __stcs(d + 2 * plane, o[2]);
+    __stcs(d + 3 * plane, o[3]);
+  }
+}
+
+template <int MODE, bool COH>
+__global__ void __launch_bounds__(kThreads) k_eval(const __grid_constant__ EvalParams p) {
+  __shared__ double s_fa[kMaxFChunk];  // SPECTRAL_INDEX: ln(f / pivot); SUBBAND: local coordinate u
+  __shared__ int s_iv[kMaxFChunk];     // SUBBAND: break interval; FULL: stored channel
+  // frequency chunk fastest so that the blocks sharing a component tile are scheduled together
+  const int64_t tile = blockIdx.x / p.nfchunks;
+  const int chunk = (int)(blockIdx.x - tile * p.nfchunks);
+  const int f0 = chunk * p.fchunk;
+  const int nfc = min(p.fchunk, p.nf - f0);
+  double pivot = 1.0;
+  if (MODE == RSK_SPECTRAL_INDEX) pivot = __ldg(p.freqs + p.nf / 2);
+  for (int k = threadIdx.x; k < nfc; k += kThreads) {
+    if (MODE == RSK_SPECTRAL_INDEX) {
+      s_fa[k] = log(__ldg(p.freqs + f0 + k) / pivot);
+    } else if (MODE == RSK_SUBBAND) {
+      const double f = __ldg(p.freqs + f0 + k);
+      int lo = 0, hi = p.nb - 1;  // largest b with breaks[b] <= f, clamped to [0, nb-1]
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(p.breaks + mid) <= f) lo = mid; else hi = mid - 1;
+      }
+      const double b0 = __ldg(p.breaks + lo), b1 = __ldg(p.breaks + lo + 1);
+      s_iv[k] = lo;
+      s_fa[k] = (f - b0) / (b1 - b0);
+    } else if (MODE == RSK_FULL) {
+      s_iv[k] = p.freq_map ? __ldg(p.freq_map + f0 + k) : f0 + k;
+    }
+  }
+  if (MODE != RSK_FLAT) __syncthreads();
+
+  const int64_t col = tile * kThreads + threadIdx.x;
+  if (col >= p.ncols) return;
+  const int64_t src = p.idx ? __ldg(p.idx + col) : col;
+
+  // per-component rotation coefficients (identity for unpolarised components, skymodel.py:2687-2688)
+  RskRot rot;
+  rot.n2 = 1.0; rot.c2 = 1.0; rot.s2 = 0.0;
+  if (COH && p.polarized && __ldg(p.polarized + src)) {
+    double sl, cl, sb, cb, sa, ca, se, ce;
+    frame_trig(p.cs, src, sl, cl, sb, cb);
+    sincos(__ldg(p.alt_az + src), &se, &ce);
+    sincos(__ldg(p.alt_az + p.n + src), &sa, &ca);
+    rot = rsk_basis_rotation(p.ravg, sl, cl, sb, cb, sa, ca, se, ce);
+  }
+  const int64_t sstride = p.nf_in * p.n;  // stride between Stokes planes
+
+  if (MODE == RSK_FLAT || MODE == RSK_SPECTRAL_INDEX) {
+    double b[4];
+    xform<COH>(rot, __ldg(p.stokes + src), __ldg(p.stokes + sstride + src), __ldg(p.stokes + 2 * sstride + src),
+               __ldg(p.stokes + 3 * sstride + src), b);
+    if (MODE == RSK_FLAT) {
+      // skymodel.py:2369-2372: np.repeat along the frequency axis
+#pragma unroll 4
+      for (int k = 0; k < nfc; ++k) emit<COH>(p, f0 + k, col, b);
+    } else {
+      // skymodel.py:2159-2163: stokes * (f / f_ref) ** alpha = stokes * exp(alpha (ln f/pivot - ln f_ref/pivot))
+      const double alpha = __ldg(p.alpha + src);
+      const double l0 = log(__ldg(p.ref_freq + src) / pivot);
+#pragma unroll 4
+      for (int k = 0; k < nfc; ++k) {
+        const double pw = exp(alpha * (s_fa[k] - l0));
+        const double o[4] = {b[0] * pw, b[1] * pw, b[2] * pw, b[3] * pw};
+        emit<COH>(p, f0 + k, col, o);
+      }
+    }
+  } else if (MODE == RSK_SUBBAND) {
+    // skymodel.py:2362-2368 through the host-built piecewise-polynomial operator
+    double cf[4][4];  // [power][output quantity]
+    int cur = -1;
+    const int nfin = (int)p.nf_in;
+    for (int k = 0; k < nfc; ++k) {
+      const int iv = s_iv[k];
+      if (iv != cur) {  // uniform across the block: every thread walks the same frequencies
+        cur = iv;
+        double acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int s = 0; s < 4; ++s) acc[a][s] = 0.0;
+        const double* P = p.ppoly + (int64_t)iv * (p.degree + 1) * nfin;
+        for (int j = 0; j < nfin; ++j) {
+          const double* y = p.stokes + (int64_t)j * p.n + src;
+          const double y0 = __ldg(y), y1 = __ldg(y + sstride), y2 = __ldg(y + 2 * sstride), y3 = __ldg(y + 3 * sstride);
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            if (a <= p.degree) {
+              const double w = __ldg(P + a * nfin + j);
+              acc[a][0] = fma(w, y0, acc[a][0]);
+              acc[a][1] = fma(w, y1, acc[a][1]);
+              acc[a][2] = fma(w, y2, acc[a][2]);
+              acc[a][3] = fma(w, y3, acc[a][3]);
+            }
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) xform<COH>(rot, acc[a][0], acc[a][1], acc[a][2], acc[a][3], cf[a]);
+      }
+      const double u = s_fa[k];
+      double o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q] = fma(fma(fma(cf[3][q], u, cf[2][q]), u, cf[1][q]), u, cf[0][q]);
+      emit<COH>(p, f0 + k, col, o);
+    }
+  } else {  // RSK_FULL: stored Stokes, skymodel.py:2165-2181 subset + utils.py:42-57
+#pragma unroll 4
+    for (int k = 0; k < nfc; ++k) {
+      const double* y = p.stokes + (int64_t)s_iv[k] * p.n + src;
+      const double y0 = __ldcs(y), y1 = __ldcs(y + sstride), y2 = __ldcs(y + 2 * sstride), y3 = __ldcs(y + 3 * sstride);
+      double o[4];
+      xform<COH>(rot, y0, y1, y2, y3, o);
+      emit<COH>(p, f0 + k, col, o);
+    }
+  }
+}
+
+// K4: Jy <-> K (sr) in place
+__global__ void __launch_bounds__(kThreads) k_convert_units(double* __restrict__ stokes, const int64_t nf,
+                                                            const int64_t n, const double* __restrict__ fchan,
+                                                            const double* __restrict__ fcomp, const int to_jansky) {
+  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (e >= nf * n) return;
+  const int64_t f = e / n, c = e - f * n;
+  const double nu = fcomp ? __ldg(fcomp + c) : __ldg(fchan + f);
+  // utils.jy_to_ksr (utils.py:105-126): astropy brightness_temperature with a 1 sr beam, CODATA 2018
+  double k = __ddiv_rn(1e-26 * (299792458.0 * 299792458.0), __dmul_rn(2.0 * 1.380649e-23, __dmul_rn(nu, nu)));
+  if (to_jansky) k = __ddiv_rn(1.0, k);  // skymodel.py:1559-1571
+  const int64_t plane = nf * n;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) stokes[s * plane + e] = __dmul_rn(stokes[s * plane + e], k);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-side launch helpers
+// ---------------------------------------------------------------------------------------------------
+inline int launch_status() {
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? RSK_OK : (int)e;
+}
+
+inline int check_coords(const RskCoords* c, CoordSrc* out) {
+  if (!c) return RSK_ERR_NULL;
+  if (c->nside < 0) return RSK_ERR_NSIDE;
+  if (c->nside > 0) {
+    if (c->nside > (1ll << 29)) return RSK_ERR_NSIDE;
+    if (c->nested && (c->nside & (c->nside - 1)) != 0) return RSK_ERR_NSIDE;
+  } else if (!c->lon || !c->lat) {
+    return RSK_ERR_NULL;
+  }
+  out->lon = c->lon;
+  out->lat = c->lat;
+  out->nside = c->nside;
+  out->nested = c->nested;
+  out->hpx_inds = c->hpx_inds;
+  out->hpx_first = c->hpx_first;
+  return RSK_OK;
+}
+
+inline unsigned blocks_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
+
+int fill_eval_params(const RskSpectrum* spec, const double* freqs, int64_t nf, int64_t ncols, EvalParams* p) {
+  if (!spec || !spec->stokes) return RSK_ERR_NULL;
+  if (nf < 0 || ncols < 0 || spec->n < 0 || spec->nf_in < 1 || nf > INT32_MAX) return RSK_ERR_SIZE;
+  if (spec->mode < RSK_FLAT || spec->mode > RSK_FULL) return RSK_ERR_MODE;
+  if ((spec->mode == RSK_SPECTRAL_INDEX || spec->mode == RSK_SUBBAND) && !freqs) return RSK_ERR_NULL;
+  if (spec->mode == RSK_SPECTRAL_INDEX && (!spec->spectral_index || !spec->ref_freq)) return RSK_ERR_NULL;
+  if (spec->mode == RSK_SUBBAND) {
+    if (!spec->breaks || !spec->ppoly) return RSK_ERR_NULL;
+    if (spec->nb < 1 || spec->nb > INT32_MAX) return RSK_ERR_SIZE;
+    if (spec->degree < 0 || spec->degree > 3) return RSK_ERR_UNSUPPORTED;
+  }
+  if (spec->mode == RSK_FULL && !spec->freq_map && nf != spec->nf_in) return RSK_ERR_SIZE;
+  if ((spec->mode == RSK_FLAT || spec->mode == RSK_SPECTRAL_INDEX) && spec->nf_in != 1) return RSK_ERR_SIZE;
+  p->stokes = spec->stokes;
+  p->nf_in = spec->nf_in;
+  p->n = spec->n;
+  p->alpha = spec->spectral_index;
+  p->ref_freq = spec->ref_freq;
+  p->breaks = spec->breaks;
+  p->ppoly = spec->ppoly;
+  p->nb = (int)spec->nb;
+  p->degree = spec->degree;
+  p->freq_map = spec->freq_map;
+  p->polarized = spec->polarized;
+  p->freqs = freqs;
+  p->nf = (int)nf;
+  p->ncols = ncols;
+  // frequency chunking: enough blocks to fill the machine, chunks no longer than the smem tables
+  const int64_t tiles = (ncols + kThreads - 1) / kThreads;
+  int64_t nch = tiles > 0 ? (kTargetBlocks + tiles - 1) / tiles : 1;
+  const int64_t min_ch = (nf + kMaxFChunk - 1) / kMaxFChunk;
+  const int64_t max_ch = (nf + 31) / 32;
+  if (nch > max_ch) nch = max_ch;
+  if (nch < min_ch) nch = min_ch;
+  if (nch < 1) nch = 1;
+  p->fchunk = (int)((nf + nch - 1) / nch);
+  if (p->fchunk < 1) p->fchunk = 1;
+  p->nfchunks = (int)((nf + p->fchunk - 1) / p->fchunk);
+  if (p->nfchunks < 1) p->nfchunks = 1;
+  return RSK_OK;
+}
+
+template <bool COH>
+int launch_eval(const EvalParams& p, int mode, cudaStream_t st) {
+  if (p.ncols == 0 || p.nf == 0) return RSK_OK;
+  const int64_t tiles = (p.ncols + kThreads - 1) / kThreads;
+  const int64_t nblocks = tiles * p.nfchunks;
+  if (nblocks > 0x7fffffffll) return RSK_ERR_SIZE;
+  const dim3 grid((unsigned)nblocks), block(kThreads);
+  switch (mode) {
+    case RSK_FLAT: k_eval<RSK_FLAT, COH><<<grid, block, 0, st>>>(p); break;
+    case RSK_SPECTRAL_INDEX: k_eval<RSK_SPECTRAL_INDEX, COH><<<grid, block, 0, st>>>(p); break;
+    case RSK_SUBBAND: k_eval<RSK_SUBBAND, COH><<<grid, block, 0, st>>>(p); break;
+    case RSK_FULL: k_eval<RSK_FULL, COH><<<grid, block, 0, st>>>(p); break;
+    default: return RSK_ERR_MODE;
+  }
+  return launch_status();
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+int rsk_positions(const RskCoords* coords, int64_t n, const double* frame2icrs, const double* astrom,
+                  double* alt_az, double* pos_lmn, uint8_t* above, void* stream) {
+  CoordSrc cs;
+  const int rc = check_coords(coords, &cs);
+  if (rc != RSK_OK) return rc;
+  if (!astrom || !alt_az) return RSK_ERR_NULL;
+  if (n < 0) return RSK_ERR_SIZE;
+  if (n == 0) return RSK_OK;
+  RskCtx ctx;
+  rsk_pack_context(astrom, frame2icrs, reinterpret_cast<double*>(&ctx));
+  k_positions<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(cs, n, ctx, alt_az, pos_lmn, above);
+  return launch_status();
+}
+
+int rsk_positions_sweep(const RskCoords* coords, int64_t n, const double* ctx, int64_t T, double* alt_az,
+                        double* pos_lmn, uint8_t* above, void* stream) {
+  CoordSrc cs;
+  const int rc = check_coords(coords, &cs);
+  if (rc != RSK_OK) return rc;
+  if (!ctx || !alt_az) return RSK_ERR_NULL;
+  if (n < 0 || T < 0) return RSK_ERR_SIZE;
+  if (n == 0 || T == 0) return RSK_OK;
+  const int64_t ntchunks = (T + kSweepTimes - 1) / kSweepTimes;
+  const int64_t nblocks = (int64_t)blocks_for(n) * ntchunks;
+  if (nblocks > 0x7fffffffll) return RSK_ERR_SIZE;
+  k_positions_sweep<<<(unsigned)nblocks, kThreads, 0, (cudaStream_t)stream>>>(cs, n, ctx, T, (int)ntchunks, alt_az,
+                                                                            pos_lmn, above);
+  return launch_status();
+}
+
+int rsk_healpix_lonlat(int64_t nside, int nested, const int64_t* hpx_inds, int64_t hpx_first, int64_t n, double* lon,
+                       double* lat, void* stream) {
+  RskCoords c = {nullptr, nullptr, nside, nested, 0, hpx_inds, hpx_first};
+  CoordSrc cs;
+  if (nside <= 0) return RSK_ERR_NSIDE;
+  const int rc = check_coords(&c, &cs);
+  if (rc != RSK_OK) return rc;
+  if (!lon || !lat) return RSK_ERR_NULL;
+  if (n < 0) return RSK_ERR_SIZE;
+  if (n == 0) return RSK_OK;
+  k_healpix_lonlat<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(nside, nested, hpx_inds, hpx_first, n, lon, lat);
+  return launch_status();
+}
+
+int rsk_compact_index(const uint8_t* above, int64_t n, int64_t* idx, int64_t* n_above, void* work, size_t work_bytes,
+                      void* stream) {
+  if (!n_above) return RSK_ERR_NULL;
+  if (n < 0) return RSK_ERR_SIZE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    const cudaError_t e = cudaMemsetAsync(n_above, 0, sizeof(int64_t), st);
+    return e == cudaSuccess ? RSK_OK : (int)e;
+  }
+  if (!above || !idx) return RSK_ERR_NULL;
+  if (!work || work_bytes < rsk_workspace_bytes(RSK_OP_COMPACT, n, 0)) return RSK_ERR_WORKSPACE;
+  const int64_t ntiles = (n + kCompactTile - 1) / kCompactTile;
+  if (ntiles > 0x7fffffffll) return RSK_ERR_SIZE;
+  const bool aligned = (reinterpret_cast<uintptr_t>(above) & 7u) == 0;
+  int64_t* tiles = static_cast<int64_t*>(work);
+  k_compact_count<<<(unsigned)ntiles, kThreads, 0, st>>>(above, n, aligned, tiles);
+  k_compact_scan<<<1, kThreads, 0, st>>>(tiles, ntiles, n_above);
+  k_compact_scatter<<<(unsigned)ntiles, kThreads, 0, st>>>(above, n, aligned, tiles, idx);
+  return launch_status();
+}
+
+int rsk_polarized_mask(const double* stokes, int64_t nf_in, int64_t n, uint8_t* pol, void* stream) {
+  if (n < 0 || nf_in < 0) return RSK_ERR_SIZE;
+  if (n == 0) return RSK_OK;
+  if (!stokes || !pol) return RSK_ERR_NULL;
+  k_polarized<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(stokes, nf_in, n, pol);
+  return launch_status();
+}
+
+int rsk_coherency(const RskSpectrum* spec, const RskCoords* coords, const double* alt_az, const double* ravg,
+                  const int64_t* idx, int64_t ncols, const double* freqs, int64_t nf, double* out, int64_t ld_out,
+                  int64_t col0, void* stream) {
+  EvalParams p = {};
+  int rc = fill_eval_params(spec, freqs, nf, ncols, &p);
+  if (rc != RSK_OK) return rc;
+  if (ncols > 0 && nf > 0 && !out) return RSK_ERR_NULL;
+  if (col0 < 0 || ld_out < col0 + ncols) return RSK_ERR_LD;
+  if (!idx && ncols > spec->n) return RSK_ERR_SIZE;
+  if (spec->polarized) {  // rotation needed: geometry must be present
+    rc = check_coords(coords, &p.cs);
+    if (rc != RSK_OK) return rc;
+    if (!alt_az || !ravg) return RSK_ERR_NULL;
+    for (int i = 0; i < 9; ++i) p.ravg[i] = ravg[i];
+  }
+  p.alt_az = alt_az;
+  p.idx = idx;
+  p.out = out;
+  p.ld_out = ld_out;
+  p.col0 = col0;
+  return launch_eval<true>(p, spec->mode, (cudaStream_t)stream);
+}
+
+int rsk_at_frequencies(const RskSpectrum* spec, const double* freqs, int64_t nf, double* stokes_out, void* stream) {
+  EvalParams p = {};
+  if (!spec) return RSK_ERR_NULL;
+  const int rc = fill_eval_params(spec, freqs, nf, spec->n, &p);
+  if (rc != RSK_OK) return rc;
+  if (spec->n > 0 && nf > 0 && !stokes_out) return RSK_ERR_NULL;
+  p.idx = nullptr;
+  p.out = stokes_out;
+  p.ld_out = spec->n;
+  p.col0 = 0;
+  return launch_eval<false>(p, spec->mode, (cudaStream_t)stream);
+}
+
+int rsk_stokes_to_coherency(const double* stokes, int64_t nf, int64_t n, double* out, void* stream) {
+  RskSpectrum spec = {};
+  spec.mode = RSK_FULL;
+  spec.stokes = stokes;
+  spec.nf_in = nf;
+  spec.n = n;
+  if (nf < 0 || n < 0) return RSK_ERR_SIZE;
+  if (nf == 0 || n == 0) return RSK_OK;
+  RskCoords none = {};
+  return rsk_coherency(&spec, &none, nullptr, nullptr, nullptr, n, nullptr, nf, out, n, 0, stream);
+}
+
+int rsk_convert_units(double* stokes, int64_t nf, int64_t n, const double* freq_per_chan, const double* freq_per_comp,
+                      int to_jansky, void* stream) {
+  if (nf < 0 || n < 0) return RSK_ERR_SIZE;
+  if (nf == 0 || n == 0) return RSK_OK;
+  if (!stokes || (!freq_per_chan && !freq_per_comp)) return RSK_ERR_NULL;
+  const int64_t total = nf * n;
+  if ((total + kThreads - 1) / kThreads > 0x7fffffffll) return RSK_ERR_SIZE;
+  k_convert_units<<<blocks_for(total), kThreads, 0, (cudaStream_t)stream>>>(stokes, nf, n, freq_per_chan, freq_per_comp,
+                                                                          to_jansky);
+  return launch_status();
+}
+
+}  // extern "C"

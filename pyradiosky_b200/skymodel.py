@@ -1,0 +1,555 @@
+"""``SkyModel``: the host-side mirror of ``pyradiosky.SkyModel`` for the per-component hot path.
+
+Same method names, argument meaning and error behaviour as the reference class
+(src/pyradiosky/skymodel.py:335) for
+
+    update_positions   :2413-2479        coherency_calc        :2648-2712
+    at_frequencies     :2084-2389        calc_frame_coherency  :2481-2497
+    jansky_to_kelvin   :1593-1635        kelvin_to_jansky      :1541-1591
+    get_lon_lat        :1646-1673        clear_time_position_specific_params
+
+but every array lives in HBM as a torch CUDA tensor (torch is used only as the device-buffer
+allocator and stream provider) and all arithmetic runs in librsk's sm_100a kernels through ctypes.
+There is no CPU fallback: constructing a SkyModel without a CUDA device or without the built
+library raises.
+
+Differences from the reference that a caller can observe (all documented in DESIGN.md):
+  * arrays are torch CUDA tensors (``.cpu().numpy()`` gives the reference's numpy layout); units are
+    carried as a plain string ``stokes_unit`` instead of astropy Quantities;
+  * ``coherency_calc(freqs=...)`` is an extension that fuses ``at_frequencies`` into the coherency
+    kernel so the (4, Nfreqs, Ncomponents) Stokes cube is never materialised;
+  * ``coherency_calc`` never needs ``frame_coherency`` (it is computed on the fly), so
+    ``store_frame_coherency=False`` works here (it raises TypeError upstream, skymodel.py:2685);
+  * a source whose R_avg-rotated direction coincides exactly with its AltAz direction gets the
+    identity perturbation instead of upstream's "axis must be a unit vector" ValueError.
+"""
+
+import copy as _copy
+import ctypes
+import warnings
+
+import numpy as np
+import torch
+
+from . import _lib, astrometry, spectral
+from .utils import _as_device_f64
+
+_JY_UNITS = {"point": "Jy", "healpix": "Jy / sr"}
+_K_UNITS = {"point": "K sr", "healpix": "K"}
+
+
+def _norm_unit(unit):
+    return " ".join(str(unit).replace("/", " / ").split())
+
+
+def _to_hz_host(freqs):
+    """1-D float64 numpy array in Hz from Quantity-like / torch / array input."""
+    if freqs is None:
+        return None
+    if hasattr(freqs, "to_value"):
+        freqs = freqs.to_value("Hz")
+    if isinstance(freqs, torch.Tensor):
+        freqs = freqs.detach().cpu().numpy()
+    return np.atleast_1d(np.asarray(freqs, dtype=np.float64))
+
+
+def _to_rad(angle):
+    if hasattr(angle, "rad"):
+        angle = angle.rad
+    elif hasattr(angle, "to_value"):
+        angle = angle.to_value("rad")
+    return angle
+
+
+class SkyModel:
+    """Catalogue of point sources or HEALPix pixels held on one GPU.
+
+    Parameters
+    ----------
+    name : sequence of str, optional
+        Component names (kept on the host, unused by the hot path).
+    ra, dec / lon, lat : array_like, radians (or objects with ``.rad``)
+        Component coordinates in ``frame`` (point catalogues).
+    frame : str
+        'icrs' (default), 'fk5' (``equinox`` as a Julian epoch, default 2000.0) or 'galactic'.
+    stokes : array_like, shape (4, Nfreqs, Ncomponents)
+        [I, Q, U, V]; numpy, torch or Quantity-like.
+    spectral_type : {'flat', 'spectral_index', 'subband', 'full'}
+    freq_array : array_like, Hz -- required for 'subband' and 'full'.
+    reference_frequency, spectral_index : array_like (Ncomponents,) -- required for 'spectral_index'.
+    component_type : {'point', 'healpix'}
+    nside, hpx_inds, hpx_order, hpx_frame : HEALPix description; ``hpx_inds=None`` with
+        ``component_type='healpix'`` means "all 12 nside^2 pixels" (or the contiguous range starting at
+        ``hpx_first`` when ``stokes`` holds fewer), without materialising an index array.
+    stokes_unit : str
+        'Jy' / 'K sr' (point) or 'Jy / sr' / 'K' (healpix).  Defaults to the Jy flavour, or to the
+        unit of ``stokes`` if it is Quantity-like.
+    device : torch device, default current CUDA device.
+    """
+
+    def __init__(
+        self,
+        name=None,
+        ra=None,
+        dec=None,
+        lon=None,
+        lat=None,
+        frame="icrs",
+        equinox=2000.0,
+        stokes=None,
+        spectral_type=None,
+        freq_array=None,
+        reference_frequency=None,
+        spectral_index=None,
+        component_type=None,
+        nside=None,
+        hpx_inds=None,
+        hpx_order=None,
+        hpx_frame=None,
+        hpx_first=0,
+        stokes_unit=None,
+        device=None,
+    ):
+        _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("pyradiosky_b200 needs a CUDA device; there is no CPU fallback.")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if spectral_type not in _lib.SPECTRAL_MODES:
+            raise ValueError("spectral_type must be one of 'flat', 'spectral_index', 'subband', 'full'")
+        self.spectral_type = spectral_type
+        self.name = None if name is None else np.atleast_1d(np.asarray(name))
+
+        if component_type is None:
+            component_type = "healpix" if nside is not None else "point"
+        if component_type not in ("point", "healpix"):
+            raise ValueError("component_type must be 'point' or 'healpix'")
+        self.component_type = component_type
+
+        unit = getattr(stokes, "unit", None)
+        if stokes_unit is None:
+            stokes_unit = str(unit) if unit is not None else _JY_UNITS[component_type]
+        self.stokes_unit = _norm_unit(stokes_unit)
+        st = _as_device_f64(stokes, self.device)
+        if st.dim() == 1:
+            st = st.reshape(4, 1, 1)
+        if st.dim() != 3 or st.shape[0] != 4:
+            raise ValueError("stokes must have shape (4, Nfreqs, Ncomponents)")
+        self.stokes = st
+        self.Nfreqs = int(st.shape[1])
+        self.Ncomponents = int(st.shape[2])
+
+        if component_type == "point":
+            lon = ra if lon is None else lon
+            lat = dec if lat is None else lat
+            if lon is None or lat is None:
+                raise ValueError("ra/dec (or lon/lat) are required for point components")
+            self.lon = _as_device_f64(np.atleast_1d(_to_rad(lon)) if not isinstance(lon, torch.Tensor) else lon, self.device)
+            self.lat = _as_device_f64(np.atleast_1d(_to_rad(lat)) if not isinstance(lat, torch.Tensor) else lat, self.device)
+            if self.lon.numel() != self.Ncomponents or self.lat.numel() != self.Ncomponents:
+                raise ValueError("coordinate arrays must have length Ncomponents")
+            self.frame = str(frame).lower()
+            self.nside = None
+            self.hpx_inds = None
+            self.hpx_order = None
+            self.hpx_first = 0
+        else:
+            if nside is None:
+                raise ValueError("nside is required for healpix components")
+            self.nside = int(nside)
+            self.hpx_order = "ring" if hpx_order is None else str(hpx_order).lower()
+            if self.hpx_order not in ("ring", "nested"):
+                raise ValueError("hpx_order must be 'ring' or 'nested'")
+            self.frame = str(hpx_frame if hpx_frame is not None else frame).lower()
+            self.hpx_first = int(hpx_first)
+            if hpx_inds is None:
+                self.hpx_inds = None
+                if self.hpx_first + self.Ncomponents > 12 * self.nside**2:
+                    raise ValueError("pixel range exceeds 12 * nside**2")
+            else:
+                if isinstance(hpx_inds, torch.Tensor):
+                    self.hpx_inds = hpx_inds.to(self.device, dtype=torch.int64).contiguous()
+                else:
+                    self.hpx_inds = torch.as_tensor(np.ascontiguousarray(hpx_inds, dtype=np.int64)).to(self.device)
+                if self.hpx_inds.numel() != self.Ncomponents:
+                    raise ValueError("hpx_inds must have length Ncomponents")
+            self.lon = None
+            self.lat = None
+        self.hpx_frame = self.frame if component_type == "healpix" else None
+        self.equinox = float(equinox)
+        self._frame_to_icrs = astrometry.frame_to_icrs_matrix(self.frame, self.equinox)
+
+        self.freq_array = _to_hz_host(freq_array)
+        if spectral_type in ("subband", "full"):
+            if self.freq_array is None:
+                raise ValueError("freq_array must be provided for spectral_type 'subband' and 'full'")
+            if self.freq_array.size != self.Nfreqs:
+                raise ValueError("freq_array must have length Nfreqs")
+        elif self.Nfreqs != 1:
+            raise ValueError("stokes must have Nfreqs == 1 for 'flat' and 'spectral_index' spectral types")
+        self.reference_frequency = None
+        self.spectral_index = None
+        if reference_frequency is not None:
+            rf = reference_frequency.to_value("Hz") if hasattr(reference_frequency, "to_value") else reference_frequency
+            self.reference_frequency = _as_device_f64(np.atleast_1d(rf) if not isinstance(rf, torch.Tensor) else rf, self.device)
+        if spectral_index is not None:
+            self.spectral_index = _as_device_f64(
+                np.atleast_1d(spectral_index) if not isinstance(spectral_index, torch.Tensor) else spectral_index, self.device)
+        if spectral_type == "spectral_index":
+            if self.reference_frequency is None or self.spectral_index is None:
+                raise ValueError("reference_frequency and spectral_index are required for spectral_type 'spectral_index'")
+            if self.reference_frequency.numel() != self.Ncomponents or self.spectral_index.numel() != self.Ncomponents:
+                raise ValueError("reference_frequency and spectral_index must have length Ncomponents")
+
+        # skymodel.py:1037-1042 -- frozen at construction, as upstream
+        self._polarized_mask = torch.empty(self.Ncomponents, dtype=torch.uint8, device=self.device)
+        self._call("rsk_polarized_mask", _lib.ptr(self.stokes), self.Nfreqs, self.Ncomponents,
+                   _lib.ptr(self._polarized_mask))
+        self._n_polarized = int(self._polarized_mask.sum().item())
+
+        self.freq_tol = 1.0  # Hz, skymodel.py:491
+        self.time = None
+        self.telescope_location = None
+        self.alt_az = None
+        self.pos_lmn = None
+        self.above_horizon = None
+        self.frame_coherency = None
+        self._astrom = None
+        self._freq_dev_cache = {}
+
+    # ------------------------------------------------------------------------------------------
+    # plumbing
+    # ------------------------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _call(self, fname, *args):
+        with torch.cuda.device(self.device):
+            code = getattr(_lib.load(), fname)(*args, self._stream())
+        _lib.check(fname, code)
+
+    @property
+    def _polarized(self):
+        """Indices of polarised components (skymodel.py:1039-1041) as a CUDA int64 tensor."""
+        return torch.nonzero(self._polarized_mask, as_tuple=False).flatten()
+
+    def _coords_struct(self):
+        c = _lib.RskCoords()
+        if self.component_type == "healpix":
+            c.lon = None
+            c.lat = None
+            c.nside = self.nside
+            c.nested = 1 if self.hpx_order == "nested" else 0
+            c.hpx_inds = None if self.hpx_inds is None else self.hpx_inds.data_ptr()
+            c.hpx_first = self.hpx_first
+        else:
+            c.lon = self.lon.data_ptr()
+            c.lat = self.lat.data_ptr()
+            c.nside = 0
+        return c
+
+    def _freqs_dev(self, freqs_host):
+        key = freqs_host.tobytes()
+        t = self._freq_dev_cache.get(key)
+        if t is None:
+            if len(self._freq_dev_cache) > 8:
+                self._freq_dev_cache.clear()
+            t = torch.as_tensor(freqs_host).to(self.device)
+            self._freq_dev_cache[key] = t
+        return t
+
+    def _spectrum_struct(self, mode, keep, freq_interp_kind="cubic", freq_map=None, polarized=True):
+        """RskSpectrum for the stored model; ``keep`` collects tensors that must outlive the call."""
+        s = _lib.RskSpectrum()
+        s.mode = mode
+        s.stokes = self.stokes.data_ptr()
+        s.nf_in = self.Nfreqs
+        s.n = self.Ncomponents
+        if mode == _lib.SPECTRAL_INDEX:
+            s.spectral_index = self.spectral_index.data_ptr()
+            s.ref_freq = self.reference_frequency.data_ptr()
+        if mode == _lib.SUBBAND:
+            degree, breaks, ppoly = spectral.build_ppoly_operator(self.freq_array, freq_interp_kind)
+            b = torch.as_tensor(breaks).to(self.device)
+            p = torch.as_tensor(np.ascontiguousarray(ppoly)).to(self.device)
+            keep += [b, p]
+            s.degree = degree
+            s.breaks = b.data_ptr()
+            s.ppoly = p.data_ptr()
+            s.nb = breaks.size - 1
+        if mode == _lib.FULL and freq_map is not None:
+            fm = torch.as_tensor(np.ascontiguousarray(freq_map, dtype=np.int32)).to(self.device)
+            keep.append(fm)
+            s.freq_map = fm.data_ptr()
+        if polarized and self._n_polarized > 0:
+            s.polarized = self._polarized_mask.data_ptr()
+        return s
+
+    def copy(self):
+        """Deep copy (device tensors are cloned)."""
+        new = _copy.copy(self)
+        for k, v in self.__dict__.items():
+            if isinstance(v, torch.Tensor):
+                setattr(new, k, v.clone())
+            elif isinstance(v, np.ndarray):
+                setattr(new, k, v.copy())
+        new._freq_dev_cache = {}
+        return new
+
+    # ------------------------------------------------------------------------------------------
+    # coordinates
+    # ------------------------------------------------------------------------------------------
+    def get_lon_lat(self):
+        """Longitudes and latitudes (radians, CUDA tensors) of the components in ``frame``.
+
+        For healpix models the pixel centres are generated on the GPU (reference: astropy_healpix,
+        skymodel.py:1656-1669)."""
+        if self.component_type != "healpix":
+            return self.lon, self.lat
+        lon = torch.empty(self.Ncomponents, dtype=torch.float64, device=self.device)
+        lat = torch.empty_like(lon)
+        self._call("rsk_healpix_lonlat", self.nside, 1 if self.hpx_order == "nested" else 0,
+                   _lib.ptr(self.hpx_inds), self.hpx_first, self.Ncomponents, _lib.ptr(lon), _lib.ptr(lat))
+        return lon, lat
+
+    def _check_tel_location(self, telescope_location):
+        # skymodel.py:2391-2411 (the lunarsky/MoonLocation branch is out of scope)
+        if not astrometry.is_earth_location(telescope_location):
+            raise ValueError(
+                "telescope_location must be an :class:`astropy.EarthLocation` "
+                f"object. value was: {str(telescope_location)}"
+            )
+
+    def clear_time_position_specific_params(self):
+        """Set time/position dependent attributes to None (skymodel.py:1385-ff)."""
+        self.time = None
+        self.telescope_location = None
+        self.alt_az = None
+        self.pos_lmn = None
+        self.above_horizon = None
+        self._astrom = None
+
+    def update_positions(self, time, telescope_location, astrom=None):
+        """Calculate the altitude/azimuth positions for source components (skymodel.py:2413-2479).
+
+        Updates ``alt_az`` (2, N) [alt; az] radians, ``pos_lmn`` (3, N), ``above_horizon`` (N,) bool,
+        ``time`` and ``telescope_location`` in place; all arrays are CUDA tensors.
+
+        ``astrom`` (extension): a ready 31-double eraASTROM for this (time, location), e.g. exported
+        from a machine that has astropy; by default the context is built from ``time`` and
+        ``telescope_location``.
+        """
+        if not astrometry.is_time(time):
+            raise ValueError(f"time must be an astropy Time object. value was: {time}")
+        self._check_tel_location(telescope_location)
+        # Don't repeat calculations (skymodel.py:2439-2441)
+        if self.time is not None and self.telescope_location is not None and astrom is None:
+            if self.time == time and self.telescope_location == telescope_location:
+                return
+        self.time = time
+        self.telescope_location = telescope_location
+        if astrom is None:
+            astrom = astrometry.astrom_context(time, telescope_location)
+        astrom = np.ascontiguousarray(astrom, dtype=np.float64).ravel()
+        if astrom.size != _lib.ASTROM_LEN:
+            raise ValueError(f"astrom must hold {_lib.ASTROM_LEN} doubles (eraASTROM)")
+        self._astrom = astrom
+        n = self.Ncomponents
+        if self.alt_az is None or self.alt_az.shape[1] != n:
+            self.alt_az = torch.empty((2, n), dtype=torch.float64, device=self.device)
+        if self.pos_lmn is None or self.pos_lmn.shape[1] != n:
+            self.pos_lmn = torch.empty((3, n), dtype=torch.float64, device=self.device)
+        above = torch.empty(n, dtype=torch.uint8, device=self.device)
+        coords = self._coords_struct()
+        self._call("rsk_positions", ctypes.byref(coords), n, _lib.host_array(self._frame_to_icrs.ravel()),
+                   _lib.host_array(astrom), _lib.ptr(self.alt_az), _lib.ptr(self.pos_lmn), _lib.ptr(above))
+        self.above_horizon = above.view(torch.bool)
+
+    # ------------------------------------------------------------------------------------------
+    # coherency
+    # ------------------------------------------------------------------------------------------
+    def calc_frame_coherency(self, store=True):
+        """Coherency in the catalogue frame (skymodel.py:2481-2497): (2, 2, Nfreqs, N) complex128."""
+        out = torch.empty((2, 2, self.Nfreqs, self.Ncomponents), dtype=torch.complex128, device=self.device)
+        self._call("rsk_stokes_to_coherency", _lib.ptr(self.stokes), self.Nfreqs, self.Ncomponents, _lib.ptr(out))
+        if store:
+            self.frame_coherency = out
+        else:
+            return out
+
+    def _calc_average_rotation_matrix(self):
+        """skymodel.py:2499-2555, from the current astrometry context: (3, 3) numpy."""
+        if self._astrom is None:
+            raise ValueError("update_positions must be called before the rotation can be computed")
+        return astrometry.average_rotation_matrix(self._astrom)
+
+    def compact_above_horizon(self):
+        """(idx, n_above): CUDA int64 indices of above-horizon components in catalogue order.
+
+        This is the boolean fancy index of skymodel.py:2685 made explicit; the count comes back to
+        the host because the output array of ``coherency_calc`` is sized by it."""
+        n = self.Ncomponents
+        idx = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
+        cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
+        nbytes = _lib.load().rsk_workspace_bytes(_lib.OP_COMPACT, n, 0)
+        work = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=self.device)
+        mask = self.above_horizon.view(torch.uint8)
+        self._call("rsk_compact_index", _lib.ptr(mask), n, _lib.ptr(idx), _lib.ptr(cnt), _lib.ptr(work),
+                   ctypes.c_size_t(nbytes))
+        n_above = int(cnt.item())
+        return idx, n_above
+
+    def coherency_calc(self, store_frame_coherency=True, freqs=None, freq_interp_kind="cubic", out=None,
+                       ld_out=None, col0=0):
+        """Calculate the local coherency in the alt/az basis (skymodel.py:2648-2712).
+
+        :meth:`update_positions` must be run prior to this method.
+
+        Parameters
+        ----------
+        store_frame_coherency : bool
+            Accepted for signature compatibility; the fused kernel never needs the stored frame
+            coherency, so nothing is stored and no extra memory is used.
+        freqs : array_like of Hz, optional  (extension)
+            Evaluate the spectral model at these frequencies inside the same kernel, i.e. the result of
+            ``at_frequencies(freqs)`` followed by ``coherency_calc()`` upstream, without materialising
+            the (4, Nfreqs, Ncomponents) Stokes cube.  Default: the stored Stokes as they are.
+        out, ld_out, col0 : optional  (extension, multi-GPU assembly)
+            Write into columns [col0, col0 + N_above) of a preallocated complex128 buffer whose last
+            axis has length ``ld_out``.
+
+        Returns
+        -------
+        torch.Tensor, complex128, shape (2, 2, Nfreqs, N_above) -- component axis fastest, only
+        components above the horizon, in catalogue order.
+        """
+        if self.above_horizon is None:
+            warnings.warn("Horizon cutoff undefined. Assuming all source components are above the horizon.")
+            idx, n_above = None, self.Ncomponents
+        else:
+            idx, n_above = self.compact_above_horizon()
+        if self.telescope_location is not None:
+            self._check_tel_location(self.telescope_location)
+
+        keep = []
+        if freqs is None:
+            spec = self._spectrum_struct(_lib.FULL, keep)
+            nf = self.Nfreqs
+            fdev = None
+        else:
+            fhost = self._check_request(_to_hz_host(freqs), freq_interp_kind)
+            mode = _lib.SPECTRAL_MODES[self.spectral_type]
+            fmap = self._full_freq_map(fhost) if mode == _lib.FULL else None
+            spec = self._spectrum_struct(mode, keep, freq_interp_kind, fmap)
+            nf = fhost.size
+            fdev = self._freqs_dev(fhost)
+        ravg = None
+        altaz = None
+        if spec.polarized:
+            if self.alt_az is None:
+                raise ValueError("update_positions must be called before coherency_calc for polarized sources")
+            ravg = _lib.host_array(self._calc_average_rotation_matrix().ravel())
+            altaz = self.alt_az
+        if out is None:
+            out = torch.empty((2, 2, nf, n_above), dtype=torch.complex128, device=self.device)
+            ld_out, col0 = n_above, 0
+        elif ld_out is None:
+            ld_out = int(out.shape[-1])
+        coords = self._coords_struct()
+        self._call("rsk_coherency", ctypes.byref(spec), ctypes.byref(coords), _lib.ptr(altaz), ravg,
+                   None if idx is None else _lib.ptr(idx), n_above, _lib.ptr(fdev), nf, _lib.ptr(out),
+                   ld_out, col0)
+        self._last_n_above = n_above
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    # spectra
+    # ------------------------------------------------------------------------------------------
+    def _check_request(self, fhost, freq_interp_kind):
+        """Argument checks of at_frequencies that raise before any GPU work (skymodel.py:2156-2192)."""
+        if self.spectral_type == "spectral_index":
+            if bool(torch.isnan(self.spectral_index).any().item()):
+                raise ValueError("Some spectral index values are NaNs.")
+        elif self.spectral_type == "subband":
+            if np.max(fhost) > np.max(self.freq_array):
+                raise ValueError("A requested frequency is larger than the highest subband frequency.")
+            if np.min(fhost) < np.min(self.freq_array):
+                raise ValueError("A requested frequency is smaller than the lowest subband frequency.")
+            if bool(torch.isnan(self.stokes).any().item()):
+                raise NotImplementedError(
+                    "Subband Stokes with NaNs (nan_handling) are not supported on the GPU path yet."
+                )
+            spectral.interp_degree(freq_interp_kind)
+        return fhost
+
+    def _full_freq_map(self, fhost, atol=None):
+        """skymodel.py:2165-2181: stored channels matching the request within ``atol`` (1 Hz)."""
+        tol = self.freq_tol if atol is None else float(atol.to_value("Hz") if hasattr(atol, "to_value") else atol)
+        matches = np.fromiter(
+            (np.isclose(freq, fhost, atol=tol).any() for freq in self.freq_array), dtype=bool
+        )
+        if np.sum(matches) != fhost.size:
+            raise ValueError("Some requested frequencies are not present in the current SkyModel.")
+        return np.nonzero(matches)[0]
+
+    def at_frequencies(self, freqs, inplace=True, freq_interp_kind="cubic", nan_handling="clip",
+                       run_check=True, check_extra=True, run_check_acceptability=True, atol=None):
+        """Evaluate the stokes array at the specified frequencies (skymodel.py:2084-2389).
+
+        full: subset of existing channels; subband: spline interpolation; spectral_index: power law;
+        flat: copy.  The object becomes ``spectral_type='full'``.  Returns the new object iff
+        ``inplace`` is False.
+        """
+        sky = self if inplace else self.copy()
+        fhost = _to_hz_host(freqs)
+        self._check_request(fhost, freq_interp_kind)
+        mode = _lib.SPECTRAL_MODES[self.spectral_type]
+        fmap = self._full_freq_map(fhost, atol) if mode == _lib.FULL else None
+        keep = []
+        spec = self._spectrum_struct(mode, keep, freq_interp_kind, fmap, polarized=False)
+        nf = fhost.size if fmap is None else fmap.size
+        new_stokes = torch.empty((4, nf, self.Ncomponents), dtype=torch.float64, device=self.device)
+        fdev = self._freqs_dev(fhost)
+        self._call("rsk_at_frequencies", ctypes.byref(spec), _lib.ptr(fdev), nf, _lib.ptr(new_stokes))
+        sky.stokes = new_stokes
+        sky.reference_frequency = None
+        sky.Nfreqs = nf
+        sky.freq_array = fhost.copy() if fmap is None else self.freq_array[fmap].copy()
+        sky.spectral_type = "full"
+        if sky.frame_coherency is not None:
+            sky.calc_frame_coherency()
+        if not inplace:
+            return sky
+
+    # ------------------------------------------------------------------------------------------
+    # units
+    # ------------------------------------------------------------------------------------------
+    def _convert(self, to_jansky):
+        if self.spectral_type == "spectral_index" or (
+            self.spectral_type == "flat" and self.reference_frequency is not None
+        ):
+            fchan, fcomp = None, self.reference_frequency
+        elif self.freq_array is not None:
+            fchan, fcomp = self._freqs_dev(self.freq_array), None
+        else:
+            raise ValueError(
+                "Either reference_frequency or freq_array must be set to convert to "
+                + ("Jy." if to_jansky else "K.")
+            )
+        self._call("rsk_convert_units", _lib.ptr(self.stokes), self.Nfreqs, self.Ncomponents, _lib.ptr(fchan),
+                   _lib.ptr(fcomp), 1 if to_jansky else 0)
+        if self.frame_coherency is not None:
+            self.calc_frame_coherency()
+
+    def jansky_to_kelvin(self):
+        """Jy -> K sr (point) or Jy/sr -> K (healpix) in place (skymodel.py:1593-1635)."""
+        if self.stokes_unit == _K_UNITS[self.component_type]:
+            return
+        self._convert(to_jansky=False)
+        self.stokes_unit = _K_UNITS[self.component_type]
+
+    def kelvin_to_jansky(self):
+        """K sr -> Jy (point) or K -> Jy/sr (healpix) in place (skymodel.py:1541-1591)."""
+        if self.stokes_unit == _JY_UNITS[self.component_type]:
+            return
+        self._convert(to_jansky=True)
+        self.stokes_unit = _JY_UNITS[self.component_type]

@@ -1,0 +1,88 @@
+"""Host-side preparation of the subband interpolation operator.
+
+``SkyModel.at_frequencies`` interpolates subband spectra with
+``scipy.interpolate.interp1d(freq_array, stokes, axis=1, kind=freq_interp_kind)``
+(src/pyradiosky/skymodel.py:2362-2368).  For every supported ``kind`` that interpolant is (a) linear in
+the data and (b) built on knots shared by all components, so it is a piecewise polynomial whose
+coefficients are a fixed linear map of the stored channel values.  The map is computed once here, with
+scipy itself (the same ``make_interp_spline`` call ``interp1d`` makes), and handed to the kernel as a
+small dense operator; the kernel then needs ``(degree+1) * Nfreqs_in`` FMAs per component per break
+interval and a Horner evaluation per output channel.
+"""
+
+import numpy as np
+import scipy.interpolate
+
+_SPLINE_ORDER = {"slinear": 1, "quadratic": 2, "cubic": 3}
+
+
+def interp_degree(kind):
+    """Polynomial degree of ``interp1d(kind=...)`` or raise for kinds the kernel does not cover."""
+    if isinstance(kind, (int, np.integer)):
+        order = int(kind)
+    elif kind == "linear":
+        order = 1
+    elif kind in _SPLINE_ORDER:
+        order = _SPLINE_ORDER[kind]
+    else:
+        raise NotImplementedError(
+            f"freq_interp_kind={kind!r} is not supported on the GPU path; use 'linear', 'slinear', "
+            "'quadratic', 'cubic' or a spline order 1-3."
+        )
+    if order < 1 or order > 3:
+        raise NotImplementedError("Only spline orders 1, 2 and 3 are supported on the GPU path.")
+    return order
+
+
+def build_ppoly_operator(freq_array, kind="cubic"):
+    """Piecewise-polynomial form of ``interp1d(freq_array, ., kind)``.
+
+    Returns ``(degree, breaks, ppoly)`` with ``breaks`` of shape (nb+1,) and ``ppoly`` of shape
+    (nb, degree+1, Nfreqs_in): on interval b, with u = (f - breaks[b]) / (breaks[b+1] - breaks[b]),
+    ``value = sum_p u**p * (ppoly[b, p, :] @ y)`` for stored channel values ``y``.
+    """
+    x = np.asarray(freq_array, dtype=np.float64)
+    n = x.size
+    degree = interp_degree(kind)
+    if n <= degree:
+        # same condition interp1d raises on (and which makes the reference fall back to linear
+        # for NaN-depleted components, skymodel.py:2302-2309)
+        raise ValueError(f"The number of derivatives at boundaries does not match: expected "
+                         f"at least {degree + 1} points for kind={kind!r}, got {n}")
+    order = np.argsort(x, kind="stable")
+    xs = x[order]
+    if np.any(np.diff(xs) <= 0):
+        raise ValueError("Expect x to not have duplicates")
+    eye = np.eye(n)[order]  # data rows follow the sorted knots; columns = original channel index
+    if degree == 1:
+        breaks = xs
+        ppoly = np.zeros((n - 1, 2, n))
+        ppoly[:, 0, :] = eye[:-1]
+        ppoly[:, 1, :] = eye[1:] - eye[:-1]
+        return degree, breaks, ppoly
+    spl = scipy.interpolate.make_interp_spline(xs, eye, k=degree, check_finite=False)
+    # B-spline -> piecewise polynomial: Taylor coefficients at the left end of every non-empty knot
+    # interval (BSpline evaluation is right-continuous at interior knots).
+    t = spl.t
+    breaks = np.unique(t[degree : t.size - degree])
+    h = np.diff(breaks)
+    ppoly = np.zeros((h.size, degree + 1, n))
+    fact = 1.0
+    for p in range(degree + 1):
+        if p > 0:
+            fact *= p
+        deriv = spl.derivative(p) if p > 0 else spl
+        ppoly[:, p, :] = deriv(breaks[:-1]) / fact * (h**p)[:, None]
+    return degree, breaks, ppoly
+
+
+def evaluate_operator(degree, breaks, ppoly, y, freqs):
+    """numpy evaluation of the operator (host-side self-check helper; not used on the hot path)."""
+    freqs = np.asarray(freqs, dtype=np.float64)
+    b = np.clip(np.searchsorted(breaks, freqs, side="right") - 1, 0, len(breaks) - 2)
+    u = (freqs - breaks[b]) / (breaks[b + 1] - breaks[b])
+    coef = np.einsum("bpj,j...->bp...", ppoly, y)  # (nb, degree+1, ...)
+    out = 0.0
+    for p in range(degree, -1, -1):
+        out = out * u.reshape((-1,) + (1,) * (coef.ndim - 2)) + coef[b, p]
+    return out

@@ -1,0 +1,205 @@
+"""Host-side logic of the product that runs without a GPU: the C-ABI library loads and exports every
+symbol of include/rsk.h, the C++ context builder agrees with the oracle, argument errors."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.interpolate
+
+from oracle import erfa_np as E
+from oracle import skymodel_np as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(librsk):
+    header = open(os.path.join(ROOT, "include", "rsk.h")).read()
+    declared = set(re.findall(r"\b(rsk_[a-z_0-9]+)\s*\(", header))
+    declared = {d for d in declared if not d.endswith("_") and d != "rsk_pack_context()"}
+    from pyradiosky_b200 import _lib
+
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(librsk, name), name
+    assert librsk.rsk_version() == 100
+    assert librsk.rsk_strerror(0) == b"success"
+    assert b"pointer" in librsk.rsk_strerror(-1)
+
+
+def test_struct_layouts_match_header():
+    from pyradiosky_b200 import _lib
+
+    assert ctypes.sizeof(_lib.RskCoords) == 48
+    assert ctypes.sizeof(_lib.RskSpectrum) == 88
+    assert _lib.ASTROM_LEN == 31 and _lib.CTX_LEN == 34
+
+
+def test_argument_errors_without_gpu(librsk):
+    """Argument validation happens before any CUDA call, so it is testable on a CPU-only box."""
+    from pyradiosky_b200 import _lib
+
+    d9 = (ctypes.c_double * 9)()
+    assert librsk.rsk_frame_to_icrs(99, 2000.0, d9) == -3
+    assert librsk.rsk_ravg(None, d9) == -1
+    coords = _lib.RskCoords()
+    coords.nside = 0
+    a = (ctypes.c_double * 31)()
+    assert librsk.rsk_positions(ctypes.byref(coords), 10, None, a, None, None, None, None) == -1  # lon/lat NULL
+    coords.nside = 12
+    coords.nested = 1
+    assert librsk.rsk_positions(ctypes.byref(coords), 10, None, a, None, None, None, None) == -7  # nested needs 2^k
+    spec = _lib.RskSpectrum()
+    spec.mode = 7
+    spec.stokes = 8
+    spec.nf_in = 1
+    spec.n = 4
+    assert librsk.rsk_coherency(ctypes.byref(spec), ctypes.byref(coords), None, None, None, 4, None, 1, None, 4, 0, None) == -3
+    spec.mode = _lib.FLAT
+    assert librsk.rsk_coherency(ctypes.byref(spec), ctypes.byref(coords), None, None, None, 4, None, 1, ctypes.c_void_p(8), 2, 0, None) == -4
+    spec.mode = _lib.SUBBAND
+    spec.degree = 5
+    spec.breaks = 8
+    spec.ppoly = 8
+    spec.nb = 3
+    assert librsk.rsk_coherency(ctypes.byref(spec), ctypes.byref(coords), None, None, None, 4, ctypes.c_void_p(8), 1, ctypes.c_void_p(8), 4, 0, None) == -6
+    assert librsk.rsk_compact_index(ctypes.c_void_p(8), 100, ctypes.c_void_p(8), ctypes.c_void_p(8), None, 0, None) == -5
+    assert librsk.rsk_workspace_bytes(_lib.OP_COMPACT, 5000, 0) == (3 + 1) * 8
+    # zero-sized problems are accepted without touching the device
+    assert librsk.rsk_polarized_mask(None, 1, 0, None, None) == 0
+    assert librsk.rsk_convert_units(None, 0, 0, None, None, 0, None) == 0
+
+
+def test_context_builder_matches_oracle(librsk, hera):
+    from pyradiosky_b200 import astrometry
+
+    lon, lat, h, jd = hera
+    loc = astrometry.EarthLocation.from_dms((-30, 43, 17.5), (21, 25, 41.9), h)
+    assert np.isclose(loc.lon, lon, rtol=0, atol=1e-16) and np.isclose(loc.lat, lat, rtol=0, atol=1e-16)
+    t0 = astrometry.Time.from_utc("2015-03-01 00:00:00")
+    assert t0.jd == jd
+    for frac, dut1, xp, yp in [(0.0, 0.0, 0.0, 0.0), (0.37, -0.47, 1e-7, 1.5e-6), (200.25, 0.3, -2e-7, 1e-6)]:
+        t = astrometry.Time(jd, frac, dut1=dut1, xp=xp, yp=yp)
+        got = astrometry.astrom_context(t, loc)
+        ref = E.astrom_context(jd, frac, lon, lat, h, dut1=dut1, xp=xp, yp=yp)
+        assert got.shape == (31,)
+        assert np.abs(got - ref).max() < 2e-15
+        ravg = astrometry.average_rotation_matrix(got)
+        assert np.abs(ravg - S.calc_average_rotation_matrix(ref)).max() < 3e-15
+        assert np.abs(ravg @ ravg.T - np.eye(3)).max() < 1e-15
+    assert np.allclose(loc.geocentric, [5109342.76, 2005241.904, -3239939.469], atol=1e-3)  # tutorial.rst:1233
+
+
+def test_time_parsing():
+    from pyradiosky_b200.astrometry import Time
+
+    assert Time.from_utc("2000-01-01 12:00:00").jd == 2451545.0
+    assert Time.from_utc("2015-03-05 00:00:00").jd == 2457086.5
+    assert abs(Time.from_utc("2018-03-01 18:00:00.500").jd2 - (18 * 3600 + 0.5) / 86400) < 1e-15
+    t = Time.from_utc("2015-03-01 00:00:00")
+    assert (t + 0.25).jd == t.jd + 0.25 and t == Time(2457082.5) and t != t + 1e-9
+
+
+def test_frame_matrices(librsk):
+    from pyradiosky_b200.astrometry import frame_to_icrs_matrix
+
+    assert np.array_equal(frame_to_icrs_matrix("icrs"), np.eye(3))
+    fk5 = frame_to_icrs_matrix("fk5")
+    gal = frame_to_icrs_matrix("galactic")
+    for m in (fk5, gal, frame_to_icrs_matrix("fk5", 1950.0)):
+        assert np.abs(m @ m.T - np.eye(3)).max() < 1e-15 and np.isclose(np.linalg.det(m), 1)
+    # frame bias off-diagonals (-22.9, -9.1, +19.9) mas (IERS conventions)
+    mas = np.pi / 180 / 3600e3
+    to_fk5 = fk5.T
+    assert np.isclose(to_fk5[0, 1] / mas, -22.9, atol=1e-3)
+    assert np.isclose(to_fk5[0, 2] / mas, -9.1, atol=1e-3)
+    assert np.isclose(to_fk5[1, 2] / mas, 19.9, atol=1e-3)
+    # galactic north pole and centre in FK5 J2000
+    pole = fk5.T @ gal @ np.array([0, 0, 1.0])
+    assert np.isclose(np.rad2deg(np.arctan2(pole[1], pole[0])) % 360, 192.8594812, atol=1e-6)
+    assert np.isclose(np.rad2deg(np.arcsin(pole[2])), 27.1282512, atol=1e-6)
+    centre = fk5.T @ gal @ np.array([1.0, 0, 0])
+    assert np.isclose(np.rad2deg(np.arctan2(centre[1], centre[0])) % 360, 266.40500, atol=1e-4)
+    assert np.isclose(np.rad2deg(np.arcsin(centre[2])), -28.93617, atol=1e-4)
+    # precession 2000 -> 1950: ~0.64 deg in RA of the pole-ward axes
+    p = frame_to_icrs_matrix("fk5", 1950.0) @ fk5.T
+    assert 0.0110 < abs(p[0, 1]) < 0.0113
+    with pytest.raises(ValueError, match="not supported"):
+        frame_to_icrs_matrix("fk4")
+
+
+def test_packed_context_reproduces_chain(librsk, hera):
+    """rsk_pack_context merges bpn, Earth rotation and polar motion into one matrix: it must map the
+    aberrated direction to the same (-HA, Dec) vector as the step-by-step ERFA chain."""
+    from pyradiosky_b200 import astrometry
+
+    lon, lat, h, jd = hera
+    a = E.astrom_context(jd, 0.2, lon, lat, h, dut1=-0.4, xp=2e-7, yp=1.4e-6)
+    ctx = astrometry.pack_context(a)
+    assert ctx.shape == (34,)
+    a1 = ctx[8:17].reshape(3, 3)
+    rng = np.random.default_rng(2)
+    p = rng.normal(size=(3, 50)); p /= np.linalg.norm(p, axis=0)
+    pi = E.rxp(a[E.I_BPN:E.I_BPN + 9], p)
+    ri, di = E.c2s(pi)
+    v = E.s2c(E.anp(ri) - a[E.I_ERAL], di)
+    sx, cx = np.sin(a[E.I_XPL]), np.cos(a[E.I_XPL]); sy, cy = np.sin(a[E.I_YPL]), np.cos(a[E.I_YPL])
+    hd = np.array([cx * v[0] + sx * v[2], sx * sy * v[0] + cy * v[1] - cx * sy * v[2], -sx * cy * v[0] + sy * v[1] + cx * cy * v[2]])
+    assert np.abs(a1 @ p - hd).max() < 1e-15
+    assert ctx[22] == E.SRS / a[E.I_EM] and ctx[23] == 1.0
+    m = astrometry.frame_to_icrs_matrix("fk5")
+    ctx2 = astrometry.pack_context(a, m)
+    assert ctx2[23] == 0.0 and np.array_equal(ctx2[25:34].reshape(3, 3), m)
+
+
+@pytest.mark.parametrize("kind", ["linear", "slinear", "quadratic", "cubic", 1, 2, 3])
+def test_ppoly_operator_matches_interp1d(kind):
+    from pyradiosky_b200 import spectral
+
+    x = np.array([76, 84, 92, 99, 107, 115, 122, 130, 143, 151, 158, 166, 174, 181, 189, 197, 204, 212, 220, 227]) * 1e6
+    rng = np.random.default_rng(0)
+    y = rng.normal(size=(20, 7)) + 3
+    f = np.linspace(x[0], x[-1], 777)
+    degree, breaks, ppoly = spectral.build_ppoly_operator(x, kind)
+    assert ppoly.shape == (breaks.size - 1, degree + 1, 20)
+    ref = scipy.interpolate.interp1d(x, y, axis=0, kind=kind)(f)
+    assert np.abs(spectral.evaluate_operator(degree, breaks, ppoly, y, f) - ref).max() < 1e-13
+    perm = rng.permutation(20)  # unsorted freq_array, as interp1d tolerates
+    degree, breaks, ppoly = spectral.build_ppoly_operator(x[perm], kind)
+    ref = scipy.interpolate.interp1d(x[perm], y[perm], axis=0, kind=kind)(f)
+    assert np.abs(spectral.evaluate_operator(degree, breaks, ppoly, y[perm], f) - ref).max() < 1e-13
+
+
+def test_ppoly_operator_errors():
+    from pyradiosky_b200 import spectral
+
+    with pytest.raises(NotImplementedError):
+        spectral.build_ppoly_operator(np.linspace(1, 2, 10), "nearest")
+    with pytest.raises(NotImplementedError):
+        spectral.build_ppoly_operator(np.linspace(1, 2, 10), 5)
+    with pytest.raises(ValueError):
+        spectral.build_ppoly_operator(np.linspace(1, 2, 3), "cubic")
+
+
+def test_no_cpu_fallback(librsk):
+    """Without a CUDA device the product must refuse to run rather than fall back."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from pyradiosky_b200 import SkyModel
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        SkyModel(ra=[0.1], dec=[0.2], stokes=np.ones((4, 1, 1)), spectral_type="flat")
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "pyradiosky_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
