@@ -384,3 +384,24 @@ def astrom_context(jd_utc1, jd_utc2, elong, phi, height, dut1=0.0, xp=0.0, yp=0.
     sp = sp00(tt1, tt2)
     ebpv, ehp = earth_pv_medium(tt1 + tt2)
     return apco(tt1, tt2, ebpv, ehp, x, y, s, theta, elong, phi, height, xp, yp, sp, 0.0, 0.0)
+
+
+def frame_to_icrs(frame):
+    """3x3 matrix taking FK5(J2000) / Galactic unit vectors to ICRS (identity for 'icrs').
+
+    astropy ``builtin_frames.icrs_fk5_transforms._icrs_to_fk5_matrix`` (frame bias eta0 = -19.9 mas,
+    xi0 = 9.1 mas, da0 = -22.9 mas) and ``galactic_transforms.fk5_to_gal`` (NGP 192.8594812065348,
+    27.12825118085622 deg; lon0 122.9319185680026 deg); the catalogue -> ICRS leg of the transform the
+    reference runs for non-ICRS catalogues such as GLEAM (skymodel.py:4182).
+    """
+    frame = str(frame).lower()
+    if frame == "icrs":
+        return np.eye(3)
+    deg = np.pi / 180.0
+    b = _rx(19.9 / 3600e3 * deg) @ _ry(9.1 / 3600e3 * deg) @ _rz(-22.9 / 3600e3 * deg)
+    if frame == "fk5":
+        return b.T
+    if frame == "galactic":
+        g = _rz((180.0 - 122.9319185680026) * deg) @ _ry((90.0 - 27.12825118085622) * deg) @ _rz(192.8594812065348 * deg)
+        return (g @ b).T
+    raise ValueError(f"unsupported frame {frame}")

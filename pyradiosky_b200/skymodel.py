@@ -364,6 +364,32 @@ class SkyModel:
                    _lib.host_array(astrom), _lib.ptr(self.alt_az), _lib.ptr(self.pos_lmn), _lib.ptr(above))
         self.above_horizon = above.view(torch.bool)
 
+    def positions_sweep(self, times, telescope_location, astroms=None, want_lmn=False, want_mask=True):
+        """Alt/Az of every component at many times in one launch (extension; BASELINE config 5).
+
+        Equivalent to calling :meth:`update_positions` for each element of ``times`` (as the
+        reference's LST-sweep test does, tests/test_skymodel.py:2661-2740) without touching the
+        object's state.  Returns ``(alt_az [T, 2, N], pos_lmn [T, 3, N] or None, above [T, N] bool or
+        None)`` as CUDA tensors.  ``astroms`` optionally supplies ready (T, 31) eraASTROM rows.
+        """
+        self._check_tel_location(telescope_location)
+        if astroms is None:
+            for t in times:
+                if not astrometry.is_time(t):
+                    raise ValueError(f"time must be an astropy Time object. value was: {t}")
+            astroms = np.stack([astrometry.astrom_context(t, telescope_location) for t in times])
+        astroms = np.ascontiguousarray(astroms, dtype=np.float64).reshape(-1, _lib.ASTROM_LEN)
+        nt, n = astroms.shape[0], self.Ncomponents
+        ctx = np.stack([astrometry.pack_context(a, self._frame_to_icrs) for a in astroms])
+        ctx_dev = torch.as_tensor(ctx).to(self.device)
+        alt_az = torch.empty((nt, 2, n), dtype=torch.float64, device=self.device)
+        lmn = torch.empty((nt, 3, n), dtype=torch.float64, device=self.device) if want_lmn else None
+        above = torch.empty((nt, n), dtype=torch.uint8, device=self.device) if want_mask else None
+        coords = self._coords_struct()
+        self._call("rsk_positions_sweep", ctypes.byref(coords), n, _lib.ptr(ctx_dev), nt, _lib.ptr(alt_az),
+                   _lib.ptr(lmn), _lib.ptr(above))
+        return alt_az, lmn, (None if above is None else above.view(torch.bool))
+
     # ------------------------------------------------------------------------------------------
     # coherency
     # ------------------------------------------------------------------------------------------
@@ -422,6 +448,19 @@ class SkyModel:
         torch.Tensor, complex128, shape (2, 2, Nfreqs, N_above) -- component axis fastest, only
         components above the horizon, in catalogue order.
         """
+        plan = self._plan_coherency(freqs, freq_interp_kind)
+        nf, n_above = plan["nf"], plan["n_above"]
+        if out is None:
+            out = torch.empty((2, 2, nf, n_above), dtype=torch.complex128, device=self.device)
+            ld_out, col0 = n_above, 0
+        elif ld_out is None:
+            ld_out = int(out.shape[-1])
+        self._launch_coherency(plan, 0, nf, out, ld_out, col0)
+        return out
+
+    def _plan_coherency(self, freqs, freq_interp_kind):
+        """Everything coherency_calc needs before the launch: horizon compaction, spectral description,
+        R_avg.  One device->host read (the above-horizon count)."""
         if self.above_horizon is None:
             warnings.warn("Horizon cutoff undefined. Assuming all source components are above the horizon.")
             idx, n_above = None, self.Ncomponents
@@ -429,19 +468,19 @@ class SkyModel:
             idx, n_above = self.compact_above_horizon()
         if self.telescope_location is not None:
             self._check_tel_location(self.telescope_location)
-
         keep = []
+        fmap = None
         if freqs is None:
-            spec = self._spectrum_struct(_lib.FULL, keep)
+            mode = _lib.FULL
             nf = self.Nfreqs
             fdev = None
         else:
             fhost = self._check_request(_to_hz_host(freqs), freq_interp_kind)
             mode = _lib.SPECTRAL_MODES[self.spectral_type]
             fmap = self._full_freq_map(fhost) if mode == _lib.FULL else None
-            spec = self._spectrum_struct(mode, keep, freq_interp_kind, fmap)
             nf = fhost.size
             fdev = self._freqs_dev(fhost)
+        spec = self._spectrum_struct(mode, keep, freq_interp_kind, fmap)
         ravg = None
         altaz = None
         if spec.polarized:
@@ -449,17 +488,81 @@ class SkyModel:
                 raise ValueError("update_positions must be called before coherency_calc for polarized sources")
             ravg = _lib.host_array(self._calc_average_rotation_matrix().ravel())
             altaz = self.alt_az
-        if out is None:
-            out = torch.empty((2, 2, nf, n_above), dtype=torch.complex128, device=self.device)
-            ld_out, col0 = n_above, 0
-        elif ld_out is None:
-            ld_out = int(out.shape[-1])
-        coords = self._coords_struct()
-        self._call("rsk_coherency", ctypes.byref(spec), ctypes.byref(coords), _lib.ptr(altaz), ravg,
-                   None if idx is None else _lib.ptr(idx), n_above, _lib.ptr(fdev), nf, _lib.ptr(out),
-                   ld_out, col0)
         self._last_n_above = n_above
-        return out
+        return dict(spec=spec, keep=keep, mode=mode, nf=nf, fdev=fdev, idx=idx, n_above=n_above, ravg=ravg,
+                    altaz=altaz, coords=self._coords_struct())
+
+    def _launch_coherency(self, plan, f0, f1, out, ld_out, col0):
+        """Launch K2 for request channels [f0, f1) into ``out`` (complex [2][2][f1-f0][ld_out])."""
+        spec, mode = plan["spec"], plan["mode"]
+        nf = f1 - f0
+        fptr = None
+        if plan["fdev"] is not None:
+            fptr = ctypes.c_void_p(plan["fdev"].data_ptr() + 8 * f0)
+        saved_map = spec.freq_map
+        if mode == _lib.FULL and (f0 != 0 or f1 != plan["nf"]):
+            if not spec.freq_map:  # identity map needed once a slab does not start at channel 0
+                ident = torch.arange(plan["nf"], dtype=torch.int32, device=self.device)
+                plan["keep"].append(ident)
+                saved_map = ident.data_ptr()
+            spec.freq_map = saved_map + 4 * f0
+        events = getattr(self, "_timing_events", None)
+        if events is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(torch.cuda.current_stream(self.device))
+        self._call("rsk_coherency", ctypes.byref(spec), ctypes.byref(plan["coords"]), _lib.ptr(plan["altaz"]),
+                   plan["ravg"], None if plan["idx"] is None else _lib.ptr(plan["idx"]), plan["n_above"], fptr, nf,
+                   _lib.ptr(out), ld_out, col0)
+        if events is not None:
+            ev1.record(torch.cuda.current_stream(self.device))
+            events.append((ev0, ev1))
+        spec.freq_map = saved_map
+
+    def coherency_calc_to_host(self, freqs, host_out, slab=64, freq_interp_kind="cubic"):
+        """``coherency_calc(freqs=...)`` delivered into pinned HOST memory (extension).
+
+        The frequency axis is processed in slabs: while the kernel fills one device slab, the previous
+        one streams to the host on a second CUDA stream, so HBM never holds more than two slabs and the
+        PCIe copy overlaps the compute.  ``host_out`` is a flat pinned complex128 tensor with room for
+        4 * Nfreqs * N_above values; the returned tensor is its (2, 2, Nfreqs, N_above) view.  The call
+        returns after the last copy has been queued; synchronise before reading.
+        """
+        plan = self._plan_coherency(freqs, freq_interp_kind)
+        nf, n_above = plan["nf"], plan["n_above"]
+        need = 4 * nf * n_above
+        if host_out.dtype != torch.complex128 or host_out.numel() < need or not host_out.is_pinned():
+            raise ValueError(f"host_out must be a pinned complex128 tensor with at least {need} elements")
+        view = host_out.reshape(-1)[:need].view(2, 2, nf, n_above)
+        if need == 0:
+            return view
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        copy = self._copy_stream
+        slab = max(1, min(slab, nf))
+        bufs = [torch.empty((2, 2, slab, n_above), dtype=torch.complex128, device=self.device) for _ in range(2)]
+        freed = [None, None]
+        for i, f0 in enumerate(range(0, nf, slab)):
+            f1 = min(nf, f0 + slab)
+            buf = bufs[i % 2]
+            if freed[i % 2] is not None:
+                main.wait_event(freed[i % 2])
+            dst = buf if f1 - f0 == slab else buf.reshape(-1)[: 4 * (f1 - f0) * n_above].view(2, 2, f1 - f0, n_above)
+            self._launch_coherency(plan, f0, f1, dst, n_above, 0)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            copy.wait_event(ready)
+            with torch.cuda.stream(copy):
+                for a in range(2):
+                    for b in range(2):
+                        view[a, b, f0:f1].copy_(dst[a, b], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(copy)
+            freed[i % 2] = done
+        main.wait_stream(copy)
+        for b in bufs:
+            b.record_stream(copy)
+        return view
 
     # ------------------------------------------------------------------------------------------
     # spectra

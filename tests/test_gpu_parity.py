@@ -1,0 +1,665 @@
+"""Parity of the CUDA path (through the C-ABI / SkyModel shim) with the CPU oracle.
+
+Tolerances (BASELINE.json north_star): Alt/Az within 1 micro-arcsecond; horizon masks identical away
+from the horizon; coherencies within 1e-12 relative (relative to Stokes I of the same component and
+channel -- off-diagonals of weakly polarised sources inherit absolute, not relative, rounding);
+integer / index / byte outputs bit-exact.
+"""
+
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import erfa_np as E
+from oracle import healpix_np as hp
+from oracle import skymodel_np as S
+
+pytestmark = pytest.mark.gpu
+
+UAS = np.pi / 180 / 3600 * 1e-6  # one micro-arcsecond in radians
+GLEAM_BANDS = np.array([76, 84, 92, 99, 107, 115, 122, 130, 143, 151, 158, 166, 174, 181, 189, 197, 204, 212, 220, 227]) * 1e6
+
+
+@pytest.fixture(scope="module")
+def rsk(librsk):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pyradiosky_b200
+
+    return pyradiosky_b200
+
+
+@pytest.fixture(scope="module")
+def site(rsk):
+    loc = rsk.EarthLocation.from_dms((-30, 43, 17.5), (21, 25, 41.9), 1073.0)
+    time = rsk.Time.from_utc("2015-03-01 00:00:00")
+    return time, loc
+
+
+def random_sky(rng, n):
+    return rng.uniform(0, 2 * np.pi, n), np.arcsin(rng.uniform(-1, 1, n))
+
+
+def polarized_stokes(rng, n, nf=1):
+    """BASELINE config 2 recipe: I = 10^U(-2,1), p = U(0, .1), psi = U(0, pi), V = .01 I N(0,1)."""
+    st = np.zeros((4, nf, n))
+    i = 10 ** rng.uniform(-2, 1, n)
+    p = rng.uniform(0, 0.1, n)
+    psi = rng.uniform(0, np.pi, n)
+    st[0] = i
+    st[1] = p * i * np.cos(2 * psi)
+    st[2] = p * i * np.sin(2 * psi)
+    st[3] = 0.01 * i * rng.normal(size=n)
+    return st
+
+
+def assert_altaz_close(got_alt_az, ref_alt_az, tol=UAS):
+    d_alt = np.abs(got_alt_az[0] - ref_alt_az[0])
+    d_az = np.abs(got_alt_az[1] - ref_alt_az[1])
+    d_az = np.minimum(d_az, 2 * np.pi - d_az) * np.cos(ref_alt_az[0])  # on-sky azimuth error
+    assert d_alt.max() < tol, f"alt differs by {d_alt.max() / UAS:.3g} uas"
+    assert d_az.max() < tol, f"az differs by {d_az.max() / UAS:.3g} uas"
+
+
+def assert_mask_equal(got, ref, alt, guard=1e-9):
+    got, ref = np.asarray(got, bool), np.asarray(ref, bool)
+    away = np.abs(alt) > guard
+    assert np.array_equal(got[away], ref[away])
+
+
+def assert_coherency_close(got, ref, stokes_i_above, tol=1e-12):
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    if got.size == 0:
+        return
+    err = np.abs(got - ref) / np.abs(stokes_i_above)[None, None]
+    assert np.nanmax(err) < tol, f"coherency error {np.nanmax(err):.3g} relative to Stokes I"
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE config 1
+# ---------------------------------------------------------------------------------------------------
+def test_config1_flat_stokes_i(rsk, site):
+    """1,000 flat-spectrum Stokes-I point sources, update_positions + coherency_calc at one time at HERA."""
+    time, loc = site
+    rng = np.random.default_rng(1)
+    n = 1000
+    ra, dec = random_sky(rng, n)
+    st = np.zeros((4, 1, n)); st[0, 0] = 10 ** rng.uniform(-2, 1, n)
+    sky = rsk.SkyModel(ra=ra, dec=dec, frame="icrs", stokes=st, spectral_type="flat")
+    assert sky._n_polarized == 0 and sky.Ncomponents == n and sky.Nfreqs == 1
+    sky.update_positions(time, loc)
+    coh = sky.coherency_calc().cpu().numpy()
+    alt_az, lmn, above = S.update_positions(ra, dec, sky._astrom)
+    assert_altaz_close(sky.alt_az.cpu().numpy(), alt_az)
+    assert np.abs(sky.pos_lmn.cpu().numpy() - lmn).max() < 1e-14
+    assert np.array_equal(sky.above_horizon.cpu().numpy(), above)
+    ref = S.coherency_calc(st, ra, dec, alt_az, above, S.calc_average_rotation_matrix(sky._astrom))
+    assert np.array_equal(coh, ref)  # unpolarised: exactly 0.5 * I on the diagonal
+    assert coh.shape == (2, 2, 1, int(above.sum()))
+    # repeated call with the same time/location is a no-op (skymodel.py:2439-2441)
+    before = sky.alt_az.data_ptr()
+    sky.update_positions(time, loc)
+    assert sky.alt_az.data_ptr() == before
+
+
+# ---------------------------------------------------------------------------------------------------
+# positions
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("frame", ["icrs", "fk5", "galactic"])
+@pytest.mark.parametrize("eop", [(0.0, 0.0, 0.0), (-0.47, 1.2e-7, 1.5e-6)])
+def test_positions_vs_oracle(rsk, site, frame, eop):
+    _, loc = site
+    rng = np.random.default_rng(2)
+    n = 20011
+    lon, lat = random_sky(rng, n)
+    lon[:4] = [0.0, np.pi, 2 * np.pi - 1e-12, 1.0]
+    lat[:4] = [np.pi / 2, -np.pi / 2, 0.0, np.pi / 2 - 1e-9]
+    st = np.zeros((4, 1, n)); st[0] = 1
+    time = rsk.Time(2457082.5, 0.31, dut1=eop[0], xp=eop[1], yp=eop[2])
+    sky = rsk.SkyModel(lon=lon, lat=lat, frame=frame, stokes=st, spectral_type="flat")
+    sky.update_positions(time, loc)
+    m = rsk.astrometry.frame_to_icrs_matrix(frame)
+    ref_astrom = E.astrom_context(time.jd1, time.jd2, loc.lon, loc.lat, loc.height, dut1=eop[0], xp=eop[1], yp=eop[2])
+    assert np.abs(ref_astrom - sky._astrom).max() < 2e-15
+    alt_az, lmn, above = S.update_positions(lon, lat, sky._astrom, None if frame == "icrs" else m)
+    assert_altaz_close(sky.alt_az.cpu().numpy(), alt_az)
+    assert np.abs(sky.pos_lmn.cpu().numpy() - lmn).max() < 1e-14
+    assert_mask_equal(sky.above_horizon.cpu().numpy(), above, alt_az[0])
+    assert 0.35 < above.mean() < 0.65
+
+
+def test_positions_zenith_and_refraction_context(rsk, site):
+    """Zenith source (tests/test_skymodel.py:481-527) and a context with refraction + diurnal aberration
+    (what erfa.apco gives for a frame with pressure / eraApio), through the astrom= extension."""
+    time, loc = site
+    a = rsk.astrometry.astrom_context(time, loc)
+    ra, dec = E.altaz_to_icrs(np.array([np.pi / 2, np.deg2rad(80.0)]), np.array([0.0, np.deg2rad(10.0)]), a)
+    st = np.zeros((4, 1, 2)); st[0] = 1
+    sky = rsk.SkyModel(ra=ra, dec=dec, stokes=st, spectral_type="flat")
+    sky.update_positions(time, loc)
+    lmn = sky.pos_lmn.cpu().numpy()
+    assert np.allclose(lmn[:, 0], [0, 0, 1], atol=1e-9)
+    assert np.allclose(sky.alt_az.cpu().numpy()[:, 1], np.deg2rad([80.0, 10.0]), atol=1e-12)
+    a2 = a.copy()
+    a2[E.I_REFA], a2[E.I_REFB], a2[E.I_DIURAB] = 2.8e-4, -3.2e-7, 1.3e-6
+    rng = np.random.default_rng(5)
+    lon, lat = random_sky(rng, 5000)
+    st = np.zeros((4, 1, 5000)); st[0] = 1
+    sky = rsk.SkyModel(ra=lon, dec=lat, stokes=st, spectral_type="flat")
+    sky.update_positions(time, loc, astrom=a2)
+    alt_az, lmn, above = S.update_positions(lon, lat, a2)
+    assert_altaz_close(sky.alt_az.cpu().numpy(), alt_az)
+    assert_mask_equal(sky.above_horizon.cpu().numpy(), above, alt_az[0])
+
+
+def test_update_positions_errors(rsk, site):
+    time, loc = site
+    st = np.zeros((4, 1, 3)); st[0] = 1
+    sky = rsk.SkyModel(ra=[0.1, 0.2, 0.3], dec=[0.0, 0.1, 0.2], stokes=st, spectral_type="flat")
+    with pytest.raises(ValueError, match="time must be an astropy Time object"):
+        sky.update_positions("2015-03-01", loc)
+    with pytest.raises(ValueError, match="telescope_location must be an"):
+        sky.update_positions(time, (0.1, 0.2, 3.0))
+    with pytest.warns(UserWarning, match="Horizon cutoff undefined"):
+        out = sky.coherency_calc()
+    assert out.shape == (2, 2, 1, 3)
+    sky.update_positions(time, loc)
+    sky.clear_time_position_specific_params()
+    assert sky.alt_az is None and sky.time is None and sky.above_horizon is None
+
+
+@pytest.mark.parametrize("order", ["ring", "nested"])
+@pytest.mark.parametrize("nside", [1, 8, 64])
+def test_healpix_positions(rsk, site, order, nside):
+    """tests/test_skymodel.py:2085-2171: healpix positions == transform of the pixel centres."""
+    time, loc = site
+    npix = 12 * nside * nside
+    rng = np.random.default_rng(nside)
+    st = np.zeros((4, 1, npix)); st[0] = rng.uniform(1, 2, npix)
+    sky = rsk.SkyModel(nside=nside, hpx_order=order, hpx_frame="icrs", stokes=st, spectral_type="flat",
+                       component_type="healpix", stokes_unit="K")
+    lon, lat = sky.get_lon_lat()
+    rlon, rlat = hp.healpix_to_lonlat(nside, np.arange(npix), nested=(order == "nested"))
+    assert np.abs(lon.cpu().numpy() - rlon).max() < 1e-14 and np.abs(lat.cpu().numpy() - rlat).max() < 1e-14
+    sky.update_positions(time, loc)
+    alt_az, lmn, above = S.update_positions(rlon, rlat, sky._astrom)
+    assert_altaz_close(sky.alt_az.cpu().numpy(), alt_az)
+    assert_mask_equal(sky.above_horizon.cpu().numpy(), above, alt_az[0])
+    # explicit, shuffled hpx_inds
+    inds = rng.permutation(npix)[: max(1, npix // 3)]
+    sky2 = rsk.SkyModel(nside=nside, hpx_order=order, hpx_inds=inds, stokes=st[:, :, : inds.size],
+                        spectral_type="flat", component_type="healpix", stokes_unit="K")
+    sky2.update_positions(time, loc)
+    assert_altaz_close(sky2.alt_az.cpu().numpy(), alt_az[:, inds])
+
+
+def test_healpix_large_nside_pixel_centres(rsk):
+    """nside 1024 (BASELINE config 3) and 2^20: spot-check both orderings against the oracle."""
+    for nside in (1024, 1 << 20):
+        npix = 12 * nside * nside
+        rng = np.random.default_rng(4)
+        inds = np.unique(np.concatenate((rng.integers(0, npix, 20000), [0, 1, 2, 3, npix - 1, npix - 4, npix // 2])))
+        for order in ("ring", "nested"):
+            st = np.zeros((4, 1, inds.size)); st[0] = 1
+            sky = rsk.SkyModel(nside=nside, hpx_order=order, hpx_inds=inds, stokes=st, spectral_type="flat",
+                               component_type="healpix", stokes_unit="K")
+            lon, lat = sky.get_lon_lat()
+            rlon, rlat = hp.healpix_to_lonlat(nside, inds, nested=(order == "nested"))
+            assert np.abs(lon.cpu().numpy() - rlon).max() < 1e-14
+            assert np.abs(lat.cpu().numpy() - rlat).max() < 1e-14
+
+
+def test_sweep_equals_repeated_update(rsk, site):
+    time, loc = site
+    rng = np.random.default_rng(6)
+    n, nt = 3001, 37
+    lon, lat = random_sky(rng, n)
+    st = np.zeros((4, 1, n)); st[0] = 1
+    sky = rsk.SkyModel(ra=lon, dec=lat, frame="fk5", stokes=st, spectral_type="flat")
+    times = [time + k * 0.9972696 / nt for k in range(nt)]
+    alt_az, lmn, above = sky.positions_sweep(times, loc, want_lmn=True)
+    assert alt_az.shape == (nt, 2, n) and lmn.shape == (nt, 3, n) and above.shape == (nt, n)
+    for k in (0, 1, 17, nt - 1):
+        sky.update_positions(times[k], loc)
+        # same device function in both kernels; allow for different FMA contraction only
+        assert float((sky.alt_az - alt_az[k]).abs().max()) < 1e-14
+        assert float((sky.pos_lmn - lmn[k]).abs().max()) < 1e-14
+        assert_mask_equal(above[k].cpu().numpy(), sky.above_horizon.cpu().numpy(), sky.alt_az[0].cpu().numpy())
+    # circumpolar / never-rising sets, tests/test_skymodel.py:2726-2737
+    m = rsk.astrometry.frame_to_icrs_matrix("fk5")
+    x = m @ np.array([np.cos(lat) * np.cos(lon), np.cos(lat) * np.sin(lon), np.sin(lat)])
+    tans = np.tan(loc.lat) * np.tan(np.arcsin(x[2]))
+    up = above.cpu().numpy()
+    margin = np.abs(np.abs(tans) - 1) > 0.1
+    assert np.array_equal(up.all(axis=0)[margin], (tans > 1)[margin])
+    assert np.array_equal((~up).all(axis=0)[margin], (tans < -1)[margin])
+    a2, _, m2 = sky.positions_sweep(times[:3], loc, want_lmn=False, want_mask=False)
+    assert m2 is None and float((a2 - alt_az[:3]).abs().max()) < 1e-14
+
+
+# ---------------------------------------------------------------------------------------------------
+# compaction, polarised predicate (bit-exact)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 2047, 2048, 2049, 100003, 1 << 21])
+def test_compact_index_bit_exact(rsk, n):
+    from pyradiosky_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(n)
+    for density, offset in ((0.5, 0), (0.02, 3), (1.0, 0), (0.0, 1)):
+        mask_full = (rng.uniform(size=n + 8) < density).astype(np.uint8)
+        mask_full *= rng.integers(1, 255, n + 8).astype(np.uint8)  # any non-zero byte counts
+        dev_full = torch.as_tensor(mask_full).cuda()
+        dev = dev_full[offset: offset + n]  # offset != 0 -> unaligned pointer path
+        idx = torch.full((max(n, 1),), -1, dtype=torch.int64, device="cuda")
+        cnt = torch.full((1,), -1, dtype=torch.int64, device="cuda")
+        nbytes = lib.rsk_workspace_bytes(_lib.OP_COMPACT, n, 0)
+        work = torch.empty(max(nbytes, 8), dtype=torch.uint8, device="cuda")
+        rc = lib.rsk_compact_index(_lib.ptr(dev), n, _lib.ptr(idx), _lib.ptr(cnt), _lib.ptr(work), nbytes,
+                                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+        expect = np.nonzero(mask_full[offset: offset + n])[0]
+        assert int(cnt.item()) == expect.size
+        assert np.array_equal(idx.cpu().numpy()[: expect.size], expect)
+
+
+def test_polarized_predicate_bit_exact(rsk):
+    rng = np.random.default_rng(8)
+    n, nf = 5003, 3
+    st = np.zeros((4, nf, n))
+    st[0] = 1.0
+    pick = rng.uniform(size=n) < 0.4
+    st[1:, :, pick] = rng.normal(size=(3, nf, int(pick.sum())))
+    st[1, :, 0], st[2, :, 0], st[3, :, 0] = 1.0, -1.0, 0.0  # sums to zero: "unpolarised" upstream
+    st[1, 1, 1] = 1e-300                                      # polarised at one channel only
+    st[2, 0, 2] = np.nan                                      # NaN != 0 -> polarised
+    sky = rsk.SkyModel(ra=np.zeros(n), dec=np.zeros(n), stokes=st, spectral_type="full", freq_array=np.linspace(1e8, 2e8, nf))
+    expect = S.polarized_indices(st)
+    assert np.array_equal(sky._polarized.cpu().numpy(), expect)
+    assert sky._n_polarized == expect.size
+    assert 0 not in expect and 1 in expect and 2 in expect
+
+
+# ---------------------------------------------------------------------------------------------------
+# Stokes -> coherency, units, at_frequencies
+# ---------------------------------------------------------------------------------------------------
+def test_stokes_to_coherency_bit_exact(rsk, known_answers):
+    ka = known_answers["stokes_coherency"]
+    got = rsk.utils.stokes_to_coherency(np.array(ka["stokes"]))
+    assert got.shape == (2, 2)
+    assert np.array_equal(got, S.stokes_to_coherency(np.array(ka["stokes"])))
+    assert np.allclose(got, 0.5 * np.array([[4.2, 1.2 + 0.15j], [1.2 - 0.15j, 4.8]]))
+    rng = np.random.default_rng(9)
+    st = rng.normal(size=(4, 13, 1001))
+    got = rsk.utils.stokes_to_coherency(torch.as_tensor(st).cuda())
+    assert isinstance(got, torch.Tensor) and got.is_cuda and got.dtype == torch.complex128
+    assert np.array_equal(got.cpu().numpy(), S.stokes_to_coherency(st))
+    with pytest.raises(ValueError, match="First dimension of stokes_vector must be length 4."):
+        rsk.utils.stokes_to_coherency(st[0:2])
+    sky = rsk.SkyModel(ra=np.zeros(1001), dec=np.zeros(1001), stokes=st, spectral_type="full", freq_array=np.linspace(1e8, 2e8, 13))
+    assert sky.calc_frame_coherency(store=False).shape == (2, 2, 13, 1001)
+    sky.calc_frame_coherency()
+    assert np.array_equal(sky.frame_coherency.cpu().numpy(), S.stokes_to_coherency(st))
+
+
+def test_unit_conversion(rsk, known_answers):
+    rng = np.random.default_rng(10)
+    n, nf = 1237, 11
+    st = rng.normal(size=(4, nf, n))
+    fa = np.linspace(100e6, 200e6, nf)
+    sky = rsk.SkyModel(ra=np.zeros(n), dec=np.zeros(n), stokes=st, spectral_type="full", freq_array=fa)
+    assert sky.stokes_unit == "Jy"
+    sky.kelvin_to_jansky()  # already Jy: no-op (skymodel.py:1548-1555)
+    assert np.array_equal(sky.stokes.cpu().numpy(), st)
+    sky.jansky_to_kelvin()
+    assert sky.stokes_unit == "K sr"
+    assert np.array_equal(sky.stokes.cpu().numpy(), S.jansky_to_kelvin(st, "full", freq_array=fa))
+    sky.jansky_to_kelvin()  # already K: no-op
+    sky.kelvin_to_jansky()
+    assert sky.stokes_unit == "Jy"
+    assert np.allclose(sky.stokes.cpu().numpy(), st, rtol=1e-15, atol=0)  # test_skymodel.py:779-857 round trip
+    # spectral_index: factor from the reference frequency per component (skymodel.py:1609-1617)
+    rf = rng.uniform(1e8, 2e8, n)
+    sky = rsk.SkyModel(ra=np.zeros(n), dec=np.zeros(n), stokes=st[:, :1], spectral_type="spectral_index",
+                       reference_frequency=rf, spectral_index=np.full(n, -0.8))
+    sky.jansky_to_kelvin()
+    assert np.array_equal(sky.stokes.cpu().numpy(), S.jansky_to_kelvin(st[:, :1], "spectral_index", reference_frequency=rf))
+    # flat without any frequency: error text of skymodel.py:1625-1628
+    sky = rsk.SkyModel(ra=np.zeros(n), dec=np.zeros(n), stokes=st[:, :1], spectral_type="flat")
+    with pytest.raises(ValueError, match="Either reference_frequency or freq_array must be set to convert to K."):
+        sky.jansky_to_kelvin()
+    # tutorial.rst:1279-1297
+    tu = known_answers["tutorial_unit_conversion"]
+    g = np.zeros((4, 1, 5)); g[0, 0] = tu["gleam_jy"]
+    sky = rsk.SkyModel(ra=np.zeros(5), dec=np.zeros(5), stokes=g, spectral_type="full", freq_array=[tu["gleam_freq_hz"]])
+    sky.jansky_to_kelvin()
+    assert np.allclose(sky.stokes.cpu().numpy()[0, 0], tu["gleam_ksr"], rtol=2e-6)
+    h = np.zeros((4, 1, 5)); h[0, 0] = tu["gsm_k"]
+    sky = rsk.SkyModel(nside=1, hpx_inds=np.arange(5), stokes=h, spectral_type="full", freq_array=[tu["gsm_freq_hz"]],
+                       component_type="healpix", stokes_unit="K")
+    sky.kelvin_to_jansky()
+    assert sky.stokes_unit == "Jy / sr"
+    assert np.allclose(sky.stokes.cpu().numpy()[0, 0], tu["gsm_jy_sr"], rtol=1e-10)
+    assert np.allclose(rsk.utils.jy_to_ksr(fa), S.jy_to_ksr(fa), rtol=1e-15)
+
+
+def make_model(rsk, rng, spectral_type, n, frame="icrs", nf_in=20):
+    lon, lat = random_sky(rng, n)
+    kw = {}
+    if spectral_type in ("flat", "spectral_index"):
+        st = polarized_stokes(rng, n)
+        if spectral_type == "spectral_index":
+            kw["spectral_index"] = np.clip(rng.normal(-0.8, 0.2, n), -2, 1)
+            kw["reference_frequency"] = rng.choice([150e6, 200e6, 185.5e6], n)
+    else:
+        fa = GLEAM_BANDS[:nf_in] if nf_in <= 20 else np.linspace(72e6, 231e6, nf_in)
+        base = polarized_stokes(rng, n)
+        alpha = np.clip(rng.normal(-0.8, 0.2, n), -2, 1)
+        st = base * (fa[None, :, None] / 200e6) ** alpha[None, None, :] * (1 + 0.02 * rng.normal(size=(4, fa.size, n)))
+        kw["freq_array"] = fa
+    unpol = rng.uniform(size=n) < 0.3
+    st[1:, :, unpol] = 0.0
+    sky = rsk.SkyModel(lon=lon, lat=lat, frame=frame, stokes=st, spectral_type=spectral_type, **kw)
+    return sky, lon, lat, st, kw
+
+
+def oracle_eval(st, spectral_type, freqs, kw, kind="cubic"):
+    return S.at_frequencies(st, spectral_type, freqs, freq_array=kw.get("freq_array"),
+                            reference_frequency=kw.get("reference_frequency"),
+                            spectral_index=kw.get("spectral_index"), freq_interp_kind=kind)
+
+
+@pytest.mark.parametrize("spectral_type", ["flat", "spectral_index", "subband", "full"])
+@pytest.mark.parametrize("inplace", [True, False])
+def test_at_frequencies(rsk, spectral_type, inplace):
+    """tests/test_skymodel.py:3542-3583."""
+    rng = np.random.default_rng(11)
+    n = 2003
+    sky, lon, lat, st, kw = make_model(rsk, rng, spectral_type, n)
+    freqs = np.linspace(80e6, 220e6, 301) if spectral_type != "full" else kw["freq_array"][3:11]
+    new = sky.at_frequencies(freqs, inplace=inplace)
+    if inplace:
+        assert new is None
+        new = sky
+    else:
+        assert sky.spectral_type == spectral_type and sky.stokes.shape == st.shape
+    assert new.spectral_type == "full" and new.Nfreqs == freqs.size and new.reference_frequency is None
+    assert np.array_equal(new.freq_array, freqs)
+    ref = oracle_eval(st, spectral_type, freqs, kw)
+    got = new.stokes.cpu().numpy()
+    assert got.shape == ref.shape
+    scale = np.abs(ref[0])[None]
+    if spectral_type in ("flat", "full"):
+        assert np.array_equal(got, ref)
+    else:
+        assert np.max(np.abs(got - ref) / scale) < 1e-12
+    if spectral_type == "full":
+        with pytest.raises(ValueError, match="Some requested frequencies are not present"):
+            new.at_frequencies(np.linspace(80e6, 220e6, 5))
+
+
+@pytest.mark.parametrize("kind", ["linear", "slinear", "quadratic", "cubic", 2])
+def test_at_frequencies_subband_kinds(rsk, kind):
+    rng = np.random.default_rng(12)
+    sky, lon, lat, st, kw = make_model(rsk, rng, "subband", 1501)
+    freqs = np.concatenate((np.linspace(76e6, 227e6, 257), kw["freq_array"]))  # includes every knot and both ends
+    sky.at_frequencies(freqs, freq_interp_kind=kind)
+    ref = oracle_eval(st, "subband", freqs, kw, kind)
+    assert np.max(np.abs(sky.stokes.cpu().numpy() - ref) / np.abs(ref[0])[None]) < 1e-12
+
+
+def test_at_frequencies_errors(rsk):
+    """tests/test_skymodel.py:3586-3608."""
+    rng = np.random.default_rng(13)
+    sky, *_ = make_model(rsk, rng, "subband", 50)
+    with pytest.raises(ValueError, match="A requested frequency is larger than the highest subband frequency."):
+        sky.at_frequencies(sky.freq_array + 10)
+    with pytest.raises(ValueError, match="A requested frequency is smaller than the lowest subband frequency."):
+        sky.at_frequencies(sky.freq_array - 10)
+    sky2, *_ = make_model(rsk, rng, "spectral_index", 50)
+    sky2.spectral_index[0] = float("nan")
+    with pytest.raises(ValueError, match="Some spectral index values are NaNs."):
+        sky2.at_frequencies(sky.freq_array)
+    with pytest.raises(NotImplementedError):
+        sky.at_frequencies(sky.freq_array, freq_interp_kind="nearest")
+
+
+# ---------------------------------------------------------------------------------------------------
+# coherency_calc
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("spectral_type", ["flat", "spectral_index", "subband", "full"])
+@pytest.mark.parametrize("frame", ["icrs", "fk5"])
+def test_coherency_fused_vs_oracle(rsk, site, spectral_type, frame):
+    """coherency_calc(freqs=...) == oracle at_frequencies -> coherency_calc, all four spectral types,
+    mixed polarised / unpolarised components, both with the GPU's own alt/az."""
+    time, loc = site
+    rng = np.random.default_rng(14)
+    n = 6007
+    sky, lon, lat, st, kw = make_model(rsk, rng, spectral_type, n, frame=frame)
+    freqs = np.linspace(80e6, 220e6, 67) if spectral_type != "full" else kw["freq_array"]
+    sky.update_positions(time, loc)
+    got = sky.coherency_calc(freqs=freqs).cpu().numpy()
+    alt_az = sky.alt_az.cpu().numpy()       # identical geometry on both sides isolates the K2 arithmetic
+    above = sky.above_horizon.cpu().numpy()
+    full = oracle_eval(st, spectral_type, freqs, kw)
+    ravg = S.calc_average_rotation_matrix(sky._astrom)
+    ref = S.coherency_calc(full, lon, lat, alt_az, above, ravg, polarized=S.polarized_indices(st), vectorized=True)
+    assert_coherency_close(got, ref, full[0][:, above])
+    # and the unfused route through the object: at_frequencies then coherency_calc()
+    sky.at_frequencies(freqs)
+    got2 = sky.coherency_calc().cpu().numpy()
+    assert_coherency_close(got2, ref, full[0][:, above])
+    # unpolarised components are untouched by the rotation: exactly the frame coherency
+    unpol_above = ~np.isin(np.nonzero(above)[0], S.polarized_indices(st))
+    assert np.array_equal(got2[..., unpol_above], S.stokes_to_coherency(sky.stokes.cpu().numpy())[..., above][..., unpol_above])
+
+
+def test_coherency_loop_oracle_end_to_end(rsk, site):
+    """Against the reference-faithful per-source Python loops, with the oracle's own alt/az (so the
+    whole chain K1 -> compaction -> K2 is compared).  Near-singular geometry (|alt| > 89.99 deg, where
+    azimuth is ill-conditioned) is excluded from the 1e-12 bound."""
+    time, loc = site
+    rng = np.random.default_rng(15)
+    n = 1500
+    sky, lon, lat, st, kw = make_model(rsk, rng, "spectral_index", n)
+    freqs = np.linspace(100e6, 200e6, 9)
+    sky.update_positions(time, loc)
+    got = sky.coherency_calc(freqs=freqs).cpu().numpy()
+    alt_az, _, above = S.update_positions(lon, lat, sky._astrom)
+    assert np.array_equal(above, sky.above_horizon.cpu().numpy())
+    full = oracle_eval(st, "spectral_index", freqs, kw)
+    ref = S.coherency_calc(full, lon, lat, alt_az, above, S.calc_average_rotation_matrix(sky._astrom),
+                           polarized=S.polarized_indices(st))
+    ok = np.abs(alt_az[0][above]) < np.deg2rad(89.99)
+    assert_coherency_close(got[..., ok], ref[..., ok], full[0][:, above][:, ok], tol=1e-12)
+
+
+def test_pol_rotator(rsk, site):
+    """tests/test_skymodel.py:1306-1385."""
+    time, loc = site
+    n = 50
+    ra = np.deg2rad(np.linspace(0, 24, n) * 15) % (2 * np.pi)
+    dec = np.deg2rad(np.linspace(-90, 90, n))
+    for spectral_type in ("flat", "full"):
+        st = np.zeros((4, 1, n)); st[:, 0, :] = np.array([5.5, 0.7, 0.3, 0.0])[:, None]
+        st[:, 0, -1] = [1.0, 0, 0, 0]
+        extra = {}
+        if spectral_type == "full":
+            st = st.repeat(10, axis=1)
+            extra = {"freq_array": np.linspace(100e6, 110e6, 10)}
+        sky = rsk.SkyModel(ra=ra, dec=dec, stokes=st, spectral_type=spectral_type, **extra)
+        assert sky._n_polarized == n - 1
+        sky.update_positions(time, loc)
+        sky.above_horizon = torch.zeros(n, dtype=torch.bool, device="cuda")
+        assert sky.coherency_calc().numel() == 0
+        sky.above_horizon = None
+        with pytest.warns(UserWarning, match="Horizon cutoff undefined"):
+            local = sky.coherency_calc().cpu().numpy()
+        frame = S.stokes_to_coherency(st)
+        assert not np.all(np.isclose(local[..., :-1], frame[..., :-1]))
+        assert np.array_equal(local[..., -1], frame[..., -1])
+        ref = S.coherency_calc(st, ra, dec, sky.alt_az.cpu().numpy(), np.ones(n, bool),
+                               S.calc_average_rotation_matrix(sky._astrom))
+        pole = np.abs(dec) > np.deg2rad(89.9)  # exact poles: basis undefined, ill-conditioned both sides
+        assert_coherency_close(local[..., ~pole], ref[..., ~pole], st[0][:, ~pole])
+    un = np.zeros((4, 1, n)); un[0] = 1.0
+    sky = rsk.SkyModel(ra=ra, dec=dec, stokes=un, spectral_type="flat")
+    assert sky._n_polarized == 0
+
+
+@pytest.mark.parametrize("eop", [(0.0, 0.0), (-0.47, 0.32)])
+def test_golden_instrumental_coherency_gpu(rsk, known_answers, eop):
+    """The reference's golden matrix (tests/test_skymodel.py:1388-1508) end to end through the GPU path."""
+    pv = known_answers["polarized_visibilities"]
+    loc = rsk.EarthLocation.from_dms((-30, 43, 17.5), (21, 25, 41.9), 1073.0)
+    t0 = rsk.Time(2457082.5, 0.0, dut1=eop[0], yp=eop[1] * E.DAS2R)
+    ra, dec = E.altaz_to_icrs(np.pi / 2, 0.0, rsk.astrometry.astrom_context(t0, loc))
+    sky = rsk.SkyModel(name="icrs_zen", ra=ra, dec=dec, stokes=np.array(pv["stokes"], float), spectral_type="flat")
+    out = np.zeros((2, 2, 5), complex)
+    alts, azs = [], []
+    for ti, off in enumerate(pv["time_offsets_hr"]):
+        sky.update_positions(t0 + off / 24.0, loc)
+        alt, az = sky.alt_az.cpu().numpy()[:, 0]
+        alts.append(alt); azs.append(az)
+        out[:, :, ti] = sky.coherency_calc().cpu().numpy()[:, :, 0, 0]
+    jones = S.short_dipole_jones(np.array(azs), np.pi / 2 - np.array(alts))
+    jones = np.flip(np.flip(np.transpose(jones, (1, 0, 2)), axis=1), axis=0)
+    inst = np.einsum("ab...,bc...,dc...->ad...", jones, out, np.conj(jones))
+    expect = np.array(pv["expected_re"]) + 1j * np.array(pv["expected_im"])
+    assert np.allclose(inst, expect)
+
+
+def test_tutorial_local_coherency_gpu(rsk, known_answers):
+    tk = known_answers["tutorial_local_coherency"]
+    loc = rsk.EarthLocation.from_dms((-30, 43, 17.5), (21, 25, 41.9), 1073.0)
+    t0 = rsk.Time(2457082.5, 0.0, dut1=-0.47, yp=0.32 * E.DAS2R)
+    ra, dec = E.altaz_to_icrs(np.deg2rad(80.0), 0.0, rsk.astrometry.astrom_context(t0, loc))
+    sky = rsk.SkyModel(name="offzen_source", ra=ra, dec=dec, stokes=np.array(tk["stokes"]), spectral_type="flat")
+    sky.calc_frame_coherency()
+    assert np.allclose(sky.frame_coherency.cpu().numpy()[:, :, 0, 0], [[0.6, 0], [0, 0.4]])
+    sky.update_positions(t0, loc)
+    c = sky.coherency_calc().cpu().numpy()[:, :, 0, 0]
+    expect = np.array(tk["coherency_re"])
+    assert np.allclose(np.diag(c.real), np.diag(expect), atol=2e-9)
+    assert abs(c[0, 1].real / expect[0, 1] - 1) < 0.01
+
+
+def test_healpix_coherency(rsk, site):
+    """Healpix + polarised + fused power law (BASELINE config 3 in miniature), ring and nested."""
+    time, loc = site
+    nside = 16
+    npix = 12 * nside * nside
+    rng = np.random.default_rng(16)
+    st = polarized_stokes(rng, npix)
+    alpha = np.clip(rng.normal(-2.5, 0.2, npix), -4, 0)
+    rf = np.full(npix, 150e6)
+    freqs = np.linspace(100e6, 200e6, 33)
+    for order in ("ring", "nested"):
+        sky = rsk.SkyModel(nside=nside, hpx_order=order, stokes=st, spectral_type="spectral_index",
+                           reference_frequency=rf, spectral_index=alpha, component_type="healpix", stokes_unit="K")
+        sky.update_positions(time, loc)
+        got = sky.coherency_calc(freqs=freqs).cpu().numpy()
+        lon, lat = hp.healpix_to_lonlat(nside, np.arange(npix), nested=(order == "nested"))
+        alt_az = sky.alt_az.cpu().numpy(); above = sky.above_horizon.cpu().numpy()
+        full = S.at_frequencies(st, "spectral_index", freqs, reference_frequency=rf, spectral_index=alpha)
+        ref = S.coherency_calc(full, lon, lat, alt_az, above, S.calc_average_rotation_matrix(sky._astrom),
+                               polarized=S.polarized_indices(st), vectorized=True)
+        assert_coherency_close(got, ref, full[0][:, above])
+
+
+def test_column_offsets_for_sharded_output(rsk, site):
+    """ld_out / col0: two shards writing disjoint column ranges of one buffer == one unsharded call."""
+    time, loc = site
+    rng = np.random.default_rng(17)
+    n = 4001
+    sky, lon, lat, st, kw = make_model(rsk, rng, "spectral_index", n)
+    freqs = np.linspace(100e6, 200e6, 17)
+    sky.update_positions(time, loc)
+    whole = sky.coherency_calc(freqs=freqs)
+    cut = 1777
+    parts = []
+    for sl in (slice(0, cut), slice(cut, n)):
+        s = rsk.SkyModel(lon=lon[sl], lat=lat[sl], stokes=st[:, :, sl], spectral_type="spectral_index",
+                         reference_frequency=kw["reference_frequency"][sl], spectral_index=kw["spectral_index"][sl])
+        s.update_positions(time, loc)
+        parts.append(s)
+    counts = [int(p.above_horizon.sum().item()) for p in parts]
+    assert sum(counts) == whole.shape[-1]
+    buf = torch.zeros((2, 2, freqs.size, sum(counts)), dtype=torch.complex128, device="cuda")
+    parts[0].coherency_calc(freqs=freqs, out=buf, col0=0)
+    parts[1].coherency_calc(freqs=freqs, out=buf, col0=counts[0])
+    assert torch.equal(buf, whole)
+
+
+# ---------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE configs 2 and 4): size-independent invariants + sampled oracle columns
+# ---------------------------------------------------------------------------------------------------
+def _check_invariants_and_samples(rsk, sky, lon, lat, st, kw, spectral_type, freqs, got, rng, nsample=400):
+    above = sky.above_horizon.cpu().numpy()
+    cols = np.nonzero(above)[0]
+    assert got.shape == (2, 2, freqs.size, cols.size)
+    # invariants on device, all columns: Hermitian, real diagonal, imag parts antisymmetric
+    assert torch.equal(got[0, 1].real, got[1, 0].real) and torch.equal(got[0, 1].imag, -got[1, 0].imag)
+    assert float(got[0, 0].imag.abs().max()) == 0.0 and float(got[1, 1].imag.abs().max()) == 0.0
+    assert bool(torch.isfinite(got.real).all())
+    pick = np.sort(rng.choice(cols.size, nsample, replace=False))
+    src = cols[pick]
+    sub_kw = {k: (v[src] if k in ("reference_frequency", "spectral_index") else v) for k, v in kw.items()}
+    full = oracle_eval(st[:, :, src], spectral_type, freqs, sub_kw)
+    alt_az = sky.alt_az.cpu().numpy()[:, src]
+    ref = S.coherency_calc(full, lon[src], lat[src], alt_az, np.ones(nsample, bool),
+                           S.calc_average_rotation_matrix(sky._astrom),
+                           polarized=S.polarized_indices(st[:, :, src]), vectorized=True)
+    sample = got[..., torch.as_tensor(pick, device="cuda")].cpu().numpy()
+    assert_coherency_close(sample, ref, full[0])
+    # rotation preserves I, V and the polarised intensity: trace = I, |Q'|^2 + |U'|^2 = Q^2 + U^2
+    i_f, q_f, u_f, v_f = full
+    assert np.max(np.abs((sample[0, 0] + sample[1, 1]).real - i_f) / i_f) < 1e-12
+    qp = (sample[0, 0] - sample[1, 1]).real
+    up = 2 * sample[0, 1].real
+    assert np.max(np.abs(np.hypot(qp, up) - np.hypot(q_f, u_f)) / i_f) < 1e-12
+    assert np.max(np.abs(2 * sample[1, 0].imag - v_f) / i_f) < 1e-12
+
+
+def test_config2_full_size_properties(rsk, site):
+    """GLEAM-like 300k point sources, full Stokes, power law, 1024 frequencies, fk5 (BASELINE config 2)."""
+    time, loc = site
+    rng = np.random.default_rng(2)
+    n = 300_000
+    sky, lon, lat, st, kw = make_model(rsk, rng, "spectral_index", n, frame="fk5")
+    freqs = np.linspace(100e6, 200e6, 1024)
+    sky.update_positions(time, loc)
+    got = sky.coherency_calc(freqs=freqs)
+    _check_invariants_and_samples(rsk, sky, lon, lat, st, kw, "spectral_index", freqs, got, rng)
+    # idempotence: a second evaluation is bit-identical
+    assert torch.equal(got, sky.coherency_calc(freqs=freqs))
+
+
+def test_config4_subband_full_size_properties(rsk, site):
+    """1M polarised sources with 20 GLEAM subbands interpolated to 1024 channels, one 125k shard of 8
+    (BASELINE config 4)."""
+    time, loc = site
+    rng = np.random.default_rng(4)
+    n = 125_000
+    sky, lon, lat, st, kw = make_model(rsk, rng, "subband", n)
+    freqs = np.linspace(80e6, 220e6, 1024)
+    sky.update_positions(time, loc)
+    got = sky.coherency_calc(freqs=freqs)
+    _check_invariants_and_samples(rsk, sky, lon, lat, st, kw, "subband", freqs, got, rng)
+
+
+def test_empty_and_tiny_models(rsk, site):
+    time, loc = site
+    st = np.array([1.0, 0.1, 0.0, 0.0])
+    sky = rsk.SkyModel(ra=[1.0], dec=[-0.5], stokes=st, spectral_type="flat")
+    sky.update_positions(time, loc)
+    out = sky.coherency_calc(freqs=np.array([1.5e8]))
+    assert out.shape[:3] == (2, 2, 1) and out.shape[3] in (0, 1)
+    # a model entirely below the horizon returns an empty last axis
+    lat = np.full(10, np.deg2rad(85.0))  # far-north sources never rise at HERA (lat -30.7)
+    sky = rsk.SkyModel(ra=np.linspace(0, 6, 10), dec=lat, stokes=np.tile(st[:, None, None], (1, 1, 10)), spectral_type="flat")
+    sky.update_positions(time, loc)
+    assert not bool(sky.above_horizon.any())
+    assert sky.coherency_calc(freqs=np.linspace(1e8, 2e8, 5)).shape == (2, 2, 5, 0)
