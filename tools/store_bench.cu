@@ -1,0 +1,119 @@
+// store_bench.cu -- microbenchmark of the K2 output write pattern on B200 (tuning aid, not product).
+// out[plane(4)][f(nf)][col(n)] complex128; block = tile of TC columns x chunk of FC frequencies.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o store_bench store_bench.cu
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
+
+template <int OP> __device__ __forceinline__ void st16(double2* p, double a, double b) {
+  if (OP == 0) *p = make_double2(a, b);
+  else if (OP == 1) __stcs(p, make_double2(a, b));
+  else if (OP == 2) __stwt(p, make_double2(a, b));
+  else if (OP == 3) asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+  else if (OP == 4) __stcg(p, make_double2(a, b));
+}
+
+__global__ void k_linear(double2* out, int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) __stcs(out + i, make_double2(1.0, 0.0));
+}
+
+// CPT columns per thread (strided by blockDim so every warp store stays 512 B contiguous)
+template <int OP, int CPT>
+__global__ void __launch_bounds__(256) k_pattern(double2* out, int64_t n, int nf, int fchunk, int nfchunks, int do_exp) {
+  const int64_t tile = blockIdx.x / nfchunks;
+  const int chunk = blockIdx.x - tile * nfchunks;
+  const int f0 = chunk * fchunk;
+  const int nfc = min(fchunk, nf - f0);
+  const int64_t plane = (int64_t)nf * n;
+  int64_t col[CPT];
+  double a[CPT];
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) { col[j] = tile * 256 * CPT + j * 256 + threadIdx.x; a[j] = -0.8 + 1e-6 * (double)(col[j] & 1023); }
+#pragma unroll 4
+  for (int k = 0; k < nfc; ++k) {
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      if (col[j] < n) {
+        double v = do_exp ? exp(a[j] * (0.001 * (double)(f0 + k))) : a[j];
+        double2* d = out + (int64_t)(f0 + k) * n + col[j];
+        st16<OP>(d, v, 0.0);
+        st16<OP>(d + plane, v, -v);
+        st16<OP>(d + 2 * plane, v, v);
+        st16<OP>(d + 3 * plane, v, 0.0);
+      }
+    }
+  }
+}
+
+// plane-major variant: block loops planes outermost (recompute), to see if fewer concurrent streams help
+template <int OP>
+__global__ void __launch_bounds__(256) k_plane_outer(double2* out, int64_t n, int nf, int fchunk, int nfchunks) {
+  const int64_t tile = blockIdx.x / nfchunks;
+  const int chunk = blockIdx.x - tile * nfchunks;
+  const int f0 = chunk * fchunk;
+  const int nfc = min(fchunk, nf - f0);
+  const int64_t plane = (int64_t)nf * n;
+  const int64_t col = tile * 256 + threadIdx.x;
+  if (col >= n) return;
+  const double a = -0.8 + 1e-6 * (double)(col & 1023);
+  for (int p = 0; p < 4; ++p) {
+#pragma unroll 4
+    for (int k = 0; k < nfc; ++k) {
+      double v = exp(a * (0.001 * (double)(f0 + k)));
+      st16<OP>(out + p * plane + (int64_t)(f0 + k) * n + col, v, p == 1 ? -v : (p == 2 ? v : 0.0));
+    }
+  }
+}
+
+template <typename F> float timeit(F f, int reps = 5) {
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  f(); f();
+  CK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int r = 0; r < reps; ++r) {
+    cudaEventRecord(e0); f(); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+    float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+  }
+  return best;
+}
+
+template <int OP, int CPT> void run_pattern(double2* out, int64_t n, int nf, int fchunk, int do_exp, const char* opname) {
+  const int nfchunks = (nf + fchunk - 1) / fchunk;
+  const int64_t tiles = (n + 256 * CPT - 1) / (256 * CPT);
+  const double bytes = 64.0 * nf * n;
+  float ms = timeit([&] { k_pattern<OP, CPT><<<(unsigned)(tiles * nfchunks), 256>>>(out, n, nf, fchunk, nfchunks, do_exp); });
+  printf("pattern op=%-8s cpt=%d fchunk=%4d exp=%d n=%lld : %7.3f ms  %7.1f GB/s\n", opname, CPT, fchunk, do_exp, (long long)n, ms, bytes / ms / 1e6);
+}
+
+int main(int argc, char** argv) {
+  int64_t n = argc > 1 ? atoll(argv[1]) : 150000;
+  int nf = argc > 2 ? atoi(argv[2]) : 1024;
+  const int64_t total = 4ll * nf * n;
+  double2* out; CK(cudaMalloc(&out, total * sizeof(double2)));
+  double2* src; CK(cudaMalloc(&src, total * sizeof(double2) / 2));
+  const double bytes = 16.0 * total;
+  float ms = timeit([&] { CK(cudaMemsetAsync(out, 0, total * sizeof(double2))); });
+  printf("cudaMemset                      : %7.3f ms  %7.1f GB/s\n", ms, bytes / ms / 1e6);
+  ms = timeit([&] { CK(cudaMemcpyAsync(out, src, total * sizeof(double2) / 2, cudaMemcpyDeviceToDevice)); });
+  printf("cudaMemcpy D2D (r+w bytes)      : %7.3f ms  %7.1f GB/s\n", ms, bytes / ms / 1e6);
+  for (int blocks : {148 * 8, 148 * 16, 148 * 32}) {
+    ms = timeit([&] { k_linear<<<blocks, 256>>>(out, total); });
+    printf("linear store grid=%5d          : %7.3f ms  %7.1f GB/s\n", blocks, ms, bytes / ms / 1e6);
+  }
+  for (int fc : {32, 64, 128, 205, 256, 1024}) run_pattern<1, 1>(out, n, nf, fc, 1, "cs");
+  for (int fc : {64, 205, 1024}) run_pattern<1, 1>(out, n, nf, fc, 0, "cs");
+  for (int fc : {64, 205}) { run_pattern<0, 1>(out, n, nf, fc, 1, "default"); run_pattern<2, 1>(out, n, nf, fc, 1, "wt"); run_pattern<3, 1>(out, n, nf, fc, 1, "noalloc"); run_pattern<4, 1>(out, n, nf, fc, 1, "cg"); }
+  for (int fc : {32, 64, 128, 256}) { run_pattern<1, 2>(out, n, nf, fc, 1, "cs"); run_pattern<1, 4>(out, n, nf, fc, 1, "cs"); run_pattern<1, 8>(out, n, nf, fc, 1, "cs"); }
+  for (int fc : {64, 256}) { run_pattern<0, 4>(out, n, nf, fc, 1, "default"); }
+  for (int fc : {64, 256, 1024}) {
+    const int nfchunks = (nf + fc - 1) / fc; const int64_t tiles = (n + 255) / 256;
+    ms = timeit([&] { k_plane_outer<1><<<(unsigned)(tiles * nfchunks), 256>>>(out, n, nf, fc, nfchunks); });
+    printf("plane-outer cs fchunk=%4d        : %7.3f ms  %7.1f GB/s\n", fc, ms, 64.0 * nf * n / ms / 1e6);
+  }
+  return 0;
+}
