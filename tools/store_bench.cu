@@ -82,12 +82,13 @@ template <typename F> float timeit(F f, int reps = 5) {
   return best;
 }
 
-template <int OP, int CPT> void run_pattern(double2* out, int64_t n, int nf, int fchunk, int do_exp, const char* opname) {
+template <int OP, int CPT> void run_pattern(double2* out, int64_t n, int nf, int fchunk, int do_exp, const char* opname, int smem = 0) {
   const int nfchunks = (nf + fchunk - 1) / fchunk;
   const int64_t tiles = (n + 256 * CPT - 1) / (256 * CPT);
   const double bytes = 64.0 * nf * n;
-  float ms = timeit([&] { k_pattern<OP, CPT><<<(unsigned)(tiles * nfchunks), 256>>>(out, n, nf, fchunk, nfchunks, do_exp); });
-  printf("pattern op=%-8s cpt=%d fchunk=%4d exp=%d n=%lld : %7.3f ms  %7.1f GB/s\n", opname, CPT, fchunk, do_exp, (long long)n, ms, bytes / ms / 1e6);
+  if (smem > 0) CK(cudaFuncSetAttribute(k_pattern<OP, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  float ms = timeit([&] { k_pattern<OP, CPT><<<(unsigned)(tiles * nfchunks), 256, smem>>>(out, n, nf, fchunk, nfchunks, do_exp); });
+  printf("pattern op=%-8s cpt=%d fchunk=%4d exp=%d n=%lld smem=%6d : %7.3f ms  %7.1f GB/s\n", opname, CPT, fchunk, do_exp, (long long)n, smem, ms, bytes / ms / 1e6);
 }
 
 int main(int argc, char** argv) {
@@ -104,6 +105,12 @@ int main(int argc, char** argv) {
   for (int blocks : {148 * 8, 148 * 16, 148 * 32}) {
     ms = timeit([&] { k_linear<<<blocks, 256>>>(out, total); });
     printf("linear store grid=%5d          : %7.3f ms  %7.1f GB/s\n", blocks, ms, bytes / ms / 1e6);
+  }
+  if (argc > 3) {  // occupancy sensitivity: dynamic smem limits resident blocks per SM (227 KB / smem)
+    for (int fc : {64, 205}) for (int smem : {0, 36 * 1024, 54 * 1024, 72 * 1024, 110 * 1024})
+      run_pattern<1, 1>(out, n, nf, fc, 1, "cs", smem);
+    for (int64_t nn : {n - 1, n - 3}) for (int fc : {64, 205}) run_pattern<1, 1>(out, nn, nf, fc, 1, "cs");
+    return 0;
   }
   for (int fc : {32, 64, 128, 205, 256, 1024}) run_pattern<1, 1>(out, n, nf, fc, 1, "cs");
   for (int fc : {64, 205, 1024}) run_pattern<1, 1>(out, n, nf, fc, 0, "cs");
