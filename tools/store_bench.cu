@@ -109,7 +109,8 @@ int main(int argc, char** argv) {
   if (argc > 3) {  // occupancy sensitivity: dynamic smem limits resident blocks per SM (227 KB / smem)
     for (int fc : {64, 205}) for (int smem : {0, 36 * 1024, 54 * 1024, 72 * 1024, 110 * 1024})
       run_pattern<1, 1>(out, n, nf, fc, 1, "cs", smem);
-    for (int64_t nn : {n - 1, n - 3}) for (int fc : {64, 205}) run_pattern<1, 1>(out, nn, nf, fc, 1, "cs");
+    for (int64_t nn : {n - 1, n - 2, n - 4, n - 6, n - 8, n - 16}) for (int fc : {64, 205}) run_pattern<1, 1>(out, nn, nf, fc, 1, "cs");
+    for (int64_t nn : {n - 1, n - 2}) for (int fc : {64}) { run_pattern<0, 1>(out, nn, nf, fc, 1, "default"); run_pattern<1, 1>(out, nn, nf, fc, 1, "cs", 110 * 1024); }
     return 0;
   }
   for (int fc : {32, 64, 128, 205, 256, 1024}) run_pattern<1, 1>(out, n, nf, fc, 1, "cs");
