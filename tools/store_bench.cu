@@ -24,9 +24,10 @@ __global__ void k_linear(double2* out, int64_t total) {
 
 // CPT columns per thread (strided by blockDim so every warp store stays 512 B contiguous)
 template <int OP, int CPT>
-__global__ void __launch_bounds__(256) k_pattern(double2* out, int64_t n, int nf, int fchunk, int nfchunks, int do_exp) {
-  const int64_t tile = blockIdx.x / nfchunks;
-  const int chunk = blockIdx.x - tile * nfchunks;
+__global__ void __launch_bounds__(256) k_pattern(double2* out, int64_t n, int nf, int fchunk, int nfchunks, int do_exp, int tile_fast = 0, int ntiles = 1) {
+  int64_t tile = blockIdx.x / nfchunks;
+  int chunk = blockIdx.x - tile * nfchunks;
+  if (tile_fast) { chunk = blockIdx.x / ntiles; tile = blockIdx.x - (int64_t)chunk * ntiles; }
   const int f0 = chunk * fchunk;
   const int nfc = min(fchunk, nf - f0);
   const int64_t plane = (int64_t)nf * n;
@@ -82,13 +83,13 @@ template <typename F> float timeit(F f, int reps = 5) {
   return best;
 }
 
-template <int OP, int CPT> void run_pattern(double2* out, int64_t n, int nf, int fchunk, int do_exp, const char* opname, int smem = 0) {
+template <int OP, int CPT> void run_pattern(double2* out, int64_t n, int nf, int fchunk, int do_exp, const char* opname, int smem = 0, int tile_fast = 0) {
   const int nfchunks = (nf + fchunk - 1) / fchunk;
   const int64_t tiles = (n + 256 * CPT - 1) / (256 * CPT);
   const double bytes = 64.0 * nf * n;
   if (smem > 0) CK(cudaFuncSetAttribute(k_pattern<OP, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  float ms = timeit([&] { k_pattern<OP, CPT><<<(unsigned)(tiles * nfchunks), 256, smem>>>(out, n, nf, fchunk, nfchunks, do_exp); });
-  printf("pattern op=%-8s cpt=%d fchunk=%4d exp=%d n=%lld smem=%6d : %7.3f ms  %7.1f GB/s\n", opname, CPT, fchunk, do_exp, (long long)n, smem, ms, bytes / ms / 1e6);
+  float ms = timeit([&] { k_pattern<OP, CPT><<<(unsigned)(tiles * nfchunks), 256, smem>>>(out, n, nf, fchunk, nfchunks, do_exp, tile_fast, (int)tiles); });
+  printf("pattern op=%-8s cpt=%d fchunk=%4d exp=%d n=%lld smem=%6d tilefast=%d : %7.3f ms  %7.1f GB/s\n", opname, CPT, fchunk, do_exp, (long long)n, smem, tile_fast, ms, bytes / ms / 1e6);
 }
 
 int main(int argc, char** argv) {
@@ -105,6 +106,12 @@ int main(int argc, char** argv) {
   for (int blocks : {148 * 8, 148 * 16, 148 * 32}) {
     ms = timeit([&] { k_linear<<<blocks, 256>>>(out, total); });
     printf("linear store grid=%5d          : %7.3f ms  %7.1f GB/s\n", blocks, ms, bytes / ms / 1e6);
+  }
+  if (argc > 3 && argv[3][0] == 'g') {  // grid order x chunk x occupancy sweep on a 256B-aligned width
+    for (int tf : {0, 1}) for (int fc : {8, 16, 32, 64, 128, 256}) for (int smem : {0, 56 * 1024, 112 * 1024})
+      run_pattern<1, 1>(out, n, nf, fc, 1, "cs", smem, tf);
+    for (int tf : {0, 1}) for (int fc : {16, 64}) { run_pattern<1, 2>(out, n, nf, fc, 1, "cs", 0, tf); run_pattern<1, 4>(out, n, nf, fc, 1, "cs", 0, tf); }
+    return 0;
   }
   if (argc > 3) {  // occupancy sensitivity: dynamic smem limits resident blocks per SM (227 KB / smem)
     for (int fc : {64, 205}) for (int smem : {0, 36 * 1024, 54 * 1024, 72 * 1024, 110 * 1024})
