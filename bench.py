@@ -306,41 +306,60 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing -------------------------------------------------------------------
-    kernel_events = []
-    evals = 0
-    k2_bytes = 0
+    # "async" (headline): the step is queued without any device->host read -- the output goes to a
+    # preallocated buffer wide enough for every component and the above-horizon count stays on the
+    # device (coherency_calc(..., out=buf, sync=False)); counts are read once after the timed region.
+    # "sync": the reference-shaped call, which returns an exactly sized array and therefore reads the
+    # count back every step (one host sync per step).
+    ld_full = -(-n // 16) * 16
+    out_buf = torch.empty((2, 2, nf, ld_full), dtype=torch.complex128, device=dev)
 
-    def step(k, record):
-        nonlocal evals, k2_bytes
-        sky.update_positions(Time(*step_time(k)), loc)
-        sky._timing_events = kernel_events if record else None
-        out = sky.coherency_calc(freqs=freqs)
-        if record:
-            evals += out.shape[2] * out.shape[3]
-            k2_bytes += k2_algorithmic_bytes(cat, out.shape[3])
-        return out
+    def run_steps(mode, first, nsteps, events):
+        counts = []
+        sky._timing_events = events
+        for k in range(first, first + nsteps):
+            sky.update_positions(Time(*step_time(k)), loc)
+            if mode == "async":
+                _, cnt = sky.coherency_calc(freqs=freqs, out=out_buf, sync=False)
+                counts.append(cnt)
+            else:
+                o = sky.coherency_calc(freqs=freqs)
+                counts.append(o.shape[3])
+        sky._timing_events = None
+        return counts
 
-    for k in range(args.warmup):
-        step(k, False)
-    barrier()
-    sampler = ClockSampler(local_rank if world > 1 else 0)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with sampler:
+    def timed(mode):
+        run_steps(mode, 0, args.warmup, None)
+        barrier()
+        events = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for k in range(args.steps):
-            step(args.warmup + k, True)
+        counts = run_steps(mode, args.warmup, args.steps, events)
         e1.record(stream)
         barrier()
-    ms_total = e0.elapsed_time(e1)
-    k2_ms = sum(a.elapsed_time(b) for a, b in kernel_events) / max(1, len(kernel_events))
-    sky._timing_events = None
+        if mode == "async":
+            counts = [int(c) for c in torch.stack(counts).flatten().cpu()]
+        ms = e0.elapsed_time(e1)
+        k2 = sum(a.elapsed_time(b) for a, b in events) / max(1, len(events))
+        return ms, counts, k2
+
+    sampler = ClockSampler(local_rank if world > 1 else 0)
+    with sampler:
+        ms_total, counts, k2_ms = timed("async")
+    evals = sum(counts) * nf
+    k2_bytes = sum(k2_algorithmic_bytes(cat, c) for c in counts)
+    n_launch = len(counts)
+    ms_sync, counts_sync, k2_ms_sync = timed("sync")
+    evals_sync = sum(counts_sync) * nf
+    del out_buf
+    torch.cuda.empty_cache()
 
     # ---- end to end through the public API with host buffers ----------------------------------------
     e2e_steps = max(2, min(args.steps, args.e2e_steps))
     host_in = {k: torch.as_tensor(np.ascontiguousarray(v)).pin_memory() for k, v in model_kwargs(cat).items()
                if isinstance(v, np.ndarray) and k != "freq_array"}
     h2d_bytes = sum(t.numel() * t.element_size() for t in host_in.values()) + freqs.nbytes
-    n_above_max = int(min(n, 1.15 * (evals / max(1, args.steps) / nf) + 1024))
+    n_above_max = int(min(n, 1.15 * max(counts) + 1024))
     host_out = torch.empty(4 * nf * n_above_max, dtype=torch.complex128).pin_memory()
     e2e_evals = 0
     d2h_bytes = 0
@@ -366,13 +385,13 @@ def run_gpu(args):
     e2e_s = time.perf_counter() - t0
 
     # ---- reduce over ranks ---------------------------------------------------------------------------
-    stats = torch.tensor([ms_total, e2e_s, k2_ms], dtype=torch.float64, device=dev)
-    sums = torch.tensor([evals, e2e_evals, k2_bytes], dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms_total, e2e_s, k2_ms, ms_sync], dtype=torch.float64, device=dev)
+    sums = torch.tensor([evals, e2e_evals, k2_bytes, evals_sync], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms_total, e2e_s, k2_ms_max = (float(v) for v in stats.cpu())
-    evals_all, e2e_evals_all, _ = (float(v) for v in sums.cpu())
+    ms_total, e2e_s, k2_ms_max, ms_sync = (float(v) for v in stats.cpu())
+    evals_all, e2e_evals_all, _, evals_sync_all = (float(v) for v in sums.cpu())
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -380,7 +399,7 @@ def run_gpu(args):
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "of measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "of fallback (B200_PROFILING.md)"
-        achieved = (k2_bytes / max(1, len(kernel_events))) / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
+        achieved = (k2_bytes / max(1, n_launch)) / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "k_eval_traffic.json")
         if os.path.exists(tpath):
@@ -391,14 +410,16 @@ def run_gpu(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": f"{args.workload}: {desc}", "components_per_gpu": n, "nfreqs": nf,
-                "spectral_type": stype, "frame": frame, "site": "HERA", "step": "update_positions + coherency_calc(freqs) at a new time",
+                "spectral_type": stype, "frame": frame, "site": "HERA", "step": "update_positions + coherency_calc(freqs, out=buf, sync=False) at a new time",
                 "sharding": "components, one catalogue per rank, no data-path collective",
                 "l2": f"output per step {evals / args.steps * 64 / 1e9:.2f} GB >> 126 MB L2, no flush needed",
             },
             "roofline": {"bound": "hbm", "kernel": "k_eval<%s, coherency>" % stype, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": k2_ms, "kernel_share_of_step": k2_ms / (ms_total / args.steps),
-                         "algorithmic_bytes_per_launch": k2_bytes / max(1, len(kernel_events))},
+                         "algorithmic_bytes_per_launch": k2_bytes / max(1, n_launch)},
+            "sync_api": {"value": evals_sync_all / (ms_sync * 1e-3), "unit": UNIT, "ms_per_step": ms_sync / args.steps,
+                         "what": "coherency_calc(freqs) returning an exactly sized array: one host read of the count per step"},
             "e2e": {"value": e2e_evals_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes / e2e_steps, "steps": e2e_steps,
                     "ms_per_step": e2e_s / e2e_steps * 1e3},

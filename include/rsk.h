@@ -181,10 +181,16 @@ int rsk_polarized_mask(const double* stokes /* [4][nf_in][n] */, int64_t nf_in, 
  * sct.spherical_basis_vector_rotation_matrix :140-186).  One thread per output column.
  * Column k (0 <= k < ncols) is component idx[k] (idx NULL = identity); its 2x2xnf block is written to
  * out[(a*2+b)*nf*ld_out + f*ld_out + col0 + k] as (re, im).  ld_out/col0 let several shards write
- * disjoint column ranges of one gathered array.  alt_az is the [2][n] output of rsk_positions. */
+ * disjoint column ranges of one gathered array, and let the caller pad rows: HBM write throughput on
+ * B200 is best when ld_out is a multiple of 16 (rows start on 256-byte boundaries).
+ * ncols_dev (optional): the live column count in device memory, e.g. the n_above written by
+ * rsk_compact_index; columns >= min(ncols, *ncols_dev) are not written.  With it the whole time step
+ * (positions -> compaction -> coherency) can be queued without a device->host read of the count;
+ * ncols is then only the upper bound that sizes the grid.  alt_az is the [2][n] output of rsk_positions. */
 int rsk_coherency(const RskSpectrum* spec, const RskCoords* coords, const double* alt_az /* [2][n] */,
                   const double* ravg /* HOST [9] */, const int64_t* idx /* [ncols] or NULL */,
-                  int64_t ncols, const double* freqs /* [nf] Hz */, int64_t nf,
+                  int64_t ncols, const int64_t* ncols_dev /* device [1] or NULL */,
+                  const double* freqs /* [nf] Hz */, int64_t nf,
                   double* out /* complex [2][2][nf][ld_out] */, int64_t ld_out, int64_t col0,
                   void* stream);
 

@@ -87,8 +87,8 @@ _SIGNATURES = {
     "rsk_coherency": (
         ctypes.c_int,
         [ctypes.POINTER(RskSpectrum), ctypes.POINTER(RskCoords), ctypes.c_void_p, c_double_p,
-         ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
-         ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p],
+         ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+         ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p],
     ),
     "rsk_at_frequencies": (
         ctypes.c_int,

@@ -8,6 +8,7 @@
 // re-read its few hundred input bytes from L2 instead of HBM.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/rsk.h"
 #include "rsk_device.cuh"
@@ -16,7 +17,8 @@ namespace {
 
 constexpr int kThreads = 256;       // threads per block for the component-parallel kernels
 constexpr int kMaxFChunk = 256;     // frequencies staged in shared memory per block
-constexpr int kTargetBlocks = 148 * 16;  // B200: 148 SMs; aim for >= 16 blocks per SM in the grid
+constexpr int kDefaultFChunk = 32;  // frequencies per block
+constexpr int kDefaultOccSmem = 72 * 1024;  // dynamic smem request that caps residency at 3 blocks / SM
 constexpr int kCompactItems = 8;    // mask bytes per thread in the compaction kernels
 constexpr int kCompactTile = kThreads * kCompactItems;  // 2048, see rsk_workspace_bytes
 constexpr int kSweepTimes = 16;     // time steps per block in the sweep kernel
@@ -241,6 +243,9 @@ struct EvalParams {
   // columns
   const int64_t* idx;
   int64_t ncols;
+  const int64_t* ncols_dev;  // optional: the live column count in device memory (<= ncols)
+  int64_t ntiles;
+  int tile_fast;
   // frequency axis
   const double* freqs;
   int nf, fchunk, nfchunks;
@@ -288,9 +293,21 @@ template <int MODE, bool COH>
 __global__ void __launch_bounds__(kThreads) k_eval(const __grid_constant__ EvalParams p) {
   __shared__ double s_fa[kMaxFChunk];  // SPECTRAL_INDEX: ln(f / pivot); SUBBAND: local coordinate u
   __shared__ int s_iv[kMaxFChunk];     // SUBBAND: break interval; FULL: stored channel
-  // frequency chunk fastest so that the blocks sharing a component tile are scheduled together
-  const int64_t tile = blockIdx.x / p.nfchunks;
-  const int chunk = (int)(blockIdx.x - tile * p.nfchunks);
+  // Block -> (component tile, frequency chunk).  tile_fast: consecutive blocks are adjacent column
+  // tiles of the same frequency chunk, so the resident blocks stream whole output rows (best DRAM page
+  // locality for the stores); otherwise the chunk index runs fastest and the blocks sharing a tile run
+  // back to back (inputs re-read from L2).
+  int64_t tile;
+  int chunk;
+  if (p.tile_fast) {
+    chunk = (int)(blockIdx.x / p.ntiles);
+    tile = blockIdx.x - (int64_t)chunk * p.ntiles;
+  } else {
+    tile = blockIdx.x / p.nfchunks;
+    chunk = (int)(blockIdx.x - tile * p.nfchunks);
+  }
+  const int64_t ncols = p.ncols_dev ? min(p.ncols, __ldg(p.ncols_dev)) : p.ncols;
+  if (tile * kThreads >= ncols) return;  // whole block past the live columns (uniform)
   const int f0 = chunk * p.fchunk;
   const int nfc = min(p.fchunk, p.nf - f0);
   double pivot = 1.0;
@@ -315,7 +332,7 @@ __global__ void __launch_bounds__(kThreads) k_eval(const __grid_constant__ EvalP
   if (MODE != RSK_FLAT) __syncthreads();
 
   const int64_t col = tile * kThreads + threadIdx.x;
-  if (col >= p.ncols) return;
+  if (col >= ncols) return;
   const int64_t src = p.idx ? __ldg(p.idx + col) : col;
 
   // per-component rotation coefficients (identity for unpolarised components, skymodel.py:2687-2688)
@@ -418,6 +435,12 @@ __global__ void __launch_bounds__(kThreads) k_convert_units(double* __restrict__
 // ---------------------------------------------------------------------------------------------------
 // host-side launch helpers
 // ---------------------------------------------------------------------------------------------------
+// Launch-shape overrides for tuning runs (read per call; no state is kept).
+inline int tuning_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
 inline int launch_status() {
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? RSK_OK : (int)e;
@@ -470,36 +493,48 @@ int fill_eval_params(const RskSpectrum* spec, const double* freqs, int64_t nf, i
   p->freqs = freqs;
   p->nf = (int)nf;
   p->ncols = ncols;
-  // frequency chunking: enough blocks to fill the machine, chunks no longer than the smem tables
+  // Frequency chunking (measured on B200 with tools/store_bench.cu): short chunks and few
+  // resident blocks per SM give the best HBM write locality; rows are streamed tile-fast.
   const int64_t tiles = (ncols + kThreads - 1) / kThreads;
-  int64_t nch = tiles > 0 ? (kTargetBlocks + tiles - 1) / tiles : 1;
-  const int64_t min_ch = (nf + kMaxFChunk - 1) / kMaxFChunk;
-  const int64_t max_ch = (nf + 31) / 32;
-  if (nch > max_ch) nch = max_ch;
-  if (nch < min_ch) nch = min_ch;
-  if (nch < 1) nch = 1;
-  p->fchunk = (int)((nf + nch - 1) / nch);
-  if (p->fchunk < 1) p->fchunk = 1;
-  p->nfchunks = (int)((nf + p->fchunk - 1) / p->fchunk);
+  int fchunk = tuning_int("RSK_K2_FCHUNK", kDefaultFChunk);
+  if (fchunk < 1) fchunk = 1;
+  if (fchunk > kMaxFChunk) fchunk = kMaxFChunk;
+  if (fchunk > nf) fchunk = (int)(nf > 0 ? nf : 1);
+  p->fchunk = fchunk;
+  p->nfchunks = (int)((nf + fchunk - 1) / fchunk);
   if (p->nfchunks < 1) p->nfchunks = 1;
+  p->ntiles = tiles > 0 ? tiles : 1;
+  p->tile_fast = tuning_int("RSK_K2_TILEFAST", 1);
   return RSK_OK;
+}
+
+template <int MODE, bool COH>
+int launch_one(const EvalParams& p, dim3 grid, int smem, cudaStream_t st) {
+  if (smem > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(k_eval<MODE, COH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  k_eval<MODE, COH><<<grid, kThreads, smem, st>>>(p);
+  return launch_status();
 }
 
 template <bool COH>
 int launch_eval(const EvalParams& p, int mode, cudaStream_t st) {
   if (p.ncols == 0 || p.nf == 0) return RSK_OK;
-  const int64_t tiles = (p.ncols + kThreads - 1) / kThreads;
-  const int64_t nblocks = tiles * p.nfchunks;
+  const int64_t nblocks = p.ntiles * p.nfchunks;
   if (nblocks > 0x7fffffffll) return RSK_ERR_SIZE;
-  const dim3 grid((unsigned)nblocks), block(kThreads);
+  const dim3 grid((unsigned)nblocks);
+  // The kernels use no dynamic shared memory; requesting some only caps how many blocks share an SM.
+  int smem = tuning_int("RSK_K2_SMEM", kDefaultOccSmem);
+  if (smem < 0) smem = 0;
+  if (smem > 200 * 1024) smem = 200 * 1024;
   switch (mode) {
-    case RSK_FLAT: k_eval<RSK_FLAT, COH><<<grid, block, 0, st>>>(p); break;
-    case RSK_SPECTRAL_INDEX: k_eval<RSK_SPECTRAL_INDEX, COH><<<grid, block, 0, st>>>(p); break;
-    case RSK_SUBBAND: k_eval<RSK_SUBBAND, COH><<<grid, block, 0, st>>>(p); break;
-    case RSK_FULL: k_eval<RSK_FULL, COH><<<grid, block, 0, st>>>(p); break;
+    case RSK_FLAT: return launch_one<RSK_FLAT, COH>(p, grid, smem, st);
+    case RSK_SPECTRAL_INDEX: return launch_one<RSK_SPECTRAL_INDEX, COH>(p, grid, smem, st);
+    case RSK_SUBBAND: return launch_one<RSK_SUBBAND, COH>(p, grid, smem, st);
+    case RSK_FULL: return launch_one<RSK_FULL, COH>(p, grid, smem, st);
     default: return RSK_ERR_MODE;
   }
-  return launch_status();
 }
 
 }  // namespace
@@ -583,8 +618,8 @@ int rsk_polarized_mask(const double* stokes, int64_t nf_in, int64_t n, uint8_t* 
 }
 
 int rsk_coherency(const RskSpectrum* spec, const RskCoords* coords, const double* alt_az, const double* ravg,
-                  const int64_t* idx, int64_t ncols, const double* freqs, int64_t nf, double* out, int64_t ld_out,
-                  int64_t col0, void* stream) {
+                  const int64_t* idx, int64_t ncols, const int64_t* ncols_dev, const double* freqs, int64_t nf,
+                  double* out, int64_t ld_out, int64_t col0, void* stream) {
   EvalParams p = {};
   int rc = fill_eval_params(spec, freqs, nf, ncols, &p);
   if (rc != RSK_OK) return rc;
@@ -599,6 +634,7 @@ int rsk_coherency(const RskSpectrum* spec, const RskCoords* coords, const double
   }
   p.alt_az = alt_az;
   p.idx = idx;
+  p.ncols_dev = ncols_dev;
   p.out = out;
   p.ld_out = ld_out;
   p.col0 = col0;
@@ -627,7 +663,7 @@ int rsk_stokes_to_coherency(const double* stokes, int64_t nf, int64_t n, double*
   if (nf < 0 || n < 0) return RSK_ERR_SIZE;
   if (nf == 0 || n == 0) return RSK_OK;
   RskCoords none = {};
-  return rsk_coherency(&spec, &none, nullptr, nullptr, nullptr, n, nullptr, nf, out, n, 0, stream);
+  return rsk_coherency(&spec, &none, nullptr, nullptr, nullptr, n, nullptr, nullptr, nf, out, n, 0, stream);
 }
 
 int rsk_convert_units(double* stokes, int64_t nf, int64_t n, const double* freq_per_chan, const double* freq_per_comp,

@@ -408,24 +408,28 @@ class SkyModel:
             raise ValueError("update_positions must be called before the rotation can be computed")
         return astrometry.average_rotation_matrix(self._astrom)
 
-    def compact_above_horizon(self):
-        """(idx, n_above): CUDA int64 indices of above-horizon components in catalogue order.
-
-        This is the boolean fancy index of skymodel.py:2685 made explicit; the count comes back to
-        the host because the output array of ``coherency_calc`` is sized by it."""
+    def _compact_async(self):
+        """Queue the horizon compaction; returns (idx, count) CUDA tensors without synchronising."""
         n = self.Ncomponents
         idx = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
-        cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
+        cnt = torch.empty(1, dtype=torch.int64, device=self.device)
         nbytes = _lib.load().rsk_workspace_bytes(_lib.OP_COMPACT, n, 0)
         work = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=self.device)
         mask = self.above_horizon.view(torch.uint8)
         self._call("rsk_compact_index", _lib.ptr(mask), n, _lib.ptr(idx), _lib.ptr(cnt), _lib.ptr(work),
                    ctypes.c_size_t(nbytes))
-        n_above = int(cnt.item())
-        return idx, n_above
+        return idx, cnt
+
+    def compact_above_horizon(self):
+        """(idx, n_above): CUDA int64 indices of above-horizon components in catalogue order.
+
+        This is the boolean fancy index of skymodel.py:2685 made explicit; the count comes back to
+        the host because the output array of ``coherency_calc`` is sized by it."""
+        idx, cnt = self._compact_async()
+        return idx, int(cnt.item())
 
     def coherency_calc(self, store_frame_coherency=True, freqs=None, freq_interp_kind="cubic", out=None,
-                       ld_out=None, col0=0):
+                       ld_out=None, col0=0, pad=True, sync=True):
         """Calculate the local coherency in the alt/az basis (skymodel.py:2648-2712).
 
         :meth:`update_positions` must be run prior to this method.
@@ -439,33 +443,48 @@ class SkyModel:
             Evaluate the spectral model at these frequencies inside the same kernel, i.e. the result of
             ``at_frequencies(freqs)`` followed by ``coherency_calc()`` upstream, without materialising
             the (4, Nfreqs, Ncomponents) Stokes cube.  Default: the stored Stokes as they are.
-        out, ld_out, col0 : optional  (extension, multi-GPU assembly)
+        out, ld_out, col0 : optional  (extension, multi-GPU assembly / buffer reuse)
             Write into columns [col0, col0 + N_above) of a preallocated complex128 buffer whose last
             axis has length ``ld_out``.
+        pad : bool  (extension)
+            When the output is allocated here, give its rows a stride that is a multiple of 16 elements
+            (256 bytes) -- B200 HBM write throughput is ~25 % higher for 256-byte aligned rows -- and
+            return the (2, 2, Nfreqs, N_above) view of it.  ``pad=False`` returns a C-contiguous tensor.
+        sync : bool  (extension)
+            ``sync=False`` queues the whole computation without reading the above-horizon count back:
+            returns ``(buffer, count)`` where ``buffer`` has room for every component
+            (2, 2, Nfreqs, >= Ncomponents) and ``count`` is a CUDA int64 tensor; columns
+            ``[col0, col0 + count)`` are valid.  Nothing in the call then waits for the GPU.
 
         Returns
         -------
         torch.Tensor, complex128, shape (2, 2, Nfreqs, N_above) -- component axis fastest, only
         components above the horizon, in catalogue order.
         """
-        plan = self._plan_coherency(freqs, freq_interp_kind)
-        nf, n_above = plan["nf"], plan["n_above"]
+        plan = self._plan_coherency(freqs, freq_interp_kind, need_count=sync)
+        nf, ncols = plan["nf"], plan["n_above"]
         if out is None:
-            out = torch.empty((2, 2, nf, n_above), dtype=torch.complex128, device=self.device)
-            ld_out, col0 = n_above, 0
+            ld_out = -(-ncols // 16) * 16 if pad else ncols
+            out = torch.empty((2, 2, nf, max(ld_out, 0)), dtype=torch.complex128, device=self.device)
+            col0 = 0
         elif ld_out is None:
             ld_out = int(out.shape[-1])
         self._launch_coherency(plan, 0, nf, out, ld_out, col0)
-        return out
+        if not sync:
+            return out, plan["count"]
+        if out.shape[-1] == ncols and col0 == 0:
+            return out
+        return out[..., col0:col0 + ncols]
 
-    def _plan_coherency(self, freqs, freq_interp_kind):
+    def _plan_coherency(self, freqs, freq_interp_kind, need_count=True):
         """Everything coherency_calc needs before the launch: horizon compaction, spectral description,
-        R_avg.  One device->host read (the above-horizon count)."""
+        R_avg.  With ``need_count`` one device->host read (the above-horizon count) is made, after all
+        other host-side preparation so the GPU is idle for as short a time as possible."""
         if self.above_horizon is None:
             warnings.warn("Horizon cutoff undefined. Assuming all source components are above the horizon.")
-            idx, n_above = None, self.Ncomponents
+            idx, count = None, None
         else:
-            idx, n_above = self.compact_above_horizon()
+            idx, count = self._compact_async()
         if self.telescope_location is not None:
             self._check_tel_location(self.telescope_location)
         keep = []
@@ -488,9 +507,16 @@ class SkyModel:
                 raise ValueError("update_positions must be called before coherency_calc for polarized sources")
             ravg = _lib.host_array(self._calc_average_rotation_matrix().ravel())
             altaz = self.alt_az
+        coords = self._coords_struct()
+        if count is None:
+            n_above, count_dev = self.Ncomponents, None
+        elif need_count:
+            n_above, count_dev = int(count.item()), None
+        else:
+            n_above, count_dev = self.Ncomponents, count
         self._last_n_above = n_above
         return dict(spec=spec, keep=keep, mode=mode, nf=nf, fdev=fdev, idx=idx, n_above=n_above, ravg=ravg,
-                    altaz=altaz, coords=self._coords_struct())
+                    altaz=altaz, coords=coords, count=count, count_dev=count_dev)
 
     def _launch_coherency(self, plan, f0, f1, out, ld_out, col0):
         """Launch K2 for request channels [f0, f1) into ``out`` (complex [2][2][f1-f0][ld_out])."""
@@ -511,8 +537,8 @@ class SkyModel:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(torch.cuda.current_stream(self.device))
         self._call("rsk_coherency", ctypes.byref(spec), ctypes.byref(plan["coords"]), _lib.ptr(plan["altaz"]),
-                   plan["ravg"], None if plan["idx"] is None else _lib.ptr(plan["idx"]), plan["n_above"], fptr, nf,
-                   _lib.ptr(out), ld_out, col0)
+                   plan["ravg"], None if plan["idx"] is None else _lib.ptr(plan["idx"]), plan["n_above"],
+                   _lib.ptr(plan["count_dev"]), fptr, nf, _lib.ptr(out), ld_out, col0)
         if events is not None:
             ev1.record(torch.cuda.current_stream(self.device))
             events.append((ev0, ev1))
@@ -570,19 +596,32 @@ class SkyModel:
     def _check_request(self, fhost, freq_interp_kind):
         """Argument checks of at_frequencies that raise before any GPU work (skymodel.py:2156-2192)."""
         if self.spectral_type == "spectral_index":
-            if bool(torch.isnan(self.spectral_index).any().item()):
+            if self._has_nan("spectral_index"):
                 raise ValueError("Some spectral index values are NaNs.")
         elif self.spectral_type == "subband":
             if np.max(fhost) > np.max(self.freq_array):
                 raise ValueError("A requested frequency is larger than the highest subband frequency.")
             if np.min(fhost) < np.min(self.freq_array):
                 raise ValueError("A requested frequency is smaller than the lowest subband frequency.")
-            if bool(torch.isnan(self.stokes).any().item()):
+            if self._has_nan("stokes"):
                 raise NotImplementedError(
                     "Subband Stokes with NaNs (nan_handling) are not supported on the GPU path yet."
                 )
             spectral.interp_degree(freq_interp_kind)
         return fhost
+
+    def _has_nan(self, attr):
+        """isnan(...).any() of a device array, cached until the tensor is modified in place or replaced
+        (the reference re-scans on every call, skymodel.py:2157, :2196; here that would cost a
+        reduction kernel and a host sync per time step)."""
+        t = getattr(self, attr)
+        key = (t.data_ptr(), t._version, tuple(t.shape))
+        cache = self.__dict__.setdefault("_nan_cache", {})
+        hit = cache.get(attr)
+        if hit is None or hit[0] != key:
+            hit = (key, bool(torch.isnan(t).any().item()))
+            cache[attr] = hit
+        return hit[1]
 
     def _full_freq_map(self, fhost, atol=None):
         """skymodel.py:2165-2181: stored channels matching the request within ``atol`` (1 Hz)."""

@@ -663,3 +663,26 @@ def test_empty_and_tiny_models(rsk, site):
     sky.update_positions(time, loc)
     assert not bool(sky.above_horizon.any())
     assert sky.coherency_calc(freqs=np.linspace(1e8, 2e8, 5)).shape == (2, 2, 5, 0)
+
+
+def test_padded_and_async_outputs(rsk, site):
+    """pad=True (256-byte aligned rows), pad=False (C-contiguous) and sync=False (count stays on the
+    device) all produce the same columns."""
+    time, loc = site
+    rng = np.random.default_rng(18)
+    n = 5003
+    sky, lon, lat, st, kw = make_model(rsk, rng, "spectral_index", n)
+    freqs = np.linspace(100e6, 200e6, 37)
+    sky.update_positions(time, loc)
+    padded = sky.coherency_calc(freqs=freqs)
+    exact = sky.coherency_calc(freqs=freqs, pad=False)
+    n_above = int(sky.above_horizon.sum().item())
+    assert padded.shape == exact.shape == (2, 2, 37, n_above)
+    assert exact.is_contiguous() and padded.stride(2) % 16 == 0
+    assert torch.equal(padded, exact)
+    ld = -(-n // 16) * 16
+    buf = torch.full((2, 2, 37, ld), float("nan"), dtype=torch.complex128, device="cuda")
+    out, count = sky.coherency_calc(freqs=freqs, out=buf, sync=False)
+    assert out.data_ptr() == buf.data_ptr() and count.is_cuda and int(count.item()) == n_above
+    assert torch.equal(buf[..., :n_above], exact)
+    assert bool(torch.isnan(buf[..., n_above:].real).all())  # nothing written past the live columns

@@ -57,15 +57,15 @@ def test_argument_errors_without_gpu(librsk):
     spec.stokes = 8
     spec.nf_in = 1
     spec.n = 4
-    assert librsk.rsk_coherency(ctypes.byref(spec), ctypes.byref(coords), None, None, None, 4, None, 1, None, 4, 0, None) == -3
+    assert librsk.rsk_coherency(ctypes.byref(spec), ctypes.byref(coords), None, None, None, 4, None, None, 1, None, 4, 0, None) == -3
     spec.mode = _lib.FLAT
-    assert librsk.rsk_coherency(ctypes.byref(spec), ctypes.byref(coords), None, None, None, 4, None, 1, ctypes.c_void_p(8), 2, 0, None) == -4
+    assert librsk.rsk_coherency(ctypes.byref(spec), ctypes.byref(coords), None, None, None, 4, None, None, 1, ctypes.c_void_p(8), 2, 0, None) == -4
     spec.mode = _lib.SUBBAND
     spec.degree = 5
     spec.breaks = 8
     spec.ppoly = 8
     spec.nb = 3
-    assert librsk.rsk_coherency(ctypes.byref(spec), ctypes.byref(coords), None, None, None, 4, ctypes.c_void_p(8), 1, ctypes.c_void_p(8), 4, 0, None) == -6
+    assert librsk.rsk_coherency(ctypes.byref(spec), ctypes.byref(coords), None, None, None, 4, None, ctypes.c_void_p(8), 1, ctypes.c_void_p(8), 4, 0, None) == -6
     assert librsk.rsk_compact_index(ctypes.c_void_p(8), 100, ctypes.c_void_p(8), ctypes.c_void_p(8), None, 0, None) == -5
     assert librsk.rsk_workspace_bytes(_lib.OP_COMPACT, 5000, 0) == (3 + 1) * 8
     # zero-sized problems are accepted without touching the device
