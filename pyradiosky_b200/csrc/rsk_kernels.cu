@@ -5,7 +5,8 @@
 // one thread per component, 128-bit streaming stores for the complex128 output, the frequency axis
 // (log-frequencies, spline interval + local coordinate, or channel map) staged in shared memory once
 // per block, and grids linearised so that blocks that share a component tile run back to back and
-// re-read its few hundred input bytes from L2 instead of HBM.
+// re-read its few hundred input bytes from L2 instead of HBM.  Output rows should start on 256-byte
+// boundaries (ld_out % 16 == 0): measured +25-30 % HBM write throughput on B200.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -17,8 +18,12 @@ namespace {
 
 constexpr int kThreads = 256;       // threads per block for the component-parallel kernels
 constexpr int kMaxFChunk = 256;     // frequencies staged in shared memory per block
-constexpr int kDefaultFChunk = 32;  // frequencies per block
-constexpr int kDefaultOccSmem = 72 * 1024;  // dynamic smem request that caps residency at 3 blocks / SM
+// K2 launch shape, from sweeps of the real kernel on B200 (profiles/r01_k2_tuning.md): 64 frequencies
+// per block, frequency chunk fastest in the grid, no residency cap.  RSK_K2_FCHUNK / RSK_K2_TILEFAST /
+// RSK_K2_SMEM override them for tuning runs.
+constexpr int kDefaultFChunk = 64;
+constexpr int kDefaultTileFast = 0;
+constexpr int kDefaultOccSmem = 0;  // > 0: dynamic smem request that caps resident blocks per SM
 constexpr int kCompactItems = 8;    // mask bytes per thread in the compaction kernels
 constexpr int kCompactTile = kThreads * kCompactItems;  // 2048, see rsk_workspace_bytes
 constexpr int kSweepTimes = 16;     // time steps per block in the sweep kernel
@@ -493,8 +498,7 @@ int fill_eval_params(const RskSpectrum* spec, const double* freqs, int64_t nf, i
   p->freqs = freqs;
   p->nf = (int)nf;
   p->ncols = ncols;
-  // Frequency chunking (measured on B200 with tools/store_bench.cu): short chunks and few
-  // resident blocks per SM give the best HBM write locality; rows are streamed tile-fast.
+  // Frequency chunking (defaults measured on B200, see the constants at the top of this file).
   const int64_t tiles = (ncols + kThreads - 1) / kThreads;
   int fchunk = tuning_int("RSK_K2_FCHUNK", kDefaultFChunk);
   if (fchunk < 1) fchunk = 1;
@@ -504,7 +508,7 @@ int fill_eval_params(const RskSpectrum* spec, const double* freqs, int64_t nf, i
   p->nfchunks = (int)((nf + fchunk - 1) / fchunk);
   if (p->nfchunks < 1) p->nfchunks = 1;
   p->ntiles = tiles > 0 ? tiles : 1;
-  p->tile_fast = tuning_int("RSK_K2_TILEFAST", 1);
+  p->tile_fast = tuning_int("RSK_K2_TILEFAST", kDefaultTileFast);
   return RSK_OK;
 }
 

@@ -464,7 +464,13 @@ class SkyModel:
         plan = self._plan_coherency(freqs, freq_interp_kind, need_count=sync)
         nf, ncols = plan["nf"], plan["n_above"]
         if out is None:
-            ld_out = -(-ncols // 16) * 16 if pad else ncols
+            if pad:
+                # rows on 256-byte boundaries; the stride is also bucketed (~N/64) so that consecutive
+                # time steps, whose N_above differ slightly, reuse the same cached allocation
+                gran = max(16, -(-(self.Ncomponents // 64) // 16) * 16)
+                ld_out = -(-ncols // gran) * gran
+            else:
+                ld_out = ncols
             out = torch.empty((2, 2, nf, max(ld_out, 0)), dtype=torch.complex128, device=self.device)
             col0 = 0
         elif ld_out is None:
