@@ -133,7 +133,8 @@ def oracle_step(cat, k, sl=slice(None)):
     if "nside" in cat:
         from oracle import healpix_np
 
-        pix = np.arange(cat["n"])[sl]
+        npix = 12 * cat["nside"] ** 2
+        pix = (np.arange(cat["n"]) * (npix // cat["n"]))[sl]  # a sample strides over the whole sphere
         clon, clat = healpix_np.healpix_to_lonlat(cat["nside"], pix)
     else:
         clon, clat = cat["lon"][sl], cat["lat"][sl]
