@@ -337,8 +337,16 @@ def run_gpu(args):
                 _, cnt = sky.coherency_calc(freqs=freqs, out=out_buf, sync=False)
                 counts.append(cnt)
             else:
+                t_dbg = time.perf_counter()
                 o = sky.coherency_calc(freqs=freqs)
                 counts.append(o.shape[3])
+                if os.environ.get("RSK_BENCH_TRACE"):
+                    st = torch.cuda.memory_stats()
+                    print(f"[trace] step {k} host {1e3 * (time.perf_counter() - t_dbg):.3f} ms n_above {o.shape[3]} "
+                          f"stride {o.stride(2)} device_allocs {st['num_device_alloc']} frees {st['num_device_free']} "
+                          f"retries {st['num_alloc_retries']} reserved {st['reserved_bytes.all.current'] / 1e9:.1f} GB",
+                          file=sys.stderr, flush=True)
+                del o
         sky._timing_events = None
         return counts
 

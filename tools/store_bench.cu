@@ -107,6 +107,11 @@ int main(int argc, char** argv) {
     ms = timeit([&] { k_linear<<<blocks, 256>>>(out, total); });
     printf("linear store grid=%5d          : %7.3f ms  %7.1f GB/s\n", blocks, ms, bytes / ms / 1e6);
   }
+  if (argc > 3 && argv[3][0] == 'w') {  // how few warps per SM still saturate the stores? (1 block of 256 per SM = 8 warps)
+    for (int fc : {64, 256, 1024}) for (int smem : {0, 112 * 1024, 200 * 1024})
+      run_pattern<1, 1>(out, n, nf, fc, 1, "cs", smem, 0);
+    return 0;
+  }
   if (argc > 3 && argv[3][0] == 'g') {  // grid order x chunk x occupancy sweep on a 256B-aligned width
     for (int tf : {0, 1}) for (int fc : {8, 16, 32, 64, 128, 256}) for (int smem : {0, 56 * 1024, 112 * 1024})
       run_pattern<1, 1>(out, n, nf, fc, 1, "cs", smem, tf);
