@@ -22,6 +22,8 @@ constexpr int kMaxFChunk = 256;     // frequencies staged in shared memory per b
 // per block, frequency chunk fastest in the grid, no residency cap.  RSK_K2_FCHUNK / RSK_K2_TILEFAST /
 // RSK_K2_SMEM override them for tuning runs.
 constexpr int kDefaultFChunk = 64;
+constexpr int kSubbandFChunk = 128;          // longer chunks: fewer break-interval rebuilds per column
+constexpr int kMaxDynSmem = 200 * 1024;      // dynamic shared memory budget per block
 constexpr int kDefaultTileFast = 0;
 constexpr int kDefaultOccSmem = 0;  // > 0: dynamic smem request that caps resident blocks per SM
 constexpr int kCompactItems = 8;    // mask bytes per thread in the compaction kernels
@@ -239,6 +241,7 @@ struct EvalParams {
   const double* breaks;
   const double* ppoly;
   int nb, degree;
+  int y_in_smem;  // SUBBAND: each thread's stored spectrum is staged in dynamic shared memory
   const int32_t* freq_map;
   const uint8_t* polarized;
   // geometry (coherency epilogue only)
@@ -294,8 +297,17 @@ __device__ __forceinline__ void emit(const EvalParams& p, int f, int64_t col, co
   }
 }
 
+// NT = threads (= columns) per block: 256, except 128 for SUBBAND so that two blocks, each holding its
+// columns' stored spectra in shared memory, fit on an SM and overlap set-up with streaming.
+template <int MODE>
+struct EvalThreads {
+  static constexpr int value = (MODE == RSK_SUBBAND) ? 128 : kThreads;
+};
+
 template <int MODE, bool COH>
-__global__ void __launch_bounds__(kThreads) k_eval(const __grid_constant__ EvalParams p) {
+__global__ void __launch_bounds__(EvalThreads<MODE>::value) k_eval(const __grid_constant__ EvalParams p) {
+  constexpr int NT = EvalThreads<MODE>::value;
+  extern __shared__ double s_dyn[];    // SUBBAND: [4 * nf_in][NT] stored Stokes of this block's columns
   __shared__ double s_fa[kMaxFChunk];  // SPECTRAL_INDEX: ln(f / pivot); SUBBAND: local coordinate u
   __shared__ int s_iv[kMaxFChunk];     // SUBBAND: break interval; FULL: stored channel
   // Block -> (component tile, frequency chunk).  tile_fast: consecutive blocks are adjacent column
@@ -312,12 +324,12 @@ __global__ void __launch_bounds__(kThreads) k_eval(const __grid_constant__ EvalP
     chunk = (int)(blockIdx.x - tile * p.nfchunks);
   }
   const int64_t ncols = p.ncols_dev ? min(p.ncols, __ldg(p.ncols_dev)) : p.ncols;
-  if (tile * kThreads >= ncols) return;  // whole block past the live columns (uniform)
+  if (tile * NT >= ncols) return;  // whole block past the live columns (uniform)
   const int f0 = chunk * p.fchunk;
   const int nfc = min(p.fchunk, p.nf - f0);
   double pivot = 1.0;
   if (MODE == RSK_SPECTRAL_INDEX) pivot = __ldg(p.freqs + p.nf / 2);
-  for (int k = threadIdx.x; k < nfc; k += kThreads) {
+  for (int k = threadIdx.x; k < nfc; k += NT) {
     if (MODE == RSK_SPECTRAL_INDEX) {
       s_fa[k] = log(__ldg(p.freqs + f0 + k) / pivot);
     } else if (MODE == RSK_SUBBAND) {
@@ -336,7 +348,7 @@ __global__ void __launch_bounds__(kThreads) k_eval(const __grid_constant__ EvalP
   }
   if (MODE != RSK_FLAT) __syncthreads();
 
-  const int64_t col = tile * kThreads + threadIdx.x;
+  const int64_t col = tile * NT + threadIdx.x;
   if (col >= ncols) return;
   const int64_t src = p.idx ? __ldg(p.idx + col) : col;
 
@@ -372,10 +384,18 @@ __global__ void __launch_bounds__(kThreads) k_eval(const __grid_constant__ EvalP
       }
     }
   } else if (MODE == RSK_SUBBAND) {
-    // skymodel.py:2362-2368 through the host-built piecewise-polynomial operator
+    // skymodel.py:2362-2368 through the host-built piecewise-polynomial operator.  The 4 * nf_in stored
+    // values of this thread's column are read from HBM once (all loads in flight together) into shared
+    // memory; each change of break interval then rebuilds the 4 x 4 polynomial coefficients from there.
+    const int nfin = (int)p.nf_in;
+    double* ycol = s_dyn + threadIdx.x;
+    if (p.y_in_smem) {
+      const double* y = p.stokes + src;
+#pragma unroll 8
+      for (int q = 0; q < 4 * nfin; ++q) ycol[q * NT] = __ldg(y + (int64_t)q * p.n);
+    }
     double cf[4][4];  // [power][output quantity]
     int cur = -1;
-    const int nfin = (int)p.nf_in;
     for (int k = 0; k < nfc; ++k) {
       const int iv = s_iv[k];
       if (iv != cur) {  // uniform across the block: every thread walks the same frequencies
@@ -386,9 +406,15 @@ __global__ void __launch_bounds__(kThreads) k_eval(const __grid_constant__ EvalP
 #pragma unroll
           for (int s = 0; s < 4; ++s) acc[a][s] = 0.0;
         const double* P = p.ppoly + (int64_t)iv * (p.degree + 1) * nfin;
+#pragma unroll 4
         for (int j = 0; j < nfin; ++j) {
-          const double* y = p.stokes + (int64_t)j * p.n + src;
-          const double y0 = __ldg(y), y1 = __ldg(y + sstride), y2 = __ldg(y + 2 * sstride), y3 = __ldg(y + 3 * sstride);
+          double y0, y1, y2, y3;
+          if (p.y_in_smem) {
+            y0 = ycol[j * NT]; y1 = ycol[(nfin + j) * NT]; y2 = ycol[(2 * nfin + j) * NT]; y3 = ycol[(3 * nfin + j) * NT];
+          } else {
+            const double* y = p.stokes + (int64_t)j * p.n + src;
+            y0 = __ldg(y); y1 = __ldg(y + sstride); y2 = __ldg(y + 2 * sstride); y3 = __ldg(y + 3 * sstride);
+          }
 #pragma unroll
           for (int a = 0; a < 4; ++a) {
             if (a <= p.degree) {
@@ -499,8 +525,11 @@ int fill_eval_params(const RskSpectrum* spec, const double* freqs, int64_t nf, i
   p->nf = (int)nf;
   p->ncols = ncols;
   // Frequency chunking (defaults measured on B200, see the constants at the top of this file).
-  const int64_t tiles = (ncols + kThreads - 1) / kThreads;
-  int fchunk = tuning_int("RSK_K2_FCHUNK", kDefaultFChunk);
+  const int nt = spec->mode == RSK_SUBBAND ? EvalThreads<RSK_SUBBAND>::value : kThreads;
+  const int64_t tiles = (ncols + nt - 1) / nt;
+  // SUBBAND: stage each column's 4 * nf_in stored values in shared memory when they fit
+  p->y_in_smem = (spec->mode == RSK_SUBBAND && 4 * spec->nf_in * nt * (int64_t)sizeof(double) <= kMaxDynSmem) ? 1 : 0;
+  int fchunk = tuning_int("RSK_K2_FCHUNK", spec->mode == RSK_SUBBAND ? kSubbandFChunk : kDefaultFChunk);
   if (fchunk < 1) fchunk = 1;
   if (fchunk > kMaxFChunk) fchunk = kMaxFChunk;
   if (fchunk > nf) fchunk = (int)(nf > 0 ? nf : 1);
@@ -514,11 +543,16 @@ int fill_eval_params(const RskSpectrum* spec, const double* freqs, int64_t nf, i
 
 template <int MODE, bool COH>
 int launch_one(const EvalParams& p, dim3 grid, int smem, cudaStream_t st) {
+  constexpr int NT = EvalThreads<MODE>::value;
+  if (MODE == RSK_SUBBAND && p.y_in_smem) {
+    const int need = (int)(4 * p.nf_in * NT * sizeof(double));
+    if (need > smem) smem = need;
+  }
   if (smem > 48 * 1024) {
     const cudaError_t e = cudaFuncSetAttribute(k_eval<MODE, COH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
   }
-  k_eval<MODE, COH><<<grid, kThreads, smem, st>>>(p);
+  k_eval<MODE, COH><<<grid, NT, smem, st>>>(p);
   return launch_status();
 }
 
@@ -531,7 +565,7 @@ int launch_eval(const EvalParams& p, int mode, cudaStream_t st) {
   // The kernels use no dynamic shared memory; requesting some only caps how many blocks share an SM.
   int smem = tuning_int("RSK_K2_SMEM", kDefaultOccSmem);
   if (smem < 0) smem = 0;
-  if (smem > 200 * 1024) smem = 200 * 1024;
+  if (smem > kMaxDynSmem) smem = kMaxDynSmem;
   switch (mode) {
     case RSK_FLAT: return launch_one<RSK_FLAT, COH>(p, grid, smem, st);
     case RSK_SPECTRAL_INDEX: return launch_one<RSK_SPECTRAL_INDEX, COH>(p, grid, smem, st);
