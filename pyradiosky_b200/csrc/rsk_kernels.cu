@@ -22,7 +22,7 @@ constexpr int kMaxFChunk = 256;     // frequencies staged in shared memory per b
 // per block, frequency chunk fastest in the grid, no residency cap.  RSK_K2_FCHUNK / RSK_K2_TILEFAST /
 // RSK_K2_SMEM override them for tuning runs.
 constexpr int kDefaultFChunk = 64;
-constexpr int kSubbandFChunk = 128;          // longer chunks: fewer break-interval rebuilds per column
+constexpr int kSubbandFChunk = 256;          // longer chunks: the per-block staging cost is amortised (measured)
 constexpr int kMaxDynSmem = 200 * 1024;      // dynamic shared memory budget per block
 constexpr int kDefaultTileFast = 0;
 constexpr int kDefaultOccSmem = 0;  // > 0: dynamic smem request that caps resident blocks per SM
