@@ -103,6 +103,14 @@ typedef struct RskSpectrum {
   /* polarised flag per component = membership of SkyModel._polarized (skymodel.py:1037-1042, frozen
    * at construction upstream); NULL = nothing is rotated.  Build it with rsk_polarized_mask(). */
   const uint8_t* polarized;     /* [n] or NULL */
+  /* SUBBAND, optional banded form (faster): spline coefficients bcoef = cmat . stokes precomputed once
+   * per catalogue by rsk_spline_coefficients(); on interval b only degree+1 of them contribute:
+   * value = sum_p u^p * sum_m pband[b][p][m] * bcoef[s][first[b] + m][comp].  When bcoef is non-NULL it
+   * is used instead of stokes/ppoly (breaks, nb, degree are shared by both forms). */
+  const double* bcoef;          /* [4][nc][n] or NULL */
+  int64_t nc;                   /* number of spline coefficients per spectrum */
+  const int32_t* first;         /* [nb] */
+  const double* pband;          /* [nb][degree + 1][degree + 1] */
 } RskSpectrum;
 
 /* ---- host-side helpers (no GPU work) -------------------------------------------------------- */
@@ -193,6 +201,13 @@ int rsk_coherency(const RskSpectrum* spec, const RskCoords* coords, const double
                   const double* freqs /* [nf] Hz */, int64_t nf,
                   double* out /* complex [2][2][nf][ld_out] */, int64_t ld_out, int64_t col0,
                   void* stream);
+
+/* Spline coefficients of every stored spectrum: bcoef[s][i][c] = sum_j cmat[i][j] * stokes[s][j][c].
+ * cmat is the (nc x nf_in) matrix of scipy's make_interp_spline for the catalogue's freq_array and
+ * freq_interp_kind (host-built, uploaded by the caller).  Time independent: run once per catalogue. */
+int rsk_spline_coefficients(const double* stokes /* [4][nf_in][n] */, int64_t nf_in, int64_t n,
+                            const double* cmat /* [nc][nf_in] */, int64_t nc,
+                            double* bcoef /* [4][nc][n] */, void* stream);
 
 /* ---- K3 / K4: unfused API-parity kernels ------------------------------------------------------- */
 

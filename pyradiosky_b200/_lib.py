@@ -48,6 +48,10 @@ class RskSpectrum(ctypes.Structure):
         ("nb", ctypes.c_int64),
         ("freq_map", ctypes.c_void_p),
         ("polarized", ctypes.c_void_p),
+        ("bcoef", ctypes.c_void_p),
+        ("nc", ctypes.c_int64),
+        ("first", ctypes.c_void_p),
+        ("pband", ctypes.c_void_p),
     ]
 
 
@@ -89,6 +93,11 @@ _SIGNATURES = {
         [ctypes.POINTER(RskSpectrum), ctypes.POINTER(RskCoords), ctypes.c_void_p, c_double_p,
          ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
          ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p],
+    ),
+    "rsk_spline_coefficients": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+         ctypes.c_void_p, ctypes.c_void_p],
     ),
     "rsk_at_frequencies": (
         ctypes.c_int,

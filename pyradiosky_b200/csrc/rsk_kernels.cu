@@ -29,6 +29,7 @@ constexpr int kDefaultOccSmem = 0;  // > 0: dynamic smem request that caps resid
 constexpr int kCompactItems = 8;    // mask bytes per thread in the compaction kernels
 constexpr int kCompactTile = kThreads * kCompactItems;  // 2048, see rsk_workspace_bytes
 constexpr int kSweepTimes = 16;     // time steps per block in the sweep kernel
+constexpr int kSubbandBanded = 4;   // internal mode: RSK_SUBBAND evaluated from precomputed spline coefficients
 
 struct CoordSrc {
   const double* lon;
@@ -242,6 +243,10 @@ struct EvalParams {
   const double* ppoly;
   int nb, degree;
   int y_in_smem;  // SUBBAND: each thread's stored spectrum is staged in dynamic shared memory
+  const double* bcoef;  // banded SUBBAND: spline coefficients [4][nc][n]
+  int64_t nc;
+  const int32_t* first;
+  const double* pband;
   const int32_t* freq_map;
   const uint8_t* polarized;
   // geometry (coherency epilogue only)
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(EvalThreads<MODE>::value) k_eval(const __grid_
   for (int k = threadIdx.x; k < nfc; k += NT) {
     if (MODE == RSK_SPECTRAL_INDEX) {
       s_fa[k] = log(__ldg(p.freqs + f0 + k) / pivot);
-    } else if (MODE == RSK_SUBBAND) {
+    } else if (MODE == RSK_SUBBAND || MODE == kSubbandBanded) {
       const double f = __ldg(p.freqs + f0 + k);
       int lo = 0, hi = p.nb - 1;  // largest b with breaks[b] <= f, clamped to [0, nb-1]
       while (lo < hi) {
@@ -435,6 +440,46 @@ __global__ void __launch_bounds__(EvalThreads<MODE>::value) k_eval(const __grid_
       for (int q = 0; q < 4; ++q) o[q] = fma(fma(fma(cf[3][q], u, cf[2][q]), u, cf[1][q]), u, cf[0][q]);
       emit<COH>(p, f0 + k, col, o);
     }
+  } else if (MODE == kSubbandBanded) {
+    // skymodel.py:2362-2368 from precomputed spline coefficients: a change of break interval costs
+    // (degree+1) x 4 independent loads and a small banded product.
+    const int64_t cstride = p.nc * p.n;
+    const int dp1 = p.degree + 1;
+    double cf[4][4];  // [power][output quantity]
+    int cur = -1;
+    for (int k = 0; k < nfc; ++k) {
+      const int iv = s_iv[k];
+      if (iv != cur) {  // uniform across the block
+        cur = iv;
+        const double* cc = p.bcoef + (int64_t)__ldg(p.first + iv) * p.n + src;
+        const double* pb = p.pband + (int64_t)iv * dp1 * dp1;
+        double c[4][4];  // [m][stokes]
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int s = 0; s < 4; ++s) c[m][s] = (m < dp1) ? __ldg(cc + (int64_t)m * p.n + s * cstride) : 0.0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          double acc[4] = {0.0, 0.0, 0.0, 0.0};
+          if (a < dp1) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              if (m < dp1) {
+                const double w = __ldg(pb + a * dp1 + m);
+#pragma unroll
+                for (int s = 0; s < 4; ++s) acc[s] = fma(w, c[m][s], acc[s]);
+              }
+            }
+          }
+          xform<COH>(rot, acc[0], acc[1], acc[2], acc[3], cf[a]);
+        }
+      }
+      const double u = s_fa[k];
+      double o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q] = fma(fma(fma(cf[3][q], u, cf[2][q]), u, cf[1][q]), u, cf[0][q]);
+      emit<COH>(p, f0 + k, col, o);
+    }
   } else {  // RSK_FULL: stored Stokes, skymodel.py:2165-2181 subset + utils.py:42-57
 #pragma unroll 4
     for (int k = 0; k < nfc; ++k) {
@@ -443,6 +488,41 @@ __global__ void __launch_bounds__(EvalThreads<MODE>::value) k_eval(const __grid_
       double o[4];
       xform<COH>(rot, y0, y1, y2, y3, o);
       emit<COH>(p, f0 + k, col, o);
+    }
+  }
+}
+
+// Spline coefficients c = cmat . y per component and Stokes parameter (time independent, run once).
+// blockIdx.y = Stokes parameter; cmat staged in shared memory; the spectrum of the thread's component is
+// held in registers when nf_in <= NFMAX.
+template <int NFMAX>
+__global__ void __launch_bounds__(kThreads) k_spline_coefficients(const double* __restrict__ stokes, const int nf_in,
+                                                                  const int64_t n, const double* __restrict__ cmat,
+                                                                  const int nc, double* __restrict__ bcoef) {
+  extern __shared__ double s_cm[];  // [nc][nf_in]
+  for (int k = threadIdx.x; k < nc * nf_in; k += kThreads) s_cm[k] = __ldg(cmat + k);
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  const int s = blockIdx.y;
+  const double* y = stokes + (int64_t)s * nf_in * n + i;
+  double* out = bcoef + (int64_t)s * nc * n + i;
+  if (NFMAX > 0) {
+    double yr[NFMAX > 0 ? NFMAX : 1];
+#pragma unroll
+    for (int j = 0; j < NFMAX; ++j) yr[j] = j < nf_in ? __ldg(y + (int64_t)j * n) : 0.0;
+    for (int c = 0; c < nc; ++c) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < NFMAX; ++j)
+        if (j < nf_in) acc = fma(s_cm[c * nf_in + j], yr[j], acc);
+      out[(int64_t)c * n] = acc;
+    }
+  } else {
+    for (int c = 0; c < nc; ++c) {
+      double acc = 0.0;
+      for (int j = 0; j < nf_in; ++j) acc = fma(s_cm[c * nf_in + j], __ldg(y + (int64_t)j * n), acc);
+      out[(int64_t)c * n] = acc;
     }
   }
 }
@@ -504,7 +584,8 @@ int fill_eval_params(const RskSpectrum* spec, const double* freqs, int64_t nf, i
   if ((spec->mode == RSK_SPECTRAL_INDEX || spec->mode == RSK_SUBBAND) && !freqs) return RSK_ERR_NULL;
   if (spec->mode == RSK_SPECTRAL_INDEX && (!spec->spectral_index || !spec->ref_freq)) return RSK_ERR_NULL;
   if (spec->mode == RSK_SUBBAND) {
-    if (!spec->breaks || !spec->ppoly) return RSK_ERR_NULL;
+    if (!spec->breaks) return RSK_ERR_NULL;
+    if (spec->bcoef ? (!spec->first || !spec->pband || spec->nc < 1) : !spec->ppoly) return RSK_ERR_NULL;
     if (spec->nb < 1 || spec->nb > INT32_MAX) return RSK_ERR_SIZE;
     if (spec->degree < 0 || spec->degree > 3) return RSK_ERR_UNSUPPORTED;
   }
@@ -521,15 +602,20 @@ int fill_eval_params(const RskSpectrum* spec, const double* freqs, int64_t nf, i
   p->degree = spec->degree;
   p->freq_map = spec->freq_map;
   p->polarized = spec->polarized;
+  p->bcoef = spec->mode == RSK_SUBBAND ? spec->bcoef : nullptr;
+  p->nc = spec->nc;
+  p->first = spec->first;
+  p->pband = spec->pband;
   p->freqs = freqs;
   p->nf = (int)nf;
   p->ncols = ncols;
   // Frequency chunking (defaults measured on B200, see the constants at the top of this file).
-  const int nt = spec->mode == RSK_SUBBAND ? EvalThreads<RSK_SUBBAND>::value : kThreads;
+  const bool dense_subband = spec->mode == RSK_SUBBAND && !spec->bcoef;
+  const int nt = dense_subband ? EvalThreads<RSK_SUBBAND>::value : kThreads;
   const int64_t tiles = (ncols + nt - 1) / nt;
   // SUBBAND: stage each column's 4 * nf_in stored values in shared memory when they fit
-  p->y_in_smem = (spec->mode == RSK_SUBBAND && 4 * spec->nf_in * nt * (int64_t)sizeof(double) <= kMaxDynSmem) ? 1 : 0;
-  int fchunk = tuning_int("RSK_K2_FCHUNK", spec->mode == RSK_SUBBAND ? kSubbandFChunk : kDefaultFChunk);
+  p->y_in_smem = (dense_subband && 4 * spec->nf_in * nt * (int64_t)sizeof(double) <= kMaxDynSmem) ? 1 : 0;
+  int fchunk = tuning_int("RSK_K2_FCHUNK", dense_subband ? kSubbandFChunk : kDefaultFChunk);
   if (fchunk < 1) fchunk = 1;
   if (fchunk > kMaxFChunk) fchunk = kMaxFChunk;
   if (fchunk > nf) fchunk = (int)(nf > 0 ? nf : 1);
@@ -569,7 +655,9 @@ int launch_eval(const EvalParams& p, int mode, cudaStream_t st) {
   switch (mode) {
     case RSK_FLAT: return launch_one<RSK_FLAT, COH>(p, grid, smem, st);
     case RSK_SPECTRAL_INDEX: return launch_one<RSK_SPECTRAL_INDEX, COH>(p, grid, smem, st);
-    case RSK_SUBBAND: return launch_one<RSK_SUBBAND, COH>(p, grid, smem, st);
+    case RSK_SUBBAND:
+      if (p.bcoef) return launch_one<kSubbandBanded, COH>(p, grid, smem, st);
+      return launch_one<RSK_SUBBAND, COH>(p, grid, smem, st);
     case RSK_FULL: return launch_one<RSK_FULL, COH>(p, grid, smem, st);
     default: return RSK_ERR_MODE;
   }
@@ -677,6 +765,25 @@ int rsk_coherency(const RskSpectrum* spec, const RskCoords* coords, const double
   p.ld_out = ld_out;
   p.col0 = col0;
   return launch_eval<true>(p, spec->mode, (cudaStream_t)stream);
+}
+
+int rsk_spline_coefficients(const double* stokes, int64_t nf_in, int64_t n, const double* cmat, int64_t nc,
+                            double* bcoef, void* stream) {
+  if (nf_in < 1 || n < 0 || nc < 1) return RSK_ERR_SIZE;
+  if (n == 0) return RSK_OK;
+  if (!stokes || !cmat || !bcoef) return RSK_ERR_NULL;
+  const size_t smem = (size_t)nc * nf_in * sizeof(double);
+  if (smem > (size_t)kMaxDynSmem) return RSK_ERR_UNSUPPORTED;
+  const dim3 grid(blocks_for(n), 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nf_in <= 32) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_spline_coefficients<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_spline_coefficients<32><<<grid, kThreads, smem, st>>>(stokes, (int)nf_in, n, cmat, (int)nc, bcoef);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_spline_coefficients<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_spline_coefficients<0><<<grid, kThreads, smem, st>>>(stokes, (int)nf_in, n, cmat, (int)nc, bcoef);
+  }
+  return launch_status();
 }
 
 int rsk_at_frequencies(const RskSpectrum* spec, const double* freqs, int64_t nf, double* stokes_out, void* stream) {

@@ -268,14 +268,15 @@ class SkyModel:
             s.spectral_index = self.spectral_index.data_ptr()
             s.ref_freq = self.reference_frequency.data_ptr()
         if mode == _lib.SUBBAND:
-            degree, breaks, ppoly = spectral.build_ppoly_operator(self.freq_array, freq_interp_kind)
-            b = torch.as_tensor(breaks).to(self.device)
-            p = torch.as_tensor(np.ascontiguousarray(ppoly)).to(self.device)
-            keep += [b, p]
-            s.degree = degree
-            s.breaks = b.data_ptr()
-            s.ppoly = p.data_ptr()
-            s.nb = breaks.size - 1
+            op = self._subband_operator(freq_interp_kind)
+            keep.append(op)
+            s.degree = op["degree"]
+            s.breaks = op["breaks"].data_ptr()
+            s.nb = op["breaks"].numel() - 1
+            s.bcoef = op["bcoef"].data_ptr()
+            s.nc = op["nc"]
+            s.first = op["first"].data_ptr()
+            s.pband = op["pband"].data_ptr()
         if mode == _lib.FULL and freq_map is not None:
             fm = torch.as_tensor(np.ascontiguousarray(freq_map, dtype=np.int32)).to(self.device)
             keep.append(fm)
@@ -283,6 +284,30 @@ class SkyModel:
         if polarized and self._n_polarized > 0:
             s.polarized = self._polarized_mask.data_ptr()
         return s
+
+    def _subband_operator(self, freq_interp_kind):
+        """Device-resident banded spline operator + the spline coefficients of every stored spectrum.
+
+        Both are time independent, so they are built once per (stokes contents, freq_array, kind) and
+        reused by every ``coherency_calc`` / ``at_frequencies`` call (the reference rebuilds its
+        ``interp1d`` on every call, skymodel.py:2362-2368)."""
+        key = (self.stokes.data_ptr(), self.stokes._version, tuple(self.stokes.shape), str(freq_interp_kind),
+               self.freq_array.tobytes())
+        op = self.__dict__.get("_subband_cache")
+        if op is not None and op["key"] == key:
+            return op
+        degree, breaks, cmat, first, pband = spectral.build_bspline_operator(self.freq_array, freq_interp_kind)
+        dev = self.device
+        cm = torch.as_tensor(cmat).to(dev)
+        nc = int(cmat.shape[0])
+        bcoef = torch.empty((4, nc, self.Ncomponents), dtype=torch.float64, device=dev)
+        self._call("rsk_spline_coefficients", _lib.ptr(self.stokes), self.Nfreqs, self.Ncomponents, _lib.ptr(cm), nc,
+                   _lib.ptr(bcoef))
+        op = dict(key=key, degree=degree, nc=nc, bcoef=bcoef, breaks=torch.as_tensor(breaks).to(dev),
+                  first=torch.as_tensor(np.ascontiguousarray(first, dtype=np.int32)).to(dev),
+                  pband=torch.as_tensor(np.ascontiguousarray(pband)).to(dev))
+        self._subband_cache = op
+        return op
 
     def copy(self):
         """Deep copy (device tensors are cloned)."""
@@ -293,6 +318,8 @@ class SkyModel:
             elif isinstance(v, np.ndarray):
                 setattr(new, k, v.copy())
         new._freq_dev_cache = {}
+        new.__dict__.pop("_subband_cache", None)
+        new.__dict__.pop("_nan_cache", None)
         return new
 
     # ------------------------------------------------------------------------------------------

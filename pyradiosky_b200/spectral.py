@@ -86,3 +86,64 @@ def evaluate_operator(degree, breaks, ppoly, y, freqs):
     for p in range(degree, -1, -1):
         out = out * u.reshape((-1,) + (1,) * (coef.ndim - 2)) + coef[b, p]
     return out
+
+
+def build_bspline_operator(freq_array, kind="cubic"):
+    """Banded (B-spline) form of ``interp1d(freq_array, ., kind)``.
+
+    The interpolant is a spline ``sum_i c_i B_i(f)`` whose coefficients are a fixed linear map of the
+    stored channel values, ``c = cmat @ y`` (dense, time independent: computed once per catalogue on
+    the GPU by ``rsk_spline_coefficients``), and on every break interval only ``degree + 1`` basis
+    functions are non-zero.  Returns ``(degree, breaks, cmat, first, pband)``:
+
+    * ``cmat``  (nc, Nfreqs_in)  -- data -> spline coefficients,
+    * ``first`` (nb,) int32      -- index of the first coefficient used on interval b,
+    * ``pband`` (nb, degree+1, degree+1) -- with u = (f - breaks[b]) / (breaks[b+1] - breaks[b]),
+      ``value = sum_p u**p * sum_m pband[b, p, m] * c[first[b] + m]``.
+    """
+    x = np.asarray(freq_array, dtype=np.float64)
+    n = x.size
+    degree = interp_degree(kind)
+    if n <= degree:
+        raise ValueError(f"The number of derivatives at boundaries does not match: expected "
+                         f"at least {degree + 1} points for kind={kind!r}, got {n}")
+    order = np.argsort(x, kind="stable")
+    xs = x[order]
+    if np.any(np.diff(xs) <= 0):
+        raise ValueError("Expect x to not have duplicates")
+    spl = scipy.interpolate.make_interp_spline(xs, np.eye(n)[order], k=degree, check_finite=False)
+    t = spl.t
+    cmat = np.ascontiguousarray(spl.c)  # (nc, n): columns are original channel indices
+    nc = cmat.shape[0]
+    breaks = np.unique(t[degree: t.size - degree])
+    h = np.diff(breaks)
+    nb = h.size
+    basis = scipy.interpolate.BSpline(t, np.eye(nc), degree)
+    span = np.searchsorted(t, breaks[:-1], side="right") - 1  # t[span] <= break < t[span + 1]
+    first = (span - degree).astype(np.int32)
+    pband = np.zeros((nb, degree + 1, degree + 1))
+    fact = 1.0
+    for p in range(degree + 1):
+        if p > 0:
+            fact *= p
+        dv = (basis.derivative(p) if p > 0 else basis)(breaks[:-1]) / fact * (h**p)[:, None]  # (nb, nc)
+        for b in range(nb):
+            pband[b, p, :] = dv[b, first[b]: first[b] + degree + 1]
+    return degree, breaks, cmat, first, pband
+
+
+def evaluate_bspline_operator(degree, breaks, cmat, first, pband, y, freqs):
+    """numpy evaluation of the banded operator (host-side self-check helper)."""
+    freqs = np.asarray(freqs, dtype=np.float64)
+    c = np.tensordot(cmat, y, axes=(1, 0))  # (nc, ...)
+    b = np.clip(np.searchsorted(breaks, freqs, side="right") - 1, 0, len(breaks) - 2)
+    u = (freqs - breaks[b]) / (breaks[b + 1] - breaks[b])
+    out = np.zeros((freqs.size,) + c.shape[1:])
+    for k in range(freqs.size):
+        loc = c[first[b[k]]: first[b[k]] + degree + 1]
+        coef = np.tensordot(pband[b[k]], loc, axes=(1, 0))  # (degree+1, ...)
+        acc = 0.0
+        for p in range(degree, -1, -1):
+            acc = acc * u[k] + coef[p]
+        out[k] = acc
+    return out

@@ -686,3 +686,38 @@ def test_padded_and_async_outputs(rsk, site):
     assert out.data_ptr() == buf.data_ptr() and count.is_cuda and int(count.item()) == n_above
     assert torch.equal(buf[..., :n_above], exact)
     assert bool(torch.isnan(buf[..., n_above:].real).all())  # nothing written past the live columns
+
+
+@pytest.mark.parametrize("kind", ["linear", "cubic"])
+def test_dense_subband_path_through_c_abi(rsk, site, kind):
+    """RskSpectrum without precomputed spline coefficients (bcoef = NULL): the kernel stages each
+    column's stored spectrum in shared memory and applies the dense piecewise-polynomial operator.
+    The SkyModel mirror always uses the banded form, so this path is driven through the C ABI."""
+    from pyradiosky_b200 import _lib, spectral
+
+    time, loc = site
+    rng = np.random.default_rng(19)
+    n = 3001
+    sky, lon, lat, st, kw = make_model(rsk, rng, "subband", n)
+    freqs = np.linspace(80e6, 220e6, 301)
+    sky.update_positions(time, loc)
+    banded = sky.coherency_calc(freqs=freqs, pad=False)
+    plan = sky._plan_coherency(freqs, kind)
+    degree, breaks, ppoly = spectral.build_ppoly_operator(sky.freq_array, kind)
+    b = torch.as_tensor(breaks).cuda()
+    p = torch.as_tensor(np.ascontiguousarray(ppoly)).cuda()
+    spec = plan["spec"]
+    spec.bcoef = None
+    spec.ppoly = p.data_ptr()
+    spec.breaks = b.data_ptr()
+    spec.nb = breaks.size - 1
+    spec.degree = degree
+    out = torch.empty((2, 2, freqs.size, plan["n_above"]), dtype=torch.complex128, device="cuda")
+    sky._launch_coherency(plan, 0, freqs.size, out, plan["n_above"], 0)
+    above = sky.above_horizon.cpu().numpy()
+    full = oracle_eval(st, "subband", freqs, kw, kind)
+    ref = S.coherency_calc(full, lon, lat, sky.alt_az.cpu().numpy(), above, S.calc_average_rotation_matrix(sky._astrom),
+                           polarized=S.polarized_indices(st), vectorized=True)
+    assert_coherency_close(out.cpu().numpy(), ref, full[0][:, above])
+    if kind == "cubic":
+        assert_coherency_close(banded.cpu().numpy(), ref, full[0][:, above])

@@ -34,7 +34,7 @@ def test_struct_layouts_match_header():
     from pyradiosky_b200 import _lib
 
     assert ctypes.sizeof(_lib.RskCoords) == 48
-    assert ctypes.sizeof(_lib.RskSpectrum) == 88
+    assert ctypes.sizeof(_lib.RskSpectrum) == 120
     assert _lib.ASTROM_LEN == 31 and _lib.CTX_LEN == 34
 
 
@@ -153,6 +153,25 @@ def test_packed_context_reproduces_chain(librsk, hera):
     m = astrometry.frame_to_icrs_matrix("fk5")
     ctx2 = astrometry.pack_context(a, m)
     assert ctx2[23] == 0.0 and np.array_equal(ctx2[25:34].reshape(3, 3), m)
+
+
+@pytest.mark.parametrize("kind", ["linear", "slinear", "quadratic", "cubic", 1, 2, 3])
+def test_bspline_operator_matches_interp1d(kind):
+    from pyradiosky_b200 import spectral
+
+    x = np.array([76, 84, 92, 99, 107, 115, 122, 130, 143, 151, 158, 166, 174, 181, 189, 197, 204, 212, 220, 227]) * 1e6
+    rng = np.random.default_rng(1)
+    y = rng.normal(size=(20, 7)) + 3
+    f = np.concatenate((np.linspace(x[0], x[-1], 555), x))
+    degree, breaks, cmat, first, pband = spectral.build_bspline_operator(x, kind)
+    assert cmat.shape[1] == 20 and pband.shape == (breaks.size - 1, degree + 1, degree + 1)
+    assert first.min() >= 0 and first.max() + degree < cmat.shape[0]
+    ref = scipy.interpolate.interp1d(x, y, axis=0, kind=kind)(f)
+    assert np.abs(spectral.evaluate_bspline_operator(degree, breaks, cmat, first, pband, y, f) - ref).max() < 2e-14
+    perm = rng.permutation(20)
+    op = spectral.build_bspline_operator(x[perm], kind)
+    ref = scipy.interpolate.interp1d(x[perm], y[perm], axis=0, kind=kind)(f)
+    assert np.abs(spectral.evaluate_bspline_operator(*op, y[perm], f) - ref).max() < 2e-14
 
 
 @pytest.mark.parametrize("kind", ["linear", "slinear", "quadratic", "cubic", 1, 2, 3])
