@@ -294,14 +294,15 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if rank == 0:
-        entry.build()
     if world > 1:
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        dist.barrier()
     else:
         torch.cuda.set_device(0)
+    if rank == 0:
+        entry.build()  # no-op when the prebuilt librsk.so is current
+    if world > 1:
+        dist.barrier()  # nobody loads the library while rank 0 might be rebuilding it
     from pyradiosky_b200 import EarthLocation, SkyModel, Time, _lib
 
     _lib.load()
