@@ -37,18 +37,100 @@ struct RskCtx {
   double refa, refb;
   double w2;      // SRS / em
   double m_ident; // != 0: frame matrix is the identity, skip it
-  double pad;
+  double inv1pbm1; // 1 / (1 + bm1)
   double m[9];    // catalogue frame -> ICRS
 };
 static_assert(sizeof(RskCtx) == 34 * sizeof(double), "RskCtx layout");
+
+
+// ---- lean fp64 primitives ---------------------------------------------------------------------------
+// The position chain is bound by the fp64 pipe, not by HBM, once many time steps are evaluated per
+// source (ncu, profiles/r01_summary.md), so the two atan2, the divisions and the square roots are
+// written out branch-free here instead of calling libdevice (which spends about as many issue slots on
+// special-case handling and on re-materialising 64-bit constants as on arithmetic).  Accuracy: ~1 ulp
+// (2e-16 rad), five orders of magnitude inside the 1 micro-arcsecond budget.  On the host the libm
+// versions are used.
+
+// atan(t) = t + t*s*P(s), s = t^2, t in [0,1]; P from tools/gen_atan_poly.py (degree 19, max abs error
+// 1.1e-16 including the rounding of the double-precision Horner evaluation).
+#if defined(__CUDACC__)
+#define RSK_TABLE __constant__
+#else
+#define RSK_TABLE static const
+#endif
+RSK_TABLE double kRskAtanP[20] = {
+    -0x1.5555555555555p-2, 0x1.9999999999620p-3,  -0x1.24924924753ecp-3, 0x1.c71c71bb00a6cp-4,
+    -0x1.745d15ee35819p-4, 0x1.3b1399d1dcdc7p-4,  -0x1.110fff599e4d2p-4, 0x1.e1d0239d392a6p-5,
+    -0x1.aebbb1647a168p-5, 0x1.841dcf603a209p-5,  -0x1.5d02278205cc7p-5, 0x1.3328700bb8169p-5,
+    -0x1.00390504e9f2fp-5, 0x1.843f4bca23369p-6,  -0x1.fd0e4de8fed90p-7, 0x1.123baedb61abdp-7,
+    -0x1.ca3677db66678p-9, 0x1.1325b2f8964bep-10, -0x1.a359b96a4eee4p-13, 0x1.2f07811f9f6e9p-16};
+
+// a / b for finite a >= 0 and normal b > 0
+RSK_HD double rsk_div(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));  // ~20 good bits
+  const double e = fma(-b, r, 1.0);
+  r = fma(r, fma(e, e, e), r);                             // cubic step: ~2^-60
+  const double q = a * r;
+  return fma(fma(-b, q, a), r, q);                         // one residual correction
+#else
+  return a / b;
+#endif
+}
+
+// 1 / sqrt(x) for normal x > 0
+RSK_HD double rsk_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double e = fma(-x * r, r, 1.0);
+  r = fma(r, fma(0.375 * e, e, 0.5 * e), r);               // cubic step
+  const double e2 = fma(-x * r, r, 1.0);
+  return fma(0.5 * r, e2, r);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
+// sqrt(x) for x >= 0 (0 -> 0)
+RSK_HD double rsk_sqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  const double r = rsk_rsqrt(fmax(x, 1e-300));
+  const double s = x * r;
+  return fma(fma(-s, s, x), 0.5 * r, s);
+#else
+  return sqrt(x);
+#endif
+}
+
+// atan2(y, x) for finite arguments, not both zero; result in (-pi, pi]
+RSK_HD double rsk_atan2(double y, double x) {
+#if defined(__CUDA_ARCH__)
+  const double ay = fabs(y), ax = fabs(x);
+  const double t = rsk_div(fmin(ax, ay), fmax(ax, ay));
+  const double s = t * t;
+  double p = kRskAtanP[19];
+#pragma unroll
+  for (int i = 18; i >= 0; --i) p = fma(p, s, kRskAtanP[i]);
+  double r = fma(t * s, p, t);
+  r = ay > ax ? RSK_HALFPI - r : r;
+  r = x < 0.0 ? RSK_DPI - r : r;
+  return copysign(r, y);
+#else
+  return atan2(y, x);
+#endif
+}
 
 struct RskAltAz {
   double alt, az;   // radians
   double l, m, n;   // direction cosines: east, north, up
 };
 
-// (px,py,pz): unit vector of the component in the catalogue frame.
-RSK_HD RskAltAz rsk_chain(const RskCtx& c, double px, double py, double pz) {
+// (px,py,pz): unit vector of the component in the catalogue frame.  WANT_LMN = false skips the
+// direction cosines (the LST-sweep kernel does not always need them).
+template <bool WANT_LMN>
+RSK_HD RskAltAz rsk_chain_t(const RskCtx& c, double px, double py, double pz) {
   if (c.m_ident == 0.0) {
     const double x = c.m[0] * px + c.m[1] * py + c.m[2] * pz;
     const double y = c.m[3] * px + c.m[4] * py + c.m[5] * pz;
@@ -56,22 +138,21 @@ RSK_HD RskAltAz rsk_chain(const RskCtx& c, double px, double py, double pz) {
     px = x; py = y; pz = z;
   }
   // eraLd(bm=1, p, q=p, e=eh, em, dlim=1e-6): light deflection by the Sun (astropy atciqz sets q = p
-  // for coordinates without distance, which is every SkyModel component).
-  const double qdqpe = px * (px + c.eh[0]) + py * (py + c.eh[1]) + pz * (pz + c.eh[2]);
-  const double w = RSK_SRS / c.em / fmax(qdqpe, 1e-6);
-  const double eqx = c.eh[1] * pz - c.eh[2] * py;
-  const double eqy = c.eh[2] * px - c.eh[0] * pz;
-  const double eqz = c.eh[0] * py - c.eh[1] * px;
-  const double nx = px + w * (py * eqz - pz * eqy);
-  const double ny = py + w * (pz * eqx - px * eqz);
-  const double nz = pz + w * (px * eqy - py * eqx);
+  // for coordinates without distance, which is every SkyModel component).  p x (e x p) is expanded as
+  // e (p.p) - p (p.e), and q.(q+e) = p.p + p.e.
+  const double pp = px * px + py * py + pz * pz;
+  const double pe = px * c.eh[0] + py * c.eh[1] + pz * c.eh[2];
+  const double w = rsk_div(c.w2, fmax(pp + pe, 1e-6));  // SRS / em / max(q.(q+e), dlim)
+  const double nx = px + w * (c.eh[0] * pp - px * pe);
+  const double ny = py + w * (c.eh[1] * pp - py * pe);
+  const double nz = pz + w * (c.eh[2] * pp - pz * pe);
   // eraAb(pnat, v, s=em, bm1): annual (+ observer) aberration
   const double pdv = nx * c.v[0] + ny * c.v[1] + nz * c.v[2];
-  const double w1 = 1.0 + pdv / (1.0 + c.bm1);
+  const double w1 = 1.0 + pdv * c.inv1pbm1;
   double ax = nx * c.bm1 + w1 * c.v[0] + c.w2 * (c.v[0] - pdv * nx);
   double ay = ny * c.bm1 + w1 * c.v[1] + c.w2 * (c.v[1] - pdv * ny);
   double az_ = nz * c.bm1 + w1 * c.v[2] + c.w2 * (c.v[2] - pdv * nz);
-  const double rinv = 1.0 / sqrt(ax * ax + ay * ay + az_ * az_);
+  const double rinv = rsk_rsqrt(ax * ax + ay * ay + az_ * az_);
   ax *= rinv; ay *= rinv; az_ *= rinv;
   // eraRxp(bpn) + eraAtioq up to the polar-motion step, as one host-built rotation.  (ERFA goes
   // through c2s -> anp -> s2c(ri - eral, di); rotating the vector directly is the same to ~1e-16.)
@@ -87,11 +168,12 @@ RSK_HD RskAltAz rsk_chain(const RskCtx& c, double px, double py, double pz) {
   const double xaet = c.sphi * xhdt - c.cphi * zhdt;
   const double yaet = yhdt;
   const double zaet = c.cphi * xhdt + c.sphi * zhdt;
-  double azobs = (xaet != 0.0 || yaet != 0.0) ? atan2(yaet, -xaet) : 0.0;
+  const double azobs = (xaet != 0.0 || yaet != 0.0) ? rsk_atan2(yaet, -xaet) : 0.0;
   // A tan z + B tan^3 z refraction (identity for refa = refb = 0, which is what AltAz(obstime,
   // location) with its default zero pressure gives at skymodel.py:2453)
   double xaeo = xaet, yaeo = yaet, zaeo = zaet;
-  if (c.refa != 0.0 || c.refb != 0.0) {
+  const bool refracted = (c.refa != 0.0 || c.refb != 0.0);
+  if (refracted) {
     const double r = fmax(sqrt(xaet * xaet + yaet * yaet), RSK_CELMIN);
     const double z = fmax(zaet, RSK_SELMIN);
     const double tz = r / z;
@@ -103,18 +185,28 @@ RSK_HD RskAltAz rsk_chain(const RskCtx& c, double px, double py, double pz) {
     yaeo = yaet * fr;
     zaeo = cosdel * zaet + del * r;
   }
-  const double rxy = sqrt(xaeo * xaeo + yaeo * yaeo);
-  const double zdobs = atan2(rxy, zaeo);
+  const double rxy = rsk_sqrt(xaeo * xaeo + yaeo * yaeo);
+  const double zdobs = rsk_atan2(rxy, zaeo);
   RskAltAz o;
   o.alt = RSK_HALFPI - zdobs;                       // astropy: lat = PIOVER2 - zen
   o.az = azobs < 0.0 ? azobs + RSK_D2PI : azobs;    // eraAnp
-  // skymodel.py:2468-2470: l = sin(az) cos(alt), m = cos(az) cos(alt), n = sin(alt); taken from the
-  // cartesian vector instead of four more trig calls.
-  const double ninv = 1.0 / sqrt(rxy * rxy + zaeo * zaeo);
-  o.l = yaeo * ninv;
-  o.m = -xaeo * ninv;
-  o.n = zaeo * ninv;
+  if (WANT_LMN) {
+    // skymodel.py:2468-2470: l = sin(az) cos(alt), m = cos(az) cos(alt), n = sin(alt); taken from the
+    // cartesian vector instead of four more trig calls.  The vector is already of unit length unless
+    // refraction or diurnal aberration rescaled it.
+    double ninv = 1.0;
+    if (refracted || c.diurab != 0.0) ninv = rsk_rsqrt(rxy * rxy + zaeo * zaeo);
+    o.l = yaeo * ninv;
+    o.m = -xaeo * ninv;
+    o.n = zaeo * ninv;
+  } else {
+    o.l = o.m = o.n = 0.0;
+  }
   return o;
+}
+
+RSK_HD RskAltAz rsk_chain(const RskCtx& c, double px, double py, double pz) {
+  return rsk_chain_t<true>(c, px, py, pz);
 }
 
 // ---- HEALPix pixel centres -----------------------------------------------------------------------

@@ -360,7 +360,7 @@ int rsk_pack_context(const double* astrom, const double* frame2icrs, double* ctx
   if (frame2icrs)
     for (int i = 0; i < 9; ++i) is_ident = is_ident && (frame2icrs[i] == id.a[i]);
   c.m_ident = is_ident ? 1.0 : 0.0;
-  c.pad = 0.0;
+  c.inv1pbm1 = 1.0 / (1.0 + astrom[A_BM1]);
   memcpy(c.m, is_ident ? id.a : frame2icrs, sizeof(c.m));
   memcpy(ctx_out, &c, sizeof(c));
   return RSK_OK;

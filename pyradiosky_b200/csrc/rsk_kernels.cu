@@ -78,8 +78,10 @@ __global__ void __launch_bounds__(kThreads) k_positions(const CoordSrc cs, const
   if (above) above[i] = o.alt > 0.0 ? 1 : 0;  // skymodel.py:2479
 }
 
-// K1 sweep: T contexts per launch.  Block = kThreads components x kSweepTimes time steps; contexts are
-// staged in shared memory; per-component trigonometry is hoisted out of the time loop.
+// K1 sweep: T contexts per launch.  Block = (CPT x kThreads) components x kSweepTimes time steps; the
+// contexts are staged in shared memory; the per-component trigonometry is hoisted out of the time loop;
+// CPT components per thread share every context load and give the fp64 pipe independent chains.
+template <int CPT, bool WANT_LMN>
 __global__ void __launch_bounds__(kThreads) k_positions_sweep(const CoordSrc cs, const int64_t n,
                                                               const double* __restrict__ ctx_g, const int64_t nt,
                                                               const int ntchunks, double* __restrict__ alt_az,
@@ -95,22 +97,35 @@ __global__ void __launch_bounds__(kThreads) k_positions_sweep(const CoordSrc cs,
     for (int k = threadIdx.x; k < ntc * RSK_CTX_LEN; k += kThreads) dst[k] = __ldg(src + k);
   }
   __syncthreads();
-  const int64_t i = tile * kThreads + threadIdx.x;
-  if (i >= n) return;
-  double sl, cl, sb, cb;
-  frame_trig(cs, i, sl, cl, sb, cb);
-  const double px = cl * cb, py = sl * cb, pz = sb;
-  for (int k = 0; k < ntc; ++k) {
-    const RskAltAz o = rsk_chain(s_ctx[k], px, py, pz);
-    const int64_t t = t0 + k;
-    __stcs(alt_az + (2 * t) * n + i, o.alt);
-    __stcs(alt_az + (2 * t + 1) * n + i, o.az);
-    if (lmn) {
-      __stcs(lmn + (3 * t) * n + i, o.l);
-      __stcs(lmn + (3 * t + 1) * n + i, o.m);
-      __stcs(lmn + (3 * t + 2) * n + i, o.n);
+  int64_t idx[CPT];
+  double px[CPT], py[CPT], pz[CPT];
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) {
+    idx[j] = (tile * CPT + j) * kThreads + threadIdx.x;
+    px[j] = py[j] = 0.0; pz[j] = 1.0;
+    if (idx[j] < n) {
+      double sl, cl, sb, cb;
+      frame_trig(cs, idx[j], sl, cl, sb, cb);
+      px[j] = cl * cb; py[j] = sl * cb; pz[j] = sb;
     }
-    if (above) above[t * n + i] = o.alt > 0.0 ? 1 : 0;
+  }
+  for (int k = 0; k < ntc; ++k) {
+    const int64_t t = t0 + k;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      const RskAltAz o = rsk_chain_t<WANT_LMN>(s_ctx[k], px[j], py[j], pz[j]);
+      if (idx[j] < n) {
+        const int64_t i = idx[j];
+        __stcs(alt_az + (2 * t) * n + i, o.alt);
+        __stcs(alt_az + (2 * t + 1) * n + i, o.az);
+        if (WANT_LMN) {
+          __stcs(lmn + (3 * t) * n + i, o.l);
+          __stcs(lmn + (3 * t + 1) * n + i, o.m);
+          __stcs(lmn + (3 * t + 2) * n + i, o.n);
+        }
+        if (above) above[t * n + i] = o.alt > 0.0 ? 1 : 0;
+      }
+    }
   }
 }
 
@@ -692,11 +707,16 @@ int rsk_positions_sweep(const RskCoords* coords, int64_t n, const double* ctx, i
   if (!ctx || !alt_az) return RSK_ERR_NULL;
   if (n < 0 || T < 0) return RSK_ERR_SIZE;
   if (n == 0 || T == 0) return RSK_OK;
+  constexpr int kCpt = 2;  // components per thread in the sweep kernel
   const int64_t ntchunks = (T + kSweepTimes - 1) / kSweepTimes;
-  const int64_t nblocks = (int64_t)blocks_for(n) * ntchunks;
+  const int64_t ntiles = (n + kCpt * kThreads - 1) / (kCpt * kThreads);
+  const int64_t nblocks = ntiles * ntchunks;
   if (nblocks > 0x7fffffffll) return RSK_ERR_SIZE;
-  k_positions_sweep<<<(unsigned)nblocks, kThreads, 0, (cudaStream_t)stream>>>(cs, n, ctx, T, (int)ntchunks, alt_az,
-                                                                            pos_lmn, above);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pos_lmn)
+    k_positions_sweep<kCpt, true><<<(unsigned)nblocks, kThreads, 0, st>>>(cs, n, ctx, T, (int)ntchunks, alt_az, pos_lmn, above);
+  else
+    k_positions_sweep<kCpt, false><<<(unsigned)nblocks, kThreads, 0, st>>>(cs, n, ctx, T, (int)ntchunks, alt_az, pos_lmn, above);
   return launch_status();
 }
 
