@@ -144,6 +144,10 @@ int rsk_ravg(const double* astrom /* HOST [31] */, double* ravg /* HOST [9] */);
 int rsk_pack_context(const double* astrom /* HOST [31] */, const double* frame2icrs /* HOST [9] or NULL */,
                      double* ctx /* HOST [RSK_CTX_LEN] */);
 
+/* The same for T contexts at once: astroms HOST [T][31] -> ctx HOST [T][RSK_CTX_LEN]. */
+int rsk_pack_contexts(const double* astroms, int64_t T, const double* frame2icrs /* HOST [9] or NULL */,
+                      double* ctx);
+
 size_t rsk_workspace_bytes(int op, int64_t n, int64_t nf);
 
 /* ---- K1: positions --------------------------------------------------------------------------- */

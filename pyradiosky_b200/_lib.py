@@ -63,6 +63,7 @@ _SIGNATURES = {
     "rsk_frame_to_icrs": (ctypes.c_int, [ctypes.c_int, ctypes.c_double, c_double_p]),
     "rsk_ravg": (ctypes.c_int, [c_double_p, c_double_p]),
     "rsk_pack_context": (ctypes.c_int, [c_double_p, c_double_p, c_double_p]),
+    "rsk_pack_contexts": (ctypes.c_int, [c_double_p, ctypes.c_int64, c_double_p, c_double_p]),
     "rsk_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int64, ctypes.c_int64]),
     "rsk_positions": (
         ctypes.c_int,

@@ -185,3 +185,13 @@ def pack_context(astrom, frame_to_icrs=None):
     out = (ctypes.c_double * _lib.CTX_LEN)()
     _lib.check("rsk_pack_context", _lib.load().rsk_pack_context(a, m, out))
     return np.array(out[:])
+
+
+def pack_contexts(astroms, frame_to_icrs=None):
+    """(T, RSK_CTX_LEN) device-ready contexts from (T, 31) eraASTROM rows, in one library call."""
+    a = np.ascontiguousarray(astroms, dtype=np.float64).reshape(-1, _lib.ASTROM_LEN)
+    out = np.empty((a.shape[0], _lib.CTX_LEN), dtype=np.float64)
+    m = None if frame_to_icrs is None else _lib.host_array(np.asarray(frame_to_icrs, dtype=np.float64).ravel())
+    _lib.check("rsk_pack_contexts", _lib.load().rsk_pack_contexts(
+        a.ctypes.data_as(_lib.c_double_p), a.shape[0], m, out.ctypes.data_as(_lib.c_double_p)))
+    return out

@@ -366,6 +366,16 @@ int rsk_pack_context(const double* astrom, const double* frame2icrs, double* ctx
   return RSK_OK;
 }
 
+int rsk_pack_contexts(const double* astroms, int64_t T, const double* frame2icrs, double* ctx) {
+  if (T < 0) return RSK_ERR_SIZE;
+  if (T > 0 && (!astroms || !ctx)) return RSK_ERR_NULL;
+  for (int64_t t = 0; t < T; ++t) {
+    const int rc = rsk_pack_context(astroms + t * RSK_ASTROM_LEN, frame2icrs, ctx + t * RSK_CTX_LEN);
+    if (rc != RSK_OK) return rc;
+  }
+  return RSK_OK;
+}
+
 int rsk_ravg(const double* astrom, double* ravg) {
   if (!astrom || !ravg) return RSK_ERR_NULL;
   RskCtx c;

@@ -407,14 +407,20 @@ class SkyModel:
             astroms = np.stack([astrometry.astrom_context(t, telescope_location) for t in times])
         astroms = np.ascontiguousarray(astroms, dtype=np.float64).reshape(-1, _lib.ASTROM_LEN)
         nt, n = astroms.shape[0], self.Ncomponents
-        ctx = np.stack([astrometry.pack_context(a, self._frame_to_icrs) for a in astroms])
-        ctx_dev = torch.as_tensor(ctx).to(self.device)
+        ctx_dev = torch.as_tensor(astrometry.pack_contexts(astroms, self._frame_to_icrs)).to(self.device)
         alt_az = torch.empty((nt, 2, n), dtype=torch.float64, device=self.device)
         lmn = torch.empty((nt, 3, n), dtype=torch.float64, device=self.device) if want_lmn else None
         above = torch.empty((nt, n), dtype=torch.uint8, device=self.device) if want_mask else None
         coords = self._coords_struct()
+        events = getattr(self, "_timing_events", None)
+        if events is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(torch.cuda.current_stream(self.device))
         self._call("rsk_positions_sweep", ctypes.byref(coords), n, _lib.ptr(ctx_dev), nt, _lib.ptr(alt_az),
                    _lib.ptr(lmn), _lib.ptr(above))
+        if events is not None:
+            ev1.record(torch.cuda.current_stream(self.device))
+            events.append((ev0, ev1))
         return alt_az, lmn, (None if above is None else above.view(torch.bool))
 
     # ------------------------------------------------------------------------------------------

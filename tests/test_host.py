@@ -150,6 +150,9 @@ def test_packed_context_reproduces_chain(librsk, hera):
     hd = np.array([cx * v[0] + sx * v[2], sx * sy * v[0] + cy * v[1] - cx * sy * v[2], -sx * cy * v[0] + sy * v[1] + cx * cy * v[2]])
     assert np.abs(a1 @ p - hd).max() < 1e-15
     assert ctx[22] == E.SRS / a[E.I_EM] and ctx[23] == 1.0
+    batch = astrometry.pack_contexts(np.stack([a, a]))
+    assert batch.shape == (2, 34) and np.array_equal(batch[0], ctx) and np.array_equal(batch[1], ctx)
+    assert ctx[24] == 1.0 / (1.0 + a[E.I_BM1])
     m = astrometry.frame_to_icrs_matrix("fk5")
     ctx2 = astrometry.pack_context(a, m)
     assert ctx2[23] == 0.0 and np.array_equal(ctx2[25:34].reshape(3, 3), m)
