@@ -111,6 +111,11 @@ typedef struct RskSpectrum {
   int64_t nc;                   /* number of spline coefficients per spectrum */
   const int32_t* first;         /* [nb] */
   const double* pband;          /* [nb][degree + 1][degree + 1] */
+  /* SUBBAND, dense form on a subset of the stored channels (NaN handling, skymodel.py:2245-2312: a group
+   * of components whose non-NaN channels are chan_map[0..nf_use)): ppoly is [nb][degree+1][nf_use] and its
+   * column j multiplies stored channel chan_map[j].  NULL = all nf_in channels. Not with bcoef. */
+  const int32_t* chan_map;      /* [nf_use] or NULL */
+  int64_t nf_use;
 } RskSpectrum;
 
 /* ---- host-side helpers (no GPU work) -------------------------------------------------------- */
@@ -181,6 +186,11 @@ int rsk_healpix_lonlat(int64_t nside, int nested, const int64_t* hpx_inds /* [n]
 int rsk_compact_index(const uint8_t* above, int64_t n, int64_t* idx /* [n] */,
                       int64_t* n_above /* device [1] */, void* work, size_t work_bytes, void* stream);
 
+/* Per-component bit mask of stored channels at which all four Stokes parameters are non-NaN (bit j =
+ * channel j; nf_in <= 64): the freq_inds_use of skymodel.py:2246-2248 for every component at once. */
+int rsk_valid_channels(const double* stokes /* [4][nf_in][n] */, int64_t nf_in, int64_t n,
+                       uint64_t* mask /* [n] */, void* stream);
+
 /* SkyModel._polarized (skymodel.py:1037-1042): pol[c] = any over stored channels of (Q+U+V != 0). */
 int rsk_polarized_mask(const double* stokes /* [4][nf_in][n] */, int64_t nf_in, int64_t n,
                        uint8_t* pol /* [n] */, void* stream);
@@ -201,6 +211,7 @@ int rsk_polarized_mask(const double* stokes /* [4][nf_in][n] */, int64_t nf_in, 
  * ncols is then only the upper bound that sizes the grid.  alt_az is the [2][n] output of rsk_positions. */
 int rsk_coherency(const RskSpectrum* spec, const RskCoords* coords, const double* alt_az /* [2][n] */,
                   const double* ravg /* HOST [9] */, const int64_t* idx /* [ncols] or NULL */,
+                  const int64_t* cols /* [ncols] or NULL: thread k computes column cols[k] (a subset) */,
                   int64_t ncols, const int64_t* ncols_dev /* device [1] or NULL */,
                   const double* freqs /* [nf] Hz */, int64_t nf,
                   double* out /* complex [2][2][nf][ld_out] */, int64_t ld_out, int64_t col0,
@@ -215,9 +226,11 @@ int rsk_spline_coefficients(const double* stokes /* [4][nf_in][n] */, int64_t nf
 
 /* ---- K3 / K4: unfused API-parity kernels ------------------------------------------------------- */
 
-/* SkyModel.at_frequencies (skymodel.py:2084-2389): evaluate the spectral model on ``freqs`` for all n
- * components -> stokes_out [4][nf][n]. */
+/* SkyModel.at_frequencies (skymodel.py:2084-2389): evaluate the spectral model on ``freqs`` ->
+ * stokes_out [4][nf][n], for all n components (comps NULL) or only for components comps[0..ncomps)
+ * (the per-NaN-pattern groups of :2245-2312; other columns of stokes_out are left untouched). */
 int rsk_at_frequencies(const RskSpectrum* spec, const double* freqs /* [nf] */, int64_t nf,
+                       const int64_t* comps /* [ncomps] or NULL */, int64_t ncomps,
                        double* stokes_out, void* stream);
 
 /* utils.stokes_to_coherency / SkyModel.calc_frame_coherency (utils.py:17-61, skymodel.py:2481-2497):

@@ -52,6 +52,8 @@ class RskSpectrum(ctypes.Structure):
         ("nc", ctypes.c_int64),
         ("first", ctypes.c_void_p),
         ("pband", ctypes.c_void_p),
+        ("chan_map", ctypes.c_void_p),
+        ("nf_use", ctypes.c_int64),
     ]
 
 
@@ -92,7 +94,7 @@ _SIGNATURES = {
     "rsk_coherency": (
         ctypes.c_int,
         [ctypes.POINTER(RskSpectrum), ctypes.POINTER(RskCoords), ctypes.c_void_p, c_double_p,
-         ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
          ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p],
     ),
     "rsk_spline_coefficients": (
@@ -102,7 +104,12 @@ _SIGNATURES = {
     ),
     "rsk_at_frequencies": (
         ctypes.c_int,
-        [ctypes.POINTER(RskSpectrum), ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p],
+        [ctypes.POINTER(RskSpectrum), ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+         ctypes.c_void_p, ctypes.c_void_p],
+    ),
+    "rsk_valid_channels": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p],
     ),
     "rsk_stokes_to_coherency": (
         ctypes.c_int,

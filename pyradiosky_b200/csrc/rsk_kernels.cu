@@ -230,6 +230,25 @@ __global__ void __launch_bounds__(kThreads) k_compact_scatter(const uint8_t* __r
     if (bits & (1u << k)) idx[o++] = base + k;
 }
 
+// Bit j of mask[c] is set when all four Stokes parameters of component c are non-NaN at stored channel j:
+// the per-component "freq_inds_use" of skymodel.py:2246-2248, for every component at once.
+__global__ void __launch_bounds__(kThreads) k_valid_channels(const double* __restrict__ stokes, const int nf,
+                                                             const int64_t n, uint64_t* __restrict__ mask) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  uint64_t m = 0;
+  for (int f = 0; f < nf; ++f) {
+    bool ok = true;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const double v = __ldg(stokes + ((int64_t)s * nf + f) * n + i);
+      ok = ok && (v == v);
+    }
+    if (ok) m |= 1ull << f;
+  }
+  mask[i] = m;
+}
+
 // SkyModel._polarized predicate, skymodel.py:1039-1041: any_f ((Q + U) + V != 0)
 __global__ void __launch_bounds__(kThreads) k_polarized(const double* __restrict__ stokes, const int64_t nf,
                                                         const int64_t n, uint8_t* __restrict__ pol) {
@@ -258,6 +277,8 @@ struct EvalParams {
   const double* ppoly;
   int nb, degree;
   int y_in_smem;  // SUBBAND: each thread's stored spectrum is staged in dynamic shared memory
+  const int32_t* chan_map;  // dense SUBBAND on a channel subset: operator column j reads stored channel chan_map[j]
+  int nf_use;               // number of operator columns (== nf_in without chan_map)
   const double* bcoef;  // banded SUBBAND: spline coefficients [4][nc][n]
   int64_t nc;
   const int32_t* first;
@@ -270,6 +291,7 @@ struct EvalParams {
   double ravg[9];
   // columns
   const int64_t* idx;
+  const int64_t* cols;       // optional: thread k works on output column cols[k] (default k)
   int64_t ncols;
   const int64_t* ncols_dev;  // optional: the live column count in device memory (<= ncols)
   int64_t ntiles;
@@ -368,8 +390,9 @@ __global__ void __launch_bounds__(EvalThreads<MODE>::value) k_eval(const __grid_
   }
   if (MODE != RSK_FLAT) __syncthreads();
 
-  const int64_t col = tile * NT + threadIdx.x;
-  if (col >= ncols) return;
+  const int64_t kcol = tile * NT + threadIdx.x;
+  if (kcol >= ncols) return;
+  const int64_t col = p.cols ? __ldg(p.cols + kcol) : kcol;
   const int64_t src = p.idx ? __ldg(p.idx + col) : col;
 
   // per-component rotation coefficients (identity for unpolarised components, skymodel.py:2687-2688)
@@ -407,7 +430,9 @@ __global__ void __launch_bounds__(EvalThreads<MODE>::value) k_eval(const __grid_
     // skymodel.py:2362-2368 through the host-built piecewise-polynomial operator.  The 4 * nf_in stored
     // values of this thread's column are read from HBM once (all loads in flight together) into shared
     // memory; each change of break interval then rebuilds the 4 x 4 polynomial coefficients from there.
-    const int nfin = (int)p.nf_in;
+    // (With chan_map the operator is built on a subset of the stored channels -- the non-NaN ones of a
+    // group of components, skymodel.py:2245-2312 -- and the spectra are read straight from global memory.)
+    const int nfin = p.nf_use;
     double* ycol = s_dyn + threadIdx.x;
     if (p.y_in_smem) {
       const double* y = p.stokes + src;
@@ -432,7 +457,8 @@ __global__ void __launch_bounds__(EvalThreads<MODE>::value) k_eval(const __grid_
           if (p.y_in_smem) {
             y0 = ycol[j * NT]; y1 = ycol[(nfin + j) * NT]; y2 = ycol[(2 * nfin + j) * NT]; y3 = ycol[(3 * nfin + j) * NT];
           } else {
-            const double* y = p.stokes + (int64_t)j * p.n + src;
+            const int ch = p.chan_map ? __ldg(p.chan_map + j) : j;
+            const double* y = p.stokes + (int64_t)ch * p.n + src;
             y0 = __ldg(y); y1 = __ldg(y + sstride); y2 = __ldg(y + 2 * sstride); y3 = __ldg(y + 3 * sstride);
           }
 #pragma unroll
@@ -603,6 +629,7 @@ int fill_eval_params(const RskSpectrum* spec, const double* freqs, int64_t nf, i
     if (spec->bcoef ? (!spec->first || !spec->pband || spec->nc < 1) : !spec->ppoly) return RSK_ERR_NULL;
     if (spec->nb < 1 || spec->nb > INT32_MAX) return RSK_ERR_SIZE;
     if (spec->degree < 0 || spec->degree > 3) return RSK_ERR_UNSUPPORTED;
+    if (spec->chan_map && (spec->bcoef || spec->nf_use < 1 || spec->nf_use > spec->nf_in)) return RSK_ERR_SIZE;
   }
   if (spec->mode == RSK_FULL && !spec->freq_map && nf != spec->nf_in) return RSK_ERR_SIZE;
   if ((spec->mode == RSK_FLAT || spec->mode == RSK_SPECTRAL_INDEX) && spec->nf_in != 1) return RSK_ERR_SIZE;
@@ -617,6 +644,8 @@ int fill_eval_params(const RskSpectrum* spec, const double* freqs, int64_t nf, i
   p->degree = spec->degree;
   p->freq_map = spec->freq_map;
   p->polarized = spec->polarized;
+  p->chan_map = spec->mode == RSK_SUBBAND ? spec->chan_map : nullptr;
+  p->nf_use = (int)((spec->mode == RSK_SUBBAND && spec->chan_map) ? spec->nf_use : spec->nf_in);
   p->bcoef = spec->mode == RSK_SUBBAND ? spec->bcoef : nullptr;
   p->nc = spec->nc;
   p->first = spec->first;
@@ -629,7 +658,7 @@ int fill_eval_params(const RskSpectrum* spec, const double* freqs, int64_t nf, i
   const int nt = dense_subband ? EvalThreads<RSK_SUBBAND>::value : kThreads;
   const int64_t tiles = (ncols + nt - 1) / nt;
   // SUBBAND: stage each column's 4 * nf_in stored values in shared memory when they fit
-  p->y_in_smem = (dense_subband && 4 * spec->nf_in * nt * (int64_t)sizeof(double) <= kMaxDynSmem) ? 1 : 0;
+  p->y_in_smem = (dense_subband && !spec->chan_map && 4 * spec->nf_in * nt * (int64_t)sizeof(double) <= kMaxDynSmem) ? 1 : 0;
   int fchunk = tuning_int("RSK_K2_FCHUNK", dense_subband ? kSubbandFChunk : kDefaultFChunk);
   if (fchunk < 1) fchunk = 1;
   if (fchunk > kMaxFChunk) fchunk = kMaxFChunk;
@@ -755,6 +784,15 @@ int rsk_compact_index(const uint8_t* above, int64_t n, int64_t* idx, int64_t* n_
   return launch_status();
 }
 
+int rsk_valid_channels(const double* stokes, int64_t nf_in, int64_t n, uint64_t* mask, void* stream) {
+  if (n < 0 || nf_in < 0) return RSK_ERR_SIZE;
+  if (nf_in > 64) return RSK_ERR_UNSUPPORTED;
+  if (n == 0) return RSK_OK;
+  if (!stokes || !mask) return RSK_ERR_NULL;
+  k_valid_channels<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(stokes, (int)nf_in, n, mask);
+  return launch_status();
+}
+
 int rsk_polarized_mask(const double* stokes, int64_t nf_in, int64_t n, uint8_t* pol, void* stream) {
   if (n < 0 || nf_in < 0) return RSK_ERR_SIZE;
   if (n == 0) return RSK_OK;
@@ -764,14 +802,14 @@ int rsk_polarized_mask(const double* stokes, int64_t nf_in, int64_t n, uint8_t* 
 }
 
 int rsk_coherency(const RskSpectrum* spec, const RskCoords* coords, const double* alt_az, const double* ravg,
-                  const int64_t* idx, int64_t ncols, const int64_t* ncols_dev, const double* freqs, int64_t nf,
-                  double* out, int64_t ld_out, int64_t col0, void* stream) {
+                  const int64_t* idx, const int64_t* cols, int64_t ncols, const int64_t* ncols_dev, const double* freqs,
+                  int64_t nf, double* out, int64_t ld_out, int64_t col0, void* stream) {
   EvalParams p = {};
   int rc = fill_eval_params(spec, freqs, nf, ncols, &p);
   if (rc != RSK_OK) return rc;
   if (ncols > 0 && nf > 0 && !out) return RSK_ERR_NULL;
-  if (col0 < 0 || ld_out < col0 + ncols) return RSK_ERR_LD;
-  if (!idx && ncols > spec->n) return RSK_ERR_SIZE;
+  if (col0 < 0 || (!cols && ld_out < col0 + ncols)) return RSK_ERR_LD;
+  if (!idx && !cols && ncols > spec->n) return RSK_ERR_SIZE;
   if (spec->polarized) {  // rotation needed: geometry must be present
     rc = check_coords(coords, &p.cs);
     if (rc != RSK_OK) return rc;
@@ -780,6 +818,7 @@ int rsk_coherency(const RskSpectrum* spec, const RskCoords* coords, const double
   }
   p.alt_az = alt_az;
   p.idx = idx;
+  p.cols = cols;
   p.ncols_dev = ncols_dev;
   p.out = out;
   p.ld_out = ld_out;
@@ -806,13 +845,17 @@ int rsk_spline_coefficients(const double* stokes, int64_t nf_in, int64_t n, cons
   return launch_status();
 }
 
-int rsk_at_frequencies(const RskSpectrum* spec, const double* freqs, int64_t nf, double* stokes_out, void* stream) {
+int rsk_at_frequencies(const RskSpectrum* spec, const double* freqs, int64_t nf, const int64_t* comps, int64_t ncomps,
+                       double* stokes_out, void* stream) {
   EvalParams p = {};
   if (!spec) return RSK_ERR_NULL;
-  const int rc = fill_eval_params(spec, freqs, nf, spec->n, &p);
+  if (comps && (ncomps < 0 || ncomps > spec->n)) return RSK_ERR_SIZE;
+  const int64_t ncols = comps ? ncomps : spec->n;
+  const int rc = fill_eval_params(spec, freqs, nf, ncols, &p);
   if (rc != RSK_OK) return rc;
-  if (spec->n > 0 && nf > 0 && !stokes_out) return RSK_ERR_NULL;
+  if (ncols > 0 && nf > 0 && !stokes_out) return RSK_ERR_NULL;
   p.idx = nullptr;
+  p.cols = comps;
   p.out = stokes_out;
   p.ld_out = spec->n;
   p.col0 = 0;
@@ -828,7 +871,7 @@ int rsk_stokes_to_coherency(const double* stokes, int64_t nf, int64_t n, double*
   if (nf < 0 || n < 0) return RSK_ERR_SIZE;
   if (nf == 0 || n == 0) return RSK_OK;
   RskCoords none = {};
-  return rsk_coherency(&spec, &none, nullptr, nullptr, nullptr, n, nullptr, nullptr, nf, out, n, 0, stream);
+  return rsk_coherency(&spec, &none, nullptr, nullptr, nullptr, nullptr, n, nullptr, nullptr, nf, out, n, 0, stream);
 }
 
 int rsk_convert_units(double* stokes, int64_t nf, int64_t n, const double* freq_per_chan, const double* freq_per_comp,

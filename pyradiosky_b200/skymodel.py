@@ -319,6 +319,7 @@ class SkyModel:
                 setattr(new, k, v.copy())
         new._freq_dev_cache = {}
         new.__dict__.pop("_subband_cache", None)
+        new.__dict__.pop("_nan_group_cache", None)
         new.__dict__.pop("_nan_cache", None)
         return new
 
@@ -462,7 +463,7 @@ class SkyModel:
         return idx, int(cnt.item())
 
     def coherency_calc(self, store_frame_coherency=True, freqs=None, freq_interp_kind="cubic", out=None,
-                       ld_out=None, col0=0, pad=True, sync=True):
+                       ld_out=None, col0=0, pad=True, sync=True, nan_handling="clip"):
         """Calculate the local coherency in the alt/az basis (skymodel.py:2648-2712).
 
         :meth:`update_positions` must be run prior to this method.
@@ -494,6 +495,11 @@ class SkyModel:
         torch.Tensor, complex128, shape (2, 2, Nfreqs, N_above) -- component axis fastest, only
         components above the horizon, in catalogue order.
         """
+        groups = None
+        if freqs is not None:
+            groups = self._nan_groups(_to_hz_host(freqs), freq_interp_kind, nan_handling)
+            if groups and not sync:
+                raise ValueError("sync=False is not available for subband models with NaN Stokes values")
         plan = self._plan_coherency(freqs, freq_interp_kind, need_count=sync)
         nf, ncols = plan["nf"], plan["n_above"]
         if out is None:
@@ -509,6 +515,19 @@ class SkyModel:
         elif ld_out is None:
             ld_out = int(out.shape[-1])
         self._launch_coherency(plan, 0, nf, out, ld_out, col0)
+        for g in groups or ():
+            # columns (positions in the compacted order) whose component belongs to this NaN pattern
+            member = torch.zeros(self.Ncomponents, dtype=torch.bool, device=self.device)
+            member[g["comps"]] = True
+            src = plan["idx"][:ncols] if plan["idx"] is not None else torch.arange(ncols, device=self.device)
+            gcols = torch.nonzero(member[src], as_tuple=False).flatten()
+            if gcols.numel() == 0:
+                continue
+            gplan = dict(plan)
+            gplan["spec"] = self._group_spectrum(g, polarized=True)
+            gplan["cols"] = gcols
+            gplan["n_above"] = int(gcols.numel())
+            self._launch_coherency(gplan, 0, nf, out, ld_out, col0)
         if not sync:
             return out, plan["count"]
         if out.shape[-1] == ncols and col0 == 0:
@@ -576,8 +595,8 @@ class SkyModel:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(torch.cuda.current_stream(self.device))
         self._call("rsk_coherency", ctypes.byref(spec), ctypes.byref(plan["coords"]), _lib.ptr(plan["altaz"]),
-                   plan["ravg"], None if plan["idx"] is None else _lib.ptr(plan["idx"]), plan["n_above"],
-                   _lib.ptr(plan["count_dev"]), fptr, nf, _lib.ptr(out), ld_out, col0)
+                   plan["ravg"], None if plan["idx"] is None else _lib.ptr(plan["idx"]), _lib.ptr(plan.get("cols")),
+                   plan["n_above"], _lib.ptr(plan["count_dev"]), fptr, nf, _lib.ptr(out), ld_out, col0)
         if events is not None:
             ev1.record(torch.cuda.current_stream(self.device))
             events.append((ev0, ev1))
@@ -592,6 +611,8 @@ class SkyModel:
         4 * Nfreqs * N_above values; the returned tensor is its (2, 2, Nfreqs, N_above) view.  The call
         returns after the last copy has been queued; synchronise before reading.
         """
+        if self.spectral_type == "subband" and self._has_nan("stokes"):
+            raise NotImplementedError("coherency_calc_to_host does not handle NaN subband spectra; use coherency_calc")
         plan = self._plan_coherency(freqs, freq_interp_kind)
         nf, n_above = plan["nf"], plan["n_above"]
         need = 4 * nf * n_above
@@ -642,12 +663,94 @@ class SkyModel:
                 raise ValueError("A requested frequency is larger than the highest subband frequency.")
             if np.min(fhost) < np.min(self.freq_array):
                 raise ValueError("A requested frequency is smaller than the lowest subband frequency.")
-            if self._has_nan("stokes"):
-                raise NotImplementedError(
-                    "Subband Stokes with NaNs (nan_handling) are not supported on the GPU path yet."
-                )
             spectral.interp_degree(freq_interp_kind)
         return fhost
+
+    def _nan_groups(self, fhost, freq_interp_kind, nan_handling):
+        """Per-NaN-pattern groups of a subband model (skymodel.py:2196-2360), or None without NaNs.
+
+        Components are grouped by the set of stored channels at which all four Stokes parameters are
+        finite (``rsk_valid_channels``); every group gets one dense operator built on its valid channels
+        (``spectral.build_nan_group_operator``).  Emits the reference's warnings.  Cached until the Stokes
+        tensor changes."""
+        if self.spectral_type != "subband" or not self._has_nan("stokes"):
+            return None
+        if nan_handling not in ("propagate", "interp", "clip"):
+            raise ValueError("nan_handling must be one of ['propagate', 'interp', 'clip']")
+        if self.Nfreqs > 64:
+            raise NotImplementedError("NaN handling on the GPU path supports at most 64 subbands.")
+        message = "Some Stokes values are NaNs."
+        if nan_handling == "propagate":
+            message += " All output Stokes values for sources with any NaN values will be NaN."
+        else:
+            message += " Interpolating using the non-NaN values only."
+        message += " You can change the way NaNs are handled using the `nan_handling` keyword."
+        warnings.warn(message)
+        key = (self.stokes.data_ptr(), self.stokes._version, tuple(self.stokes.shape), str(freq_interp_kind),
+               nan_handling, self.freq_array.tobytes())
+        cache = self.__dict__.get("_nan_group_cache")
+        if cache is None or cache["key"] != key:
+            mask = torch.empty(self.Ncomponents, dtype=torch.int64, device=self.device)
+            self._call("rsk_valid_channels", _lib.ptr(self.stokes), self.Nfreqs, self.Ncomponents, _lib.ptr(mask))
+            mask_h = mask.cpu().numpy().view(np.uint64)
+            full = np.uint64((1 << self.Nfreqs) - 1) if self.Nfreqs < 64 else np.uint64(0xFFFFFFFFFFFFFFFF)
+            bad = np.nonzero(mask_h != full)[0]
+            groups = []
+            for pat in np.unique(mask_h[bad]):
+                comps = bad[mask_h[bad] == pat]
+                use = np.array([j for j in range(self.Nfreqs) if (int(pat) >> j) & 1], dtype=np.int64)
+                degree, breaks, ppoly, chan, fallback = spectral.build_nan_group_operator(
+                    self.freq_array, use, freq_interp_kind, nan_handling)
+                groups.append(dict(
+                    comps_host=comps, use=use, fallback=fallback and use.size > 0, degree=degree,
+                    comps=torch.as_tensor(comps.astype(np.int64)).to(self.device),
+                    breaks=torch.as_tensor(breaks).to(self.device),
+                    ppoly=torch.as_tensor(np.ascontiguousarray(ppoly)).to(self.device),
+                    chan=torch.as_tensor(np.ascontiguousarray(chan, dtype=np.int32)).to(self.device)))
+            cache = dict(key=key, groups=groups)
+            self._nan_group_cache = cache
+        groups = cache["groups"]
+        if nan_handling != "propagate":  # the per-category warnings of skymodel.py:2315-2359
+            n_all = sum(g["comps_host"].size for g in groups if g["use"].size == 0)
+            n_high = sum(g["comps_host"].size for g in groups
+                         if g["use"].size and np.max(fhost) > np.max(self.freq_array[g["use"]]))
+            n_low = sum(g["comps_host"].size for g in groups
+                        if g["use"].size and np.min(fhost) < np.min(self.freq_array[g["use"]]))
+            n_many = sum(g["comps_host"].size for g in groups if g["fallback"])
+            if n_all:
+                warnings.warn(f"{n_all} components had all NaN Stokes values. "
+                              "Output Stokes for these components will all be NaN.")
+            tail = ("The Stokes for these components at these frequencies will be NaN."
+                    if nan_handling == "interp" else None)
+            if n_high:
+                warnings.warn(f"{n_high} components had all NaN Stokes values above one or more of the requested "
+                              "frequencies. " + (tail or "Using the Stokes value at the highest frequency without a "
+                                                 "NaN for these components at these frequencies."))
+            if n_low:
+                warnings.warn(f"{n_low} components had all NaN Stokes values below one or more of the requested "
+                              "frequencies. " + (tail or "Using the Stokes value at the lowest frequency without a "
+                                                 "NaN for these components at these frequencies."))
+            if n_many:
+                warnings.warn(f"{n_many} components had too few non-NaN Stokes values for chosen interpolation. "
+                              "Using linear interpolation for these components instead.")
+        return groups
+
+    def _group_spectrum(self, group, polarized):
+        """RskSpectrum of one NaN-pattern group: dense operator on the group's valid channels."""
+        s = _lib.RskSpectrum()
+        s.mode = _lib.SUBBAND
+        s.stokes = self.stokes.data_ptr()
+        s.nf_in = self.Nfreqs
+        s.n = self.Ncomponents
+        s.degree = group["degree"]
+        s.breaks = group["breaks"].data_ptr()
+        s.ppoly = group["ppoly"].data_ptr()
+        s.nb = group["breaks"].numel() - 1
+        s.chan_map = group["chan"].data_ptr()
+        s.nf_use = group["chan"].numel()
+        if polarized and self._n_polarized > 0:
+            s.polarized = self._polarized_mask.data_ptr()
+        return s
 
     def _has_nan(self, attr):
         """isnan(...).any() of a device array, cached until the tensor is modified in place or replaced
@@ -683,6 +786,7 @@ class SkyModel:
         sky = self if inplace else self.copy()
         fhost = _to_hz_host(freqs)
         self._check_request(fhost, freq_interp_kind)
+        groups = self._nan_groups(fhost, freq_interp_kind, nan_handling)
         mode = _lib.SPECTRAL_MODES[self.spectral_type]
         fmap = self._full_freq_map(fhost, atol) if mode == _lib.FULL else None
         keep = []
@@ -690,7 +794,11 @@ class SkyModel:
         nf = fhost.size if fmap is None else fmap.size
         new_stokes = torch.empty((4, nf, self.Ncomponents), dtype=torch.float64, device=self.device)
         fdev = self._freqs_dev(fhost)
-        self._call("rsk_at_frequencies", ctypes.byref(spec), _lib.ptr(fdev), nf, _lib.ptr(new_stokes))
+        self._call("rsk_at_frequencies", ctypes.byref(spec), _lib.ptr(fdev), nf, None, 0, _lib.ptr(new_stokes))
+        for g in groups or ():  # components with NaNs: re-evaluated per pattern on their valid channels
+            gs = self._group_spectrum(g, polarized=False)
+            self._call("rsk_at_frequencies", ctypes.byref(gs), _lib.ptr(fdev), nf, _lib.ptr(g["comps"]),
+                       g["comps"].numel(), _lib.ptr(new_stokes))
         sky.stokes = new_stokes
         sky.reference_frequency = None
         sky.Nfreqs = nf

@@ -147,3 +147,56 @@ def evaluate_bspline_operator(degree, breaks, cmat, first, pband, y, freqs):
             acc = acc * u[k] + coef[p]
         out[k] = acc
     return out
+
+
+def build_nan_group_operator(freq_array, use, kind="cubic", nan_handling="clip"):
+    """Dense operator for components whose only non-NaN stored channels are ``use`` (storage indices).
+
+    Restates the per-component branch of skymodel.py:2245-2312 as a piecewise polynomial over the whole
+    frequency axis: inside [min, max] of the valid channel frequencies the ``interp1d`` of the valid
+    subset (falling back to linear when there are too few points for ``kind``, :2302-2309); outside,
+    the value at the first / last valid channel (``clip``) or NaN (``interp``).  ``propagate`` and
+    components without any valid channel give NaN everywhere.
+
+    Returns ``(degree, breaks, ppoly, chan_map, fallback_linear)`` with ``ppoly`` of shape
+    (nb, degree+1, len(chan_map)).
+    """
+    if nan_handling not in ("propagate", "interp", "clip"):
+        raise ValueError("nan_handling must be one of ['propagate', 'interp', 'clip']")
+    x = np.asarray(freq_array, dtype=np.float64)
+    use = np.asarray(use, dtype=np.int64)
+    big = 1e300
+    if nan_handling == "propagate" or use.size == 0:
+        return 0, np.array([0.0, big]), np.full((1, 1, 1), np.nan), np.zeros(1, dtype=np.int32), False
+    xs = x[use]
+    fmin, fmax = xs.min(), xs.max()
+    fallback = False
+    if use.size == 1:
+        # One valid channel: upstream falls back to a linear interp1d on a single point (:2302-2309),
+        # whose 0/0 weights give NaN at that exact frequency; outside it clips / NaNs as usual.
+        degree = 0
+        core_breaks = np.array([fmin, np.nextafter(fmin, np.inf)])
+        core = np.full((1, 1, 1), np.nan)
+        fallback = True
+    else:
+        degree = interp_degree(kind)
+        eff_kind = kind
+        if use.size <= degree:
+            eff_kind, degree, fallback = "linear", 1, True
+        degree, core_breaks, core = build_ppoly_operator(xs, eff_kind)
+    nuse = use.size
+    edge = np.nan if nan_handling == "interp" else 1.0
+    low = np.zeros((1, degree + 1, nuse))
+    high = np.zeros((1, degree + 1, nuse))
+    # the reference clips to stokes[:, freq_inds_use[0]] / [-1]: first / last valid index in storage order
+    low[0, 0, 0] = edge
+    high[0, 0, nuse - 1] = edge
+    if nan_handling == "interp":
+        low[0, 0, :] = np.nan
+        high[0, 0, :] = np.nan
+    # f == fmax must still be interpolated (reference: at_freq_arr <= max), so the upper edge interval
+    # starts one ulp above it
+    breaks = np.concatenate(([min(0.0, fmin - 1.0)], core_breaks[:-1], [np.nextafter(fmax, np.inf), big]))
+    last_core = core[-1:].copy()
+    ppoly = np.concatenate((low, core[:-1], last_core, high), axis=0) if core.shape[0] > 1 else np.concatenate((low, last_core, high), axis=0)
+    return degree, breaks, ppoly, use.astype(np.int32), fallback

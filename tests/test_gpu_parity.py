@@ -424,6 +424,9 @@ def test_at_frequencies_errors(rsk):
         sky2.at_frequencies(sky.freq_array)
     with pytest.raises(NotImplementedError):
         sky.at_frequencies(sky.freq_array, freq_interp_kind="nearest")
+    sky.stokes[0, 0, 0] = float("nan")
+    with pytest.raises(ValueError, match="nan_handling must be one of "):
+        sky.at_frequencies(sky.freq_array, nan_handling="foo")
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -721,3 +724,93 @@ def test_dense_subband_path_through_c_abi(rsk, site, kind):
     assert_coherency_close(out.cpu().numpy(), ref, full[0][:, above])
     if kind == "cubic":
         assert_coherency_close(banded.cpu().numpy(), ref, full[0][:, above])
+
+
+def _nan_model(rsk, rng, n):
+    """Subband model whose components carry a variety of NaN patterns (GLEAM has NaN / missing subbands)."""
+    sky, lon, lat, st, kw = make_model(rsk, rng, "subband", n)
+    pat = rng.integers(0, 9, n)
+    for c in range(n):
+        if pat[c] == 1:
+            st[rng.integers(0, 4), : rng.integers(1, 4), c] = np.nan            # low edge missing
+        elif pat[c] == 2:
+            st[rng.integers(0, 4), -rng.integers(1, 4):, c] = np.nan            # high edge missing
+        elif pat[c] == 3:
+            st[rng.integers(0, 4), rng.choice(20, rng.integers(1, 6), replace=False), c] = np.nan  # scattered
+        elif pat[c] == 4 and c % 7 == 0:
+            st[:, :, c] = np.nan                                                 # nothing valid
+        elif pat[c] == 5 and c % 5 == 0:
+            keep = rng.choice(20, rng.integers(1, 4), replace=False)            # too few for a cubic
+            gone = np.ones(20, bool); gone[keep] = False
+            st[1, gone, c] = np.nan
+    model = rsk.SkyModel(lon=lon, lat=lat, stokes=st, spectral_type="subband", freq_array=kw["freq_array"])
+    return model, lon, lat, st, kw
+
+
+@pytest.mark.filterwarnings("ignore:Some Stokes values are NaNs")
+@pytest.mark.filterwarnings("ignore:invalid value encountered")
+@pytest.mark.parametrize("nan_handling", ["clip", "interp", "propagate"])
+@pytest.mark.parametrize("kind", ["cubic", "linear"])
+def test_at_frequencies_nan_handling(rsk, nan_handling, kind):
+    """skymodel.py:2196-2360 (tests/test_skymodel.py:3630-3846 exercise it on GLEAM): per-pattern groups
+    on the GPU == the reference's per-component loop."""
+    rng = np.random.default_rng(21)
+    sky, lon, lat, st, kw = _nan_model(rsk, rng, 1201)
+    freqs = np.concatenate((np.linspace(76e6, 227e6, 151), kw["freq_array"][[0, 3, 19]]))
+    with pytest.warns(UserWarning, match="Some Stokes values are NaNs."):
+        sky.at_frequencies(freqs, freq_interp_kind=kind, nan_handling=nan_handling)
+    got = sky.stokes.cpu().numpy()
+    import warnings as _w
+    with _w.catch_warnings():
+        _w.simplefilter("ignore")
+        ref = S.at_frequencies(st, "subband", freqs, freq_array=kw["freq_array"], freq_interp_kind=kind,
+                               nan_handling=nan_handling)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = np.isfinite(ref)
+    scale = np.broadcast_to(np.nanmax(np.abs(st), axis=(0, 1))[None, None, :], ref.shape)
+    assert np.max(np.abs(got[ok] - ref[ok]) / scale[ok]) < 1e-12
+    assert np.isnan(ref).any() and ok.any()
+
+
+@pytest.mark.filterwarnings("ignore:Some Stokes values are NaNs")
+@pytest.mark.filterwarnings("ignore:invalid value encountered")
+def test_nan_handling_warnings(rsk):
+    rng = np.random.default_rng(22)
+    sky, lon, lat, st, kw = _nan_model(rsk, rng, 800)
+    freqs = np.linspace(76e6, 227e6, 31)
+    with pytest.warns(UserWarning) as rec:
+        sky.at_frequencies(freqs, inplace=False, nan_handling="clip")
+    msgs = " | ".join(str(w.message) for w in rec)
+    assert "Interpolating using the non-NaN values only." in msgs
+    assert "components had all NaN Stokes values. Output Stokes" in msgs
+    assert "Using the Stokes value at the highest frequency without a NaN" in msgs
+    assert "Using the Stokes value at the lowest frequency without a NaN" in msgs
+    assert "too few non-NaN Stokes values for chosen interpolation" in msgs
+    with pytest.warns(UserWarning) as rec:
+        sky.at_frequencies(freqs, inplace=False, nan_handling="propagate")
+    assert "will be NaN" in str(rec[0].message)
+
+
+@pytest.mark.filterwarnings("ignore:Some Stokes values are NaNs")
+@pytest.mark.filterwarnings("ignore:invalid value encountered")
+@pytest.mark.filterwarnings("ignore:.*components had")
+def test_coherency_fused_with_nan_spectra(rsk, site):
+    time, loc = site
+    rng = np.random.default_rng(23)
+    sky, lon, lat, st, kw = _nan_model(rsk, rng, 1500)
+    freqs = np.linspace(80e6, 220e6, 41)
+    sky.update_positions(time, loc)
+    got = sky.coherency_calc(freqs=freqs, nan_handling="clip").cpu().numpy()
+    above = sky.above_horizon.cpu().numpy()
+    import warnings as _w
+    with _w.catch_warnings():
+        _w.simplefilter("ignore")
+        full = S.at_frequencies(st, "subband", freqs, freq_array=kw["freq_array"], nan_handling="clip")
+    ref = S.coherency_calc(full, lon, lat, sky.alt_az.cpu().numpy(), above, S.calc_average_rotation_matrix(sky._astrom),
+                           polarized=S.polarized_indices(st), vectorized=True)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = np.isfinite(ref)
+    scale = np.broadcast_to(np.nanmax(np.abs(st[0]), axis=0)[above][None, None, None, :], ref.shape)
+    assert np.max(np.abs(got[ok] - ref[ok]) / scale[ok]) < 1e-12
+    with pytest.raises(ValueError, match="sync=False is not available"):
+        sky.coherency_calc(freqs=freqs, out=torch.empty((2, 2, 41, 1504), dtype=torch.complex128, device="cuda"), sync=False)

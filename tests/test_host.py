@@ -34,7 +34,7 @@ def test_struct_layouts_match_header():
     from pyradiosky_b200 import _lib
 
     assert ctypes.sizeof(_lib.RskCoords) == 48
-    assert ctypes.sizeof(_lib.RskSpectrum) == 120
+    assert ctypes.sizeof(_lib.RskSpectrum) == 136
     assert _lib.ASTROM_LEN == 31 and _lib.CTX_LEN == 34
 
 
@@ -57,15 +57,15 @@ def test_argument_errors_without_gpu(librsk):
     spec.stokes = 8
     spec.nf_in = 1
     spec.n = 4
-    assert librsk.rsk_coherency(ctypes.byref(spec), ctypes.byref(coords), None, None, None, 4, None, None, 1, None, 4, 0, None) == -3
+    assert librsk.rsk_coherency(ctypes.byref(spec), ctypes.byref(coords), None, None, None, None, 4, None, None, 1, None, 4, 0, None) == -3
     spec.mode = _lib.FLAT
-    assert librsk.rsk_coherency(ctypes.byref(spec), ctypes.byref(coords), None, None, None, 4, None, None, 1, ctypes.c_void_p(8), 2, 0, None) == -4
+    assert librsk.rsk_coherency(ctypes.byref(spec), ctypes.byref(coords), None, None, None, None, 4, None, None, 1, ctypes.c_void_p(8), 2, 0, None) == -4
     spec.mode = _lib.SUBBAND
     spec.degree = 5
     spec.breaks = 8
     spec.ppoly = 8
     spec.nb = 3
-    assert librsk.rsk_coherency(ctypes.byref(spec), ctypes.byref(coords), None, None, None, 4, None, ctypes.c_void_p(8), 1, ctypes.c_void_p(8), 4, 0, None) == -6
+    assert librsk.rsk_coherency(ctypes.byref(spec), ctypes.byref(coords), None, None, None, None, 4, None, ctypes.c_void_p(8), 1, ctypes.c_void_p(8), 4, 0, None) == -6
     assert librsk.rsk_compact_index(ctypes.c_void_p(8), 100, ctypes.c_void_p(8), ctypes.c_void_p(8), None, 0, None) == -5
     assert librsk.rsk_workspace_bytes(_lib.OP_COMPACT, 5000, 0) == (3 + 1) * 8
     # zero-sized problems are accepted without touching the device
@@ -225,3 +225,31 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+@pytest.mark.filterwarnings("ignore:Some Stokes values are NaNs")
+@pytest.mark.parametrize("kind", ["cubic", "linear"])
+@pytest.mark.parametrize("nan_handling", ["clip", "interp", "propagate"])
+def test_nan_group_operator_matches_reference_branch(kind, nan_handling):
+    """spectral.build_nan_group_operator == the per-component NaN branch of at_frequencies
+    (skymodel.py:2245-2312, via the oracle) for a range of valid-channel patterns."""
+    from pyradiosky_b200 import spectral
+
+    x = np.array([76, 84, 92, 99, 107, 115, 122, 130, 143, 151, 158, 166, 174, 181, 189, 197, 204, 212, 220, 227]) * 1e6
+    rng = np.random.default_rng(3)
+    f = np.concatenate((np.linspace(76e6, 227e6, 211), x))
+    for use in (np.arange(2, 20), np.arange(0, 17), np.array([0, 1, 2, 5, 6, 9, 15, 19]), np.array([3, 7]),
+                np.array([4, 8, 11]), np.array([5]), np.array([], dtype=int)):
+        st = rng.normal(size=(4, 20, 1)) + 3
+        gone = np.ones(20, bool)
+        gone[use] = False
+        st[rng.integers(0, 4), gone, 0] = np.nan
+        ref = S.at_frequencies(st, "subband", f, freq_array=x, freq_interp_kind=kind, nan_handling=nan_handling)[:, :, 0].T
+        degree, breaks, ppoly, chan, _ = spectral.build_nan_group_operator(x, use, kind, nan_handling)
+        with np.errstate(all="ignore"):
+            got = spectral.evaluate_operator(degree, breaks, ppoly, st[:, chan, 0].T, f)
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        ok = np.isfinite(ref)
+        assert np.abs(got[ok] - ref[ok]).max() < 1e-13 if ok.any() else True
+    with pytest.raises(ValueError, match="nan_handling must be one of"):
+        spectral.build_nan_group_operator(x, np.arange(20), kind, "foo")
