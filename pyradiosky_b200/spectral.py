@@ -177,7 +177,7 @@ def build_nan_group_operator(freq_array, use, kind="cubic", nan_handling="clip")
         degree = 0
         core_breaks = np.array([fmin, np.nextafter(fmin, np.inf)])
         core = np.full((1, 1, 1), np.nan)
-        fallback = True
+        fallback = kind != "linear"  # interp1d(kind="linear") accepts one point silently
     else:
         degree = interp_degree(kind)
         eff_kind = kind
