@@ -90,6 +90,8 @@ def synth_catalog(workload, seed, n_override=None):
         cat["freqs"] = np.linspace(80e6, 220e6, nf)
     else:
         cat["freqs"] = np.array([150e6]) if nf == 1 else np.linspace(100e6, 200e6, nf)
+    if os.environ.get("RSK_BENCH_UNPOLARIZED"):  # tuning aid: no component takes the rotation branch
+        st[1:] = 0.0
     cat["stokes"] = np.ascontiguousarray(st)
     return cat
 
