@@ -346,8 +346,22 @@ struct EvalThreads {
   static constexpr int value = (MODE == RSK_SUBBAND) ? 128 : kThreads;
 };
 
+// Minimum resident blocks per SM asked of ptxas per mode (register cap); overridable at build time for
+// tuning (-DRSK_MINB_SI=4 ...).
+#ifndef RSK_MINB_SI
+#define RSK_MINB_SI 1
+#endif
+#ifndef RSK_MINB_BANDED
+#define RSK_MINB_BANDED 1
+#endif
+template <int MODE>
+struct EvalMinBlocks {
+  static constexpr int value = (MODE == RSK_SPECTRAL_INDEX) ? RSK_MINB_SI : (MODE == 4 ? RSK_MINB_BANDED : 1);
+};
+
 template <int MODE, bool COH>
-__global__ void __launch_bounds__(EvalThreads<MODE>::value) k_eval(const __grid_constant__ EvalParams p) {
+__global__ void __launch_bounds__(EvalThreads<MODE>::value, EvalMinBlocks<MODE>::value)
+k_eval(const __grid_constant__ EvalParams p) {
   constexpr int NT = EvalThreads<MODE>::value;
   extern __shared__ double s_dyn[];    // SUBBAND: [4 * nf_in][NT] stored Stokes of this block's columns
   __shared__ double s_fa[kMaxFChunk];  // SPECTRAL_INDEX: ln(f / pivot); SUBBAND: local coordinate u
