@@ -79,6 +79,11 @@ typedef struct RskCoords {
   int32_t reserved;
   const int64_t* hpx_inds; /* [n] or NULL */
   int64_t hpx_first;
+  /* Optional per-component polarisation-rotation coefficients [3][n] = (cos^2 X + sin^2 X,
+   * cos^2 X - sin^2 X, 2 sin X cos X) of skymodel.py:2603-2646.  rsk_positions writes them (it already has
+   * every sine and cosine they need) when this pointer and its ravg argument are non-NULL; rsk_coherency
+   * reads them instead of recomputing them when the pointer is non-NULL. */
+  double* rot;
 } RskCoords;
 
 /* The spectral model of the catalogue = what SkyModel.at_frequencies (skymodel.py:2084-2389) reads. */
@@ -165,6 +170,7 @@ size_t rsk_workspace_bytes(int op, int64_t n, int64_t nf);
 int rsk_positions(const RskCoords* coords, int64_t n,
                   const double* frame2icrs /* HOST [9] row-major, NULL = identity */,
                   const double* astrom /* HOST [31] */,
+                  const double* ravg /* HOST [9] or NULL: with coords->rot, also emit the rotation coefficients */,
                   double* alt_az /* [2][n] */, double* pos_lmn /* [3][n] or NULL */,
                   uint8_t* above /* [n] or NULL */, void* stream);
 

@@ -31,6 +31,7 @@ class RskCoords(ctypes.Structure):
         ("reserved", ctypes.c_int32),
         ("hpx_inds", ctypes.c_void_p),
         ("hpx_first", ctypes.c_int64),
+        ("rot", ctypes.c_void_p),
     ]
 
 
@@ -69,7 +70,7 @@ _SIGNATURES = {
     "rsk_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int64, ctypes.c_int64]),
     "rsk_positions": (
         ctypes.c_int,
-        [ctypes.POINTER(RskCoords), ctypes.c_int64, c_double_p, c_double_p, ctypes.c_void_p,
+        [ctypes.POINTER(RskCoords), ctypes.c_int64, c_double_p, c_double_p, c_double_p, ctypes.c_void_p,
          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p],
     ),
     "rsk_positions_sweep": (

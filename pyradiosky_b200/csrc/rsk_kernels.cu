@@ -38,6 +38,7 @@ struct CoordSrc {
   int nested;
   const int64_t* hpx_inds;
   int64_t hpx_first;
+  double* rot;  // optional [3][n] rotation coefficients (written by K1, read by K2)
 };
 
 // sin/cos of the catalogue-frame longitude and latitude of component i
@@ -59,8 +60,14 @@ __device__ __forceinline__ void frame_trig(const CoordSrc& c, int64_t i, double&
 // ---------------------------------------------------------------------------------------------------
 // K1: positions (one time step)
 // ---------------------------------------------------------------------------------------------------
+struct Ravg {
+  double m[9];
+  int valid;
+};
+
 __global__ void __launch_bounds__(kThreads) k_positions(const CoordSrc cs, const int64_t n,
                                                         const __grid_constant__ RskCtx ctx,
+                                                        const __grid_constant__ Ravg ravg,
                                                         double* __restrict__ alt_az, double* __restrict__ lmn,
                                                         uint8_t* __restrict__ above) {
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -68,6 +75,19 @@ __global__ void __launch_bounds__(kThreads) k_positions(const CoordSrc cs, const
   double sl, cl, sb, cb;
   frame_trig(cs, i, sl, cl, sb, cb);
   const RskAltAz o = rsk_chain(ctx, cl * cb, sl * cb, sb);
+  if (ravg.valid) {
+    // Polarisation-rotation coefficients for K2.  sin/cos of alt and az come from the direction cosines
+    // (l, m, n) = (sin az cos alt, cos az cos alt, sin alt), so no further trigonometry is needed.
+    const double se = o.n;
+    const double ce = rsk_sqrt(o.l * o.l + o.m * o.m);
+    const double cinv = ce > 0.0 ? rsk_div(1.0, ce) : 0.0;
+    const double sa = ce > 0.0 ? o.l * cinv : 0.0;
+    const double ca = ce > 0.0 ? o.m * cinv : 1.0;
+    const RskRot r = rsk_basis_rotation(ravg.m, sl, cl, sb, cb, sa, ca, se, ce);
+    cs.rot[i] = r.n2;
+    cs.rot[n + i] = r.c2;
+    cs.rot[2 * n + i] = r.s2;
+  }
   __stcs(alt_az + i, o.alt);
   __stcs(alt_az + n + i, o.az);
   if (lmn) {
@@ -349,7 +369,7 @@ struct EvalThreads {
 // Minimum resident blocks per SM asked of ptxas per mode (register cap); overridable at build time for
 // tuning (-DRSK_MINB_SI=4 ...).
 #ifndef RSK_MINB_SI
-#define RSK_MINB_SI 1
+#define RSK_MINB_SI 3
 #endif
 #ifndef RSK_MINB_BANDED
 #define RSK_MINB_BANDED 1
@@ -413,11 +433,17 @@ k_eval(const __grid_constant__ EvalParams p) {
   RskRot rot;
   rot.n2 = 1.0; rot.c2 = 1.0; rot.s2 = 0.0;
   if (COH && p.polarized && __ldg(p.polarized + src)) {
-    double sl, cl, sb, cb, sa, ca, se, ce;
-    frame_trig(p.cs, src, sl, cl, sb, cb);
-    sincos(__ldg(p.alt_az + src), &se, &ce);
-    sincos(__ldg(p.alt_az + p.n + src), &sa, &ca);
-    rot = rsk_basis_rotation(p.ravg, sl, cl, sb, cb, sa, ca, se, ce);
+    if (p.cs.rot) {  // coefficients already produced by K1 for this time step
+      rot.n2 = __ldg(p.cs.rot + src);
+      rot.c2 = __ldg(p.cs.rot + p.n + src);
+      rot.s2 = __ldg(p.cs.rot + 2 * p.n + src);
+    } else {
+      double sl, cl, sb, cb, sa, ca, se, ce;
+      frame_trig(p.cs, src, sl, cl, sb, cb);
+      sincos(__ldg(p.alt_az + src), &se, &ce);
+      sincos(__ldg(p.alt_az + p.n + src), &sa, &ca);
+      rot = rsk_basis_rotation(p.ravg, sl, cl, sb, cb, sa, ca, se, ce);
+    }
   }
   const int64_t sstride = p.nf_in * p.n;  // stride between Stokes planes
 
@@ -627,6 +653,7 @@ inline int check_coords(const RskCoords* c, CoordSrc* out) {
   out->nested = c->nested;
   out->hpx_inds = c->hpx_inds;
   out->hpx_first = c->hpx_first;
+  out->rot = c->rot;
   return RSK_OK;
 }
 
@@ -729,7 +756,7 @@ int launch_eval(const EvalParams& p, int mode, cudaStream_t st) {
 extern "C" {
 
 int rsk_positions(const RskCoords* coords, int64_t n, const double* frame2icrs, const double* astrom,
-                  double* alt_az, double* pos_lmn, uint8_t* above, void* stream) {
+                  const double* ravg, double* alt_az, double* pos_lmn, uint8_t* above, void* stream) {
   CoordSrc cs;
   const int rc = check_coords(coords, &cs);
   if (rc != RSK_OK) return rc;
@@ -738,7 +765,12 @@ int rsk_positions(const RskCoords* coords, int64_t n, const double* frame2icrs, 
   if (n == 0) return RSK_OK;
   RskCtx ctx;
   rsk_pack_context(astrom, frame2icrs, reinterpret_cast<double*>(&ctx));
-  k_positions<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(cs, n, ctx, alt_az, pos_lmn, above);
+  Ravg rv = {};
+  if (ravg && cs.rot) {
+    for (int i = 0; i < 9; ++i) rv.m[i] = ravg[i];
+    rv.valid = 1;
+  }
+  k_positions<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(cs, n, ctx, rv, alt_az, pos_lmn, above);
   return launch_status();
 }
 
@@ -765,7 +797,7 @@ int rsk_positions_sweep(const RskCoords* coords, int64_t n, const double* ctx, i
 
 int rsk_healpix_lonlat(int64_t nside, int nested, const int64_t* hpx_inds, int64_t hpx_first, int64_t n, double* lon,
                        double* lat, void* stream) {
-  RskCoords c = {nullptr, nullptr, nside, nested, 0, hpx_inds, hpx_first};
+  RskCoords c = {nullptr, nullptr, nside, nested, 0, hpx_inds, hpx_first, nullptr};
   CoordSrc cs;
   if (nside <= 0) return RSK_ERR_NSIDE;
   const int rc = check_coords(&c, &cs);
@@ -825,10 +857,15 @@ int rsk_coherency(const RskSpectrum* spec, const RskCoords* coords, const double
   if (col0 < 0 || (!cols && ld_out < col0 + ncols)) return RSK_ERR_LD;
   if (!idx && !cols && ncols > spec->n) return RSK_ERR_SIZE;
   if (spec->polarized) {  // rotation needed: geometry must be present
-    rc = check_coords(coords, &p.cs);
-    if (rc != RSK_OK) return rc;
-    if (!alt_az || !ravg) return RSK_ERR_NULL;
-    for (int i = 0; i < 9; ++i) p.ravg[i] = ravg[i];
+    if (!coords) return RSK_ERR_NULL;
+    if (coords->rot) {
+      p.cs.rot = coords->rot;  // precomputed by rsk_positions: nothing else is read
+    } else {
+      rc = check_coords(coords, &p.cs);
+      if (rc != RSK_OK) return rc;
+      if (!alt_az || !ravg) return RSK_ERR_NULL;
+      for (int i = 0; i < 9; ++i) p.ravg[i] = ravg[i];
+    }
   }
   p.alt_az = alt_az;
   p.idx = idx;

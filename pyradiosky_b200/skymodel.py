@@ -355,6 +355,7 @@ class SkyModel:
         self.pos_lmn = None
         self.above_horizon = None
         self._astrom = None
+        self._rot_key = None
 
     def update_positions(self, time, telescope_location, astrom=None):
         """Calculate the altitude/azimuth positions for source components (skymodel.py:2413-2479).
@@ -388,8 +389,17 @@ class SkyModel:
             self.pos_lmn = torch.empty((3, n), dtype=torch.float64, device=self.device)
         above = torch.empty(n, dtype=torch.uint8, device=self.device)
         coords = self._coords_struct()
+        ravg = None
+        if self._n_polarized > 0:
+            # K1 already holds every sine and cosine the polarisation rotation needs, so it also writes the
+            # per-component rotation coefficients that coherency_calc will apply at this time step.
+            if self.__dict__.get("_rot") is None or self._rot.shape[1] != n:
+                self._rot = torch.empty((3, n), dtype=torch.float64, device=self.device)
+            coords.rot = self._rot.data_ptr()
+            ravg = _lib.host_array(astrometry.average_rotation_matrix(astrom).ravel())
         self._call("rsk_positions", ctypes.byref(coords), n, _lib.host_array(self._frame_to_icrs.ravel()),
-                   _lib.host_array(astrom), _lib.ptr(self.alt_az), _lib.ptr(self.pos_lmn), _lib.ptr(above))
+                   _lib.host_array(astrom), ravg, _lib.ptr(self.alt_az), _lib.ptr(self.pos_lmn), _lib.ptr(above))
+        self._rot_key = (self.alt_az.data_ptr(), self.alt_az._version) if ravg is not None else None
         self.above_horizon = above.view(torch.bool)
 
     def positions_sweep(self, times, telescope_location, astroms=None, want_lmn=False, want_mask=True):
@@ -572,6 +582,8 @@ class SkyModel:
             n_above, count_dev = int(count.item()), None
         else:
             n_above, count_dev = self.Ncomponents, count
+        if spec.polarized and self.__dict__.get("_rot_key") == (self.alt_az.data_ptr(), self.alt_az._version):
+            coords.rot = self._rot.data_ptr()  # still valid: alt_az untouched since update_positions
         self._last_n_above = n_above
         return dict(spec=spec, keep=keep, mode=mode, nf=nf, fdev=fdev, idx=idx, n_above=n_above, ravg=ravg,
                     altaz=altaz, coords=coords, count=count, count_dev=count_dev)

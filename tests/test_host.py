@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(librsk):
 def test_struct_layouts_match_header():
     from pyradiosky_b200 import _lib
 
-    assert ctypes.sizeof(_lib.RskCoords) == 48
+    assert ctypes.sizeof(_lib.RskCoords) == 56
     assert ctypes.sizeof(_lib.RskSpectrum) == 136
     assert _lib.ASTROM_LEN == 31 and _lib.CTX_LEN == 34
 
@@ -48,10 +48,10 @@ def test_argument_errors_without_gpu(librsk):
     coords = _lib.RskCoords()
     coords.nside = 0
     a = (ctypes.c_double * 31)()
-    assert librsk.rsk_positions(ctypes.byref(coords), 10, None, a, None, None, None, None) == -1  # lon/lat NULL
+    assert librsk.rsk_positions(ctypes.byref(coords), 10, None, a, None, None, None, None, None) == -1  # lon/lat NULL
     coords.nside = 12
     coords.nested = 1
-    assert librsk.rsk_positions(ctypes.byref(coords), 10, None, a, None, None, None, None) == -7  # nested needs 2^k
+    assert librsk.rsk_positions(ctypes.byref(coords), 10, None, a, None, None, None, None, None) == -7  # nested needs 2^k
     spec = _lib.RskSpectrum()
     spec.mode = 7
     spec.stokes = 8
