@@ -223,6 +223,21 @@ int rsk_coherency(const RskSpectrum* spec, const RskCoords* coords, const double
                   double* out /* complex [2][2][nf][ld_out] */, int64_t ld_out, int64_t col0,
                   void* stream);
 
+/* The same computation, written in a Hermitian-packed form for transfers over PCIe: the 2x2 coherency is
+ * Hermitian with a real diagonal, so 4 real numbers per evaluation carry it.  out is real [4][nf][ld_out] with
+ * planes (C00, C11, Re C01 = Re C10, Im C10 = -Im C01): 32 instead of 64 bytes per evaluation. */
+int rsk_coherency_packed(const RskSpectrum* spec, const RskCoords* coords, const double* alt_az,
+                         const double* ravg, const int64_t* idx, const int64_t* cols, int64_t ncols,
+                         const int64_t* ncols_dev, const double* freqs, int64_t nf,
+                         double* out /* real [4][nf][ld_out] */, int64_t ld_out, int64_t col0, void* stream);
+
+/* HOST: expand a packed slab (HOST pointer, e.g. pinned staging memory that a cudaMemcpyAsync has filled)
+ * into rows [f0_out, f0_out + nf) of the reference-layout array out = complex [2][2][nf_out][ld_out] in host
+ * memory, with nthreads threads.  Pure data movement (duplicate / negate), no arithmetic of the path. */
+int rsk_unpack_coherency_host(const double* packed /* HOST [4][nf][ld_packed] */, int64_t nf, int64_t ncols,
+                              int64_t ld_packed, double* out /* HOST complex [2][2][nf_out][ld_out] */,
+                              int64_t nf_out, int64_t f0_out, int64_t ld_out, int nthreads);
+
 /* Spline coefficients of every stored spectrum: bcoef[s][i][c] = sum_j cmat[i][j] * stokes[s][j][c].
  * cmat is the (nc x nf_in) matrix of scipy's make_interp_spline for the catalogue's freq_array and
  * freq_interp_kind (host-built, uploaded by the caller).  Time independent: run once per catalogue. */

@@ -98,6 +98,17 @@ _SIGNATURES = {
          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
          ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p],
     ),
+    "rsk_coherency_packed": (
+        ctypes.c_int,
+        [ctypes.POINTER(RskSpectrum), ctypes.POINTER(RskCoords), ctypes.c_void_p, c_double_p,
+         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+         ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p],
+    ),
+    "rsk_unpack_coherency_host": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+         ctypes.c_int64, ctypes.c_int64, ctypes.c_int],
+    ),
     "rsk_spline_coefficients": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,

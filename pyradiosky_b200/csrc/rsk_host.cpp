@@ -12,6 +12,12 @@
 #include <math.h>
 #include <string.h>
 
+#include <thread>
+#include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
 #include "../../include/rsk.h"
 #include "rsk_device.cuh"
 
@@ -392,6 +398,62 @@ int rsk_ravg(const double* astrom, double* ravg) {
   // scipy.linalg.orthogonal_procrustes(R_screwy, I)[0].T == orthogonal polar factor of R_screwy
   const M3 r = polar_factor(screwy);
   memcpy(ravg, r.a, sizeof(r.a));
+  return RSK_OK;
+}
+
+// Host-side unpack of the Hermitian-packed transfer format (see rsk.h): pure data movement, split over
+// threads by frequency row, non-temporal stores so the output does not pass through the caches.
+int rsk_unpack_coherency_host(const double* packed, int64_t nf, int64_t ncols, int64_t ld_packed, double* out,
+                              int64_t nf_out, int64_t f0_out, int64_t ld_out, int nthreads) {
+  if (nf < 0 || ncols < 0 || ld_packed < ncols || ld_out < ncols || f0_out < 0 || nf_out < f0_out + nf) return RSK_ERR_SIZE;
+  if (nf == 0 || ncols == 0) return RSK_OK;
+  if (!packed || !out) return RSK_ERR_NULL;
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 256) nthreads = 256;
+  if ((int64_t)nthreads > nf) nthreads = (int)nf;
+  auto work = [=](int t) {
+    const int64_t r0 = nf * t / nthreads, r1 = nf * (t + 1) / nthreads;
+    for (int64_t r = r0; r < r1; ++r) {
+      const double* h00 = packed + (0 * nf + r) * ld_packed;
+      const double* h11 = packed + (1 * nf + r) * ld_packed;
+      const double* re = packed + (2 * nf + r) * ld_packed;
+      const double* im = packed + (3 * nf + r) * ld_packed;
+      double* o00 = out + 2 * ((0 * nf_out + f0_out + r) * ld_out);
+      double* o01 = out + 2 * ((1 * nf_out + f0_out + r) * ld_out);
+      double* o10 = out + 2 * ((2 * nf_out + f0_out + r) * ld_out);
+      double* o11 = out + 2 * ((3 * nf_out + f0_out + r) * ld_out);
+#if defined(__SSE2__)
+      const bool aligned = (((uintptr_t)o00 | (uintptr_t)o01 | (uintptr_t)o10 | (uintptr_t)o11) & 15u) == 0;
+      if (aligned) {
+        for (int64_t c = 0; c < ncols; ++c) {
+          _mm_stream_pd(o00 + 2 * c, _mm_set_pd(0.0, h00[c]));
+          _mm_stream_pd(o01 + 2 * c, _mm_set_pd(-im[c], re[c]));
+          _mm_stream_pd(o10 + 2 * c, _mm_set_pd(im[c], re[c]));
+          _mm_stream_pd(o11 + 2 * c, _mm_set_pd(0.0, h11[c]));
+        }
+        continue;
+      }
+#endif
+      for (int64_t c = 0; c < ncols; ++c) {
+        o00[2 * c] = h00[c]; o00[2 * c + 1] = 0.0;
+        o01[2 * c] = re[c];  o01[2 * c + 1] = -im[c];
+        o10[2 * c] = re[c];  o10[2 * c + 1] = im[c];
+        o11[2 * c] = h11[c]; o11[2 * c + 1] = 0.0;
+      }
+    }
+#if defined(__SSE2__)
+    _mm_sfence();
+#endif
+  };
+  if (nthreads == 1) {
+    work(0);
+    return RSK_OK;
+  }
+  std::vector<std::thread> pool;
+  pool.reserve(nthreads - 1);
+  for (int t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
+  work(0);
+  for (auto& th : pool) th.join();
   return RSK_OK;
 }
 

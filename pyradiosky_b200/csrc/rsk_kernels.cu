@@ -322,6 +322,7 @@ struct EvalParams {
   // output
   double* out;
   int64_t ld_out, col0;
+  int packed;  // coherency epilogue, Hermitian-packed: 4 real planes (C00, C11, Re C01, Im C10) instead of 2x2 complex
 };
 
 template <bool COH>
@@ -342,7 +343,7 @@ __device__ __forceinline__ void xform(const RskRot& r, double si, double sq, dou
 
 template <bool COH>
 __device__ __forceinline__ void emit(const EvalParams& p, int f, int64_t col, const double* o) {
-  if (COH) {
+  if (COH && !p.packed) {
     const int64_t plane = (int64_t)p.nf * p.ld_out;
     double2* d = reinterpret_cast<double2*>(p.out) + (int64_t)f * p.ld_out + p.col0 + col;
     __stcs(d, make_double2(o[0], 0.0));
@@ -847,10 +848,12 @@ int rsk_polarized_mask(const double* stokes, int64_t nf_in, int64_t n, uint8_t* 
   return launch_status();
 }
 
-int rsk_coherency(const RskSpectrum* spec, const RskCoords* coords, const double* alt_az, const double* ravg,
-                  const int64_t* idx, const int64_t* cols, int64_t ncols, const int64_t* ncols_dev, const double* freqs,
-                  int64_t nf, double* out, int64_t ld_out, int64_t col0, void* stream) {
+static int coherency_impl(const RskSpectrum* spec, const RskCoords* coords, const double* alt_az, const double* ravg,
+                          const int64_t* idx, const int64_t* cols, int64_t ncols, const int64_t* ncols_dev,
+                          const double* freqs, int64_t nf, double* out, int64_t ld_out, int64_t col0, int packed,
+                          void* stream) {
   EvalParams p = {};
+  p.packed = packed;
   int rc = fill_eval_params(spec, freqs, nf, ncols, &p);
   if (rc != RSK_OK) return rc;
   if (ncols > 0 && nf > 0 && !out) return RSK_ERR_NULL;
@@ -894,6 +897,18 @@ int rsk_spline_coefficients(const double* stokes, int64_t nf_in, int64_t n, cons
     k_spline_coefficients<0><<<grid, kThreads, smem, st>>>(stokes, (int)nf_in, n, cmat, (int)nc, bcoef);
   }
   return launch_status();
+}
+
+int rsk_coherency(const RskSpectrum* spec, const RskCoords* coords, const double* alt_az, const double* ravg,
+                  const int64_t* idx, const int64_t* cols, int64_t ncols, const int64_t* ncols_dev, const double* freqs,
+                  int64_t nf, double* out, int64_t ld_out, int64_t col0, void* stream) {
+  return coherency_impl(spec, coords, alt_az, ravg, idx, cols, ncols, ncols_dev, freqs, nf, out, ld_out, col0, 0, stream);
+}
+
+int rsk_coherency_packed(const RskSpectrum* spec, const RskCoords* coords, const double* alt_az, const double* ravg,
+                         const int64_t* idx, const int64_t* cols, int64_t ncols, const int64_t* ncols_dev,
+                         const double* freqs, int64_t nf, double* out, int64_t ld_out, int64_t col0, void* stream) {
+  return coherency_impl(spec, coords, alt_az, ravg, idx, cols, ncols, ncols_dev, freqs, nf, out, ld_out, col0, 1, stream);
 }
 
 int rsk_at_frequencies(const RskSpectrum* spec, const double* freqs, int64_t nf, const int64_t* comps, int64_t ncomps,

@@ -588,7 +588,7 @@ class SkyModel:
         return dict(spec=spec, keep=keep, mode=mode, nf=nf, fdev=fdev, idx=idx, n_above=n_above, ravg=ravg,
                     altaz=altaz, coords=coords, count=count, count_dev=count_dev)
 
-    def _launch_coherency(self, plan, f0, f1, out, ld_out, col0):
+    def _launch_coherency(self, plan, f0, f1, out, ld_out, col0, packed=False):
         """Launch K2 for request channels [f0, f1) into ``out`` (complex [2][2][f1-f0][ld_out])."""
         spec, mode = plan["spec"], plan["mode"]
         nf = f1 - f0
@@ -606,7 +606,8 @@ class SkyModel:
         if events is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(torch.cuda.current_stream(self.device))
-        self._call("rsk_coherency", ctypes.byref(spec), ctypes.byref(plan["coords"]), _lib.ptr(plan["altaz"]),
+        self._call("rsk_coherency_packed" if packed else "rsk_coherency", ctypes.byref(spec),
+                   ctypes.byref(plan["coords"]), _lib.ptr(plan["altaz"]),
                    plan["ravg"], None if plan["idx"] is None else _lib.ptr(plan["idx"]), _lib.ptr(plan.get("cols")),
                    plan["n_above"], _lib.ptr(plan["count_dev"]), fptr, nf, _lib.ptr(out), ld_out, col0)
         if events is not None:
@@ -614,22 +615,39 @@ class SkyModel:
             events.append((ev0, ev1))
         spec.freq_map = saved_map
 
-    def coherency_calc_to_host(self, freqs, host_out, slab=64, freq_interp_kind="cubic"):
-        """``coherency_calc(freqs=...)`` delivered into pinned HOST memory (extension).
+    def coherency_calc_to_host(self, freqs, host_out=None, slab=64, freq_interp_kind="cubic", packed=True,
+                               nthreads=None):
+        """``coherency_calc(freqs=...)`` delivered into HOST memory (extension).
 
         The frequency axis is processed in slabs: while the kernel fills one device slab, the previous
         one streams to the host on a second CUDA stream, so HBM never holds more than two slabs and the
-        PCIe copy overlaps the compute.  ``host_out`` is a flat pinned complex128 tensor with room for
-        4 * Nfreqs * N_above values; the returned tensor is its (2, 2, Nfreqs, N_above) view.  The call
-        returns after the last copy has been queued; synchronise before reading.
+        PCIe copy overlaps the compute.
+
+        ``packed=True`` (default): a 2x2 coherency is Hermitian with a real diagonal, so the kernel writes
+        4 real numbers per evaluation (``rsk_coherency_packed``), half the bytes cross PCIe into small
+        pinned staging buffers, and ``rsk_unpack_coherency_host`` expands each slab with ``nthreads`` host
+        threads (pure data movement) into the reference-layout array while the next slab is in flight.
+        ``host_out`` may then be any C-contiguous complex128 numpy array / CPU tensor with room for
+        4 * Nfreqs * N_above values (allocated if None); the result is complete when the call returns.
+
+        ``packed=False``: the full complex array is copied; ``host_out`` must be a flat *pinned* complex128
+        tensor, and the call returns after the last copy has been queued (synchronise before reading).
+
+        Returns the (2, 2, Nfreqs, N_above) view of ``host_out``.
         """
         if self.spectral_type == "subband" and self._has_nan("stokes"):
             raise NotImplementedError("coherency_calc_to_host does not handle NaN subband spectra; use coherency_calc")
         plan = self._plan_coherency(freqs, freq_interp_kind)
         nf, n_above = plan["nf"], plan["n_above"]
         need = 4 * nf * n_above
-        if host_out.dtype != torch.complex128 or host_out.numel() < need or not host_out.is_pinned():
-            raise ValueError(f"host_out must be a pinned complex128 tensor with at least {need} elements")
+        if host_out is None:
+            host_out = torch.empty(max(need, 1), dtype=torch.complex128, pin_memory=not packed)
+        if isinstance(host_out, np.ndarray):
+            host_out = torch.from_numpy(host_out.reshape(-1))
+        if host_out.dtype != torch.complex128 or host_out.numel() < need or host_out.is_cuda:
+            raise ValueError(f"host_out must be a host complex128 buffer with at least {need} elements")
+        if not packed and not host_out.is_pinned():
+            raise ValueError("host_out must be pinned when packed=False")
         view = host_out.reshape(-1)[:need].view(2, 2, nf, n_above)
         if need == 0:
             return view
@@ -638,28 +656,78 @@ class SkyModel:
             self._copy_stream = torch.cuda.Stream(self.device)
         copy = self._copy_stream
         slab = max(1, min(slab, nf))
-        bufs = [torch.empty((2, 2, slab, n_above), dtype=torch.complex128, device=self.device) for _ in range(2)]
-        freed = [None, None]
+        if not packed:
+            bufs = [torch.empty((2, 2, slab, n_above), dtype=torch.complex128, device=self.device) for _ in range(2)]
+            freed = [None, None]
+            for i, f0 in enumerate(range(0, nf, slab)):
+                f1 = min(nf, f0 + slab)
+                buf = bufs[i % 2]
+                if freed[i % 2] is not None:
+                    main.wait_event(freed[i % 2])
+                dst = buf if f1 - f0 == slab else buf.reshape(-1)[: 4 * (f1 - f0) * n_above].view(2, 2, f1 - f0, n_above)
+                self._launch_coherency(plan, f0, f1, dst, n_above, 0)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                copy.wait_event(ready)
+                with torch.cuda.stream(copy):
+                    for a in range(2):
+                        for b in range(2):
+                            view[a, b, f0:f1].copy_(dst[a, b], non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(copy)
+                freed[i % 2] = done
+            main.wait_stream(copy)
+            for b in bufs:
+                b.record_stream(copy)
+            return view
+        # packed route: device slab (4, slab, ld) real -> pinned staging -> threaded unpack into host_out
+        import os
+
+        if nthreads is None:
+            nthreads = max(1, min(32, os.cpu_count() or 1))
+        ld = -(-n_above // 32) * 32  # 256-byte aligned rows of doubles
+        nbuf = 3  # ring of staging pairs: two slabs stay queued on the GPU while one is unpacked
+        key = (slab, ld)
+        st = self.__dict__.get("_staging")
+        if st is None or st["key"] != key:
+            st = dict(key=key,
+                      dev=[torch.empty((4, slab, ld), dtype=torch.float64, device=self.device) for _ in range(nbuf)],
+                      host=[torch.empty((4, slab, ld), dtype=torch.float64, pin_memory=True) for _ in range(nbuf)])
+            self._staging = st
+        lib = _lib.load()
+        out_ptr = view.data_ptr()
+        pending = []      # (copy-done event, host staging view, f0, nfs), oldest first
+        copied = [None] * nbuf
+
+        def drain(item):
+            ev, hbuf, f0, nfs = item
+            ev.synchronize()
+            _lib.check("rsk_unpack_coherency_host",
+                       lib.rsk_unpack_coherency_host(hbuf.data_ptr(), nfs, n_above, ld, out_ptr, nf, f0, n_above, nthreads))
+
         for i, f0 in enumerate(range(0, nf, slab)):
             f1 = min(nf, f0 + slab)
-            buf = bufs[i % 2]
-            if freed[i % 2] is not None:
-                main.wait_event(freed[i % 2])
-            dst = buf if f1 - f0 == slab else buf.reshape(-1)[: 4 * (f1 - f0) * n_above].view(2, 2, f1 - f0, n_above)
-            self._launch_coherency(plan, f0, f1, dst, n_above, 0)
+            nfs = f1 - f0
+            k = i % nbuf
+            if len(pending) == nbuf:  # host staging buffer k is about to be overwritten: unpack it first
+                drain(pending.pop(0))
+            dbuf, hbuf = st["dev"][k], st["host"][k]
+            dview = dbuf if nfs == slab else dbuf.reshape(-1)[: 4 * nfs * ld].view(4, nfs, ld)
+            hview = hbuf if nfs == slab else hbuf.reshape(-1)[: 4 * nfs * ld].view(4, nfs, ld)
+            if copied[k] is not None:
+                main.wait_event(copied[k])  # device slab k must have left for the host before it is refilled
+            self._launch_coherency(plan, f0, f1, dview, ld, 0, packed=True)
             ready = torch.cuda.Event()
             ready.record(main)
             copy.wait_event(ready)
             with torch.cuda.stream(copy):
-                for a in range(2):
-                    for b in range(2):
-                        view[a, b, f0:f1].copy_(dst[a, b], non_blocking=True)
+                hview.copy_(dview, non_blocking=True)
                 done = torch.cuda.Event()
                 done.record(copy)
-            freed[i % 2] = done
-        main.wait_stream(copy)
-        for b in bufs:
-            b.record_stream(copy)
+            copied[k] = done
+            pending.append((done, hview, f0, nfs))
+        while pending:
+            drain(pending.pop(0))
         return view
 
     # ------------------------------------------------------------------------------------------

@@ -831,3 +831,25 @@ def test_rotation_coefficients_from_k1(rsk, site):
     scale = torch.as_tensor(st[0, 0][sky.above_horizon.cpu().numpy()], device="cuda")[None, None, None, :]
     assert float(((with_k1 - recomputed).abs() / scale).max()) < 1e-14
     assert not torch.equal(with_k1, recomputed) or True
+
+
+@pytest.mark.parametrize("spectral_type", ["spectral_index", "subband", "full"])
+def test_coherency_to_host_packed_and_plain(rsk, site, spectral_type):
+    """Host delivery: Hermitian-packed slabs + threaded unpack == plain complex copy == device result."""
+    time, loc = site
+    rng = np.random.default_rng(25)
+    sky, lon, lat, st, kw = make_model(rsk, rng, spectral_type, 3003)
+    freqs = np.linspace(80e6, 220e6, 70) if spectral_type != "full" else kw["freq_array"]
+    sky.update_positions(time, loc)
+    dev = sky.coherency_calc(freqs=freqs, pad=False).cpu()
+    n_above = dev.shape[-1]
+    host = np.full(4 * freqs.size * n_above + 7, np.nan + 0j)
+    got = sky.coherency_calc_to_host(freqs, host, slab=16, packed=True, nthreads=3)
+    assert got.shape == dev.shape and torch.equal(got, dev)
+    assert np.isnan(host[-7:]).all()
+    got2 = sky.coherency_calc_to_host(freqs, None, slab=32, packed=True)
+    assert torch.equal(got2, dev)
+    pinned = torch.empty(4 * freqs.size * n_above, dtype=torch.complex128).pin_memory()
+    got3 = sky.coherency_calc_to_host(freqs, pinned, slab=16, packed=False)
+    torch.cuda.synchronize()
+    assert torch.equal(got3, dev)
