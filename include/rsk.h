@@ -121,6 +121,10 @@ typedef struct RskSpectrum {
    * column j multiplies stored channel chan_map[j].  NULL = all nf_in channels. Not with bcoef. */
   const int32_t* chan_map;      /* [nf_use] or NULL */
   int64_t nf_use;
+  /* SPECTRAL_INDEX: the power law is evaluated as exp(alpha * (ln(f / pivot) - ln(f_ref / pivot))); any
+   * pivot inside the band works (it only keeps the logarithms small).  0 = the middle requested channel.
+   * Callers that evaluate the frequency axis in slabs pass one pivot so every slab rounds identically. */
+  double pivot_hz;
 } RskSpectrum;
 
 /* ---- host-side helpers (no GPU work) -------------------------------------------------------- */

@@ -55,6 +55,7 @@ class RskSpectrum(ctypes.Structure):
         ("pband", ctypes.c_void_p),
         ("chan_map", ctypes.c_void_p),
         ("nf_use", ctypes.c_int64),
+        ("pivot_hz", ctypes.c_double),
     ]
 
 

@@ -297,6 +297,7 @@ struct EvalParams {
   const double* ppoly;
   int nb, degree;
   int y_in_smem;  // SUBBAND: each thread's stored spectrum is staged in dynamic shared memory
+  double pivot_hz;          // SPECTRAL_INDEX: > 0 fixes the log pivot
   const int32_t* chan_map;  // dense SUBBAND on a channel subset: operator column j reads stored channel chan_map[j]
   int nf_use;               // number of operator columns (== nf_in without chan_map)
   const double* bcoef;  // banded SUBBAND: spline coefficients [4][nc][n]
@@ -405,7 +406,7 @@ k_eval(const __grid_constant__ EvalParams p) {
   const int f0 = chunk * p.fchunk;
   const int nfc = min(p.fchunk, p.nf - f0);
   double pivot = 1.0;
-  if (MODE == RSK_SPECTRAL_INDEX) pivot = __ldg(p.freqs + p.nf / 2);
+  if (MODE == RSK_SPECTRAL_INDEX) pivot = p.pivot_hz > 0.0 ? p.pivot_hz : __ldg(p.freqs + p.nf / 2);
   for (int k = threadIdx.x; k < nfc; k += NT) {
     if (MODE == RSK_SPECTRAL_INDEX) {
       s_fa[k] = log(__ldg(p.freqs + f0 + k) / pivot);
@@ -686,6 +687,7 @@ int fill_eval_params(const RskSpectrum* spec, const double* freqs, int64_t nf, i
   p->degree = spec->degree;
   p->freq_map = spec->freq_map;
   p->polarized = spec->polarized;
+  p->pivot_hz = spec->pivot_hz;
   p->chan_map = spec->mode == RSK_SUBBAND ? spec->chan_map : nullptr;
   p->nf_use = (int)((spec->mode == RSK_SUBBAND && spec->chan_map) ? spec->nf_use : spec->nf_in);
   p->bcoef = spec->mode == RSK_SUBBAND ? spec->bcoef : nullptr;

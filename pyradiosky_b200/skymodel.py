@@ -568,6 +568,8 @@ class SkyModel:
             nf = fhost.size
             fdev = self._freqs_dev(fhost)
         spec = self._spectrum_struct(mode, keep, freq_interp_kind, fmap)
+        if mode == _lib.SPECTRAL_INDEX:
+            spec.pivot_hz = float(fhost[fhost.size // 2])  # one pivot for every slab of the request
         ravg = None
         altaz = None
         if spec.polarized:

@@ -34,7 +34,7 @@ def test_struct_layouts_match_header():
     from pyradiosky_b200 import _lib
 
     assert ctypes.sizeof(_lib.RskCoords) == 56
-    assert ctypes.sizeof(_lib.RskSpectrum) == 136
+    assert ctypes.sizeof(_lib.RskSpectrum) == 144
     assert _lib.ASTROM_LEN == 31 and _lib.CTX_LEN == 34
 
 
