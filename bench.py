@@ -398,7 +398,8 @@ def run_gpu(args):
         host_out.zero_()  # touch the pages outside the timed region
         e2e_evals = 0
         d2h_bytes = 0
-        e2e_threads = max(1, min(32, (os.cpu_count() or 1) // max(1, world)))
+        e2e_threads = int(os.environ.get("RSK_E2E_THREADS", max(1, min(32, (os.cpu_count() or 1) // max(1, world)))))
+        e2e_slab = int(os.environ.get("RSK_E2E_SLAB", 64))
 
         def e2e_step(k, record):
             nonlocal e2e_evals, d2h_bytes
@@ -406,7 +407,7 @@ def run_gpu(args):
             kw.update({key: t.to(dev, non_blocking=True) for key, t in host_in.items()})
             s = SkyModel(**kw, device=dev)
             s.update_positions(Time(*step_time(k)), loc)
-            view = s.coherency_calc_to_host(freqs, host_out, packed=True, nthreads=e2e_threads)
+            view = s.coherency_calc_to_host(freqs, host_out, slab=e2e_slab, packed=True, nthreads=e2e_threads)
             if record:
                 e2e_evals += view.shape[2] * view.shape[3]
                 d2h_bytes += view.shape[2] * view.shape[3] * 32  # Hermitian-packed on the wire
