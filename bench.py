@@ -398,7 +398,7 @@ def run_gpu(args):
         host_out.zero_()  # touch the pages outside the timed region
         e2e_evals = 0
         d2h_bytes = 0
-        e2e_threads = int(os.environ.get("RSK_E2E_THREADS", max(1, min(32, (os.cpu_count() or 1) // max(1, world)))))
+        e2e_threads = int(os.environ.get("RSK_E2E_THREADS", max(1, min(32, (3 * (os.cpu_count() or 1)) // (4 * max(1, world))))))
         e2e_slab = int(os.environ.get("RSK_E2E_SLAB", 64))
 
         def e2e_step(k, record):

@@ -686,7 +686,7 @@ class SkyModel:
         import os
 
         if nthreads is None:
-            nthreads = max(1, min(32, os.cpu_count() or 1))
+            nthreads = max(1, min(32, (3 * (os.cpu_count() or 1)) // 4))  # leave cores for the DMA / main thread
         ld = -(-n_above // 32) * 32  # 256-byte aligned rows of doubles
         nbuf = 3  # ring of staging pairs: two slabs stay queued on the GPU while one is unpacked
         key = (slab, ld)
