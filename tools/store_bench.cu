@@ -51,6 +51,28 @@ __global__ void __launch_bounds__(256) k_pattern(double2* out, int64_t n, int nf
   }
 }
 
+// two adjacent columns per thread, one 256-bit store per plane per frequency (STG.256)
+__global__ void __launch_bounds__(256) k_pattern_v4(double2* out, int64_t n, int nf, int fchunk, int nfchunks, int tile_fast, int ntiles) {
+  int64_t tile = blockIdx.x / nfchunks;
+  int chunk = blockIdx.x - tile * nfchunks;
+  if (tile_fast) { chunk = blockIdx.x / ntiles; tile = blockIdx.x - (int64_t)chunk * ntiles; }
+  const int f0 = chunk * fchunk;
+  const int nfc = min(fchunk, nf - f0);
+  const int64_t plane = (int64_t)nf * n;
+  const int64_t col = (tile * 256 + threadIdx.x) * 2;
+  if (col >= n) return;
+  const double a0 = -0.8 + 1e-6 * (double)(col & 1023), a1 = -0.8 + 1e-6 * (double)((col + 1) & 1023);
+#pragma unroll 4
+  for (int k = 0; k < nfc; ++k) {
+    const double v0 = exp(a0 * (0.001 * (double)(f0 + k))), v1 = exp(a1 * (0.001 * (double)(f0 + k)));
+    double2* d = out + (int64_t)(f0 + k) * n + col;
+    asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(d), "d"(v0), "d"(0.0), "d"(v1), "d"(0.0) : "memory");
+    asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(d + plane), "d"(v0), "d"(-v0), "d"(v1), "d"(-v1) : "memory");
+    asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(d + 2 * plane), "d"(v0), "d"(v0), "d"(v1), "d"(v1) : "memory");
+    asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(d + 3 * plane), "d"(v0), "d"(0.0), "d"(v1), "d"(0.0) : "memory");
+  }
+}
+
 // plane-major variant: block loops planes outermost (recompute), to see if fewer concurrent streams help
 template <int OP>
 __global__ void __launch_bounds__(256) k_plane_outer(double2* out, int64_t n, int nf, int fchunk, int nfchunks) {
@@ -106,6 +128,16 @@ int main(int argc, char** argv) {
   for (int blocks : {148 * 8, 148 * 16, 148 * 32}) {
     ms = timeit([&] { k_linear<<<blocks, 256>>>(out, total); });
     printf("linear store grid=%5d          : %7.3f ms  %7.1f GB/s\n", blocks, ms, bytes / ms / 1e6);
+  }
+  if (argc > 3 && argv[3][0] == 'v') {  // 256-bit stores, two adjacent columns per thread
+    for (int tf : {0, 1}) for (int fc : {16, 32, 64, 128}) for (int smem : {0, 72 * 1024, 112 * 1024}) {
+      const int nfchunks = (nf + fc - 1) / fc; const int64_t tiles = (n + 511) / 512;
+      if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_pattern_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      ms = timeit([&] { k_pattern_v4<<<(unsigned)(tiles * nfchunks), 256, smem>>>(out, n, nf, fc, nfchunks, tf, (int)tiles); });
+      printf("v4 pattern fchunk=%4d smem=%6d tilefast=%d : %7.3f ms  %7.1f GB/s\n", fc, smem, tf, ms, 64.0 * nf * n / ms / 1e6);
+    }
+    for (int fc : {32, 64}) for (int smem : {0, 72 * 1024}) run_pattern<1, 1>(out, n, nf, fc, 1, "cs", smem, 0);
+    return 0;
   }
   if (argc > 3 && argv[3][0] == 'w') {  // how few warps per SM still saturate the stores? (1 block of 256 per SM = 8 warps)
     for (int fc : {64, 256, 1024}) for (int smem : {0, 112 * 1024, 200 * 1024})
