@@ -135,6 +135,71 @@ _SIGNATURES = {
     ),
 }
 
+
+class RskH5Info(ctypes.Structure):
+    """``RskH5Info`` of include/rsk_io.h."""
+
+    _fields_ = [
+        ("kind", ctypes.c_int32),
+        ("type_class", ctypes.c_int32),
+        ("elem_size", ctypes.c_int32),
+        ("rank", ctypes.c_int32),
+        ("dims", ctypes.c_int64 * 8),
+        ("count", ctypes.c_int64),
+        ("layout", ctypes.c_int32),
+        ("nfilters", ctypes.c_int32),
+        ("chunk", ctypes.c_int64 * 8),
+        ("nchunks", ctypes.c_int64),
+    ]
+
+
+H5_ABSENT, H5_GROUP, H5_DATASET = 0, 1, 2
+H5_INT, H5_UINT, H5_FLOAT, H5_STRING, H5_VLEN_STRING = 0, 1, 2, 3, 4
+H5_AS_F64, H5_AS_I64 = 0, 1
+H5_ERR_NOTFOUND = -105
+
+_c_int64_p = ctypes.POINTER(ctypes.c_int64)
+
+# include/rsk_io.h: the SkyH5 (HDF5 subset) reader / writer and the file -> HBM streaming path
+_IO_SIGNATURES = {
+    "rsk_h5_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "rsk_h5_close": (None, [ctypes.c_void_p]),
+    "rsk_h5_kind": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
+    "rsk_h5_list": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int64]),
+    "rsk_h5_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(RskH5Info)]),
+    "rsk_h5_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
+    "rsk_h5_read_as": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int],
+    ),
+    "rsk_h5_read_strings": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int64]),
+    "rsk_h5_attr_string": (
+        ctypes.c_int64,
+        [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int64],
+    ),
+    "rsk_h5_attr_f64": (
+        ctypes.c_int64,
+        [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, c_double_p, ctypes.c_int64],
+    ),
+    "rsk_h5_read_device": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+         ctypes.c_int64, ctypes.c_void_p],
+    ),
+    "rsk_h5_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "rsk_h5_strerror": (ctypes.c_char_p, [ctypes.c_int]),
+    "rsk_h5w_create": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "rsk_h5w_group": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
+    "rsk_h5w_dataset": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_int64_p, ctypes.c_void_p,
+         _c_int64_p, ctypes.c_int],
+    ),
+    "rsk_h5w_attr_string": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]),
+    "rsk_h5w_close": (ctypes.c_int, [ctypes.c_void_p]),
+}
+_SIGNATURES.update(_IO_SIGNATURES)
+
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 _lib = None

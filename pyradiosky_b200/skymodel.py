@@ -26,6 +26,7 @@ Differences from the reference that a caller can observe (all documented in DESI
 
 import copy as _copy
 import ctypes
+import os
 import warnings
 
 import numpy as np
@@ -85,6 +86,8 @@ class SkyModel:
         'Jy' / 'K sr' (point) or 'Jy / sr' / 'K' (healpix).  Defaults to the Jy flavour, or to the
         unit of ``stokes`` if it is Quantity-like.
     device : torch device, default current CUDA device.
+    freq_edge_array, history, filename, extended_model_group, stokes_error, beam_amp, extra_columns :
+        Catalogue metadata carried through file I/O (skymodel.py:578-700); not used by the hot path.
     """
 
     def __init__(
@@ -109,6 +112,13 @@ class SkyModel:
         hpx_first=0,
         stokes_unit=None,
         device=None,
+        freq_edge_array=None,
+        history=None,
+        filename=None,
+        extended_model_group=None,
+        stokes_error=None,
+        beam_amp=None,
+        extra_columns=None,
     ):
         _lib.load()
         if not torch.cuda.is_available():
@@ -206,6 +216,13 @@ class SkyModel:
                    _lib.ptr(self._polarized_mask))
         self._n_polarized = int(self._polarized_mask.sum().item())
 
+        self.freq_edge_array = None if freq_edge_array is None else np.asarray(_to_hz_host(freq_edge_array)).reshape(2, -1)
+        self.history = history
+        self.filename = filename
+        self.extended_model_group = None if extended_model_group is None else np.atleast_1d(np.asarray(extended_model_group))
+        self.stokes_error = None if stokes_error is None else _as_device_f64(stokes_error, self.device)
+        self.beam_amp = None if beam_amp is None else _as_device_f64(beam_amp, self.device)
+        self.extra_columns = extra_columns
         self.freq_tol = 1.0  # Hz, skymodel.py:491
         self.time = None
         self.telescope_location = None
@@ -322,6 +339,48 @@ class SkyModel:
         new.__dict__.pop("_nan_group_cache", None)
         new.__dict__.pop("_nan_cache", None)
         return new
+
+    # ------------------------------------------------------------------------------------------
+    # file I/O (SkyH5): skymodel.py:3491-3774, :4629-4868, :4871-5029
+    # ------------------------------------------------------------------------------------------
+    @classmethod
+    def from_skyh5(cls, filename, skip_params=False, device=None, nthreads=0, **_checks):
+        """Create a :class:`SkyModel` from a SkyH5 file (skymodel.py:3768-3774).
+
+        The Stokes cube is streamed from the file into HBM by librsk (include/rsk_io.h); h5py is not
+        used.  ``run_check`` / ``check_extra`` / ``run_check_acceptability`` are accepted and ignored
+        (the UVBase validation framework is out of scope)."""
+        from . import skyh5
+
+        _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("pyradiosky_b200 needs a CUDA device; there is no CPU fallback.")
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        return cls(**skyh5.read_skyh5_params(filename, dev, skip_params=skip_params, nthreads=nthreads), device=dev)
+
+    def read_skyh5(self, filename, skip_params=False, nthreads=0, **_checks):
+        """Read a SkyH5 file into this object (skymodel.py:3491-3766)."""
+        from . import skyh5
+
+        self.__init__(**skyh5.read_skyh5_params(filename, self.device, skip_params=skip_params, nthreads=nthreads),
+                      device=self.device)
+
+    @classmethod
+    def from_file(cls, filename, filetype=None, **kwargs):
+        """``SkyModel.from_file`` (skymodel.py:4864-4868) for the formats this build reads: 'skyh5'."""
+        if filetype is None:
+            ext = os.path.splitext(os.fspath(filename))[1]
+            filetype = {".skyh5": "skyh5"}.get(ext)
+        if filetype != "skyh5":
+            raise ValueError("Only the 'skyh5' file type is supported by pyradiosky_b200; got "
+                             f"{filetype!r} for {filename}")
+        return cls.from_skyh5(filename, **kwargs)
+
+    def write_skyh5(self, filename, clobber=False, data_compression=None, **_checks):
+        """Write this object to a SkyH5 file (skymodel.py:4871-5029)."""
+        from . import skyh5
+
+        skyh5.write_skyh5(self, filename, clobber=clobber, data_compression=data_compression)
 
     # ------------------------------------------------------------------------------------------
     # coordinates

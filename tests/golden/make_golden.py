@@ -205,7 +205,44 @@ def make_known_answers():
         json.dump(ka, fh, indent=1)
 
 
+def copy_skyh5_fixtures():
+    """Two of the reference's own (small) SkyH5 test fixtures, byte for byte: data files written by h5py /
+    libhdf5 that the product's HDF5 reader (include/rsk_io.h) must read without libhdf5.
+
+    * ``gsm_icrs.skyh5`` (768-pixel HEALPix map, nside 8, 10 channels, K; chunked Stokes, old-style
+      ``lon``/``lat``/``frame`` header) -- the tutorial prints its first five Stokes I values
+      (docs/tutorial.rst:1288-1297, transcribed into ``skyh5_known_answers.json``).
+    * ``old_skyh5_point_sources.skyh5`` (50 GLEAM sources x 20 subbands, ``ra``/``dec`` in degrees) -- read by
+      tests/test_skymodel.py:4507-4522, which fixes the warnings and the subband -> full downgrade.
+    """
+    import shutil
+
+    src = "/root/reference/src/pyradiosky/data"
+    for name in ("gsm_icrs.skyh5", "old_skyh5_point_sources.skyh5"):
+        shutil.copyfile(os.path.join(src, name), os.path.join(HERE, name))
+    ka = {
+        "gsm_icrs": {
+            "cite": "docs/tutorial.rst:1288-1297",
+            "Ncomponents": 768,
+            "stokes_I_first5_K": [4704.91299386, 3864.90157423, 3933.76949248, 4258.30083558, 6520.16612935],
+            "stokes_I_first5_Jy_per_sr": [361379.47094723, 296859.06795353, 302148.74108755, 327075.65583124,
+                                          500807.17526256],
+        },
+        "old_skyh5_point_sources": {
+            "cite": "tests/test_skymodel.py:4507-4522; docs/tutorial.rst:1279-1286 (same 50 GLEAM sources)",
+            "warnings": ["Parameter skycoord not found in skyh5 file.",
+                         "No freq_edge_array in this file and frequencies are not evenly spaced"],
+            "spectral_type_after_read": "full",
+            "stokes_I_first5_Jy": [0.528997, -0.032702, 0.463359, 2.686571, 0.393777],
+            "stokes_I_first5_K_sr": [0.00298095, -0.00018428, 0.00261107, 0.01513907, 0.00221897],
+        },
+    }
+    with open(os.path.join(HERE, "skyh5_known_answers.json"), "w") as fh:
+        json.dump(ka, fh, indent=1)
+
+
 if __name__ == "__main__":
     make_sct_golden()
     make_known_answers()
+    copy_skyh5_fixtures()
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".json")))

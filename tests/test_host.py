@@ -1,5 +1,5 @@
 """Host-side logic of the product that runs without a GPU: the C-ABI library loads and exports every
-symbol of include/rsk.h, the C++ context builder agrees with the oracle, argument errors."""
+symbol of include/rsk.h and include/rsk_io.h, the C++ context builder agrees with the oracle, argument errors."""
 
 import ctypes
 import os
@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_library_exports_every_declared_symbol(librsk):
-    header = open(os.path.join(ROOT, "include", "rsk.h")).read()
+    header = open(os.path.join(ROOT, "include", "rsk.h")).read() + open(os.path.join(ROOT, "include", "rsk_io.h")).read()
     declared = set(re.findall(r"\b(rsk_[a-z_0-9]+)\s*\(", header))
     declared = {d for d in declared if not d.endswith("_") and d != "rsk_pack_context()"}
     from pyradiosky_b200 import _lib
