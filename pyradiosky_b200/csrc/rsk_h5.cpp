@@ -510,8 +510,10 @@ struct RskH5File {
 
   // Scatter one decoded chunk into a destination laid out as the (sub)array
   // [dst_lo[a], dst_lo[a] + dst_ext[a]) of the dataset, C order; elements outside it are skipped.
+  // file_off >= 0: the chunk is stored unfiltered at that file offset and needs no conversion, so long
+  // rows are pread() straight into the destination (no page faults on the mapping, one copy).
   void scatter_chunk(const Dataset& d, const ChunkRec& r, const uint8_t* data, uint8_t* dst, const int64_t* dst_lo,
-                     const int64_t* dst_ext, int conv, int out_size) {
+                     const int64_t* dst_ext, int conv, int out_size, int64_t file_off = -1) {
     const int rank = d.rank;
     if (rank == 0) {
       convert(d.dt, data, dst, conv, 1);
@@ -533,13 +535,40 @@ struct RskH5File {
         so = so * d.chunk[a] + (idx[a] - (int64_t)r.off[a]);
         dof = dof * dst_ext[a] + (idx[a] - dst_lo[a]);
       }
-      convert(d.dt, data + so * d.dt.size, dst + dof * out_size, conv, run);
+      if (file_off >= 0 && run * d.dt.size >= 16384) {
+        uint8_t* to = dst + dof * out_size;
+        int64_t left = run * d.dt.size, fo = file_off + so * d.dt.size;
+        while (left > 0) {
+          const ssize_t got = pread(fd, to, (size_t)left, (off_t)fo);
+          if (got <= 0) fail(RSK_H5_ERR_OPEN, "read failed");
+          to += got;
+          fo += got;
+          left -= got;
+        }
+      } else {
+        convert(d.dt, data + so * d.dt.size, dst + dof * out_size, conv, run);
+      }
       int a = last - 1;
       for (; a >= 0; --a) {
         if (++idx[a] < hi[a]) break;
         idx[a] = lo[a];
       }
       if (a < 0) break;
+    }
+  }
+
+  // decode (if filtered) and scatter one chunk
+  void place_chunk(const Dataset& d, const ChunkRec& r, std::vector<uint8_t>& s0, std::vector<uint8_t>& s1, uint8_t* dst,
+                   const int64_t* dst_lo, const int64_t* dst_ext, int conv, int out_size) {
+    bool filtered = false;
+    for (size_t k = 0; k < d.filters.size(); ++k) filtered = filtered || !(r.mask & (1u << k));
+    const bool identity = conv == kRaw || (conv == kF64 && d.dt.cls == RSK_H5_FLOAT && d.dt.size == 8) ||
+                          (conv == kI64 && d.dt.cls == RSK_H5_INT && d.dt.size == 8);
+    if (!filtered && identity) {
+      if ((int64_t)r.size < chunk_bytes(d)) fail(RSK_H5_ERR_FORMAT, "chunk shorter than its shape");
+      scatter_chunk(d, r, b + base + r.addr, dst, dst_lo, dst_ext, conv, out_size, (int64_t)(base + r.addr));
+    } else {
+      scatter_chunk(d, r, decode_chunk(d, r, s0, s1), dst, dst_lo, dst_ext, conv, out_size);
     }
   }
 
@@ -606,8 +635,7 @@ struct RskH5File {
       std::vector<std::vector<uint8_t>> s0((size_t)std::max(nthreads, 1)), s1((size_t)std::max(nthreads, 1));
       parallel_for((int64_t)d.chunks.size(), std::min(nthreads, 64), [&](int64_t i, int t) {
         const ChunkRec& r = d.chunks[(size_t)i];
-        const uint8_t* data = decode_chunk(d, r, s0[(size_t)t], s1[(size_t)t]);
-        scatter_chunk(d, r, data, static_cast<uint8_t*>(dst), zero, d.dims, conv, out_size);
+        place_chunk(d, r, s0[(size_t)t], s1[(size_t)t], static_cast<uint8_t*>(dst), zero, d.dims, conv, out_size);
       });
     }
   }
@@ -932,9 +960,23 @@ int rsk_h5_read_device(RskH5File* f, const char* path, int as_type, void* dst_de
         const int64_t piece = 1 << 18;
         const int64_t np = (n + piece - 1) / piece;
         uint8_t* sbuf = stage[slot];
+        const bool direct = whole.empty() && sdt.size == 8 &&
+                            ((conv == kF64 && sdt.cls == RSK_H5_FLOAT) || (conv == kI64 && sdt.cls == RSK_H5_INT));
         RskH5File::parallel_for(np, nt, [&](int64_t i, int) {
           const int64_t a = i * piece, m = std::min(piece, n - a);
-          convert(sdt, src + (e0 + a) * sdt.size, sbuf + a * 8, conv, m);
+          if (direct) {  // pread: no page faults on the mapping
+            uint8_t* to = sbuf + a * 8;
+            int64_t left = m * 8, fo = (int64_t)(f->base + d.addr) + (e0 + a) * 8;
+            while (left > 0) {
+              const ssize_t got = pread(f->fd, to, (size_t)left, (off_t)fo);
+              if (got <= 0) fail(RSK_H5_ERR_OPEN, "read failed");
+              to += got;
+              fo += got;
+              left -= got;
+            }
+          } else {
+            convert(sdt, src + (e0 + a) * sdt.size, sbuf + a * 8, conv, m);
+          }
         });
         cu(cudaMemcpyAsync(dst + e0 * 8, sbuf, (size_t)n * 8, cudaMemcpyHostToDevice, st));
         cu(cudaEventRecord(ev[slot], st));
@@ -986,8 +1028,7 @@ int rsk_h5_read_device(RskH5File* f, const char* path, int as_type, void* dst_de
         }
         RskH5File::parallel_for((int64_t)ids.size(), nt, [&](int64_t i, int t) {
           const ChunkRec& r = d.chunks[(size_t)ids[(size_t)i]];
-          const uint8_t* data = f->decode_chunk(d, r, s0[(size_t)t], s1[(size_t)t]);
-          f->scatter_chunk(d, r, data, sbuf, lo, ext, conv, 8);
+          f->place_chunk(d, r, s0[(size_t)t], s1[(size_t)t], sbuf, lo, ext, conv, 8);
         });
         cu(cudaMemcpy2DAsync(dst + ((a0 * D[1] + b0) * D[2]) * 8, (size_t)(D[1] * D[2] * 8), sbuf,
                              (size_t)(nb * D[2] * 8), (size_t)(nb * D[2] * 8), (size_t)ha, cudaMemcpyHostToDevice, st));

@@ -288,20 +288,18 @@ int rsk_h5w_dataset(RskH5Writer* w, const char* path, int type_class, int elem_s
       cbytes *= d.chunk[a];
     }
     if (cbytes > 0xffffffffll) return RSK_H5_ERR_SIZE;
-    // chunks are produced in batches by a few threads (gather + shuffle + deflate) and written in order
+    // Chunks are produced by a few threads: gather (+ shuffle + deflate).  Uncompressed chunks have a known
+    // size, so their addresses are assigned up front and every thread writes its own chunks; deflated ones
+    // are produced in batches and written in order.
     unsigned hc = std::thread::hardware_concurrency();
-    const int nt = d.gzip ? (int)std::max(1u, std::min(hc ? hc : 4u, 16u)) : 1;
-    const int64_t batch = (int64_t)nt * 4;
-    std::vector<std::vector<uint8_t>> outb((size_t)batch);
-    std::vector<int> status((size_t)batch);
-    auto make_chunk = [&](int64_t ci, std::vector<uint8_t>& ob) -> int {
+    const int nt = (int)std::max(1u, std::min(hc ? hc : 4u, 16u));
+    auto gather = [&](int64_t ci, std::vector<uint8_t>& raw) {
       int64_t c[8], rem = ci;
       for (int a = rank - 1; a >= 0; --a) {
         c[a] = rem % grid[a];
         rem /= grid[a];
       }
-      std::vector<uint8_t> raw((size_t)cbytes, 0);
-      // copy the rows of this chunk that lie inside the dataset
+      raw.assign((size_t)cbytes, 0);
       int64_t lo[8], ext[8];
       for (int a = 0; a < rank; ++a) {
         lo[a] = c[a] * d.chunk[a];
@@ -309,7 +307,7 @@ int rsk_h5w_dataset(RskH5Writer* w, const char* path, int type_class, int elem_s
       }
       int64_t idx[8] = {0};
       const int last = rank - 1;
-      for (;;) {
+      for (;;) {  // copy the rows of this chunk that lie inside the dataset
         int64_t so = 0, dof = 0;
         for (int a = 0; a < rank; ++a) {
           so = so * d.dims[a] + (lo[a] + idx[a]);
@@ -323,46 +321,69 @@ int rsk_h5w_dataset(RskH5Writer* w, const char* path, int type_class, int elem_s
         }
         if (a < 0) break;
       }
-      if (!d.gzip) {
-        ob.swap(raw);
-        return RSK_H5_OK;
-      }
-      std::vector<uint8_t> sh((size_t)cbytes);
-      const size_t ne = (size_t)(cbytes / elem_size);
-      for (size_t e = 0; e < ne; ++e)
-        for (int byte = 0; byte < elem_size; ++byte) sh[(size_t)byte * ne + e] = raw[e * elem_size + byte];
-      uLongf dl = compressBound((uLong)cbytes);
-      ob.resize(dl);
-      if (compress2(ob.data(), &dl, sh.data(), (uLong)cbytes, d.gzip) != Z_OK) return RSK_H5_ERR_FILTER;
-      ob.resize(dl);
-      return RSK_H5_OK;
     };
-    for (int64_t c0 = 0; c0 < nchunks; c0 += batch) {
-      const int64_t nb = std::min(batch, nchunks - c0);
+    auto chunk_offsets = [&](int64_t ci, uint64_t* off) {
+      int64_t rem = ci;
+      for (int a = rank - 1; a >= 0; --a) {
+        off[a] = (uint64_t)((rem % grid[a]) * d.chunk[a]);
+        rem /= grid[a];
+      }
+    };
+    auto run_parallel = [&](int64_t n, auto&& body) {
       std::atomic<int64_t> next{0};
       auto worker = [&]() {
+        std::vector<uint8_t> raw, tmp;
         for (;;) {
           const int64_t i = next.fetch_add(1);
-          if (i >= nb) break;
-          status[(size_t)i] = make_chunk(c0 + i, outb[(size_t)i]);
+          if (i >= n) break;
+          body(i, raw, tmp);
         }
       };
       std::vector<std::thread> th;
-      for (int t = 1; t < nt && t < nb; ++t) th.emplace_back(worker);
+      for (int t = 1; t < nt && t < n; ++t) th.emplace_back(worker);
       worker();
       for (auto& t : th) t.join();
-      for (int64_t i = 0; i < nb; ++i) {
-        if (status[(size_t)i] != RSK_H5_OK) return status[(size_t)i];
-        ChunkOut co;
-        co.size = (uint32_t)outb[(size_t)i].size();
-        co.addr = w->alloc(co.size);
-        int64_t rem = c0 + i;
-        for (int a = rank - 1; a >= 0; --a) {
-          co.off[a] = (uint64_t)((rem % grid[a]) * d.chunk[a]);
-          rem /= grid[a];
+    };
+    if (!d.gzip) {
+      d.chunks.resize((size_t)nchunks);
+      for (int64_t ci = 0; ci < nchunks; ++ci) {
+        d.chunks[(size_t)ci].size = (uint32_t)cbytes;
+        d.chunks[(size_t)ci].addr = w->alloc((uint64_t)cbytes);
+        chunk_offsets(ci, d.chunks[(size_t)ci].off);
+      }
+      std::atomic<bool> io_ok{true};
+      run_parallel(nchunks, [&](int64_t ci, std::vector<uint8_t>& raw, std::vector<uint8_t>&) {
+        gather(ci, raw);
+        if (!w->write_at(d.chunks[(size_t)ci].addr, raw.data(), (size_t)cbytes)) io_ok = false;
+      });
+      if (!io_ok) return RSK_H5_ERR_OPEN;
+    } else {
+      const int64_t batch = (int64_t)nt * 4;
+      std::vector<std::vector<uint8_t>> outb((size_t)batch);
+      std::vector<int> status((size_t)batch);
+      for (int64_t c0 = 0; c0 < nchunks; c0 += batch) {
+        const int64_t nb = std::min(batch, nchunks - c0);
+        run_parallel(nb, [&](int64_t i, std::vector<uint8_t>& raw, std::vector<uint8_t>& sh) {
+          gather(c0 + i, raw);
+          sh.resize((size_t)cbytes);
+          const size_t ne = (size_t)(cbytes / elem_size);
+          for (size_t e = 0; e < ne; ++e)
+            for (int byte = 0; byte < elem_size; ++byte) sh[(size_t)byte * ne + e] = raw[e * elem_size + byte];
+          std::vector<uint8_t>& ob = outb[(size_t)i];
+          uLongf dl = compressBound((uLong)cbytes);
+          ob.resize(dl);
+          status[(size_t)i] = compress2(ob.data(), &dl, sh.data(), (uLong)cbytes, d.gzip) == Z_OK ? RSK_H5_OK : RSK_H5_ERR_FILTER;
+          ob.resize(dl);
+        });
+        for (int64_t i = 0; i < nb; ++i) {
+          if (status[(size_t)i] != RSK_H5_OK) return status[(size_t)i];
+          ChunkOut co;
+          co.size = (uint32_t)outb[(size_t)i].size();
+          co.addr = w->alloc(co.size);
+          chunk_offsets(c0 + i, co.off);
+          if (!w->write_at(co.addr, outb[(size_t)i].data(), co.size)) return RSK_H5_ERR_OPEN;
+          d.chunks.push_back(co);
         }
-        if (!w->write_at(co.addr, outb[(size_t)i].data(), co.size)) return RSK_H5_ERR_OPEN;
-        d.chunks.push_back(co);
       }
     }
   }

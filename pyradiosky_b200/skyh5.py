@@ -98,6 +98,15 @@ class H5File:
 
     def read_strings(self, path):
         info = self.info(path)
+        if info.type_class == _lib.H5_STRING and info.rank > 0 and info.count > 0:
+            # fixed-length records: one raw read, then numpy's S -> U cast (a C loop; 1M names in ~30 ms)
+            raw = np.empty(int(info.count), dtype=f"S{info.elem_size}")
+            _h5check(self._lib, self._h, "rsk_h5_read",
+                     self._lib.rsk_h5_read(self._h, path.encode(), raw.ctypes.data, raw.nbytes, 0))
+            try:
+                return raw.astype(str).reshape(tuple(info.dims[: info.rank]))
+            except UnicodeDecodeError:  # non-ASCII names: decode as UTF-8 like the reference (skymodel.py:297)
+                return np.char.decode(raw, "utf8").reshape(tuple(info.dims[: info.rank]))
         need = _h5check(self._lib, self._h, "rsk_h5_read_strings",
                         self._lib.rsk_h5_read_strings(self._h, path.encode(), None, 0))
         buf = ctypes.create_string_buffer(max(int(need), 1))
