@@ -127,6 +127,22 @@ typedef struct RskSpectrum {
   double pivot_hz;
 } RskSpectrum;
 
+/* Antenna response for rsk_apparent_coherency.  Jones matrices are [feed][basis] with
+ * basis 0 = the zenith-angle direction and basis 1 = the azimuth direction, i.e. the (theta_hat, phi_hat)
+ * basis the output of coherency_calc is expressed in. */
+#define RSK_BEAM_JONES 0        /* caller-evaluated matrices (any beam model), one per column and frequency */
+#define RSK_BEAM_SHORT_DIPOLE 1 /* analytic short dipole, feeds (north, east), as the reference's golden test
+                                 * arranges pyuvdata's ShortDipoleBeam (tests/test_skymodel.py:1446-1462):
+                                 * J = [[cos za sin az, cos az], [cos za cos az, -sin az]], all frequencies */
+#define RSK_BEAM_UNIFORM 2      /* J = identity: the output equals rsk_coherency's */
+typedef struct RskBeam {
+  int32_t type;
+  int32_t reserved;
+  const double* jones1; /* RSK_BEAM_JONES: complex [2][2][nf][ld_jones], column k = output column k */
+  const double* jones2; /* second antenna of the baseline, or NULL = jones1 */
+  int64_t ld_jones;
+} RskBeam;
+
 /* ---- host-side helpers (no GPU work) -------------------------------------------------------- */
 
 int rsk_version(void);
@@ -234,6 +250,18 @@ int rsk_coherency_packed(const RskSpectrum* spec, const RskCoords* coords, const
                          const double* ravg, const int64_t* idx, const int64_t* cols, int64_t ncols,
                          const int64_t* ncols_dev, const double* freqs, int64_t nf,
                          double* out /* real [4][nf][ld_out] */, int64_t ld_out, int64_t col0, void* stream);
+
+/* The consumer of coherency_calc fused into the same kernel: the apparent (instrumental) coherency
+ * A = J1 C J2^H of every (above-horizon component, frequency), i.e. the contraction
+ * einsum("ab...,bc...,dc...->ad...", J, C, conj(J)) that pyuvsim and the reference's golden test
+ * (tests/test_skymodel.py:1464-1466) apply to the output of coherency_calc.  The Az/El coherency is never
+ * written: per evaluation the kernel reads the Jones matrices (RSK_BEAM_JONES: 64 or 128 bytes) and writes
+ * 64 bytes.  Arguments as rsk_coherency; alt_az is required for RSK_BEAM_SHORT_DIPOLE. */
+int rsk_apparent_coherency(const RskSpectrum* spec, const RskCoords* coords, const double* alt_az,
+                            const double* ravg, const int64_t* idx, const int64_t* cols, int64_t ncols,
+                            const int64_t* ncols_dev, const double* freqs, int64_t nf, const RskBeam* beam,
+                            double* out /* complex [2][2][nf][ld_out] */, int64_t ld_out, int64_t col0,
+                            void* stream);
 
 /* HOST: expand a packed slab (HOST pointer, e.g. pinned staging memory that a cudaMemcpyAsync has filled)
  * into rows [f0_out, f0_out + nf) of the reference-layout array out = complex [2][2][nf_out][ld_out] in host

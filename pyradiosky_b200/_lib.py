@@ -59,6 +59,18 @@ class RskSpectrum(ctypes.Structure):
     ]
 
 
+class RskBeam(ctypes.Structure):
+    _fields_ = [
+        ("type", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("jones1", ctypes.c_void_p),
+        ("jones2", ctypes.c_void_p),
+        ("ld_jones", ctypes.c_int64),
+    ]
+
+
+BEAM_JONES, BEAM_SHORT_DIPOLE, BEAM_UNIFORM = 0, 1, 2
+
 _SIGNATURES = {
     "rsk_version": (ctypes.c_int, []),
     "rsk_strerror": (ctypes.c_char_p, [ctypes.c_int]),
@@ -104,6 +116,12 @@ _SIGNATURES = {
         [ctypes.POINTER(RskSpectrum), ctypes.POINTER(RskCoords), ctypes.c_void_p, c_double_p,
          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
          ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p],
+    ),
+    "rsk_apparent_coherency": (
+        ctypes.c_int,
+        [ctypes.POINTER(RskSpectrum), ctypes.POINTER(RskCoords), ctypes.c_void_p, c_double_p,
+         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+         ctypes.POINTER(RskBeam), ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p],
     ),
     "rsk_unpack_coherency_host": (
         ctypes.c_int,

@@ -324,11 +324,36 @@ struct EvalParams {
   double* out;
   int64_t ld_out, col0;
   int packed;  // coherency epilogue, Hermitian-packed: 4 real planes (C00, C11, Re C01, Im C10) instead of 2x2 complex
+  // apparent-coherency epilogue (EPI == 2): A = J1 C J2^H
+  int beam_type;
+  const double2* jones1;  // [2][2][nf][ld_jones]
+  const double2* jones2;  // or NULL = jones1
+  int64_t ld_jones;
 };
 
-template <bool COH>
+// epilogues of k_eval
+constexpr int kEpiStokes = 0;     // (4, nf, n) Stokes                      -- at_frequencies
+constexpr int kEpiCoherency = 1;  // (2, 2, nf, ld) coherency, or packed   -- coherency_calc
+constexpr int kEpiApparent = 2;   // (2, 2, nf, ld) J1 C J2^H               -- coherency_calc + beam Jones
+
+// Jones matrices of one output column, [feed][basis] row-major (basis 0 = zenith-angle direction, 1 = azimuth
+// direction: the basis the Az/El coherency is expressed in).
+struct JonesPair {
+  double2 a[4];  // antenna 1
+  double2 b[4];  // antenna 2
+};
+
+__device__ __forceinline__ double2 cmul(double2 x, double2 y) {
+  return make_double2(x.x * y.x - x.y * y.y, x.x * y.y + x.y * y.x);
+}
+__device__ __forceinline__ double2 cmulc(double2 x, double2 y) {  // x * conj(y)
+  return make_double2(x.x * y.x + x.y * y.y, x.y * y.x - x.x * y.y);
+}
+__device__ __forceinline__ double2 cadd(double2 x, double2 y) { return make_double2(x.x + y.x, x.y + y.y); }
+
+template <int EPI>
 __device__ __forceinline__ void xform(const RskRot& r, double si, double sq, double su, double sv, double* o) {
-  if (COH) {
+  if (EPI != kEpiStokes) {
     // R^T C R of skymodel.py:2704-2710 in Stokes terms, then utils.py:42-57 halves
     const double qr = r.c2 * sq - r.s2 * su;
     const double ur = r.s2 * sq + r.c2 * su;
@@ -342,9 +367,42 @@ __device__ __forceinline__ void xform(const RskRot& r, double si, double sq, dou
   }
 }
 
-template <bool COH>
-__device__ __forceinline__ void emit(const EvalParams& p, int f, int64_t col, const double* o) {
-  if (COH && !p.packed) {
+template <int EPI>
+__device__ __forceinline__ void emit(const EvalParams& p, int f, int64_t col, const double* o, const JonesPair& jp) {
+  if (EPI == kEpiApparent) {
+    // A = J1 C J2^H with C = [[o0, o2 - i o3], [o2 + i o3, o1]]: the contraction
+    // einsum("ab...,bc...,dc...->ad...", J, C, conj(J)) of tests/test_skymodel.py:1464-1466
+    const int64_t plane = (int64_t)p.nf * p.ld_out;
+    double2 j1[4], j2[4];
+    if (p.beam_type == RSK_BEAM_JONES) {
+      const int64_t jplane = (int64_t)p.nf * p.ld_jones;
+      const double2* a = p.jones1 + (int64_t)f * p.ld_jones + col;
+      const double2* b = (p.jones2 ? p.jones2 : p.jones1) + (int64_t)f * p.ld_jones + col;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) j1[k] = __ldcs(a + k * jplane);
+      if (p.jones2) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) j2[k] = __ldcs(b + k * jplane);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) j2[k] = j1[k];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { j1[k] = jp.a[k]; j2[k] = jp.b[k]; }
+    }
+    const double2 c00 = make_double2(o[0], 0.0), c11 = make_double2(o[1], 0.0);
+    const double2 c01 = make_double2(o[2], -o[3]), c10 = make_double2(o[2], o[3]);
+    const double2 t00 = cadd(cmul(j1[0], c00), cmul(j1[1], c10));
+    const double2 t01 = cadd(cmul(j1[0], c01), cmul(j1[1], c11));
+    const double2 t10 = cadd(cmul(j1[2], c00), cmul(j1[3], c10));
+    const double2 t11 = cadd(cmul(j1[2], c01), cmul(j1[3], c11));
+    double2* d = reinterpret_cast<double2*>(p.out) + (int64_t)f * p.ld_out + p.col0 + col;
+    __stcs(d, cadd(cmulc(t00, j2[0]), cmulc(t01, j2[1])));
+    __stcs(d + plane, cadd(cmulc(t00, j2[2]), cmulc(t01, j2[3])));
+    __stcs(d + 2 * plane, cadd(cmulc(t10, j2[0]), cmulc(t11, j2[1])));
+    __stcs(d + 3 * plane, cadd(cmulc(t10, j2[2]), cmulc(t11, j2[3])));
+  } else if (EPI == kEpiCoherency && !p.packed) {
     const int64_t plane = (int64_t)p.nf * p.ld_out;
     double2* d = reinterpret_cast<double2*>(p.out) + (int64_t)f * p.ld_out + p.col0 + col;
     __stcs(d, make_double2(o[0], 0.0));
@@ -376,15 +434,17 @@ struct EvalThreads {
 #ifndef RSK_MINB_BANDED
 #define RSK_MINB_BANDED 1
 #endif
-template <int MODE>
+template <int MODE, int EPI>
 struct EvalMinBlocks {
-  static constexpr int value = (MODE == RSK_SPECTRAL_INDEX) ? RSK_MINB_SI : (MODE == 4 ? RSK_MINB_BANDED : 1);
+  // the Jones epilogue needs ~140 registers: cap at 128 (two 256-thread blocks per SM), not at 80
+  static constexpr int value = EPI == 2 ? (EvalThreads<MODE>::value == 256 ? 2 : 1) : (MODE == RSK_SPECTRAL_INDEX) ? RSK_MINB_SI : (MODE == 4 ? RSK_MINB_BANDED : 1);
 };
 
-template <int MODE, bool COH>
-__global__ void __launch_bounds__(EvalThreads<MODE>::value, EvalMinBlocks<MODE>::value)
+template <int MODE, int EPI>
+__global__ void __launch_bounds__(EvalThreads<MODE>::value, EvalMinBlocks<MODE, EPI>::value)
 k_eval(const __grid_constant__ EvalParams p) {
   constexpr int NT = EvalThreads<MODE>::value;
+  constexpr bool COH = EPI != kEpiStokes;
   extern __shared__ double s_dyn[];    // SUBBAND: [4 * nf_in][NT] stored Stokes of this block's columns
   __shared__ double s_fa[kMaxFChunk];  // SPECTRAL_INDEX: ln(f / pivot); SUBBAND: local coordinate u
   __shared__ int s_iv[kMaxFChunk];     // SUBBAND: break interval; FULL: stored channel
@@ -447,16 +507,34 @@ k_eval(const __grid_constant__ EvalParams p) {
       rot = rsk_basis_rotation(p.ravg, sl, cl, sb, cb, sa, ca, se, ce);
     }
   }
+  // analytic beams: one Jones matrix per column, frequency independent
+  JonesPair jp;
+  if (EPI == kEpiApparent && p.beam_type != RSK_BEAM_JONES) {
+    double ja[4] = {1.0, 0.0, 0.0, 1.0};  // RSK_BEAM_UNIFORM
+    if (p.beam_type == RSK_BEAM_SHORT_DIPOLE) {
+      // pyuvdata ShortDipoleBeam.efield_eval as the reference's golden test arranges it
+      // (tests/test_skymodel.py:1446-1462): feeds (north, east) x basis (zenith angle, azimuth)
+      double se, ce, sa, ca;
+      sincos(__ldg(p.alt_az + src), &se, &ce);
+      sincos(__ldg(p.alt_az + p.n + src), &sa, &ca);
+      ja[0] = se * sa;  // cos(za) sin(az)
+      ja[1] = ca;
+      ja[2] = se * ca;  // cos(za) cos(az)
+      ja[3] = -sa;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) jp.a[k] = jp.b[k] = make_double2(ja[k], 0.0);
+  }
   const int64_t sstride = p.nf_in * p.n;  // stride between Stokes planes
 
   if (MODE == RSK_FLAT || MODE == RSK_SPECTRAL_INDEX) {
     double b[4];
-    xform<COH>(rot, __ldg(p.stokes + src), __ldg(p.stokes + sstride + src), __ldg(p.stokes + 2 * sstride + src),
+    xform<EPI>(rot, __ldg(p.stokes + src), __ldg(p.stokes + sstride + src), __ldg(p.stokes + 2 * sstride + src),
                __ldg(p.stokes + 3 * sstride + src), b);
     if (MODE == RSK_FLAT) {
       // skymodel.py:2369-2372: np.repeat along the frequency axis
 #pragma unroll 4
-      for (int k = 0; k < nfc; ++k) emit<COH>(p, f0 + k, col, b);
+      for (int k = 0; k < nfc; ++k) emit<EPI>(p, f0 + k, col, b, jp);
     } else {
       // skymodel.py:2159-2163: stokes * (f / f_ref) ** alpha = stokes * exp(alpha (ln f/pivot - ln f_ref/pivot))
       const double alpha = __ldg(p.alpha + src);
@@ -465,7 +543,7 @@ k_eval(const __grid_constant__ EvalParams p) {
       for (int k = 0; k < nfc; ++k) {
         const double pw = exp(alpha * (s_fa[k] - l0));
         const double o[4] = {b[0] * pw, b[1] * pw, b[2] * pw, b[3] * pw};
-        emit<COH>(p, f0 + k, col, o);
+        emit<EPI>(p, f0 + k, col, o, jp);
       }
     }
   } else if (MODE == RSK_SUBBAND) {
@@ -515,13 +593,13 @@ k_eval(const __grid_constant__ EvalParams p) {
           }
         }
 #pragma unroll
-        for (int a = 0; a < 4; ++a) xform<COH>(rot, acc[a][0], acc[a][1], acc[a][2], acc[a][3], cf[a]);
+        for (int a = 0; a < 4; ++a) xform<EPI>(rot, acc[a][0], acc[a][1], acc[a][2], acc[a][3], cf[a]);
       }
       const double u = s_fa[k];
       double o[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) o[q] = fma(fma(fma(cf[3][q], u, cf[2][q]), u, cf[1][q]), u, cf[0][q]);
-      emit<COH>(p, f0 + k, col, o);
+      emit<EPI>(p, f0 + k, col, o, jp);
     }
   } else if (MODE == kSubbandBanded) {
     // skymodel.py:2362-2368 from precomputed spline coefficients: a change of break interval costs
@@ -554,14 +632,14 @@ k_eval(const __grid_constant__ EvalParams p) {
               }
             }
           }
-          xform<COH>(rot, acc[0], acc[1], acc[2], acc[3], cf[a]);
+          xform<EPI>(rot, acc[0], acc[1], acc[2], acc[3], cf[a]);
         }
       }
       const double u = s_fa[k];
       double o[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) o[q] = fma(fma(fma(cf[3][q], u, cf[2][q]), u, cf[1][q]), u, cf[0][q]);
-      emit<COH>(p, f0 + k, col, o);
+      emit<EPI>(p, f0 + k, col, o, jp);
     }
   } else {  // RSK_FULL: stored Stokes, skymodel.py:2165-2181 subset + utils.py:42-57
 #pragma unroll 4
@@ -569,8 +647,8 @@ k_eval(const __grid_constant__ EvalParams p) {
       const double* y = p.stokes + (int64_t)s_iv[k] * p.n + src;
       const double y0 = __ldcs(y), y1 = __ldcs(y + sstride), y2 = __ldcs(y + 2 * sstride), y3 = __ldcs(y + 3 * sstride);
       double o[4];
-      xform<COH>(rot, y0, y1, y2, y3, o);
-      emit<COH>(p, f0 + k, col, o);
+      xform<EPI>(rot, y0, y1, y2, y3, o);
+      emit<EPI>(p, f0 + k, col, o, jp);
     }
   }
 }
@@ -715,7 +793,7 @@ int fill_eval_params(const RskSpectrum* spec, const double* freqs, int64_t nf, i
   return RSK_OK;
 }
 
-template <int MODE, bool COH>
+template <int MODE, int EPI>
 int launch_one(const EvalParams& p, dim3 grid, int smem, cudaStream_t st) {
   constexpr int NT = EvalThreads<MODE>::value;
   if (MODE == RSK_SUBBAND && p.y_in_smem) {
@@ -723,14 +801,14 @@ int launch_one(const EvalParams& p, dim3 grid, int smem, cudaStream_t st) {
     if (need > smem) smem = need;
   }
   if (smem > 48 * 1024) {
-    const cudaError_t e = cudaFuncSetAttribute(k_eval<MODE, COH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const cudaError_t e = cudaFuncSetAttribute(k_eval<MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
   }
-  k_eval<MODE, COH><<<grid, NT, smem, st>>>(p);
+  k_eval<MODE, EPI><<<grid, NT, smem, st>>>(p);
   return launch_status();
 }
 
-template <bool COH>
+template <int EPI>
 int launch_eval(const EvalParams& p, int mode, cudaStream_t st) {
   if (p.ncols == 0 || p.nf == 0) return RSK_OK;
   const int64_t nblocks = p.ntiles * p.nfchunks;
@@ -741,12 +819,12 @@ int launch_eval(const EvalParams& p, int mode, cudaStream_t st) {
   if (smem < 0) smem = 0;
   if (smem > kMaxDynSmem) smem = kMaxDynSmem;
   switch (mode) {
-    case RSK_FLAT: return launch_one<RSK_FLAT, COH>(p, grid, smem, st);
-    case RSK_SPECTRAL_INDEX: return launch_one<RSK_SPECTRAL_INDEX, COH>(p, grid, smem, st);
+    case RSK_FLAT: return launch_one<RSK_FLAT, EPI>(p, grid, smem, st);
+    case RSK_SPECTRAL_INDEX: return launch_one<RSK_SPECTRAL_INDEX, EPI>(p, grid, smem, st);
     case RSK_SUBBAND:
-      if (p.bcoef) return launch_one<kSubbandBanded, COH>(p, grid, smem, st);
-      return launch_one<RSK_SUBBAND, COH>(p, grid, smem, st);
-    case RSK_FULL: return launch_one<RSK_FULL, COH>(p, grid, smem, st);
+      if (p.bcoef) return launch_one<kSubbandBanded, EPI>(p, grid, smem, st);
+      return launch_one<RSK_SUBBAND, EPI>(p, grid, smem, st);
+    case RSK_FULL: return launch_one<RSK_FULL, EPI>(p, grid, smem, st);
     default: return RSK_ERR_MODE;
   }
 }
@@ -853,9 +931,22 @@ int rsk_polarized_mask(const double* stokes, int64_t nf_in, int64_t n, uint8_t* 
 static int coherency_impl(const RskSpectrum* spec, const RskCoords* coords, const double* alt_az, const double* ravg,
                           const int64_t* idx, const int64_t* cols, int64_t ncols, const int64_t* ncols_dev,
                           const double* freqs, int64_t nf, double* out, int64_t ld_out, int64_t col0, int packed,
-                          void* stream) {
+                          void* stream, const RskBeam* beam = nullptr) {
   EvalParams p = {};
   p.packed = packed;
+  if (beam) {
+    if (beam->type < RSK_BEAM_JONES || beam->type > RSK_BEAM_UNIFORM) return RSK_ERR_MODE;
+    p.beam_type = beam->type;
+    if (beam->type == RSK_BEAM_JONES) {
+      if (ncols > 0 && nf > 0 && !beam->jones1) return RSK_ERR_NULL;
+      if (cols ? beam->ld_jones < 1 : beam->ld_jones < ncols) return RSK_ERR_LD;
+      p.jones1 = reinterpret_cast<const double2*>(beam->jones1);
+      p.jones2 = reinterpret_cast<const double2*>(beam->jones2);
+      p.ld_jones = beam->ld_jones;
+    } else if (beam->type == RSK_BEAM_SHORT_DIPOLE && !alt_az) {
+      return RSK_ERR_NULL;
+    }
+  }
   int rc = fill_eval_params(spec, freqs, nf, ncols, &p);
   if (rc != RSK_OK) return rc;
   if (ncols > 0 && nf > 0 && !out) return RSK_ERR_NULL;
@@ -879,7 +970,8 @@ static int coherency_impl(const RskSpectrum* spec, const RskCoords* coords, cons
   p.out = out;
   p.ld_out = ld_out;
   p.col0 = col0;
-  return launch_eval<true>(p, spec->mode, (cudaStream_t)stream);
+  if (beam) return launch_eval<kEpiApparent>(p, spec->mode, (cudaStream_t)stream);
+  return launch_eval<kEpiCoherency>(p, spec->mode, (cudaStream_t)stream);
 }
 
 int rsk_spline_coefficients(const double* stokes, int64_t nf_in, int64_t n, const double* cmat, int64_t nc,
@@ -913,6 +1005,15 @@ int rsk_coherency_packed(const RskSpectrum* spec, const RskCoords* coords, const
   return coherency_impl(spec, coords, alt_az, ravg, idx, cols, ncols, ncols_dev, freqs, nf, out, ld_out, col0, 1, stream);
 }
 
+int rsk_apparent_coherency(const RskSpectrum* spec, const RskCoords* coords, const double* alt_az, const double* ravg,
+                            const int64_t* idx, const int64_t* cols, int64_t ncols, const int64_t* ncols_dev,
+                            const double* freqs, int64_t nf, const RskBeam* beam, double* out, int64_t ld_out,
+                            int64_t col0, void* stream) {
+  if (!beam) return RSK_ERR_NULL;
+  return coherency_impl(spec, coords, alt_az, ravg, idx, cols, ncols, ncols_dev, freqs, nf, out, ld_out, col0, 0, stream,
+                        beam);
+}
+
 int rsk_at_frequencies(const RskSpectrum* spec, const double* freqs, int64_t nf, const int64_t* comps, int64_t ncomps,
                        double* stokes_out, void* stream) {
   EvalParams p = {};
@@ -927,7 +1028,7 @@ int rsk_at_frequencies(const RskSpectrum* spec, const double* freqs, int64_t nf,
   p.out = stokes_out;
   p.ld_out = spec->n;
   p.col0 = 0;
-  return launch_eval<false>(p, spec->mode, (cudaStream_t)stream);
+  return launch_eval<kEpiStokes>(p, spec->mode, (cudaStream_t)stream);
 }
 
 int rsk_stokes_to_coherency(const double* stokes, int64_t nf, int64_t n, double* out, void* stream) {

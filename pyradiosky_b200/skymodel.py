@@ -603,6 +603,60 @@ class SkyModel:
             return out
         return out[..., col0:col0 + ncols]
 
+    def apparent_coherency_calc(self, beam="short_dipole", jones=None, jones2=None, freqs=None,
+                                freq_interp_kind="cubic", pad=True):
+        """Instrumental coherency ``J1 C J2^H`` of every above-horizon component (extension).
+
+        What a simulator does with the result of :meth:`coherency_calc` -- the contraction
+        ``einsum("ab...,bc...,dc...->ad...", J, C, conj(J))`` of tests/test_skymodel.py:1464-1466 -- fused
+        into the same kernel, so the Az/El coherency itself is never written to HBM.
+
+        Parameters
+        ----------
+        beam : {'short_dipole', 'uniform'} -- analytic responses evaluated in the kernel from ``alt_az``
+            ('short_dipole': feeds (north, east), as that test arranges pyuvdata's ShortDipoleBeam).
+            Ignored when ``jones`` is given.
+        jones, jones2 : complex128 CUDA tensors (2, 2, Nfreqs, N_above), optional
+            Caller-evaluated Jones matrices [feed][basis] (basis 0 = zenith-angle direction, 1 = azimuth
+            direction) for the above-horizon components in catalogue order; ``jones2`` is the second
+            antenna of the baseline (default: the same antenna).
+        freqs, freq_interp_kind : as :meth:`coherency_calc`.
+
+        Returns
+        -------
+        torch.Tensor complex128 (2, 2, Nfreqs, N_above).
+        """
+        if freqs is not None and self._nan_groups(_to_hz_host(freqs), freq_interp_kind, "clip"):
+            raise NotImplementedError("apparent_coherency_calc does not handle NaN subband spectra")
+        plan = self._plan_coherency(freqs, freq_interp_kind, need_count=True)
+        nf, ncols = plan["nf"], plan["n_above"]
+        b = _lib.RskBeam()
+        if jones is not None:
+            for name, j in (("jones", jones), ("jones2", jones2)):
+                if j is None:
+                    continue
+                if (not isinstance(j, torch.Tensor) or j.dtype != torch.complex128 or not j.is_cuda
+                        or tuple(j.shape) != (2, 2, nf, ncols) or not j.is_contiguous()):
+                    raise ValueError(f"{name} must be a contiguous complex128 CUDA tensor of shape (2, 2, {nf}, {ncols})")
+            b.type = _lib.BEAM_JONES
+            b.jones1 = jones.data_ptr()
+            b.jones2 = None if jones2 is None else jones2.data_ptr()
+            b.ld_jones = max(ncols, 1)
+        else:
+            kinds = {"short_dipole": _lib.BEAM_SHORT_DIPOLE, "uniform": _lib.BEAM_UNIFORM}
+            if beam not in kinds:
+                raise ValueError("beam must be 'short_dipole' or 'uniform' (or pass jones=)")
+            b.type = kinds[beam]
+            if b.type == _lib.BEAM_SHORT_DIPOLE:
+                if self.alt_az is None:
+                    raise ValueError("update_positions must be called before apparent_coherency_calc")
+                plan["altaz"] = self.alt_az
+        plan["beam"] = b
+        ld = -(-ncols // 16) * 16 if pad else ncols
+        out = torch.empty((2, 2, nf, max(ld, 0)), dtype=torch.complex128, device=self.device)
+        self._launch_coherency(plan, 0, nf, out, ld, 0)
+        return out if ld == ncols else out[..., :ncols]
+
     def _plan_coherency(self, freqs, freq_interp_kind, need_count=True):
         """Everything coherency_calc needs before the launch: horizon compaction, spectral description,
         R_avg.  With ``need_count`` one device->host read (the above-horizon count) is made, after all
@@ -667,10 +721,13 @@ class SkyModel:
         if events is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(torch.cuda.current_stream(self.device))
-        self._call("rsk_coherency_packed" if packed else "rsk_coherency", ctypes.byref(spec),
-                   ctypes.byref(plan["coords"]), _lib.ptr(plan["altaz"]),
-                   plan["ravg"], None if plan["idx"] is None else _lib.ptr(plan["idx"]), _lib.ptr(plan.get("cols")),
-                   plan["n_above"], _lib.ptr(plan["count_dev"]), fptr, nf, _lib.ptr(out), ld_out, col0)
+        head = (ctypes.byref(spec), ctypes.byref(plan["coords"]), _lib.ptr(plan["altaz"]), plan["ravg"],
+                None if plan["idx"] is None else _lib.ptr(plan["idx"]), _lib.ptr(plan.get("cols")), plan["n_above"],
+                _lib.ptr(plan["count_dev"]), fptr, nf)
+        if plan.get("beam") is not None:
+            self._call("rsk_apparent_coherency", *head, ctypes.byref(plan["beam"]), _lib.ptr(out), ld_out, col0)
+        else:
+            self._call("rsk_coherency_packed" if packed else "rsk_coherency", *head, _lib.ptr(out), ld_out, col0)
         if events is not None:
             ev1.record(torch.cuda.current_stream(self.device))
             events.append((ev0, ev1))

@@ -853,3 +853,100 @@ def test_coherency_to_host_packed_and_plain(rsk, site, spectral_type):
     got3 = sky.coherency_calc_to_host(freqs, pinned, slab=16, packed=False)
     torch.cuda.synchronize()
     assert torch.equal(got3, dev)
+
+
+# ---------------------------------------------------------------------------------------------------
+# N4: the consumer J1 C J2^H fused into K2 (rsk_apparent_coherency)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("eop", [(0.0, 0.0), (-0.47, 0.32)])
+def test_golden_instrumental_coherency_in_kernel(rsk, known_answers, eop):
+    """tests/test_skymodel.py:1388-1508 with the short-dipole Jones applied inside the kernel: the golden
+    2x2x5 matrix comes straight out of apparent_coherency_calc."""
+    pv = known_answers["polarized_visibilities"]
+    loc = rsk.EarthLocation.from_dms((-30, 43, 17.5), (21, 25, 41.9), 1073.0)
+    t0 = rsk.Time(2457082.5, 0.0, dut1=eop[0], yp=eop[1] * E.DAS2R)
+    ra, dec = E.altaz_to_icrs(np.pi / 2, 0.0, rsk.astrometry.astrom_context(t0, loc))
+    sky = rsk.SkyModel(name="icrs_zen", ra=ra, dec=dec, stokes=np.array(pv["stokes"], float), spectral_type="flat")
+    inst = np.zeros((2, 2, 5), complex)
+    for ti, off in enumerate(pv["time_offsets_hr"]):
+        sky.update_positions(t0 + off / 24.0, loc)
+        inst[:, :, ti] = sky.apparent_coherency_calc(beam="short_dipole").cpu().numpy()[:, :, 0, 0]
+    expect = np.array(pv["expected_re"]) + 1j * np.array(pv["expected_im"])
+    assert np.allclose(inst, expect)  # the reference's own tolerance (rtol 1e-5)
+
+
+def _apparent_reference(coh, j1, j2):
+    return np.einsum("ab...,bc...,dc...->ad...", j1, coh, np.conj(j2))
+
+
+@pytest.mark.parametrize("spectral_type", ["flat", "spectral_index", "subband", "full"])
+def test_apparent_coherency_matches_einsum(rsk, site, spectral_type):
+    """Random complex Jones matrices for two different antennas: kernel == einsum applied to the kernel's own
+    (oracle-checked) coherency_calc output, and == the oracle chain end to end."""
+    time, loc = site
+    rng = np.random.default_rng(41)
+    n, nf = 3000, 24
+    ra, dec = random_sky(rng, n)
+    freqs = np.linspace(110e6, 190e6, nf)
+    kw = {}
+    if spectral_type == "flat":
+        st = polarized_stokes(rng, n)
+    elif spectral_type == "spectral_index":
+        st = polarized_stokes(rng, n)
+        kw = dict(reference_frequency=np.full(n, 150e6), spectral_index=rng.normal(-0.8, 0.2, n))
+    elif spectral_type == "subband":
+        base = polarized_stokes(rng, n)
+        fa = GLEAM_BANDS[:12]
+        st = base * (fa[None, :, None] / 150e6) ** -0.7 * (1 + 0.02 * rng.normal(size=(1, 12, n)))
+        kw = dict(freq_array=fa)
+    else:
+        st = polarized_stokes(rng, n, nf) * (1 + 0.1 * rng.normal(size=(4, nf, n)))
+        kw = dict(freq_array=freqs)
+    sky = rsk.SkyModel(ra=ra, dec=dec, stokes=st, spectral_type=spectral_type, **kw)
+    sky.update_positions(time, loc)
+    coh = sky.coherency_calc(freqs=freqs).cpu().numpy()
+    na = coh.shape[-1]
+    j1 = rng.normal(size=(2, 2, nf, na)) + 1j * rng.normal(size=(2, 2, nf, na))
+    j2 = rng.normal(size=(2, 2, nf, na)) + 1j * rng.normal(size=(2, 2, nf, na))
+    t1, t2 = torch.as_tensor(j1).cuda(), torch.as_tensor(j2).cuda()
+    scale = np.abs(coh[0, 0] + coh[1, 1])[None, None].real  # Stokes I
+    for pad in (True, False):
+        got = sky.apparent_coherency_calc(jones=t1, jones2=t2, freqs=freqs, pad=pad).cpu().numpy()
+        ref = _apparent_reference(coh, j1, j2)
+        assert got.shape == ref.shape
+        assert np.max(np.abs(got - ref) / scale) < 1e-11  # |J| ~ 2: a few more roundings than C itself
+    got = sky.apparent_coherency_calc(jones=t1, freqs=freqs).cpu().numpy()
+    assert np.max(np.abs(got - _apparent_reference(coh, j1, j1)) / scale) < 1e-11
+    # one antenna: the result is Hermitian
+    assert np.max(np.abs(got - np.conj(np.swapaxes(got, 0, 1))) / scale) < 1e-12
+    # uniform beam = identity Jones = coherency_calc itself, bit for bit
+    assert np.array_equal(sky.apparent_coherency_calc(beam="uniform", freqs=freqs).cpu().numpy(), coh)
+    # analytic dipole == the same Jones passed as arrays
+    alt, az = sky.alt_az.cpu().numpy()[:, sky.above_horizon.cpu().numpy()]
+    jd = S.short_dipole_jones(az, np.pi / 2 - alt)
+    jd = np.flip(np.flip(np.transpose(jd, (1, 0, 2)), axis=1), axis=0)  # test_skymodel.py:1456-1462
+    jd = np.ascontiguousarray(np.broadcast_to(jd[:, :, None, :], (2, 2, nf, na))).astype(complex)
+    a = sky.apparent_coherency_calc(beam="short_dipole", freqs=freqs).cpu().numpy()
+    assert np.max(np.abs(a - _apparent_reference(coh, jd, jd)) / scale) < 1e-12
+
+
+def test_apparent_coherency_argument_errors(rsk, site):
+    time, loc = site
+    rng = np.random.default_rng(2)
+    ra, dec = random_sky(rng, 50)
+    sky = rsk.SkyModel(ra=ra, dec=dec, stokes=polarized_stokes(rng, 50), spectral_type="flat")
+    sky.update_positions(time, loc)
+    with pytest.raises(ValueError, match="beam must be"):
+        sky.apparent_coherency_calc(beam="airy")
+    with pytest.raises(ValueError, match="jones must be a contiguous complex128 CUDA tensor"):
+        sky.apparent_coherency_calc(jones=torch.zeros((2, 2, 1, 3), dtype=torch.complex128, device="cuda"))
+    from pyradiosky_b200 import _lib
+
+    lib = _lib.load()
+    spec = _lib.RskSpectrum()
+    spec.mode = 0; spec.stokes = 8; spec.nf_in = 1; spec.n = 4
+    b = _lib.RskBeam(); b.type = 9
+    assert lib.rsk_apparent_coherency(ctypes.byref(spec), None, None, None, None, None, 4, None, None, 1,
+                                      ctypes.byref(b), None, 4, 0, None) == -3
+    assert lib.rsk_apparent_coherency(ctypes.byref(spec), None, None, None, None, None, 4, None, None, 1,
+                                      None, None, 4, 0, None) == -1

@@ -110,6 +110,20 @@ def main():
                    spectral_index=np.clip(rng.normal(-0.8, 0.2, n), -2, 1), reference_frequency=np.full(n, 200e6))
     rec("k_eval<spectral_index,stokes> at_frequencies 300k x 1024", timeit(lambda: sky.at_frequencies(freqs, inplace=False)),
         32 * n * nf, "32 B/eval written")
+    # N4: coherency_calc + Jones contraction fused (apparent coherency), analytic and caller-supplied beams
+    sky.update_positions(t0, loc)
+    na = int(sky.above_horizon.sum().item())
+    rec("k_eval<spectral_index,apparent> short dipole 300k x 1024",
+        timeit(lambda: sky.apparent_coherency_calc(beam="short_dipole", freqs=freqs)), 64 * na * nf, "64 B/eval written")
+    j1 = torch.randn((2, 2, nf, na), dtype=torch.complex128, device="cuda")
+    rec("k_eval<spectral_index,apparent> Jones arrays, one antenna 300k x 1024",
+        timeit(lambda: sky.apparent_coherency_calc(jones=j1, freqs=freqs)), 128 * na * nf, "64 B/eval read + 64 written")
+    j2 = torch.randn((2, 2, nf, na), dtype=torch.complex128, device="cuda")
+    rec("k_eval<spectral_index,apparent> Jones arrays, two antennas 300k x 1024",
+        timeit(lambda: sky.apparent_coherency_calc(jones=j1, jones2=j2, freqs=freqs)), 192 * na * nf,
+        "128 B/eval read + 64 written")
+    del j1, j2
+    torch.cuda.empty_cache()
     full = sky.at_frequencies(freqs, inplace=False)  # (4, 1024, 300k) = 9.8 GB, spectral_type 'full'
     full.update_positions(t0, loc)
     n_above = int(full.above_horizon.sum().item())
