@@ -48,12 +48,12 @@ __device__ __forceinline__ void frame_trig(const CoordSrc& c, int64_t i, double&
     const int64_t pix = c.hpx_inds ? __ldg(c.hpx_inds + i) : c.hpx_first + i;
     double z, st, phi;
     rsk_hpx_center(c.nside, c.nested, pix, z, st, phi);
-    sincos(phi, &sl, &cl);
+    rsk_sincos(phi, &sl, &cl);
     sb = z;
     cb = st;
   } else {
-    sincos(__ldg(c.lon + i), &sl, &cl);
-    sincos(__ldg(c.lat + i), &sb, &cb);
+    rsk_sincos(__ldg(c.lon + i), &sl, &cl);
+    rsk_sincos(__ldg(c.lat + i), &sb, &cb);
   }
 }
 
@@ -688,20 +688,59 @@ __global__ void __launch_bounds__(kThreads) k_spline_coefficients(const double* 
   }
 }
 
-// K4: Jy <-> K (sr) in place
-__global__ void __launch_bounds__(kThreads) k_convert_units(double* __restrict__ stokes, const int64_t nf,
-                                                            const int64_t n, const double* __restrict__ fchan,
-                                                            const double* __restrict__ fcomp, const int to_jansky) {
-  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (e >= nf * n) return;
-  const int64_t f = e / n, c = e - f * n;
-  const double nu = fcomp ? __ldg(fcomp + c) : __ldg(fchan + f);
-  // utils.jy_to_ksr (utils.py:105-126): astropy brightness_temperature with a 1 sr beam, CODATA 2018
+// K4: Jy <-> K (sr) in place.  utils.jy_to_ksr (utils.py:105-126): astropy brightness_temperature with a
+// 1 sr beam, CODATA 2018; every operation individually rounded so the factor is bit-identical to numpy's.
+__device__ __forceinline__ double jy_to_ksr_factor(double nu, int to_jansky) {
   double k = __ddiv_rn(1e-26 * (299792458.0 * 299792458.0), __dmul_rn(2.0 * 1.380649e-23, __dmul_rn(nu, nu)));
   if (to_jansky) k = __ddiv_rn(1.0, k);  // skymodel.py:1559-1571
+  return k;
+}
+
+constexpr int kConvChunk = 32;  // channels per block
+
+// Block = 256 threads x 2 adjacent components x kConvChunk channels.  The per-channel factors are computed once
+// per block (shared memory), the per-component ones once per thread; VEC = 128-bit accesses (n even).
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads) k_convert_units(double* __restrict__ stokes, const int64_t nf,
+                                                            const int64_t n, const double* __restrict__ fchan,
+                                                            const double* __restrict__ fcomp, const int to_jansky,
+                                                            const int nfchunks) {
+  __shared__ double s_k[kConvChunk];
+  const int64_t tile = blockIdx.x / nfchunks;
+  const int chunk = (int)(blockIdx.x - tile * nfchunks);
+  const int64_t f0 = (int64_t)chunk * kConvChunk;
+  const int nfc = (int)min((int64_t)kConvChunk, nf - f0);
+  if (!fcomp) {
+    if (threadIdx.x < nfc) s_k[threadIdx.x] = jy_to_ksr_factor(__ldg(fchan + f0 + threadIdx.x), to_jansky);
+    __syncthreads();
+  }
+  const int64_t c0 = (tile * kThreads + threadIdx.x) * 2;
+  if (c0 >= n) return;
+  const bool two = c0 + 1 < n;
+  double k0 = 0.0, k1 = 0.0;
+  if (fcomp) {
+    k0 = jy_to_ksr_factor(__ldg(fcomp + c0), to_jansky);
+    k1 = two ? jy_to_ksr_factor(__ldg(fcomp + c0 + 1), to_jansky) : 0.0;
+  }
   const int64_t plane = nf * n;
+#pragma unroll 2
+  for (int k = 0; k < nfc; ++k) {
+    if (!fcomp) k0 = k1 = s_k[k];
+    double* row = stokes + (f0 + k) * n + c0;
 #pragma unroll
-  for (int s = 0; s < 4; ++s) stokes[s * plane + e] = __dmul_rn(stokes[s * plane + e], k);
+    for (int s = 0; s < 4; ++s) {
+      double* q = row + s * plane;
+      if (VEC) {
+        double2 v = *reinterpret_cast<double2*>(q);
+        v.x = __dmul_rn(v.x, k0);
+        v.y = __dmul_rn(v.y, k1);
+        *reinterpret_cast<double2*>(q) = v;
+      } else {
+        q[0] = __dmul_rn(q[0], k0);
+        if (two) q[1] = __dmul_rn(q[1], k1);
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1048,10 +1087,17 @@ int rsk_convert_units(double* stokes, int64_t nf, int64_t n, const double* freq_
   if (nf < 0 || n < 0) return RSK_ERR_SIZE;
   if (nf == 0 || n == 0) return RSK_OK;
   if (!stokes || (!freq_per_chan && !freq_per_comp)) return RSK_ERR_NULL;
-  const int64_t total = nf * n;
-  if ((total + kThreads - 1) / kThreads > 0x7fffffffll) return RSK_ERR_SIZE;
-  k_convert_units<<<blocks_for(total), kThreads, 0, (cudaStream_t)stream>>>(stokes, nf, n, freq_per_chan, freq_per_comp,
-                                                                          to_jansky);
+  const int64_t ntiles = (n + 2 * kThreads - 1) / (2 * kThreads);
+  const int64_t nfchunks = (nf + kConvChunk - 1) / kConvChunk;
+  if (ntiles * nfchunks > 0x7fffffffll) return RSK_ERR_SIZE;
+  const bool vec = (n % 2 == 0) && (reinterpret_cast<uintptr_t>(stokes) & 15u) == 0;
+  const unsigned grid = (unsigned)(ntiles * nfchunks);
+  if (vec)
+    k_convert_units<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(stokes, nf, n, freq_per_chan, freq_per_comp,
+                                                                        to_jansky, (int)nfchunks);
+  else
+    k_convert_units<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(stokes, nf, n, freq_per_chan, freq_per_comp,
+                                                                         to_jansky, (int)nfchunks);
   return launch_status();
 }
 

@@ -950,3 +950,22 @@ def test_apparent_coherency_argument_errors(rsk, site):
                                       ctypes.byref(b), None, 4, 0, None) == -3
     assert lib.rsk_apparent_coherency(ctypes.byref(spec), None, None, None, None, None, 4, None, None, 1,
                                       None, None, 4, 0, None) == -1
+
+
+@pytest.mark.parametrize("n,nf", [(1238, 70), (2, 33), (513, 1), (512, 32), (1, 5)])
+def test_unit_conversion_launch_shapes(rsk, n, nf):
+    """K4 bit-exact for even/odd component counts (128-bit and scalar paths) and several channel chunks."""
+    rng = np.random.default_rng(n + nf)
+    st = rng.normal(size=(4, nf, n))
+    fa = np.linspace(50e6, 250e6, nf) if nf > 1 else np.array([150e6])
+    sky = rsk.SkyModel(ra=np.zeros(n), dec=np.zeros(n), stokes=st, spectral_type="full", freq_array=fa)
+    sky.jansky_to_kelvin()
+    want = S.jansky_to_kelvin(st, "full", freq_array=fa)
+    assert np.array_equal(sky.stokes.cpu().numpy(), want)
+    sky.kelvin_to_jansky()
+    assert np.array_equal(sky.stokes.cpu().numpy(), S.kelvin_to_jansky(want, "full", freq_array=fa))
+    rf = rng.uniform(1e8, 2e8, n)
+    sky = rsk.SkyModel(ra=np.zeros(n), dec=np.zeros(n), stokes=st[:, :1], spectral_type="spectral_index",
+                       reference_frequency=rf, spectral_index=np.full(n, -0.8))
+    sky.jansky_to_kelvin()
+    assert np.array_equal(sky.stokes.cpu().numpy(), S.jansky_to_kelvin(st[:, :1], "spectral_index", reference_frequency=rf))
