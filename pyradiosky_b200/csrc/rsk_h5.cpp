@@ -13,7 +13,10 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -106,6 +109,90 @@ void convert(const Dtype& dt, const uint8_t* src, void* dst, int conv, int64_t n
 #undef RSK_LOAD
 }
 
+// A few worker threads that live for one file -> HBM read (creating threads per slab costs more than
+// filling the slab).  run(count, body) calls body(i, thread) for i in [0, count) and returns when all are done;
+// the first exception is re-thrown on the caller's thread.
+class Pool {
+ public:
+  explicit Pool(int n) : n_(n < 1 ? 1 : n) {
+    for (int t = 1; t < n_; ++t) th_.emplace_back([this, t] { loop(t); });
+  }
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> g(m_);
+      stop_ = true;
+      ++gen_;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  int size() const { return n_; }
+  void run(int64_t count, const std::function<void(int64_t, int)>& body) {
+    {
+      std::lock_guard<std::mutex> g(m_);
+      job_ = &body;
+      count_ = count;
+      next_.store(0);
+      pending_ = n_ - 1;
+      err_ = H5Err{0, ""};
+      ++gen_;
+    }
+    cv_.notify_all();
+    work(0);
+    std::unique_lock<std::mutex> g(m_);
+    done_.wait(g, [this] { return pending_ == 0; });
+    job_ = nullptr;
+    if (err_.code != 0) throw err_;
+  }
+
+ private:
+  void work(int t) {
+    try {
+      for (;;) {
+        const int64_t i = next_.fetch_add(1);
+        if (i >= count_) break;
+        (*job_)(i, t);
+      }
+    } catch (const H5Err& e) {
+      std::lock_guard<std::mutex> g(m_);
+      if (err_.code == 0) err_ = e;
+      next_.store(count_);
+    } catch (const std::exception& e) {
+      std::lock_guard<std::mutex> g(m_);
+      if (err_.code == 0) err_ = H5Err{RSK_H5_ERR_FORMAT, e.what()};
+      next_.store(count_);
+    }
+  }
+  void loop(int t) {
+    int seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> g(m_);
+        cv_.wait(g, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+      }
+      work(t);
+      {
+        std::lock_guard<std::mutex> g(m_);
+        --pending_;
+      }
+      done_.notify_one();
+    }
+  }
+  int n_;
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int64_t, int)>* job_ = nullptr;
+  int64_t count_ = 0;
+  std::atomic<int64_t> next_{0};
+  int pending_ = 0;
+  int gen_ = 0;
+  bool stop_ = false;
+  H5Err err_{0, ""};
+};
+
 }  // namespace
 
 struct RskH5File {
@@ -117,10 +204,34 @@ struct RskH5File {
   std::string err;
   std::map<uint64_t, std::map<std::string, uint64_t>> group_cache;
   std::map<std::string, Dataset> ds_cache;
+  // pinned staging ring of rsk_h5_read_device, kept for the life of the handle (pinning memory is slow)
+  static constexpr int kRing = 3;
+  uint8_t* stage[kRing] = {nullptr, nullptr, nullptr};
+  cudaEvent_t stage_ev[kRing] = {nullptr, nullptr, nullptr};
+  size_t stage_bytes = 0;
 
   ~RskH5File() {
+    for (int i = 0; i < kRing; ++i) {
+      if (stage_ev[i]) cudaEventDestroy(stage_ev[i]);
+      if (stage[i]) cudaFreeHost(stage[i]);
+    }
     if (b) munmap(const_cast<uint8_t*>(b), size);
     if (fd >= 0) close(fd);
+  }
+
+  void ensure_stage(size_t bytes) {
+    if (bytes <= stage_bytes && stage[0]) return;
+    for (int i = 0; i < kRing; ++i) {
+      if (stage[i]) cudaFreeHost(stage[i]);
+      stage[i] = nullptr;
+    }
+    stage_bytes = 0;
+    for (int i = 0; i < kRing; ++i) {
+      cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&stage[i]), bytes, cudaHostAllocDefault);
+      if (e == cudaSuccess && !stage_ev[i]) e = cudaEventCreateWithFlags(&stage_ev[i], cudaEventDisableTiming);
+      if (e != cudaSuccess) throw H5Err{(int)e, cudaGetErrorString(e)};
+    }
+    stage_bytes = bytes;
   }
 
   const uint8_t* at(uint64_t addr, uint64_t len) const {
@@ -906,18 +1017,10 @@ int64_t rsk_h5_attr_f64(RskH5File* f, const char* path, const char* attr, double
 // single pitched copy.  Three pinned slabs rotate: while one is in flight the next is being filled.
 int rsk_h5_read_device(RskH5File* f, const char* path, int as_type, void* dst_device, int64_t count, int nthreads,
                        int64_t slab_bytes, void* stream) {
-  constexpr int kRing = 3;
-  uint8_t* stage[kRing] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev[kRing] = {nullptr, nullptr, nullptr};
+  constexpr int kRing = RskH5File::kRing;
+  if (!f) return RSK_H5_ERR_NULL;
   bool used[kRing] = {false, false, false};
   cudaStream_t st = (cudaStream_t)stream;
-  auto cleanup = [&]() {
-    for (int i = 0; i < kRing; ++i) {
-      if (used[i]) cudaEventSynchronize(ev[i]);
-      if (ev[i]) cudaEventDestroy(ev[i]);
-      if (stage[i]) cudaFreeHost(stage[i]);
-    }
-  };
   const int64_t rc = guarded(f, [&]() -> int64_t {
     if (as_type != RSK_H5_AS_F64 && as_type != RSK_H5_AS_I64) fail(RSK_H5_ERR_TYPE, "bad destination type");
     const int conv = as_type == RSK_H5_AS_F64 ? kF64 : kI64;
@@ -926,8 +1029,11 @@ int rsk_h5_read_device(RskH5File* f, const char* path, int as_type, void* dst_de
     if (d.count == 0) return RSK_H5_OK;
     if (!dst_device) return RSK_H5_ERR_NULL;
     if (d.dt.cls == RSK_H5_STRING || d.dt.cls == RSK_H5_VLEN_STRING) fail(RSK_H5_ERR_TYPE, "string dataset");
-    const int nt = default_threads(nthreads);
-    if (slab_bytes <= 0) slab_bytes = 32ll << 20;
+    const int nt = d.count < (1 << 17) ? 1 : default_threads(nthreads);  // small columns: no helpers
+    Pool pool(nt);
+    if (slab_bytes <= 0) slab_bytes = 64ll << 20;
+    uint8_t** stage = f->stage;
+    cudaEvent_t* ev = f->stage_ev;
     auto cu = [&](cudaError_t e) {
       if (e != cudaSuccess) throw H5Err{(int)e, cudaGetErrorString(e)};
     };
@@ -949,10 +1055,7 @@ int rsk_h5_read_device(RskH5File* f, const char* path, int as_type, void* dst_de
       }
       const int64_t per = std::max<int64_t>(slab_bytes / 8, 1);
       const int64_t cap_elems = std::min(per, d.count);
-      for (int i = 0; i < kRing; ++i) {
-        cu(cudaHostAlloc(reinterpret_cast<void**>(&stage[i]), (size_t)cap_elems * 8, cudaHostAllocDefault));
-        cu(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
-      }
+      f->ensure_stage((size_t)cap_elems * 8);
       int slot = 0;
       for (int64_t e0 = 0; e0 < d.count; e0 += cap_elems, slot = (slot + 1) % kRing) {
         const int64_t n = std::min(cap_elems, d.count - e0);
@@ -962,7 +1065,7 @@ int rsk_h5_read_device(RskH5File* f, const char* path, int as_type, void* dst_de
         uint8_t* sbuf = stage[slot];
         const bool direct = whole.empty() && sdt.size == 8 &&
                             ((conv == kF64 && sdt.cls == RSK_H5_FLOAT) || (conv == kI64 && sdt.cls == RSK_H5_INT));
-        RskH5File::parallel_for(np, nt, [&](int64_t i, int) {
+        pool.run(np, [&](int64_t i, int) {
           const int64_t a = i * piece, m = std::min(piece, n - a);
           if (direct) {  // pread: no page faults on the mapping
             uint8_t* to = sbuf + a * 8;
@@ -1002,10 +1105,7 @@ int rsk_h5_read_device(RskH5File* f, const char* path, int as_type, void* dst_de
     const int64_t row_bytes = Cc[0] * Cc[1] * D[2] * 8;  // one chunk-row along B, all of C, Cc[0] planes
     const int64_t rows_per_slab = std::max<int64_t>(1, std::min(nB, slab_bytes / std::max<int64_t>(row_bytes, 1)));
     const size_t stage_bytes = (size_t)(rows_per_slab * row_bytes);
-    for (int i = 0; i < kRing; ++i) {
-      cu(cudaHostAlloc(reinterpret_cast<void**>(&stage[i]), stage_bytes, cudaHostAllocDefault));
-      cu(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
-    }
+    f->ensure_stage(stage_bytes);
     std::vector<std::vector<uint8_t>> s0((size_t)nt), s1((size_t)nt);
     int slot = 0;
     for (int64_t ia = 0; ia < nA; ++ia) {
@@ -1026,7 +1126,7 @@ int rsk_h5_read_device(RskH5File* f, const char* path, int as_type, void* dst_de
           lo[a] = lo3[3 - d.rank + a];
           ext[a] = ext3[3 - d.rank + a];
         }
-        RskH5File::parallel_for((int64_t)ids.size(), nt, [&](int64_t i, int t) {
+        pool.run((int64_t)ids.size(), [&](int64_t i, int t) {
           const ChunkRec& r = d.chunks[(size_t)ids[(size_t)i]];
           f->place_chunk(d, r, s0[(size_t)t], s1[(size_t)t], sbuf, lo, ext, conv, 8);
         });
@@ -1038,7 +1138,8 @@ int rsk_h5_read_device(RskH5File* f, const char* path, int as_type, void* dst_de
     }
     return RSK_H5_OK;
   });
-  cleanup();
+  for (int i = 0; i < kRing; ++i)  // the staging memory is reused by the next call: wait for its copies
+    if (used[i]) cudaEventSynchronize(f->stage_ev[i]);
   return (int)rc;
 }
 

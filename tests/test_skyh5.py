@@ -482,3 +482,130 @@ def test_loaded_healpix_model_runs_the_hot_path():
     got = coh.cpu().numpy()
     assert got.shape == ref.shape
     assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(stokes[0]))
+
+
+# ---------------------------------------------------------------------------------------------------
+# The reference's own GLEAM NaN-handling tests (tests/test_skymodel.py:3630-3846), on the same 50 GLEAM
+# sources (old_skyh5_point_sources.skyh5 holds the catalogue the reference reads from gleam_50srcs.vot).
+# ---------------------------------------------------------------------------------------------------
+def _gleam_subband_model():
+    from pyradiosky_b200 import SkyModel
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        full = SkyModel.from_file(OLD_POINT)
+    return SkyModel(name=full.name, ra=full.lon, dec=full.lat, frame="icrs", stokes=full.stokes.clone(),
+                    spectral_type="subband", freq_array=full.freq_array)
+
+
+def _collect_warnings(fn):
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        out = fn()
+    return out, [str(w.message) for w in rec]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nan_handling", ["propagate", "interp", "clip"])
+def test_reference_gleam_nan_handling(nan_handling):
+    """tests/test_skymodel.py:3630-3793, line for line."""
+    skyobj = _gleam_subband_model()
+    interp_freqs = np.asarray([77, 154, 225]) * 1e6
+    skyobj_interp = skyobj.at_frequencies(interp_freqs, inplace=False)
+
+    skyobj2 = skyobj.copy()
+    nan = float("nan")
+    skyobj2.stokes[0, 0:2, 0] = nan  # no low freq support
+    skyobj2.stokes[0, 10:11, 1] = nan  # missing freqs in middle
+    skyobj2.stokes[0, -2:, 2] = nan  # no high freq support
+    skyobj2.stokes[0, :, 3] = nan  # all NaNs
+    skyobj2.stokes[0, 1:-2, 4] = nan  # only 2 good freqs
+    skyobj2.stokes[0, 0, 5] = nan  # no low or high frequency support
+    skyobj2.stokes[0, -1, 5] = nan
+    skyobj2.stokes[0, 1:, 6] = nan  # only 1 good freqs
+
+    message = ["Some Stokes values are NaNs."]
+    if nan_handling == "propagate":
+        message[0] += " All output Stokes values for sources with any NaN values will be NaN."
+    else:
+        message[0] += " Interpolating using the non-NaN values only."
+        message.extend([
+            "1 components had all NaN Stokes values. ",
+            "3 components had all NaN Stokes values above one or more of the requested frequencies. ",
+            "2 components had all NaN Stokes values below one or more of the requested frequencies. ",
+            "1 components had too few non-NaN Stokes values for chosen interpolation. Using linear "
+            "interpolation for these components instead.",
+        ])
+        if nan_handling == "interp":
+            message[2] += "The Stokes for these components at these frequencies will be NaN."
+            message[3] += "The Stokes for these components at these frequencies will be NaN."
+        else:
+            message[2] += "Using the Stokes value at the highest frequency "
+            message[3] += "Using the Stokes value at the lowest frequency "
+    message[0] += " You can change the way NaNs are handled using the `nan_handling` keyword."
+    skyobj2_interp, texts = _collect_warnings(
+        lambda: skyobj2.at_frequencies(interp_freqs, inplace=False, nan_handling=nan_handling))
+    for m in message:
+        assert any(t.startswith(m) for t in texts), (m, texts)
+
+    got = skyobj2_interp.stokes.cpu().numpy()
+    ref = skyobj_interp.stokes.cpu().numpy()
+    orig = skyobj.stokes.cpu().numpy()
+    if nan_handling == "propagate":
+        assert np.all(np.isnan(got[:, :, 0:7]))
+        assert np.all(~np.isnan(got[:, :, 7:]))
+    elif nan_handling == "interp":
+        assert np.all(np.isnan(got[:, 0, 0]))
+        assert np.allclose(got[:, 1:, 0], ref[:, 1:, 0], atol=1e-5, rtol=0)
+        assert np.all(np.isnan(got[:, 2, 2]))
+        assert np.allclose(got[:, 0:-1, 2], ref[:, 0:-1, 2], atol=1e-5, rtol=0)
+        assert np.all(np.isnan(got[:, 0, 5]))
+        assert np.all(np.isnan(got[:, 2, 5]))
+        assert np.allclose(got[:, 1, 2], ref[:, 1, 2], atol=1e-5, rtol=0)
+    else:  # clip
+        assert np.all(~np.isnan(got[:, :, 0:3]))
+        assert np.allclose(got[:, 0, 0], orig[:, 2, 0])
+        assert np.allclose(got[:, 1:, 0], ref[:, 1:, 0], atol=1e-5, rtol=0)
+        assert np.allclose(got[:, 2, 2], orig[:, -3, 2])
+        assert np.allclose(got[:, 0:-1, 2], ref[:, 0:-1, 2], atol=1e-5, rtol=0)
+        assert np.allclose(got[:, 0, 5], orig[:, 1, 5])
+        assert np.allclose(got[:, 2, 5], orig[:, -2, 5])
+        assert np.allclose(got[:, 1, 5], ref[:, 1, 5], atol=1e-5, rtol=0)
+    if nan_handling in ["interp", "clip"]:
+        assert np.all(np.isnan(got[:, :, 3]))
+        assert np.all(~np.isnan(got[:, :, 1]))
+        assert np.allclose(got[:, 0, 1], ref[:, 0, 1])
+        assert np.allclose(got[:, 2, 1], ref[:, 2, 1])
+        assert not np.allclose(got[:, 1, 1], ref[:, 1, 1])
+        assert np.allclose(got[:, 1, 1], ref[:, 1, 1], atol=1e-2, rtol=0)
+        assert np.all(~np.isnan(got[:, :, 4]))
+        assert np.allclose(got[:, 0, 4], ref[:, 0, 4], atol=1e-1, rtol=0)
+        assert np.allclose(got[:, 2, 4], ref[:, 2, 4], atol=1e-1, rtol=0)
+        assert not np.allclose(got[:, 1, 4], ref[:, 1, 4], atol=1e-1, rtol=0)
+        assert np.allclose(got[:, 1, 4], ref[:, 1, 4], atol=2e-1, rtol=0)
+    assert np.allclose(got[:, :, 7:], ref[:, :, 7:])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nan_handling", ["propagate", "interp", "clip"])
+def test_reference_gleam_nan_handling_allsrc(nan_handling):
+    """tests/test_skymodel.py:3796-3846."""
+    skyobj = _gleam_subband_model()
+    interp_freqs = np.asarray([77, 154, 225]) * 1e6
+    ref = skyobj.at_frequencies(interp_freqs, inplace=False).stokes.cpu().numpy()
+    skyobj2 = skyobj.copy()
+    skyobj2.stokes[0, 10:11, :] = float("nan")
+    out, texts = _collect_warnings(lambda: skyobj2.at_frequencies(interp_freqs, inplace=False, nan_handling=nan_handling))
+    head = "Some Stokes values are NaNs." + (
+        " All output Stokes values for sources with any NaN values will be NaN." if nan_handling == "propagate"
+        else " Interpolating using the non-NaN values only.")
+    assert any(t.startswith(head) for t in texts), texts
+    got = out.stokes.cpu().numpy()
+    if nan_handling == "propagate":
+        assert np.all(np.isnan(got))
+    else:
+        assert np.all(~np.isnan(got))
+        assert np.allclose(got[:, 0, :], ref[:, 0, :], atol=1e-5, rtol=0)
+        assert np.allclose(got[:, 2, :], ref[:, 2, :], atol=1e-5, rtol=0)
+        assert not np.allclose(got[:, 1, :], ref[:, 1, :], atol=1e-5, rtol=0)
+        assert np.allclose(got[:, 1, :], ref[:, 1, :], atol=1e-1, rtol=0)
