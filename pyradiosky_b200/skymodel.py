@@ -914,7 +914,9 @@ class SkyModel:
                          if g["use"].size and np.max(fhost) > np.max(self.freq_array[g["use"]]))
             n_low = sum(g["comps_host"].size for g in groups
                         if g["use"].size and np.min(fhost) < np.min(self.freq_array[g["use"]]))
-            n_many = sum(g["comps_host"].size for g in groups if g["fallback"])
+            # counted only when something is left to interpolate (at_freq_inds_use.size > 0, skymodel.py:2295-2303)
+            n_many = sum(g["comps_host"].size for g in groups if g["fallback"] and np.any(
+                (fhost >= np.min(self.freq_array[g["use"]])) & (fhost <= np.max(self.freq_array[g["use"]]))))
             if n_all:
                 warnings.warn(f"{n_all} components had all NaN Stokes values. "
                               "Output Stokes for these components will all be NaN.")
