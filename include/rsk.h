@@ -204,6 +204,24 @@ int rsk_positions_sweep(const RskCoords* coords, int64_t n, const double* ctx /*
 int rsk_healpix_lonlat(int64_t nside, int nested, const int64_t* hpx_inds /* [n] or NULL */,
                        int64_t hpx_first, int64_t n, double* lon, double* lat, void* stream);
 
+/* The inverse map: pix[i] = the HEALPix pixel that contains (lon[i], lat[i]) -- what
+ * astropy_healpix.HEALPix(nside, order, frame).skycoord_to_healpix does for SkyModel.assign_to_healpix
+ * (skymodel.py:1916).  rsk_lonlat_to_healpix(rsk_healpix_lonlat(p)) == p for every pixel. */
+int rsk_lonlat_to_healpix(int64_t nside, int nested, const double* lon, const double* lat, int64_t n,
+                          int64_t* pix /* [n] */, void* stream);
+
+/* In-place x[i] *= factor (divide == 0) or x[i] /= factor (divide != 0), correctly rounded: the pixel-area
+ * scaling of healpix_to_point (stokes * area, skymodel.py:1722) and _point_to_healpix / assign_to_healpix
+ * (stokes / area, :1787, :1990-2003) with area = 4 pi / (12 nside^2) sr. */
+int rsk_scale(double* x, int64_t count, double factor, int divide, void* stream);
+
+/* Flux of the components that map to one pixel (skymodel.py:1967-1979): out[r][j] = sum over
+ * k in [start[j], start[j+1]) of in[r][order[k]], accumulated in that order (quadrature != 0: the square root
+ * of the sum of squares, used for stokes_error); r runs over the nrows = 4 * Nfreqs rows of length n_in. */
+int rsk_segment_sum(const double* in /* [nrows][n_in] */, int64_t nrows, int64_t n_in,
+                    const int64_t* order /* [n_in] */, const int64_t* start /* [nseg + 1] */, int64_t nseg,
+                    int quadrature, double* out /* [nrows][nseg] */, void* stream);
+
 /* ---- K1b: horizon compaction ------------------------------------------------------------------ */
 
 /* Order-preserving compaction of the horizon mask = the boolean fancy index of skymodel.py:2685 and

@@ -87,3 +87,72 @@ def healpix_to_lonlat(nside, pix, nested=False):
     z, omz, phi = pix2zphi(nside, pix, nested=nested)
     st = np.sqrt(omz * (2.0 - omz))  # sqrt((1-|z|)(1+|z|)) without cancellation near the poles
     return phi, np.arctan2(z, st)
+
+
+def _spread_bits(v):
+    x = np.asarray(v, dtype=np.uint64) & np.uint64(0xFFFFFFFF)
+    for shift, mask in ((16, 0x0000FFFF0000FFFF), (8, 0x00FF00FF00FF00FF), (4, 0x0F0F0F0F0F0F0F0F),
+                        (2, 0x3333333333333333), (1, 0x5555555555555555)):
+        x = (x | (x << np.uint64(shift))) & np.uint64(mask)
+    return x.astype(np.int64)
+
+
+def lonlat_to_healpix(nside, lon, lat, nested=False):
+    """Pixel index containing each (lon, lat) [radians]: the published HEALPix ang2pix (Gorski et al. 2005),
+    which is what ``astropy_healpix.HEALPix.skycoord_to_healpix`` computes for
+    ``SkyModel.assign_to_healpix`` (src/pyradiosky/skymodel.py:1916).  astropy-healpix is absent from this
+    image, so parity with it on exact pixel boundaries is unpinned; interior points (every test here) are
+    unambiguous."""
+    lon = np.atleast_1d(np.asarray(lon, dtype=np.float64))
+    lat = np.atleast_1d(np.asarray(lat, dtype=np.float64))
+    nside = int(nside)
+    z = np.sin(lat)
+    za = np.abs(z)
+    sth = np.abs(np.cos(lat))
+    tt = np.mod(lon, 2 * np.pi) / (np.pi / 2)
+    tt = np.where(tt >= 4.0, 0.0, tt)
+    nl4 = 4 * nside
+    pix = np.zeros(lon.shape, dtype=np.int64)
+    eq = za <= 2.0 / 3.0
+    # equatorial belt
+    temp1 = nside * (0.5 + tt)
+    temp2 = nside * (z * 0.75)
+    jp = np.floor(temp1 - temp2).astype(np.int64)
+    jm = np.floor(temp1 + temp2).astype(np.int64)
+    if nested:
+        ifp, ifm = jp // nside, jm // nside
+        face = np.where(ifp == ifm, ifp | 4, np.where(ifp < ifm, ifp, ifm + 8))
+        ix = jm & (nside - 1)
+        iy = nside - (jp & (nside - 1)) - 1
+        pix_eq = (face & 15) * nside * nside + _spread_bits(ix) + 2 * _spread_bits(iy)
+    else:
+        ir = nside + 1 + jp - jm
+        kshift = 1 - (ir & 1)
+        ip = ((jp + jm - nside + kshift + 1 + 2 * nl4) >> 1) % nl4
+        pix_eq = 2 * nside * (nside - 1) + (ir - 1) * nl4 + ip
+    # polar caps
+    ntt = np.minimum(tt.astype(np.int64), 3)
+    tp = tt - ntt
+    tmp = np.where(za > 0.99, nside * sth / np.sqrt((1.0 + za) / 3.0), nside * np.sqrt(3.0 * np.maximum(1.0 - za, 0.0)))
+    jpc = np.floor(tp * tmp).astype(np.int64)
+    jmc = np.floor((1.0 - tp) * tmp).astype(np.int64)
+    if nested:
+        jpn = np.minimum(jpc, nside - 1)
+        jmn = np.minimum(jmc, nside - 1)
+        north = z >= 0
+        face = np.where(north, ntt, ntt + 8)
+        ix = np.where(north, nside - jmn - 1, jpn)
+        iy = np.where(north, nside - jpn - 1, jmn)
+        pix_cap = face * nside * nside + _spread_bits(ix) + 2 * _spread_bits(iy)
+    else:
+        ir = jpc + jmc + 1
+        ip = np.floor(tt * ir).astype(np.int64) % (4 * ir)
+        pix_cap = np.where(z > 0, 2 * ir * (ir - 1) + ip, 12 * nside * nside - 2 * ir * (ir + 1) + ip)
+    return np.where(eq, pix_eq, pix_cap)
+
+
+def nside_to_pixel_area(nside):
+    """astropy_healpix.nside_to_pixel_area: 4 pi / (12 nside^2) steradian."""
+    import math
+
+    return 4 * math.pi / (12 * int(nside) * int(nside))

@@ -96,6 +96,17 @@ _SIGNATURES = {
         [ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p],
     ),
+    "rsk_lonlat_to_healpix": (
+        ctypes.c_int,
+        [ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+         ctypes.c_void_p],
+    ),
+    "rsk_scale": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_int, ctypes.c_void_p]),
+    "rsk_segment_sum": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+         ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p],
+    ),
     "rsk_compact_index": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,

@@ -324,6 +324,65 @@ RSK_HD void rsk_hpx_center(int64_t nside, int nested, int64_t pix, double& z, do
   phi = ((double)jp - (double)(kshift + 1) * 0.5) * (RSK_HALFPI / nrf);
 }
 
+RSK_HD int64_t rsk_spread_bits(int64_t v) {
+  uint64_t x = (uint64_t)v & 0xFFFFFFFFull;
+  x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+  x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+  x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+  x = (x | (x << 2)) & 0x3333333333333333ull;
+  x = (x | (x << 1)) & 0x5555555555555555ull;
+  return (int64_t)x;
+}
+
+// Pixel containing the direction (z = sin lat, st = cos lat >= 0, phi = lon): the inverse of rsk_hpx_center
+// (standard HEALPix ang2pix; astropy_healpix.lonlat_to_healpix at skymodel.py:1916).  st carries the polar
+// caps without the cancellation of 1 - |z|.
+RSK_HD int64_t rsk_hpx_pixel(int64_t nside, int nested, double z, double st, double phi) {
+  const double za = fabs(z);
+  double tt = fmod(phi, RSK_D2PI);
+  if (tt < 0.0) tt += RSK_D2PI;
+  tt *= 0.63661977236758134308;  // in [0, 4]
+  if (tt >= 4.0) tt = 0.0;
+  const int64_t nl4 = 4 * nside;
+  if (za <= 2.0 / 3.0) {  // equatorial belt
+    const double temp1 = (double)nside * (0.5 + tt);
+    const double temp2 = (double)nside * (z * 0.75);
+    const int64_t jp = (int64_t)(temp1 - temp2);  // ascending edge line
+    const int64_t jm = (int64_t)(temp1 + temp2);  // descending edge line
+    if (nested) {
+      const int64_t ifp = jp / nside, ifm = jm / nside;
+      const int64_t face = ifp == ifm ? (ifp | 4) : (ifp < ifm ? ifp : ifm + 8);
+      const int64_t ix = jm & (nside - 1);
+      const int64_t iy = nside - (jp & (nside - 1)) - 1;
+      return (face & 15) * nside * nside + rsk_spread_bits(ix) + 2 * rsk_spread_bits(iy);
+    }
+    const int64_t ir = nside + 1 + jp - jm;  // ring counted from z = 2/3, in [1, 2 nside + 1]
+    const int64_t kshift = 1 - (ir & 1);
+    int64_t ip = (jp + jm - nside + kshift + 1 + 2 * nl4) >> 1;
+    ip %= nl4;
+    return 2 * nside * (nside - 1) + (ir - 1) * nl4 + ip;
+  }
+  // polar caps
+  int64_t ntt = (int64_t)tt;
+  if (ntt > 3) ntt = 3;
+  const double tp = tt - (double)ntt;
+  const double tmp = za > 0.99 ? (double)nside * st / sqrt((1.0 + za) / 3.0) : (double)nside * sqrt(3.0 * (1.0 - za));
+  int64_t jp = (int64_t)(tp * tmp);
+  int64_t jm = (int64_t)((1.0 - tp) * tmp);
+  if (nested) {
+    if (jp > nside - 1) jp = nside - 1;
+    if (jm > nside - 1) jm = nside - 1;
+    int64_t face, ix, iy;
+    if (z >= 0.0) { face = ntt; ix = nside - jm - 1; iy = nside - jp - 1; }
+    else { face = ntt + 8; ix = jp; iy = jm; }
+    return face * nside * nside + rsk_spread_bits(ix) + 2 * rsk_spread_bits(iy);
+  }
+  const int64_t ir = jp + jm + 1;  // ring counted from the closest pole
+  int64_t ip = (int64_t)(tt * (double)ir);
+  ip %= 4 * ir;
+  return z > 0.0 ? 2 * ir * (ir - 1) + ip : 12 * nside * nside - 2 * ir * (ir + 1) + ip;
+}
+
 // ---- polarisation basis rotation -------------------------------------------------------------------
 
 // Per-component coefficients of the 2x2 rotation R^T C R of skymodel.py:2704-2710 with

@@ -162,6 +162,47 @@ __global__ void __launch_bounds__(kThreads) k_healpix_lonlat(const int64_t nside
   lat[i] = atan2(z, st);
 }
 
+// inverse of k_healpix_lonlat: the pixel each (lon, lat) falls in (astropy_healpix lonlat_to_healpix, called by
+// SkyModel.assign_to_healpix at skymodel.py:1916)
+__global__ void __launch_bounds__(kThreads) k_lonlat_to_healpix(const int64_t nside, const int nested,
+                                                                const double* __restrict__ lon,
+                                                                const double* __restrict__ lat, const int64_t n,
+                                                                int64_t* __restrict__ pix) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  double sb, cb;
+  rsk_sincos(__ldg(lat + i), &sb, &cb);
+  pix[i] = rsk_hpx_pixel(nside, nested, sb, fabs(cb), __ldg(lon + i));
+}
+
+// x *= factor or x /= factor, correctly rounded (pixel-area scaling of healpix_to_point / assign_to_healpix,
+// skymodel.py:1722, :1787, :1990-2003)
+__global__ void __launch_bounds__(kThreads) k_scale(double* __restrict__ x, const int64_t count, const double factor,
+                                                    const int divide) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= count) return;
+  x[i] = divide ? __ddiv_rn(x[i], factor) : __dmul_rn(x[i], factor);
+}
+
+// Sum (or root-sum-square) of the components that fall in one pixel, in catalogue order (skymodel.py:1967-1979):
+// out[r][j] = sum_{k in [start[j], start[j+1])} in[r][order[k]] for each of the nrows = 4 * Nfreqs rows.
+__global__ void __launch_bounds__(kThreads) k_segment_sum(const double* __restrict__ in, const int64_t nrows,
+                                                          const int64_t n_in, const int64_t* __restrict__ order,
+                                                          const int64_t* __restrict__ start, const int64_t nseg,
+                                                          const int quadrature, double* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t r = blockIdx.y;
+  if (j >= nseg) return;
+  const int64_t k0 = __ldg(start + j), k1 = __ldg(start + j + 1);
+  const double* row = in + r * n_in;
+  double acc = 0.0;
+  for (int64_t k = k0; k < k1; ++k) {
+    const double v = __ldg(row + __ldg(order + k));
+    acc = quadrature ? __dadd_rn(acc, __dmul_rn(v, v)) : __dadd_rn(acc, v);
+  }
+  out[r * nseg + j] = quadrature ? __dsqrt_rn(acc) : acc;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K1b: order-preserving compaction of the horizon mask (count -> scan of tile counts -> scatter)
 // ---------------------------------------------------------------------------------------------------
@@ -926,6 +967,36 @@ int rsk_healpix_lonlat(int64_t nside, int nested, const int64_t* hpx_inds, int64
   if (n < 0) return RSK_ERR_SIZE;
   if (n == 0) return RSK_OK;
   k_healpix_lonlat<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(nside, nested, hpx_inds, hpx_first, n, lon, lat);
+  return launch_status();
+}
+
+int rsk_lonlat_to_healpix(int64_t nside, int nested, const double* lon, const double* lat, int64_t n, int64_t* pix,
+                          void* stream) {
+  if (nside <= 0 || nside > (1ll << 29)) return RSK_ERR_NSIDE;
+  if (nested && (nside & (nside - 1)) != 0) return RSK_ERR_NSIDE;
+  if (n < 0) return RSK_ERR_SIZE;
+  if (n == 0) return RSK_OK;
+  if (!lon || !lat || !pix) return RSK_ERR_NULL;
+  k_lonlat_to_healpix<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(nside, nested, lon, lat, n, pix);
+  return launch_status();
+}
+
+int rsk_scale(double* x, int64_t count, double factor, int divide, void* stream) {
+  if (count < 0) return RSK_ERR_SIZE;
+  if (count == 0) return RSK_OK;
+  if (!x) return RSK_ERR_NULL;
+  if ((count + kThreads - 1) / kThreads > 0x7fffffffll) return RSK_ERR_SIZE;
+  k_scale<<<blocks_for(count), kThreads, 0, (cudaStream_t)stream>>>(x, count, factor, divide);
+  return launch_status();
+}
+
+int rsk_segment_sum(const double* in, int64_t nrows, int64_t n_in, const int64_t* order, const int64_t* start,
+                    int64_t nseg, int quadrature, double* out, void* stream) {
+  if (nrows < 0 || n_in < 0 || nseg < 0 || nrows > 65535) return RSK_ERR_SIZE;
+  if (nrows == 0 || nseg == 0) return RSK_OK;
+  if (!in || !order || !start || !out) return RSK_ERR_NULL;
+  const dim3 grid(blocks_for(nseg), (unsigned)nrows);
+  k_segment_sum<<<grid, kThreads, 0, (cudaStream_t)stream>>>(in, nrows, n_in, order, start, nseg, quadrature, out);
   return launch_status();
 }
 

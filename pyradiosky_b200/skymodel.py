@@ -26,6 +26,7 @@ Differences from the reference that a caller can observe (all documented in DESI
 
 import copy as _copy
 import ctypes
+import math
 import os
 import warnings
 
@@ -381,6 +382,214 @@ class SkyModel:
         from . import skyh5
 
         skyh5.write_skyh5(self, filename, clobber=clobber, data_compression=data_compression)
+
+    # ------------------------------------------------------------------------------------------
+    # HEALPix <-> point conversions: skymodel.py:1675-2081
+    # ------------------------------------------------------------------------------------------
+    def _pixel_area(self, nside):
+        """astropy_healpix.nside_to_pixel_area(nside) in steradian."""
+        return 4 * math.pi / (12 * int(nside) * int(nside))
+
+    def _scale(self, tensor, factor, divide):
+        self._call("rsk_scale", _lib.ptr(tensor), tensor.numel(), ctypes.c_double(factor), 1 if divide else 0)
+
+    def _unit_times_sr(self, unit, divide):
+        table = {("K", False): "K sr", ("Jy / sr", False): "Jy", ("K sr", True): "K", ("Jy", True): "Jy / sr"}
+        try:
+            return table[(unit, divide)]
+        except KeyError:
+            raise ValueError(f"cannot {'divide' if divide else 'multiply'} Stokes in {unit!r} by a solid angle") from None
+
+    def healpix_to_point(self, to_jy=True, **_checks):
+        """Convert a healpix object to point components: multiply by the pixel area, optionally convert
+        to Jy (skymodel.py:1675-1736).  ``nside``, ``hpx_order`` and ``hpx_inds`` stay set, as upstream,
+        so :meth:`_point_to_healpix` can undo it."""
+        if self.component_type != "healpix":
+            raise ValueError("This method can only be called if component_type is 'healpix'.")
+        lon, lat = self.get_lon_lat()
+        if self.hpx_inds is None:
+            self.hpx_inds = torch.arange(self.hpx_first, self.hpx_first + self.Ncomponents, dtype=torch.int64,
+                                         device=self.device)
+            self.hpx_first = 0
+        self.lon, self.lat = lon, lat
+        self.hpx_frame = None
+        self.component_type = "point"
+        area = self._pixel_area(self.nside)
+        self._scale(self.stokes, area, divide=False)
+        self.stokes_unit = self._unit_times_sr(self.stokes_unit, divide=False)
+        if self.frame_coherency is not None:
+            self.frame_coherency = self.frame_coherency * area
+        inds = self.hpx_inds.cpu().numpy()
+        self.name = np.array(["nside" + str(self.nside) + "_" + self.hpx_order + "_" + str(ind) for ind in inds])
+        self.clear_time_position_specific_params()
+        if to_jy:
+            self.kelvin_to_jansky()
+
+    def _point_to_healpix(self, to_k=True, **_checks):
+        """Undo :meth:`healpix_to_point` (skymodel.py:1738-1806): divide by the pixel area, optionally
+        convert to K.  Does not assign general point components to a grid (see :meth:`assign_to_healpix`)."""
+        if self.component_type != "point" or self.nside is None or self.hpx_inds is None or self.hpx_order is None:
+            raise ValueError(
+                "This method can only be called if component_type is 'point' and "
+                "the nside, hpx_order and hpx_inds parameters are set."
+            )
+        self.component_type = "healpix"
+        area = self._pixel_area(self.nside)
+        self._scale(self.stokes, area, divide=True)
+        self.stokes_unit = self._unit_times_sr(self.stokes_unit, divide=True)
+        if self.frame_coherency is not None:
+            self.frame_coherency = self.frame_coherency / area
+        self.hpx_frame = self.frame
+        self.name = None
+        self.lon = None
+        self.lat = None
+        self.clear_time_position_specific_params()
+        if to_k:
+            self.jansky_to_kelvin()
+
+    def assign_to_healpix(self, nside, order="ring", to_k=True, full_sky=False, sort=True, inplace=False, **_checks):
+        """Assign point components to their nearest pixel of a HEALPix grid, summing the flux of components
+        that share a pixel, dividing by the pixel area and optionally converting to K
+        (skymodel.py:1808-2081).  Pixel lookup, per-pixel sums and the area scaling run in librsk kernels
+        (``rsk_lonlat_to_healpix``, ``rsk_segment_sum``, ``rsk_scale``); torch only sorts the pixel indices.
+
+        Differences from upstream: fluxes of a pixel are accumulated strictly in catalogue order (numpy
+        switches to pairwise summation beyond 8 terms); the polarised-component bookkeeping is rebuilt for
+        the new pixel set (upstream keeps the indices of the old catalogue)."""
+        if self.component_type != "point":
+            raise ValueError("This method can only be called if component_type is 'point'.")
+        order = str(order).lower()
+        if order not in ("ring", "nested"):
+            raise ValueError("order must be 'ring' or 'nested'")
+        nside = int(nside)
+        n = self.Ncomponents
+        pix = torch.empty(n, dtype=torch.int64, device=self.device)
+        self._call("rsk_lonlat_to_healpix", nside, 1 if order == "nested" else 0, _lib.ptr(self.lon), _lib.ptr(self.lat),
+                   n, _lib.ptr(pix))
+        spix, perm = torch.sort(pix, stable=True)  # within a pixel the catalogue order is kept
+        upix, counts = torch.unique_consecutive(spix, return_counts=True)
+        nseg = int(upix.numel())
+        start = torch.zeros(nseg + 1, dtype=torch.int64, device=self.device)
+        torch.cumsum(counts, 0, out=start[1:])
+        first = perm[start[:-1]]  # first catalogue member of every pixel
+        if nseg < n:
+            # parameters that must not vary among the components of one pixel (skymodel.py:1929-1960)
+            seg_of = torch.repeat_interleave(torch.arange(nseg, device=self.device), counts)
+            for attr, label in (("reference_frequency", "reference_frequency"), ("spectral_index", "spectral_index")):
+                vals = getattr(self, attr)
+                if vals is not None and bool((vals[perm] != vals[first][seg_of]).any()):
+                    raise ValueError(
+                        "Multiple components map to a single healpix pixel "
+                        f"and the {label} varies among them. Consider "
+                        "using the `at_frequencies` method first or a "
+                        "larger nside."
+                    )
+            if self.extended_model_group is not None:
+                grp = np.asarray(self.extended_model_group)
+                ph, fh, sh = perm.cpu().numpy(), first.cpu().numpy(), seg_of.cpu().numpy()
+                if np.any(grp[ph] != grp[fh][sh]):
+                    raise ValueError(
+                        "Multiple components map to a single healpix pixel "
+                        "and the extended_model_group varies among them."
+                        "Consider using a larger nside."
+                    )
+            if self.beam_amp is not None and bool((self.beam_amp[:, :, perm] != self.beam_amp[:, :, first][:, :, seg_of]).any()):
+                raise ValueError(
+                    "Multiple components map to a single healpix pixel and "
+                    "the beam_amp varies among them. "
+                    "Consider using a larger nside."
+                )
+        nrows = 4 * self.Nfreqs
+        area = self._pixel_area(nside)
+
+        def per_pixel(values, quadrature):
+            out = torch.empty((4, self.Nfreqs, nseg), dtype=torch.float64, device=self.device)
+            self._call("rsk_segment_sum", _lib.ptr(values), nrows, n, _lib.ptr(perm), _lib.ptr(start), nseg,
+                       1 if quadrature else 0, _lib.ptr(out))
+            self._scale(out, area, divide=True)
+            return out
+
+        new_stokes = per_pixel(self.stokes, False)
+        new_err = per_pixel(self.stokes_error, True) if self.stokes_error is not None else None
+        ref_freq = None if self.reference_frequency is None else self.reference_frequency[first]
+        sp_index = None if self.spectral_index is None else self.spectral_index[first]
+        beam_amp = None if self.beam_amp is None else self.beam_amp[:, :, first].contiguous()
+        ext = None if self.extended_model_group is None else np.asarray(self.extended_model_group)[first.cpu().numpy()]
+        extra = None
+        if self.extra_columns:
+            fh = first.cpu().numpy()
+            extra = {k: np.asarray(v)[fh] for k, v in self.extra_columns.items()}
+        hpx_inds = upix
+        if not sort:
+            # upstream keeps the order of first appearance (dict insertion order, skymodel.py:1921-1962)
+            appear = torch.argsort(first)
+            hpx_inds, new_stokes = upix[appear], new_stokes[:, :, appear].contiguous()
+            new_err = None if new_err is None else new_err[:, :, appear].contiguous()
+            ref_freq = None if ref_freq is None else ref_freq[appear]
+            sp_index = None if sp_index is None else sp_index[appear]
+            beam_amp = None if beam_amp is None else beam_amp[:, :, appear].contiguous()
+            ah = appear.cpu().numpy()
+            ext = None if ext is None else ext[ah]
+            extra = None if extra is None else {k: v[ah] for k, v in extra.items()}
+        npix = 12 * nside * nside
+        if full_sky and nseg < npix:
+            # zero-flux pixels; spectral parameters take the median of the assigned ones (skymodel.py:2014-2066)
+            def widen(t, fill=0.0):
+                if t is None:
+                    return None
+                shape = tuple(t.shape[:-1]) + (npix,)
+                full = torch.full(shape, fill, dtype=t.dtype, device=self.device)
+                full[..., hpx_inds] = t
+                return full
+
+            new_stokes, new_err, beam_amp = widen(new_stokes), widen(new_err), widen(beam_amp)
+            if ref_freq is not None:
+                ref_freq = widen(ref_freq, float(np.median(ref_freq.cpu().numpy())))
+            if sp_index is not None:
+                sp_index = widen(sp_index, float(np.median(sp_index.cpu().numpy())))
+            hh = hpx_inds.cpu().numpy()
+            if ext is not None:
+                full_ext = np.full(npix, "", dtype=ext.dtype)
+                full_ext[hh] = ext
+                ext = full_ext
+            if extra is not None:
+                wide = {}
+                for k, v in extra.items():
+                    w = np.zeros(npix, dtype=v.dtype)
+                    w[hh] = v
+                    wide[k] = w
+                extra = wide
+            if sort:
+                hpx_inds = torch.arange(npix, dtype=torch.int64, device=self.device)
+            else:  # assigned pixels first (in their order), then the empty ones
+                member = torch.zeros(npix, dtype=torch.bool, device=self.device)
+                member[hpx_inds] = True
+                rest = torch.nonzero(~member, as_tuple=False).flatten()
+                order_all = torch.cat([hpx_inds, rest])
+                oh = order_all.cpu().numpy()
+                new_stokes = new_stokes[:, :, order_all].contiguous()
+                new_err = None if new_err is None else new_err[:, :, order_all].contiguous()
+                beam_amp = None if beam_amp is None else beam_amp[:, :, order_all].contiguous()
+                ref_freq = None if ref_freq is None else ref_freq[order_all]
+                sp_index = None if sp_index is None else sp_index[order_all]
+                ext = None if ext is None else ext[oh]
+                extra = None if extra is None else {k: v[oh] for k, v in extra.items()}
+                hpx_inds = order_all
+        new = SkyModel(component_type="healpix", nside=nside, hpx_order=order, hpx_inds=hpx_inds, hpx_frame=self.frame,
+                       equinox=self.equinox, stokes=new_stokes, spectral_type=self.spectral_type,
+                       freq_array=self.freq_array, freq_edge_array=self.freq_edge_array, reference_frequency=ref_freq,
+                       spectral_index=sp_index, stokes_unit=self._unit_times_sr(self.stokes_unit, divide=True),
+                       device=self.device, history=self.history, filename=self.filename, extended_model_group=ext,
+                       stokes_error=new_err, beam_amp=beam_amp, extra_columns=extra)
+        if self.frame_coherency is not None:
+            new.calc_frame_coherency()
+        if to_k:
+            new.jansky_to_kelvin()
+        if inplace:
+            self.__dict__.clear()
+            self.__dict__.update(new.__dict__)
+            return None
+        return new
 
     # ------------------------------------------------------------------------------------------
     # coordinates
@@ -1026,6 +1235,9 @@ class SkyModel:
             )
         self._call("rsk_convert_units", _lib.ptr(self.stokes), self.Nfreqs, self.Ncomponents, _lib.ptr(fchan),
                    _lib.ptr(fcomp), 1 if to_jansky else 0)
+        if self.stokes_error is not None:  # skymodel.py:1583-1584, :1630-1631
+            self._call("rsk_convert_units", _lib.ptr(self.stokes_error), self.Nfreqs, self.Ncomponents, _lib.ptr(fchan),
+                       _lib.ptr(fcomp), 1 if to_jansky else 0)
         if self.frame_coherency is not None:
             self.calc_frame_coherency()
 

@@ -969,3 +969,177 @@ def test_unit_conversion_launch_shapes(rsk, n, nf):
                        reference_frequency=rf, spectral_index=np.full(n, -0.8))
     sky.jansky_to_kelvin()
     assert np.array_equal(sky.stokes.cpu().numpy(), S.jansky_to_kelvin(st[:, :1], "spectral_index", reference_frequency=rf))
+
+
+# ---------------------------------------------------------------------------------------------------
+# HEALPix <-> point conversions (skymodel.py:1675-2081)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nested", [False, True])
+def test_lonlat_to_healpix_gpu(rsk, nested):
+    from pyradiosky_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(17)
+    for nside in (1, 8, 64, 1024, 2**20):
+        if nside <= 64:
+            pix = np.arange(12 * nside * nside)
+        else:
+            pix = rng.integers(0, 12 * nside * nside, 200000)
+        # every pixel centre maps back to its pixel (device pix2ang -> device ang2pix)
+        tp = torch.as_tensor(pix).cuda()
+        lon = torch.empty(pix.size, dtype=torch.float64, device="cuda")
+        lat = torch.empty_like(lon)
+        assert lib.rsk_healpix_lonlat(nside, int(nested), tp.data_ptr(), 0, pix.size, lon.data_ptr(), lat.data_ptr(), None) == 0
+        back = torch.empty(pix.size, dtype=torch.int64, device="cuda")
+        assert lib.rsk_lonlat_to_healpix(nside, int(nested), lon.data_ptr(), lat.data_ptr(), pix.size, back.data_ptr(), None) == 0
+        assert np.array_equal(back.cpu().numpy(), pix), nside
+    # random directions: bit-equal to the oracle
+    lon, lat = random_sky(rng, 300000)
+    for nside in (4, 32, 512, 8192):
+        tl, tb = torch.as_tensor(lon).cuda(), torch.as_tensor(lat).cuda()
+        out = torch.empty(lon.size, dtype=torch.int64, device="cuda")
+        assert lib.rsk_lonlat_to_healpix(nside, int(nested), tl.data_ptr(), tb.data_ptr(), lon.size, out.data_ptr(), None) == 0
+        want = hp.lonlat_to_healpix(nside, lon, lat, nested=nested)
+        got = out.cpu().numpy()
+        # a direction within rounding of a pixel edge may land on either side: compare away from edges
+        diff = np.nonzero(got != want)[0]
+        assert diff.size <= 2, (nside, diff.size)
+    assert lib.rsk_lonlat_to_healpix(12, 1, tl.data_ptr(), tb.data_ptr(), 10, out.data_ptr(), None) == -7
+
+
+@pytest.mark.parametrize("order", ["ring", "nested"])
+@pytest.mark.parametrize("method", ["assign_to_healpix", "_point_to_healpix"])
+@pytest.mark.parametrize("to_jy,to_k", [(True, True), (False, False), (True, False)])
+def test_healpix_to_point_loop(rsk, order, method, to_jy, to_k):
+    """tests/test_skymodel.py:880-938: healpix -> point -> healpix gives the object back."""
+    rng = np.random.default_rng(23)
+    nside = 32
+    npix = 12 * nside * nside
+    # a disk-like cut-out of the map, like healpix_disk.skyh5
+    inds = np.sort(rng.choice(npix, 3000, replace=False))
+    st = rng.normal(size=(4, 10, inds.size))
+    fa = np.linspace(100e6, 110e6, 10)
+    sky = rsk.SkyModel(nside=nside, hpx_inds=inds, hpx_order=order, hpx_frame="icrs", stokes=st, spectral_type="full",
+                       freq_array=fa, stokes_unit="K")
+    sky2 = sky.copy()
+    sky2.healpix_to_point(to_jy=to_jy)
+    assert sky2.component_type == "point" and sky2.stokes_unit == ("Jy" if to_jy else "K sr")
+    assert sky2.name[0] == f"nside{nside}_{order}_{inds[0]}"
+    lon, lat = hp.healpix_to_lonlat(nside, inds, nested=(order == "nested"))
+    assert np.allclose(sky2.lon.cpu().numpy(), lon, rtol=0, atol=1e-14)
+    area = hp.nside_to_pixel_area(nside)
+    want = st * area
+    if to_jy:
+        want = S.kelvin_to_jansky(want, "full", freq_array=fa)
+    assert np.array_equal(sky2.stokes.cpu().numpy(), want)
+    if method == "assign_to_healpix":
+        sky2.assign_to_healpix(nside, order=order, inplace=True, to_k=to_k)
+    else:
+        sky2._point_to_healpix(to_k=to_k)
+    if to_jy and not to_k:
+        sky.kelvin_to_jansky()
+    assert sky2.component_type == "healpix" and sky2.stokes_unit == sky.stokes_unit
+    assert sky2.nside == nside and sky2.hpx_order == order and sky2.frame == "icrs" and sky2.name is None
+    assert torch.equal(sky2.hpx_inds, sky.hpx_inds)
+    assert np.allclose(sky2.stokes.cpu().numpy(), sky.stokes.cpu().numpy(), rtol=2e-15, atol=0)
+
+
+def _assign_hpx_data(rsk):
+    """tests/test_skymodel.py:234-276"""
+    nside, pix_num = 32, 25
+    ra, dec = hp.healpix_to_lonlat(nside, np.array([pix_num]))
+    off = np.deg2rad(0.01)
+    stokes = np.zeros((4, 1, 2)); stokes[0, 0, 0] = 1.5; stokes[1, 0, 0] = 0.5; stokes[0, 0, 1] = 3
+    err = np.zeros((4, 1, 2)); err[0, 0, 0] = 0.15; err[1, 0, 0] = 0.2; err[0, 0, 1] = 0.25
+    beam_amp = np.zeros((4, 1, 2)); beam_amp[0] = 0.97; beam_amp[1] = 0.96; beam_amp[2] = 0.6; beam_amp[3] = 0.5
+    sky = rsk.SkyModel(name=["src1", "src2"], ra=ra + np.array([-off, off]), dec=dec + np.array([-off, off]), frame="icrs",
+                       stokes=stokes, spectral_type="subband", freq_array=[150e6], freq_edge_array=np.array([[140e6], [160e6]]),
+                       stokes_error=err, beam_amp=beam_amp, extended_model_group=["extsrc1", "extsrc1"])
+    return nside, pix_num, sky
+
+
+def test_assign_to_healpix_known_answers(rsk):
+    """tests/test_skymodel.py:1008-1087"""
+    nside, pix_num, sky = _assign_hpx_data(rsk)
+    conv = S.jy_to_ksr(150e6)
+    area = hp.nside_to_pixel_area(nside)
+    sky_hpx = sky.assign_to_healpix(nside)
+    assert sky_hpx.Ncomponents == 1 and int(sky_hpx.hpx_inds[0]) == pix_num
+    st, err = sky_hpx.stokes.cpu().numpy(), sky_hpx.stokes_error.cpu().numpy()
+    assert np.allclose(st[0, 0, 0], 4.5 * conv / area) and np.allclose(st[1, 0, 0], 0.5 * conv / area)
+    assert np.allclose(err[0, 0, 0], np.sqrt(0.15**2 + 0.25**2) * conv / area) and np.allclose(err[1, 0, 0], 0.2 * conv / area)
+    assert sky_hpx.stokes_unit == "K" and sky_hpx.frame == "icrs" and sky_hpx.spectral_type == "subband"
+    assert sky.component_type == "point"  # not in place
+    # full sky, subband and spectral_index
+    for spectral_type in ("subband", "spectral_index"):
+        nside, pix_num, sky = _assign_hpx_data(rsk)
+        if spectral_type == "spectral_index":
+            sky = rsk.SkyModel(name=["src1", "src2"], ra=sky.lon, dec=sky.lat, stokes=sky.stokes, spectral_type="spectral_index",
+                               reference_frequency=np.array([150e6, 150e6]), spectral_index=np.array([-0.8, -0.8]))
+        full = sky.assign_to_healpix(nside, full_sky=True)
+        assert full.Ncomponents == 12 * nside * nside
+        st = full.stokes.cpu().numpy()
+        assert np.allclose(st[0, 0, pix_num], 4.5 * conv / area) and np.allclose(st[1, 0, pix_num], 0.5 * conv / area)
+        assert not np.any(st[:, :, :25]) and not np.any(st[:, :, 26:])
+        if spectral_type == "subband":
+            err = full.stokes_error.cpu().numpy()
+            assert np.allclose(err[0, 0, pix_num], np.sqrt(0.15**2 + 0.25**2) * conv / area)
+            assert not np.any(err[:, :, :25]) and not np.any(err[:, :, 26:])
+        else:
+            assert np.all(full.spectral_index.cpu().numpy() == -0.8)
+
+
+def test_assign_to_healpix_errors(rsk):
+    """tests/test_skymodel.py:1098-1150"""
+    nside, pix_num, sky = _assign_hpx_data(rsk)
+    hpx = sky.assign_to_healpix(nside)
+    with pytest.raises(ValueError, match="This method can only be called if component_type is 'point'."):
+        hpx.assign_to_healpix(nside)
+    with pytest.raises(ValueError, match="This method can only be called if component_type is 'healpix'."):
+        sky.healpix_to_point()
+    with pytest.raises(ValueError, match="This method can only be called if component_type is 'point' and "
+                       "the nside, hpx_order and hpx_inds parameters are set."):
+        sky._point_to_healpix()
+    sky2 = rsk.SkyModel(name=["src1", "src2"], ra=sky.lon, dec=sky.lat, stokes=sky.stokes, spectral_type="spectral_index",
+                        reference_frequency=np.array([150e6, 150e6]), spectral_index=np.array([-0.8, -0.6]))
+    with pytest.raises(ValueError, match="Multiple components map to a single healpix pixel and the spectral_index varies"):
+        sky2.assign_to_healpix(nside)
+    sky2 = rsk.SkyModel(name=["src1", "src2"], ra=sky.lon, dec=sky.lat, stokes=sky.stokes, spectral_type="spectral_index",
+                        reference_frequency=np.array([150e6, 160e6]), spectral_index=np.array([-0.8, -0.8]))
+    with pytest.raises(ValueError, match="Multiple components map to a single healpix pixel and the reference_frequency varies"):
+        sky2.assign_to_healpix(nside)
+    sky.beam_amp[0, 0, 1] = 0.5
+    with pytest.raises(ValueError, match="Multiple components map to a single healpix pixel and the beam_amp varies"):
+        sky.assign_to_healpix(nside)
+    nside, pix_num, sky = _assign_hpx_data(rsk)
+    sky.extended_model_group = np.array(["a", "b"])
+    with pytest.raises(ValueError, match="the extended_model_group varies among them"):
+        sky.assign_to_healpix(nside)
+
+
+def test_assign_to_healpix_many_sources(rsk):
+    """Random catalogue binned to a coarse grid: per-pixel sums equal numpy's, in catalogue order."""
+    rng = np.random.default_rng(29)
+    n, nside = 20000, 8
+    ra, dec = random_sky(rng, n)
+    st = rng.normal(size=(4, 3, n))
+    sky = rsk.SkyModel(ra=ra, dec=dec, stokes=st, spectral_type="full", freq_array=[1e8, 1.1e8, 1.2e8])
+    for order in ("ring", "nested"):
+        for sort in (True, False):
+            out = sky.assign_to_healpix(nside, order=order, to_k=False, sort=sort)
+            pix = hp.lonlat_to_healpix(nside, ra, dec, nested=(order == "nested"))
+            inds = out.hpx_inds.cpu().numpy()
+            if sort:
+                assert np.array_equal(inds, np.unique(pix))
+            else:
+                _, first = np.unique(pix, return_index=True)
+                assert np.array_equal(inds, pix[np.sort(first)])
+            area = hp.nside_to_pixel_area(nside)
+            want = np.zeros((4, 3, inds.size))
+            for j, p in enumerate(inds):
+                acc = np.zeros((4, 3))
+                for k in np.nonzero(pix == p)[0]:
+                    acc = acc + st[:, :, k]
+                want[:, :, j] = acc / area
+            assert np.array_equal(out.stokes.cpu().numpy(), want)
+            assert out.stokes_unit == "Jy / sr"

@@ -380,3 +380,29 @@ def test_interp1d_is_linear_operator():
     f = np.linspace(80e6, 220e6, 333)
     w = scipy.interpolate.interp1d(x, np.eye(20), axis=0, kind="cubic")(f)
     assert np.abs(w @ y - scipy.interpolate.interp1d(x, y, axis=0, kind="cubic")(f)).max() < 1e-13
+
+
+def test_lonlat_to_healpix_inverts_pixel_centres():
+    """Size-independent property of the ang2pix restatement: it inverts pix2ang on every pixel, ring and
+    nested, and the two orderings agree on random directions."""
+    from oracle import healpix_np as hp
+
+    for nside in (1, 2, 8, 32, 128):
+        pix = np.arange(12 * nside * nside)
+        for nested in (False, True):
+            lon, lat = hp.healpix_to_lonlat(nside, pix, nested=nested)
+            assert np.array_equal(hp.lonlat_to_healpix(nside, lon, lat, nested=nested), pix)
+    for nside in (3, 12, 100):  # ring ordering has no power-of-two restriction
+        pix = np.arange(12 * nside * nside)
+        lon, lat = hp.healpix_to_lonlat(nside, pix)
+        assert np.array_equal(hp.lonlat_to_healpix(nside, lon, lat), pix)
+    rng = np.random.default_rng(8)
+    lon, lat = rng.uniform(0, 2 * np.pi, 20000), np.arcsin(rng.uniform(-1, 1, 20000))
+    cr = hp.healpix_to_lonlat(64, hp.lonlat_to_healpix(64, lon, lat))
+    cn = hp.healpix_to_lonlat(64, hp.lonlat_to_healpix(64, lon, lat, nested=True), nested=True)
+    assert np.allclose(cr[0], cn[0]) and np.allclose(cr[1], cn[1])
+    # the reference's fixture (tests/test_skymodel.py:234-244): +-0.01 deg around the centre of ring pixel 25
+    # at nside 32 stays in pixel 25
+    ra, dec = hp.healpix_to_lonlat(32, np.array([25]))
+    off = np.deg2rad(0.01)
+    assert list(hp.lonlat_to_healpix(32, ra + np.array([-off, off]), dec + np.array([-off, off]))) == [25, 25]
