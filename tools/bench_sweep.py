@@ -33,10 +33,25 @@ def main():
     from oracle import erfa_np, skymodel_np
     from pyradiosky_b200 import EarthLocation, SkyModel, Time, astrometry
 
+    # under torchrun: strong scaling, the n sources are sharded over the ranks (contiguous blocks), every rank
+    # sweeps all T contexts; time = max over ranks (device events), value = n * T / that time
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
     rng = np.random.default_rng(5)
-    n, nt = args.n, args.t
-    lon = rng.uniform(0, 2 * np.pi, n)
-    lat = np.arcsin(rng.uniform(-1, 1, n))
+    n_total, nt = args.n, args.t
+    lon = rng.uniform(0, 2 * np.pi, n_total)
+    lat = np.arcsin(rng.uniform(-1, 1, n_total))
+    if world > 1:
+        from pyradiosky_b200.dist import shard_bounds
+
+        lo, hi = shard_bounds(n_total, world, rank)
+        lon, lat = lon[lo:hi], lat[lo:hi]
+    n = lon.size
     st = np.zeros((4, 1, n))
     st[0] = 1.0
     sky = SkyModel(ra=lon, dec=lat, frame="icrs", stokes=st, spectral_type="flat")
@@ -50,15 +65,27 @@ def main():
     sky._timing_events = kev
     for r in range(args.reps + 1):
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         alt_az, lmn, above = sky.positions_sweep(None, loc, astroms=astroms, want_lmn=args.lmn)
         e1.record()
         torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            ms = float(tmax.item())
         if r > 0:
-            best = min(best, e0.elapsed_time(e1))
+            best = min(best, ms)
         if r < args.reps:
             del alt_az, lmn, above
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
     bytes_per = 41 if args.lmn else 17
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     # spot check against the oracle
@@ -74,11 +101,13 @@ def main():
     cpu_rate = 5 * ns / (time.perf_counter() - tc)
     kernel_ms = min(a.elapsed_time(b) for a, b in kev[1:])
     out = {
-        "metric": "position_source_time_evals_per_s", "value": n * nt / (best * 1e-3), "ms": best, "n": n, "t": nt,
+        "metric": "position_source_time_evals_per_s", "value": n_total * nt / (best * 1e-3), "ms": best, "n": n_total,
+        "t": nt, "n_gpus": world, "scaling": "strong", "sources_per_gpu": n,
         "kernel_ms": kernel_ms, "kernel_value": n * nt / (kernel_ms * 1e-3),
         "kernel_frac_of_hbm_peak": n * nt * (41 if args.lmn else 17) / (kernel_ms * 1e-3) / 1e9 / peak,
-        "bytes_per_eval": bytes_per, "achieved_gbs": n * nt * bytes_per / (best * 1e-3) / 1e9,
-        "frac_of_hbm_peak": n * nt * bytes_per / (best * 1e-3) / 1e9 / peak, "host_context_build_s": host_ctx_s,
+        "bytes_per_eval": bytes_per, "achieved_gbs": n_total * nt * bytes_per / (best * 1e-3) / 1e9,
+        "frac_of_hbm_peak_per_gpu": n_total * nt * bytes_per / (best * 1e-3) / 1e9 / peak / world,
+        "host_context_build_s": host_ctx_s,
         "max_alt_err_uas_vs_oracle": err_uas,
         "cpu_oracle_1core_evals_per_s": cpu_rate,
     }
