@@ -51,21 +51,27 @@ static_assert(sizeof(RskCtx) == 34 * sizeof(double), "RskCtx layout");
 // (2e-16 rad), five orders of magnitude inside the 1 micro-arcsecond budget.  On the host the libm
 // versions are used.
 
-// atan(t) = t + t*s*P(s), s = t^2, t in [0,1]; P from tools/gen_atan_poly.py (degree 19, max abs error
-// 1.1e-16 including the rounding of the double-precision Horner evaluation).
+// atan2 by table-driven argument reduction.  With t = min/max in [0, 1] and t_k = k/8 the nearest eighth,
+//   atan(t) = atan(t_k) + atan((min - t_k max) / (max + t_k min)),
+// so the reduction costs two fused multiply-adds *before* the one division, the interval index k comes from a
+// single-precision quotient (fp32 / SFU pipes, not the fp64 pipe), and the remaining argument is below
+// 1/16 + 2^-20: atan(u) = u + u s P(s), s = u^2, with a degree-5 P (tools/gen_atan_poly.py, |u| <= 0.08: max
+// error of the double-precision Horner evaluation < 1e-17).  The previous form, a degree-19 polynomial on
+// [0, 1], spent twice the fp64 issue slots; the LST sweep is bound by that pipe (profiles/r01_summary.md).
 #if defined(__CUDACC__)
-#define RSK_TABLE __constant__
-#else
-#define RSK_TABLE static const
+__device__ const double2 kRskAtanTab[9] = {  // (atan(k/8), k/8)
+    {0x0.0p+0, 0x0.0p+0},
+    {0x1.fd5ba9aac2f6ep-4, 0x1.0000000000000p-3},
+    {0x1.f5b75f92c80ddp-3, 0x1.0000000000000p-2},
+    {0x1.6f61941e4def1p-2, 0x1.8000000000000p-2},
+    {0x1.dac670561bb4fp-2, 0x1.0000000000000p-1},
+    {0x1.1e00babdefeb4p-1, 0x1.4000000000000p-1},
+    {0x1.4978fa3269ee1p-1, 0x1.8000000000000p-1},
+    {0x1.700a7c5784634p-1, 0x1.c000000000000p-1},
+    {0x1.921fb54442d18p-1, 0x1.0000000000000p+0}};
 #endif
-RSK_TABLE double kRskAtanP[20] = {
-    -0x1.5555555555555p-2, 0x1.9999999999620p-3,  -0x1.24924924753ecp-3, 0x1.c71c71bb00a6cp-4,
-    -0x1.745d15ee35819p-4, 0x1.3b1399d1dcdc7p-4,  -0x1.110fff599e4d2p-4, 0x1.e1d0239d392a6p-5,
-    -0x1.aebbb1647a168p-5, 0x1.841dcf603a209p-5,  -0x1.5d02278205cc7p-5, 0x1.3328700bb8169p-5,
-    -0x1.00390504e9f2fp-5, 0x1.843f4bca23369p-6,  -0x1.fd0e4de8fed90p-7, 0x1.123baedb61abdp-7,
-    -0x1.ca3677db66678p-9, 0x1.1325b2f8964bep-10, -0x1.a359b96a4eee4p-13, 0x1.2f07811f9f6e9p-16};
 
-// a / b for finite a >= 0 and normal b > 0
+// a / b for finite a and normal b > 0
 RSK_HD double rsk_div(double a, double b) {
 #if defined(__CUDA_ARCH__)
   double r;
@@ -107,13 +113,26 @@ RSK_HD double rsk_sqrt(double x) {
 // atan2(y, x) for finite arguments, not both zero; result in (-pi, pi]
 RSK_HD double rsk_atan2(double y, double x) {
 #if defined(__CUDA_ARCH__)
-  const double ay = fabs(y), ax = fabs(x);
-  const double t = rsk_div(fmin(ax, ay), fmax(ax, ay));
-  const double s = t * t;
-  double p = kRskAtanP[19];
-#pragma unroll
-  for (int i = 18; i >= 0; --i) p = fma(p, s, kRskAtanP[i]);
-  double r = fma(t * s, p, t);
+  double ay = fabs(y), ax = fabs(x);
+  if (fmax(ax, ay) < 1e-30) {  // keep the single-precision index meaningful (exactly-at-zenith directions)
+    ay *= 0x1p+200;
+    ax *= 0x1p+200;
+  }
+  const double mn = fmin(ax, ay), mx = fmax(ax, ay);
+  int k = __float2int_rn(8.0f * __fdividef((float)mn, (float)mx));
+  k = min(max(k, 0), 8);
+  const double2 tab = __ldg(&kRskAtanTab[k]);
+  const double num = fma(-tab.y, mx, mn);
+  const double den = fma(tab.y, mn, mx);
+  const double u = rsk_div(num, den);
+  const double s = u * u;
+  double p = 0x1.35e39ab2b4160p-4;
+  p = fma(p, s, -0x1.74538fb4bb13fp-4);
+  p = fma(p, s, 0x1.c71c69b1ebea4p-4);
+  p = fma(p, s, -0x1.249249230555ap-3);
+  p = fma(p, s, 0x1.999999999961ep-3);
+  p = fma(p, s, -0x1.5555555555555p-2);
+  double r = tab.x + fma(u * s, p, u);
   r = ay > ax ? RSK_HALFPI - r : r;
   r = x < 0.0 ? RSK_DPI - r : r;
   return copysign(r, y);
@@ -166,11 +185,19 @@ struct RskAltAz {
   double l, m, n;   // direction cosines: east, north, up
 };
 
-// (px,py,pz): unit vector of the component in the catalogue frame.  WANT_LMN = false skips the
-// direction cosines (the LST-sweep kernel does not always need them).
-template <bool WANT_LMN>
+// A context is "folded" when it has no diurnal-aberration term and no refraction (every context astropy
+// builds for the reference's AltAz(obstime, location), skymodel.py:2453): rsk_pack_context then multiplies
+// the latitude rotation into a1 and stores sphi = 1, cphi = 0, and the chain below skips the steps that
+// have become identities.
+RSK_HD bool rsk_ctx_folded(const RskCtx& c) {
+  return c.cphi == 0.0 && c.sphi == 1.0 && c.diurab == 0.0 && c.refa == 0.0 && c.refb == 0.0;
+}
+
+// (px,py,pz): unit vector of the component in the catalogue frame (in ICRS already when FRAME_DONE).
+// WANT_LMN = false skips the direction cosines (the LST-sweep kernel does not always need them).
+template <bool WANT_LMN, bool FRAME_DONE = false>
 RSK_HD RskAltAz rsk_chain_t(const RskCtx& c, double px, double py, double pz) {
-  if (c.m_ident == 0.0) {
+  if (!FRAME_DONE && c.m_ident == 0.0) {
     const double x = c.m[0] * px + c.m[1] * py + c.m[2] * pz;
     const double y = c.m[3] * px + c.m[4] * py + c.m[5] * pz;
     const double z = c.m[6] * px + c.m[7] * py + c.m[8] * pz;
@@ -178,10 +205,19 @@ RSK_HD RskAltAz rsk_chain_t(const RskCtx& c, double px, double py, double pz) {
   }
   // eraLd(bm=1, p, q=p, e=eh, em, dlim=1e-6): light deflection by the Sun (astropy atciqz sets q = p
   // for coordinates without distance, which is every SkyModel component).  p x (e x p) is expanded as
-  // e (p.p) - p (p.e), and q.(q+e) = p.p + p.e.
+  // e (p.p) - p (p.e), and q.(q+e) = p.p + p.e.  The deflection is below 1e-5 rad, so a quotient good to
+  // 2^-40 (reciprocal seed + one Newton step) leaves an error below 1e-17 rad.
   const double pp = px * px + py * py + pz * pz;
   const double pe = px * c.eh[0] + py * c.eh[1] + pz * c.eh[2];
-  const double w = rsk_div(c.w2, fmax(pp + pe, 1e-6));  // SRS / em / max(q.(q+e), dlim)
+#if defined(__CUDA_ARCH__)
+  const double den = fmax(pp + pe, 1e-6);
+  double rd;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rd) : "d"(den));
+  rd = fma(fma(-den, rd, 1.0), rd, rd);
+  const double w = c.w2 * rd;  // SRS / em / max(q.(q+e), dlim)
+#else
+  const double w = c.w2 / fmax(pp + pe, 1e-6);
+#endif
   const double nx = px + w * (c.eh[0] * pp - px * pe);
   const double ny = py + w * (c.eh[1] * pp - py * pe);
   const double nz = pz + w * (c.eh[2] * pp - pz * pe);
@@ -191,6 +227,29 @@ RSK_HD RskAltAz rsk_chain_t(const RskCtx& c, double px, double py, double pz) {
   double ax = nx * c.bm1 + w1 * c.v[0] + c.w2 * (c.v[0] - pdv * nx);
   double ay = ny * c.bm1 + w1 * c.v[1] + c.w2 * (c.v[1] - pdv * ny);
   double az_ = nz * c.bm1 + w1 * c.v[2] + c.w2 * (c.v[2] - pdv * nz);
+  RskAltAz o;
+  if (rsk_ctx_folded(c)) {
+    // No diurnal aberration, no refraction: everything after the aberration is one rotation (a1 holds
+    // latitude . polar motion . Earth rotation . bpn) and both angles are ratios of its components, so the
+    // normalisation of eraAb is not needed for them.
+    const double xaeo = c.a1[0] * ax + c.a1[1] * ay + c.a1[2] * az_;
+    const double yaeo = c.a1[3] * ax + c.a1[4] * ay + c.a1[5] * az_;
+    const double zaeo = c.a1[6] * ax + c.a1[7] * ay + c.a1[8] * az_;
+    const double azobs = (xaeo != 0.0 || yaeo != 0.0) ? rsk_atan2(yaeo, -xaeo) : 0.0;
+    const double r2 = xaeo * xaeo + yaeo * yaeo;
+    const double rxy = rsk_sqrt(r2);
+    o.alt = RSK_HALFPI - rsk_atan2(rxy, zaeo);
+    o.az = azobs < 0.0 ? azobs + RSK_D2PI : azobs;
+    if (WANT_LMN) {
+      const double ninv = rsk_rsqrt(r2 + zaeo * zaeo);
+      o.l = yaeo * ninv;
+      o.m = -xaeo * ninv;
+      o.n = zaeo * ninv;
+    } else {
+      o.l = o.m = o.n = 0.0;
+    }
+    return o;
+  }
   const double rinv = rsk_rsqrt(ax * ax + ay * ay + az_ * az_);
   ax *= rinv; ay *= rinv; az_ *= rinv;
   // eraRxp(bpn) + eraAtioq up to the polar-motion step, as one host-built rotation.  (ERFA goes
@@ -226,7 +285,6 @@ RSK_HD RskAltAz rsk_chain_t(const RskCtx& c, double px, double py, double pz) {
   }
   const double rxy = rsk_sqrt(xaeo * xaeo + yaeo * yaeo);
   const double zdobs = rsk_atan2(rxy, zaeo);
-  RskAltAz o;
   o.alt = RSK_HALFPI - zdobs;                       // astropy: lat = PIOVER2 - zen
   o.az = azobs < 0.0 ? azobs + RSK_D2PI : azobs;    // eraAnp
   if (WANT_LMN) {

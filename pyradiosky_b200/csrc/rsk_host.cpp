@@ -353,13 +353,25 @@ int rsk_pack_context(const double* astrom, const double* frame2icrs, double* ctx
   pm.a[0] = cx;       pm.a[1] = 0.0; pm.a[2] = sx;
   pm.a[3] = sx * sy;  pm.a[4] = cy;  pm.a[5] = -cx * sy;
   pm.a[6] = -sx * cy; pm.a[7] = sy;  pm.a[8] = cx * cy;
-  const M3 a1 = mul(pm, mul(rotz(astrom[A_ERAL]), bpn));
-  memcpy(c.a1, a1.a, sizeof(a1.a));
+  M3 a1 = mul(pm, mul(rotz(astrom[A_ERAL]), bpn));
   c.sphi = astrom[A_SPHI];
   c.cphi = astrom[A_CPHI];
   c.diurab = astrom[A_DIURAB];
   c.refa = astrom[A_REFA];
   c.refb = astrom[A_REFB];
+  if (c.diurab == 0.0 && c.refa == 0.0 && c.refb == 0.0) {
+    // Nothing non-linear sits between the polar-motion step and the latitude rotation (eraApco sets diurab
+    // = 0; AltAz without pressure gives refa = refb = 0): fold the latitude rotation into a1 and mark the
+    // context as folded (rsk_ctx_folded) so the kernels skip the identity steps.
+    M3 rl;
+    rl.a[0] = c.sphi; rl.a[1] = 0.0; rl.a[2] = -c.cphi;
+    rl.a[3] = 0.0;    rl.a[4] = 1.0; rl.a[5] = 0.0;
+    rl.a[6] = c.cphi; rl.a[7] = 0.0; rl.a[8] = c.sphi;
+    a1 = mul(rl, a1);
+    c.sphi = 1.0;
+    c.cphi = 0.0;
+  }
+  memcpy(c.a1, a1.a, sizeof(a1.a));
   c.w2 = RSK_SRS / astrom[A_EM];
   bool is_ident = true;
   const M3 id = ident();

@@ -127,13 +127,20 @@ __global__ void __launch_bounds__(kThreads) k_positions_sweep(const CoordSrc cs,
       double sl, cl, sb, cb;
       frame_trig(cs, idx[j], sl, cl, sb, cb);
       px[j] = cl * cb; py[j] = sl * cb; pz[j] = sb;
+      if (s_ctx[0].m_ident == 0.0) {  // catalogue frame -> ICRS: the same matrix in every context, applied once
+        const double* m = s_ctx[0].m;
+        const double x = m[0] * px[j] + m[1] * py[j] + m[2] * pz[j];
+        const double y = m[3] * px[j] + m[4] * py[j] + m[5] * pz[j];
+        const double z = m[6] * px[j] + m[7] * py[j] + m[8] * pz[j];
+        px[j] = x; py[j] = y; pz[j] = z;
+      }
     }
   }
   for (int k = 0; k < ntc; ++k) {
     const int64_t t = t0 + k;
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
-      const RskAltAz o = rsk_chain_t<WANT_LMN>(s_ctx[k], px[j], py[j], pz[j]);
+      const RskAltAz o = rsk_chain_t<WANT_LMN, true>(s_ctx[k], px[j], py[j], pz[j]);
       if (idx[j] < n) {
         const int64_t i = idx[j];
         __stcs(alt_az + (2 * t) * n + i, o.alt);

@@ -148,7 +148,17 @@ def test_packed_context_reproduces_chain(librsk, hera):
     v = E.s2c(E.anp(ri) - a[E.I_ERAL], di)
     sx, cx = np.sin(a[E.I_XPL]), np.cos(a[E.I_XPL]); sy, cy = np.sin(a[E.I_YPL]), np.cos(a[E.I_YPL])
     hd = np.array([cx * v[0] + sx * v[2], sx * sy * v[0] + cy * v[1] - cx * sy * v[2], -sx * cy * v[0] + sy * v[1] + cx * cy * v[2]])
-    assert np.abs(a1 @ p - hd).max() < 1e-15
+    # no diurnal aberration and no refraction in this context: the latitude rotation is folded in as well
+    sphi, cphi = a[E.I_SPHI], a[E.I_CPHI]
+    ae = np.array([sphi * hd[0] - cphi * hd[2], hd[1], cphi * hd[0] + sphi * hd[2]])
+    assert np.abs(a1 @ p - ae).max() < 1e-15
+    assert ctx[17] == 1.0 and ctx[18] == 0.0
+    # a context with a diurnal-aberration term is left unfolded
+    b = a.copy()
+    b[E.I_DIURAB] = 1e-6
+    ctxb = astrometry.pack_context(b)
+    assert ctxb[17] == sphi and ctxb[18] == cphi and ctxb[19] == 1e-6
+    assert np.abs(ctxb[8:17].reshape(3, 3) @ p - hd).max() < 1e-15
     assert ctx[22] == E.SRS / a[E.I_EM] and ctx[23] == 1.0
     batch = astrometry.pack_contexts(np.stack([a, a]))
     assert batch.shape == (2, 34) and np.array_equal(batch[0], ctx) and np.array_equal(batch[1], ctx)
