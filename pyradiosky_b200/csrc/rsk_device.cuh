@@ -55,8 +55,8 @@ static_assert(sizeof(RskCtx) == 34 * sizeof(double), "RskCtx layout");
 //   atan(t) = atan(t_k) + atan((min - t_k max) / (max + t_k min)),
 // so the reduction costs two fused multiply-adds *before* the one division, the interval index k comes from a
 // single-precision quotient (fp32 / SFU pipes, not the fp64 pipe), and the remaining argument is below
-// 1/16 + 2^-20: atan(u) = u + u s P(s), s = u^2, with a degree-5 P (tools/gen_atan_poly.py, |u| <= 0.08: max
-// error of the double-precision Horner evaluation < 1e-17).  The previous form, a degree-19 polynomial on
+// 1/16 + 2^-20: atan(u) = u + u s Q(s), s = u^2, with a degree-4 Q (mpmath.chebyfit on s in [0, 0.0064] as in
+// tools/gen_atan_poly.py: max error of the double-precision Horner evaluation 1.4e-17).  The previous form, a degree-19 polynomial on
 // [0, 1], spent twice the fp64 issue slots; the LST sweep is bound by that pipe (profiles/r01_summary.md).
 #if defined(__CUDACC__)
 __device__ const double2 kRskAtanTab[9] = {  // (atan(k/8), k/8)
@@ -69,6 +69,9 @@ __device__ const double2 kRskAtanTab[9] = {  // (atan(k/8), k/8)
     {0x1.4978fa3269ee1p-1, 0x1.8000000000000p-1},
     {0x1.700a7c5784634p-1, 0x1.c000000000000p-1},
     {0x1.921fb54442d18p-1, 0x1.0000000000000p+0}};
+// atan(u) = u + u s Q(s), s = u^2, |u| <= 0.08 (degree 4: 1.4e-17 maximum error)
+__constant__ double kRskAtanQ[5] = {-0x1.5555555555539p-2, 0x1.999999992c40dp-3, -0x1.2492470e5748ap-3,
+                                    0x1.c7154d717ee6ap-4, -0x1.6f5e1489511f6p-4};
 #endif
 
 // a / b for finite a and normal b > 0
@@ -102,7 +105,7 @@ RSK_HD double rsk_rsqrt(double x) {
 // sqrt(x) for x >= 0 (0 -> 0)
 RSK_HD double rsk_sqrt(double x) {
 #if defined(__CUDA_ARCH__)
-  const double r = rsk_rsqrt(fmax(x, 1e-300));
+  const double r = rsk_rsqrt(x + 1e-300);  // x = 0 -> 0 (the bias only matters below 1e-284)
   const double s = x * r;
   return fma(fma(-s, s, x), 0.5 * r, s);
 #else
@@ -110,34 +113,41 @@ RSK_HD double rsk_sqrt(double x) {
 #endif
 }
 
-// atan2(y, x) for finite arguments, not both zero; result in (-pi, pi]
+// atan2(y, x) for finite arguments; result in (-pi, pi], 0 for y = x = 0.  Written for the issue slots it
+// takes, not only the fp64 ones (the sweep kernel is issue-bound): explicit compare + select instead of
+// fmin/fmax (whose NaN handling costs ~8 instructions each), coefficients in the constant bank (operands of
+// DFMA, no register moves), no branch.
 RSK_HD double rsk_atan2(double y, double x) {
 #if defined(__CUDA_ARCH__)
-  double ay = fabs(y), ax = fabs(x);
-  if (fmax(ax, ay) < 1e-30) {  // keep the single-precision index meaningful (exactly-at-zenith directions)
-    ay *= 0x1p+200;
-    ax *= 0x1p+200;
-  }
-  const double mn = fmin(ax, ay), mx = fmax(ax, ay);
-  int k = __float2int_rn(8.0f * __fdividef((float)mn, (float)mx));
+  const bool sw = fabs(y) > fabs(x);
+  const double mn = fabs(sw ? x : y), mx = fabs(sw ? y : x);
+  // interval index from a single-precision quotient: fp32 / SFU pipes.  (float)mx == 0 needs mx < 1e-45, i.e.
+  // a direction closer than that to the pole of the angle, where k = 0 still gives a finite, if inexact, value.
+  float fr;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(fr) : "f"((float)mx));
+  int k = __float2int_rn(8.0f * ((float)mn * fr));
   k = min(max(k, 0), 8);
   const double2 tab = __ldg(&kRskAtanTab[k]);
   const double num = fma(-tab.y, mx, mn);
   const double den = fma(tab.y, mn, mx);
-  const double u = rsk_div(num, den);
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+  const double e = fma(-den, r, 1.0);
+  r = fma(r, fma(e, e, e), r);  // 1 / den to ~2^-60
+  const double u = num * r;     // |u| <= 0.07: an ulp of u is below 1e-17
   const double s = u * u;
-  double p = 0x1.35e39ab2b4160p-4;
-  p = fma(p, s, -0x1.74538fb4bb13fp-4);
-  p = fma(p, s, 0x1.c71c69b1ebea4p-4);
-  p = fma(p, s, -0x1.249249230555ap-3);
-  p = fma(p, s, 0x1.999999999961ep-3);
-  p = fma(p, s, -0x1.5555555555555p-2);
-  double r = tab.x + fma(u * s, p, u);
-  r = ay > ax ? RSK_HALFPI - r : r;
-  r = x < 0.0 ? RSK_DPI - r : r;
-  return copysign(r, y);
+  double p = kRskAtanQ[4];
+  p = fma(p, s, kRskAtanQ[3]);
+  p = fma(p, s, kRskAtanQ[2]);
+  p = fma(p, s, kRskAtanQ[1]);
+  p = fma(p, s, kRskAtanQ[0]);
+  double a = tab.x + fma(u * s, p, u);
+  a = sw ? RSK_HALFPI - a : a;
+  a = x < 0.0 ? RSK_DPI - a : a;
+  a = mx > 0.0 ? a : 0.0;  // atan2(0, 0) = 0 (eraAtioq's own convention for the azimuth at the zenith)
+  return copysign(a, y);
 #else
-  return atan2(y, x);
+  return (y != 0.0 || x != 0.0) ? atan2(y, x) : 0.0;
 #endif
 }
 
@@ -235,7 +245,7 @@ RSK_HD RskAltAz rsk_chain_t(const RskCtx& c, double px, double py, double pz) {
     const double xaeo = c.a1[0] * ax + c.a1[1] * ay + c.a1[2] * az_;
     const double yaeo = c.a1[3] * ax + c.a1[4] * ay + c.a1[5] * az_;
     const double zaeo = c.a1[6] * ax + c.a1[7] * ay + c.a1[8] * az_;
-    const double azobs = (xaeo != 0.0 || yaeo != 0.0) ? rsk_atan2(yaeo, -xaeo) : 0.0;
+    const double azobs = rsk_atan2(yaeo, -xaeo);  // 0 at the zenith, as eraAtioq
     const double r2 = xaeo * xaeo + yaeo * yaeo;
     const double rxy = rsk_sqrt(r2);
     o.alt = RSK_HALFPI - rsk_atan2(rxy, zaeo);
@@ -266,7 +276,7 @@ RSK_HD RskAltAz rsk_chain_t(const RskCtx& c, double px, double py, double pz) {
   const double xaet = c.sphi * xhdt - c.cphi * zhdt;
   const double yaet = yhdt;
   const double zaet = c.cphi * xhdt + c.sphi * zhdt;
-  const double azobs = (xaet != 0.0 || yaet != 0.0) ? rsk_atan2(yaet, -xaet) : 0.0;
+  const double azobs = rsk_atan2(yaet, -xaet);  // 0 at the zenith, as eraAtioq
   // A tan z + B tan^3 z refraction (identity for refa = refb = 0, which is what AltAz(obstime,
   // location) with its default zero pressure gives at skymodel.py:2453)
   double xaeo = xaet, yaeo = yaet, zaeo = zaet;

@@ -136,22 +136,33 @@ __global__ void __launch_bounds__(kThreads) k_positions_sweep(const CoordSrc cs,
       }
     }
   }
+  // running output pointers (one 64-bit add per plane and time step instead of a 64-bit multiply per store)
+  double* pa[CPT];
+  double* pl[CPT];
+  uint8_t* pm[CPT];
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) {
+    pa[j] = alt_az + (2 * t0) * n + idx[j];
+    pl[j] = WANT_LMN ? lmn + (3 * t0) * n + idx[j] : nullptr;
+    pm[j] = above ? above + t0 * n + idx[j] : nullptr;
+  }
   for (int k = 0; k < ntc; ++k) {
-    const int64_t t = t0 + k;
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
       const RskAltAz o = rsk_chain_t<WANT_LMN, true>(s_ctx[k], px[j], py[j], pz[j]);
       if (idx[j] < n) {
-        const int64_t i = idx[j];
-        __stcs(alt_az + (2 * t) * n + i, o.alt);
-        __stcs(alt_az + (2 * t + 1) * n + i, o.az);
+        __stcs(pa[j], o.alt);
+        __stcs(pa[j] + n, o.az);
         if (WANT_LMN) {
-          __stcs(lmn + (3 * t) * n + i, o.l);
-          __stcs(lmn + (3 * t + 1) * n + i, o.m);
-          __stcs(lmn + (3 * t + 2) * n + i, o.n);
+          __stcs(pl[j], o.l);
+          __stcs(pl[j] + n, o.m);
+          __stcs(pl[j] + 2 * n, o.n);
         }
-        if (above) above[t * n + i] = o.alt > 0.0 ? 1 : 0;
+        if (above) *pm[j] = o.alt > 0.0 ? 1 : 0;
       }
+      pa[j] += 2 * n;
+      if (WANT_LMN) pl[j] += 3 * n;
+      if (above) pm[j] += n;
     }
   }
 }
