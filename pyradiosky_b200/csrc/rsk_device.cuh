@@ -102,12 +102,17 @@ RSK_HD double rsk_rsqrt(double x) {
 #endif
 }
 
-// sqrt(x) for x >= 0 (0 -> 0)
+// sqrt(x) for x >= 0 (0 -> 0): reciprocal-square-root seed, one coupled (Goldschmidt) iteration on
+// g ~ sqrt(x), h ~ 1 / (2 sqrt(x)), one residual correction: 7 fp64 instructions, < 1 ulp.
 RSK_HD double rsk_sqrt(double x) {
 #if defined(__CUDA_ARCH__)
-  const double r = rsk_rsqrt(x + 1e-300);  // x = 0 -> 0 (the bias only matters below 1e-284)
-  const double s = x * r;
-  return fma(fma(-s, s, x), 0.5 * r, s);
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x + 1e-300));  // x = 0 -> 0 (the bias matters below 1e-284)
+  double g = x * r, h = 0.5 * r;
+  const double e = fma(-h, g, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  return fma(fma(-g, g, x), h, g);
 #else
   return sqrt(x);
 #endif
@@ -117,7 +122,9 @@ RSK_HD double rsk_sqrt(double x) {
 // takes, not only the fp64 ones (the sweep kernel is issue-bound): explicit compare + select instead of
 // fmin/fmax (whose NaN handling costs ~8 instructions each), coefficients in the constant bank (operands of
 // DFMA, no register moves), no branch.
-RSK_HD double rsk_atan2(double y, double x) {
+// XPOS: the caller guarantees x >= 0 and (x, y) != (0, 0) (result in [-pi/2, pi/2]; two fix-ups fewer).
+template <bool XPOS>
+RSK_HD double rsk_atan2_t(double y, double x) {
 #if defined(__CUDA_ARCH__)
   const bool sw = fabs(y) > fabs(x);
   const double mn = fabs(sw ? x : y), mx = fabs(sw ? y : x);
@@ -143,13 +150,17 @@ RSK_HD double rsk_atan2(double y, double x) {
   p = fma(p, s, kRskAtanQ[0]);
   double a = tab.x + fma(u * s, p, u);
   a = sw ? RSK_HALFPI - a : a;
-  a = x < 0.0 ? RSK_DPI - a : a;
-  a = mx > 0.0 ? a : 0.0;  // atan2(0, 0) = 0 (eraAtioq's own convention for the azimuth at the zenith)
+  if (!XPOS) {
+    a = x < 0.0 ? RSK_DPI - a : a;
+    a = mx > 0.0 ? a : 0.0;  // atan2(0, 0) = 0 (eraAtioq's own convention for the azimuth at the zenith)
+  }
   return copysign(a, y);
 #else
   return (y != 0.0 || x != 0.0) ? atan2(y, x) : 0.0;
 #endif
 }
+
+RSK_HD double rsk_atan2(double y, double x) { return rsk_atan2_t<false>(y, x); }
 
 // sin and cos of an angle of catalogue size (|x| <= 16: longitudes, latitudes, HEALPix azimuths): two-term
 // Cody-Waite reduction by pi/2 (exact for |k| <= 10) and the fdlibm kernel polynomials on [-pi/4, pi/4]
@@ -205,8 +216,10 @@ RSK_HD bool rsk_ctx_folded(const RskCtx& c) {
 
 // (px,py,pz): unit vector of the component in the catalogue frame (in ICRS already when FRAME_DONE).
 // WANT_LMN = false skips the direction cosines (the LST-sweep kernel does not always need them).
-template <bool WANT_LMN, bool FRAME_DONE = false>
-RSK_HD RskAltAz rsk_chain_t(const RskCtx& c, double px, double py, double pz) {
+// FOLD: 0 = look at the context, 1 = the caller has checked rsk_ctx_folded(c) already (the sweep kernel does it
+// once per block, outside its time loop).
+template <bool WANT_LMN, bool FRAME_DONE = false, int FOLD = 0>
+RSK_HD RskAltAz rsk_chain_t(const RskCtx& c, double px, double py, double pz, double pp_in = -1.0) {
   if (!FRAME_DONE && c.m_ident == 0.0) {
     const double x = c.m[0] * px + c.m[1] * py + c.m[2] * pz;
     const double y = c.m[3] * px + c.m[4] * py + c.m[5] * pz;
@@ -217,10 +230,12 @@ RSK_HD RskAltAz rsk_chain_t(const RskCtx& c, double px, double py, double pz) {
   // for coordinates without distance, which is every SkyModel component).  p x (e x p) is expanded as
   // e (p.p) - p (p.e), and q.(q+e) = p.p + p.e.  The deflection is below 1e-5 rad, so a quotient good to
   // 2^-40 (reciprocal seed + one Newton step) leaves an error below 1e-17 rad.
-  const double pp = px * px + py * py + pz * pz;
+  // p.p: time independent, so callers that loop over contexts pass it in (pp_in >= 0)
+  const double pp = (FRAME_DONE && pp_in >= 0.0) ? pp_in : px * px + py * py + pz * pz;
   const double pe = px * c.eh[0] + py * c.eh[1] + pz * c.eh[2];
 #if defined(__CUDA_ARCH__)
-  const double den = fmax(pp + pe, 1e-6);
+  double den = pp + pe;
+  den = den < 1e-6 ? 1e-6 : den;
   double rd;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rd) : "d"(den));
   rd = fma(fma(-den, rd, 1.0), rd, rd);
@@ -232,13 +247,15 @@ RSK_HD RskAltAz rsk_chain_t(const RskCtx& c, double px, double py, double pz) {
   const double ny = py + w * (c.eh[1] * pp - py * pe);
   const double nz = pz + w * (c.eh[2] * pp - pz * pe);
   // eraAb(pnat, v, s=em, bm1): annual (+ observer) aberration
+  // p' = pnat bm1 + w1 v + w2 (v - (pnat.v) pnat), grouped as pnat (bm1 - w2 pnat.v) + v (w1 + w2)
   const double pdv = nx * c.v[0] + ny * c.v[1] + nz * c.v[2];
-  const double w1 = 1.0 + pdv * c.inv1pbm1;
-  double ax = nx * c.bm1 + w1 * c.v[0] + c.w2 * (c.v[0] - pdv * nx);
-  double ay = ny * c.bm1 + w1 * c.v[1] + c.w2 * (c.v[1] - pdv * ny);
-  double az_ = nz * c.bm1 + w1 * c.v[2] + c.w2 * (c.v[2] - pdv * nz);
+  const double g1 = fma(-c.w2, pdv, c.bm1);
+  const double g2 = fma(pdv, c.inv1pbm1, 1.0) + c.w2;
+  double ax = fma(nx, g1, c.v[0] * g2);
+  double ay = fma(ny, g1, c.v[1] * g2);
+  double az_ = fma(nz, g1, c.v[2] * g2);
   RskAltAz o;
-  if (rsk_ctx_folded(c)) {
+  if (FOLD == 1 || rsk_ctx_folded(c)) {
     // No diurnal aberration, no refraction: everything after the aberration is one rotation (a1 holds
     // latitude . polar motion . Earth rotation . bpn) and both angles are ratios of its components, so the
     // normalisation of eraAb is not needed for them.
@@ -248,7 +265,9 @@ RSK_HD RskAltAz rsk_chain_t(const RskCtx& c, double px, double py, double pz) {
     const double azobs = rsk_atan2(yaeo, -xaeo);  // 0 at the zenith, as eraAtioq
     const double r2 = xaeo * xaeo + yaeo * yaeo;
     const double rxy = rsk_sqrt(r2);
-    o.alt = RSK_HALFPI - rsk_atan2(rxy, zaeo);
+    // astropy forms pi/2 - zd with zd = atan2(rxy, z); atan2(z, rxy) is the same angle (to an ulp of pi/2)
+    // without the two reflections
+    o.alt = rsk_atan2_t<true>(zaeo, rxy);
     o.az = azobs < 0.0 ? azobs + RSK_D2PI : azobs;
     if (WANT_LMN) {
       const double ninv = rsk_rsqrt(r2 + zaeo * zaeo);

@@ -98,11 +98,44 @@ __global__ void __launch_bounds__(kThreads) k_positions(const CoordSrc cs, const
   if (above) above[i] = o.alt > 0.0 ? 1 : 0;  // skymodel.py:2479
 }
 
+// minimum resident blocks per SM asked of ptxas for the sweep kernel (register cap); -DRSK_SWEEP_MINB=n to tune
+#ifndef RSK_SWEEP_MINB
+#define RSK_SWEEP_MINB 4  // 64 registers, 4 x 256 threads per SM: best of the measured caps (profiles/r01_sweep_tuning.log)
+#endif
+
+template <int CPT, bool WANT_LMN, int FOLD>
+__device__ __forceinline__ void sweep_times(const RskCtx* s_ctx, const int ntc, const int64_t n, const int64_t* idx,
+                                            const double* px, const double* py, const double* pz, double** pa,
+                                            double** pl, uint8_t** pm) {
+  double pp[CPT];
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) pp[j] = px[j] * px[j] + py[j] * py[j] + pz[j] * pz[j];
+  for (int k = 0; k < ntc; ++k) {
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      const RskAltAz o = rsk_chain_t<WANT_LMN, true, FOLD>(s_ctx[k], px[j], py[j], pz[j], pp[j]);
+      if (idx[j] < n) {
+        __stcs(pa[j], o.alt);
+        __stcs(pa[j] + n, o.az);
+        if (WANT_LMN) {
+          __stcs(pl[j], o.l);
+          __stcs(pl[j] + n, o.m);
+          __stcs(pl[j] + 2 * n, o.n);
+        }
+        if (pm[j]) *pm[j] = o.alt > 0.0 ? 1 : 0;
+      }
+      pa[j] += 2 * n;
+      if (WANT_LMN) pl[j] += 3 * n;
+      if (pm[j]) pm[j] += n;
+    }
+  }
+}
+
 // K1 sweep: T contexts per launch.  Block = (CPT x kThreads) components x kSweepTimes time steps; the
 // contexts are staged in shared memory; the per-component trigonometry is hoisted out of the time loop;
 // CPT components per thread share every context load and give the fp64 pipe independent chains.
 template <int CPT, bool WANT_LMN>
-__global__ void __launch_bounds__(kThreads) k_positions_sweep(const CoordSrc cs, const int64_t n,
+__global__ void __launch_bounds__(kThreads, RSK_SWEEP_MINB) k_positions_sweep(const CoordSrc cs, const int64_t n,
                                                               const double* __restrict__ ctx_g, const int64_t nt,
                                                               const int ntchunks, double* __restrict__ alt_az,
                                                               double* __restrict__ lmn, uint8_t* __restrict__ above) {
@@ -146,25 +179,14 @@ __global__ void __launch_bounds__(kThreads) k_positions_sweep(const CoordSrc cs,
     pl[j] = WANT_LMN ? lmn + (3 * t0) * n + idx[j] : nullptr;
     pm[j] = above ? above + t0 * n + idx[j] : nullptr;
   }
-  for (int k = 0; k < ntc; ++k) {
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-      const RskAltAz o = rsk_chain_t<WANT_LMN, true>(s_ctx[k], px[j], py[j], pz[j]);
-      if (idx[j] < n) {
-        __stcs(pa[j], o.alt);
-        __stcs(pa[j] + n, o.az);
-        if (WANT_LMN) {
-          __stcs(pl[j], o.l);
-          __stcs(pl[j] + n, o.m);
-          __stcs(pl[j] + 2 * n, o.n);
-        }
-        if (above) *pm[j] = o.alt > 0.0 ? 1 : 0;
-      }
-      pa[j] += 2 * n;
-      if (WANT_LMN) pl[j] += 3 * n;
-      if (above) pm[j] += n;
-    }
-  }
+  // every context of this block folded (the case for contexts built for the reference's AltAz frame)?  Decided
+  // once here, so the time loop carries no per-step test.
+  bool folded = true;
+  for (int k = 0; k < ntc; ++k) folded = folded && rsk_ctx_folded(s_ctx[k]);
+  if (folded)
+    sweep_times<CPT, WANT_LMN, 1>(s_ctx, ntc, n, idx, px, py, pz, pa, pl, pm);
+  else
+    sweep_times<CPT, WANT_LMN, 0>(s_ctx, ntc, n, idx, px, py, pz, pa, pl, pm);
 }
 
 __global__ void __launch_bounds__(kThreads) k_healpix_lonlat(const int64_t nside, const int nested,
@@ -961,16 +983,24 @@ int rsk_positions_sweep(const RskCoords* coords, int64_t n, const double* ctx, i
   if (!ctx || !alt_az) return RSK_ERR_NULL;
   if (n < 0 || T < 0) return RSK_ERR_SIZE;
   if (n == 0 || T == 0) return RSK_OK;
-  constexpr int kCpt = 2;  // components per thread in the sweep kernel
+  // components per thread (independent chains per thread): 1 measured best once the chain was trimmed to ~90 fp64
+  // instructions (profiles/r01_sweep_tuning.log); RSK_SWEEP_CPT = 1, 2 or 4 overrides it for tuning runs
+  int cpt = tuning_int("RSK_SWEEP_CPT", 1);
+  if (cpt != 1 && cpt != 2 && cpt != 4) cpt = 1;
   const int64_t ntchunks = (T + kSweepTimes - 1) / kSweepTimes;
-  const int64_t ntiles = (n + kCpt * kThreads - 1) / (kCpt * kThreads);
+  const int64_t ntiles = (n + cpt * kThreads - 1) / (cpt * kThreads);
   const int64_t nblocks = ntiles * ntchunks;
   if (nblocks > 0x7fffffffll) return RSK_ERR_SIZE;
   cudaStream_t st = (cudaStream_t)stream;
-  if (pos_lmn)
-    k_positions_sweep<kCpt, true><<<(unsigned)nblocks, kThreads, 0, st>>>(cs, n, ctx, T, (int)ntchunks, alt_az, pos_lmn, above);
-  else
-    k_positions_sweep<kCpt, false><<<(unsigned)nblocks, kThreads, 0, st>>>(cs, n, ctx, T, (int)ntchunks, alt_az, pos_lmn, above);
+  const unsigned grid = (unsigned)nblocks;
+  const int ntch = (int)ntchunks;
+#define RSK_SWEEP(C, L) k_positions_sweep<C, L><<<grid, kThreads, 0, st>>>(cs, n, ctx, T, ntch, alt_az, pos_lmn, above)
+  if (pos_lmn) {
+    if (cpt == 1) RSK_SWEEP(1, true); else if (cpt == 2) RSK_SWEEP(2, true); else RSK_SWEEP(4, true);
+  } else {
+    if (cpt == 1) RSK_SWEEP(1, false); else if (cpt == 2) RSK_SWEEP(2, false); else RSK_SWEEP(4, false);
+  }
+#undef RSK_SWEEP
   return launch_status();
 }
 
