@@ -407,7 +407,7 @@ RSK_HD void rsk_hpx_center(int64_t nside, int nested, int64_t pix, double& z, do
     z = (double)(2 * nside - jr_eq) * (2.0 / (3.0 * (double)nside));
     omz = 1.0 - fabs(z);
   }
-  st = sqrt(omz * (2.0 - omz));
+  st = rsk_sqrt(omz * (2.0 - omz));
   phi = ((double)jp - (double)(kshift + 1) * 0.5) * (RSK_HALFPI / nrf);
 }
 

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kThreads) k_healpix_lonlat(const int64_t nside
   double z, st, phi;
   rsk_hpx_center(nside, nested, pix, z, st, phi);
   lon[i] = phi;
-  lat[i] = atan2(z, st);
+  lat[i] = rsk_atan2_t<true>(z, st);  // st >= 0, (z, st) on the unit circle
 }
 
 // inverse of k_healpix_lonlat: the pixel each (lon, lat) falls in (astropy_healpix lonlat_to_healpix, called by
