@@ -386,7 +386,7 @@ def run_gpu(args):
 
     # ---- end to end through the public API with host buffers ----------------------------------------
     e2e_steps = max(2, min(args.steps, args.e2e_steps))
-    do_e2e = 64.0 * nf * max(counts) < 45e9
+    do_e2e = 64.0 * nf * max(counts) < 45e9 and args.e2e_steps > 0  # --e2e-steps 0: profiling runs only
     e2e_evals, d2h_bytes, h2d_bytes, e2e_s, e2e_route = 0, 0, 0, float('nan'), None
     if do_e2e:
         host_in = {k: torch.as_tensor(np.ascontiguousarray(v)).pin_memory() for k, v in model_kwargs(cat).items()
