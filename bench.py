@@ -412,22 +412,31 @@ def run_gpu(args):
             view = s.coherency_calc_to_host(freqs, host_out, slab=e2e_slab, packed=packed, nthreads=e2e_threads)
             if record:
                 e2e_evals += view.shape[2] * view.shape[3]
-                d2h_bytes += view.shape[2] * view.shape[3] * (32 if packed else 64)
+                if packed == "auto":
+                    npk, npl = s._e2e_route_counts
+                    d2h_bytes += view.shape[2] * view.shape[3] * (32 * npk + 64 * npl) / max(1, npk + npl)
+                else:
+                    d2h_bytes += view.shape[2] * view.shape[3] * (32 if packed else 64)
             return view
 
         trial = {}
-        for packed in (True, False):
+        routes = ("auto", True, False)
+        for packed in routes:
             e2e_step(0, False, packed)
+            if packed == "auto":  # two more untimed steps: the mixed route learns the host's unpack rate as it goes
+                e2e_step(0, False, packed)
+                e2e_step(0, False, packed)
             barrier()
             t0 = time.perf_counter()
             e2e_step(0, False, packed)
             barrier()
             trial[packed] = time.perf_counter() - t0
-        choice = torch.tensor([trial[True], trial[False]], dtype=torch.float64, device=dev)
+        choice = torch.tensor([trial[r] for r in routes], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(choice, op=dist.ReduceOp.MAX)
-        use_packed = bool(choice[0] <= choice[1])
-        e2e_route = "packed" if use_packed else "plain"
+        use_packed = routes[int(torch.argmin(choice).item())]
+        e2e_route = {"auto": "mixed", True: "packed", False: "plain"}[use_packed]
+        e2e_trials = {{"auto": "mixed", True: "packed", False: "plain"}[r]: float(c) * 1e3 for r, c in zip(routes, choice.cpu())}
         barrier()
         t0 = time.perf_counter()
         for k in range(e2e_steps):
@@ -475,11 +484,12 @@ def run_gpu(args):
             "e2e": ({"value": e2e_evals_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                      "d2h_bytes_per_step": d2h_bytes / e2e_steps, "steps": e2e_steps,
                      "ms_per_step": e2e_s / e2e_steps * 1e3,
-                     "route": e2e_route,
+                     "route": e2e_route, "route_trials_ms": e2e_trials,
                      "how": "pinned host inputs -> H2D -> SkyModel -> update_positions -> coherency_calc_to_host into the "
                             "(2,2,Nf,N_above) complex128 array in host memory; route 'packed' = Hermitian-packed slabs "
-                            "(32 B/eval over PCIe) unpacked by host threads, 'plain' = 64 B/eval copied as is; the faster "
-                            "of the two (one untimed trial each) is used"} if do_e2e else None),
+                            "(32 B/eval over PCIe) unpacked by host threads, 'plain' = 64 B/eval copied as is, 'mixed' = each slab takes "
+                            "whichever of the two finishes earlier given the measured host unpack rate; the fastest "
+                            "of the three (one untimed trial each) is used"} if do_e2e else None),
             "gpu_launches": 5 * args.steps,
             "clocks": sampler.summary(),
         }

@@ -28,6 +28,8 @@ import copy as _copy
 import ctypes
 import math
 import os
+import queue as _queue
+import threading as _threading
 import warnings
 
 import numpy as np
@@ -35,6 +37,10 @@ import torch
 
 from . import _lib, astrometry, spectral
 from .utils import _as_device_f64
+
+# running estimates used by coherency_calc_to_host(packed="auto"): PCIe device->host rate and the host cost of
+# expanding one packed evaluation (measured on every call; process-wide because they describe the machine)
+_E2E_STATE = {"link_bytes_per_s": 50e9, "unpack_s_per_eval": 1.0e-9}
 
 _JY_UNITS = {"point": "Jy", "healpix": "Jy / sr"}
 _K_UNITS = {"point": "K sr", "healpix": "K"}
@@ -960,6 +966,11 @@ class SkyModel:
         ``packed=False``: the full complex array is copied; ``host_out`` must be a flat *pinned* complex128
         tensor, and the call returns after the last copy has been queued (synchronise before reading).
 
+        ``packed="auto"`` (``host_out`` pinned): every slab takes whichever of the two routes finishes earlier
+        under a two-resource model -- the PCIe link (32 or 64 bytes per evaluation) and the host threads that
+        expand packed slabs -- so a slow or busy host is not the bottleneck and a fast one still halves the
+        wire bytes.  The unpack cost per evaluation is measured on every call and carried to the next one.
+
         Returns the (2, 2, Nfreqs, N_above) view of ``host_out``.
         """
         if self.spectral_type == "subband" and self._has_nan("stokes"):
@@ -973,7 +984,7 @@ class SkyModel:
             host_out = torch.from_numpy(host_out.reshape(-1))
         if host_out.dtype != torch.complex128 or host_out.numel() < need or host_out.is_cuda:
             raise ValueError(f"host_out must be a host complex128 buffer with at least {need} elements")
-        if not packed and not host_out.is_pinned():
+        if packed is False and not host_out.is_pinned():
             raise ValueError("host_out must be pinned when packed=False")
         view = host_out.reshape(-1)[:need].view(2, 2, nf, n_above)
         if need == 0:
@@ -983,7 +994,7 @@ class SkyModel:
             self._copy_stream = torch.cuda.Stream(self.device)
         copy = self._copy_stream
         slab = max(1, min(slab, nf))
-        if not packed:
+        if packed is False:
             bufs = [torch.empty((2, 2, slab, n_above), dtype=torch.complex128, device=self.device) for _ in range(2)]
             freed = [None, None]
             for i, f0 in enumerate(range(0, nf, slab)):
@@ -1007,37 +1018,106 @@ class SkyModel:
             for b in bufs:
                 b.record_stream(copy)
             return view
-        # packed route: device slab (4, slab, ld) real -> pinned staging -> threaded unpack into host_out
+        # packed / mixed route: device slab (4, slab, ld) real -> pinned staging -> threaded unpack into host_out;
+        # in "auto" mode some slabs instead leave as full complex rows straight into (pinned) host_out
         import os
+        import time as _time
 
+        auto = packed == "auto"
+        if auto and not host_out.is_pinned():
+            auto = False  # plain slabs need a DMA-able destination
         if nthreads is None:
             nthreads = max(1, min(32, (3 * (os.cpu_count() or 1)) // 4))  # leave cores for the DMA / main thread
         ld = -(-n_above // 32) * 32  # 256-byte aligned rows of doubles
         nbuf = 3  # ring of staging pairs: two slabs stay queued on the GPU while one is unpacked
-        key = (slab, ld)
+        key = (slab, ld, auto)
         st = self.__dict__.get("_staging")
         if st is None or st["key"] != key:
             st = dict(key=key,
                       dev=[torch.empty((4, slab, ld), dtype=torch.float64, device=self.device) for _ in range(nbuf)],
-                      host=[torch.empty((4, slab, ld), dtype=torch.float64, pin_memory=True) for _ in range(nbuf)])
+                      host=[torch.empty((4, slab, ld), dtype=torch.float64, pin_memory=True) for _ in range(nbuf)],
+                      cdev=[torch.empty((2, 2, slab, n_above), dtype=torch.complex128, device=self.device)
+                            for _ in range(2)] if auto else None)
             self._staging = st
         lib = _lib.load()
         out_ptr = view.data_ptr()
         pending = []      # (copy-done event, host staging view, f0, nfs), oldest first
         copied = [None] * nbuf
+        cfreed = [None, None]
+        # two-resource list scheduling for "auto": PCIe busy-until (tp) and host-unpack busy-until (th), in
+        # seconds from now, with running estimates of the link rate and of the unpack cost per evaluation
+        rate = _E2E_STATE["link_bytes_per_s"]
+        h_eval = _E2E_STATE["unpack_s_per_eval"]
+        tp = th = 0.0
+        n_packed = n_plain = 0
+        unpack_s = unpack_evals = 0.0
+        errors = []
 
         def drain(item):
-            ev, hbuf, f0, nfs = item
-            ev.synchronize()
-            _lib.check("rsk_unpack_coherency_host",
-                       lib.rsk_unpack_coherency_host(hbuf.data_ptr(), nfs, n_above, ld, out_ptr, nf, f0, n_above, nthreads))
+            nonlocal unpack_s, unpack_evals
+            ev, hbuf, f0, nfs, fin = item
+            try:
+                ev.synchronize()
+                t0 = _time.perf_counter()
+                _lib.check("rsk_unpack_coherency_host",
+                           lib.rsk_unpack_coherency_host(hbuf.data_ptr(), nfs, n_above, ld, out_ptr, nf, f0, n_above,
+                                                         nthreads))
+                unpack_s += _time.perf_counter() - t0
+                unpack_evals += nfs * n_above
+            except Exception as exc:  # surfaced on the calling thread below
+                errors.append(exc)
+            finally:
+                fin.set()
 
-        for i, f0 in enumerate(range(0, nf, slab)):
+        # the unpack runs on a helper thread (ctypes releases the GIL) so this thread keeps the GPU queue fed
+        work = _queue.Queue()
+
+        def worker():
+            while True:
+                item = work.get()
+                if item is None:
+                    return
+                drain(item)
+
+        helper = _threading.Thread(target=worker, daemon=True)
+        helper.start()
+
+        kp = kc = 0
+        for f0 in range(0, nf, slab):
             f1 = min(nf, f0 + slab)
             nfs = f1 - f0
-            k = i % nbuf
-            if len(pending) == nbuf:  # host staging buffer k is about to be overwritten: unpack it first
-                drain(pending.pop(0))
+            ev_n = nfs * n_above
+            use_plain = False
+            if auto:
+                tp_packed = tp + 32.0 * ev_n / rate
+                finish_packed = max(max(th, tp_packed) + ev_n * h_eval, tp_packed)
+                finish_plain = max(tp + 64.0 * ev_n / rate, th)
+                use_plain = finish_plain < finish_packed
+            if use_plain:
+                k = kc % 2
+                kc += 1
+                cbuf = st["cdev"][k]
+                dst = cbuf if nfs == slab else cbuf.reshape(-1)[: 4 * nfs * n_above].view(2, 2, nfs, n_above)
+                if cfreed[k] is not None:
+                    main.wait_event(cfreed[k])
+                self._launch_coherency(plan, f0, f1, dst, n_above, 0)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                copy.wait_event(ready)
+                with torch.cuda.stream(copy):
+                    for a in range(2):
+                        for b in range(2):
+                            view[a, b, f0:f1].copy_(dst[a, b], non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(copy)
+                cfreed[k] = done
+                tp += 64.0 * ev_n / rate
+                n_plain += 1
+                continue
+            k = kp % nbuf
+            kp += 1
+            if len(pending) == nbuf:  # host staging buffer k is about to be overwritten: its unpack must be done
+                pending.pop(0)[4].wait()
             dbuf, hbuf = st["dev"][k], st["host"][k]
             dview = dbuf if nfs == slab else dbuf.reshape(-1)[: 4 * nfs * ld].view(4, nfs, ld)
             hview = hbuf if nfs == slab else hbuf.reshape(-1)[: 4 * nfs * ld].view(4, nfs, ld)
@@ -1052,9 +1132,21 @@ class SkyModel:
                 done = torch.cuda.Event()
                 done.record(copy)
             copied[k] = done
-            pending.append((done, hview, f0, nfs))
-        while pending:
-            drain(pending.pop(0))
+            item = (done, hview, f0, nfs, _threading.Event())
+            pending.append(item)
+            work.put(item)
+            tp += 32.0 * ev_n / rate
+            th = max(th, tp) + ev_n * h_eval
+            n_packed += 1
+        work.put(None)
+        helper.join()
+        if errors:
+            raise errors[0]
+        if auto:
+            copy.synchronize()  # plain slabs: complete when the call returns, like the packed ones
+            if unpack_evals > 0:  # refine the cost estimate for the next call (the host's speed is not known a priori)
+                _E2E_STATE["unpack_s_per_eval"] = 0.5 * h_eval + 0.5 * unpack_s / unpack_evals
+            self._e2e_route_counts = (n_packed, n_plain)
         return view
 
     # ------------------------------------------------------------------------------------------

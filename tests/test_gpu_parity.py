@@ -853,6 +853,23 @@ def test_coherency_to_host_packed_and_plain(rsk, site, spectral_type):
     got3 = sky.coherency_calc_to_host(freqs, pinned, slab=16, packed=False)
     torch.cuda.synchronize()
     assert torch.equal(got3, dev)
+    # mixed route: whatever share of the slabs goes packed or plain, the array is the same
+    from pyradiosky_b200 import skymodel as sm
+
+    for h in (1e-12, 1e-9, 1e-6):  # host believed very fast / typical / very slow
+        sm._E2E_STATE["unpack_s_per_eval"] = h
+        pinned.fill_(float("nan"))
+        got4 = sky.coherency_calc_to_host(freqs, pinned, slab=8, packed="auto", nthreads=2)
+        assert torch.equal(got4, dev), h
+        npk, npl = sky._e2e_route_counts
+        assert npk + npl == -(-freqs.size // 8)
+        if h == 1e-12:
+            assert npl == 0
+        if h == 1e-6:
+            assert npl > npk
+    # an unpinned destination silently falls back to the packed route
+    got5 = sky.coherency_calc_to_host(freqs, host, slab=16, packed="auto")
+    assert torch.equal(got5, dev)
 
 
 # ---------------------------------------------------------------------------------------------------
