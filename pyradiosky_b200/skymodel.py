@@ -1044,8 +1044,8 @@ class SkyModel:
         pending = []      # (copy-done event, host staging view, f0, nfs), oldest first
         copied = [None] * nbuf
         cfreed = [None, None]
-        # two-resource list scheduling for "auto": PCIe busy-until (tp) and host-unpack busy-until (th), in
-        # seconds from now, with running estimates of the link rate and of the unpack cost per evaluation
+        # two-resource model for "auto": PCIe busy-until (tp) and host-unpack busy-until (th), in seconds from
+        # now, with running estimates of the link rate and of the unpack cost per evaluation
         rate = _E2E_STATE["link_bytes_per_s"]
         h_eval = _E2E_STATE["unpack_s_per_eval"]
         tp = th = 0.0
@@ -1089,10 +1089,15 @@ class SkyModel:
             ev_n = nfs * n_above
             use_plain = False
             if auto:
-                tp_packed = tp + 32.0 * ev_n / rate
-                finish_packed = max(max(th, tp_packed) + ev_n * h_eval, tp_packed)
-                finish_plain = max(tp + 64.0 * ev_n / rate, th)
-                use_plain = finish_plain < finish_packed
+                # Packed halves the wire bytes but costs host time.  Keep sending packed slabs while the host
+                # keeps up (at most about one slab of unpacking queued by the time this slab would arrive);
+                # when it falls behind, ship this slab in full instead: the link has the spare capacity and
+                # the host catches up meanwhile.  In steady state this balances the two resources.
+                arrive = tp + 32.0 * ev_n / rate
+                backlog = th - arrive
+                # ... nor when its unpack would end after everything left could have been shipped in full
+                late = max(th, arrive) + ev_n * h_eval > tp + 64.0 * (nf - f0) * n_above / rate
+                use_plain = backlog >= ev_n * h_eval or late
             if use_plain:
                 k = kc % 2
                 kc += 1
