@@ -866,7 +866,7 @@ def test_coherency_to_host_packed_and_plain(rsk, site, spectral_type):
         if h == 1e-12:
             assert npl == 0
         if h == 1e-6:
-            assert npl > 0 and npk > 0
+            assert npl > npk
     # an unpinned destination silently falls back to the packed route
     got5 = sky.coherency_calc_to_host(freqs, host, slab=16, packed="auto")
     assert torch.equal(got5, dev)
