@@ -103,18 +103,21 @@ __global__ void __launch_bounds__(kThreads) k_positions(const CoordSrc cs, const
 #define RSK_SWEEP_MINB 4  // 64 registers, 4 x 256 threads per SM: best of the measured caps (profiles/r01_sweep_tuning.log)
 #endif
 
-template <int CPT, bool WANT_LMN, int FOLD>
+// The time loop of the sweep kernel.  MASK: the horizon mask is wanted; with CPT == 1 threads past the end of the
+// catalogue have left already, so the loop body carries no bounds test.
+template <int CPT, bool WANT_LMN, int FOLD, bool MASK>
 __device__ __forceinline__ void sweep_times(const RskCtx* s_ctx, const int ntc, const int64_t n, const int64_t* idx,
                                             const double* px, const double* py, const double* pz, double** pa,
                                             double** pl, uint8_t** pm) {
   double pp[CPT];
 #pragma unroll
   for (int j = 0; j < CPT; ++j) pp[j] = px[j] * px[j] + py[j] * py[j] + pz[j] * pz[j];
+#pragma unroll 2
   for (int k = 0; k < ntc; ++k) {
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
       const RskAltAz o = rsk_chain_t<WANT_LMN, true, FOLD>(s_ctx[k], px[j], py[j], pz[j], pp[j]);
-      if (idx[j] < n) {
+      if (CPT == 1 || idx[j] < n) {
         __stcs(pa[j], o.alt);
         __stcs(pa[j] + n, o.az);
         if (WANT_LMN) {
@@ -122,11 +125,11 @@ __device__ __forceinline__ void sweep_times(const RskCtx* s_ctx, const int ntc, 
           __stcs(pl[j] + n, o.m);
           __stcs(pl[j] + 2 * n, o.n);
         }
-        if (pm[j]) *pm[j] = o.alt > 0.0 ? 1 : 0;
+        if (MASK) *pm[j] = o.alt > 0.0 ? 1 : 0;
       }
       pa[j] += 2 * n;
       if (WANT_LMN) pl[j] += 3 * n;
-      if (pm[j]) pm[j] += n;
+      if (MASK) pm[j] += n;
     }
   }
 }
@@ -183,10 +186,14 @@ __global__ void __launch_bounds__(kThreads, RSK_SWEEP_MINB) k_positions_sweep(co
   // once here, so the time loop carries no per-step test.
   bool folded = true;
   for (int k = 0; k < ntc; ++k) folded = folded && rsk_ctx_folded(s_ctx[k]);
-  if (folded)
-    sweep_times<CPT, WANT_LMN, 1>(s_ctx, ntc, n, idx, px, py, pz, pa, pl, pm);
-  else
-    sweep_times<CPT, WANT_LMN, 0>(s_ctx, ntc, n, idx, px, py, pz, pa, pl, pm);
+  if (CPT == 1 && idx[0] >= n) return;  // (after the only barrier of the kernel)
+  if (above) {
+    if (folded) sweep_times<CPT, WANT_LMN, 1, true>(s_ctx, ntc, n, idx, px, py, pz, pa, pl, pm);
+    else sweep_times<CPT, WANT_LMN, 0, true>(s_ctx, ntc, n, idx, px, py, pz, pa, pl, pm);
+  } else {
+    if (folded) sweep_times<CPT, WANT_LMN, 1, false>(s_ctx, ntc, n, idx, px, py, pz, pa, pl, pm);
+    else sweep_times<CPT, WANT_LMN, 0, false>(s_ctx, ntc, n, idx, px, py, pz, pa, pl, pm);
+  }
 }
 
 __global__ void __launch_bounds__(kThreads) k_healpix_lonlat(const int64_t nside, const int nested,
@@ -456,9 +463,12 @@ __device__ __forceinline__ void emit(const EvalParams& p, int f, int64_t col, co
     const int64_t plane = (int64_t)p.nf * p.ld_out;
     double2 j1[4], j2[4];
     if (p.beam_type == RSK_BEAM_JONES) {
+      // __restrict__: the Jones arrays never alias the output, so the loads of the next (unrolled) frequency may
+      // be issued before this one's stores -- more bytes in flight per thread for a kernel that reads 2/3 of its
+      // traffic
       const int64_t jplane = (int64_t)p.nf * p.ld_jones;
-      const double2* a = p.jones1 + (int64_t)f * p.ld_jones + col;
-      const double2* b = (p.jones2 ? p.jones2 : p.jones1) + (int64_t)f * p.ld_jones + col;
+      const double2* __restrict__ a = p.jones1 + (int64_t)f * p.ld_jones + col;
+      const double2* __restrict__ b = (p.jones2 ? p.jones2 : p.jones1) + (int64_t)f * p.ld_jones + col;
 #pragma unroll
       for (int k = 0; k < 4; ++k) j1[k] = __ldcs(a + k * jplane);
       if (p.jones2) {
@@ -478,7 +488,7 @@ __device__ __forceinline__ void emit(const EvalParams& p, int f, int64_t col, co
     const double2 t01 = cadd(cmul(j1[0], c01), cmul(j1[1], c11));
     const double2 t10 = cadd(cmul(j1[2], c00), cmul(j1[3], c10));
     const double2 t11 = cadd(cmul(j1[2], c01), cmul(j1[3], c11));
-    double2* d = reinterpret_cast<double2*>(p.out) + (int64_t)f * p.ld_out + p.col0 + col;
+    double2* __restrict__ d = reinterpret_cast<double2*>(p.out) + (int64_t)f * p.ld_out + p.col0 + col;
     __stcs(d, cadd(cmulc(t00, j2[0]), cmulc(t01, j2[1])));
     __stcs(d + plane, cadd(cmulc(t00, j2[2]), cmulc(t01, j2[3])));
     __stcs(d + 2 * plane, cadd(cmulc(t10, j2[0]), cmulc(t11, j2[1])));
