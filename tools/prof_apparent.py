@@ -27,3 +27,15 @@ j2 = torch.randn((2, 2, nf, na), dtype=torch.complex128, device="cuda")
 out = sky.apparent_coherency_calc(jones=j1, jones2=j2, freqs=freqs)
 torch.cuda.synchronize()
 print("apparent", tuple(out.shape))
+if "--time" in sys.argv:  # throughput of the two Jones-array variants (not under ncu)
+    peak = 6547.8
+    for label, kw, nbytes in (("one antenna", dict(jones=j1), 128), ("two antennas", dict(jones=j1, jones2=j2), 192)):
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = sky.apparent_coherency_calc(freqs=freqs, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        print(f"{label}: {best:.3f} ms  {nbytes * na * nf / best / 1e6:.0f} GB/s  frac {nbytes * na * nf / best / 1e6 / peak:.3f}")
