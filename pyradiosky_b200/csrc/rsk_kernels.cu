@@ -422,11 +422,7 @@ struct EvalParams {
 // epilogues of k_eval
 constexpr int kEpiStokes = 0;     // (4, nf, n) Stokes                      -- at_frequencies
 constexpr int kEpiCoherency = 1;  // (2, 2, nf, ld) coherency, or packed   -- coherency_calc
-constexpr int kEpiApparent = 2;   // (2, 2, nf, ld) J1 C J2^H               -- coherency_calc + analytic beam Jones
-constexpr int kEpiApparentPlane = 3;  // the same with Jones arrays, one output plane (a, d) per blockIdx.y:
-                                      // a thread then reads 4 and writes 1 complex number per frequency and needs
-                                      // half the registers, so twice the warps (and loads in flight) fit on an SM;
-                                      // the spectrum is evaluated four times, which this memory-bound kernel affords
+constexpr int kEpiApparent = 2;   // (2, 2, nf, ld) J1 C J2^H               -- coherency_calc + beam Jones
 
 // Jones matrices of one output column, [feed][basis] row-major (basis 0 = zenith-angle direction, 1 = azimuth
 // direction: the basis the Az/El coherency is expressed in).
@@ -461,22 +457,7 @@ __device__ __forceinline__ void xform(const RskRot& r, double si, double sq, dou
 
 template <int EPI>
 __device__ __forceinline__ void emit(const EvalParams& p, int f, int64_t col, const double* o, const JonesPair& jp) {
-  if (EPI == kEpiApparentPlane) {
-    // A[a][d] = sum_bc J1[a][b] C[b][c] conj(J2[d][c]) for the plane (a, d) of this block
-    const int a = blockIdx.y >> 1, dd = blockIdx.y & 1;
-    const int64_t jplane = (int64_t)p.nf * p.ld_jones;
-    const double2* __restrict__ ja = p.jones1 + (int64_t)(2 * a) * jplane + (int64_t)f * p.ld_jones + col;
-    const double2* __restrict__ jb = (p.jones2 ? p.jones2 : p.jones1) + (int64_t)(2 * dd) * jplane + (int64_t)f * p.ld_jones + col;
-    const double2 a0 = __ldcs(ja), a1 = __ldcs(ja + jplane);
-    const double2 b0 = __ldcs(jb), b1 = __ldcs(jb + jplane);
-    const double2 c00 = make_double2(o[0], 0.0), c11 = make_double2(o[1], 0.0);
-    const double2 c01 = make_double2(o[2], -o[3]), c10 = make_double2(o[2], o[3]);
-    const double2 t0 = cadd(cmul(a0, c00), cmul(a1, c10));
-    const double2 t1 = cadd(cmul(a0, c01), cmul(a1, c11));
-    double2* __restrict__ d = reinterpret_cast<double2*>(p.out) + (int64_t)blockIdx.y * p.nf * p.ld_out +
-                              (int64_t)f * p.ld_out + p.col0 + col;
-    __stcs(d, cadd(cmulc(t0, b0), cmulc(t1, b1)));
-  } else if (EPI == kEpiApparent) {
+  if (EPI == kEpiApparent) {
     // A = J1 C J2^H with C = [[o0, o2 - i o3], [o2 + i o3, o1]]: the contraction
     // einsum("ab...,bc...,dc...->ad...", J, C, conj(J)) of tests/test_skymodel.py:1464-1466
     const int64_t plane = (int64_t)p.nf * p.ld_out;
@@ -544,14 +525,10 @@ struct EvalThreads {
 #ifndef RSK_MINB_BANDED
 #define RSK_MINB_BANDED 1
 #endif
-#ifndef RSK_MINB_PLANE
-#define RSK_MINB_PLANE 3
-#endif
 template <int MODE, int EPI>
 struct EvalMinBlocks {
   // the Jones epilogue needs ~140 registers: cap at 128 (two 256-thread blocks per SM), not at 80
   static constexpr int value = EPI == 2 ? (EvalThreads<MODE>::value == 256 ? 2 : 1)
-                               : EPI == 3 ? (EvalThreads<MODE>::value == 256 ? RSK_MINB_PLANE : 1)
                                : (MODE == RSK_SPECTRAL_INDEX) ? RSK_MINB_SI : (MODE == 4 ? RSK_MINB_BANDED : 1);
 };
 
@@ -967,7 +944,7 @@ int launch_eval(const EvalParams& p, int mode, cudaStream_t st) {
   if (p.ncols == 0 || p.nf == 0) return RSK_OK;
   const int64_t nblocks = p.ntiles * p.nfchunks;
   if (nblocks > 0x7fffffffll) return RSK_ERR_SIZE;
-  const dim3 grid((unsigned)nblocks, EPI == kEpiApparentPlane ? 4u : 1u);
+  const dim3 grid((unsigned)nblocks);
   // The kernels use no dynamic shared memory; requesting some only caps how many blocks share an SM.
   int smem = tuning_int("RSK_K2_SMEM", kDefaultOccSmem);
   if (smem < 0) smem = 0;
@@ -1162,7 +1139,6 @@ static int coherency_impl(const RskSpectrum* spec, const RskCoords* coords, cons
   p.out = out;
   p.ld_out = ld_out;
   p.col0 = col0;
-  if (beam && beam->type == RSK_BEAM_JONES) return launch_eval<kEpiApparentPlane>(p, spec->mode, (cudaStream_t)stream);
   if (beam) return launch_eval<kEpiApparent>(p, spec->mode, (cudaStream_t)stream);
   return launch_eval<kEpiCoherency>(p, spec->mode, (cudaStream_t)stream);
 }
