@@ -25,6 +25,29 @@ _ANGLE_TO_RAD = {"rad": 1.0, "deg": np.pi / 180.0, "hourangle": np.pi / 12.0, "a
 _FREQ_TO_HZ = {"Hz": 1.0, "kHz": 1e3, "MHz": 1e6, "GHz": 1e9}
 
 
+def _ascii_bytes_to_str(raw):
+    """Fixed-length byte strings -> numpy str array.  ASCII (every SkyH5 name in practice) is widened bytewise,
+    ~20x faster than numpy's own S -> U cast; anything else is decoded as UTF-8 like the reference
+    (skymodel.py:297)."""
+    k = raw.dtype.itemsize
+    codes = raw.view(np.uint8).reshape(-1, k)
+    if codes.size == 0 or codes.max() < 128:
+        return np.ascontiguousarray(codes.astype(np.uint32)).view(f"U{k}").reshape(raw.shape)
+    return np.char.decode(raw, "utf8")
+
+
+def _str_to_bytes(arr):
+    """numpy str array -> fixed-length UTF-8 byte strings (bytewise narrowing for ASCII)."""
+    arr = np.ascontiguousarray(arr)
+    k = arr.dtype.itemsize // 4
+    if k == 0:
+        return arr.astype("S1")
+    codes = arr.view(np.uint32).reshape(-1, k)
+    if codes.size == 0 or codes.max() < 128:
+        return np.ascontiguousarray(codes.astype(np.uint8)).view(f"S{k}").reshape(arr.shape)
+    return np.char.encode(arr, "utf8")
+
+
 class H5Error(OSError):
     """librsk's HDF5 layer returned an error."""
 
@@ -99,14 +122,11 @@ class H5File:
     def read_strings(self, path):
         info = self.info(path)
         if info.type_class == _lib.H5_STRING and info.rank > 0 and info.count > 0:
-            # fixed-length records: one raw read, then numpy's S -> U cast (a C loop; 1M names in ~30 ms)
+            # fixed-length records: one raw read, then a bytewise widening to numpy str
             raw = np.empty(int(info.count), dtype=f"S{info.elem_size}")
             _h5check(self._lib, self._h, "rsk_h5_read",
                      self._lib.rsk_h5_read(self._h, path.encode(), raw.ctypes.data, raw.nbytes, 0))
-            try:
-                return raw.astype(str).reshape(tuple(info.dims[: info.rank]))
-            except UnicodeDecodeError:  # non-ASCII names: decode as UTF-8 like the reference (skymodel.py:297)
-                return np.char.decode(raw, "utf8").reshape(tuple(info.dims[: info.rank]))
+            return _ascii_bytes_to_str(raw).reshape(tuple(info.dims[: info.rank]))
         need = _h5check(self._lib, self._h, "rsk_h5_read_strings",
                         self._lib.rsk_h5_read_strings(self._h, path.encode(), None, 0))
         buf = ctypes.create_string_buffer(max(int(need), 1))
@@ -396,7 +416,7 @@ class H5Writer:
             value = np.bytes_(value.encode("utf8"))
         arr = np.asarray(value)
         if arr.dtype.kind == "U":
-            arr = np.char.encode(arr, "utf8")
+            arr = _str_to_bytes(arr) if arr.ndim > 0 else np.char.encode(arr, "utf8")
         if arr.dtype.kind == "b":
             arr = arr.astype(np.int8)
         if arr.ndim > 0:
