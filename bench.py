@@ -213,6 +213,22 @@ def run_reference(args):
     emit(line)
 
 
+def positions_cpu_baseline(lon, lat, astroms):
+    """cpu_baseline leg of the LST-sweep bench (tools/bench_sweep.py, BASELINE config 5): the oracle's
+    update_positions on one core.  Returns (alt_az of the first context, source.time evaluations per second).
+    Lives here because bench.py is the one place outside tests/ that may execute oracle/ (as checker and as the
+    CPU baseline, never as the thing measured)."""
+    from oracle import skymodel_np
+
+    t0 = time.perf_counter()
+    first = None
+    for a in astroms:
+        alt_az, _, _ = skymodel_np.update_positions(lon, lat, a)
+        if first is None:
+            first = alt_az
+    return first, len(astroms) * lon.size / (time.perf_counter() - t0)
+
+
 # ---------------------------------------------------------------------------------------------------
 # clocks sampler
 # ---------------------------------------------------------------------------------------------------

@@ -30,7 +30,7 @@ def main():
     import __graft_entry__ as entry
 
     entry.build()
-    from oracle import erfa_np, skymodel_np
+    import bench  # its cpu_baseline leg is the only place outside tests/ that runs the oracle
     from pyradiosky_b200 import EarthLocation, SkyModel, Time, astrometry
 
     # under torchrun: strong scaling, the n sources are sharded over the ranks (contiguous blocks), every rank
@@ -90,15 +90,12 @@ def main():
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     # spot check against the oracle
     k = nt // 3
-    ref_alt_az, _, ref_above = skymodel_np.update_positions(lon[:5000], lat[:5000], astroms[k])
+    ref_alt_az, _ = bench.positions_cpu_baseline(lon[:5000], lat[:5000], astroms[k:k + 1])
     got = alt_az[k][:, :5000].cpu().numpy()
     err_uas = np.abs(got[0] - ref_alt_az[0]).max() / (np.pi / 180 / 3600 * 1e-6)
     # CPU oracle on a sample, one core
     ns = min(n, args.cpu_sample)
-    tc = time.perf_counter()
-    for kk in range(5):
-        skymodel_np.update_positions(lon[:ns], lat[:ns], astroms[kk])
-    cpu_rate = 5 * ns / (time.perf_counter() - tc)
+    _, cpu_rate = bench.positions_cpu_baseline(lon[:ns], lat[:ns], astroms[:5])
     kernel_ms = min(a.elapsed_time(b) for a, b in kev[1:])
     out = {
         "metric": "position_source_time_evals_per_s", "value": n_total * nt / (best * 1e-3), "ms": best, "n": n_total,
