@@ -1160,3 +1160,32 @@ def test_assign_to_healpix_many_sources(rsk):
                 want[:, :, j] = acc / area
             assert np.array_equal(out.stokes.cpu().numpy(), want)
             assert out.stokes_unit == "Jy / sr"
+
+
+def test_polarized_source_smooth_visibilities(rsk):
+    """tests/test_skymodel.py:1511-1617: the instrumental coherency of a polarised source changes smoothly as it
+    transits the zenith (201 time steps over +-1 h; second differences of every element below 1e-6)."""
+    loc = rsk.EarthLocation.from_dms((-30, 43, 17.5), (21, 25, 41.9), 1073.0)
+    t0 = rsk.Time(2457082.5, 0.0)
+    offsets = np.arange(-1.0, 1.0 + 0.01, 0.01)
+    zero = int(np.argmin(np.abs(offsets)))
+    offsets[zero] = 0.0
+    ra, dec = E.altaz_to_icrs(np.pi / 2, 0.0, rsk.astrometry.astrom_context(t0, loc))
+    sky = rsk.SkyModel(name="icrs_zen", ra=ra, dec=dec, stokes=np.array([1, -0.2, 0.3, 0.1], float), spectral_type="flat")
+    inst = np.zeros((2, 2, offsets.size), complex)
+    alts = np.zeros(offsets.size)
+    for ti, off in enumerate(offsets):
+        sky.update_positions(t0 + off / 24.0, loc)
+        alts[ti] = float(sky.alt_az[0, 0])
+        inst[:, :, ti] = sky.apparent_coherency_calc(beam="short_dipole").cpu().numpy()[:, :, 0, 0]
+    assert np.isclose(alts[zero], np.pi / 2)
+    dt = np.diff(offsets) * 3600.0
+    for a in range(2):
+        for b in range(2):
+            for part in (inst[a, b].real, inst[a, b].imag):
+                assert np.max(np.abs(np.diff(np.diff(part) / dt))) < 1e-6
+    # utils.coherency_to_stokes (utils.py:64-102): I, Q, U, V are real for a Hermitian matrix
+    stokes = np.array([inst[0, 0] + inst[1, 1], inst[0, 0] - inst[1, 1], inst[0, 1] + inst[1, 0], 1j * (inst[0, 1] - inst[1, 0])])
+    for s in range(4):
+        assert np.max(np.abs(np.diff(np.diff(stokes[s].real) / dt))) < 1e-6
+        assert np.max(np.abs(stokes[s].imag)) < 1e-15
