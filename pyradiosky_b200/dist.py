@@ -14,6 +14,11 @@ Only two exchanges exist, both optional and outside the compute path:
     NCCL/NVLink.  Its volume is the full output per receiving GPU (tens of GB), ~50x the compute time,
     so it is never part of the timed hot path.
 
+  * :class:`PeerGather` -- the B200-native form of the same assembly: the gathered array lives in symmetric
+    (peer-mapped) memory and every rank's coherency kernel *writes its column range directly into the
+    destination GPU's HBM* through NVLink (``ld_out`` / ``col0`` of ``rsk_coherency``), so the transfer is the
+    kernel's own stores, tile by tile, and no data collective runs at all.
+
 Works with the ``nccl`` backend on CUDA tensors and with ``gloo`` on CPU tensors (used by the CPU tests).
 """
 
@@ -98,3 +103,55 @@ def gather_columns(local, counts, group=None):
             full.narrow(ax, off, c).copy_(gathered[r].narrow(ax, 0, c))
         off += c
     return torch.view_as_complex(full) if is_complex else full
+
+
+class PeerGather:
+    """Gathered coherency array in symmetric memory, filled by the kernels themselves over NVLink.
+
+    ``PeerGather(nfreqs, max_cols)`` allocates, once, a ``(2, 2, nfreqs, ld)`` complex128 buffer on every rank
+    (``ld`` = ``max_cols`` rounded up to 16 columns: 256-byte rows) with
+    ``torch.distributed._symmetric_memory`` and maps every peer's copy.  :meth:`coherency_calc` then runs, per
+    time step: the 8-byte count exchange (column offsets), one ``rsk_coherency`` launch per destination whose
+    ``out`` pointer is the *destination's* buffer and whose ``col0`` is this rank's offset, and a device-side
+    barrier.  ``dst=None`` leaves the full array on every rank (all-gather semantics: each rank stores its block
+    world_size times, once locally and world_size - 1 times through NVLink); ``dst=r`` assembles it on rank r
+    only.  No NCCL data collective is involved and nothing is staged: the compute kernel's 128-bit streaming
+    stores are the transfer.
+    """
+
+    def __init__(self, nfreqs, max_cols, device=None, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerGather needs an initialised torch.distributed process group (nccl)")
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.nfreqs = int(nfreqs)
+        self.ld = max(16, -(-int(max_cols) // 16) * 16)
+        shape = (2, 2, self.nfreqs, self.ld)
+        try:  # older torch releases need the group enabled explicitly
+            symm_mem.enable_symm_mem_for_group(self.group.group_name)
+        except Exception:
+            pass
+        self.buf = symm_mem.empty(*shape, dtype=torch.complex128, device=self.device)
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
+        self.peers = [self.buf if r == self.rank else self.handle.get_buffer(r, shape, torch.complex128)
+                      for r in range(self.world)]
+
+    def coherency_calc(self, sky, freqs=None, dst=None, **kwargs):
+        """Sharded ``sky.coherency_calc`` written straight into the gathered array.
+
+        Returns ``(view, counts)``: the (2, 2, nfreqs, sum N_above) view of this rank's buffer (valid on the
+        destination rank(s) once the call returns) and the per-rank above-horizon counts."""
+        _, n_above = sky.compact_above_horizon()
+        counts, col0, total = exchange_counts(n_above, self.device, self.group)
+        if total > self.ld:
+            raise ValueError(f"gathered array needs {total} columns, the buffer has {self.ld}")
+        targets = range(self.world) if dst is None else [int(dst)]
+        self.handle.barrier()  # nobody is still reading the previous step's array
+        for r in targets:
+            sky.coherency_calc(freqs=freqs, out=self.peers[r], ld_out=self.ld, col0=col0, **kwargs)
+        self.handle.barrier()  # every rank's stores have landed
+        return self.buf[..., :total], counts

@@ -185,10 +185,14 @@ def _write_sample(skyh5, path, gzip, rng):
         items["/Header/skycoord/frame"] = "icrs"
         items["/Header/small_ints"] = rng.integers(-5, 5, size=(700, 300)).astype(np.int16)
         items["/Header/unsigned"] = rng.integers(0, 255, size=(17,)).astype(np.uint8)
+        items["/Header/rank4"] = rng.normal(size=(3, 4, 5, 6))
+        items["/Header/chunked1d"] = rng.normal(size=(1000,))
+        items["/Header/empty"] = np.zeros((0,), dtype=np.float64)
+        chunk_of = {"/Header/small_ints": (64, 64), "/Header/rank4": (2, 2, 3, 4), "/Header/chunked1d": (128,)}
         for k, v in items.items():
             if k == "/Data/stokes":
                 continue
-            w.dataset(k, v, chunks=(64, 64) if k.endswith("small_ints") else None, gzip=gzip)
+            w.dataset(k, v, chunks=chunk_of.get(k), gzip=gzip)
         w.attr("/Header/skycoord/ra", "unit", "rad")
         w.attr("/Header/skycoord/ra", "object_type", "longitude")
         w.attr("/Header", "note", "group attribute")
@@ -262,7 +266,7 @@ def test_read_device_matches_host(skyh5, tmp_path):
         items = _write_sample(skyh5, path, gzip, rng)
         with skyh5.H5File(path) as f:
             for k in ("/Data/stokes", "/Header/small_ints", "/Header/par20", "/Header/par21", "/Header/skycoord/ra",
-                      "/Header/unsigned", "/Header/Ncomponents"):
+                      "/Header/unsigned", "/Header/Ncomponents", "/Header/rank4", "/Header/chunked1d", "/Header/empty"):
                 want = np.asarray(items[k])
                 dtype = torch.float64 if want.dtype.kind == "f" else torch.int64
                 for slab in (0, 4096, 200000):  # default, tiny (ring reuse), medium
