@@ -131,10 +131,6 @@ class PeerGather:
         self.nfreqs = int(nfreqs)
         self.ld = max(16, -(-int(max_cols) // 16) * 16)
         shape = (2, 2, self.nfreqs, self.ld)
-        try:  # older torch releases need the group enabled explicitly
-            symm_mem.enable_symm_mem_for_group(self.group.group_name)
-        except Exception:
-            pass
         self.buf = symm_mem.empty(*shape, dtype=torch.complex128, device=self.device)
         self.handle = symm_mem.rendezvous(self.buf, self.group)
         self.peers = [self.buf if r == self.rank else self.handle.get_buffer(r, shape, torch.complex128)
