@@ -145,7 +145,9 @@ class PeerGather:
         counts, col0, total = exchange_counts(n_above, self.device, self.group)
         if total > self.ld:
             raise ValueError(f"gathered array needs {total} columns, the buffer has {self.ld}")
-        targets = range(self.world) if dst is None else [int(dst)]
+        # all-gather: at step k rank i writes to rank (i + k) mod world, so every step is a permutation -- each GPU
+        # receives from exactly one sender at a time instead of all ranks converging on the same destination
+        targets = [(self.rank + k) % self.world for k in range(self.world)] if dst is None else [int(dst)]
         self.handle.barrier()  # nobody is still reading the previous step's array
         for r in targets:
             sky.coherency_calc(freqs=freqs, out=self.peers[r], ld_out=self.ld, col0=col0, **kwargs)
