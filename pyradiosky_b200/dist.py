@@ -119,7 +119,7 @@ class PeerGather:
     stores are the transfer.
     """
 
-    def __init__(self, nfreqs, max_cols, device=None, group=None):
+    def __init__(self, nfreqs, max_cols, device=None, group=None, streams=2):
         import torch.distributed._symmetric_memory as symm_mem
 
         if not (dist.is_available() and dist.is_initialized()):
@@ -135,6 +135,9 @@ class PeerGather:
         self.handle = symm_mem.rendezvous(self.buf, self.group)
         self.peers = [self.buf if r == self.rank else self.handle.get_buffer(r, shape, torch.complex128)
                       for r in range(self.world)]
+        # launches for different destinations go round-robin over a few streams so that several NVLink
+        # destinations are in flight at once (one remote-store kernel alone reaches ~520 of the 900 GB/s)
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(max(1, int(streams)))]
 
     def coherency_calc(self, sky, freqs=None, dst=None, **kwargs):
         """Sharded ``sky.coherency_calc`` written straight into the gathered array.
@@ -149,7 +152,17 @@ class PeerGather:
         # receives from exactly one sender at a time instead of all ranks converging on the same destination
         targets = [(self.rank + k) % self.world for k in range(self.world)] if dst is None else [int(dst)]
         self.handle.barrier()  # nobody is still reading the previous step's array
-        for r in targets:
-            sky.coherency_calc(freqs=freqs, out=self.peers[r], ld_out=self.ld, col0=col0, **kwargs)
+        main = torch.cuda.current_stream(self.device)
+        if len(targets) == 1 or len(self.streams) == 1:
+            for r in targets:
+                sky.coherency_calc(freqs=freqs, out=self.peers[r], ld_out=self.ld, col0=col0, sync=False, **kwargs)
+        else:
+            for st in self.streams:
+                st.wait_stream(main)
+            for k, r in enumerate(targets):
+                with torch.cuda.stream(self.streams[k % len(self.streams)]):
+                    sky.coherency_calc(freqs=freqs, out=self.peers[r], ld_out=self.ld, col0=col0, sync=False, **kwargs)
+            for st in self.streams:
+                main.wait_stream(st)
         self.handle.barrier()  # every rank's stores have landed
         return self.buf[..., :total], counts

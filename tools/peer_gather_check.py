@@ -59,8 +59,15 @@ def main():
     mine = SkyModel(**rdist.shard_kwargs(kwargs, world, rank))
     mine.update_positions(t, loc)
 
-    pg = rdist.PeerGather(nf, n)
     res = {"world": world, "n": n, "nf": nf}
+    by_streams = {}
+    for ns in (1, 2, 4):  # concurrent destinations
+        pgs = rdist.PeerGather(nf, n, streams=ns)
+        by_streams[ns], _ = timed(lambda: pgs.coherency_calc(mine, freqs=freqs))
+        del pgs
+        torch.cuda.empty_cache()
+    res["peer_write_all_ranks_ms_by_streams"] = by_streams
+    pg = rdist.PeerGather(nf, n)
     # all ranks get the array
     ms_all, (view, counts) = timed(lambda: pg.coherency_calc(mine, freqs=freqs))
     whole = SkyModel(**kwargs)
