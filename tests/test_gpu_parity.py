@@ -1189,3 +1189,23 @@ def test_polarized_source_smooth_visibilities(rsk):
     for s in range(4):
         assert np.max(np.abs(np.diff(np.diff(stokes[s].real) / dt))) < 1e-6
         assert np.max(np.abs(stokes[s].imag)) < 1e-15
+
+
+def test_peer_gather_single_rank(rsk):
+    """dist.PeerGather (gathered array in symmetric memory, filled by the kernels' own stores) in a one-rank
+    NCCL group: the same code path the 2- and 8-GPU runs take (profiles/r01_peer_gather_*.json), here checked
+    bit for bit against coherency_calc and the NCCL all_gather route."""
+    import json as _json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", MASTER_ADDR="127.0.0.1", MASTER_PORT="29577",
+               GC_N="20000", GC_NF="16")
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "peer_gather_check.py")], env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1]
+    out = _json.loads(line)
+    assert out["equal_to_unsharded"] is True and out["world"] == 1
