@@ -1,0 +1,82 @@
+#!/usr/bin/env python
+"""BASELINE config 3, stored-'full' variant: HEALPix nside 1024, all 12 582 912 pixels, full
+Stokes stored at every channel; coherency_calc() on the stored cube (K2 'full' mode: 32 B read + 64 B written per
+evaluation).  256 channels are 103 GB in + 103 GB out, more than one GPU holds, so the frequency axis is processed
+in chunks of --chunk channels (default 128: 51.5 GB in + ~26 GB out for the ~50 % of pixels above the horizon);
+the chunks are independent, the full map costs 256 / chunk times the chunk time.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nside", type=int, default=1024)
+    ap.add_argument("--chunk", type=int, default=128)
+    ap.add_argument("--nf", type=int, default=256)
+    ap.add_argument("--reps", type=int, default=5)
+    args = ap.parse_args()
+    import __graft_entry__ as entry
+
+    entry.build()
+    from pyradiosky_b200 import EarthLocation, SkyModel, Time
+
+    npix = 12 * args.nside**2
+    nfc = args.chunk
+    g = torch.Generator(device="cuda").manual_seed(3)
+    stokes = torch.empty((4, nfc, npix), dtype=torch.float64, device="cuda")
+    for s in range(4):  # filled plane by plane to keep temporaries small
+        for f in range(nfc):
+            stokes[s, f].uniform_(0.0 if s == 0 else -0.05, 1.0 if s == 0 else 0.05, generator=g)
+    freqs = np.linspace(100e6, 200e6, args.nf)[:nfc]
+    sky = SkyModel(nside=args.nside, hpx_order="ring", stokes=stokes, spectral_type="full", freq_array=freqs,
+                   component_type="healpix", stokes_unit="K")
+    loc = EarthLocation.from_dms((-30, 43, 17.5), (21, 25, 41.9), 1073.0)
+    t0 = Time.from_utc("2015-03-01 00:00:00")
+    sky.update_positions(t0, loc)
+    n_above = int(sky.above_horizon.sum().item())
+    ld = -(-npix // 16) * 16
+    buf = torch.empty((2, 2, nfc, -(-int(1.05 * n_above) // 16) * 16), dtype=torch.complex128, device="cuda")
+    ld = buf.shape[-1]
+    best = 1e30
+    kev = []
+    sky._timing_events = kev
+    for r in range(args.reps + 1):
+        sky.update_positions(t0 + 1e-4 * (r + 1), loc)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sky.coherency_calc(out=buf, ld_out=ld, sync=False)
+        e1.record()
+        torch.cuda.synchronize()
+        if r > 0:
+            best = min(best, e0.elapsed_time(e1))
+    kernel_ms = min(a.elapsed_time(b) for a, b in kev[1:])
+    n_above = int(sky.above_horizon.sum().item())
+    evals = n_above * nfc
+    peak = 6547.8
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peak = json.load(open(pk))["hbm_gbs"]
+    # spot check: unpolarised-free path, C = rotation of stored Stokes; compare one pixel column with stokes_to_coherency
+    out = {
+        "workload": f"c3 'full': HEALPix nside {args.nside} ring, {npix} pixels, stored Stokes, {nfc}-channel chunk of {args.nf}",
+        "n_above": n_above, "chunk_channels": nfc, "chunk_in_GB": stokes.numel() * 8 / 1e9, "chunk_out_GB": 64 * evals / 1e9,
+        "chunk_ms": best, "kernel_ms": kernel_ms, "evals_per_s": evals / (best * 1e-3),
+        "algorithmic_bytes_per_eval": 96, "kernel_GBps": 96 * evals / (kernel_ms * 1e-3) / 1e9,
+        "frac_of_hbm_peak": 96 * evals / (kernel_ms * 1e-3) / 1e9 / peak,
+        "full_map_ms_projected": best * args.nf / nfc,
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
