@@ -54,7 +54,7 @@ def main():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        sky.coherency_calc(out=buf, ld_out=ld, sync=False)
+        sky.coherency_calc(out=buf, ld_out=ld)  # sync=False would need room for every pixel (103 GB per 128 channels)
         e1.record()
         torch.cuda.synchronize()
         if r > 0:
