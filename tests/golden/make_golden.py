@@ -206,8 +206,9 @@ def make_known_answers():
 
 
 def copy_skyh5_fixtures():
-    """Two of the reference's own (small) SkyH5 test fixtures, byte for byte: data files written by h5py /
-    libhdf5 that the product's HDF5 reader (include/rsk_io.h) must read without libhdf5.
+    """Two of the reference's own (small) SkyH5 test *data* fixtures, byte for byte (under names that say where
+    they come from): files written by h5py / libhdf5 that the product's HDF5 reader (include/rsk_io.h) must read
+    without libhdf5 -- the only h5py-written bytes available in an image that has neither h5py nor libhdf5.
 
     * ``gsm_icrs.skyh5`` (768-pixel HEALPix map, nside 8, 10 channels, K; chunked Stokes, old-style
       ``lon``/``lat``/``frame`` header) -- the tutorial prints its first five Stokes I values
@@ -218,8 +219,9 @@ def copy_skyh5_fixtures():
     import shutil
 
     src = "/root/reference/src/pyradiosky/data"
-    for name in ("gsm_icrs.skyh5", "old_skyh5_point_sources.skyh5"):
-        shutil.copyfile(os.path.join(src, name), os.path.join(HERE, name))
+    for name, fixture in (("gsm_icrs.skyh5", "ref_fixture_gsm_icrs_nside8.skyh5"),
+                          ("old_skyh5_point_sources.skyh5", "ref_fixture_gleam50_old_header.skyh5")):
+        shutil.copyfile(os.path.join(src, name), os.path.join(HERE, fixture))
     ka = {
         "gsm_icrs": {
             "cite": "docs/tutorial.rst:1288-1297",

@@ -20,8 +20,8 @@ from oracle import h5_np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-GSM = os.path.join(GOLDEN, "gsm_icrs.skyh5")
-OLD_POINT = os.path.join(GOLDEN, "old_skyh5_point_sources.skyh5")
+GSM = os.path.join(GOLDEN, "ref_fixture_gsm_icrs_nside8.skyh5")  # the reference's gsm_icrs.skyh5
+OLD_POINT = os.path.join(GOLDEN, "ref_fixture_gleam50_old_header.skyh5")  # its old_skyh5_point_sources.skyh5
 
 
 @pytest.fixture(scope="module")
@@ -293,7 +293,7 @@ def test_from_skyh5_gsm_tutorial_values(answers):
     assert sky.Ncomponents == a["Ncomponents"] and sky.Nfreqs == 10
     assert sky.component_type == "healpix" and sky.nside == 8 and sky.hpx_order == "ring" and sky.frame == "icrs"
     assert sky.spectral_type == "full" and sky.stokes_unit == "K"
-    assert sky.filename == ["gsm_icrs.skyh5"]
+    assert sky.filename == [os.path.basename(GSM)]
     assert torch.equal(sky.hpx_inds, torch.arange(768, device=sky.device))
     np.testing.assert_allclose(sky.stokes[0, 0, :5].cpu().numpy(), a["stokes_I_first5_K"], rtol=0, atol=5e-9)
     np.testing.assert_allclose(sky.freq_array[:2], [50e6, 61111111.11111111])
