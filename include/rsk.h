@@ -281,6 +281,22 @@ int rsk_apparent_coherency(const RskSpectrum* spec, const RskCoords* coords, con
                             double* out /* complex [2][2][nf][ld_out] */, int64_t ld_out, int64_t col0,
                             void* stream);
 
+/* The source sum of the apparent coherency -- what a visibility simulator finally needs from this path:
+ *   vis[b][a][d][f] = sum over the ncols above-horizon components s of
+ *                     (J1 C J2^H)[a][d][f][s] * exp(2 pi i (f / c) (uvw_b . lmn_s))
+ * (pyuvsim's convention: fringe = exp(2j pi uvw_wavelengths . pos_lmn)).  Nothing per-component is written:
+ * neither the (4, Nf, N) Stokes cube, nor the Az/El coherency, nor the apparent one.  uvw_m == NULL (or nbl == 0)
+ * gives the zero-baseline sum, vis[0].  Spectral modes FLAT, SPECTRAL_INDEX and FULL (evaluate subband models with
+ * rsk_at_frequencies first).  pos_lmn is the [3][n] output of rsk_positions.  work: rsk_visibility_workspace_bytes().
+ * Deterministic: per-thread running sums in a fixed column order, fixed-shape block reduction, column groups
+ * added in order. */
+int rsk_visibility(const RskSpectrum* spec, const RskCoords* coords, const double* alt_az, const double* ravg,
+                   const int64_t* idx, int64_t ncols, const int64_t* ncols_dev, const double* freqs, int64_t nf,
+                   const RskBeam* beam, const double* pos_lmn /* [3][n] or NULL */,
+                   const double* uvw_m /* DEVICE [nbl][3] metres, or NULL */, int64_t nbl,
+                   double* vis /* complex [max(nbl,1)][2][2][nf] */, void* work, size_t work_bytes, void* stream);
+size_t rsk_visibility_workspace_bytes(int64_t ncols, int64_t nf, int64_t nbl);
+
 /* HOST: expand a packed slab (HOST pointer, e.g. pinned staging memory that a cudaMemcpyAsync has filled)
  * into rows [f0_out, f0_out + nf) of the reference-layout array out = complex [2][2][nf_out][ld_out] in host
  * memory, with nthreads threads.  Pure data movement (duplicate / negate), no arithmetic of the path. */

@@ -134,6 +134,13 @@ _SIGNATURES = {
          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
          ctypes.POINTER(RskBeam), ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p],
     ),
+    "rsk_visibility": (
+        ctypes.c_int,
+        [ctypes.POINTER(RskSpectrum), ctypes.POINTER(RskCoords), ctypes.c_void_p, c_double_p, ctypes.c_void_p,
+         ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(RskBeam), ctypes.c_void_p,
+         ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p],
+    ),
+    "rsk_visibility_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int64, ctypes.c_int64]),
     "rsk_unpack_coherency_host": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,

@@ -835,6 +835,199 @@ __global__ void __launch_bounds__(kThreads) k_convert_units(double* __restrict__
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// N4, second half: the source sum.  vis[b][a][d][f] = sum over above-horizon components s of
+// (J1 C J2^H)[a][d][f][s] * exp(2 pi i f/c (uvw_b . lmn_s)) -- the apparent coherency is consumed where it is
+// produced and never reaches HBM.  blockIdx.x = group of kVisF frequencies, blockIdx.y = column group,
+// blockIdx.z = baseline; a thread walks its columns (stride = 256 * column groups) with kVisF x 8 accumulators
+// in registers, the block reduces them once (shuffles, then shared memory) and writes one partial sum per
+// (baseline, column group, frequency); k_visibility_finish adds the column groups in a fixed order, so the
+// result is deterministic.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kVisF = 4;        // frequencies per thread
+constexpr int kVisGroups = 16;  // upper bound of column groups per (frequency group, baseline)
+
+struct VisParams {
+  const double* stokes;
+  int64_t nf_in, n;
+  const double* alpha;
+  const double* ref_freq;
+  const int32_t* freq_map;
+  const uint8_t* polarized;
+  double pivot_hz;
+  CoordSrc cs;
+  const double* alt_az;
+  double ravg[9];
+  const int64_t* idx;
+  int64_t ncols;
+  const int64_t* ncols_dev;
+  const double* freqs;
+  int nf;
+  int beam_type;
+  const double2* jones1;
+  const double2* jones2;
+  int64_t ld_jones;
+  const double* lmn;   // [3][n] or NULL
+  const double* uvw;   // [nbl][3] metres or NULL
+  double* partial;     // [nbl][ngroups][nf][8]
+  int ngroups;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) k_visibility(const __grid_constant__ VisParams p) {
+  __shared__ double s_lf[kVisF];    // ln(f / pivot)
+  __shared__ double s_turn[kVisF];  // f / c: turns of phase per metre of delay
+  __shared__ double s_red[kThreads / 32][kVisF * 8];
+  const int f0 = blockIdx.x * kVisF;
+  const int nfc = min(kVisF, p.nf - f0);
+  const double pivot = (MODE == RSK_SPECTRAL_INDEX) ? (p.pivot_hz > 0.0 ? p.pivot_hz : __ldg(p.freqs + p.nf / 2)) : 1.0;
+  if (threadIdx.x < kVisF) {
+    const double f = (p.freqs && threadIdx.x < nfc) ? __ldg(p.freqs + f0 + threadIdx.x) : 1.0;
+    s_lf[threadIdx.x] = MODE == RSK_SPECTRAL_INDEX ? log(f / pivot) : 0.0;
+    s_turn[threadIdx.x] = f / 299792458.0;
+  }
+  __syncthreads();
+  const int64_t ncols = p.ncols_dev ? min(p.ncols, __ldg(p.ncols_dev)) : p.ncols;
+  double bu = 0.0, bv = 0.0, bw = 0.0;
+  const bool fringe = p.uvw != nullptr && p.lmn != nullptr;
+  if (fringe) {
+    bu = __ldg(p.uvw + 3 * blockIdx.z);
+    bv = __ldg(p.uvw + 3 * blockIdx.z + 1);
+    bw = __ldg(p.uvw + 3 * blockIdx.z + 2);
+  }
+  double acc[kVisF][8];
+#pragma unroll
+  for (int k = 0; k < kVisF; ++k)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[k][c] = 0.0;
+  const int64_t sstride = p.nf_in * p.n;
+  for (int64_t col = (int64_t)blockIdx.y * kThreads + threadIdx.x; col < ncols; col += (int64_t)kThreads * p.ngroups) {
+    const int64_t src = p.idx ? __ldg(p.idx + col) : col;
+    RskRot rot;
+    rot.n2 = 1.0; rot.c2 = 1.0; rot.s2 = 0.0;
+    if (p.polarized && __ldg(p.polarized + src)) {
+      if (p.cs.rot) {
+        rot.n2 = __ldg(p.cs.rot + src);
+        rot.c2 = __ldg(p.cs.rot + p.n + src);
+        rot.s2 = __ldg(p.cs.rot + 2 * p.n + src);
+      } else {
+        double sl, cl, sb, cb, sa, ca, se, ce;
+        frame_trig(p.cs, src, sl, cl, sb, cb);
+        sincos(__ldg(p.alt_az + src), &se, &ce);
+        sincos(__ldg(p.alt_az + p.n + src), &sa, &ca);
+        rot = rsk_basis_rotation(p.ravg, sl, cl, sb, cb, sa, ca, se, ce);
+      }
+    }
+    double ja[4] = {1.0, 0.0, 0.0, 1.0};  // analytic beams: real, frequency independent
+    if (p.beam_type == RSK_BEAM_SHORT_DIPOLE) {
+      double se, ce, sa, ca;
+      sincos(__ldg(p.alt_az + src), &se, &ce);
+      sincos(__ldg(p.alt_az + p.n + src), &sa, &ca);
+      ja[0] = se * sa; ja[1] = ca; ja[2] = se * ca; ja[3] = -sa;
+    }
+    double delay = 0.0;  // metres
+    if (fringe) delay = bu * __ldg(p.lmn + src) + bv * __ldg(p.lmn + p.n + src) + bw * __ldg(p.lmn + 2 * p.n + src);
+    double b[4] = {0.0, 0.0, 0.0, 0.0}, alpha = 0.0, l0 = 0.0;
+    if (MODE != RSK_FULL) {
+      xform<kEpiCoherency>(rot, __ldg(p.stokes + src), __ldg(p.stokes + sstride + src), __ldg(p.stokes + 2 * sstride + src),
+                           __ldg(p.stokes + 3 * sstride + src), b);
+      if (MODE == RSK_SPECTRAL_INDEX) {
+        alpha = __ldg(p.alpha + src);
+        l0 = log(__ldg(p.ref_freq + src) / pivot);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kVisF; ++k) {
+      if (k < nfc) {
+        double o[4];
+        if (MODE == RSK_FULL) {
+          const int ch = p.freq_map ? __ldg(p.freq_map + f0 + k) : f0 + k;
+          const double* y = p.stokes + (int64_t)ch * p.n + src;
+          xform<kEpiCoherency>(rot, __ldcs(y), __ldcs(y + sstride), __ldcs(y + 2 * sstride), __ldcs(y + 3 * sstride), o);
+        } else {
+          const double pw = MODE == RSK_SPECTRAL_INDEX ? exp(alpha * (s_lf[k] - l0)) : 1.0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[q] = b[q] * pw;
+        }
+        double2 j1[4], j2[4];
+        if (p.beam_type == RSK_BEAM_JONES) {
+          const int64_t jplane = (int64_t)p.nf * p.ld_jones;
+          const double2* a = p.jones1 + (int64_t)(f0 + k) * p.ld_jones + col;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) j1[q] = __ldcs(a + q * jplane);
+          if (p.jones2) {
+            const double2* bb = p.jones2 + (int64_t)(f0 + k) * p.ld_jones + col;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) j2[q] = __ldcs(bb + q * jplane);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) j2[q] = j1[q];
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) j1[q] = j2[q] = make_double2(ja[q], 0.0);
+        }
+        const double2 c00 = make_double2(o[0], 0.0), c11 = make_double2(o[1], 0.0);
+        const double2 c01 = make_double2(o[2], -o[3]), c10 = make_double2(o[2], o[3]);
+        const double2 t00 = cadd(cmul(j1[0], c00), cmul(j1[1], c10));
+        const double2 t01 = cadd(cmul(j1[0], c01), cmul(j1[1], c11));
+        const double2 t10 = cadd(cmul(j1[2], c00), cmul(j1[3], c10));
+        const double2 t11 = cadd(cmul(j1[2], c01), cmul(j1[3], c11));
+        double2 a4[4] = {cadd(cmulc(t00, j2[0]), cmulc(t01, j2[1])), cadd(cmulc(t00, j2[2]), cmulc(t01, j2[3])),
+                         cadd(cmulc(t10, j2[0]), cmulc(t11, j2[1])), cadd(cmulc(t10, j2[2]), cmulc(t11, j2[3]))};
+        if (fringe) {
+          const double turns = s_turn[k] * delay;
+          double sn, cs;
+          rsk_sincos(RSK_D2PI * (turns - rint(turns)), &sn, &cs);
+          const double2 ph = make_double2(cs, sn);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) a4[q] = cmul(a4[q], ph);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          acc[k][2 * q] += a4[q].x;
+          acc[k][2 * q + 1] += a4[q].y;
+        }
+      }
+    }
+  }
+  // block reduction: lanes, then warps
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kVisF; ++k)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      double v = acc[k][c];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+      if (lane == 0) s_red[warp][k * 8 + c] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < kVisF * 8) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) v += s_red[w][threadIdx.x];
+    const int k = threadIdx.x >> 3, c = threadIdx.x & 7;
+    if (k < nfc)
+      p.partial[(((int64_t)blockIdx.z * p.ngroups + blockIdx.y) * p.nf + f0 + k) * 8 + c] = v;
+  }
+}
+
+// vis[b][plane][f] (complex) = sum over column groups of partial[b][g][f][plane], groups added in order
+__global__ void __launch_bounds__(kThreads) k_visibility_finish(const double* __restrict__ partial, const int ngroups,
+                                                                const int nf, const int64_t total, double* __restrict__ vis) {
+  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;  // over nbl * nf * 8
+  if (e >= total) return;
+  const int c = (int)(e & 7);
+  const int64_t bf = e >> 3;
+  const int64_t b = bf / nf;
+  const int f = (int)(bf - b * nf);
+  double v = 0.0;
+  for (int g = 0; g < ngroups; ++g) v += partial[((b * ngroups + g) * nf + f) * 8 + c];
+  vis[((b * 4 + (c >> 1)) * nf + f) * 2 + (c & 1)] = v;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host-side launch helpers
 // ---------------------------------------------------------------------------------------------------
@@ -1181,6 +1374,88 @@ int rsk_apparent_coherency(const RskSpectrum* spec, const RskCoords* coords, con
   if (!beam) return RSK_ERR_NULL;
   return coherency_impl(spec, coords, alt_az, ravg, idx, cols, ncols, ncols_dev, freqs, nf, out, ld_out, col0, 0, stream,
                         beam);
+}
+
+static int visibility_groups(int64_t ncols) {
+  int g = (int)((ncols + 16 * kThreads - 1) / (16 * kThreads));  // at least ~16 columns per thread
+  return g < 1 ? 1 : (g > kVisGroups ? kVisGroups : g);
+}
+
+int rsk_visibility(const RskSpectrum* spec, const RskCoords* coords, const double* alt_az, const double* ravg,
+                   const int64_t* idx, int64_t ncols, const int64_t* ncols_dev, const double* freqs, int64_t nf,
+                   const RskBeam* beam, const double* pos_lmn, const double* uvw_m, int64_t nbl, double* vis, void* work,
+                   size_t work_bytes, void* stream) {
+  if (!spec || !spec->stokes || !beam) return RSK_ERR_NULL;
+  if (nf < 0 || ncols < 0 || spec->n < 0 || spec->nf_in < 1 || nf > INT32_MAX || nbl < 0 || nbl > 65535) return RSK_ERR_SIZE;
+  if (spec->mode != RSK_FLAT && spec->mode != RSK_SPECTRAL_INDEX && spec->mode != RSK_FULL) return RSK_ERR_UNSUPPORTED;
+  if (beam->type < RSK_BEAM_JONES || beam->type > RSK_BEAM_UNIFORM) return RSK_ERR_MODE;
+  if (spec->mode == RSK_SPECTRAL_INDEX && (!spec->spectral_index || !spec->ref_freq || !freqs)) return RSK_ERR_NULL;
+  if (spec->mode != RSK_FULL && spec->nf_in != 1) return RSK_ERR_SIZE;
+  if (spec->mode == RSK_FULL && !spec->freq_map && nf != spec->nf_in) return RSK_ERR_SIZE;
+  const bool fringe = uvw_m != nullptr && nbl > 0;
+  if (fringe && (!pos_lmn || !freqs)) return RSK_ERR_NULL;
+  const int64_t nb = fringe ? nbl : 1;
+  if (nf == 0) return RSK_OK;
+  if (!vis) return RSK_ERR_NULL;
+  if (!idx && ncols > spec->n) return RSK_ERR_SIZE;
+  VisParams p = {};
+  p.stokes = spec->stokes;
+  p.nf_in = spec->nf_in;
+  p.n = spec->n;
+  p.alpha = spec->spectral_index;
+  p.ref_freq = spec->ref_freq;
+  p.freq_map = spec->freq_map;
+  p.polarized = spec->polarized;
+  p.pivot_hz = spec->pivot_hz;
+  if (spec->polarized) {
+    if (!coords) return RSK_ERR_NULL;
+    if (coords->rot) {
+      p.cs.rot = coords->rot;
+    } else {
+      const int rc = check_coords(coords, &p.cs);
+      if (rc != RSK_OK) return rc;
+      if (!alt_az || !ravg) return RSK_ERR_NULL;
+      for (int i = 0; i < 9; ++i) p.ravg[i] = ravg[i];
+    }
+  }
+  if (beam->type == RSK_BEAM_SHORT_DIPOLE && !alt_az) return RSK_ERR_NULL;
+  if (beam->type == RSK_BEAM_JONES) {
+    if (ncols > 0 && !beam->jones1) return RSK_ERR_NULL;
+    if (beam->ld_jones < ncols) return RSK_ERR_LD;
+    p.jones1 = reinterpret_cast<const double2*>(beam->jones1);
+    p.jones2 = reinterpret_cast<const double2*>(beam->jones2);
+    p.ld_jones = beam->ld_jones;
+  }
+  p.beam_type = beam->type;
+  p.alt_az = alt_az;
+  p.idx = idx;
+  p.ncols = ncols;
+  p.ncols_dev = ncols_dev;
+  p.freqs = freqs;
+  p.nf = (int)nf;
+  p.lmn = fringe ? pos_lmn : nullptr;
+  p.uvw = fringe ? uvw_m : nullptr;
+  p.ngroups = visibility_groups(ncols);
+  const size_t need = (size_t)nb * p.ngroups * nf * 8 * sizeof(double);
+  if (!work || work_bytes < need) return RSK_ERR_WORKSPACE;
+  p.partial = static_cast<double*>(work);
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid((unsigned)((nf + kVisF - 1) / kVisF), (unsigned)p.ngroups, (unsigned)nb);
+  switch (spec->mode) {
+    case RSK_FLAT: k_visibility<RSK_FLAT><<<grid, kThreads, 0, st>>>(p); break;
+    case RSK_SPECTRAL_INDEX: k_visibility<RSK_SPECTRAL_INDEX><<<grid, kThreads, 0, st>>>(p); break;
+    default: k_visibility<RSK_FULL><<<grid, kThreads, 0, st>>>(p); break;
+  }
+  int rc = launch_status();
+  if (rc != RSK_OK) return rc;
+  const int64_t total = nb * nf * 8;
+  k_visibility_finish<<<blocks_for(total), kThreads, 0, st>>>(p.partial, p.ngroups, (int)nf, total, vis);
+  return launch_status();
+}
+
+size_t rsk_visibility_workspace_bytes(int64_t ncols, int64_t nf, int64_t nbl) {
+  if (ncols < 0 || nf < 0 || nbl < 0) return 0;
+  return (size_t)(nbl > 0 ? nbl : 1) * visibility_groups(ncols) * (size_t)nf * 8 * sizeof(double);
 }
 
 int rsk_at_frequencies(const RskSpectrum* spec, const double* freqs, int64_t nf, const int64_t* comps, int64_t ncomps,

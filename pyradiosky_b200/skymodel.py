@@ -872,6 +872,66 @@ class SkyModel:
         self._launch_coherency(plan, 0, nf, out, ld, 0)
         return out if ld == ncols else out[..., :ncols]
 
+    def visibility_calc(self, beam="short_dipole", jones=None, jones2=None, freqs=None, uvw=None):
+        """Source-summed instrumental coherency (extension; the last step of SURVEY.md 8f N4):
+
+            vis[b, a, d, f] = sum_s (J1 C J2^H)[a, d, f, s] * exp(2j pi (f / c) uvw[b] . pos_lmn[:, s])
+
+        over the above-horizon components, i.e. what a visibility simulator (pyuvsim) computes from
+        :meth:`coherency_calc`, the beam Jones matrices and ``pos_lmn``.  Nothing per-component is written to
+        HBM.  ``uvw``: (Nbls, 3) baseline vectors in metres (array_like or CUDA tensor); ``None`` gives the
+        zero-baseline sum.  ``beam`` / ``jones`` / ``jones2`` / ``freqs`` as :meth:`apparent_coherency_calc`.
+        Spectral types flat, spectral_index and full (call :meth:`at_frequencies` first for subband models).
+
+        Returns a complex128 CUDA tensor of shape (max(Nbls, 1), 2, 2, Nfreqs).
+        """
+        if self.spectral_type == "subband" and freqs is not None:
+            raise NotImplementedError("visibility_calc evaluates flat, spectral_index and full spectra; call "
+                                      "at_frequencies() first for subband models")
+        plan = self._plan_coherency(freqs, "cubic", need_count=True)
+        nf, ncols = plan["nf"], plan["n_above"]
+        b = _lib.RskBeam()
+        if jones is not None:
+            for name, j in (("jones", jones), ("jones2", jones2)):
+                if j is None:
+                    continue
+                if (not isinstance(j, torch.Tensor) or j.dtype != torch.complex128 or not j.is_cuda
+                        or tuple(j.shape) != (2, 2, nf, ncols) or not j.is_contiguous()):
+                    raise ValueError(f"{name} must be a contiguous complex128 CUDA tensor of shape (2, 2, {nf}, {ncols})")
+            b.type = _lib.BEAM_JONES
+            b.jones1 = jones.data_ptr()
+            b.jones2 = None if jones2 is None else jones2.data_ptr()
+            b.ld_jones = max(ncols, 1)
+        else:
+            kinds = {"short_dipole": _lib.BEAM_SHORT_DIPOLE, "uniform": _lib.BEAM_UNIFORM}
+            if beam not in kinds:
+                raise ValueError("beam must be 'short_dipole' or 'uniform' (or pass jones=)")
+            b.type = kinds[beam]
+        altaz = plan["altaz"]
+        if b.type == _lib.BEAM_SHORT_DIPOLE:
+            if self.alt_az is None:
+                raise ValueError("update_positions must be called before visibility_calc")
+            altaz = self.alt_az
+        nbl = 0
+        uvw_dev = None
+        if uvw is not None:
+            if self.pos_lmn is None:
+                raise ValueError("update_positions must be called before visibility_calc with baselines")
+            uvw_dev = _as_device_f64(uvw, self.device).reshape(-1, 3).contiguous()
+            nbl = int(uvw_dev.shape[0])
+        lib = _lib.load()
+        wbytes = int(lib.rsk_visibility_workspace_bytes(ncols, nf, nbl))
+        work = torch.empty(max(wbytes, 8), dtype=torch.uint8, device=self.device)
+        vis = torch.empty((max(nbl, 1), 2, 2, nf), dtype=torch.complex128, device=self.device)
+        fptr = None if plan["fdev"] is None else _lib.ptr(plan["fdev"])
+        if fptr is None and nbl > 0:
+            fptr = _lib.ptr(self._freqs_dev(self.freq_array))  # stored channels: the fringe needs their frequencies
+        self._call("rsk_visibility", ctypes.byref(plan["spec"]), ctypes.byref(plan["coords"]), _lib.ptr(altaz), plan["ravg"],
+                   None if plan["idx"] is None else _lib.ptr(plan["idx"]), ncols, None, fptr, nf, ctypes.byref(b),
+                   _lib.ptr(self.pos_lmn) if nbl > 0 else None, _lib.ptr(uvw_dev), nbl, _lib.ptr(vis), _lib.ptr(work),
+                   ctypes.c_size_t(wbytes))
+        return vis
+
     def _plan_coherency(self, freqs, freq_interp_kind, need_count=True):
         """Everything coherency_calc needs before the launch: horizon compaction, spectral description,
         R_avg.  With ``need_count`` one device->host read (the above-horizon count) is made, after all

@@ -1209,3 +1209,71 @@ def test_peer_gather_single_rank(rsk):
     line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1]
     out = _json.loads(line)
     assert out["equal_to_unsharded"] is True and out["world"] == 1
+
+
+@pytest.mark.parametrize("spectral_type", ["flat", "spectral_index", "full"])
+def test_visibility_is_the_source_sum_of_apparent_coherency(rsk, site, spectral_type):
+    """rsk_visibility: sum over above-horizon components of J1 C J2^H times the baseline fringe, against the
+    same sum formed in numpy from the (oracle-checked) apparent coherency and pos_lmn."""
+    time, loc = site
+    rng = np.random.default_rng(57)
+    n, nf = 9000, 11
+    ra, dec = random_sky(rng, n)
+    freqs = np.linspace(110e6, 190e6, nf)
+    kw = {}
+    if spectral_type == "full":
+        st = polarized_stokes(rng, n, nf) * (1 + 0.1 * rng.normal(size=(4, nf, n)))
+        kw = dict(freq_array=freqs)
+    else:
+        st = polarized_stokes(rng, n)
+        if spectral_type == "spectral_index":
+            kw = dict(reference_frequency=np.full(n, 150e6), spectral_index=rng.normal(-0.8, 0.2, n))
+    sky = rsk.SkyModel(ra=ra, dec=dec, stokes=st, spectral_type=spectral_type, **kw)
+    sky.update_positions(time, loc)
+    req = None if spectral_type == "full" else freqs
+    above = sky.above_horizon.cpu().numpy()
+    lmn = sky.pos_lmn.cpu().numpy()[:, above]
+    uvw = np.array([[0.0, 0.0, 0.0], [14.6, 0.0, 0.0], [-120.3, 310.9, 2.4], [3000.0, -4100.0, 15.0]])
+    fringe = np.exp(2j * np.pi * (freqs[None, :, None] / 299792458.0) * np.einsum("bi,is->bs", uvw, lmn)[:, None, :])
+    # analytic beam
+    app = sky.apparent_coherency_calc(beam="short_dipole", freqs=req).cpu().numpy()
+    want0 = app.sum(axis=-1)
+    scale = np.abs(app).sum(axis=-1).max()
+    got0 = sky.visibility_calc(beam="short_dipole", freqs=req).cpu().numpy()
+    assert got0.shape == (1, 2, 2, nf)
+    assert np.max(np.abs(got0[0] - want0)) < 1e-12 * scale
+    got = sky.visibility_calc(beam="short_dipole", freqs=req, uvw=uvw).cpu().numpy()
+    want = np.einsum("adfs,bfs->badf", app, fringe)
+    assert got.shape == (4, 2, 2, nf)
+    assert np.max(np.abs(got - want)) < 1e-11 * scale  # 3000 m baselines: 1e4 turns of phase, 1e-12 turn each
+    assert np.max(np.abs(got[0] - got0[0])) == 0.0  # zero baseline == no baseline, bit for bit
+    # two different antennas with Jones arrays
+    na = app.shape[-1]
+    j1 = torch.as_tensor(rng.normal(size=(2, 2, nf, na)) + 1j * rng.normal(size=(2, 2, nf, na))).cuda()
+    j2 = torch.as_tensor(rng.normal(size=(2, 2, nf, na)) + 1j * rng.normal(size=(2, 2, nf, na))).cuda()
+    app = sky.apparent_coherency_calc(jones=j1, jones2=j2, freqs=req).cpu().numpy()
+    got = sky.visibility_calc(jones=j1, jones2=j2, freqs=req, uvw=uvw[1:3]).cpu().numpy()
+    want = np.einsum("adfs,bfs->badf", app, fringe[1:3])
+    assert np.max(np.abs(got - want)) < 1e-11 * np.abs(app).sum(axis=-1).max()
+    # deterministic
+    again = sky.visibility_calc(jones=j1, jones2=j2, freqs=req, uvw=uvw[1:3]).cpu().numpy()
+    assert np.array_equal(got, again)
+
+
+def test_visibility_errors_and_empty(rsk, site):
+    time, loc = site
+    rng = np.random.default_rng(3)
+    ra, dec = random_sky(rng, 200)
+    sub = rsk.SkyModel(ra=ra, dec=dec, stokes=polarized_stokes(rng, 200, 4), spectral_type="subband", freq_array=GLEAM_BANDS[:4])
+    sub.update_positions(time, loc)
+    with pytest.raises(NotImplementedError, match="at_frequencies"):
+        sub.visibility_calc(freqs=[90e6])
+    sky = rsk.SkyModel(ra=ra, dec=dec, stokes=polarized_stokes(rng, 200), spectral_type="flat")
+    with pytest.raises(ValueError, match="update_positions must be called"):
+        sky.visibility_calc(beam="short_dipole")
+    # everything below the horizon: zeros
+    low = rsk.SkyModel(ra=ra[:5], dec=np.full(5, np.pi / 2 - 0.01), stokes=polarized_stokes(rng, 5), spectral_type="flat")
+    low.update_positions(time, loc)
+    assert int(low.above_horizon.sum()) == 0
+    v = low.visibility_calc(beam="uniform", uvw=[[10.0, 0, 0]])
+    assert v.shape == (1, 2, 2, 1) and float(v.abs().max()) == 0.0
