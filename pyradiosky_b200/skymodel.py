@@ -924,8 +924,10 @@ class SkyModel:
         work = torch.empty(max(wbytes, 8), dtype=torch.uint8, device=self.device)
         vis = torch.empty((max(nbl, 1), 2, 2, nf), dtype=torch.complex128, device=self.device)
         fptr = None if plan["fdev"] is None else _lib.ptr(plan["fdev"])
-        if fptr is None and nbl > 0:
-            fptr = _lib.ptr(self._freqs_dev(self.freq_array))  # stored channels: the fringe needs their frequencies
+        if fptr is None and nbl > 0:  # stored channels: the fringe needs their frequencies
+            if self.freq_array is None:
+                raise ValueError("freqs must be given to form baseline fringes for a model without a freq_array")
+            fptr = _lib.ptr(self._freqs_dev(self.freq_array))
         self._call("rsk_visibility", ctypes.byref(plan["spec"]), ctypes.byref(plan["coords"]), _lib.ptr(altaz), plan["ravg"],
                    None if plan["idx"] is None else _lib.ptr(plan["idx"]), ncols, None, fptr, nf, ctypes.byref(b),
                    _lib.ptr(self.pos_lmn) if nbl > 0 else None, _lib.ptr(uvw_dev), nbl, _lib.ptr(vis), _lib.ptr(work),

@@ -1275,5 +1275,7 @@ def test_visibility_errors_and_empty(rsk, site):
     low = rsk.SkyModel(ra=ra[:5], dec=np.full(5, np.pi / 2 - 0.01), stokes=polarized_stokes(rng, 5), spectral_type="flat")
     low.update_positions(time, loc)
     assert int(low.above_horizon.sum()) == 0
-    v = low.visibility_calc(beam="uniform", uvw=[[10.0, 0, 0]])
+    with pytest.raises(ValueError, match="freqs must be given to form baseline fringes"):
+        low.visibility_calc(beam="uniform", uvw=[[10.0, 0, 0]])
+    v = low.visibility_calc(beam="uniform", uvw=[[10.0, 0, 0]], freqs=[150e6])
     assert v.shape == (1, 2, 2, 1) and float(v.abs().max()) == 0.0

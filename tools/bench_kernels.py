@@ -127,6 +127,18 @@ def main():
     rec("k_eval<spectral_index,apparent> Jones arrays, two antennas 300k x 1024",
         timeit(lambda: sky.apparent_coherency_calc(jones=j1, jones2=j2, freqs=freqs)), 192 * na * nf,
         "128 B/eval read + 64 written")
+    # source-summed consumer: nothing per-component is written; "bytes" = what the materialising route would move
+    uvw = np.array([[14.6, 0.0, 0.0]])
+    for label, kwv in (("short dipole, zero baseline", dict(beam="short_dipole")),
+                       ("short dipole, 1 baseline", dict(beam="short_dipole", uvw=uvw)),
+                       ("short dipole, 8 baselines", dict(beam="short_dipole", uvw=np.repeat(uvw, 8, axis=0) * np.arange(1, 9)[:, None])),
+                       ("Jones arrays (1 antenna), 1 baseline", dict(jones=j1, uvw=uvw))):
+        ms = timeit(lambda: sky.visibility_calc(freqs=freqs, **kwv))
+        nb = 1 if "uvw" not in kwv else len(kwv["uvw"])
+        out["k_visibility<spectral_index> " + label + " 300k x 1024"] = {
+            "ms": ms, "evals_per_s": na * nf * nb / (ms * 1e-3), "GBps": 64 * na * nf / (ms * 1e-3) / 1e9,
+            "frac_of_hbm_peak": 64 * na * nf / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": 64 * na * nf,
+            "note": "compute-bound; GBps/frac = the 64 B/eval the materialised route would have written, for comparison"}
     del j1, j2
     torch.cuda.empty_cache()
     full = sky.at_frequencies(freqs, inplace=False)  # (4, 1024, 300k) = 9.8 GB, spectral_type 'full'
