@@ -845,7 +845,7 @@ __global__ void __launch_bounds__(kThreads) k_convert_units(double* __restrict__
 // (baseline, column group, frequency); k_visibility_finish adds the column groups in a fixed order, so the
 // result is deterministic.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kVisF = 4;        // frequencies per thread
+constexpr int kVisF = 8;        // frequencies per thread (the per-column set-up is amortised over them)
 constexpr int kVisGroups = 16;  // upper bound of column groups per (frequency group, baseline)
 
 struct VisParams {
@@ -950,8 +950,22 @@ __global__ void __launch_bounds__(kThreads) k_visibility(const __grid_constant__
 #pragma unroll
           for (int q = 0; q < 4; ++q) o[q] = b[q] * pw;
         }
+        double2 a4[4];
+        if (p.beam_type != RSK_BEAM_JONES) {
+          // real Jones matrix J = [[g0, g1], [g2, g3]] on both sides: A = J C J^T in real arithmetic
+          // (C = [[o0, o2 - i o3], [o2 + i o3, o1]])
+          const double g0 = ja[0], g1 = ja[1], g2 = ja[2], g3 = ja[3];
+          const double r00 = g0 * g0 * o[0] + g1 * g1 * o[1] + 2.0 * g0 * g1 * o[2];
+          const double r11 = g2 * g2 * o[0] + g3 * g3 * o[1] + 2.0 * g2 * g3 * o[2];
+          const double r01 = g0 * g2 * o[0] + g1 * g3 * o[1] + (g0 * g3 + g1 * g2) * o[2];
+          const double i01 = (g1 * g2 - g0 * g3) * o[3];  // Im A01 = -Im A10
+          a4[0] = make_double2(r00, 0.0);
+          a4[1] = make_double2(r01, i01);
+          a4[2] = make_double2(r01, -i01);
+          a4[3] = make_double2(r11, 0.0);
+        } else {
         double2 j1[4], j2[4];
-        if (p.beam_type == RSK_BEAM_JONES) {
+        {
           const int64_t jplane = (int64_t)p.nf * p.ld_jones;
           const double2* a = p.jones1 + (int64_t)(f0 + k) * p.ld_jones + col;
 #pragma unroll
@@ -964,9 +978,6 @@ __global__ void __launch_bounds__(kThreads) k_visibility(const __grid_constant__
 #pragma unroll
             for (int q = 0; q < 4; ++q) j2[q] = j1[q];
           }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) j1[q] = j2[q] = make_double2(ja[q], 0.0);
         }
         const double2 c00 = make_double2(o[0], 0.0), c11 = make_double2(o[1], 0.0);
         const double2 c01 = make_double2(o[2], -o[3]), c10 = make_double2(o[2], o[3]);
@@ -974,8 +985,11 @@ __global__ void __launch_bounds__(kThreads) k_visibility(const __grid_constant__
         const double2 t01 = cadd(cmul(j1[0], c01), cmul(j1[1], c11));
         const double2 t10 = cadd(cmul(j1[2], c00), cmul(j1[3], c10));
         const double2 t11 = cadd(cmul(j1[2], c01), cmul(j1[3], c11));
-        double2 a4[4] = {cadd(cmulc(t00, j2[0]), cmulc(t01, j2[1])), cadd(cmulc(t00, j2[2]), cmulc(t01, j2[3])),
-                         cadd(cmulc(t10, j2[0]), cmulc(t11, j2[1])), cadd(cmulc(t10, j2[2]), cmulc(t11, j2[3]))};
+        a4[0] = cadd(cmulc(t00, j2[0]), cmulc(t01, j2[1]));
+        a4[1] = cadd(cmulc(t00, j2[2]), cmulc(t01, j2[3]));
+        a4[2] = cadd(cmulc(t10, j2[0]), cmulc(t11, j2[1]));
+        a4[3] = cadd(cmulc(t10, j2[2]), cmulc(t11, j2[3]));
+        }
         if (fringe) {
           const double turns = s_turn[k] * delay;
           double sn, cs;
