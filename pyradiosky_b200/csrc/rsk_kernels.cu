@@ -845,8 +845,8 @@ __global__ void __launch_bounds__(kThreads) k_convert_units(double* __restrict__
 // (baseline, column group, frequency); k_visibility_finish adds the column groups in a fixed order, so the
 // result is deterministic.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kVisF = 8;        // frequencies per thread (the per-column set-up is amortised over them)
-constexpr int kVisGroups = 16;  // upper bound of column groups per (frequency group, baseline)
+constexpr int kVisWork = 8;     // (frequencies per thread) x (baselines per thread): 64 accumulators in registers
+constexpr int kVisGroups = 16;  // upper bound of column groups per (frequency group, baseline group)
 
 struct VisParams {
   const double* stokes;
@@ -870,37 +870,43 @@ struct VisParams {
   int64_t ld_jones;
   const double* lmn;   // [3][n] or NULL
   const double* uvw;   // [nbl][3] metres or NULL
+  int nbl;             // >= 1 (1 with uvw == NULL: the zero baseline)
   double* partial;     // [nbl][ngroups][nf][8]
   int ngroups;
 };
 
-template <int MODE>
+// FPT frequencies x BPB baselines per thread (FPT * BPB = kVisWork).  The apparent coherency of a (column,
+// frequency) is formed once and then multiplied by the fringe of each of the BPB baselines of this block.
+template <int MODE, int FPT, int BPB>
 __global__ void __launch_bounds__(kThreads) k_visibility(const __grid_constant__ VisParams p) {
-  __shared__ double s_lf[kVisF];    // ln(f / pivot)
-  __shared__ double s_turn[kVisF];  // f / c: turns of phase per metre of delay
-  __shared__ double s_red[kThreads / 32][kVisF * 8];
-  const int f0 = blockIdx.x * kVisF;
-  const int nfc = min(kVisF, p.nf - f0);
+  __shared__ double s_lf[FPT];    // ln(f / pivot)
+  __shared__ double s_turn[FPT];  // f / c: turns of phase per metre of delay
+  __shared__ double s_uvw[BPB][3];
+  __shared__ double s_red[kThreads / 32][FPT * BPB * 8];
+  const int f0 = blockIdx.x * FPT;
+  const int nfc = min(FPT, p.nf - f0);
+  const int b0 = blockIdx.z * BPB;
+  const int nbc = min(BPB, p.nbl - b0);
   const double pivot = (MODE == RSK_SPECTRAL_INDEX) ? (p.pivot_hz > 0.0 ? p.pivot_hz : __ldg(p.freqs + p.nf / 2)) : 1.0;
-  if (threadIdx.x < kVisF) {
+  const bool fringe = p.uvw != nullptr && p.lmn != nullptr;
+  if (threadIdx.x < FPT) {
     const double f = (p.freqs && threadIdx.x < nfc) ? __ldg(p.freqs + f0 + threadIdx.x) : 1.0;
     s_lf[threadIdx.x] = MODE == RSK_SPECTRAL_INDEX ? log(f / pivot) : 0.0;
     s_turn[threadIdx.x] = f / 299792458.0;
   }
+  if (threadIdx.x < BPB * 3) {
+    const int bb = threadIdx.x / 3, ax = threadIdx.x - 3 * bb;
+    s_uvw[bb][ax] = (fringe && bb < nbc) ? __ldg(p.uvw + 3 * (b0 + bb) + ax) : 0.0;
+  }
   __syncthreads();
   const int64_t ncols = p.ncols_dev ? min(p.ncols, __ldg(p.ncols_dev)) : p.ncols;
-  double bu = 0.0, bv = 0.0, bw = 0.0;
-  const bool fringe = p.uvw != nullptr && p.lmn != nullptr;
-  if (fringe) {
-    bu = __ldg(p.uvw + 3 * blockIdx.z);
-    bv = __ldg(p.uvw + 3 * blockIdx.z + 1);
-    bw = __ldg(p.uvw + 3 * blockIdx.z + 2);
-  }
-  double acc[kVisF][8];
+  double acc[FPT][BPB][8];
 #pragma unroll
-  for (int k = 0; k < kVisF; ++k)
+  for (int k = 0; k < FPT; ++k)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[k][c] = 0.0;
+    for (int bb = 0; bb < BPB; ++bb)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[k][bb][c] = 0.0;
   const int64_t sstride = p.nf_in * p.n;
   for (int64_t col = (int64_t)blockIdx.y * kThreads + threadIdx.x; col < ncols; col += (int64_t)kThreads * p.ngroups) {
     const int64_t src = p.idx ? __ldg(p.idx + col) : col;
@@ -926,8 +932,14 @@ __global__ void __launch_bounds__(kThreads) k_visibility(const __grid_constant__
       sincos(__ldg(p.alt_az + p.n + src), &sa, &ca);
       ja[0] = se * sa; ja[1] = ca; ja[2] = se * ca; ja[3] = -sa;
     }
-    double delay = 0.0;  // metres
-    if (fringe) delay = bu * __ldg(p.lmn + src) + bv * __ldg(p.lmn + p.n + src) + bw * __ldg(p.lmn + 2 * p.n + src);
+    double delay[BPB];  // metres
+#pragma unroll
+    for (int bb = 0; bb < BPB; ++bb) delay[bb] = 0.0;
+    if (fringe) {
+      const double l = __ldg(p.lmn + src), m = __ldg(p.lmn + p.n + src), nn = __ldg(p.lmn + 2 * p.n + src);
+#pragma unroll
+      for (int bb = 0; bb < BPB; ++bb) delay[bb] = s_uvw[bb][0] * l + s_uvw[bb][1] * m + s_uvw[bb][2] * nn;
+    }
     double b[4] = {0.0, 0.0, 0.0, 0.0}, alpha = 0.0, l0 = 0.0;
     if (MODE != RSK_FULL) {
       xform<kEpiCoherency>(rot, __ldg(p.stokes + src), __ldg(p.stokes + sstride + src), __ldg(p.stokes + 2 * sstride + src),
@@ -938,7 +950,7 @@ __global__ void __launch_bounds__(kThreads) k_visibility(const __grid_constant__
       }
     }
 #pragma unroll
-    for (int k = 0; k < kVisF; ++k) {
+    for (int k = 0; k < FPT; ++k) {
       if (k < nfc) {
         double o[4];
         if (MODE == RSK_FULL) {
@@ -964,44 +976,43 @@ __global__ void __launch_bounds__(kThreads) k_visibility(const __grid_constant__
           a4[2] = make_double2(r01, -i01);
           a4[3] = make_double2(r11, 0.0);
         } else {
-        double2 j1[4], j2[4];
-        {
+          double2 j1[4], j2[4];
           const int64_t jplane = (int64_t)p.nf * p.ld_jones;
           const double2* a = p.jones1 + (int64_t)(f0 + k) * p.ld_jones + col;
 #pragma unroll
           for (int q = 0; q < 4; ++q) j1[q] = __ldcs(a + q * jplane);
           if (p.jones2) {
-            const double2* bb = p.jones2 + (int64_t)(f0 + k) * p.ld_jones + col;
+            const double2* bb2 = p.jones2 + (int64_t)(f0 + k) * p.ld_jones + col;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) j2[q] = __ldcs(bb + q * jplane);
+            for (int q = 0; q < 4; ++q) j2[q] = __ldcs(bb2 + q * jplane);
           } else {
 #pragma unroll
             for (int q = 0; q < 4; ++q) j2[q] = j1[q];
           }
-        }
-        const double2 c00 = make_double2(o[0], 0.0), c11 = make_double2(o[1], 0.0);
-        const double2 c01 = make_double2(o[2], -o[3]), c10 = make_double2(o[2], o[3]);
-        const double2 t00 = cadd(cmul(j1[0], c00), cmul(j1[1], c10));
-        const double2 t01 = cadd(cmul(j1[0], c01), cmul(j1[1], c11));
-        const double2 t10 = cadd(cmul(j1[2], c00), cmul(j1[3], c10));
-        const double2 t11 = cadd(cmul(j1[2], c01), cmul(j1[3], c11));
-        a4[0] = cadd(cmulc(t00, j2[0]), cmulc(t01, j2[1]));
-        a4[1] = cadd(cmulc(t00, j2[2]), cmulc(t01, j2[3]));
-        a4[2] = cadd(cmulc(t10, j2[0]), cmulc(t11, j2[1]));
-        a4[3] = cadd(cmulc(t10, j2[2]), cmulc(t11, j2[3]));
-        }
-        if (fringe) {
-          const double turns = s_turn[k] * delay;
-          double sn, cs;
-          rsk_sincos(RSK_D2PI * (turns - rint(turns)), &sn, &cs);
-          const double2 ph = make_double2(cs, sn);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) a4[q] = cmul(a4[q], ph);
+          const double2 c00 = make_double2(o[0], 0.0), c11 = make_double2(o[1], 0.0);
+          const double2 c01 = make_double2(o[2], -o[3]), c10 = make_double2(o[2], o[3]);
+          const double2 t00 = cadd(cmul(j1[0], c00), cmul(j1[1], c10));
+          const double2 t01 = cadd(cmul(j1[0], c01), cmul(j1[1], c11));
+          const double2 t10 = cadd(cmul(j1[2], c00), cmul(j1[3], c10));
+          const double2 t11 = cadd(cmul(j1[2], c01), cmul(j1[3], c11));
+          a4[0] = cadd(cmulc(t00, j2[0]), cmulc(t01, j2[1]));
+          a4[1] = cadd(cmulc(t00, j2[2]), cmulc(t01, j2[3]));
+          a4[2] = cadd(cmulc(t10, j2[0]), cmulc(t11, j2[1]));
+          a4[3] = cadd(cmulc(t10, j2[2]), cmulc(t11, j2[3]));
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          acc[k][2 * q] += a4[q].x;
-          acc[k][2 * q + 1] += a4[q].y;
+        for (int bb = 0; bb < BPB; ++bb) {
+          double2 ph = make_double2(1.0, 0.0);
+          if (fringe) {
+            const double turns = s_turn[k] * delay[bb];
+            rsk_sincos(RSK_D2PI * (turns - rint(turns)), &ph.y, &ph.x);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const double2 v = fringe ? cmul(a4[q], ph) : a4[q];
+            acc[k][bb][2 * q] += v.x;
+            acc[k][bb][2 * q + 1] += v.y;
+          }
         }
       }
     }
@@ -1009,22 +1020,25 @@ __global__ void __launch_bounds__(kThreads) k_visibility(const __grid_constant__
   // block reduction: lanes, then warps
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < kVisF; ++k)
+  for (int k = 0; k < FPT; ++k)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      double v = acc[k][c];
+    for (int bb = 0; bb < BPB; ++bb)
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
-      if (lane == 0) s_red[warp][k * 8 + c] = v;
-    }
+      for (int c = 0; c < 8; ++c) {
+        double v = acc[k][bb][c];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+        if (lane == 0) s_red[warp][(k * BPB + bb) * 8 + c] = v;
+      }
   __syncthreads();
-  if (threadIdx.x < kVisF * 8) {
+  if (threadIdx.x < FPT * BPB * 8) {
     double v = 0.0;
 #pragma unroll
     for (int w = 0; w < kThreads / 32; ++w) v += s_red[w][threadIdx.x];
-    const int k = threadIdx.x >> 3, c = threadIdx.x & 7;
-    if (k < nfc)
-      p.partial[(((int64_t)blockIdx.z * p.ngroups + blockIdx.y) * p.nf + f0 + k) * 8 + c] = v;
+    const int c = threadIdx.x & 7, kb = threadIdx.x >> 3;
+    const int k = kb / BPB, bb = kb - k * BPB;
+    if (k < nfc && bb < nbc)
+      p.partial[(((int64_t)(b0 + bb) * p.ngroups + blockIdx.y) * p.nf + f0 + k) * 8 + c] = v;
   }
 }
 
@@ -1449,17 +1463,30 @@ int rsk_visibility(const RskSpectrum* spec, const RskCoords* coords, const doubl
   p.nf = (int)nf;
   p.lmn = fringe ? pos_lmn : nullptr;
   p.uvw = fringe ? uvw_m : nullptr;
+  p.nbl = (int)nb;
   p.ngroups = visibility_groups(ncols);
   const size_t need = (size_t)nb * p.ngroups * nf * 8 * sizeof(double);
   if (!work || work_bytes < need) return RSK_ERR_WORKSPACE;
   p.partial = static_cast<double*>(work);
   cudaStream_t st = (cudaStream_t)stream;
-  const dim3 grid((unsigned)((nf + kVisF - 1) / kVisF), (unsigned)p.ngroups, (unsigned)nb);
-  switch (spec->mode) {
-    case RSK_FLAT: k_visibility<RSK_FLAT><<<grid, kThreads, 0, st>>>(p); break;
-    case RSK_SPECTRAL_INDEX: k_visibility<RSK_SPECTRAL_INDEX><<<grid, kThreads, 0, st>>>(p); break;
-    default: k_visibility<RSK_FULL><<<grid, kThreads, 0, st>>>(p); break;
+  // work per thread: 8 frequencies x 1 baseline, 4 x 2 or 2 x 4 -- the apparent coherency is shared by the
+  // baselines of a block, the per-column set-up by its frequencies
+#define RSK_VIS(M, F, B)                                                                                 \
+  do {                                                                                                   \
+    const dim3 grid((unsigned)((nf + (F) - 1) / (F)), (unsigned)p.ngroups, (unsigned)((nb + (B) - 1) / (B))); \
+    k_visibility<M, F, B><<<grid, kThreads, 0, st>>>(p);                                                 \
+  } while (0)
+#define RSK_VIS_MODE(F, B)                                                        \
+  switch (spec->mode) {                                                           \
+    case RSK_FLAT: RSK_VIS(RSK_FLAT, F, B); break;                                \
+    case RSK_SPECTRAL_INDEX: RSK_VIS(RSK_SPECTRAL_INDEX, F, B); break;            \
+    default: RSK_VIS(RSK_FULL, F, B); break;                                      \
   }
+  if (nb >= 4) { RSK_VIS_MODE(2, 4) }
+  else if (nb >= 2) { RSK_VIS_MODE(4, 2) }
+  else { RSK_VIS_MODE(8, 1) }
+#undef RSK_VIS_MODE
+#undef RSK_VIS
   int rc = launch_status();
   if (rc != RSK_OK) return rc;
   const int64_t total = nb * nf * 8;
