@@ -27,7 +27,7 @@ pinned = {k: torch.as_tensor(v).pin_memory() for k, v in host.items()}
 freqs = np.linspace(100e6, 200e6, nf)
 loc = EarthLocation.from_dms((-30, 43, 17.5), (21, 25, 41.9), 1073.0)
 out = torch.empty(4 * nf * n, dtype=torch.complex128).pin_memory()
-threads = max(1, (3 * (os.cpu_count() or 1)) // 4)
+threads = int(os.environ.get("THREADS", max(1, (3 * (os.cpu_count() or 1)) // 4)))
 res = {"n": n, "nf": nf, "cpu_count": os.cpu_count(), "unpack_threads": threads}
 
 
