@@ -237,6 +237,19 @@ def test_sweep_equals_repeated_update(rsk, site):
     assert np.array_equal((~up).all(axis=0)[margin], (tans < -1)[margin])
     a2, _, m2 = sky.positions_sweep(times[:3], loc, want_lmn=False, want_mask=False)
     assert m2 is None and float((a2 - alt_az[:3]).abs().max()) < 1e-14
+    # contexts with refraction / diurnal aberration mixed with plain ones (some time blocks folded, some not):
+    # the sweep takes the general chain where it must, and agrees with the oracle
+    astroms = np.stack([rsk.astrometry.astrom_context(t, loc) for t in times])
+    for k in (3, 4, 20, 36):
+        astroms[k, E.I_REFA], astroms[k, E.I_REFB], astroms[k, E.I_DIURAB] = 2.8e-4, -3.2e-7, 1.3e-6
+    a3, l3, m3 = sky.positions_sweep(None, loc, astroms=astroms, want_lmn=True)
+    for k in (0, 3, 4, 5, 20, 33, 36):
+        sky.update_positions(times[k], loc, astrom=astroms[k])
+        assert float((sky.alt_az - a3[k]).abs().max()) < 1e-14
+        assert float((sky.pos_lmn - l3[k]).abs().max()) < 1e-14
+        xi = m @ np.array([np.cos(lat) * np.cos(lon), np.cos(lat) * np.sin(lon), np.sin(lat)])
+        ref_alt_az, _, _ = S.update_positions(np.arctan2(xi[1], xi[0]), np.arcsin(np.clip(xi[2], -1, 1)), astroms[k])
+        assert_altaz_close(a3[k].cpu().numpy(), ref_alt_az)
 
 
 # ---------------------------------------------------------------------------------------------------
