@@ -363,9 +363,14 @@ RSK_HD void rsk_hpx_center(int64_t nside, int nested, int64_t pix, double& z, do
   int64_t nr, jp, kshift, jr_eq;
   int region;  // +1 north cap, 0 belt, -1 south cap
   if (nested) {
-    const int64_t npface = nside * nside;
-    const int64_t face = pix / npface;
-    const uint64_t ipf = (uint64_t)(pix - face * npface);
+    // nside is a power of two here (checked by the entry points): shifts and masks instead of 64-bit divisions
+#if defined(__CUDA_ARCH__)
+    const int sh = 2 * (63 - __clzll((long long)nside));
+#else
+    const int sh = 2 * (63 - __builtin_clzll((unsigned long long)nside));
+#endif
+    const int64_t face = pix >> sh;
+    const uint64_t ipf = (uint64_t)pix & (((uint64_t)1 << sh) - 1);
     const int64_t ix = rsk_compact_bits(ipf);
     const int64_t iy = rsk_compact_bits(ipf >> 1);
     const int64_t jrll = 2 + (face >> 2);
@@ -387,8 +392,10 @@ RSK_HD void rsk_hpx_center(int64_t nside, int nested, int64_t pix, double& z, do
   } else if (pix < npix - ncap) {
     region = 0;
     const int64_t ip = pix - ncap;
-    jr_eq = ip / nl4 + nside;
-    jp = ip - (jr_eq - nside) * nl4 + 1;
+    // 32-bit division when the map is small enough (nside <= 8192 always is): a 64-bit one costs ~100 instructions
+    const int64_t q = ((uint64_t)ip | (uint64_t)nl4) >> 32 ? ip / nl4 : (int64_t)((uint32_t)ip / (uint32_t)nl4);
+    jr_eq = q + nside;
+    jp = ip - q * nl4 + 1;
     nr = nside;
     kshift = (jr_eq - nside) & 1;
   } else {
