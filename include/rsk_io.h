@@ -117,6 +117,13 @@ int rsk_h5w_group(RskH5Writer* w, const char* path);
  * chunk == NULL: contiguous.  gzip_level 1-9 with a chunk shape adds shuffle + deflate. */
 int rsk_h5w_dataset(RskH5Writer* w, const char* path, int type_class, int elem_size, int rank, const int64_t* dims,
                     const void* data, const int64_t* chunk, int gzip_level);
+/* The same from a DEVICE array (HBM -> file): up to three dimensions; the array is fetched in slabs (one chunk-row
+ * along the first axis times a run of chunk-rows along the second) through two pinned staging buffers, each pitched
+ * device->host copy on ``stream`` overlapping the chunking / deflating / writing of the previous slab.  Returns when
+ * the data has been written. */
+int rsk_h5w_dataset_device(RskH5Writer* w, const char* path, int type_class, int elem_size, int rank,
+                           const int64_t* dims, const void* device_data, const int64_t* chunk, int gzip_level,
+                           void* stream);
 int rsk_h5w_attr_string(RskH5Writer* w, const char* path, const char* name, const char* value);
 /* Writes the file; the handle is freed whatever the result. */
 int rsk_h5w_close(RskH5Writer* w);

@@ -231,6 +231,11 @@ _IO_SIGNATURES = {
         [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_int64_p, ctypes.c_void_p,
          _c_int64_p, ctypes.c_int],
     ),
+    "rsk_h5w_dataset_device": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_int64_p, ctypes.c_void_p,
+         _c_int64_p, ctypes.c_int, ctypes.c_void_p],
+    ),
     "rsk_h5w_attr_string": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]),
     "rsk_h5w_close": (ctypes.c_int, [ctypes.c_void_p]),
 }

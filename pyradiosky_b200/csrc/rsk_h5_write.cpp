@@ -10,6 +10,7 @@
 //
 // Raw data is written as soon as rsk_h5w_dataset() is called (nothing big is kept in memory); all
 // metadata is laid out and written by rsk_h5w_close().
+#include <cuda_runtime.h>
 #include <fcntl.h>
 #include <stdint.h>
 #include <string.h>
@@ -241,8 +242,50 @@ int rsk_h5w_group(RskH5Writer* w, const char* path) {
   return RSK_H5_OK;
 }
 
-int rsk_h5w_dataset(RskH5Writer* w, const char* path, int type_class, int elem_size, int rank, const int64_t* dims,
-                    const void* data, const int64_t* chunk, int gzip_level) {
+}  // extern "C"
+
+namespace {
+
+// A piece of the dataset that is in host memory: the sub-array [lo, lo + ext) in C order at ``base``.
+struct Slab {
+  const uint8_t* base;
+  int64_t lo[8];
+  int64_t ext[8];
+  int64_t c_first, c_count;  // the chunks (C order of the chunk grid) that lie inside it
+};
+
+// Where the data comes from.  Host arrays are one slab; device arrays are staged through two pinned buffers:
+// a slab is one chunk-row along the first axis times a run of chunk-rows along the second (all of the last
+// axis), fetched with one pitched device->host copy while the previous slab is being chunked and written.
+struct Source {
+  const uint8_t* host = nullptr;
+  const uint8_t* dev = nullptr;
+  cudaStream_t stream = nullptr;
+  uint8_t* stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  size_t stage_bytes = 0;
+  ~Source() {
+    for (int i = 0; i < 2; ++i) {
+      if (ev[i]) cudaEventDestroy(ev[i]);
+      if (stage[i]) cudaFreeHost(stage[i]);
+    }
+  }
+  int ensure(size_t bytes) {
+    if (bytes <= stage_bytes) return RSK_H5_OK;
+    for (int i = 0; i < 2; ++i) {
+      if (stage[i]) cudaFreeHost(stage[i]);
+      stage[i] = nullptr;
+      cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&stage[i]), bytes, cudaHostAllocDefault);
+      if (e == cudaSuccess && !ev[i]) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+      if (e != cudaSuccess) return (int)e;
+    }
+    stage_bytes = bytes;
+    return RSK_H5_OK;
+  }
+};
+
+int write_dataset_impl(RskH5Writer* w, const char* path, int type_class, int elem_size, int rank, const int64_t* dims,
+                       Source& source, const int64_t* chunk, int gzip_level) {
   if (!w || !path) return RSK_H5_ERR_NULL;
   if (rank < 0 || rank > 7 || (rank > 0 && !dims)) return RSK_H5_ERR_SIZE;
   if (type_class < RSK_H5_INT || type_class > RSK_H5_STRING) return RSK_H5_ERR_TYPE;
@@ -266,94 +309,182 @@ int rsk_h5w_dataset(RskH5Writer* w, const char* path, int type_class, int elem_s
     d.dims[a] = dims[a];
     count *= dims[a];
   }
-  if (count > 0 && !data) return RSK_H5_ERR_NULL;
-  const uint8_t* src = static_cast<const uint8_t*>(data);
-  if (type_class == RSK_H5_STRING)
-    for (int64_t i = 0; i < count * elem_size; ++i) d.utf8 = d.utf8 || src[i] >= 0x80;
+  if (count > 0 && !source.host && !source.dev) return RSK_H5_ERR_NULL;
+  if (type_class == RSK_H5_STRING) {
+    if (!source.host && count > 0) return RSK_H5_ERR_TYPE;  // strings live on the host
+    for (int64_t i = 0; i < count * elem_size; ++i) d.utf8 = d.utf8 || source.host[i] >= 0x80;
+  }
   d.chunked = chunk != nullptr && rank > 0 && count > 0;
+  const int64_t slab_target = 64ll << 20;
   if (!d.chunked) {
     d.data_size = (uint64_t)count * elem_size;
     if (d.data_size > 0) {
       d.data_addr = w->alloc(d.data_size);
-      if (!w->write_at(d.data_addr, src, d.data_size)) return RSK_H5_ERR_OPEN;
+      if (source.host) {
+        if (!w->write_at(d.data_addr, source.host, d.data_size)) return RSK_H5_ERR_OPEN;
+      } else {  // device array, contiguous layout: flat slabs through the two staging buffers
+        const uint64_t per = (uint64_t)std::min<int64_t>(slab_target, (int64_t)d.data_size);
+        int rc = source.ensure(per);
+        if (rc != RSK_H5_OK) return rc;
+        const uint64_t nslabs = (d.data_size + per - 1) / per;
+        auto fetch = [&](uint64_t sidx) {
+          const uint64_t o = sidx * per, nbytes = std::min(per, d.data_size - o);
+          cudaMemcpyAsync(source.stage[sidx & 1], source.dev + o, nbytes, cudaMemcpyDeviceToHost, source.stream);
+          cudaEventRecord(source.ev[sidx & 1], source.stream);
+        };
+        fetch(0);
+        for (uint64_t sidx = 0; sidx < nslabs; ++sidx) {
+          if (cudaEventSynchronize(source.ev[sidx & 1]) != cudaSuccess) return (int)cudaGetLastError();
+          if (sidx + 1 < nslabs) fetch(sidx + 1);
+          const uint64_t o = sidx * per, nbytes = std::min(per, d.data_size - o);
+          if (!w->write_at(d.data_addr + o, source.stage[sidx & 1], nbytes)) return RSK_H5_ERR_OPEN;
+        }
+      }
     }
-  } else {
-    d.gzip = gzip_level < 0 ? 0 : (gzip_level > 9 ? 9 : gzip_level);
-    int64_t grid[8], nchunks = 1, cbytes = elem_size;
+    p->kids[leaf] = std::move(node);
+    return RSK_H5_OK;
+  }
+
+  d.gzip = gzip_level < 0 ? 0 : (gzip_level > 9 ? 9 : gzip_level);
+  int64_t grid[8], nchunks = 1, cbytes = elem_size;
+  for (int a = 0; a < rank; ++a) {
+    if (chunk[a] < 1 || chunk[a] > 0xffffffffll) return RSK_H5_ERR_SIZE;
+    d.chunk[a] = std::min(chunk[a], std::max<int64_t>(d.dims[a], 1));
+    grid[a] = (d.dims[a] + d.chunk[a] - 1) / d.chunk[a];
+    nchunks *= grid[a];
+    cbytes *= d.chunk[a];
+  }
+  if (cbytes > 0xffffffffll) return RSK_H5_ERR_SIZE;
+
+  // ---- slabs ----------------------------------------------------------------------------------------
+  std::vector<Slab> slabs;
+  if (source.host) {
+    Slab sl = {};
+    sl.base = source.host;
     for (int a = 0; a < rank; ++a) {
-      if (chunk[a] < 1 || chunk[a] > 0xffffffffll) return RSK_H5_ERR_SIZE;
-      d.chunk[a] = std::min(chunk[a], std::max<int64_t>(d.dims[a], 1));
-      grid[a] = (d.dims[a] + d.chunk[a] - 1) / d.chunk[a];
-      nchunks *= grid[a];
-      cbytes *= d.chunk[a];
+      sl.lo[a] = 0;
+      sl.ext[a] = d.dims[a];
     }
-    if (cbytes > 0xffffffffll) return RSK_H5_ERR_SIZE;
-    // Chunks are produced by a few threads: gather (+ shuffle + deflate).  Uncompressed chunks have a known
-    // size, so their addresses are assigned up front and every thread writes its own chunks; deflated ones
-    // are produced in batches and written in order.
-    unsigned hc = std::thread::hardware_concurrency();
-    const int nt = (int)std::max(1u, std::min(hc ? hc : 4u, 16u));
-    auto gather = [&](int64_t ci, std::vector<uint8_t>& raw) {
-      int64_t c[8], rem = ci;
-      for (int a = rank - 1; a >= 0; --a) {
-        c[a] = rem % grid[a];
-        rem /= grid[a];
-      }
-      raw.assign((size_t)cbytes, 0);
-      int64_t lo[8], ext[8];
-      for (int a = 0; a < rank; ++a) {
-        lo[a] = c[a] * d.chunk[a];
-        ext[a] = std::min(d.chunk[a], d.dims[a] - lo[a]);
-      }
-      int64_t idx[8] = {0};
-      const int last = rank - 1;
-      for (;;) {  // copy the rows of this chunk that lie inside the dataset
-        int64_t so = 0, dof = 0;
+    sl.c_first = 0;
+    sl.c_count = nchunks;
+    slabs.push_back(sl);
+  } else {
+    if (rank > 3) return RSK_H5_ERR_UNSUPPORTED;  // device arrays: up to three dimensions
+    // (A, B, C) view with leading ones
+    int64_t D[3] = {1, 1, 1}, Cc[3] = {1, 1, 1}, G[3] = {1, 1, 1};
+    for (int a = 0; a < rank; ++a) {
+      D[3 - rank + a] = d.dims[a];
+      Cc[3 - rank + a] = d.chunk[a];
+      G[3 - rank + a] = grid[a];
+    }
+    const int64_t row_bytes = Cc[0] * Cc[1] * D[2] * elem_size;
+    const int64_t rows_per_slab = std::max<int64_t>(1, std::min(G[1], slab_target / std::max<int64_t>(row_bytes, 1)));
+    int rc = source.ensure((size_t)(rows_per_slab * row_bytes));
+    if (rc != RSK_H5_OK) return rc;
+    for (int64_t ia = 0; ia < G[0]; ++ia)
+      for (int64_t ib0 = 0; ib0 < G[1]; ib0 += rows_per_slab) {
+        const int64_t ib1 = std::min(G[1], ib0 + rows_per_slab);
+        Slab sl = {};
+        int64_t lo3[3] = {ia * Cc[0], ib0 * Cc[1], 0};
+        int64_t ext3[3] = {std::min(Cc[0], D[0] - lo3[0]), std::min(ib1 * Cc[1], D[1]) - lo3[1], D[2]};
         for (int a = 0; a < rank; ++a) {
-          so = so * d.dims[a] + (lo[a] + idx[a]);
-          dof = dof * d.chunk[a] + idx[a];
+          sl.lo[a] = lo3[3 - rank + a];
+          sl.ext[a] = ext3[3 - rank + a];
         }
-        memcpy(raw.data() + dof * elem_size, src + so * elem_size, (size_t)ext[last] * elem_size);
-        int a = last - 1;
-        for (; a >= 0; --a) {
-          if (++idx[a] < ext[a]) break;
-          idx[a] = 0;
-        }
-        if (a < 0) break;
+        sl.c_first = (ia * G[1] + ib0) * G[2];
+        sl.c_count = (ib1 - ib0) * G[2];
+        slabs.push_back(sl);
+      }
+  }
+  auto fetch = [&](size_t si) {  // device -> staging buffer si & 1 (asynchronous)
+    Slab& sl = slabs[si];
+    int64_t lo3[3] = {0, 0, 0}, ext3[3] = {1, 1, 1}, D[3] = {1, 1, 1};
+    for (int a = 0; a < rank; ++a) {
+      lo3[3 - rank + a] = sl.lo[a];
+      ext3[3 - rank + a] = sl.ext[a];
+      D[3 - rank + a] = d.dims[a];
+    }
+    const size_t width = (size_t)(ext3[1] * D[2] * elem_size);
+    cudaMemcpy2DAsync(source.stage[si & 1], width, source.dev + ((lo3[0] * D[1] + lo3[1]) * D[2]) * elem_size,
+                      (size_t)(D[1] * D[2] * elem_size), width, (size_t)ext3[0], cudaMemcpyDeviceToHost, source.stream);
+    cudaEventRecord(source.ev[si & 1], source.stream);
+    sl.base = source.stage[si & 1];
+  };
+
+  // ---- chunks ---------------------------------------------------------------------------------------
+  // Chunks are produced by a few threads: gather (+ shuffle + deflate).  Uncompressed chunks have a known
+  // size, so their addresses are assigned up front and every thread writes its own chunks; deflated ones
+  // are produced in batches and written in order.
+  unsigned hc = std::thread::hardware_concurrency();
+  const int nt = (int)std::max(1u, std::min(hc ? hc : 4u, 16u));
+  auto chunk_offsets = [&](int64_t ci, uint64_t* off) {
+    int64_t rem = ci;
+    for (int a = rank - 1; a >= 0; --a) {
+      off[a] = (uint64_t)((rem % grid[a]) * d.chunk[a]);
+      rem /= grid[a];
+    }
+  };
+  auto gather = [&](int64_t ci, const Slab& sl, std::vector<uint8_t>& raw) {
+    uint64_t off[8];
+    chunk_offsets(ci, off);
+    raw.assign((size_t)cbytes, 0);
+    int64_t lo[8], ext[8];
+    for (int a = 0; a < rank; ++a) {
+      lo[a] = (int64_t)off[a];
+      ext[a] = std::min(d.chunk[a], d.dims[a] - lo[a]);
+    }
+    int64_t idx[8] = {0};
+    const int last = rank - 1;
+    for (;;) {  // copy the rows of this chunk that lie inside the dataset
+      int64_t so = 0, dof = 0;
+      for (int a = 0; a < rank; ++a) {
+        so = so * sl.ext[a] + (lo[a] + idx[a] - sl.lo[a]);
+        dof = dof * d.chunk[a] + idx[a];
+      }
+      memcpy(raw.data() + dof * elem_size, sl.base + so * elem_size, (size_t)ext[last] * elem_size);
+      int a = last - 1;
+      for (; a >= 0; --a) {
+        if (++idx[a] < ext[a]) break;
+        idx[a] = 0;
+      }
+      if (a < 0) break;
+    }
+  };
+  auto run_parallel = [&](int64_t n, auto&& body) {
+    std::atomic<int64_t> next{0};
+    auto worker = [&]() {
+      std::vector<uint8_t> raw, tmp;
+      for (;;) {
+        const int64_t i = next.fetch_add(1);
+        if (i >= n) break;
+        body(i, raw, tmp);
       }
     };
-    auto chunk_offsets = [&](int64_t ci, uint64_t* off) {
-      int64_t rem = ci;
-      for (int a = rank - 1; a >= 0; --a) {
-        off[a] = (uint64_t)((rem % grid[a]) * d.chunk[a]);
-        rem /= grid[a];
-      }
-    };
-    auto run_parallel = [&](int64_t n, auto&& body) {
-      std::atomic<int64_t> next{0};
-      auto worker = [&]() {
-        std::vector<uint8_t> raw, tmp;
-        for (;;) {
-          const int64_t i = next.fetch_add(1);
-          if (i >= n) break;
-          body(i, raw, tmp);
-        }
-      };
-      std::vector<std::thread> th;
-      for (int t = 1; t < nt && t < n; ++t) th.emplace_back(worker);
-      worker();
-      for (auto& t : th) t.join();
-    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt && t < n; ++t) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
+  };
+  if (!d.gzip) {
+    d.chunks.resize((size_t)nchunks);
+    for (int64_t ci = 0; ci < nchunks; ++ci) {
+      d.chunks[(size_t)ci].size = (uint32_t)cbytes;
+      d.chunks[(size_t)ci].addr = w->alloc((uint64_t)cbytes);
+      chunk_offsets(ci, d.chunks[(size_t)ci].off);
+    }
+  }
+  if (source.dev) fetch(0);
+  for (size_t si = 0; si < slabs.size(); ++si) {
+    if (source.dev) {
+      if (cudaEventSynchronize(source.ev[si & 1]) != cudaSuccess) return (int)cudaGetLastError();
+      if (si + 1 < slabs.size()) fetch(si + 1);  // the other buffer: its chunks were written one iteration ago
+    }
+    const Slab& sl = slabs[si];
     if (!d.gzip) {
-      d.chunks.resize((size_t)nchunks);
-      for (int64_t ci = 0; ci < nchunks; ++ci) {
-        d.chunks[(size_t)ci].size = (uint32_t)cbytes;
-        d.chunks[(size_t)ci].addr = w->alloc((uint64_t)cbytes);
-        chunk_offsets(ci, d.chunks[(size_t)ci].off);
-      }
       std::atomic<bool> io_ok{true};
-      run_parallel(nchunks, [&](int64_t ci, std::vector<uint8_t>& raw, std::vector<uint8_t>&) {
-        gather(ci, raw);
+      run_parallel(sl.c_count, [&](int64_t i, std::vector<uint8_t>& raw, std::vector<uint8_t>&) {
+        const int64_t ci = sl.c_first + i;
+        gather(ci, sl, raw);
         if (!w->write_at(d.chunks[(size_t)ci].addr, raw.data(), (size_t)cbytes)) io_ok = false;
       });
       if (!io_ok) return RSK_H5_ERR_OPEN;
@@ -361,10 +492,10 @@ int rsk_h5w_dataset(RskH5Writer* w, const char* path, int type_class, int elem_s
       const int64_t batch = (int64_t)nt * 4;
       std::vector<std::vector<uint8_t>> outb((size_t)batch);
       std::vector<int> status((size_t)batch);
-      for (int64_t c0 = 0; c0 < nchunks; c0 += batch) {
-        const int64_t nb = std::min(batch, nchunks - c0);
+      for (int64_t c0 = 0; c0 < sl.c_count; c0 += batch) {
+        const int64_t nb = std::min(batch, sl.c_count - c0);
         run_parallel(nb, [&](int64_t i, std::vector<uint8_t>& raw, std::vector<uint8_t>& sh) {
-          gather(c0 + i, raw);
+          gather(sl.c_first + c0 + i, sl, raw);
           sh.resize((size_t)cbytes);
           const size_t ne = (size_t)(cbytes / elem_size);
           for (size_t e = 0; e < ne; ++e)
@@ -380,7 +511,7 @@ int rsk_h5w_dataset(RskH5Writer* w, const char* path, int type_class, int elem_s
           ChunkOut co;
           co.size = (uint32_t)outb[(size_t)i].size();
           co.addr = w->alloc(co.size);
-          chunk_offsets(c0 + i, co.off);
+          chunk_offsets(sl.c_first + c0 + i, co.off);
           if (!w->write_at(co.addr, outb[(size_t)i].data(), co.size)) return RSK_H5_ERR_OPEN;
           d.chunks.push_back(co);
         }
@@ -389,6 +520,26 @@ int rsk_h5w_dataset(RskH5Writer* w, const char* path, int type_class, int elem_s
   }
   p->kids[leaf] = std::move(node);
   return RSK_H5_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rsk_h5w_dataset(RskH5Writer* w, const char* path, int type_class, int elem_size, int rank, const int64_t* dims,
+                    const void* data, const int64_t* chunk, int gzip_level) {
+  Source src;
+  src.host = static_cast<const uint8_t*>(data);
+  return write_dataset_impl(w, path, type_class, elem_size, rank, dims, src, chunk, gzip_level);
+}
+
+int rsk_h5w_dataset_device(RskH5Writer* w, const char* path, int type_class, int elem_size, int rank,
+                           const int64_t* dims, const void* device_data, const int64_t* chunk, int gzip_level,
+                           void* stream) {
+  Source src;
+  src.dev = static_cast<const uint8_t*>(device_data);
+  src.stream = (cudaStream_t)stream;
+  return write_dataset_impl(w, path, type_class, elem_size, rank, dims, src, chunk, gzip_level);
 }
 
 int rsk_h5w_attr_string(RskH5Writer* w, const char* path, const char* name, const char* value) {

@@ -438,6 +438,24 @@ class H5Writer:
         if object_type is not None:
             self.attr(path, "object_type", object_type)
 
+    def dataset_device(self, path, tensor, chunks=None, gzip=0, unit=None):
+        """float64 / int64 CUDA tensor (up to 3-D) -> dataset, streamed HBM -> pinned slabs -> file."""
+        t = tensor.contiguous()
+        if t.dtype not in (torch.float64, torch.int64) or not t.is_cuda or t.dim() > 3:
+            raise TypeError("dataset_device takes float64 or int64 CUDA tensors of up to three dimensions")
+        kind = _lib.H5_FLOAT if t.dtype == torch.float64 else _lib.H5_INT
+        dims = (ctypes.c_int64 * max(t.dim(), 1))(*t.shape)
+        ch = None
+        if chunks is not None and t.dim() > 0 and t.numel() > 0:
+            ch = (ctypes.c_int64 * t.dim())(*[int(c) for c in chunks])
+        with torch.cuda.device(t.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+            self._check("rsk_h5w_dataset_device",
+                        self._lib.rsk_h5w_dataset_device(self._h, path.encode(), kind, 8, t.dim(), dims,
+                                                         ctypes.c_void_p(t.data_ptr()), ch, int(gzip), stream))
+        if unit is not None:
+            self.attr(path, "unit", unit)
+
     def attr(self, path, name, value):
         self._check("rsk_h5w_attr_string",
                     self._lib.rsk_h5w_attr_string(self._h, path.encode(), name.encode(), str(value).encode("utf8")))
@@ -536,11 +554,10 @@ def write_skyh5(sky, filename, clobber=False, data_compression=None):
             for key, value in sky.extra_columns.items():
                 w.dataset(f"/Header/extra_columns/{key}", value)
         w.group("/Data")
-        stokes = _host(sky.stokes)
-        w.dataset("/Data/stokes", stokes, chunks=guess_chunks(stokes.shape), gzip=gz, unit=sky.stokes_unit)
+        # the cubes go HBM -> pinned slabs -> file, without a host copy of the whole array
+        w.dataset_device("/Data/stokes", sky.stokes, chunks=guess_chunks(sky.stokes.shape), gzip=gz, unit=sky.stokes_unit)
         for extra in ("stokes_error", "beam_amp"):
             val = getattr(sky, extra, None)
             if val is not None:
-                arr = _host(val)
-                w.dataset(f"/Data/{extra}", arr, chunks=guess_chunks(arr.shape), gzip=gz,
-                          unit=sky.stokes_unit if extra == "stokes_error" else None)
+                w.dataset_device(f"/Data/{extra}", val, chunks=guess_chunks(val.shape), gzip=gz,
+                                 unit=sky.stokes_unit if extra == "stokes_error" else None)
