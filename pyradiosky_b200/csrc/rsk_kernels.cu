@@ -7,6 +7,7 @@
 // per block, and grids linearised so that blocks that share a component tile run back to back and
 // re-read its few hundred input bytes from L2 instead of HBM.  Output rows should start on 256-byte
 // boundaries (ld_out % 16 == 0): measured +25-30 % HBM write throughput on B200.
+#include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -429,7 +430,30 @@ constexpr int kEpiApparent = 2;   // (2, 2, nf, ld) J1 C J2^H               -- c
 struct JonesPair {
   double2 a[4];  // antenna 1
   double2 b[4];  // antenna 2
+  // Jones arrays: asynchronous global -> shared copies (cp.async) run kJonesDepth - 1 frequencies ahead of the
+  // arithmetic, so the 64 / 128 bytes a thread needs per frequency are in flight without occupying registers.
+  // ring[(stage * nant + ant) * 4 + q][thread]; each thread consumes only what it copied itself.
+  double2* ring;
+  int f0, nfc, nant, nt;
+  bool piped;
 };
+constexpr int kJonesDepth = 3;  // 3 x 2 antennas x 16 KB = 96 KB per block: two blocks still share an SM
+
+__device__ __forceinline__ void jones_prefetch(const EvalParams& p, const JonesPair& jp, int kk, int64_t col) {
+  if (kk < jp.nfc) {
+    const int stage = kk % kJonesDepth;
+    const int64_t jplane = (int64_t)p.nf * p.ld_jones;
+    const int64_t off = (int64_t)(jp.f0 + kk) * p.ld_jones + col;
+    double2* dst = jp.ring + (int64_t)(stage * jp.nant) * 4 * jp.nt + threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) __pipeline_memcpy_async(dst + q * jp.nt, p.jones1 + q * jplane + off, sizeof(double2));
+    if (jp.nant == 2) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) __pipeline_memcpy_async(dst + (4 + q) * jp.nt, p.jones2 + q * jplane + off, sizeof(double2));
+    }
+  }
+  __pipeline_commit();
+}
 
 __device__ __forceinline__ double2 cmul(double2 x, double2 y) {
   return make_double2(x.x * y.x - x.y * y.y, x.x * y.y + x.y * y.x);
@@ -462,7 +486,22 @@ __device__ __forceinline__ void emit(const EvalParams& p, int f, int64_t col, co
     // einsum("ab...,bc...,dc...->ad...", J, C, conj(J)) of tests/test_skymodel.py:1464-1466
     const int64_t plane = (int64_t)p.nf * p.ld_out;
     double2 j1[4], j2[4];
-    if (p.beam_type == RSK_BEAM_JONES) {
+    if (p.beam_type == RSK_BEAM_JONES && jp.piped) {
+      const int k = f - jp.f0;
+      jones_prefetch(p, jp, k + kJonesDepth - 1, col);
+      __pipeline_wait_prior(kJonesDepth - 1);  // the copies of frequency k have landed
+      const double2* src = jp.ring + (int64_t)((k % kJonesDepth) * jp.nant) * 4 * jp.nt + threadIdx.x;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) j1[q] = src[q * jp.nt];
+      if (jp.nant == 2) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) j2[q] = src[(4 + q) * jp.nt];
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) j2[q] = j1[q];
+      }
+    } else if (p.beam_type == RSK_BEAM_JONES) {
+      // (dense subband mode, whose shared memory holds the stored spectra: direct loads)
       // __restrict__: the Jones arrays never alias the output, so the loads of the next (unrolled) frequency may
       // be issued before this one's stores -- more bytes in flight per thread for a kernel that reads 2/3 of its
       // traffic
@@ -601,6 +640,17 @@ k_eval(const __grid_constant__ EvalParams p) {
   }
   // analytic beams: one Jones matrix per column, frequency independent
   JonesPair jp;
+  jp.piped = false;
+  if (EPI == kEpiApparent && p.beam_type == RSK_BEAM_JONES && MODE != RSK_SUBBAND) {
+    jp.ring = reinterpret_cast<double2*>(s_dyn);
+    jp.f0 = f0;
+    jp.nfc = nfc;
+    jp.nant = p.jones2 ? 2 : 1;
+    jp.nt = NT;
+    jp.piped = true;
+#pragma unroll
+    for (int kk = 0; kk < kJonesDepth - 1; ++kk) jones_prefetch(p, jp, kk, col);
+  }
   if (EPI == kEpiApparent && p.beam_type != RSK_BEAM_JONES) {
     double ja[4] = {1.0, 0.0, 0.0, 1.0};  // RSK_BEAM_UNIFORM
     if (p.beam_type == RSK_BEAM_SHORT_DIPOLE) {
@@ -1148,6 +1198,10 @@ int fill_eval_params(const RskSpectrum* spec, const double* freqs, int64_t nf, i
 template <int MODE, int EPI>
 int launch_one(const EvalParams& p, dim3 grid, int smem, cudaStream_t st) {
   constexpr int NT = EvalThreads<MODE>::value;
+  if (EPI == kEpiApparent && p.beam_type == RSK_BEAM_JONES && MODE != RSK_SUBBAND) {
+    const int need = kJonesDepth * (p.jones2 ? 2 : 1) * 4 * NT * (int)sizeof(double2);  // the cp.async ring
+    if (need > smem) smem = need;
+  }
   if (MODE == RSK_SUBBAND && p.y_in_smem) {
     const int need = (int)(4 * p.nf_in * NT * sizeof(double));
     if (need > smem) smem = need;
