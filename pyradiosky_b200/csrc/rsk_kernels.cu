@@ -434,14 +434,16 @@ struct JonesPair {
   // arithmetic, so the 64 / 128 bytes a thread needs per frequency are in flight without occupying registers.
   // ring[(stage * nant + ant) * 4 + q][thread]; each thread consumes only what it copied itself.
   double2* ring;
-  int f0, nfc, nant, nt;
+  int f0, nfc, nant, nt, depth;
   bool piped;
 };
-constexpr int kJonesDepth = 3;  // 3 x 2 antennas x 16 KB = 96 KB per block: two blocks still share an SM
+// ring depth: 96 KB per 256-thread block either way (two blocks still share an SM)
+constexpr int kJonesDepth2 = 3;  // two antennas: 3 stages x 32 KB
+constexpr int kJonesDepth1 = 6;  // one antenna: 6 stages x 16 KB
 
 __device__ __forceinline__ void jones_prefetch(const EvalParams& p, const JonesPair& jp, int kk, int64_t col) {
   if (kk < jp.nfc) {
-    const int stage = kk % kJonesDepth;
+    const int stage = kk % jp.depth;
     const int64_t jplane = (int64_t)p.nf * p.ld_jones;
     const int64_t off = (int64_t)(jp.f0 + kk) * p.ld_jones + col;
     double2* dst = jp.ring + (int64_t)(stage * jp.nant) * 4 * jp.nt + threadIdx.x;
@@ -488,9 +490,10 @@ __device__ __forceinline__ void emit(const EvalParams& p, int f, int64_t col, co
     double2 j1[4], j2[4];
     if (p.beam_type == RSK_BEAM_JONES && jp.piped) {
       const int k = f - jp.f0;
-      jones_prefetch(p, jp, k + kJonesDepth - 1, col);
-      __pipeline_wait_prior(kJonesDepth - 1);  // the copies of frequency k have landed
-      const double2* src = jp.ring + (int64_t)((k % kJonesDepth) * jp.nant) * 4 * jp.nt + threadIdx.x;
+      jones_prefetch(p, jp, k + jp.depth - 1, col);
+      if (jp.nant == 2) __pipeline_wait_prior(kJonesDepth2 - 1);  // the copies of frequency k have landed
+      else __pipeline_wait_prior(kJonesDepth1 - 1);
+      const double2* src = jp.ring + (int64_t)((k % jp.depth) * jp.nant) * 4 * jp.nt + threadIdx.x;
 #pragma unroll
       for (int q = 0; q < 4; ++q) j1[q] = src[q * jp.nt];
       if (jp.nant == 2) {
@@ -646,10 +649,10 @@ k_eval(const __grid_constant__ EvalParams p) {
     jp.f0 = f0;
     jp.nfc = nfc;
     jp.nant = p.jones2 ? 2 : 1;
+    jp.depth = p.jones2 ? kJonesDepth2 : kJonesDepth1;
     jp.nt = NT;
     jp.piped = true;
-#pragma unroll
-    for (int kk = 0; kk < kJonesDepth - 1; ++kk) jones_prefetch(p, jp, kk, col);
+    for (int kk = 0; kk < jp.depth - 1; ++kk) jones_prefetch(p, jp, kk, col);
   }
   if (EPI == kEpiApparent && p.beam_type != RSK_BEAM_JONES) {
     double ja[4] = {1.0, 0.0, 0.0, 1.0};  // RSK_BEAM_UNIFORM
@@ -1199,7 +1202,7 @@ template <int MODE, int EPI>
 int launch_one(const EvalParams& p, dim3 grid, int smem, cudaStream_t st) {
   constexpr int NT = EvalThreads<MODE>::value;
   if (EPI == kEpiApparent && p.beam_type == RSK_BEAM_JONES && MODE != RSK_SUBBAND) {
-    const int need = kJonesDepth * (p.jones2 ? 2 : 1) * 4 * NT * (int)sizeof(double2);  // the cp.async ring
+    const int need = (p.jones2 ? 2 * kJonesDepth2 : kJonesDepth1) * 4 * NT * (int)sizeof(double2);  // the cp.async ring
     if (need > smem) smem = need;
   }
   if (MODE == RSK_SUBBAND && p.y_in_smem) {
