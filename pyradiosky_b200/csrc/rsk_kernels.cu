@@ -1228,7 +1228,7 @@ int launch_one(const EvalParams& p, dim3 grid, int smem, cudaStream_t st) {
     const int need = (int)(4 * p.nf_in * NT * sizeof(double));
     if (need > smem) smem = need;
   }
-  if (smem > 48 * 1024) {
+  if (smem > 40 * 1024) {  // dynamic + the kernel's ~3 KB of static shared memory must stay under the 48 KB default
     const cudaError_t e = cudaFuncSetAttribute(k_eval<MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
   }
