@@ -437,7 +437,6 @@ struct JonesPair {
   int f0, nfc, nant, nt, depth;
   bool piped;
 };
-constexpr int kFullDepth = 6;  // RSK_FULL stored-Stokes ring: 6 channels x 4 x 8 B per thread = 48 KB per block
 // ring depth: 96 KB per 256-thread block either way (two blocks still share an SM)
 constexpr int kJonesDepth2 = 3;  // two antennas: 3 stages x 32 KB
 constexpr int kJonesDepth1 = 6;  // one antenna: 6 stages x 16 KB
@@ -788,27 +787,14 @@ k_eval(const __grid_constant__ EvalParams p) {
       emit<EPI>(p, f0 + k, col, o, jp);
     }
   } else {  // RSK_FULL: stored Stokes, skymodel.py:2165-2181 subset + utils.py:42-57
-    // The four stored values of each channel come through a cp.async ring (8-byte copies, kFullDepth - 1 channels
-    // ahead): this mode reads a third of its traffic and was latency-bound on those loads.
-    double* ring = s_dyn + (jp.piped ? (int64_t)jp.depth * jp.nant * 4 * NT * 2 : 0) + threadIdx.x;
-    auto prefetch = [&](int kk) {
-      if (kk < nfc) {
-        const double* y = p.stokes + (int64_t)s_iv[kk] * p.n + src;
-        double* dst = ring + (int64_t)(kk % kFullDepth) * 4 * NT;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) __pipeline_memcpy_async(dst + q * NT, y + q * sstride, sizeof(double));
-      }
-      __pipeline_commit();
-    };
-    for (int kk = 0; kk < kFullDepth - 1; ++kk) prefetch(kk);
+#pragma unroll 4
     for (int k = 0; k < nfc; ++k) {
-      prefetch(k + kFullDepth - 1);
-      // (with the Jones ring active too, its groups interleave with these: the wait is then stricter than needed,
-      // never weaker)
-      __pipeline_wait_prior(kFullDepth - 1);
-      const double* src_s = ring + (int64_t)(k % kFullDepth) * 4 * NT;
+      // (a cp.async ring for these four 8-byte loads was measured and is slower: 0.93 -> 0.70 on the HEALPix
+      // 'full' map, 0.66 -> 0.53 on the randomly gathered catalogue; 16-byte copies are what that path is good at)
+      const double* y = p.stokes + (int64_t)s_iv[k] * p.n + src;
+      const double y0 = __ldcs(y), y1 = __ldcs(y + sstride), y2 = __ldcs(y + 2 * sstride), y3 = __ldcs(y + 3 * sstride);
       double o[4];
-      xform<EPI>(rot, src_s[0], src_s[NT], src_s[2 * NT], src_s[3 * NT], o);
+      xform<EPI>(rot, y0, y1, y2, y3, o);
       emit<EPI>(p, f0 + k, col, o, jp);
     }
   }
@@ -1221,7 +1207,6 @@ int launch_one(const EvalParams& p, dim3 grid, int smem, cudaStream_t st) {
     int need = 0;
     if (EPI == kEpiApparent && p.beam_type == RSK_BEAM_JONES && MODE != RSK_SUBBAND)
       need += (p.jones2 ? 2 * kJonesDepth2 : kJonesDepth1) * 4 * NT * (int)sizeof(double2);  // the Jones cp.async ring
-    if (MODE == RSK_FULL) need += kFullDepth * 4 * NT * (int)sizeof(double);                  // the stored-Stokes ring
     if (need > smem) smem = need;
   }
   if (MODE == RSK_SUBBAND && p.y_in_smem) {
