@@ -442,11 +442,14 @@ def run_gpu(args):
             if packed == "auto":  # two more untimed steps: the mixed route learns the host's unpack rate as it goes
                 e2e_step(0, False, packed)
                 e2e_step(0, False, packed)
-            barrier()
-            t0 = time.perf_counter()
-            e2e_step(0, False, packed)
-            barrier()
-            trial[packed] = time.perf_counter() - t0
+            best = float("inf")
+            for _ in range(2):  # the hosts of the pool are shared: take the better of two timed trials per route
+                barrier()
+                t0 = time.perf_counter()
+                e2e_step(0, False, packed)
+                barrier()
+                best = min(best, time.perf_counter() - t0)
+            trial[packed] = best
         choice = torch.tensor([trial[r] for r in routes], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(choice, op=dist.ReduceOp.MAX)
@@ -505,7 +508,7 @@ def run_gpu(args):
                             "(2,2,Nf,N_above) complex128 array in host memory; route 'packed' = Hermitian-packed slabs "
                             "(32 B/eval over PCIe) unpacked by host threads, 'plain' = 64 B/eval copied as is, 'mixed' = each slab takes "
                             "whichever of the two finishes earlier given the measured host unpack rate; the fastest "
-                            "of the three (one untimed trial each) is used"} if do_e2e else None),
+                            "of the three (best of two untimed trials each) is used"} if do_e2e else None),
             "gpu_launches": 5 * args.steps,
             "clocks": sampler.summary(),
         }
