@@ -157,6 +157,11 @@ const char* rsk_strerror(int code);
 int rsk_astrom_context(double jd_utc1, double jd_utc2, double dut1, double elong, double phi,
                        double height, double xp, double yp, double* astrom /* HOST [31] */);
 
+/* The same for T times at once (an LST sweep's contexts in one call; Earth-orientation parameters shared):
+ * jd_utc1/jd_utc2 HOST [T] -> astroms HOST [T][31]. */
+int rsk_astrom_contexts(const double* jd_utc1, const double* jd_utc2, int64_t T, double dut1, double elong,
+                        double phi, double height, double xp, double yp, double* astroms);
+
 /* Geodetic WGS84 -> geocentric metres (astropy EarthLocation.geocentric; tutorial.rst:1231-1233). */
 int rsk_geodetic_to_geocentric(double elong, double phi, double height, double* xyz /* HOST [3] */);
 

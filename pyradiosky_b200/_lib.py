@@ -75,6 +75,7 @@ _SIGNATURES = {
     "rsk_version": (ctypes.c_int, []),
     "rsk_strerror": (ctypes.c_char_p, [ctypes.c_int]),
     "rsk_astrom_context": (ctypes.c_int, [ctypes.c_double] * 8 + [c_double_p]),
+    "rsk_astrom_contexts": (ctypes.c_int, [c_double_p, c_double_p, ctypes.c_int64] + [ctypes.c_double] * 6 + [c_double_p]),
     "rsk_geodetic_to_geocentric": (ctypes.c_int, [ctypes.c_double] * 3 + [c_double_p]),
     "rsk_frame_to_icrs": (ctypes.c_int, [ctypes.c_int, ctypes.c_double, c_double_p]),
     "rsk_ravg": (ctypes.c_int, [c_double_p, c_double_p]),

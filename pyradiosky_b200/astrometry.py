@@ -157,6 +157,25 @@ def astrom_context(time, location):
     return np.array(out[:])
 
 
+def astrom_contexts(times, location):
+    """(T, 31) ``eraASTROM`` rows for a sequence of times at one location.
+
+    Package ``Time`` objects that share their Earth-orientation parameters are built in one library call
+    (``rsk_astrom_contexts``); anything else falls back to :func:`astrom_context` per time."""
+    times = list(times)
+    if (times and isinstance(location, EarthLocation) and all(isinstance(t, Time) for t in times)
+            and len({(t.dut1, t.xp, t.yp) for t in times}) == 1):
+        jd1 = np.ascontiguousarray([t.jd1 for t in times], dtype=np.float64)
+        jd2 = np.ascontiguousarray([t.jd2 for t in times], dtype=np.float64)
+        out = np.empty((len(times), _lib.ASTROM_LEN), dtype=np.float64)
+        t0 = times[0]
+        _lib.check("rsk_astrom_contexts", _lib.load().rsk_astrom_contexts(
+            jd1.ctypes.data_as(_lib.c_double_p), jd2.ctypes.data_as(_lib.c_double_p), len(times), t0.dut1,
+            location.lon, location.lat, location.height, t0.xp, t0.yp, out.ctypes.data_as(_lib.c_double_p)))
+        return out
+    return np.stack([astrom_context(t, location) for t in times]) if times else np.empty((0, _lib.ASTROM_LEN))
+
+
 def average_rotation_matrix(astrom):
     """``SkyModel._calc_average_rotation_matrix`` (skymodel.py:2499-2555) for a context: (3, 3)."""
     a = _lib.host_array(np.asarray(astrom, dtype=np.float64).ravel())

@@ -314,6 +314,17 @@ int rsk_astrom_context(double jd_utc1, double jd_utc2, double dut1, double elong
   return RSK_OK;
 }
 
+int rsk_astrom_contexts(const double* jd_utc1, const double* jd_utc2, int64_t T, double dut1, double elong, double phi,
+                        double height, double xp, double yp, double* astroms) {
+  if (T < 0) return RSK_ERR_SIZE;
+  if (T > 0 && (!jd_utc1 || !jd_utc2 || !astroms)) return RSK_ERR_NULL;
+  for (int64_t t = 0; t < T; ++t) {
+    const int rc = rsk_astrom_context(jd_utc1[t], jd_utc2[t], dut1, elong, phi, height, xp, yp, astroms + t * RSK_ASTROM_LEN);
+    if (rc != RSK_OK) return rc;
+  }
+  return RSK_OK;
+}
+
 int rsk_frame_to_icrs(int frame, double equinox_jyear, double* m) {
   if (!m) return RSK_ERR_NULL;
   M3 to_frame;  // ICRS -> frame

@@ -689,7 +689,7 @@ class SkyModel:
             for t in times:
                 if not astrometry.is_time(t):
                     raise ValueError(f"time must be an astropy Time object. value was: {t}")
-            astroms = np.stack([astrometry.astrom_context(t, telescope_location) for t in times])
+            astroms = astrometry.astrom_contexts(times, telescope_location)
         astroms = np.ascontiguousarray(astroms, dtype=np.float64).reshape(-1, _lib.ASTROM_LEN)
         nt, n = astroms.shape[0], self.Ncomponents
         ctx_dev = torch.as_tensor(astrometry.pack_contexts(astroms, self._frame_to_icrs)).to(self.device)

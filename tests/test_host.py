@@ -263,3 +263,19 @@ def test_nan_group_operator_matches_reference_branch(kind, nan_handling):
         assert np.abs(got[ok] - ref[ok]).max() < 1e-13 if ok.any() else True
     with pytest.raises(ValueError, match="nan_handling must be one of"):
         spectral.build_nan_group_operator(x, np.arange(20), kind, "foo")
+
+
+def test_batched_contexts_equal_single_calls(librsk):
+    """rsk_astrom_contexts == rsk_astrom_context per time, bit for bit; mixed inputs fall back per time."""
+    from pyradiosky_b200 import EarthLocation, Time, astrometry
+
+    loc = EarthLocation.from_dms((-30, 43, 17.5), (21, 25, 41.9), 1073.0)
+    t0 = Time(2457082.5, 0.0, dut1=-0.3, xp=1e-7, yp=2e-7)
+    times = [t0 + k * 0.01 for k in range(37)]
+    batch = astrometry.astrom_contexts(times, loc)
+    assert batch.shape == (37, 31)
+    for k in (0, 1, 17, 36):
+        assert np.array_equal(batch[k], astrometry.astrom_context(times[k], loc))
+    mixed = times[:3] + [Time(2457083.5, 0.0, dut1=0.1)]
+    assert np.array_equal(astrometry.astrom_contexts(mixed, loc)[3], astrometry.astrom_context(mixed[3], loc))
+    assert astrometry.astrom_contexts([], loc).shape == (0, 31)

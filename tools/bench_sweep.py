@@ -58,7 +58,7 @@ def main():
     loc = EarthLocation.from_dms((-30, 43, 17.5), (21, 25, 41.9), 1073.0)
     t0 = Time.from_utc("2015-03-01 00:00:00")
     th = time.perf_counter()
-    astroms = np.stack([astrometry.astrom_context(t0 + k * 86.164 / 86400.0, loc) for k in range(nt)])
+    astroms = astrometry.astrom_contexts([t0 + k * 86.164 / 86400.0 for k in range(nt)], loc)
     host_ctx_s = time.perf_counter() - th
     best = 1e30
     kev = []
