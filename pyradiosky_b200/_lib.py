@@ -284,11 +284,16 @@ def check(func, code):
 
 
 def host_array(values, n=None):
-    """ctypes double array from a sequence (or zeros of length n)."""
+    """Pointer to a host double array for a ctypes call (or zeros of length n).
+
+    numpy input is passed without a Python-level copy loop: the returned pointer keeps the (contiguous float64)
+    array alive."""
     if values is None:
         return (ctypes.c_double * n)()
-    vals = [float(v) for v in values]
-    return (ctypes.c_double * len(vals))(*vals)
+    import numpy as np
+
+    arr = np.ascontiguousarray(values, dtype=np.float64)
+    return arr.ctypes.data_as(c_double_p)
 
 
 def ptr(tensor):

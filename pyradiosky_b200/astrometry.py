@@ -148,13 +148,13 @@ def astrom_context(time, location):
         return np.frombuffer(np.ascontiguousarray(rec).tobytes(), dtype=np.float64)[: _lib.ASTROM_LEN].copy()
     if not isinstance(time, Time) or not isinstance(location, EarthLocation):
         raise TypeError("time/location must both be pyradiosky_b200.astrometry (or both astropy) objects")
-    out = (ctypes.c_double * _lib.ASTROM_LEN)()
+    out = np.empty(_lib.ASTROM_LEN, dtype=np.float64)
     _lib.check(
         "rsk_astrom_context",
         _lib.load().rsk_astrom_context(time.jd1, time.jd2, time.dut1, location.lon, location.lat,
-                                       location.height, time.xp, time.yp, out),
+                                       location.height, time.xp, time.yp, out.ctypes.data_as(_lib.c_double_p)),
     )
-    return np.array(out[:])
+    return out
 
 
 def astrom_contexts(times, location):
@@ -179,9 +179,9 @@ def astrom_contexts(times, location):
 def average_rotation_matrix(astrom):
     """``SkyModel._calc_average_rotation_matrix`` (skymodel.py:2499-2555) for a context: (3, 3)."""
     a = _lib.host_array(np.asarray(astrom, dtype=np.float64).ravel())
-    out = (ctypes.c_double * 9)()
-    _lib.check("rsk_ravg", _lib.load().rsk_ravg(a, out))
-    return np.array(out[:]).reshape(3, 3)
+    out = np.empty(9, dtype=np.float64)
+    _lib.check("rsk_ravg", _lib.load().rsk_ravg(a, out.ctypes.data_as(_lib.c_double_p)))
+    return out.reshape(3, 3)
 
 
 _FRAMES = {"icrs": _lib.FRAME_ICRS, "fk5": _lib.FRAME_FK5, "galactic": _lib.FRAME_GALACTIC}
