@@ -113,14 +113,22 @@ class Time:
         return f"Time(jd_utc={self.jd1}+{self.jd2}, dut1={self.dut1}, xp={self.xp}, yp={self.yp})"
 
 
-def _astropy_types():
-    try:
-        from astropy.coordinates import EarthLocation as AEL
-        from astropy.time import Time as ATime
+_ASTROPY_TYPES = None
 
-        return ATime, AEL
-    except ImportError:
-        return None, None
+
+def _astropy_types():
+    """(astropy Time, astropy EarthLocation) or (None, None); resolved once -- a failing import costs ~100 us and
+    this is asked several times per time step."""
+    global _ASTROPY_TYPES
+    if _ASTROPY_TYPES is None:
+        try:
+            from astropy.coordinates import EarthLocation as AEL
+            from astropy.time import Time as ATime
+
+            _ASTROPY_TYPES = (ATime, AEL)
+        except ImportError:
+            _ASTROPY_TYPES = (None, None)
+    return _ASTROPY_TYPES
 
 
 def is_time(obj):
