@@ -41,6 +41,9 @@ extern "C" {
 #define RSK_ASTROM_LEN 31
 /* Length of the device-ready context produced by rsk_pack_context(). */
 #define RSK_CTX_LEN 34
+/* Length of the per-time-step device record of rsk_pack_step() / rsk_positions_step(): packed context, R_avg[9],
+ * one flag (R_avg valid). */
+#define RSK_STEP_LEN 44
 
 /* error codes */
 #define RSK_OK 0
@@ -198,6 +201,18 @@ int rsk_positions(const RskCoords* coords, int64_t n,
                   const double* ravg /* HOST [9] or NULL: with coords->rot, also emit the rotation coefficients */,
                   double* alt_az /* [2][n] */, double* pos_lmn /* [3][n] or NULL */,
                   uint8_t* above /* [n] or NULL */, void* stream);
+
+/* rsk_positions with everything that depends on the time read from DEVICE memory: ``step`` holds the RSK_STEP_LEN
+ * doubles of rsk_pack_step() (packed context, R_avg, flag).  No launch argument changes from one time step to the
+ * next, so positions -> compaction -> coherency can be captured once in a CUDA graph (cudaStreamBeginCapture on the
+ * caller's stream; all entry points only enqueue work) and replayed after copying a new ``step`` record into place.
+ * With coords->rot non-NULL and the flag set, the rotation coefficients are written as by rsk_positions. */
+int rsk_positions_step(const RskCoords* coords, int64_t n, const double* step /* DEVICE [RSK_STEP_LEN] */,
+                       double* alt_az, double* pos_lmn, uint8_t* above, void* stream);
+
+/* HOST: the record above from an eraASTROM (rsk_pack_context + rsk_ravg). */
+int rsk_pack_step(const double* astrom /* HOST [31] */, const double* frame2icrs /* HOST [9] or NULL */,
+                  int with_ravg, double* step /* HOST [RSK_STEP_LEN] */);
 
 /* LST sweep: the same for T contexts in one launch (BASELINE config 5; the loop of
  * tests/test_skymodel.py:2661-2740).  ctx = T packed contexts from rsk_pack_context(), uploaded by

@@ -11,6 +11,6 @@ built ``csrc/librsk.so`` must exist (``__graft_entry__.build()``).  There is no 
 
 from . import astrometry, utils  # noqa: F401
 from .astrometry import EarthLocation, Time  # noqa: F401
-from .skymodel import SkyModel  # noqa: F401
+from .skymodel import SkyModel, StepGraph  # noqa: F401
 
 __version__ = "0.1.0"

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "librsk.so")
 
 ASTROM_LEN = 31
 CTX_LEN = 34
+STEP_LEN = 44
 
 FLAT, SPECTRAL_INDEX, SUBBAND, FULL = 0, 1, 2, 3
 SPECTRAL_MODES = {"flat": FLAT, "spectral_index": SPECTRAL_INDEX, "subband": SUBBAND, "full": FULL}
@@ -87,6 +88,12 @@ _SIGNATURES = {
         [ctypes.POINTER(RskCoords), ctypes.c_int64, c_double_p, c_double_p, c_double_p, ctypes.c_void_p,
          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p],
     ),
+    "rsk_positions_step": (
+        ctypes.c_int,
+        [ctypes.POINTER(RskCoords), ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+         ctypes.c_void_p, ctypes.c_void_p],
+    ),
+    "rsk_pack_step": (ctypes.c_int, [c_double_p, c_double_p, ctypes.c_int, c_double_p]),
     "rsk_positions_sweep": (
         ctypes.c_int,
         [ctypes.POINTER(RskCoords), ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,

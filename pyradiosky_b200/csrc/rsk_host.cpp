@@ -395,6 +395,20 @@ int rsk_pack_context(const double* astrom, const double* frame2icrs, double* ctx
   return RSK_OK;
 }
 
+int rsk_pack_step(const double* astrom, const double* frame2icrs, int with_ravg, double* step) {
+  if (!astrom || !step) return RSK_ERR_NULL;
+  int rc = rsk_pack_context(astrom, frame2icrs, step);
+  if (rc != RSK_OK) return rc;
+  if (with_ravg) {
+    rc = rsk_ravg(astrom, step + RSK_CTX_LEN);
+    if (rc != RSK_OK) return rc;
+  } else {
+    for (int i = 0; i < 9; ++i) step[RSK_CTX_LEN + i] = 0.0;
+  }
+  step[RSK_CTX_LEN + 9] = with_ravg ? 1.0 : 0.0;
+  return RSK_OK;
+}
+
 int rsk_pack_contexts(const double* astroms, int64_t T, const double* frame2icrs, double* ctx) {
   if (T < 0) return RSK_ERR_SIZE;
   if (T > 0 && (!astroms || !ctx)) return RSK_ERR_NULL;

@@ -66,17 +66,14 @@ struct Ravg {
   int valid;
 };
 
-__global__ void __launch_bounds__(kThreads) k_positions(const CoordSrc cs, const int64_t n,
-                                                        const __grid_constant__ RskCtx ctx,
-                                                        const __grid_constant__ Ravg ravg,
-                                                        double* __restrict__ alt_az, double* __restrict__ lmn,
-                                                        uint8_t* __restrict__ above) {
-  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (i >= n) return;
+// The per-component body of K1, shared by the two entry kernels below.
+__device__ __forceinline__ void positions_body(const CoordSrc& cs, const int64_t n, const int64_t i, const RskCtx& ctx,
+                                               const double* ravg_m, const bool have_ravg, double* __restrict__ alt_az,
+                                               double* __restrict__ lmn, uint8_t* __restrict__ above) {
   double sl, cl, sb, cb;
   frame_trig(cs, i, sl, cl, sb, cb);
   const RskAltAz o = rsk_chain(ctx, cl * cb, sl * cb, sb);
-  if (ravg.valid) {
+  if (have_ravg) {
     // Polarisation-rotation coefficients for K2.  sin/cos of alt and az come from the direction cosines
     // (l, m, n) = (sin az cos alt, cos az cos alt, sin alt), so no further trigonometry is needed.
     const double se = o.n;
@@ -84,7 +81,7 @@ __global__ void __launch_bounds__(kThreads) k_positions(const CoordSrc cs, const
     const double cinv = ce > 0.0 ? rsk_div(1.0, ce) : 0.0;
     const double sa = ce > 0.0 ? o.l * cinv : 0.0;
     const double ca = ce > 0.0 ? o.m * cinv : 1.0;
-    const RskRot r = rsk_basis_rotation(ravg.m, sl, cl, sb, cb, sa, ca, se, ce);
+    const RskRot r = rsk_basis_rotation(ravg_m, sl, cl, sb, cb, sa, ca, se, ce);
     cs.rot[i] = r.n2;
     cs.rot[n + i] = r.c2;
     cs.rot[2 * n + i] = r.s2;
@@ -97,6 +94,31 @@ __global__ void __launch_bounds__(kThreads) k_positions(const CoordSrc cs, const
     __stcs(lmn + 2 * n + i, o.n);
   }
   if (above) above[i] = o.alt > 0.0 ? 1 : 0;  // skymodel.py:2479
+}
+
+__global__ void __launch_bounds__(kThreads) k_positions(const CoordSrc cs, const int64_t n,
+                                                        const __grid_constant__ RskCtx ctx,
+                                                        const __grid_constant__ Ravg ravg,
+                                                        double* __restrict__ alt_az, double* __restrict__ lmn,
+                                                        uint8_t* __restrict__ above) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  positions_body(cs, n, i, ctx, ravg.m, ravg.valid != 0, alt_az, lmn, above);
+}
+
+// The same with the context and R_avg read from device memory (RSK_STEP_LEN doubles: packed context, R_avg, flag):
+// the launch then has no time-dependent argument, so a whole time step can be captured in a CUDA graph once and
+// replayed after refreshing that small buffer.
+__global__ void __launch_bounds__(kThreads) k_positions_ctxdev(const CoordSrc cs, const int64_t n,
+                                                               const double* __restrict__ step, double* __restrict__ alt_az,
+                                                               double* __restrict__ lmn, uint8_t* __restrict__ above) {
+  __shared__ double s_step[RSK_STEP_LEN];
+  if (threadIdx.x < RSK_STEP_LEN) s_step[threadIdx.x] = __ldg(step + threadIdx.x);
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  const RskCtx& ctx = *reinterpret_cast<const RskCtx*>(s_step);
+  positions_body(cs, n, i, ctx, s_step + RSK_CTX_LEN, s_step[RSK_CTX_LEN + 9] != 0.0 && cs.rot != nullptr, alt_az, lmn, above);
 }
 
 // minimum resident blocks per SM asked of ptxas for the sweep kernel (register cap); -DRSK_SWEEP_MINB=n to tune
@@ -1265,6 +1287,18 @@ int rsk_positions(const RskCoords* coords, int64_t n, const double* frame2icrs, 
     rv.valid = 1;
   }
   k_positions<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(cs, n, ctx, rv, alt_az, pos_lmn, above);
+  return launch_status();
+}
+
+int rsk_positions_step(const RskCoords* coords, int64_t n, const double* step, double* alt_az, double* pos_lmn,
+                       uint8_t* above, void* stream) {
+  CoordSrc cs;
+  const int rc = check_coords(coords, &cs);
+  if (rc != RSK_OK) return rc;
+  if (!step || !alt_az) return RSK_ERR_NULL;
+  if (n < 0) return RSK_ERR_SIZE;
+  if (n == 0) return RSK_OK;
+  k_positions_ctxdev<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(cs, n, step, alt_az, pos_lmn, above);
   return launch_status();
 }
 

@@ -676,6 +676,22 @@ class SkyModel:
         self._rot_key = (self.alt_az.data_ptr(), self.alt_az._version) if ravg is not None else None
         self.above_horizon = above.view(torch.bool)
 
+    def _positions_from_step(self, step_dev):
+        """update_positions with the time-dependent record (astrometry.pack_step) read from device memory."""
+        n = self.Ncomponents
+        coords = self._coords_struct()
+        if self._n_polarized > 0:
+            coords.rot = self._rot.data_ptr()
+        self._call("rsk_positions_step", ctypes.byref(coords), n, _lib.ptr(step_dev), _lib.ptr(self.alt_az),
+                   _lib.ptr(self.pos_lmn), _lib.ptr(self.above_horizon.view(torch.uint8)))
+
+    def capture_step(self, freqs=None, freq_interp_kind="cubic"):
+        """Capture one whole time step -- positions, horizon compaction, fused ``coherency_calc(freqs)`` -- in a CUDA
+        graph (extension).  Returns a :class:`StepGraph`; ``graph.run(time, telescope_location)`` replays it for a
+        new time with one small host->device copy and one graph launch instead of five kernel launches and their
+        Python set-up, which is what a step costs for small catalogues."""
+        return StepGraph(self, freqs, freq_interp_kind)
+
     def positions_sweep(self, times, telescope_location, astroms=None, want_lmn=False, want_mask=True):
         """Alt/Az of every component at many times in one launch (extension; BASELINE config 5).
 
@@ -1413,3 +1429,76 @@ class SkyModel:
             return
         self._convert(to_jansky=True)
         self.stokes_unit = _JY_UNITS[self.component_type]
+
+
+class StepGraph:
+    """``update_positions`` + horizon compaction + fused ``coherency_calc`` of one :class:`SkyModel` as a CUDA graph.
+
+    Everything that changes from one time step to the next is the 44-double record of ``rsk_pack_step`` (packed
+    astrometry context + R_avg); the graph copies it from a pinned host buffer to the device and the position kernel
+    reads it there (``rsk_positions_step``), so no launch argument ever changes and the captured graph is replayed
+    as is.  The outputs live in fixed buffers: ``sky.alt_az``, ``sky.pos_lmn``, ``sky.above_horizon`` and
+    ``self.out`` (2, 2, Nfreqs, ld) with the number of valid columns in ``self.count`` (CUDA int64), exactly what
+    ``coherency_calc(out=..., sync=False)`` returns.
+    """
+
+    def __init__(self, sky, freqs=None, freq_interp_kind="cubic"):
+        if sky.spectral_type == "subband" and sky._has_nan("stokes"):
+            raise NotImplementedError("capture_step does not handle NaN subband spectra")
+        self.sky = sky
+        self.freqs = None if freqs is None else _to_hz_host(freqs)
+        self.kind = freq_interp_kind
+        dev, n = sky.device, sky.Ncomponents
+        nf = sky.Nfreqs if self.freqs is None else self.freqs.size
+        sky.alt_az = torch.empty((2, n), dtype=torch.float64, device=dev)
+        sky.pos_lmn = torch.empty((3, n), dtype=torch.float64, device=dev)
+        sky.above_horizon = torch.zeros(n, dtype=torch.bool, device=dev)
+        if sky._n_polarized > 0:
+            sky._rot = torch.empty((3, n), dtype=torch.float64, device=dev)
+            sky._rot_key = (sky.alt_az.data_ptr(), sky.alt_az._version)
+        self.ld = max(16, -(-n // 16) * 16)
+        self.out = torch.empty((2, 2, nf, self.ld), dtype=torch.complex128, device=dev)
+        self.step_host = torch.zeros(_lib.STEP_LEN, dtype=torch.float64).pin_memory()
+        self.step_dev = torch.zeros(_lib.STEP_LEN, dtype=torch.float64, device=dev)
+        self._step_np = self.step_host.numpy()
+        self.count = None
+        self._graph = None
+
+    def _pack(self, time, telescope_location, astrom):
+        sky = self.sky
+        if astrom is None:
+            if not astrometry.is_time(time):
+                raise ValueError(f"time must be an astropy Time object. value was: {time}")
+            sky._check_tel_location(telescope_location)
+            astrom = astrometry.astrom_context(time, telescope_location)
+        astrom = np.ascontiguousarray(astrom, dtype=np.float64).ravel()
+        if astrom.size != _lib.ASTROM_LEN:
+            raise ValueError(f"astrom must hold {_lib.ASTROM_LEN} doubles (eraASTROM)")
+        _lib.check("rsk_pack_step", _lib.load().rsk_pack_step(
+            _lib.host_array(astrom), _lib.host_array(sky._frame_to_icrs.ravel()), 1 if sky._n_polarized > 0 else 0,
+            self._step_np.ctypes.data_as(_lib.c_double_p)))
+        sky.time, sky.telescope_location, sky._astrom = time, telescope_location, astrom
+
+    def _body(self):
+        sky = self.sky
+        self.step_dev.copy_(self.step_host, non_blocking=True)
+        sky._positions_from_step(self.step_dev)
+        _, self.count = sky.coherency_calc(freqs=self.freqs, freq_interp_kind=self.kind, out=self.out, ld_out=self.ld,
+                                           sync=False)
+
+    def run(self, time, telescope_location, astrom=None):
+        """One time step.  Returns ``(out, count)``: columns ``[0, count)`` of ``out`` are valid."""
+        self._pack(time, telescope_location, astrom)
+        if self._graph is None:
+            # eager warm-up on a side stream (fills the caches that would otherwise synchronise during capture)
+            side = torch.cuda.Stream(self.sky.device)
+            side.wait_stream(torch.cuda.current_stream(self.sky.device))
+            with torch.cuda.stream(side):
+                self._body()
+            torch.cuda.current_stream(self.sky.device).wait_stream(side)
+            torch.cuda.synchronize(self.sky.device)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._body()
+        self._graph.replay()
+        return self.out, self.count

@@ -1292,3 +1292,37 @@ def test_visibility_errors_and_empty(rsk, site):
         low.visibility_calc(beam="uniform", uvw=[[10.0, 0, 0]])
     v = low.visibility_calc(beam="uniform", uvw=[[10.0, 0, 0]], freqs=[150e6])
     assert v.shape == (1, 2, 2, 1) and float(v.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("spectral_type,frame", [("spectral_index", "fk5"), ("flat", "icrs"), ("subband", "icrs")])
+def test_step_graph_equals_eager_step(rsk, site, spectral_type, frame):
+    """capture_step: a CUDA-graph replay of positions -> compaction -> coherency gives, bit for bit, what
+    update_positions + coherency_calc(freqs) give, for a sequence of times."""
+    time, loc = site
+    rng = np.random.default_rng(77)
+    n, nf = 5003, 19
+    freqs = np.linspace(100e6, 160e6, nf)
+    sky = make_model(rsk, rng, spectral_type, n, frame=frame, nf_in=12)
+    ref = sky.copy()
+    graph = sky.capture_step(freqs=freqs)
+    for k in range(5):
+        t = time + 0.01 * k
+        out, count = graph.run(t, loc)
+        ref.update_positions(t, loc)
+        want = ref.coherency_calc(freqs=freqs, pad=False)
+        c = int(count.item())
+        assert c == want.shape[-1]
+        assert torch.equal(out[..., :c], want)
+        assert torch.equal(sky.alt_az, ref.alt_az) and torch.equal(sky.pos_lmn, ref.pos_lmn)
+        assert torch.equal(sky.above_horizon, ref.above_horizon)
+    # an unpolarised model (no rotation coefficients) and the stored-Stokes path
+    un = np.zeros((4, 3, 700)); un[0] = rng.uniform(1, 2, size=(3, 700))
+    lon, lat = random_sky(rng, 700)
+    s2 = rsk.SkyModel(ra=lon, dec=lat, stokes=un, spectral_type="full", freq_array=[1e8, 1.1e8, 1.2e8])
+    r2 = s2.copy()
+    g2 = s2.capture_step()
+    for k in range(3):
+        out, count = g2.run(time + 0.02 * k, loc)
+        r2.update_positions(time + 0.02 * k, loc)
+        want = r2.coherency_calc(pad=False)
+        assert torch.equal(out[..., : int(count.item())], want)
