@@ -1302,7 +1302,7 @@ def test_step_graph_equals_eager_step(rsk, site, spectral_type, frame):
     rng = np.random.default_rng(77)
     n, nf = 5003, 19
     freqs = np.linspace(100e6, 160e6, nf)
-    sky = make_model(rsk, rng, spectral_type, n, frame=frame, nf_in=12)
+    sky = make_model(rsk, rng, spectral_type, n, frame=frame, nf_in=12)[0]
     ref = sky.copy()
     graph = sky.capture_step(freqs=freqs)
     for k in range(5):
