@@ -448,7 +448,7 @@ def run_gpu(args):
             view = s.coherency_calc_to_host(freqs, host_out, slab=e2e_slab, packed=packed, nthreads=e2e_threads)
             if record:
                 e2e_evals += view.shape[2] * view.shape[3]
-                if packed == "auto":
+                if packed == "auto" or isinstance(packed, float):
                     npk, npl = s._e2e_route_counts
                     d2h_bytes += view.shape[2] * view.shape[3] * (32 * npk + 64 * npl) / max(1, npk + npl)
                 else:
@@ -456,7 +456,9 @@ def run_gpu(args):
             return view
 
         trial = {}
-        routes = ("auto", True, False)
+        routes = ("auto", True, False)  # fixed packed shares 0.5 .. 0.875 measured: never ahead of these three
+        if os.environ.get("RSK_E2E_SHARES"):
+            routes += tuple(float(x) for x in os.environ["RSK_E2E_SHARES"].split(","))
         for packed in routes:
             e2e_step(0, False, packed)
             if packed == "auto":  # two more untimed steps: the mixed route learns the host's unpack rate as it goes
@@ -474,8 +476,12 @@ def run_gpu(args):
         if world > 1:
             dist.all_reduce(choice, op=dist.ReduceOp.MAX)
         use_packed = routes[int(torch.argmin(choice).item())]
-        e2e_route = {"auto": "mixed", True: "packed", False: "plain"}[use_packed]
-        e2e_trials = {{"auto": "mixed", True: "packed", False: "plain"}[r]: float(c) * 1e3 for r, c in zip(routes, choice.cpu())}
+
+        def label(r):
+            return f"packed_share_{r}" if isinstance(r, float) else {"auto": "mixed", True: "packed", False: "plain"}[r]
+
+        e2e_route = label(use_packed)
+        e2e_trials = {label(r): float(c) * 1e3 for r, c in zip(routes, choice.cpu())}
         barrier()
         t0 = time.perf_counter()
         for k in range(e2e_steps):
@@ -531,8 +537,9 @@ def run_gpu(args):
                      "how": "pinned host inputs -> H2D -> SkyModel -> update_positions -> coherency_calc_to_host into the "
                             "(2,2,Nf,N_above) complex128 array in host memory; route 'packed' = Hermitian-packed slabs "
                             "(32 B/eval over PCIe) unpacked by host threads, 'plain' = 64 B/eval copied as is, 'mixed' = each slab takes "
-                            "whichever of the two finishes earlier given the measured host unpack rate; the fastest "
-                            "of the three (best of two untimed trials each) is used"} if do_e2e else None),
+                            "whichever of the two finishes earlier given the measured host unpack rate, 'packed_share_x' = "
+                            "a fixed share x of the slabs packed; the fastest of these (best of two untimed trials "
+                            "each) is used"} if do_e2e else None),
             "gpu_launches": 5 * args.steps,
             "clocks": sampler.summary(),
         }

@@ -444,9 +444,10 @@ int rsk_ravg(const double* astrom, double* ravg) {
 }
 
 // Host-side unpack of the Hermitian-packed transfer format (see rsk.h): pure data movement, split over
-// threads by frequency row, non-temporal stores so the output does not pass through the caches.  The expansion is
-// bound by how fast a core retires non-temporal stores; with AVX-512 a whole 64-byte line leaves per store
-// (measured ~1.5x the 16-byte SSE2 form per core), chosen at run time.
+// threads by frequency row, non-temporal stores so the output does not pass through the caches.  With AVX-512
+// (chosen at run time) a whole 64-byte line leaves per store: measured 1.2x the 16-byte SSE2 form on one core,
+// and no change with 8+ threads, where the expansion is bound by the host's memory system, not the store width
+// (profiles/r01_summary.md).
 }  // extern "C"
 
 namespace {

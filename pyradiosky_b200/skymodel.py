@@ -1044,6 +1044,9 @@ class SkyModel:
         ``packed=False``: the full complex array is copied; ``host_out`` must be a flat *pinned* complex128
         tensor, and the call returns after the last copy has been queued (synchronise before reading).
 
+        ``packed=x`` with 0 < x < 1 (``host_out`` pinned): that share of the slabs goes packed, the rest plain,
+        evenly interleaved (for tuning: the best share balances host memory traffic against PCIe time).
+
         ``packed="auto"`` (``host_out`` pinned): every slab takes whichever of the two routes finishes earlier
         under a two-resource model -- the PCIe link (32 or 64 bytes per evaluation) and the host threads that
         expand packed slabs -- so a slow or busy host is not the bottleneck and a fast one still halves the
@@ -1101,9 +1104,10 @@ class SkyModel:
         import os
         import time as _time
 
-        auto = packed == "auto"
+        ratio = float(packed) if isinstance(packed, float) and 0.0 < packed < 1.0 else None
+        auto = packed == "auto" or ratio is not None
         if auto and not host_out.is_pinned():
-            auto = False  # plain slabs need a DMA-able destination
+            auto, ratio = False, None  # plain slabs need a DMA-able destination
         if nthreads is None:
             nthreads = max(1, min(32, (3 * (os.cpu_count() or 1)) // 4))  # leave cores for the DMA / main thread
         ld = -(-n_above // 32) * 32  # 256-byte aligned rows of doubles
@@ -1176,6 +1180,8 @@ class SkyModel:
                 # ... nor when its unpack would end after everything left could have been shipped in full
                 late = max(th, arrive) + ev_n * h_eval > tp + 64.0 * (nf - f0) * n_above / rate
                 use_plain = backlog >= ev_n * h_eval or late
+                if ratio is not None:  # fixed share of packed slabs, evenly interleaved
+                    use_plain = (n_packed + n_plain + 1) * (1.0 - ratio) - n_plain >= 1.0 - 1e-9
             if use_plain:
                 k = kc % 2
                 kc += 1

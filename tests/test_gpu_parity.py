@@ -880,6 +880,12 @@ def test_coherency_to_host_packed_and_plain(rsk, site, spectral_type):
             assert npl == 0
         if h == 1e-6:
             assert npl > npk
+    for share in (0.25, 0.5, 0.75):  # a fixed share of packed slabs, evenly interleaved
+        pinned.fill_(float("nan"))
+        got6 = sky.coherency_calc_to_host(freqs, pinned, slab=8, packed=share, nthreads=2)
+        assert torch.equal(got6, dev), share
+        npk, npl = sky._e2e_route_counts
+        assert npk + npl == -(-freqs.size // 8) and abs(npk - share * (npk + npl)) <= 1, (share, npk, npl)
     # an unpinned destination silently falls back to the packed route
     got5 = sky.coherency_calc_to_host(freqs, host, slab=16, packed="auto")
     assert torch.equal(got5, dev)
