@@ -26,18 +26,20 @@
 
 // Device-ready astrometry context (RSK_CTX_LEN doubles): eraASTROM with the orthogonal steps between
 // aberration and the latitude rotation pre-multiplied on the host.
+// The first 18 doubles are everything a folded context (see rsk_ctx_folded) needs per evaluation: nine aligned
+// 16-byte shared-memory loads in the sweep kernel.
 struct RskCtx {
   double eh[3];   // Sun -> observer unit vector
-  double em;      // Sun-observer distance, au
+  double w2;      // SRS / em
   double v[3];    // observer barycentric velocity / c
   double bm1;     // sqrt(1 - |v|^2)
   double a1[9];   // polar-motion(xpl, ypl) . Rz(eral) . bpn : GCRS proper direction -> (-HA, Dec) frame
+  double inv1pbm1; // 1 / (1 + bm1)
   double sphi, cphi;
   double diurab;
   double refa, refb;
-  double w2;      // SRS / em
+  double em;      // Sun-observer distance, au
   double m_ident; // != 0: frame matrix is the identity, skip it
-  double inv1pbm1; // 1 / (1 + bm1)
   double m[9];    // catalogue frame -> ICRS
 };
 static_assert(sizeof(RskCtx) == 34 * sizeof(double), "RskCtx layout");
@@ -59,7 +61,7 @@ static_assert(sizeof(RskCtx) == 34 * sizeof(double), "RskCtx layout");
 // tools/gen_atan_poly.py: max error of the double-precision Horner evaluation 1.4e-17).  The previous form, a degree-19 polynomial on
 // [0, 1], spent twice the fp64 issue slots; the LST sweep is bound by that pipe (profiles/r01_summary.md).
 #if defined(__CUDACC__)
-__device__ const double2 kRskAtanTab[9] = {  // (atan(k/8), k/8)
+__device__ const double2 kRskAtanTab[16] = {  // (atan(k/8), k/8)
     {0x0.0p+0, 0x0.0p+0},
     {0x1.fd5ba9aac2f6ep-4, 0x1.0000000000000p-3},
     {0x1.f5b75f92c80ddp-3, 0x1.0000000000000p-2},
@@ -68,7 +70,32 @@ __device__ const double2 kRskAtanTab[9] = {  // (atan(k/8), k/8)
     {0x1.1e00babdefeb4p-1, 0x1.4000000000000p-1},
     {0x1.4978fa3269ee1p-1, 0x1.8000000000000p-1},
     {0x1.700a7c5784634p-1, 0x1.c000000000000p-1},
-    {0x1.921fb54442d18p-1, 0x1.0000000000000p+0}};
+    {0x1.921fb54442d18p-1, 0x1.0000000000000p+0},
+    {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};  // (padding: the index is not clamped)
+// Azimuth table: entry [octant][k] = (B, +-k/8) with the octant = 4 (y < 0) + 2 (x < 0) + (|y| > |x|), so that
+// atan2(y, x) mod 2 pi = B + sign * atan(u): every reflection of the arctangent (swap, x < 0, y < 0, the wrap of
+// negative angles by eraAnp) is in B and in the sign, which rides on the second member (-0.0 for k = 0).
+__device__ const double2 kRskAzTab[80] = {
+    {0x0.0p+0, 0x0.0p+0}, {0x1.fd5ba9aac2f6ep-4, 0x1.0000000000000p-3}, {0x1.f5b75f92c80ddp-3, 0x1.0000000000000p-2}, {0x1.6f61941e4def1p-2, 0x1.8000000000000p-2}, {0x1.dac670561bb4fp-2, 0x1.0000000000000p-1},
+    {0x1.1e00babdefeb4p-1, 0x1.4000000000000p-1}, {0x1.4978fa3269ee1p-1, 0x1.8000000000000p-1}, {0x1.700a7c5784634p-1, 0x1.c000000000000p-1}, {0x1.921fb54442d18p-1, 0x1.0000000000000p+0},  // octant 0
+    {0x1.921fb54442d18p+0, -0x0.0p+0}, {0x1.7249faa996a21p+0, -0x1.0000000000000p-3}, {0x1.5368c951e9cfdp+0, -0x1.0000000000000p-2}, {0x1.3647503caf55cp+0, -0x1.8000000000000p-2}, {0x1.1b6e192ebbe44p+0, -0x1.0000000000000p-1},
+    {0x1.031f57e54adbep+0, -0x1.4000000000000p-1}, {0x1.dac670561bb4fp-1, -0x1.8000000000000p-1}, {0x1.b434ee31013fdp-1, -0x1.c000000000000p-1}, {0x1.921fb54442d18p-1, -0x1.0000000000000p+0},  // octant 1
+    {0x1.921fb54442d18p+1, -0x0.0p+0}, {0x1.8234d7f6ecb9dp+1, -0x1.0000000000000p-3}, {0x1.72c43f4b1650ap+1, -0x1.0000000000000p-2}, {0x1.643382c07913ap+1, -0x1.8000000000000p-2}, {0x1.56c6e7397f5aep+1, -0x1.0000000000000p-1},
+    {0x1.4a9f8694c6d6bp+1, -0x1.4000000000000p-1}, {0x1.3fc176b7a8560p+1, -0x1.8000000000000p-1}, {0x1.361d162e61b8bp+1, -0x1.c000000000000p-1}, {0x1.2d97c7f3321d2p+1, -0x1.0000000000000p+0},  // octant 2
+    {0x1.921fb54442d18p+0, 0x0.0p+0}, {0x1.b1f56fdeef00fp+0, 0x1.0000000000000p-3}, {0x1.d0d6a1369bd34p+0, 0x1.0000000000000p-2}, {0x1.edf81a4bd64d4p+0, 0x1.8000000000000p-2}, {0x1.0468a8ace4df6p+1, 0x1.0000000000000p-1},
+    {0x1.109009519d639p+1, 0x1.4000000000000p-1}, {0x1.1b6e192ebbe44p+1, 0x1.8000000000000p-1}, {0x1.251279b802819p+1, 0x1.c000000000000p-1}, {0x1.2d97c7f3321d2p+1, 0x1.0000000000000p+0},  // octant 3
+    {0x1.921fb54442d18p+2, -0x0.0p+0}, {0x1.8a2a469d97c5bp+2, -0x1.0000000000000p-3}, {0x1.8271fa47ac911p+2, -0x1.0000000000000p-2}, {0x1.7b299c025df29p+2, -0x1.8000000000000p-2}, {0x1.74734e3ee1163p+2, -0x1.0000000000000p-1},
+    {0x1.6e5f9dec84d42p+2, -0x1.4000000000000p-1}, {0x1.68f095fdf593cp+2, -0x1.8000000000000p-1}, {0x1.641e65b952452p+2, -0x1.c000000000000p-1}, {0x1.5fdbbe9bba775p+2, -0x1.0000000000000p+0},  // octant 4
+    {0x1.2d97c7f3321d2p+2, 0x0.0p+0}, {0x1.358d3699dd290p+2, 0x1.0000000000000p-3}, {0x1.3d4582efc85d9p+2, 0x1.0000000000000p-2}, {0x1.448de13516fc1p+2, 0x1.8000000000000p-2}, {0x1.4b442ef893d87p+2, 0x1.0000000000000p-1},
+    {0x1.5157df4af01a9p+2, 0x1.4000000000000p-1}, {0x1.56c6e7397f5aep+2, 0x1.8000000000000p-1}, {0x1.5b99177e22a99p+2, 0x1.c000000000000p-1}, {0x1.5fdbbe9bba775p+2, 0x1.0000000000000p+0},  // octant 5
+    {0x1.921fb54442d18p+1, 0x0.0p+0}, {0x1.a20a929198e94p+1, 0x1.0000000000000p-3}, {0x1.b17b2b3d6f526p+1, 0x1.0000000000000p-2}, {0x1.c00be7c80c8f6p+1, 0x1.8000000000000p-2}, {0x1.cd78834f06482p+1, 0x1.0000000000000p-1},
+    {0x1.d99fe3f3becc5p+1, 0x1.4000000000000p-1}, {0x1.e47df3d0dd4d1p+1, 0x1.8000000000000p-1}, {0x1.ee22545a23ea5p+1, 0x1.c000000000000p-1}, {0x1.f6a7a2955385ep+1, 0x1.0000000000000p+0},  // octant 6
+    {0x1.2d97c7f3321d2p+2, -0x0.0p+0}, {0x1.25a2594c87114p+2, -0x1.0000000000000p-3}, {0x1.1dea0cf69bdcbp+2, -0x1.0000000000000p-2}, {0x1.16a1aeb14d3e3p+2, -0x1.8000000000000p-2}, {0x1.0feb60edd061dp+2, -0x1.0000000000000p-1},
+    {0x1.09d7b09b741fcp+2, -0x1.4000000000000p-1}, {0x1.0468a8ace4df6p+2, -0x1.8000000000000p-1}, {0x1.ff2cf0d083217p+1, -0x1.c000000000000p-1}, {0x1.f6a7a2955385ep+1, -0x1.0000000000000p+0},  // octant 7
+    {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};
+// 64-bit literals the chain needs: operands straight from the constant bank (a literal in the code costs two
+// UMOV per use inside the sweep loop)
+__constant__ double kRskC[4] = {1e-6, 1e-300, RSK_HALFPI, RSK_DPI};
 // atan(u) = u + u s Q(s), s = u^2, |u| <= 0.08 (degree 4: 1.4e-17 maximum error)
 __constant__ double kRskAtanQ[5] = {-0x1.5555555555539p-2, 0x1.999999992c40dp-3, -0x1.2492470e5748ap-3,
                                     0x1.c7154d717ee6ap-4, -0x1.6f5e1489511f6p-4};
@@ -107,7 +134,7 @@ RSK_HD double rsk_rsqrt(double x) {
 RSK_HD double rsk_sqrt(double x) {
 #if defined(__CUDA_ARCH__)
   double r;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x + 1e-300));  // x = 0 -> 0 (the bias matters below 1e-284)
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x + kRskC[1]));  // x = 0 -> 0 (the bias matters below 1e-284)
   double g = x * r, h = 0.5 * r;
   const double e = fma(-h, g, 0.5);
   g = fma(g, e, g);
@@ -132,8 +159,9 @@ RSK_HD double rsk_atan2_t(double y, double x) {
   // a direction closer than that to the pole of the angle, where k = 0 still gives a finite, if inexact, value.
   float fr;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(fr) : "f"((float)mx));
-  int k = __float2int_rn(8.0f * ((float)mn * fr));
-  k = min(max(k, 0), 8);
+  // not clamped: mn <= mx survives the rounding to float and the reciprocal is good to an ulp, so the quotient
+  // is at most 1 + 2^-22 and k <= 8; NaN (0 * inf) converts to 0
+  const int k = __float2int_rn(8.0f * ((float)mn * fr));
   const double2 tab = __ldg(&kRskAtanTab[k]);
   const double num = fma(-tab.y, mx, mn);
   const double den = fma(tab.y, mn, mx);
@@ -149,9 +177,9 @@ RSK_HD double rsk_atan2_t(double y, double x) {
   p = fma(p, s, kRskAtanQ[1]);
   p = fma(p, s, kRskAtanQ[0]);
   double a = tab.x + fma(u * s, p, u);
-  a = sw ? RSK_HALFPI - a : a;
+  a = sw ? kRskC[2] - a : a;
   if (!XPOS) {
-    a = x < 0.0 ? RSK_DPI - a : a;
+    a = x < 0.0 ? kRskC[3] - a : a;
     a = mx > 0.0 ? a : 0.0;  // atan2(0, 0) = 0 (eraAtioq's own convention for the azimuth at the zenith)
   }
   return copysign(a, y);
@@ -161,6 +189,47 @@ RSK_HD double rsk_atan2_t(double y, double x) {
 }
 
 RSK_HD double rsk_atan2(double y, double x) { return rsk_atan2_t<false>(y, x); }
+
+// eraAnp(atan2(y, x)), 0 for y = x = 0: the azimuth of eraAtioq in [0, 2 pi] in one go.  Same reduction as
+// rsk_atan2_t, but the octant picks (B, sign) from kRskAzTab, so the reflections and the wrap cost one table load, one
+// sign flip and the final addition instead of three compares, three subtractions and four 64-bit selects.
+// (Like eraAnp, an angle within an ulp below zero comes back as 2 pi itself.)
+RSK_HD double rsk_azimuth(double y, double x) {
+#if defined(__CUDA_ARCH__)
+  const bool sw = fabs(y) > fabs(x);
+  const double mn = fabs(sw ? x : y);
+  double mx = fabs(sw ? y : x);
+  const float fmx = (float)mx;
+  float fr;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(fr) : "f"(fmx));
+  const int k = __float2int_rn(8.0f * ((float)mn * fr));  // <= 8 and 0 for NaN, see rsk_atan2_t
+  int oct = (int)((unsigned)__double2hiint(y) >> 31) * 4 + (int)((unsigned)__double2hiint(x) >> 31) * 2 + (sw ? 1 : 0);
+  oct = fmx == 0.0f ? 0 : oct;  // the zenith itself: azimuth 0 whatever the signs of the zeros
+  const double2 tab = __ldg(&kRskAzTab[oct * 9 + k]);
+  // keeps the quotient below finite (0) at the zenith: the smallest normal number instead of 0
+  mx = __hiloint2double(max(__double2hiint(mx), 0x00100000), __double2loint(mx));
+  const double t = fabs(tab.y);
+  const double num = fma(-t, mx, mn);
+  const double den = fma(t, mn, mx);
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+  const double e = fma(-den, r, 1.0);
+  r = fma(r, fma(e, e, e), r);
+  const double u = num * r;
+  const double s = u * u;
+  double p = kRskAtanQ[4];
+  p = fma(p, s, kRskAtanQ[3]);
+  p = fma(p, s, kRskAtanQ[2]);
+  p = fma(p, s, kRskAtanQ[1]);
+  p = fma(p, s, kRskAtanQ[0]);
+  const double w = fma(u * s, p, u);
+  const double ws = __hiloint2double(__double2hiint(w) ^ (__double2hiint(tab.y) & 0x80000000), __double2loint(w));
+  return tab.x + ws;
+#else
+  const double a = (y != 0.0 || x != 0.0) ? atan2(y, x) : 0.0;
+  return a < 0.0 ? a + RSK_D2PI : a;
+#endif
+}
 
 // sin and cos of an angle of catalogue size (|x| <= 16: longitudes, latitudes, HEALPix azimuths): two-term
 // Cody-Waite reduction by pi/2 (exact for |k| <= 10) and the fdlibm kernel polynomials on [-pi/4, pi/4]
@@ -218,7 +287,9 @@ RSK_HD bool rsk_ctx_folded(const RskCtx& c) {
 // WANT_LMN = false skips the direction cosines (the LST-sweep kernel does not always need them).
 // FOLD: 0 = look at the context, 1 = the caller has checked rsk_ctx_folded(c) already (the sweep kernel does it
 // once per block, outside its time loop).
-template <bool WANT_LMN, bool FRAME_DONE = false, int FOLD = 0>
+// UNIT: (with FRAME_DONE) the caller's vector is of unit length to rounding, so p.p is taken as 1 in the light
+// deflection (a relative change of 1e-16 in a term below 3e-5 rad).
+template <bool WANT_LMN, bool FRAME_DONE = false, int FOLD = 0, bool UNIT = false>
 RSK_HD RskAltAz rsk_chain_t(const RskCtx& c, double px, double py, double pz, double pp_in = -1.0) {
   if (!FRAME_DONE && c.m_ident == 0.0) {
     const double x = c.m[0] * px + c.m[1] * py + c.m[2] * pz;
@@ -231,11 +302,11 @@ RSK_HD RskAltAz rsk_chain_t(const RskCtx& c, double px, double py, double pz, do
   // e (p.p) - p (p.e), and q.(q+e) = p.p + p.e.  The deflection is below 1e-5 rad, so a quotient good to
   // 2^-40 (reciprocal seed + one Newton step) leaves an error below 1e-17 rad.
   // p.p: time independent, so callers that loop over contexts pass it in (pp_in >= 0)
-  const double pp = (FRAME_DONE && pp_in >= 0.0) ? pp_in : px * px + py * py + pz * pz;
+  const double pp = (FRAME_DONE && UNIT) ? 1.0 : (FRAME_DONE && pp_in >= 0.0) ? pp_in : px * px + py * py + pz * pz;
   const double pe = px * c.eh[0] + py * c.eh[1] + pz * c.eh[2];
 #if defined(__CUDA_ARCH__)
   double den = pp + pe;
-  den = den < 1e-6 ? 1e-6 : den;
+  den = den < kRskC[0] ? kRskC[0] : den;
   double rd;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rd) : "d"(den));
   rd = fma(fma(-den, rd, 1.0), rd, rd);
@@ -243,9 +314,16 @@ RSK_HD RskAltAz rsk_chain_t(const RskCtx& c, double px, double py, double pz, do
 #else
   const double w = c.w2 / fmax(pp + pe, 1e-6);
 #endif
-  const double nx = px + w * (c.eh[0] * pp - px * pe);
-  const double ny = py + w * (c.eh[1] * pp - py * pe);
-  const double nz = pz + w * (c.eh[2] * pp - pz * pe);
+  double nx, ny, nz;
+  if (FRAME_DONE && UNIT) {
+    nx = fma(w, fma(-px, pe, c.eh[0]), px);
+    ny = fma(w, fma(-py, pe, c.eh[1]), py);
+    nz = fma(w, fma(-pz, pe, c.eh[2]), pz);
+  } else {
+    nx = px + w * (c.eh[0] * pp - px * pe);
+    ny = py + w * (c.eh[1] * pp - py * pe);
+    nz = pz + w * (c.eh[2] * pp - pz * pe);
+  }
   // eraAb(pnat, v, s=em, bm1): annual (+ observer) aberration
   // p' = pnat bm1 + w1 v + w2 (v - (pnat.v) pnat), grouped as pnat (bm1 - w2 pnat.v) + v (w1 + w2)
   const double pdv = nx * c.v[0] + ny * c.v[1] + nz * c.v[2];
@@ -259,20 +337,21 @@ RSK_HD RskAltAz rsk_chain_t(const RskCtx& c, double px, double py, double pz, do
     // No diurnal aberration, no refraction: everything after the aberration is one rotation (a1 holds
     // latitude . polar motion . Earth rotation . bpn) and both angles are ratios of its components, so the
     // normalisation of eraAb is not needed for them.
-    const double xaeo = c.a1[0] * ax + c.a1[1] * ay + c.a1[2] * az_;
+    // (the north component: -x of the (-HA, Dec) -> Az/El step, negated term by term so that no fp64 instruction
+    // is spent on the sign)
+    const double xn = (-c.a1[0]) * ax - c.a1[1] * ay - c.a1[2] * az_;
     const double yaeo = c.a1[3] * ax + c.a1[4] * ay + c.a1[5] * az_;
     const double zaeo = c.a1[6] * ax + c.a1[7] * ay + c.a1[8] * az_;
-    const double azobs = rsk_atan2(yaeo, -xaeo);  // 0 at the zenith, as eraAtioq
-    const double r2 = xaeo * xaeo + yaeo * yaeo;
+    o.az = rsk_azimuth(yaeo, xn);  // eraAtioq + eraAnp: [0, 2 pi], 0 at the zenith
+    const double r2 = xn * xn + yaeo * yaeo;
     const double rxy = rsk_sqrt(r2);
     // astropy forms pi/2 - zd with zd = atan2(rxy, z); atan2(z, rxy) is the same angle (to an ulp of pi/2)
     // without the two reflections
     o.alt = rsk_atan2_t<true>(zaeo, rxy);
-    o.az = azobs < 0.0 ? azobs + RSK_D2PI : azobs;
     if (WANT_LMN) {
       const double ninv = rsk_rsqrt(r2 + zaeo * zaeo);
       o.l = yaeo * ninv;
-      o.m = -xaeo * ninv;
+      o.m = xn * ninv;
       o.n = zaeo * ninv;
     } else {
       o.l = o.m = o.n = 0.0;

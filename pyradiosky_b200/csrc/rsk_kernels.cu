@@ -29,7 +29,10 @@ constexpr int kDefaultTileFast = 0;
 constexpr int kDefaultOccSmem = 0;  // > 0: dynamic smem request that caps resident blocks per SM
 constexpr int kCompactItems = 8;    // mask bytes per thread in the compaction kernels
 constexpr int kCompactTile = kThreads * kCompactItems;  // 2048, see rsk_workspace_bytes
-constexpr int kSweepTimes = 16;     // time steps per block in the sweep kernel
+#ifndef RSK_SWEEP_TIMES
+#define RSK_SWEEP_TIMES 64
+#endif
+constexpr int kSweepTimes = RSK_SWEEP_TIMES;  // time steps per block in the sweep kernel
 constexpr int kSubbandBanded = 4;   // internal mode: RSK_SUBBAND evaluated from precomputed spline coefficients
 
 struct CoordSrc {
@@ -132,14 +135,12 @@ template <int CPT, bool WANT_LMN, int FOLD, bool MASK>
 __device__ __forceinline__ void sweep_times(const RskCtx* s_ctx, const int ntc, const int64_t n, const int64_t* idx,
                                             const double* px, const double* py, const double* pz, double** pa,
                                             double** pl, uint8_t** pm) {
-  double pp[CPT];
-#pragma unroll
-  for (int j = 0; j < CPT; ++j) pp[j] = px[j] * px[j] + py[j] * py[j] + pz[j] * pz[j];
 #pragma unroll 2
   for (int k = 0; k < ntc; ++k) {
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
-      const RskAltAz o = rsk_chain_t<WANT_LMN, true, FOLD>(s_ctx[k], px[j], py[j], pz[j], pp[j]);
+      // (px, py, pz) is a product of sines and cosines, rotated by an orthogonal matrix at most: unit length
+      const RskAltAz o = rsk_chain_t<WANT_LMN, true, FOLD, true>(s_ctx[k], px[j], py[j], pz[j]);
       if (CPT == 1 || idx[j] < n) {
         __stcs(pa[j], o.alt);
         __stcs(pa[j] + n, o.az);
@@ -148,7 +149,8 @@ __device__ __forceinline__ void sweep_times(const RskCtx* s_ctx, const int ntc, 
           __stcs(pl[j] + n, o.m);
           __stcs(pl[j] + 2 * n, o.n);
         }
-        if (MASK) *pm[j] = o.alt > 0.0 ? 1 : 0;
+        // alt > 0 read off the high word (alt is never a positive denormal): an integer compare, not an fp64 one
+        if (MASK) *pm[j] = __double2hiint(o.alt) > 0 ? 1 : 0;
       }
       pa[j] += 2 * n;
       if (WANT_LMN) pl[j] += 3 * n;
@@ -206,10 +208,12 @@ __global__ void __launch_bounds__(kThreads, RSK_SWEEP_MINB) k_positions_sweep(co
     pm[j] = above ? above + t0 * n + idx[j] : nullptr;
   }
   // every context of this block folded (the case for contexts built for the reference's AltAz frame)?  Decided
-  // once here, so the time loop carries no per-step test.
-  bool folded = true;
-  for (int k = 0; k < ntc; ++k) folded = folded && rsk_ctx_folded(s_ctx[k]);
-  if (CPT == 1 && idx[0] >= n) return;  // (after the only barrier of the kernel)
+  // once here, one context per thread and a block-wide vote, so neither the time loop nor each thread's prologue
+  // carries a per-step test (as a per-thread loop over the contexts it was a tenth of the kernel's instructions).
+  bool mine = true;
+  for (int k = threadIdx.x; k < ntc; k += kThreads) mine = mine && rsk_ctx_folded(s_ctx[k]);
+  const bool folded = __syncthreads_and(mine) != 0;
+  if (CPT == 1 && idx[0] >= n) return;  // (after the last barrier of the kernel)
   if (above) {
     if (folded) sweep_times<CPT, WANT_LMN, 1, true>(s_ctx, ntc, n, idx, px, py, pz, pa, pl, pm);
     else sweep_times<CPT, WANT_LMN, 0, true>(s_ctx, ntc, n, idx, px, py, pz, pa, pl, pm);

@@ -154,6 +154,36 @@ def test_positions_zenith_and_refraction_context(rsk, site):
     assert_mask_equal(sky.above_horizon.cpu().numpy(), above, alt_az[0])
 
 
+def test_azimuth_octants_and_axes(rsk):
+    """The azimuth comes from an octant table (rsk_azimuth): every octant, the exact axes and diagonals, both
+    horizons and the neighbourhood of the zenith, with a context whose chain is the identity up to a reflection
+    (observer at the pole, no Earth rotation, Sun infinitely far, observer at rest), so az = pi - ra, alt = dec."""
+    a = np.zeros(E.ASTROM_LEN)
+    a[E.I_EH:E.I_EH + 3] = [1.0, 0.0, 0.0]
+    a[E.I_EM] = 1e30
+    a[E.I_BM1] = 1.0
+    a[E.I_BPN:E.I_BPN + 9] = np.eye(3).ravel()
+    a[E.I_PHI], a[E.I_SPHI], a[E.I_CPHI] = np.pi / 2, 1.0, 0.0
+    ra = np.concatenate([np.arange(16) * (np.pi / 8), np.linspace(0, 2 * np.pi, 4001)[:-1],
+                         np.arange(16) * (np.pi / 8) + 1e-12, np.arange(16) * (np.pi / 8) - 1e-12])
+    dec = np.concatenate([[-1.2, -1e-9, 0.0, 1e-9, 0.3, 1.2, np.pi / 2 - 1e-9, np.pi / 2 - 1e-6]])
+    lon, lat = (x.ravel() for x in np.meshgrid(ra, dec))
+    st = np.zeros((4, 1, lon.size)); st[0] = 1
+    sky = rsk.SkyModel(ra=lon, dec=lat, stokes=st, spectral_type="flat")
+    for astrom in (a, np.where(np.arange(a.size) == E.I_DIURAB, 1e-9, a)):  # folded and general chain
+        sky.update_positions(rsk.astrometry.Time(2457082.5), rsk.astrometry.EarthLocation(0.0, np.pi / 2, 0.0), astrom=astrom)
+        got = sky.alt_az.cpu().numpy()
+        alt_az, _, above = S.update_positions(lon, lat, astrom)
+        assert_altaz_close(got, alt_az)
+        assert got[1].min() >= 0.0 and got[1].max() <= 2 * np.pi
+        assert_mask_equal(sky.above_horizon.cpu().numpy(), above, alt_az[0], guard=1e-12)
+    # folded context: the identity chain
+    sky.update_positions(rsk.astrometry.Time(2457082.5), rsk.astrometry.EarthLocation(0.0, np.pi / 2, 0.0), astrom=a)
+    got = sky.alt_az.cpu().numpy()
+    d = np.abs(np.mod(got[1] - (np.pi - lon) + np.pi, 2 * np.pi) - np.pi) * np.cos(lat)
+    assert d.max() < 2e-15 and np.abs(got[0] - lat).max() < 1e-15
+
+
 def test_update_positions_errors(rsk, site):
     time, loc = site
     st = np.zeros((4, 1, 3)); st[0] = 1

@@ -152,20 +152,20 @@ def test_packed_context_reproduces_chain(librsk, hera):
     sphi, cphi = a[E.I_SPHI], a[E.I_CPHI]
     ae = np.array([sphi * hd[0] - cphi * hd[2], hd[1], cphi * hd[0] + sphi * hd[2]])
     assert np.abs(a1 @ p - ae).max() < 1e-15
-    assert ctx[17] == 1.0 and ctx[18] == 0.0
+    assert ctx[18] == 1.0 and ctx[19] == 0.0  # (sphi, cphi)
     # a context with a diurnal-aberration term is left unfolded
     b = a.copy()
     b[E.I_DIURAB] = 1e-6
     ctxb = astrometry.pack_context(b)
-    assert ctxb[17] == sphi and ctxb[18] == cphi and ctxb[19] == 1e-6
+    assert ctxb[18] == sphi and ctxb[19] == cphi and ctxb[20] == 1e-6
     assert np.abs(ctxb[8:17].reshape(3, 3) @ p - hd).max() < 1e-15
-    assert ctx[22] == E.SRS / a[E.I_EM] and ctx[23] == 1.0
+    assert ctx[3] == E.SRS / a[E.I_EM] and ctx[24] == 1.0  # (w2, m_ident)
     batch = astrometry.pack_contexts(np.stack([a, a]))
     assert batch.shape == (2, 34) and np.array_equal(batch[0], ctx) and np.array_equal(batch[1], ctx)
-    assert ctx[24] == 1.0 / (1.0 + a[E.I_BM1])
+    assert ctx[17] == 1.0 / (1.0 + a[E.I_BM1]) and ctx[23] == a[E.I_EM]
     m = astrometry.frame_to_icrs_matrix("fk5")
     ctx2 = astrometry.pack_context(a, m)
-    assert ctx2[23] == 0.0 and np.array_equal(ctx2[25:34].reshape(3, 3), m)
+    assert ctx2[24] == 0.0 and np.array_equal(ctx2[25:34].reshape(3, 3), m)
 
 
 @pytest.mark.parametrize("kind", ["linear", "slinear", "quadratic", "cubic", 1, 2, 3])
