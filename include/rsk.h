@@ -242,6 +242,45 @@ int rsk_segment_sum(const double* in /* [nrows][n_in] */, int64_t nrows, int64_t
                     const int64_t* order /* [n_in] */, const int64_t* start /* [nseg + 1] */, int64_t nseg,
                     int quadrature, double* out /* [nrows][nseg] */, void* stream);
 
+/* ---- component down-selection: SkyModel.select / cut_nonrising / calculate_rise_set_lsts ---------- */
+
+/* The per-component predicates of SkyModel.select (skymodel.py:3127-3283 with _select_lat :3012-3026, _select_lon
+ * :3028-3045, _select_brightness :3047-3124) and cut_nonrising (:3331-3393), evaluated together.  A component is
+ * kept when it passes every enabled test; the tests are the reference's comparisons (>=, <= bounds inclusive; a NaN
+ * Stokes I among the tested channels fails a brightness cut, as np.min / np.max propagate it). */
+typedef struct RskSelect {
+  int32_t use_lat;        /* lat_lo <= lat <= lat_hi */
+  int32_t use_lon;        /* lon_lo <= lon <= lon_hi, or lon >= lon_lo || lon <= lon_hi when lon_hi < lon_lo (wrap) */
+  int32_t use_min;        /* min over the tested channels of Stokes I >= min_brightness */
+  int32_t use_max;        /* max over the tested channels of Stokes I <= max_brightness */
+  int32_t non_nan;        /* 0 = off, 1 = "any": no NaN in any Stokes at any channel, 2 = "all": not NaN at all channels */
+  int32_t non_negative;   /* no Stokes I < 0 at any channel */
+  int32_t cut_nonrising;  /* drop tan(tel_lat) tan(lat) < -1 (never above the horizon) */
+  int32_t reserved;
+  double lat_lo, lat_hi, lon_lo, lon_hi; /* radians, in the catalogue frame */
+  double min_brightness, max_brightness; /* in the unit of stokes */
+  double tan_tel_lat;
+  const uint8_t* freq_use; /* DEVICE [nf]: channels the brightness cuts look at, NULL = all (brightness_freq_range) */
+} RskSelect;
+
+/* keep[j] = 1 if component comp_inds[j] (j itself when comp_inds is NULL) passes, else 0.  Feed keep to
+ * rsk_compact_index for the order-preserving index list.  For HEALPix coordinates the pixel centres are used, as
+ * SkyModel.get_lon_lat gives them. */
+int rsk_select_mask(const RskCoords* coords, const double* stokes /* [4][nf][n] */, int64_t nf, int64_t n,
+                    const int64_t* comp_inds /* DEVICE [m] in [0, n), or NULL */, int64_t m, const RskSelect* sel,
+                    uint8_t* keep /* [m] */, void* stream);
+
+/* out[r][j] = in[r][idx[j]] for nrows rows: the fancy index along the component axis that
+ * SkyModel._select_along_param_axis applies to every Ncomponents-shaped parameter (stokes, coordinates, spectral
+ * parameters, masks).  elem_bytes = 8 (doubles, int64 indices) or 1 (masks). */
+int rsk_gather_rows(const void* in /* [nrows][n_in] */, int64_t nrows, int64_t n_in, const int64_t* idx /* [n_out] */,
+                    int64_t n_out, int elem_bytes, void* out /* [nrows][n_out] */, void* stream);
+
+/* SkyModel.calculate_rise_set_lsts (skymodel.py:3284-3329): rise = lon - acos(-tan(tel_lat) tan(lat)) - buffer,
+ * set = lon + acos(...) + buffer, each wrapped once into [0, 2 pi]; NaN for components that never rise or never set. */
+int rsk_rise_set_lsts(const RskCoords* coords, int64_t n, double tel_lat, double horizon_buffer,
+                      double* rise_lst /* [n] */, double* set_lst /* [n] */, void* stream);
+
 /* ---- K1b: horizon compaction ------------------------------------------------------------------ */
 
 /* Order-preserving compaction of the horizon mask = the boolean fancy index of skymodel.py:2685 and

@@ -72,6 +72,28 @@ class RskBeam(ctypes.Structure):
 
 BEAM_JONES, BEAM_SHORT_DIPOLE, BEAM_UNIFORM = 0, 1, 2
 
+
+class RskSelect(ctypes.Structure):
+    _fields_ = [
+        ("use_lat", ctypes.c_int32),
+        ("use_lon", ctypes.c_int32),
+        ("use_min", ctypes.c_int32),
+        ("use_max", ctypes.c_int32),
+        ("non_nan", ctypes.c_int32),
+        ("non_negative", ctypes.c_int32),
+        ("cut_nonrising", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("lat_lo", ctypes.c_double),
+        ("lat_hi", ctypes.c_double),
+        ("lon_lo", ctypes.c_double),
+        ("lon_hi", ctypes.c_double),
+        ("min_brightness", ctypes.c_double),
+        ("max_brightness", ctypes.c_double),
+        ("tan_tel_lat", ctypes.c_double),
+        ("freq_use", ctypes.c_void_p),
+    ]
+
+
 _SIGNATURES = {
     "rsk_version": (ctypes.c_int, []),
     "rsk_strerror": (ctypes.c_char_p, [ctypes.c_int]),
@@ -114,6 +136,21 @@ _SIGNATURES = {
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
          ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p],
+    ),
+    "rsk_select_mask": (
+        ctypes.c_int,
+        [ctypes.POINTER(RskCoords), ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+         ctypes.POINTER(RskSelect), ctypes.c_void_p, ctypes.c_void_p],
+    ),
+    "rsk_gather_rows": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+         ctypes.c_void_p, ctypes.c_void_p],
+    ),
+    "rsk_rise_set_lsts": (
+        ctypes.c_int,
+        [ctypes.POINTER(RskCoords), ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_void_p,
+         ctypes.c_void_p, ctypes.c_void_p],
     ),
     "rsk_compact_index": (
         ctypes.c_int,

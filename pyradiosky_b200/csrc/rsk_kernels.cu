@@ -278,6 +278,110 @@ __global__ void __launch_bounds__(kThreads) k_segment_sum(const double* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Component down-selection (SkyModel.select, cut_nonrising, calculate_rise_set_lsts)
+// ---------------------------------------------------------------------------------------------------
+// longitude and latitude of component i in the catalogue frame, as SkyModel.get_lon_lat gives them
+__device__ __forceinline__ void frame_lonlat(const CoordSrc& c, int64_t i, double& lon, double& lat) {
+  if (c.nside > 0) {
+    const int64_t pix = c.hpx_inds ? __ldg(c.hpx_inds + i) : c.hpx_first + i;
+    double z, st, phi;
+    rsk_hpx_center(c.nside, c.nested, pix, z, st, phi);
+    lon = phi;
+    lat = rsk_atan2_t<true>(z, st);  // as k_healpix_lonlat
+  } else {
+    lon = __ldg(c.lon + i);
+    lat = __ldg(c.lat + i);
+  }
+}
+
+// One thread per candidate component: every enabled predicate of RskSelect, one byte out.  The Stokes reads are
+// coalesced across components (the component axis is the fastest); only the planes a predicate needs are touched.
+__global__ void __launch_bounds__(kThreads) k_select_mask(const CoordSrc cs, const double* __restrict__ stokes,
+                                                          const int64_t nf, const int64_t n,
+                                                          const int64_t* __restrict__ inds, const int64_t m,
+                                                          const RskSelect p, uint8_t* __restrict__ keep) {
+  const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (j >= m) return;
+  const int64_t i = inds ? __ldg(inds + j) : j;
+  bool k = i >= 0 && i < n;
+  if (k && (p.use_lat || p.use_lon || p.cut_nonrising)) {
+    double lon, lat;
+    frame_lonlat(cs, i, lon, lat);
+    if (p.use_lat) k = k && lat >= p.lat_lo && lat <= p.lat_hi;
+    if (p.use_lon) {
+      // skymodel.py:3036-3044: a range whose end is below its start wraps through lon = 0
+      if (p.lon_hi < p.lon_lo) k = k && (lon >= p.lon_lo || lon <= p.lon_hi);
+      else k = k && lon >= p.lon_lo && lon <= p.lon_hi;
+    }
+    if (p.cut_nonrising) k = k && !(p.tan_tel_lat * tan(lat) < -1.0);  // skymodel.py:3380-3381
+  }
+  if (k && (p.use_min || p.use_max || p.non_negative || p.non_nan)) {
+    double mn = INFINITY, mx = -INFINITY;
+    bool nan_used = false, any_neg = false, any_nan = false, all_nan = true;
+    for (int64_t f = 0; f < nf; ++f) {
+      const double si = __ldg(stokes + f * n + i);
+      if (p.use_min || p.use_max) {
+        if (!p.freq_use || __ldg(p.freq_use + f)) {
+          nan_used = nan_used || isnan(si);
+          mn = si < mn ? si : mn;
+          mx = si > mx ? si : mx;
+        }
+      }
+      any_neg = any_neg || si < 0.0;
+      if (p.non_nan) {
+        bool nanf = isnan(si);
+        for (int q = 1; q < 4; ++q) nanf = nanf || isnan(__ldg(stokes + (q * nf + f) * n + i));
+        any_nan = any_nan || nanf;
+        all_nan = all_nan && nanf;
+      }
+    }
+    if (p.use_min) k = k && !nan_used && mn >= p.min_brightness;  // np.min(...) >= min (:3096-3098)
+    if (p.use_max) k = k && !nan_used && mx <= p.max_brightness;  // np.max(...) <= max (:3120-3122)
+    if (p.non_negative) k = k && !any_neg;                        // :3232
+    if (p.non_nan == 1) k = k && !any_nan;                        // :3215-3218
+    if (p.non_nan == 2) k = k && !(all_nan && nf > 0);            // :3222-3224
+  }
+  keep[j] = k ? 1 : 0;
+}
+
+// out[r][j] = in[r][idx[j]]: the index is read once per thread and reused for RPT rows (gridDim.y strides the rows)
+template <typename T, int RPT>
+__global__ void __launch_bounds__(kThreads) k_gather_rows(const T* __restrict__ in, const int64_t nrows,
+                                                          const int64_t n_in, const int64_t* __restrict__ idx,
+                                                          const int64_t n_out, T* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (j >= n_out) return;
+  const int64_t i = __ldg(idx + j);
+  for (int64_t r0 = (int64_t)blockIdx.y * RPT; r0 < nrows; r0 += (int64_t)gridDim.y * RPT) {
+    T v[RPT];
+#pragma unroll
+    for (int q = 0; q < RPT; ++q)
+      if (r0 + q < nrows) v[q] = __ldg(in + (r0 + q) * n_in + i);
+#pragma unroll
+    for (int q = 0; q < RPT; ++q)
+      if (r0 + q < nrows) out[(r0 + q) * n_out + j] = v[q];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_rise_set(const CoordSrc cs, const int64_t n, const double tan_tel,
+                                                       const double buff, double* __restrict__ rise,
+                                                       double* __restrict__ set) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  double lon, lat;
+  frame_lonlat(cs, i, lon, lat);
+  const double ha = acos(-(tan_tel * tan(lat)));  // NaN when the component never rises or never sets
+  double r = lon - ha - buff, s = lon + ha + buff;
+  // skymodel.py:3323-3326: one wrap each way, in this order
+  if (r < 0.0) r += RSK_D2PI;
+  if (s < 0.0) s += RSK_D2PI;
+  if (r > RSK_D2PI) r -= RSK_D2PI;
+  if (s > RSK_D2PI) s -= RSK_D2PI;
+  rise[i] = r;
+  set[i] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // K1b: order-preserving compaction of the horizon mask (count -> scan of tile counts -> scatter)
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t load_mask8(const uint8_t* __restrict__ m, int64_t base, int64_t n, bool aligned) {
@@ -1366,6 +1470,56 @@ int rsk_scale(double* x, int64_t count, double factor, int divide, void* stream)
   if (!x) return RSK_ERR_NULL;
   if ((count + kThreads - 1) / kThreads > 0x7fffffffll) return RSK_ERR_SIZE;
   k_scale<<<blocks_for(count), kThreads, 0, (cudaStream_t)stream>>>(x, count, factor, divide);
+  return launch_status();
+}
+
+int rsk_select_mask(const RskCoords* coords, const double* stokes, int64_t nf, int64_t n, const int64_t* comp_inds,
+                    int64_t m, const RskSelect* sel, uint8_t* keep, void* stream) {
+  if (!sel) return RSK_ERR_NULL;
+  if (nf < 0 || n < 0 || m < 0) return RSK_ERR_SIZE;
+  if (sel->non_nan < 0 || sel->non_nan > 2) return RSK_ERR_MODE;
+  if (m == 0) return RSK_OK;
+  if (!keep) return RSK_ERR_NULL;
+  const bool need_coords = sel->use_lat || sel->use_lon || sel->cut_nonrising;
+  const bool need_stokes = sel->use_min || sel->use_max || sel->non_negative || sel->non_nan;
+  CoordSrc cs = {};
+  if (need_coords) {
+    const int rc = check_coords(coords, &cs);
+    if (rc != RSK_OK) return rc;
+  }
+  if (need_stokes && !stokes) return RSK_ERR_NULL;
+  if (sel->use_lat && !(sel->lat_lo <= sel->lat_hi)) return RSK_ERR_SIZE;
+  k_select_mask<<<blocks_for(m), kThreads, 0, (cudaStream_t)stream>>>(cs, stokes, nf, n, comp_inds, m, *sel, keep);
+  return launch_status();
+}
+
+int rsk_gather_rows(const void* in, int64_t nrows, int64_t n_in, const int64_t* idx, int64_t n_out, int elem_bytes,
+                    void* out, void* stream) {
+  if (nrows < 0 || n_in < 0 || n_out < 0) return RSK_ERR_SIZE;
+  if (elem_bytes != 1 && elem_bytes != 8) return RSK_ERR_MODE;
+  if (nrows == 0 || n_out == 0) return RSK_OK;
+  if (!in || !idx || !out) return RSK_ERR_NULL;
+  if ((n_out + kThreads - 1) / kThreads > 0x7fffffffll) return RSK_ERR_SIZE;
+  constexpr int kRpt = 4;
+  const int64_t row_groups = (nrows + kRpt - 1) / kRpt;
+  const dim3 grid(blocks_for(n_out), (unsigned)std::min<int64_t>(row_groups, 65535));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (elem_bytes == 8)
+    k_gather_rows<double, kRpt><<<grid, kThreads, 0, st>>>((const double*)in, nrows, n_in, idx, n_out, (double*)out);
+  else
+    k_gather_rows<uint8_t, kRpt><<<grid, kThreads, 0, st>>>((const uint8_t*)in, nrows, n_in, idx, n_out, (uint8_t*)out);
+  return launch_status();
+}
+
+int rsk_rise_set_lsts(const RskCoords* coords, int64_t n, double tel_lat, double horizon_buffer, double* rise_lst,
+                      double* set_lst, void* stream) {
+  CoordSrc cs;
+  const int rc = check_coords(coords, &cs);
+  if (rc != RSK_OK) return rc;
+  if (n < 0) return RSK_ERR_SIZE;
+  if (n == 0) return RSK_OK;
+  if (!rise_lst || !set_lst) return RSK_ERR_NULL;
+  k_rise_set<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(cs, n, tan(tel_lat), horizon_buffer, rise_lst, set_lst);
   return launch_status();
 }
 

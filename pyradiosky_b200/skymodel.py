@@ -725,6 +725,216 @@ class SkyModel:
         return alt_az, lmn, (None if above is None else above.view(torch.bool))
 
     # ------------------------------------------------------------------------------------------
+    # component down-selection: select / cut_nonrising / calculate_rise_set_lsts
+    # ------------------------------------------------------------------------------------------
+    def _gather(self, t, idx, m):
+        """t[..., idx] for a CUDA tensor whose last axis is the component axis (rsk_gather_rows)."""
+        t = t.contiguous()
+        n_in = t.shape[-1]
+        nrows = t.numel() // max(n_in, 1)
+        out = torch.empty(t.shape[:-1] + (m,), dtype=t.dtype, device=self.device)
+        esize = t.element_size()
+        if esize not in (1, 8):
+            raise TypeError(f"cannot gather tensors of dtype {t.dtype}")
+        self._call("rsk_gather_rows", _lib.ptr(t), nrows, n_in, _lib.ptr(idx), m, esize, _lib.ptr(out))
+        return out
+
+    def _take_components(self, idx, m):
+        """Keep the components ``idx[:m]`` (CUDA int64), in that order, on every Ncomponents-shaped attribute:
+        what ``_select_along_param_axis({"Ncomponents": inds})`` does in the reference (skymodel.py:3258)."""
+        idx = idx[:m].contiguous()
+        self.stokes = self._gather(self.stokes, idx, m)
+        if self.component_type == "point":
+            self.lon = self._gather(self.lon, idx, m)
+            self.lat = self._gather(self.lat, idx, m)
+        elif self.hpx_inds is not None:
+            self.hpx_inds = self._gather(self.hpx_inds, idx, m)
+        else:  # an implicit pixel range becomes an explicit list
+            self.hpx_inds = idx + self.hpx_first
+            self.hpx_first = 0
+        for attr in ("spectral_index", "reference_frequency", "stokes_error", "beam_amp", "alt_az", "pos_lmn",
+                     "_polarized_mask", "_rise_lst", "_set_lst"):
+            t = self.__dict__.get(attr)
+            if t is not None:
+                setattr(self, attr, self._gather(t, idx, m))
+        if self.above_horizon is not None:
+            self.above_horizon = self._gather(self.above_horizon.view(torch.uint8), idx, m).view(torch.bool)
+        host_idx = None
+        if self.name is not None or self.extended_model_group is not None or self.extra_columns:
+            host_idx = idx.cpu().numpy()
+        if self.name is not None:
+            self.name = self.name[host_idx]
+        if self.extended_model_group is not None:
+            self.extended_model_group = self.extended_model_group[host_idx]
+        if self.extra_columns:
+            self.extra_columns = {k: np.asarray(v)[host_idx] for k, v in self.extra_columns.items()}
+        self.Ncomponents = m
+        self._n_polarized = int(self._polarized_mask.sum().item())
+        self._rot_key = None  # the cached rotation coefficients belong to the old component list
+        self.__dict__.pop("_rot", None)
+        for cache in ("_subband_cache", "_nan_group_cache", "_nan_cache", "_staging", "_graph"):
+            self.__dict__.pop(cache, None)
+        if self.frame_coherency is not None:
+            self.calc_frame_coherency()
+
+    @staticmethod
+    def _range_rad(value, what, other):
+        """A (lo, hi) range in radians from an astropy Latitude / Longitude or plain radians."""
+        if type(value).__name__ == other:
+            raise TypeError(f"{what}_range must be an astropy {'Latitude' if what == 'lat' else 'Longitude'} object.")
+        return np.atleast_1d(np.asarray(_to_rad(value), dtype=np.float64))
+
+    def _brightness_value(self, value, what):
+        if value is None:
+            return None
+        if hasattr(value, "to_value"):
+            try:
+                return float(value.to_value(self.stokes_unit))
+            except Exception as err:  # astropy UnitConversionError
+                raise TypeError(
+                    f"{what} must be a Quantity object with units that can be converted to {self.stokes_unit}"
+                ) from err
+        return float(value)  # plain numbers are taken to be in the unit of ``stokes``
+
+    def select(self, component_inds=None, lat_range=None, lon_range=None, min_brightness=None, max_brightness=None,
+               brightness_freq_range=None, non_nan=None, non_negative=False, inplace=True, run_check=True,
+               check_extra=True, run_check_acceptability=True):
+        """Downselect sources based on various criteria (skymodel.py:3127-3283).
+
+        ``component_inds``: indices to keep; ``lat_range`` / ``lon_range``: (2,) ranges in the catalogue frame
+        (astropy Latitude / Longitude or radians; a lon range whose end is below its start wraps through 0);
+        ``min_brightness`` / ``max_brightness``: Stokes I cuts (>=, <=; Quantity or a number in the unit of
+        ``stokes``) over ``brightness_freq_range`` (Hz, 2 elements; default all stored frequencies); ``non_nan``:
+        "any" / "all" / None; ``non_negative``: drop components with any negative Stokes I.  The predicates are
+        evaluated in one kernel (rsk_select_mask), the surviving indices come from the horizon-compaction kernels and
+        every per-component array is gathered on the GPU (rsk_gather_rows).  The ``run_check*`` arguments are accepted
+        and ignored (the UVBase validation framework is out of scope)."""
+        skyobj = self if inplace else self.copy()
+        if (component_inds is None and lat_range is None and lon_range is None and min_brightness is None
+                and max_brightness is None and non_nan is None and non_negative is False):
+            return None if inplace else skyobj
+        sel = _lib.RskSelect()
+        if non_nan is not None:
+            allowed_vals = ["any", "all"]
+            if non_nan not in allowed_vals:
+                raise ValueError(f"If set, non_nan can only be set to one of: {allowed_vals}")
+            sel.non_nan = 1 if non_nan == "any" else 2
+        sel.non_negative = 1 if non_negative else 0
+        if lat_range is not None:
+            r = skyobj._range_rad(lat_range, "lat", "Longitude")
+            if r.size != 2 or r[0] >= r[1]:
+                raise ValueError("lat_range must be 2 element range with the second component larger than the first.")
+            sel.use_lat, sel.lat_lo, sel.lat_hi = 1, float(r[0]), float(r[1])
+        if lon_range is not None:
+            r = skyobj._range_rad(lon_range, "lon", "Latitude")
+            if r.size != 2:
+                raise ValueError("lon_range must be 2 element range.")
+            sel.use_lon, sel.lon_lo, sel.lon_hi = 1, float(r[0]), float(r[1])
+        freq_use = None
+        if min_brightness is not None or max_brightness is not None:
+            # skymodel.py:3047-3124
+            if skyobj.spectral_type == "spectral_index":
+                raise NotImplementedError("Flux cuts with spectral index type objects is not supported yet.")
+            fr = brightness_freq_range
+            if fr is not None:
+                fr = np.atleast_1d(np.asarray(fr.to_value("Hz") if hasattr(fr, "to_value") else fr, dtype=np.float64))
+                if fr.size != 2:
+                    raise ValueError("brightness_freq_range must have 2 elements.")
+                if skyobj.freq_array is not None:
+                    use = (skyobj.freq_array >= fr.min()) & (skyobj.freq_array <= fr.max())
+                    if not use.any():
+                        raise ValueError("No object frequencies in specified range for flux cuts.")
+                    freq_use = torch.as_tensor(use.astype(np.uint8)).to(skyobj.device)
+                    sel.freq_use = freq_use.data_ptr()
+            mn = skyobj._brightness_value(min_brightness, "min_brightness")
+            mx = skyobj._brightness_value(max_brightness, "max_brightness")
+            if mn is not None:
+                sel.use_min, sel.min_brightness = 1, mn
+            if mx is not None:
+                sel.use_max, sel.max_brightness = 1, mx
+        n = skyobj.Ncomponents
+        inds = None
+        if component_inds is not None:
+            if isinstance(component_inds, torch.Tensor):
+                inds = component_inds.to(skyobj.device, dtype=torch.int64).flatten().contiguous()
+            else:
+                inds = torch.as_tensor(np.atleast_1d(np.asarray(component_inds)).astype(np.int64)).to(skyobj.device)
+            if inds.numel() > 0:
+                lo, hi = int(inds.min().item()), int(inds.max().item())
+                if lo < -n or hi >= n:
+                    raise IndexError(f"index {hi if hi >= n else lo} is out of bounds for axis 0 with size {n}")
+                if lo < 0:
+                    inds = torch.where(inds < 0, inds + n, inds)
+            # np.intersect1d (:3226, :3234) and np.union1d (:3041) leave the list sorted and free of repeats
+            if sel.non_nan or sel.non_negative or (sel.use_lon and sel.lon_hi < sel.lon_lo):
+                inds = torch.unique(inds, sorted=True)
+        m = n if inds is None else int(inds.numel())
+        predicates = (sel.use_lat or sel.use_lon or sel.use_min or sel.use_max or sel.non_nan or sel.non_negative
+                      or sel.cut_nonrising)
+        if predicates and m > 0:
+            keep = torch.empty(m, dtype=torch.uint8, device=skyobj.device)
+            coords = skyobj._coords_struct()
+            skyobj._call("rsk_select_mask", ctypes.byref(coords), _lib.ptr(skyobj.stokes), skyobj.Nfreqs, n,
+                         _lib.ptr(inds), m, ctypes.byref(sel), _lib.ptr(keep))
+            pos, m_out = skyobj._compact_mask(keep)
+            idx = pos[:m_out] if inds is None else skyobj._gather(inds, pos[:m_out].contiguous(), m_out)
+        else:
+            m_out = m
+            idx = inds if inds is not None else torch.arange(n, dtype=torch.int64, device=skyobj.device)
+        if m_out == 0:
+            raise ValueError("Select would result in an empty object.")
+        if m_out == n:  # nothing removed (skymodel.py:3250-3254)
+            return None if inplace else skyobj
+        skyobj.history = (skyobj.history or "") + "  Downselected to specific components using pyradiosky."
+        skyobj._take_components(idx, m_out)
+        # if all extended models were removed in select, set extended_model_group to None (:3260-3265)
+        if skyobj.extended_model_group is not None and not np.any(skyobj.extended_model_group != ""):
+            skyobj.extended_model_group = None
+        return None if inplace else skyobj
+
+    def calculate_rise_set_lsts(self, telescope_latitude, horizon_buffer=0.04364):
+        """Calculate the rise & set LSTs given a telescope latitude (skymodel.py:3284-3329).
+
+        Sets ``_rise_lst`` and ``_set_lst`` (radians, CUDA tensors; NaN for sources that never rise or never set).
+        ``telescope_latitude``: astropy Latitude or radians; ``horizon_buffer``: angle buffer in radians."""
+        lat_rad = float(np.asarray(_to_rad(telescope_latitude), dtype=np.float64))
+        n = self.Ncomponents
+        self._rise_lst = torch.empty(n, dtype=torch.float64, device=self.device)
+        self._set_lst = torch.empty(n, dtype=torch.float64, device=self.device)
+        coords = self._coords_struct()
+        self._call("rsk_rise_set_lsts", ctypes.byref(coords), n, lat_rad, float(horizon_buffer),
+                   _lib.ptr(self._rise_lst), _lib.ptr(self._set_lst))
+
+    def cut_nonrising(self, telescope_latitude, inplace=True, run_check=True, check_extra=True,
+                      run_check_acceptability=True):
+        """Remove sources that will never rise (skymodel.py:3331-3393): tan(lat_tel) tan(lat) < -1."""
+        if type(telescope_latitude).__name__ in ("Longitude", "Angle", "Quantity") or isinstance(telescope_latitude, str):
+            raise TypeError("telescope_latitude must be an astropy Latitude object.")
+        skyobj = self if inplace else self.copy()
+        lat_rad = float(np.asarray(_to_rad(telescope_latitude), dtype=np.float64))
+        n = skyobj.Ncomponents
+        sel = _lib.RskSelect()
+        sel.cut_nonrising, sel.tan_tel_lat = 1, math.tan(lat_rad)
+        keep = torch.empty(n, dtype=torch.uint8, device=skyobj.device)
+        coords = skyobj._coords_struct()
+        skyobj._call("rsk_select_mask", ctypes.byref(coords), _lib.ptr(skyobj.stokes), skyobj.Nfreqs, n, None, n,
+                     ctypes.byref(sel), _lib.ptr(keep))
+        idx, cnt = skyobj._compact_mask(keep)
+        skyobj.select(component_inds=idx[:cnt])
+        return None if inplace else skyobj
+
+    def _compact_mask(self, mask_u8):
+        """(idx, count) of the non-zero entries of a CUDA uint8 mask, in order (rsk_compact_index)."""
+        m = int(mask_u8.numel())
+        idx = torch.empty(max(m, 1), dtype=torch.int64, device=self.device)
+        cnt = torch.empty(1, dtype=torch.int64, device=self.device)
+        nbytes = _lib.load().rsk_workspace_bytes(_lib.OP_COMPACT, m, 0)
+        work = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=self.device)
+        self._call("rsk_compact_index", _lib.ptr(mask_u8), m, _lib.ptr(idx), _lib.ptr(cnt), _lib.ptr(work),
+                   ctypes.c_size_t(nbytes))
+        return idx, int(cnt.item())
+
+    # ------------------------------------------------------------------------------------------
     # coherency
     # ------------------------------------------------------------------------------------------
     def calc_frame_coherency(self, store=True):

@@ -1,0 +1,486 @@
+"""Component down-selection: SkyModel.select / cut_nonrising / calculate_rise_set_lsts.
+
+CPU part: the numpy oracle (oracle/select_np.py) against the reference's own known answers.
+GPU part (``-m gpu``): the reference's tests for these methods (tests/test_skymodel.py:2174-2760), line for line where
+astropy types are not essential, on the CUDA path (rsk_select_mask -> rsk_compact_index -> rsk_gather_rows,
+rsk_rise_set_lsts), plus random parity against the oracle and the C-ABI error paths.
+"""
+
+import ctypes
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import erfa_np as E
+from oracle import h5_np
+from oracle import healpix_np as hp
+from oracle import select_np as SEL
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GLEAM50 = os.path.join(ROOT, "tests", "golden", "ref_fixture_gleam50_old_header.skyh5")
+
+
+def _gleam_with_nans():
+    f = h5_np.File(GLEAM50)
+    st = np.array(f["/Data/stokes"].read(), dtype=np.float64)
+    # tests/test_skymodel.py:2181-2185
+    st[0, 0:2, 0] = np.nan
+    st[0, 10:11, 1] = np.nan
+    st[0, -2:, 2] = np.nan
+    st[0, :, 3] = np.nan
+    lon = np.deg2rad(np.array(f["/Header/ra"].read(), dtype=np.float64))
+    lat = np.deg2rad(np.array(f["/Header/dec"].read(), dtype=np.float64))
+    fa = np.array(f["/Header/freq_array"].read(), dtype=np.float64)
+    return lon, lat, st, fa
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU: the oracle is pinned by the reference's known answers
+# ---------------------------------------------------------------------------------------------------
+def test_oracle_reproduces_reference_counts():
+    """tests/test_skymodel.py:2193-2223: 46 / 49 / 32 / 31 / 29 / 4 components survive."""
+    lon, lat, st, fa = _gleam_with_nans()
+    kw = dict(spectral_type="subband", freq_array=fa)
+    assert SEL.select_indices(lon, lat, st, non_nan="any", **kw).size == 46
+    assert SEL.select_indices(lon, lat, st, non_nan="all", **kw).size == 49
+    assert SEL.select_indices(lon, lat, st, non_nan=None, non_negative=True, **kw).size == 32
+    assert SEL.select_indices(lon, lat, st, non_nan="all", non_negative=True, **kw).size == 31
+    assert SEL.select_indices(lon, lat, st, non_nan="any", non_negative=True, **kw).size == 29
+    assert SEL.select_indices(lon, lat, st, component_inds=np.arange(10), non_nan="any", non_negative=True, **kw).size == 4
+    assert SEL.select_indices(lon, lat, st, **kw) is None
+
+
+def test_oracle_rise_set_identities():
+    """tests/test_skymodel.py:2726-2737: circumpolar <=> tan tan > 1 (set/rise NaN), never rising <=> < -1."""
+    rng = np.random.default_rng(3)
+    lon = rng.uniform(0, 2 * np.pi, 2000)
+    lat = np.arcsin(rng.uniform(-1, 1, 2000))
+    tel = -0.5361
+    rise, sett = SEL.rise_set_lsts(lon, lat, tel)
+    tans = np.tan(tel) * np.tan(lat)
+    assert np.array_equal(np.isnan(rise), np.abs(tans) > 1) and np.array_equal(np.isnan(sett), np.abs(tans) > 1)
+    ok = ~np.isnan(rise)
+    assert rise[ok].min() >= 0 and rise[ok].max() <= 2 * np.pi and sett[ok].min() >= 0 and sett[ok].max() <= 2 * np.pi
+    keep = SEL.nonrising_keep(lat, tel)
+    assert np.array_equal(keep, np.nonzero(~(tans < -1))[0])
+    # the time above the (buffered) horizon is 2 acos(-tans) + 2 buffer
+    up = np.mod(sett[ok] - rise[ok], 2 * np.pi)
+    want = np.mod(2 * np.arccos(-tans[ok]) + 2 * 0.04364, 2 * np.pi)
+    assert np.abs(up - want).max() < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def rsk(librsk):
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pyradiosky_b200
+
+    return pyradiosky_b200
+
+
+@pytest.fixture(scope="module")
+def site(rsk):
+    loc = rsk.EarthLocation.from_dms((-30, 43, 17.5), (21, 25, 41.9), 1073.0)
+    time = rsk.Time.from_utc("2015-03-01 00:00:00")
+    return time, loc
+
+
+def _gleam_model(rsk, with_nans=True):
+    lon, lat, st, fa = _gleam_with_nans()
+    if not with_nans:
+        st = np.array(h5_np.File(GLEAM50)["/Data/stokes"].read(), dtype=np.float64)
+    names = np.array([f"GLEAM {k}" for k in range(st.shape[2])])
+    sky = rsk.SkyModel(name=names, ra=lon, dec=lat, frame="fk5", stokes=st, spectral_type="subband", freq_array=fa,
+                       history="read from the fixture.")
+    return sky, lon, lat, st, fa
+
+
+@pytest.mark.gpu
+def test_cut_nan_neg(rsk):
+    """tests/test_skymodel.py:2174-2223."""
+    sky, *_ = _gleam_model(rsk)
+    assert sky.select(non_nan="any", inplace=False).Ncomponents == 46
+    assert sky.select(non_nan="all", inplace=False).Ncomponents == 49
+    assert sky.select(non_nan=None, non_negative=True, inplace=False).Ncomponents == 32
+    assert sky.select(non_nan="all", non_negative=True, inplace=False).Ncomponents == 31
+    assert sky.select(non_nan="any", non_negative=True, inplace=False).Ncomponents == 29
+    sky3 = sky.select(component_inds=np.arange(10), non_nan="any", non_negative=True, inplace=False)
+    assert sky3.Ncomponents == 4
+    assert sky.Ncomponents == 50  # inplace=False left the object alone
+
+
+def _assert_same_model(a, b):
+    import torch
+
+    assert a.Ncomponents == b.Ncomponents and a.Nfreqs == b.Nfreqs
+    for attr in ("stokes", "lon", "lat", "spectral_index", "reference_frequency", "stokes_error", "beam_amp", "alt_az",
+                 "pos_lmn", "above_horizon", "hpx_inds"):
+        x, y = getattr(a, attr), getattr(b, attr)
+        assert (x is None) == (y is None), attr
+        if x is not None:
+            assert torch.equal(torch.nan_to_num(x.double(), nan=-7.0), torch.nan_to_num(y.double(), nan=-7.0)), attr
+    assert (a.name is None) == (b.name is None) and (a.name is None or np.array_equal(a.name, b.name))
+    assert (a.extended_model_group is None) == (b.extended_model_group is None)
+    assert (a.extra_columns is None) == (b.extra_columns is None)
+    if a.extra_columns:
+        for k in a.extra_columns:
+            assert np.array_equal(a.extra_columns[k], b.extra_columns[k])
+
+
+@pytest.mark.gpu
+def test_flux_source_cuts(rsk):
+    """tests/test_skymodel.py:2226-2258."""
+    sky, *_ = _gleam_model(rsk, with_nans=False)
+    sky.select(non_negative=True)
+    sky2 = sky.select(min_brightness=0.2, max_brightness=1.5, inplace=False)
+    assert sky2.Ncomponents < sky.Ncomponents
+    s0 = sky2.stokes[0].cpu().numpy()
+    assert np.all((s0 > 0.2) & (s0 < 1.5))
+    st = sky.stokes[0].cpu().numpy()
+    keep = np.where((st.min(axis=0) > 0.2) & (st.max(axis=0) < 1.5))[0]
+    sky3 = sky.select(component_inds=keep, inplace=False)
+    expected = sky.history + "  Downselected to specific components using pyradiosky."
+    assert sky2.history == expected and sky3.history == expected
+    _assert_same_model(sky2, sky3)
+
+
+@pytest.mark.gpu
+def test_select(rsk, site):
+    """tests/test_skymodel.py:2261-2285: every per-component attribute follows, also the time-dependent ones."""
+    import torch
+
+    time, loc = site
+    sky, *_ = _gleam_model(rsk, with_nans=False)
+    sky.select(non_negative=True)
+    n = sky.Ncomponents
+    sky.beam_amp = torch.ones((4, sky.Nfreqs, n), dtype=torch.float64, device=sky.device)
+    sky.stokes_error = sky.stokes * 0.1
+    sky.extended_model_group = np.full(n, "", dtype="<U10")
+    sky.update_positions(time, loc)
+    sky.extra_columns = {"foo": np.arange(n, dtype=float), "bar": np.arange(n, dtype=int),
+                         "gah": np.array(["gah " + str(i) for i in range(n)])}
+    before = {k: getattr(sky, k).cpu().numpy().copy() for k in ("stokes", "lon", "lat", "alt_az", "pos_lmn", "above_horizon")}
+    sky2 = sky.select(component_inds=np.arange(10), inplace=False)
+    sky.select(component_inds=np.arange(10), run_check=False)
+    _assert_same_model(sky, sky2)
+    assert sky.extended_model_group is None and sky.Ncomponents == 10
+    for k, v in before.items():
+        assert np.array_equal(getattr(sky, k).cpu().numpy(), v[..., :10], equal_nan=True), k
+    assert np.array_equal(sky.extra_columns["gah"], np.array(["gah " + str(i) for i in range(10)]))
+    full = np.array(h5_np.File(GLEAM50)["/Data/stokes"].read(), dtype=np.float64)
+    nonneg = np.nonzero(~np.any(full[0] < 0, axis=0))[0]
+    assert np.array_equal(sky.name, np.array([f"GLEAM {k}" for k in nonneg[:10]]))
+    # the selected object keeps working: a new time step, coherencies of the right width
+    sky.update_positions(time + 0.01, loc)
+    out = sky.coherency_calc(freqs=np.array([150e6, 160e6]))
+    assert out.shape[:3] == (2, 2, 2) and out.shape[3] == int(sky.above_horizon.sum())
+    # unsorted indices with repeats are kept in the order given (numpy fancy indexing)
+    sky4, *_ = _gleam_model(rsk, with_nans=False)
+    pick = np.array([7, 3, 3, 49, 0, -1])
+    ref = sky4.stokes.cpu().numpy()[..., pick]
+    sky4.select(component_inds=pick)
+    assert np.array_equal(sky4.stokes.cpu().numpy(), ref)
+    with pytest.raises(IndexError):
+        sky4.select(component_inds=[0, 99])
+
+
+@pytest.mark.gpu
+def test_select_none(rsk):
+    """tests/test_skymodel.py:2288-2299."""
+    sky, *_ = _gleam_model(rsk, with_nans=False)
+    sky2 = sky.select(non_nan=None, component_inds=None, inplace=False)
+    _assert_same_model(sky, sky2)
+    sky2 = sky.select(non_nan="all", component_inds=None, inplace=False)
+    _assert_same_model(sky, sky2)
+    assert sky2.history == sky.history  # nothing removed, history untouched
+    assert sky.select(non_nan=None, component_inds=None) is None
+    _assert_same_model(sky, sky2)
+
+
+def _twenty(rsk, spec_type, init_kwargs, frame="fk5"):
+    """The 20-source model of tests/test_skymodel.py:2328-2350 (angles in radians)."""
+    nsrcs, minflux, maxflux = 20, 0.5, 3.0
+    ras = np.deg2rad(np.linspace(0, 360.0, nsrcs))
+    decs = np.deg2rad(np.linspace(-90, 90, nsrcs))
+    if spec_type in ("flat", "spectral_index"):
+        stokes = np.zeros((4, 1, nsrcs))
+        stokes[0, :, :] = np.linspace(minflux, maxflux, nsrcs)
+    else:
+        stokes = np.zeros((4, 2, nsrcs))
+        stokes[0, 0, :] = np.linspace(minflux, maxflux / 2.0, nsrcs)
+        stokes[0, 1, :] = np.linspace(minflux * 2.0, maxflux, nsrcs)
+    ucomp = maxflux + 1.3
+    stokes[2, :, :] = ucomp
+    sky = rsk.SkyModel(name=[f"src{i}" for i in range(nsrcs)], ra=ras, dec=decs, frame=frame, stokes=stokes,
+                       spectral_type=spec_type, **init_kwargs)
+    return sky, ucomp
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize(
+    "spec_type, init_kwargs, cut_kwargs, cut_type",
+    [
+        ("flat", {}, {}, "min"),
+        ("flat", {"reference_frequency": np.ones(20) * 200e6}, {}, "max"),
+        ("full", {"freq_array": np.array([1e8, 1.5e8])}, {}, "both"),
+        ("subband", {"freq_array": np.array([1e8, 1.5e8])}, {"freq_range": np.array([0.9e8, 2e8])}, "both"),
+        ("subband", {"freq_array": np.array([1e8, 1.5e8])}, {"freq_range": np.array([1.1e8, 2e8])}, "both"),
+        ("flat", {"freq_array": np.array([1e8])}, {"freq_range": np.array([0.9e8, 2e8])}, "both"),
+    ],
+)
+def test_select_flux(rsk, spec_type, init_kwargs, cut_kwargs, cut_type):
+    """tests/test_skymodel.py:2302-2384."""
+    sky, ucomp = _twenty(rsk, spec_type, init_kwargs)
+    st0 = sky.stokes.cpu().numpy().copy()
+    min_cut = 1.0 if cut_type in ("min", "both") else None
+    max_cut = 2.3 if cut_type in ("max", "both") else None
+    freq_range = cut_kwargs.get("freq_range")
+    sky.select(min_brightness=min_cut, max_brightness=max_cut, brightness_freq_range=freq_range, non_nan=None)
+    s0 = sky.stokes[0].cpu().numpy()
+    if freq_range is not None and max_cut is not None and np.min(freq_range) > np.min(init_kwargs["freq_array"]):
+        assert np.all(s0 <= max_cut)
+    else:
+        if min_cut is not None:
+            assert np.all(s0 >= min_cut)
+        if max_cut is not None:
+            assert np.all(s0 <= max_cut)
+    assert np.all(sky.stokes[2].cpu().numpy() == ucomp)
+    want = SEL.select_indices(sky.lon.cpu().numpy() * 0, sky.lat.cpu().numpy() * 0, st0, spectral_type=spec_type,
+                              freq_array=init_kwargs.get("freq_array"), min_brightness=min_cut, max_brightness=max_cut,
+                              brightness_freq_range=freq_range)
+    assert np.array_equal(sky.stokes.cpu().numpy(), st0[..., want])
+    assert np.array_equal(sky.name, np.array([f"src{i}" for i in range(20)])[want])
+
+
+@pytest.mark.gpu
+def test_select_flux_cut_error(rsk):
+    """tests/test_skymodel.py:2387-2485 (the unit-checking decorator of astropy is not mirrored)."""
+    sky, _ = _twenty(rsk, "subband", {"freq_array": np.array([1e8, 1.5e8])}, frame="icrs")
+    with pytest.raises(ValueError, match=r"If set, non_nan can only be set to one of: \['any', 'all'\]"):
+        sky.select(min_brightness=1.0, max_brightness=2.3, non_nan=True)
+    si, _ = _twenty(rsk, "spectral_index", {"reference_frequency": np.ones(20) * 200e6, "spectral_index": np.ones(20) * 0.8},
+                    frame="icrs")
+    with pytest.raises(NotImplementedError, match="Flux cuts with spectral index type objects is not supported yet."):
+        si.select(min_brightness=1.0, max_brightness=2.3, non_nan="all")
+    with pytest.raises(ValueError, match="brightness_freq_range must have 2 elements."):
+        sky.select(min_brightness=1.0, max_brightness=2.3, brightness_freq_range=0.9e8, non_nan="all")
+    with pytest.raises(ValueError, match="No object frequencies in specified range for flux cuts."):
+        sky.select(min_brightness=1.0, max_brightness=2.3, brightness_freq_range=np.array([1.1e8, 1.4e8]), non_nan="all")
+    assert sky.Ncomponents == 20
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize(
+    "spec_type, init_kwargs",
+    [
+        ("flat", {}),
+        ("flat", {"reference_frequency": np.ones(20) * 200e6}),
+        ("full", {"freq_array": np.array([1e8, 1.5e8])}),
+        ("subband", {"freq_array": np.array([1e8, 1.5e8])}),
+        ("flat", {"freq_array": np.array([1e8])}),
+    ],
+)
+def test_select_field(rsk, spec_type, init_kwargs):
+    """tests/test_skymodel.py:2517-2599."""
+    sky, _ = _twenty(rsk, spec_type, init_kwargs, frame="icrs")
+    lon_range = np.deg2rad([90.0, 240.0])
+    sky2 = sky.copy()
+    sky2.select(lon_range=lon_range)
+    ra = sky2.lon.cpu().numpy()
+    assert ra.size > 0 and np.all(ra >= lon_range[0]) and np.all(ra <= lon_range[1])
+    lat_range = np.deg2rad([-45.0, 45.0])
+    sky2 = sky.copy()
+    sky2.select(lat_range=lat_range)
+    dec = sky2.lat.cpu().numpy()
+    assert dec.size > 0 and np.all(dec >= lat_range[0]) and np.all(dec <= lat_range[1])
+    sky2 = sky.copy()
+    sky2.select(lon_range=lon_range, lat_range=lat_range)
+    ra, dec = sky2.lon.cpu().numpy(), sky2.lat.cpu().numpy()
+    assert np.all(ra >= lon_range[0]) and np.all(ra <= lon_range[1])
+    assert np.all(dec >= lat_range[0]) and np.all(dec <= lat_range[1])
+    # wrapping longitude
+    lon_range = np.deg2rad([270.0, 90.0])
+    sky2 = sky.copy()
+    sky2.select(lon_range=lon_range)
+    ra = sky2.lon.cpu().numpy()
+    assert np.nonzero((ra > lon_range[1]) & (ra < lon_range[0]))[0].size == 0
+    full = sky.lon.cpu().numpy()
+    assert ra.size == np.count_nonzero((full >= lon_range[0]) | (full <= lon_range[1]))
+
+
+@pytest.mark.gpu
+def test_select_field_error(rsk):
+    """tests/test_skymodel.py:2602-2651 (type errors need astropy's Latitude / Longitude classes: mimicked)."""
+    sky, _ = _twenty(rsk, "flat", {"reference_frequency": np.ones(20) * 200e6})
+
+    class Longitude(np.ndarray):
+        pass
+
+    class Latitude(np.ndarray):
+        pass
+
+    lon_range = np.deg2rad([90.0, 240.0]).view(Longitude)
+    lat_range = np.deg2rad([-45.0, 45.0]).view(Latitude)
+    with pytest.raises(TypeError, match="lat_range must be an astropy Latitude object."):
+        sky.select(lat_range=lon_range)
+    with pytest.raises(ValueError, match="lat_range must be 2 element range with the second component larger than the first."):
+        sky.select(lat_range=lat_range[0:1])
+    with pytest.raises(ValueError, match="lat_range must be 2 element range with the second component larger than the first."):
+        sky.select(lat_range=np.array([lat_range[1], lat_range[0]]))
+    with pytest.raises(TypeError, match="lon_range must be an astropy Longitude object."):
+        sky.select(lon_range=lat_range)
+    with pytest.raises(ValueError, match="lon_range must be 2 element range."):
+        sky.select(lon_range=lon_range[0:1])
+    sky.select(lat_range=lat_range)
+    with pytest.raises(ValueError, match="Select would result in an empty object."):
+        sky.select(lat_range=np.deg2rad([-90.0, -75.0]))
+
+
+def _gmst06(jd_ut1, jd_tt):
+    """Greenwich mean sidereal time, IAU 2006 (eraGmst06): what Time.sidereal_time("mean") is built on."""
+    t = (jd_tt - E.DJ00) / E.DJC
+    poly = 0.014506 + (4612.156534 + (1.3915817 + (-0.00000044 + (-0.000029956 - 0.0000000368 * t) * t) * t) * t) * t
+    return E.anp(E.era00(jd_ut1, 0.0) + poly * E.DAS2R)
+
+
+@pytest.mark.gpu
+def test_circumpolar_nonrising(rsk, site):
+    """tests/test_skymodel.py:2661-2740: cut_nonrising, the rise/set LST coarse cut against 100 position updates,
+    circumpolar / never-rising sets against tan(lat) tan(dec)."""
+    time, loc = site
+    ntimes, nras, ndecs = 100, 20, 20
+    nsrcs = nras * ndecs
+    lon_deg = np.rad2deg(loc.lon)
+    ra = np.linspace(lon_deg - 90, lon_deg + 90, nras)
+    dec = np.linspace(-90, 90, ndecs)
+    ra, dec = map(np.ndarray.flatten, np.meshgrid(ra, dec))
+    ra, dec = np.deg2rad(np.mod(ra, 360.0)), np.deg2rad(dec)
+    names = np.array([f"src{i}" for i in range(nsrcs)])
+    st = np.zeros((4, 1, nsrcs)); st[0] = 1.0
+    sky = rsk.SkyModel(name=names, ra=ra, dec=dec, frame="icrs", stokes=st, spectral_type="flat")
+    sky2 = sky.cut_nonrising(loc.lat, inplace=False)
+    sky3 = sky.copy()
+    sky3.cut_nonrising(loc.lat)
+    _assert_same_model(sky2, sky3)
+    nonrising = np.array([sky.name[i] not in sky2.name for i in range(nsrcs)])
+    sky2.calculate_rise_set_lsts(loc.lat)
+    rise, sett = sky2._rise_lst.cpu().numpy(), sky2._set_lst.cpu().numpy()
+    r_ref, s_ref = SEL.rise_set_lsts(sky2.lon.cpu().numpy(), sky2.lat.cpu().numpy(), loc.lat)
+    assert np.allclose(rise, r_ref, rtol=0, atol=1e-13, equal_nan=True)
+    assert np.allclose(sett, s_ref, rtol=0, atol=1e-13, equal_nan=True)
+    is_below = np.zeros(nsrcs, dtype=bool)
+    is_below[nonrising] = True
+    alts = []
+    for ti in range(ntimes):
+        t = time + ti / (ntimes - 1.0)
+        sky.update_positions(t, loc)
+        alt = sky.alt_az[0].cpu().numpy()
+        alts.append(alt)
+        jd_utc = t.jd1 + t.jd2
+        lst = E.anp(_gmst06(jd_utc, jd_utc + 67.184 / 86400.0) + loc.lon)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            dt0 = lst - rise
+            dt1 = sett - rise
+            dt0[dt0 < 0] += 2 * np.pi
+            dt1[dt1 < 0] += 2 * np.pi
+            is_below[~nonrising] = dt0 > dt1
+        assert np.all(alt[is_below] < 0.0)
+    alts = np.array(alts)
+    nonrising_test = np.where(np.all(alts < 0, axis=0))[0]
+    circumpolar_test = np.where(np.all(alts > 0, axis=0))[0]
+    tans = np.tan(loc.lat) * np.tan(dec)
+    assert np.array_equal(np.where(tans > 1)[0], circumpolar_test)
+    assert np.array_equal(np.where(tans < -1)[0], nonrising_test)
+    assert np.array_equal(np.where(nonrising)[0], nonrising_test)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["point", "healpix_ring", "healpix_nested_subset"])
+def test_select_matches_oracle_random(rsk, kind):
+    """Random catalogues with NaNs and negative fluxes, random criteria: same index list as the oracle, and every
+    array is the numpy fancy index of the original."""
+    import torch
+
+    rng = np.random.default_rng(11)
+    nf = 7
+    fa = np.sort(rng.uniform(100e6, 200e6, nf))
+    if kind == "point":
+        n = 20011
+        lon, lat = rng.uniform(0, 2 * np.pi, n), np.arcsin(rng.uniform(-1, 1, n))
+        coords = dict(ra=lon, dec=lat, frame="icrs")
+    else:
+        nside = 32
+        nested = kind.endswith("subset")
+        pix = np.sort(rng.choice(12 * nside * nside, 9000, replace=False)) if nested else np.arange(12 * nside * nside)
+        n = pix.size
+        lon, lat = hp.healpix_to_lonlat(nside, pix, nested=nested)
+        coords = dict(nside=nside, hpx_order="nested" if nested else "ring", hpx_frame="icrs",
+                      hpx_inds=pix if nested else None)
+    st = rng.normal(1.0, 1.0, (4, nf, n))
+    st[0][rng.random((nf, n)) < 0.02] = np.nan
+    st[2][rng.random((nf, n)) < 0.01] = np.nan
+    st[:, :, rng.choice(n, 50, replace=False)] = np.nan
+    err = rng.random((4, nf, n))
+    cases = [
+        dict(non_nan="any"),
+        dict(non_nan="all", non_negative=True),
+        dict(lat_range=np.array([-0.3, 0.9])),
+        dict(lon_range=np.array([1.0, 4.0]), min_brightness=0.1),
+        dict(lon_range=np.array([5.5, 0.7]), max_brightness=2.5, brightness_freq_range=np.array([fa[1], fa[4]])),
+        dict(component_inds=rng.integers(0, n, 5000), lat_range=np.array([-1.0, 0.2])),
+        dict(component_inds=rng.integers(0, n, 5000), lon_range=np.array([6.0, 0.5]), non_negative=True),
+        dict(component_inds=rng.permutation(n)[: n // 2], min_brightness=-0.5, max_brightness=3.0, non_nan="all",
+             lat_range=np.array([-1.2, 1.2]), lon_range=np.array([0.2, 6.0])),
+    ]
+    for kw in cases:
+        sky = rsk.SkyModel(stokes=st, spectral_type="full", freq_array=fa, stokes_error=err, **coords)
+        want = SEL.select_indices(lon, lat, st, spectral_type="full", freq_array=fa, **kw)
+        sky.select(**kw)
+        assert sky.Ncomponents == want.size, kw
+        assert np.array_equal(sky.stokes.cpu().numpy(), st[..., want], equal_nan=True), kw
+        assert np.array_equal(sky.stokes_error.cpu().numpy(), err[..., want]), kw
+        glon, glat = (x.cpu().numpy() for x in sky.get_lon_lat())
+        assert np.abs(glon - lon[want]).max() < 1e-14 and np.abs(glat - lat[want]).max() < 1e-14, kw
+        if kind != "point":
+            assert torch.equal(sky.hpx_inds.cpu(), torch.as_tensor(pix[want])), kw
+
+
+@pytest.mark.gpu
+def test_select_large_and_abi_errors(rsk):
+    """A million components through the three kernels, checked against torch boolean indexing; argument errors."""
+    import torch
+    from pyradiosky_b200 import _lib
+
+    rng = np.random.default_rng(12)
+    n, nf = 1_000_003, 3
+    lon, lat = rng.uniform(0, 2 * np.pi, n), np.arcsin(rng.uniform(-1, 1, n))
+    st = np.abs(rng.normal(1.0, 1.0, (4, nf, n)))
+    sky = rsk.SkyModel(ra=lon, dec=lat, stokes=st, spectral_type="full", freq_array=np.array([1e8, 1.1e8, 1.2e8]))
+    keep = (sky.lat >= -0.5) & (sky.lat <= 0.7) & (sky.stokes[0].min(dim=0).values >= 0.3)
+    ref = sky.stokes[..., keep].clone()
+    sky.select(lat_range=np.array([-0.5, 0.7]), min_brightness=0.3)
+    assert torch.equal(sky.stokes, ref) and sky.Ncomponents == int(keep.sum())
+    lib = _lib.load()
+    sel = _lib.RskSelect()
+    sel.non_nan = 5
+    buf = torch.zeros(16, dtype=torch.uint8, device=sky.device)
+    assert lib.rsk_select_mask(None, _lib.ptr(sky.stokes), 1, 16, None, 16, ctypes.byref(sel), _lib.ptr(buf), None) == -3
+    sel.non_nan = 1
+    assert lib.rsk_select_mask(None, None, 1, 16, None, 16, ctypes.byref(sel), _lib.ptr(buf), None) == -1
+    assert lib.rsk_select_mask(None, None, 1, 16, None, 16, None, _lib.ptr(buf), None) == -1
+    sel.non_nan, sel.use_lat = 0, 1
+    assert lib.rsk_select_mask(None, None, 1, 16, None, 16, ctypes.byref(sel), _lib.ptr(buf), None) == -1  # no coords
+    assert lib.rsk_select_mask(None, None, 1, 16, None, -1, ctypes.byref(sel), _lib.ptr(buf), None) == -2
+    idx = torch.zeros(4, dtype=torch.int64, device=sky.device)
+    assert lib.rsk_gather_rows(_lib.ptr(sky.stokes), 1, 16, _lib.ptr(idx), 4, 4, _lib.ptr(buf), None) == -3
+    assert lib.rsk_gather_rows(None, 1, 16, _lib.ptr(idx), 4, 8, _lib.ptr(buf), None) == -1
+    assert lib.rsk_gather_rows(None, 0, 16, None, 4, 8, None, None) == 0
+    assert lib.rsk_rise_set_lsts(None, 4, 0.1, 0.0, None, None, None) == -1
