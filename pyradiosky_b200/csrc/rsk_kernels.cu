@@ -318,21 +318,36 @@ __global__ void __launch_bounds__(kThreads) k_select_mask(const CoordSrc cs, con
   if (k && (p.use_min || p.use_max || p.non_negative || p.non_nan)) {
     double mn = INFINITY, mx = -INFINITY;
     bool nan_used = false, any_neg = false, any_nan = false, all_nan = true;
-    for (int64_t f = 0; f < nf; ++f) {
-      const double si = __ldg(stokes + f * n + i);
-      if (p.use_min || p.use_max) {
-        if (!p.freq_use || __ldg(p.freq_use + f)) {
-          nan_used = nan_used || isnan(si);
-          mn = si < mn ? si : mn;
-          mx = si > mx ? si : mx;
+    const bool cuts = p.use_min || p.use_max;
+    const double* __restrict__ sp = stokes + i;
+    // four channels per trip, every load of the trip issued before the first use (the planes are nf * n apart, so
+    // each load is its own coalesced stream; what limits this kernel is the number of loads in flight)
+    for (int64_t f0 = 0; f0 < nf; f0 += 4) {
+      double si[4], sq[4], su[4], sv[4];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const int64_t f = f0 + d < nf ? f0 + d : nf - 1;  // (the tail repeats the last channel: idempotent tests)
+        si[d] = __ldg(sp + f * n);
+        if (p.non_nan) {
+          sq[d] = __ldg(sp + (nf + f) * n);
+          su[d] = __ldg(sp + (2 * nf + f) * n);
+          sv[d] = __ldg(sp + (3 * nf + f) * n);
         }
       }
-      any_neg = any_neg || si < 0.0;
-      if (p.non_nan) {
-        bool nanf = isnan(si);
-        for (int q = 1; q < 4; ++q) nanf = nanf || isnan(__ldg(stokes + (q * nf + f) * n + i));
-        any_nan = any_nan || nanf;
-        all_nan = all_nan && nanf;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const int64_t f = f0 + d < nf ? f0 + d : nf - 1;
+        if (cuts && (!p.freq_use || __ldg(p.freq_use + f))) {
+          nan_used = nan_used || isnan(si[d]);
+          mn = si[d] < mn ? si[d] : mn;
+          mx = si[d] > mx ? si[d] : mx;
+        }
+        any_neg = any_neg || si[d] < 0.0;
+        if (p.non_nan) {
+          const bool nanf = isnan(si[d]) || isnan(sq[d]) || isnan(su[d]) || isnan(sv[d]);
+          any_nan = any_nan || nanf;
+          all_nan = all_nan && nanf;
+        }
       }
     }
     if (p.use_min) k = k && !nan_used && mn >= p.min_brightness;  // np.min(...) >= min (:3096-3098)

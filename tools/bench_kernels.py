@@ -169,6 +169,43 @@ def main():
         sb._subband_operator("cubic")
 
     rec("k_spline_coefficients 1M x 20 (once per catalogue)", timeit(coef, reps=3), 2 * 640 * n, "640 B read + 640 B written per component")
+    del sb, st
+    torch.cuda.empty_cache()
+
+    # --- select: predicate mask, compaction, gather on 4M x 20 subbands (GLEAM-like, 2.6 GB of Stokes) -----------
+    n, nf = 4_000_000, 20
+    lon = torch.rand(n, dtype=torch.float64, device="cuda") * (2 * np.pi)
+    lat = torch.asin(torch.rand(n, dtype=torch.float64, device="cuda") * 2 - 1)
+    st = torch.rand((4, nf, n), dtype=torch.float64, device="cuda") + 0.01
+    sky = SkyModel(lon=lon, lat=lat, stokes=st, spectral_type="subband", freq_array=bands)
+    sel = _lib.RskSelect()
+    sel.use_lat, sel.lat_lo, sel.lat_hi = 1, -0.6, 0.9
+    sel.use_min, sel.min_brightness, sel.non_nan, sel.non_negative = 1, 0.02, 1, 1
+    keep = torch.empty(n, dtype=torch.uint8, device="cuda")
+    coords = sky._coords_struct()
+    import ctypes
+
+    rec("k_select_mask 4M x 20 (lat range, min brightness, non_nan any, non_negative)",
+        timeit(lambda: sky._call("rsk_select_mask", ctypes.byref(coords), _lib.ptr(st), nf, n, None, n, ctypes.byref(sel),
+                                 _lib.ptr(keep))), n * (4 * nf * 8 + 8 + 1), "all four Stokes planes + latitude read, 1 B written")
+    idx, m = sky._compact_mask(keep)
+    idx = idx[:m].contiguous()
+    outbuf = torch.empty((4, nf, m), dtype=torch.float64, device="cuda")
+    rec(f"k_gather_rows stokes 4M -> {m} x 80 rows",
+        timeit(lambda: sky._call("rsk_gather_rows", _lib.ptr(st), 4 * nf, n, _lib.ptr(idx), m, 8, _lib.ptr(outbuf))),
+        m * (4 * nf * 16 + 8), "8 B read + 8 B written per kept element, index read once")
+    rise = torch.empty(n, dtype=torch.float64, device="cuda")
+    sett = torch.empty(n, dtype=torch.float64, device="cuda")
+    rec("k_rise_set 4M", timeit(lambda: sky._call("rsk_rise_set_lsts", ctypes.byref(coords), n, -0.536, 0.04364,
+                                                    _lib.ptr(rise), _lib.ptr(sett))), n * 32, "16 B read + 16 B written")
+
+    def whole():
+        s2 = SkyModel.__new__(SkyModel)
+        s2.__dict__.update(sky.__dict__)
+        s2.select(lat_range=np.array([-0.6, 0.9]), min_brightness=0.02, non_nan="any", non_negative=True)
+
+    rec("SkyModel.select end to end 4M x 20 (mask + compaction + all gathers + host sync)", timeit(whole, reps=3),
+        n * (4 * nf * 8 + 9) + m * (4 * nf * 16 + 8 + 32), "sum of the above")
     print(json.dumps(out, indent=1))
 
 
