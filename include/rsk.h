@@ -276,6 +276,13 @@ int rsk_select_mask(const RskCoords* coords, const double* stokes /* [4][nf][n] 
 int rsk_gather_rows(const void* in /* [nrows][n_in] */, int64_t nrows, int64_t n_in, const int64_t* idx /* [n_out] */,
                     int64_t n_out, int elem_bytes, void* out /* [nrows][n_out] */, void* stream);
 
+/* out[r] = a[r] followed by b[r] for nrows rows: np.concatenate along the component axis, as SkyModel.concat applies
+ * it to every Ncomponents-shaped parameter (skymodel.py:2905-2999).  a or b may be NULL: that side is then filled
+ * with NaN (elem_bytes = 8; the reference's fill for a numeric parameter only one object has, :2960-2999) or 0
+ * (elem_bytes = 1). */
+int rsk_concat_rows(const void* a /* [nrows][n_a] or NULL */, int64_t n_a, const void* b /* [nrows][n_b] or NULL */,
+                    int64_t n_b, int64_t nrows, int elem_bytes, void* out /* [nrows][n_a + n_b] */, void* stream);
+
 /* SkyModel.calculate_rise_set_lsts (skymodel.py:3284-3329): rise = lon - acos(-tan(tel_lat) tan(lat)) - buffer,
  * set = lon + acos(...) + buffer, each wrapped once into [0, 2 pi]; NaN for components that never rise or never set. */
 int rsk_rise_set_lsts(const RskCoords* coords, int64_t n, double tel_lat, double horizon_buffer,

@@ -378,6 +378,26 @@ __global__ void __launch_bounds__(kThreads) k_gather_rows(const T* __restrict__ 
   }
 }
 
+// out[r] = a[r] followed by b[r]; a missing side (NULL) is filled with ``fill`` (NaN for the numeric parameters
+// only one of two concatenated objects has, skymodel.py:2960-2999)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_concat_rows(const T* __restrict__ a, const int64_t n_a,
+                                                          const T* __restrict__ b, const int64_t n_b,
+                                                          const int64_t nrows, const T fill, T* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t n = n_a + n_b;
+  if (j >= n) return;
+  for (int64_t r = blockIdx.y; r < nrows; r += gridDim.y) {
+    T v = fill;
+    if (j < n_a) {
+      if (a) v = __ldg(a + r * n_a + j);
+    } else if (b) {
+      v = __ldg(b + r * n_b + (j - n_a));
+    }
+    out[r * n + j] = v;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) k_rise_set(const CoordSrc cs, const int64_t n, const double tan_tel,
                                                        const double buff, double* __restrict__ rise,
                                                        double* __restrict__ set) {
@@ -1523,6 +1543,24 @@ int rsk_gather_rows(const void* in, int64_t nrows, int64_t n_in, const int64_t* 
     k_gather_rows<double, kRpt><<<grid, kThreads, 0, st>>>((const double*)in, nrows, n_in, idx, n_out, (double*)out);
   else
     k_gather_rows<uint8_t, kRpt><<<grid, kThreads, 0, st>>>((const uint8_t*)in, nrows, n_in, idx, n_out, (uint8_t*)out);
+  return launch_status();
+}
+
+int rsk_concat_rows(const void* a, int64_t n_a, const void* b, int64_t n_b, int64_t nrows, int elem_bytes, void* out,
+                    void* stream) {
+  if (nrows < 0 || n_a < 0 || n_b < 0) return RSK_ERR_SIZE;
+  if (elem_bytes != 1 && elem_bytes != 8) return RSK_ERR_MODE;
+  if (nrows == 0 || n_a + n_b == 0) return RSK_OK;
+  if (!out) return RSK_ERR_NULL;
+  if ((n_a + n_b + kThreads - 1) / kThreads > 0x7fffffffll) return RSK_ERR_SIZE;
+  const dim3 grid(blocks_for(n_a + n_b), (unsigned)std::min<int64_t>(nrows, 65535));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (elem_bytes == 8)
+    k_concat_rows<double><<<grid, kThreads, 0, st>>>((const double*)a, n_a, (const double*)b, n_b, nrows, (double)NAN,
+                                                     (double*)out);
+  else
+    k_concat_rows<uint8_t><<<grid, kThreads, 0, st>>>((const uint8_t*)a, n_a, (const uint8_t*)b, n_b, nrows, (uint8_t)0,
+                                                      (uint8_t*)out);
   return launch_status();
 }
 

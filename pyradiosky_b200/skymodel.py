@@ -892,6 +892,185 @@ class SkyModel:
             skyobj.extended_model_group = None
         return None if inplace else skyobj
 
+    # ------------------------------------------------------------------------------------------
+    # concat (skymodel.py:2714-3010)
+    # ------------------------------------------------------------------------------------------
+    def _cat(self, a, na, b, nb):
+        """np.concatenate((a, b), axis=-1) for CUDA tensors; a missing side is filled with NaN (rsk_concat_rows)."""
+        ref = a if a is not None else b
+        out = torch.empty(ref.shape[:-1] + (na + nb,), dtype=ref.dtype, device=self.device)
+        nrows = ref.numel() // max(ref.shape[-1], 1)
+        a = None if a is None else a.contiguous()
+        b = None if b is None else b.contiguous()
+        self._call("rsk_concat_rows", _lib.ptr(a), na, _lib.ptr(b), nb, nrows, ref.element_size(), _lib.ptr(out))
+        return out
+
+    @staticmethod
+    def _histories_match(h1, h2):
+        # pyuvdata history_utils._check_histories: equal up to white space
+        return h1 == h2 or "".join((h1 or "").split()) == "".join((h2 or "").split())
+
+    @staticmethod
+    def _history_addition(h1, h2):
+        """The words of ``h2`` that do not occur in ``h1``, in order (pyuvdata's _combine_history_addition)."""
+        have = " " + (h1 or "") + " "
+        words = [w for w in (h2 or "").split(" ") if " " + w + " " not in have]
+        return " ".join(words) if words else None
+
+    def concat(self, other, clear_time_position=True, verbose_history=False, inplace=True, run_check=True,
+               check_extra=True, run_check_acceptability=True):
+        """Combine two SkyModel objects along source axis (skymodel.py:2714-3010).
+
+        Same compatibility rules, warnings, NaN / empty-string fills and history handling as the reference; every
+        per-component array is concatenated on the GPU.  Both objects must live on the same device and hold Stokes
+        values in the same unit and coordinates in the same frame (the reference converts through astropy there).
+        The ``run_check*`` arguments are accepted and ignored."""
+        this = self if inplace else self.copy()
+        if not isinstance(other, SkyModel):
+            raise ValueError("Only SkyModel (or subclass) objects can be added to a SkyModel (or subclass) object")
+        if other.device != this.device:
+            raise ValueError("Both objects must be on the same device to be combined.")
+
+        def mismatch(name, time_pos=False):
+            msg = "UVParameter " + name + " does not match. Cannot combine objects."
+            if time_pos:
+                msg += (" Set the clear_time_position keyword to True to set this and other time and position "
+                        "dependent metadata to None to allow the concatenation to proceed. Time and position dependent "
+                        "metadata can be set afterwards using the update_positions method.")
+            raise ValueError(msg)
+
+        def same_array(x, y):
+            if x is None or y is None:
+                return x is None and y is None
+            x, y = np.asarray(x), np.asarray(y)
+            return x.shape == y.shape and bool(np.allclose(x, y, rtol=0, atol=this.freq_tol))
+
+        if this.component_type != other.component_type:
+            mismatch("component_type")
+        if this.spectral_type != other.spectral_type:
+            mismatch("spectral_type")
+        if this.spectral_type in ("subband", "full") and not same_array(this.freq_array, other.freq_array):
+            mismatch("freq_array")
+        if this.spectral_type == "subband" and not same_array(this.freq_edge_array, other.freq_edge_array):
+            mismatch("freq_edge_array")
+        if this.component_type == "healpix":
+            if this.nside != other.nside:
+                mismatch("nside")
+            if this.hpx_order != other.hpx_order:
+                mismatch("hpx_order")
+        if this.stokes_unit != other.stokes_unit:
+            mismatch("stokes")
+        if this.frame != other.frame or this.equinox != other.equinox:
+            mismatch("skycoord" if this.component_type == "point" else "hpx_frame")
+        if clear_time_position:
+            this.clear_time_position_specific_params()
+            other.clear_time_position_specific_params()
+        else:
+            if this.time != other.time:
+                mismatch("time", True)
+            if this.telescope_location != other.telescope_location:
+                mismatch("telescope_location", True)
+            for name in ("alt_az", "pos_lmn", "above_horizon"):
+                x, y = getattr(this, name), getattr(other, name)
+                if (x is None) != (y is None) or (x is not None and (x.shape != y.shape or not torch.equal(x, y))):
+                    mismatch(name, True)
+        if this.extra_columns is not None or other.extra_columns is not None:
+            if this.extra_columns is None or other.extra_columns is None:
+                raise ValueError("One object has extra_columns and the other does not. Cannot combine objects.")
+            left, right = tuple(this.extra_columns), tuple(other.extra_columns)
+            if set(left) != set(right):
+                raise ValueError(
+                    "Both objects have extra_columns but the column names do not match. Cannot combine objects. "
+                    f"Left object columns are: {left}. Right object columns are: {right}. Unmatched columns are "
+                    f"{set(left) - set(right)}")
+            for name in left:
+                if np.asarray(this.extra_columns[name]).dtype.type != np.asarray(other.extra_columns[name]).dtype.type:
+                    raise ValueError(f"Both objects have extra_columns but the dtypes for column {name} do not match. "
+                                     "Cannot combine objects.")
+            this.extra_columns = {k: np.concatenate((np.asarray(this.extra_columns[k]), np.asarray(other.extra_columns[k])))
+                                  for k in left}
+        na, nb = this.Ncomponents, other.Ncomponents
+        # check for non-overlapping names or healpix inds (:2861-2875)
+        if this.component_type == "healpix":
+            pa = this.hpx_inds if this.hpx_inds is not None else torch.arange(
+                this.hpx_first, this.hpx_first + na, dtype=torch.int64, device=this.device)
+            pb = other.hpx_inds if other.hpx_inds is not None else torch.arange(
+                other.hpx_first, other.hpx_first + nb, dtype=torch.int64, device=this.device)
+            if bool(torch.isin(pa, pb).any()):
+                raise ValueError("The two SkyModel objects contain overlapping Healpix pixels.")
+            this.hpx_inds = torch.cat((pa, pb))
+            this.hpx_first = 0
+            if this.name is not None and other.name is not None:
+                this.name = np.concatenate((this.name, other.name))
+            elif this.name is not None or other.name is not None:
+                warnings.warn("Only one object has name values, setting name to None on final object.")
+                this.name = None
+        else:
+            if this.name is not None and other.name is not None:
+                if np.intersect1d(this.name, other.name).size > 0:
+                    raise ValueError("The two SkyModel objects contain components with the same name.")
+                this.name = np.concatenate((this.name, other.name))
+            elif this.name is not None or other.name is not None:
+                warnings.warn("Only one object has name values, setting name to None on final object.")
+                this.name = None
+            this.lon = this._cat(this.lon, na, other.lon, nb)
+            this.lat = this._cat(this.lat, na, other.lat, nb)
+        this.stokes = this._cat(this.stokes, na, other.stokes, nb)
+        had_fc = this.frame_coherency is not None, other.frame_coherency is not None
+        this.frame_coherency = None
+        if had_fc[0] != had_fc[1]:
+            warnings.warn("Only one object has frame_coherency values, setting frame_coherency to None on final object. "
+                          "Use `calc_frame_coherency` to recalculate them.")
+        numeric = ["stokes_error", "beam_amp", "reference_frequency", "spectral_index"]
+        for param in numeric:
+            x, y = getattr(this, param), getattr(other, param)
+            if x is None and y is None:
+                continue
+            if x is None or y is None:
+                warnings.warn(f"Only one object has {param} values. Filling missing values with NaNs.")
+            setattr(this, param, this._cat(x, na, y, nb))
+        x, y = this.extended_model_group, other.extended_model_group
+        if x is not None or y is not None:
+            if x is None or y is None:
+                warnings.warn("Only one object has extended_model_group values. Filling missing values with empty strings.")
+                ref = x if x is not None else y
+                x = np.full(na, "", dtype=ref.dtype) if x is None else x
+                y = np.full(nb, "", dtype=ref.dtype) if y is None else y
+            this.extended_model_group = np.concatenate((x, y))
+        this._polarized_mask = this._cat(this._polarized_mask, na, other._polarized_mask, nb)
+        this._n_polarized = this._n_polarized + other._n_polarized
+        if not clear_time_position:
+            for name in ("alt_az", "pos_lmn"):
+                if getattr(this, name) is not None:
+                    setattr(this, name, this._cat(getattr(this, name), na, getattr(other, name), nb))
+            if this.above_horizon is not None:
+                this.above_horizon = this._cat(this.above_horizon.view(torch.uint8), na,
+                                               other.above_horizon.view(torch.uint8), nb).view(torch.bool)
+        this.Ncomponents = na + nb
+        this._rot_key = None
+        for cache in ("_rot", "_subband_cache", "_nan_group_cache", "_nan_cache", "_staging", "_graph", "_rise_lst",
+                      "_set_lst"):
+            this.__dict__.pop(cache, None)
+        if all(had_fc):
+            this.calc_frame_coherency()
+        # filename (pyuvdata utils._combine_filenames) and history (:3001-3021)
+        f1 = this.filename if this.filename is None or isinstance(this.filename, (list, tuple)) else [this.filename]
+        f2 = other.filename if other.filename is None or isinstance(other.filename, (list, tuple)) else [other.filename]
+        if f1 is not None and f2 is not None:
+            this.filename = sorted(set(f1).union(set(f2)))
+        elif f2 is not None:
+            this.filename = list(f2)
+        histories_match = this._histories_match(this.history, other.history)
+        this.history = (this.history or "") + " Combined skymodels along the component axis using pyradiosky."
+        if not histories_match:
+            if verbose_history:
+                this.history += " Next object history follows. " + (other.history or "")
+            else:
+                extra = this._history_addition(this.history, other.history)
+                if extra is not None:
+                    this.history += " Unique part of next object history follows. " + extra
+        return None if inplace else this
+
     def calculate_rise_set_lsts(self, telescope_latitude, horizon_buffer=0.04364):
         """Calculate the rise & set LSTs given a telescope latitude (skymodel.py:3284-3329).
 

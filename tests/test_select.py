@@ -484,3 +484,204 @@ def test_select_large_and_abi_errors(rsk):
     assert lib.rsk_gather_rows(None, 1, 16, _lib.ptr(idx), 4, 8, _lib.ptr(buf), None) == -1
     assert lib.rsk_gather_rows(None, 0, 16, None, 4, 8, None, None) == 0
     assert lib.rsk_rise_set_lsts(None, 4, 0.1, 0.0, None, None, None) == -1
+
+
+# ---------------------------------------------------------------------------------------------------
+# concat (skymodel.py:2714-3010): select into thirds, concatenate, get the original back
+# ---------------------------------------------------------------------------------------------------
+GSM = os.path.join(ROOT, "tests", "golden", "ref_fixture_gsm_icrs_nside8.skyh5")
+
+
+def _full_model(rsk, comp_type, spec_type="subband"):
+    import torch
+
+    if comp_type == "point":
+        sky, lon, lat, st, fa = _gleam_model(rsk, with_nans=False)
+        if spec_type == "flat":
+            sky = rsk.SkyModel(name=sky.name, ra=lon, dec=lat, frame="fk5", stokes=st[:, 9:10, :], spectral_type="flat",
+                               history="read from the fixture.")
+        elif spec_type == "spectral_index":
+            sky = rsk.SkyModel(name=sky.name, ra=lon, dec=lat, frame="fk5", stokes=st[:, 9:10, :],
+                               spectral_type="spectral_index", reference_frequency=np.full(50, 200e6),
+                               spectral_index=np.linspace(-1.2, 0.2, 50), history="read from the fixture.")
+        sky.filename = ["gleam_50srcs.vot"]
+        sky.select(non_negative=True, non_nan="all")
+    else:
+        sky = rsk.SkyModel.from_skyh5(GSM)
+        sky.filename = ["healpix_disk.skyh5"]
+    return sky
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("comp_type, spec_type", [("point", "subband"), ("point", "spectral_index"), ("point", "flat"),
+                                                  ("healpix", "full")])
+def test_concat(rsk, comp_type, spec_type):
+    """tests/test_skymodel.py:1629-1722."""
+    import torch
+
+    full = _full_model(rsk, comp_type, spec_type)
+    n = full.Ncomponents
+    full.extended_model_group = np.array([f"g{k}" for k in range(n)]) if full.name is None else full.name.copy()
+    full.beam_amp = torch.ones((4, full.Nfreqs, n), dtype=torch.float64, device=full.device)
+    full.calc_frame_coherency()
+    full.extra_columns = {"foo": np.arange(n, dtype=float), "bar": np.arange(n, dtype=int),
+                          "gah": np.array(["gah " + str(i) for i in range(n)])}
+    s1 = full.select(component_inds=np.arange(n // 3), inplace=False)
+    s2 = full.select(component_inds=np.arange(n // 3, 2 * n // 3), inplace=False)
+    s3 = full.select(component_inds=np.arange(2 * n // 3, n), inplace=False)
+    new = s1.concat(s2, inplace=False)
+    assert new.Ncomponents == s1.Ncomponents + s2.Ncomponents and s1.Ncomponents == n // 3
+    new.concat(s3)
+    assert new.filename == full.filename
+    expected = (full.history + "  Downselected to specific components using pyradiosky."
+                + " Combined skymodels along the component axis using pyradiosky."
+                + " Combined skymodels along the component axis using pyradiosky.")
+    assert new.history != full.history and rsk.SkyModel._histories_match(new.history, expected)
+    _assert_same_model(new, full)
+    assert torch.equal(new.frame_coherency, full.frame_coherency)
+    assert np.array_equal(new.extended_model_group, full.extended_model_group)
+    assert torch.equal(new._polarized_mask, full._polarized_mask) and new._n_polarized == full._n_polarized
+    # the combined object works on the hot path exactly like the original
+    loc = rsk.EarthLocation.from_dms((-30, 43, 17.5), (21, 25, 41.9), 1073.0)
+    t = rsk.Time.from_utc("2015-03-01 00:00:00")
+    freqs = np.array([110e6, 150e6]) if spec_type != "full" else None
+    outs = []
+    for obj in (new, full):
+        obj.update_positions(t, loc)
+        outs.append(obj.coherency_calc(freqs=freqs) if freqs is not None else obj.coherency_calc())
+    assert torch.equal(outs[0], outs[1])
+    # history handling
+    s2.history += " testing the history."
+    new = s1.concat(s2, inplace=False, run_check=False)
+    new.concat(s3)
+    expected = (full.history + "  Downselected to specific components using pyradiosky."
+                + " Combined skymodels along the component axis using pyradiosky. "
+                + "Unique part of next object history follows.  testing history."
+                + " Combined skymodels along the component axis using pyradiosky.")
+    assert rsk.SkyModel._histories_match(new.history, expected), new.history
+    new = s1.concat(s2, inplace=False, verbose_history=True)
+    new.concat(s3, verbose_history=True)
+    expected = (full.history + "  Downselected to specific components using pyradiosky."
+                + " Combined skymodels along the component axis using pyradiosky. "
+                + "Next object history follows. " + s2.history
+                + " Combined skymodels along the component axis using pyradiosky. "
+                + "Next object history follows. " + s3.history)
+    assert rsk.SkyModel._histories_match(new.history, expected)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("param", ["reference_frequency", "extended_model_group", "beam_amp", "stokes_error", "name",
+                                   "spectral_index", "frame_coherency"])
+def test_concat_optional_params(rsk, param):
+    """tests/test_skymodel.py:1725-1896: a parameter only one object has is filled with NaNs / empty strings (or dropped,
+    for name and frame_coherency), with the reference's warning."""
+    import torch
+
+    full = _full_model(rsk, "healpix" if param == "name" else "point", "flat")
+    n = full.Ncomponents
+    dev = full.device
+    if param == "name":
+        full.name = np.array(["hpx" + str(i) for i in range(n)])
+    elif param == "extended_model_group":
+        full.extended_model_group = full.name.copy()
+    elif param == "beam_amp":
+        full.beam_amp = torch.ones((4, full.Nfreqs, n), dtype=torch.float64, device=dev)
+    elif param == "stokes_error":
+        full.stokes_error = full.stokes * 0.05
+    elif param == "spectral_index":
+        full.spectral_index = torch.full((n,), -0.7, dtype=torch.float64, device=dev)
+    elif param == "reference_frequency":
+        full.reference_frequency = torch.full((n,), 2e8, dtype=torch.float64, device=dev)
+    elif param == "frame_coherency":
+        full.calc_frame_coherency()
+    assert getattr(full, param) is not None
+    base = full.filename[0]
+    for drop_first in (True, False):
+        s1 = full.select(component_inds=np.arange(n // 2), inplace=False)
+        s1.filename = [base + "_1"]
+        s2 = full.select(component_inds=np.arange(n // 2, n), inplace=False)
+        s2.filename = [base + "_2"]
+        new = s1.concat(s2, inplace=False)
+        _assert_same_model(new, full)
+        setattr(s1 if drop_first else s2, param, None)
+        with pytest.warns(UserWarning, match=f"Only one object has {param}"):
+            new = s1.concat(s2, inplace=False)
+        assert new.filename == [base + "_1", base + "_2"]
+        got = getattr(new, param)
+        if param in ("name", "frame_coherency"):
+            assert got is None
+            continue
+        assert got is not None
+        want = getattr(full, param)
+        kept = slice(n // 2, n) if drop_first else slice(0, n // 2)
+        lost = slice(0, n // 2) if drop_first else slice(n // 2, n)
+        if param == "extended_model_group":
+            assert got[kept].tolist() == want[kept].tolist() and np.all(got[lost] == "")
+        else:
+            assert torch.equal(got[..., kept], want[..., kept]) and bool(torch.isnan(got[..., lost]).all())
+        setattr(new, param, want)
+        _assert_same_model(new, full)
+
+
+@pytest.mark.gpu
+def test_concat_errors(rsk, site):
+    """tests/test_skymodel.py:1899-2060."""
+    time, loc = site
+    for comp_type, msg in (("point", "The two SkyModel objects contain components with the same name."),
+                           ("healpix", "The two SkyModel objects contain overlapping Healpix pixels.")):
+        full = _full_model(rsk, comp_type)
+        n = full.Ncomponents
+        s1 = full.select(component_inds=np.arange(n // 2), inplace=False)
+        s2 = full.select(component_inds=np.arange(n // 3, n), inplace=False)
+        with pytest.raises(ValueError, match=msg):
+            s1.concat(s2)
+    sub = _full_model(rsk, "point", "subband")
+    spi = _full_model(rsk, "point", "spectral_index")
+    hpx = _full_model(rsk, "healpix")
+    with pytest.raises(ValueError, match="Only SkyModel"):
+        sub.concat("foo")
+    with pytest.raises(ValueError, match="UVParameter component_type does not match. "):
+        sub.concat(hpx)
+    with pytest.raises(ValueError, match="UVParameter spectral_type does not match. "):
+        sub.concat(spi)
+    n = sub.Ncomponents
+    s1 = sub.select(component_inds=np.arange(n // 2), inplace=False)
+    s2 = sub.select(component_inds=np.arange(n // 2, n), inplace=False)
+    s2.freq_array = s2.freq_array * 2.0
+    with pytest.raises(ValueError, match="UVParameter freq_array does not match. "):
+        s1.concat(s2)
+    m = hpx.Ncomponents
+    h1 = hpx.select(component_inds=np.arange(m // 2), inplace=False)
+    h2 = hpx.select(component_inds=np.arange(m // 2, m), inplace=False)
+    h2.nside = h2.nside * 2
+    with pytest.raises(ValueError, match="UVParameter nside does not match. "):
+        h1.concat(h2)
+    hpx.update_positions(time, loc)
+    h1 = hpx.select(component_inds=np.arange(m // 2), inplace=False)
+    h2 = hpx.select(component_inds=np.arange(m // 2, m), inplace=False)
+    h2.update_positions(time + 1.0, loc)
+    with pytest.raises(ValueError, match="UVParameter time does not match. "):
+        h1.concat(h2, clear_time_position=False)
+    h1.concat(h2, clear_time_position=True)
+    hpx.clear_time_position_specific_params()
+    _assert_same_model(h1, hpx)
+    s1 = sub.select(component_inds=np.arange(n // 2), inplace=False)
+    s2 = sub.select(component_inds=np.arange(n // 2, n), inplace=False)
+    s1.extra_columns = {"foo": np.arange(s1.Ncomponents, dtype=float), "bar": np.arange(s1.Ncomponents, dtype=int)}
+    with pytest.raises(ValueError, match="One object has extra_columns and the other does not. Cannot combine objects."):
+        s1.concat(s2)
+    s2.extra_columns = {"foo": np.arange(s2.Ncomponents, dtype=float), "blech": np.arange(s2.Ncomponents, dtype=int)}
+    with pytest.raises(ValueError, match="Both objects have extra_columns but the column names do not match."):
+        s1.concat(s2)
+    s2.extra_columns = {"foo": np.arange(s2.Ncomponents, dtype=float), "bar": np.arange(s2.Ncomponents, dtype=float)}
+    with pytest.raises(ValueError, match="Both objects have extra_columns but the dtypes for column bar do not match."):
+        s1.concat(s2)
+    # positions kept when both halves were updated for the same time
+    s1 = sub.select(component_inds=np.arange(n // 2), inplace=False)
+    s2 = sub.select(component_inds=np.arange(n // 2, n), inplace=False)
+    for obj in (sub, s1, s2):
+        obj.update_positions(time, loc)
+    with pytest.raises(ValueError, match="UVParameter alt_az does not match. "):
+        s1.concat(s2, clear_time_position=False)  # (arrays of different halves never compare equal, as upstream)
+    lib_rc = __import__("pyradiosky_b200")._lib.load().rsk_concat_rows(None, 1, None, 1, 1, 3, None, None)
+    assert lib_rc == -3
