@@ -283,6 +283,13 @@ int rsk_gather_rows(const void* in /* [nrows][n_in] */, int64_t nrows, int64_t n
 int rsk_concat_rows(const void* a /* [nrows][n_a] or NULL */, int64_t n_a, const void* b /* [nrows][n_b] or NULL */,
                     int64_t n_b, int64_t nrows, int elem_bytes, void* out /* [nrows][n_a + n_b] */, void* stream);
 
+/* SkyModel.transform_to (skymodel.py:1419-1446, astropy SkyCoord.transform_to) between frames related by a fixed
+ * rotation (icrs, fk5(equinox), galactic): unit vector of (lon, lat), times rot (HOST [9], row-major, = the transpose
+ * of the new frame's rsk_frame_to_icrs matrix times the old frame's), back to angles; lon in [0, 2 pi].  In place
+ * (lon_out == lon, lat_out == lat) is allowed. */
+int rsk_rotate_lonlat(const double* lon, const double* lat, int64_t n, const double* rot /* HOST [9] */,
+                      double* lon_out, double* lat_out, void* stream);
+
 /* SkyModel.calculate_rise_set_lsts (skymodel.py:3284-3329): rise = lon - acos(-tan(tel_lat) tan(lat)) - buffer,
  * set = lon + acos(...) + buffer, each wrapped once into [0, 2 pi]; NaN for components that never rise or never set. */
 int rsk_rise_set_lsts(const RskCoords* coords, int64_t n, double tel_lat, double horizon_buffer,

@@ -398,6 +398,28 @@ __global__ void __launch_bounds__(kThreads) k_concat_rows(const T* __restrict__ 
   }
 }
 
+// (lon, lat) -> (lon', lat') under a rotation of the unit sphere: SkyCoord.transform_to between frames that differ by
+// a fixed matrix (icrs, fk5(equinox), galactic), skymodel.py:1419-1446
+struct Rot9 {
+  double m[9];
+};
+__global__ void __launch_bounds__(kThreads) k_rotate_lonlat(const double* __restrict__ lon,
+                                                            const double* __restrict__ lat, const int64_t n,
+                                                            const Rot9 r, double* __restrict__ lon_out,
+                                                            double* __restrict__ lat_out) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  double sl, cl, sb, cb;
+  rsk_sincos(__ldg(lon + i), &sl, &cl);
+  rsk_sincos(__ldg(lat + i), &sb, &cb);
+  const double px = cl * cb, py = sl * cb, pz = sb;
+  const double x = r.m[0] * px + r.m[1] * py + r.m[2] * pz;
+  const double y = r.m[3] * px + r.m[4] * py + r.m[5] * pz;
+  const double z = r.m[6] * px + r.m[7] * py + r.m[8] * pz;
+  lon_out[i] = rsk_azimuth(y, x);  // [0, 2 pi], as astropy's Longitude wraps
+  lat_out[i] = rsk_atan2_t<true>(z, rsk_sqrt(x * x + y * y));
+}
+
 __global__ void __launch_bounds__(kThreads) k_rise_set(const CoordSrc cs, const int64_t n, const double tan_tel,
                                                        const double buff, double* __restrict__ rise,
                                                        double* __restrict__ set) {
@@ -1561,6 +1583,17 @@ int rsk_concat_rows(const void* a, int64_t n_a, const void* b, int64_t n_b, int6
   else
     k_concat_rows<uint8_t><<<grid, kThreads, 0, st>>>((const uint8_t*)a, n_a, (const uint8_t*)b, n_b, nrows, (uint8_t)0,
                                                       (uint8_t*)out);
+  return launch_status();
+}
+
+int rsk_rotate_lonlat(const double* lon, const double* lat, int64_t n, const double* rot, double* lon_out,
+                      double* lat_out, void* stream) {
+  if (n < 0) return RSK_ERR_SIZE;
+  if (n == 0) return RSK_OK;
+  if (!lon || !lat || !rot || !lon_out || !lat_out) return RSK_ERR_NULL;
+  Rot9 r;
+  for (int i = 0; i < 9; ++i) r.m[i] = rot[i];
+  k_rotate_lonlat<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(lon, lat, n, r, lon_out, lat_out);
   return launch_status();
 }
 

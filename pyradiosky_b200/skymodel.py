@@ -333,6 +333,80 @@ class SkyModel:
         self._subband_cache = op
         return op
 
+    def __eq__(self, other):
+        """Equality of every parameter, as UVBase.__eq__ gives the reference's object (arrays to the UVParameter default
+        tolerances rtol 1e-5 / atol 1e-8, angles to 1e-12 rad, NaNs equal to NaNs, histories up to white space)."""
+        if not isinstance(other, SkyModel):
+            return False
+        for attr in ("component_type", "spectral_type", "Ncomponents", "Nfreqs", "stokes_unit", "frame", "equinox", "nside",
+                     "hpx_order", "time", "telescope_location"):
+            if getattr(self, attr) != getattr(other, attr):
+                return False
+        if not self._histories_match(self.history, other.history):
+            return False
+        f1 = None if self.filename is None else list(np.atleast_1d(self.filename))
+        f2 = None if other.filename is None else list(np.atleast_1d(other.filename))
+        if f1 != f2:
+            return False
+        for attr in ("freq_array", "freq_edge_array", "name", "extended_model_group"):
+            x, y = getattr(self, attr), getattr(other, attr)
+            if (x is None) != (y is None):
+                return False
+            if x is not None:
+                x, y = np.asarray(x), np.asarray(y)
+                if x.shape != y.shape:
+                    return False
+                if x.dtype.kind in "fc":
+                    if not np.allclose(x, y, rtol=1e-5, atol=1e-8, equal_nan=True):
+                        return False
+                elif not np.array_equal(x, y):
+                    return False
+        if (self.extra_columns is None) != (other.extra_columns is None):
+            return False
+        if self.extra_columns is not None:
+            if set(self.extra_columns) != set(other.extra_columns):
+                return False
+            for k in self.extra_columns:
+                if not np.array_equal(np.asarray(self.extra_columns[k]), np.asarray(other.extra_columns[k])):
+                    return False
+        angles = {"alt_az"}
+        lon1, lat1 = self.get_lon_lat()
+        lon2, lat2 = other.get_lon_lat()
+        pairs = [("lon", lon1, lon2), ("lat", lat1, lat2)]
+        for attr in ("stokes", "spectral_index", "reference_frequency", "stokes_error", "beam_amp", "hpx_inds", "alt_az",
+                     "pos_lmn", "above_horizon", "frame_coherency"):
+            pairs.append((attr, getattr(self, attr), getattr(other, attr)))
+        if self.component_type == "healpix" and (self.hpx_inds is None) != (other.hpx_inds is None):
+            n = self.Ncomponents  # an implicit pixel range equals the same pixels listed explicitly
+            pairs = [p for p in pairs if p[0] != "hpx_inds"]
+            a = self.hpx_inds if self.hpx_inds is not None else torch.arange(self.hpx_first, self.hpx_first + n, device=self.device)
+            b = other.hpx_inds if other.hpx_inds is not None else torch.arange(other.hpx_first, other.hpx_first + n, device=other.device)
+            pairs.append(("hpx_inds", a, b))
+        elif self.component_type == "healpix" and self.hpx_inds is None and self.hpx_first != other.hpx_first:
+            return False
+        for attr, x, y in pairs:
+            if (x is None) != (y is None):
+                return False
+            if x is None:
+                continue
+            if x.shape != y.shape:
+                return False
+            y = y.to(x.device)
+            if x.dtype in (torch.bool, torch.int64, torch.uint8):
+                if not torch.equal(x, y):
+                    return False
+            elif attr in angles or attr in ("lon", "lat"):
+                if not torch.allclose(x, y, rtol=0.0, atol=1e-12, equal_nan=True):
+                    return False
+            elif not torch.allclose(x, y, rtol=1e-5, atol=1e-8, equal_nan=True):
+                return False
+        return True
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    __hash__ = object.__hash__
+
     def copy(self):
         """Deep copy (device tensors are cloned)."""
         new = _copy.copy(self)
@@ -612,6 +686,32 @@ class SkyModel:
         self._call("rsk_healpix_lonlat", self.nside, 1 if self.hpx_order == "nested" else 0,
                    _lib.ptr(self.hpx_inds), self.hpx_first, self.Ncomponents, _lib.ptr(lon), _lib.ptr(lat))
         return lon, lat
+
+    def transform_to(self, frame, equinox=2000.0):
+        """Transform to a different coordinate frame (skymodel.py:1419-1446; there a thin wrapper on
+        ``SkyCoord.transform_to``): 'icrs', 'fk5' (with ``equinox``) or 'galactic'.  The coordinates are rotated on the
+        GPU (rsk_rotate_lonlat); as in the reference the Stokes parameters are left as they are."""
+        if self.component_type == "healpix":
+            raise ValueError(
+                "Direct coordinate transformation between frames is not valid "
+                "for `healpix` type catalogs. Please use the "
+                "`healpix_interp_transform` to transform to a new frame and "
+                "interpolate to the new pixel centers. Alternatively, you can "
+                "call `healpix_to_point` to convert the healpix map to a point "
+                "source catalog before calling this function."
+            )
+        frame = getattr(frame, "name", frame)
+        new_m = astrometry.frame_to_icrs_matrix(str(frame).lower(), float(equinox))
+        rot = np.ascontiguousarray(new_m.T @ self._frame_to_icrs)
+        lon = torch.empty_like(self.lon)
+        lat = torch.empty_like(self.lat)
+        self._call("rsk_rotate_lonlat", _lib.ptr(self.lon), _lib.ptr(self.lat), self.Ncomponents,
+                   _lib.host_array(rot.ravel()), _lib.ptr(lon), _lib.ptr(lat))
+        self.lon, self.lat = lon, lat
+        self.frame = str(frame).lower()
+        self.equinox = float(equinox)
+        self._frame_to_icrs = new_m
+        self._rot_key = None  # the cached polarisation-rotation coefficients were for the old frame's basis
 
     def _check_tel_location(self, telescope_location):
         # skymodel.py:2391-2411 (the lunarsky/MoonLocation branch is out of scope)

@@ -685,3 +685,86 @@ def test_concat_errors(rsk, site):
         s1.concat(s2, clear_time_position=False)  # (arrays of different halves never compare equal, as upstream)
     lib_rc = __import__("pyradiosky_b200")._lib.load().rsk_concat_rows(None, 1, None, 1, 1, 3, None, None)
     assert lib_rc == -3
+
+
+# ---------------------------------------------------------------------------------------------------
+# transform_to (skymodel.py:1419-1446)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_transform_to(rsk, site):
+    import torch
+
+    rng = np.random.default_rng(21)
+    n = 50021
+    lon, lat = rng.uniform(0, 2 * np.pi, n), np.arcsin(rng.uniform(-1, 1, n))
+    lon[:4], lat[:4] = [0.0, np.pi / 2, np.pi, 3 * np.pi / 2], [0.0, 0.0, np.pi / 2 - 1e-9, -np.pi / 2 + 1e-9]
+    st = np.zeros((4, 1, n)); st[0] = 1.0; st[1] = 0.1
+    sky = rsk.SkyModel(ra=lon, dec=lat, frame="icrs", stokes=st, spectral_type="flat")
+    time, loc = site
+    sky.update_positions(time, loc)
+    alt_az0 = sky.alt_az.clone()
+    coh0 = sky.coherency_calc()
+    for frame in ("galactic", "fk5", "icrs"):
+        old = sky.frame
+        prev = np.stack([x.cpu().numpy() for x in (sky.lon, sky.lat)])
+        sky.transform_to(frame)
+        assert sky.frame == frame
+        m = E.frame_to_icrs(frame).T @ E.frame_to_icrs(old)
+        v = m @ E.s2c(prev[0], prev[1])
+        want_lon, want_lat = np.mod(np.arctan2(v[1], v[0]), 2 * np.pi), np.arctan2(v[2], np.hypot(v[0], v[1]))
+        got_lon, got_lat = sky.lon.cpu().numpy(), sky.lat.cpu().numpy()
+        dlon = np.abs(np.mod(got_lon - want_lon + np.pi, 2 * np.pi) - np.pi) * np.cos(want_lat)
+        assert dlon.max() < 1e-15 and np.abs(got_lat - want_lat).max() < 1e-15
+        assert got_lon.min() >= 0 and got_lon.max() <= 2 * np.pi
+        # the sky has not moved: same Alt/Az from the new coordinates (the frame matrix goes with them)
+        sky.clear_time_position_specific_params()
+        sky.update_positions(time, loc)
+        d = (sky.alt_az - alt_az0).abs()
+        d[1] = torch.minimum(d[1], 2 * np.pi - d[1]) * torch.cos(alt_az0[0])
+        assert float(d.max()) < 1e-14
+    # back in ICRS after the round trip
+    dl = np.abs(np.mod(sky.lon.cpu().numpy() - lon + np.pi, 2 * np.pi) - np.pi) * np.cos(lat)
+    assert dl.max() < 5e-15 and np.abs(sky.lat.cpu().numpy() - lat).max() < 5e-15  # (three rotations)
+    assert coh0.shape == sky.coherency_calc().shape
+    # known answers: the galactic centre and the north galactic pole in ICRS (IAU 1958 definition via FK5 J2000)
+    gal = rsk.SkyModel(ra=np.array([0.0, 0.0]), dec=np.array([0.0, np.pi / 2]), frame="galactic",
+                       stokes=np.ones((4, 1, 2)), spectral_type="flat")
+    gal.transform_to("icrs")
+    ra, dec = np.rad2deg(gal.lon.cpu().numpy()), np.rad2deg(gal.lat.cpu().numpy())
+    assert abs(ra[0] - 266.40499) < 2e-4 and abs(dec[0] + 28.93617) < 2e-4
+    assert abs(ra[1] - 192.85948) < 2e-4 and abs(dec[1] - 27.12825) < 2e-4
+    hpx = rsk.SkyModel(nside=2, stokes=np.ones((4, 1, 48)), spectral_type="flat", hpx_frame="icrs")
+    with pytest.raises(ValueError, match="Direct coordinate transformation between frames is not valid"):
+        hpx.transform_to("galactic")
+    with pytest.raises(ValueError, match="not supported"):
+        sky.transform_to("fk4")
+
+
+@pytest.mark.gpu
+def test_equality_operator(rsk, site):
+    """``==`` as the reference's tests use it (UVBase.__eq__): copies, select / concat round trips, differences."""
+    time, loc = site
+    full = _full_model(rsk, "point", "subband")
+    n = full.Ncomponents
+    other = full.copy()
+    assert full == other and not (full != other)
+    s1 = full.select(component_inds=np.arange(n // 2), inplace=False)
+    s2 = full.select(component_inds=np.arange(n // 2, n), inplace=False)
+    assert s1 != full and s1 != s2
+    new = s1.concat(s2, inplace=False)
+    assert new != full  # histories differ
+    new.history = full.history
+    assert new == full
+    new.stokes[0, 0, 0] *= 1.001
+    assert new != full
+    other.update_positions(time, loc)
+    assert other != full
+    full.update_positions(time, loc)
+    assert other == full
+    other.name = other.name.copy(); other.name[0] = "different"
+    assert other != full and full != "foo"
+    hp_a = rsk.SkyModel(nside=4, stokes=np.ones((4, 1, 192)), spectral_type="flat", hpx_frame="icrs")
+    hp_b = rsk.SkyModel(nside=4, stokes=np.ones((4, 1, 192)), spectral_type="flat", hpx_frame="icrs", hpx_inds=np.arange(192))
+    assert hp_a == hp_b
+    hp_c = rsk.SkyModel(nside=4, stokes=np.ones((4, 1, 192)), spectral_type="flat", hpx_frame="icrs", hpx_order="nested")
+    assert hp_a != hp_c
