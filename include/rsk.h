@@ -397,6 +397,10 @@ int rsk_at_frequencies(const RskSpectrum* spec, const double* freqs /* [nf] */, 
  * stokes [4][nf][n] -> out complex [2][2][nf][n]. */
 int rsk_stokes_to_coherency(const double* stokes, int64_t nf, int64_t n, double* out, void* stream);
 
+/* utils.coherency_to_stokes (utils.py:64-103), the inverse: coherency [2][2][count] complex128 (interleaved re, im)
+ * -> stokes [4][count] = (Re(C00 + C11), Re(C00 - C11), Re(C01 + C10), -Im(C01 - C10)). */
+int rsk_coherency_to_stokes(const double* coherency, int64_t count, double* stokes, void* stream);
+
 /* SkyModel.jansky_to_kelvin / kelvin_to_jansky (skymodel.py:1593-1635, :1541-1591) with
  * utils.jy_to_ksr (utils.py:105-126): in-place stokes[s][f][c] *= k(nu) where k = 1e-26 c^2 / (2 k_B nu^2)
  * (or 1/k when to_jansky != 0); nu = freq_per_comp[c] if that pointer is non-NULL (spectral_index /

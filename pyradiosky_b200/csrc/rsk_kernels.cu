@@ -149,8 +149,9 @@ __device__ __forceinline__ void sweep_times(const RskCtx* s_ctx, const int ntc, 
           __stcs(pl[j] + n, o.m);
           __stcs(pl[j] + 2 * n, o.n);
         }
-        // alt > 0 read off the high word (alt is never a positive denormal): an integer compare, not an fp64 one
-        if (MASK) *pm[j] = __double2hiint(o.alt) > 0 ? 1 : 0;
+        // alt > 0 read off the high word (alt is never a positive denormal; a NaN is not "above"): integer compares,
+        // not an fp64 one
+        if (MASK) *pm[j] = (unsigned)(__double2hiint(o.alt) - 1) < 0x7fefffffu ? 1 : 0;
       }
       pa[j] += 2 * n;
       if (WANT_LMN) pl[j] += 3 * n;
@@ -418,6 +419,20 @@ __global__ void __launch_bounds__(kThreads) k_rotate_lonlat(const double* __rest
   const double z = r.m[6] * px + r.m[7] * py + r.m[8] * pz;
   lon_out[i] = rsk_azimuth(y, x);  // [0, 2 pi], as astropy's Longitude wraps
   lat_out[i] = rsk_atan2_t<true>(z, rsk_sqrt(x * x + y * y));
+}
+
+// utils.coherency_to_stokes (utils.py:64-103): I = Re(C00 + C11), Q = Re(C00 - C11), U = Re(C01 + C10),
+// V = -Im(C01 - C10); count = elements per plane, 64 B read + 32 B written each
+__global__ void __launch_bounds__(kThreads) k_coherency_to_stokes(const double2* __restrict__ coh, const int64_t count,
+                                                                  double* __restrict__ stokes) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= count) return;
+  const double2 c00 = __ldcs(coh + i), c01 = __ldcs(coh + count + i);
+  const double2 c10 = __ldcs(coh + 2 * count + i), c11 = __ldcs(coh + 3 * count + i);
+  __stcs(stokes + i, c00.x + c11.x);
+  __stcs(stokes + count + i, c00.x - c11.x);
+  __stcs(stokes + 2 * count + i, c01.x + c10.x);
+  __stcs(stokes + 3 * count + i, -(c01.y - c10.y));
 }
 
 __global__ void __launch_bounds__(kThreads) k_rise_set(const CoordSrc cs, const int64_t n, const double tan_tel,
@@ -1865,6 +1880,16 @@ int rsk_stokes_to_coherency(const double* stokes, int64_t nf, int64_t n, double*
   if (nf == 0 || n == 0) return RSK_OK;
   RskCoords none = {};
   return rsk_coherency(&spec, &none, nullptr, nullptr, nullptr, nullptr, n, nullptr, nullptr, nf, out, n, 0, stream);
+}
+
+int rsk_coherency_to_stokes(const double* coherency, int64_t count, double* stokes, void* stream) {
+  if (count < 0) return RSK_ERR_SIZE;
+  if (count == 0) return RSK_OK;
+  if (!coherency || !stokes) return RSK_ERR_NULL;
+  if ((count + kThreads - 1) / kThreads > 0x7fffffffll) return RSK_ERR_SIZE;
+  k_coherency_to_stokes<<<blocks_for(count), kThreads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const double2*>(coherency), count, stokes);
+  return launch_status();
 }
 
 int rsk_convert_units(double* stokes, int64_t nf, int64_t n, const double* freq_per_chan, const double* freq_per_comp,

@@ -69,6 +69,33 @@ def stokes_to_coherency(stokes_arr):
     return out if want_torch else out.cpu().numpy()
 
 
+def coherency_to_stokes(coherency_matrix):
+    """Convert coherency matrix to vector of 4 Stokes parameter in order [I, Q, U, V] (utils.py:64-103).
+
+    ``coherency_matrix``: complex, shape (2, 2) or (2, 2, ...) (numpy, torch or Quantity-like).  Returns float64 of shape
+    (4,) or (4, ...): a torch CUDA tensor if the input was a torch tensor, otherwise a numpy array."""
+    shape = tuple(coherency_matrix.shape)
+    if len(shape) < 2 or shape[0] != 2 or shape[1] != 2:
+        raise ValueError("First two dimensions of coherency_matrix must be length 2.")
+    want_torch = isinstance(coherency_matrix, torch.Tensor)
+    arr = coherency_matrix
+    if hasattr(arr, "unit") and hasattr(arr, "value"):
+        arr = arr.value
+    if want_torch:
+        coh = arr.to(dtype=torch.complex128)
+        coh = coh if coh.is_cuda else coh.to("cuda")
+    else:
+        coh = torch.as_tensor(np.ascontiguousarray(arr, dtype=np.complex128)).to("cuda")
+    coh = coh.contiguous()
+    count = coh.numel() // 4
+    out = torch.empty((4,) + shape[2:], dtype=torch.float64, device=coh.device)
+    with torch.cuda.device(coh.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check("rsk_coherency_to_stokes",
+                   _lib.load().rsk_coherency_to_stokes(_lib.ptr(coh), count, _lib.ptr(out), stream))
+    return out if want_torch else out.cpu().numpy()
+
+
 def jy_to_ksr(freqs):
     """Multiplicative factors taking [Jy] to [K sr] at ``freqs`` (Hz): 1e-26 c^2 / (2 k_B nu^2).
 

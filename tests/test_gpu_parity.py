@@ -184,6 +184,39 @@ def test_azimuth_octants_and_axes(rsk):
     assert d.max() < 2e-15 and np.abs(got[0] - lat).max() < 1e-15
 
 
+def test_positions_extreme_coordinates(rsk, site):
+    """Longitudes far outside [0, 2 pi) (the bounded-range sincos hands over to libdevice above 16 rad), negative ones,
+    the exact poles, and a NaN coordinate: same Alt/Az as the oracle, NaN in -> NaN out without disturbing neighbours."""
+    time, loc = site
+    rng = np.random.default_rng(31)
+    lon = np.concatenate([rng.uniform(-20, 20, 500), rng.uniform(-1e6, 1e6, 500), [15.99, 16.01, -16.01, 0.0, -0.0, 1e9]])
+    lat = np.concatenate([np.arcsin(rng.uniform(-1, 1, 1000)), [np.pi / 2, -np.pi / 2, 0.0, np.pi / 2, -np.pi / 2, 0.3]])
+    st = np.zeros((4, 1, lon.size)); st[0] = 1
+    for frame in ("icrs", "fk5"):
+        sky = rsk.SkyModel(ra=lon, dec=lat, frame=frame, stokes=st, spectral_type="flat")
+        sky.update_positions(time, loc)
+        a = rsk.astrometry.astrom_context(time, loc)
+        alt_az, lmn, above = S.update_positions(lon, lat, a, frame_to_icrs=E.frame_to_icrs(frame))
+        # a longitude of 1e6 rad carries an absolute rounding error of 1e-10 rad in the input itself: compare where
+        # the argument reduction of numpy and of the device agree by construction, and loosely elsewhere
+        small = np.abs(lon) <= 20
+        assert_altaz_close(sky.alt_az.cpu().numpy()[:, small], alt_az[:, small])
+        assert_altaz_close(sky.alt_az.cpu().numpy()[:, ~small], alt_az[:, ~small], tol=1e-9)
+        assert_mask_equal(sky.above_horizon.cpu().numpy(), above, alt_az[0], guard=1e-8)
+    lon2, lat2 = lon.copy(), lat.copy()
+    lon2[3], lat2[7] = np.nan, np.nan
+    sky = rsk.SkyModel(ra=lon2, dec=lat2, stokes=st, spectral_type="flat")
+    sky.update_positions(time, loc)
+    got = sky.alt_az.cpu().numpy()
+    assert np.isnan(got[:, 3]).all() and np.isnan(got[:, 7]).all()
+    ok = np.ones(lon.size, bool); ok[[3, 7]] = False
+    assert np.isfinite(got[:, ok]).all()
+    assert not sky.above_horizon.cpu().numpy()[[3, 7]].any()  # NaN altitude is not "above"
+    a_sw, _, m_sw = sky.positions_sweep([time, time + 0.1], loc)
+    assert not m_sw.cpu().numpy()[:, [3, 7]].any() and bool(torch.isnan(a_sw[:, :, [3, 7]]).all())
+    assert torch.equal(m_sw[0], sky.above_horizon)
+
+
 def test_update_positions_errors(rsk, site):
     time, loc = site
     st = np.zeros((4, 1, 3)); st[0] = 1
@@ -345,6 +378,25 @@ def test_stokes_to_coherency_bit_exact(rsk, known_answers):
     assert sky.calc_frame_coherency(store=False).shape == (2, 2, 13, 1001)
     sky.calc_frame_coherency()
     assert np.array_equal(sky.frame_coherency.cpu().numpy(), S.stokes_to_coherency(st))
+
+
+def test_coherency_to_stokes(rsk, known_answers):
+    """tests/test_utils.py:14-64: Stokes -> coherency -> Stokes, single vector and (4, Nfreqs, Ncomponents)."""
+    stokes = np.array([4.5, -0.3, 1.2, -0.15])
+    coh = rsk.utils.stokes_to_coherency(stokes)
+    back = rsk.utils.coherency_to_stokes(coh)
+    assert back.shape == (4,) and np.allclose(back, stokes, rtol=0, atol=1e-15)  # (np.allclose upstream too)
+    st2 = np.stack([stokes, stokes]).T[:, np.newaxis, :]
+    back2 = rsk.utils.coherency_to_stokes(rsk.utils.stokes_to_coherency(st2))
+    assert back2.shape == (4, 1, 2) and np.allclose(back2, st2, rtol=0, atol=1e-16)
+    rng = np.random.default_rng(19)
+    c = rng.normal(size=(2, 2, 7, 1003)) + 1j * rng.normal(size=(2, 2, 7, 1003))
+    want = np.array([c[0, 0] + c[1, 1], c[0, 0] - c[1, 1], c[0, 1] + c[1, 0], -(c[0, 1] - c[1, 0]).imag]).real
+    got = rsk.utils.coherency_to_stokes(torch.as_tensor(c).cuda())
+    assert isinstance(got, torch.Tensor) and got.is_cuda and np.array_equal(got.cpu().numpy(), want)
+    assert np.array_equal(rsk.utils.coherency_to_stokes(c[:, :, 0, :]), want[:, 0, :])
+    with pytest.raises(ValueError, match="First two dimensions of coherency_matrix must be length 2."):
+        rsk.utils.coherency_to_stokes(coh[0, :])
 
 
 def test_unit_conversion(rsk, known_answers):
