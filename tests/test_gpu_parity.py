@@ -388,7 +388,7 @@ def test_coherency_to_stokes(rsk, known_answers):
     assert back.shape == (4,) and np.allclose(back, stokes, rtol=0, atol=1e-15)  # (np.allclose upstream too)
     st2 = np.stack([stokes, stokes]).T[:, np.newaxis, :]
     back2 = rsk.utils.coherency_to_stokes(rsk.utils.stokes_to_coherency(st2))
-    assert back2.shape == (4, 1, 2) and np.allclose(back2, st2, rtol=0, atol=1e-16)
+    assert back2.shape == (4, 1, 2) and np.allclose(back2, st2, rtol=0, atol=1e-15)
     rng = np.random.default_rng(19)
     c = rng.normal(size=(2, 2, 7, 1003)) + 1j * rng.normal(size=(2, 2, 7, 1003))
     want = np.array([c[0, 0] + c[1, 1], c[0, 0] - c[1, 1], c[0, 1] + c[1, 0], -(c[0, 1] - c[1, 0]).imag]).real
