@@ -81,8 +81,9 @@ class Time:
         self.yp = float(yp)
 
     @classmethod
-    def from_utc(cls, text, **eop):
-        """Parse ``YYYY-MM-DD HH:MM:SS[.fff]`` (UTC)."""
+    def from_utc(cls, text, iers=None, **eop):
+        """Parse ``YYYY-MM-DD HH:MM:SS[.fff]`` (UTC).  ``iers``: an :class:`IERSTable` to take UT1-UTC and the polar
+        motion from (explicit ``dut1`` / ``xp`` / ``yp`` keywords win)."""
         fmt = "%Y-%m-%d %H:%M:%S.%f" if "." in text else "%Y-%m-%d %H:%M:%S"
         t = _dt.datetime.strptime(text.replace("T", " "), fmt)
         a = (14 - t.month) // 12
@@ -90,6 +91,9 @@ class Time:
         m = t.month + 12 * a - 3
         jdn = t.day + (153 * m + 2) // 5 + 365 * y + y // 4 - y // 100 + y // 400 - 32045
         frac = (t.hour * 3600 + t.minute * 60 + t.second + t.microsecond * 1e-6) / 86400.0
+        if iers is not None:
+            dut1, xp, yp = iers.eop(jdn - 0.5, frac)
+            eop = {"dut1": dut1, "xp": xp, "yp": yp, **eop}
         return cls(jdn - 0.5, frac, **eop)
 
     @property
@@ -111,6 +115,75 @@ class Time:
 
     def __repr__(self):
         return f"Time(jd_utc={self.jd1}+{self.jd2}, dut1={self.dut1}, xp={self.xp}, yp={self.yp})"
+
+
+class IERSTable:
+    """Earth-orientation parameters from an IERS ``finals2000A`` file (``finals2000A.all`` / ``.daily`` / ``.data``):
+    the table astropy's ``iers.IERS_A`` reads to turn a UTC instant into UT1-UTC and polar motion before it builds the
+    ``eraASTROM`` of ``AltAz(obstime, location)`` (the reference's call at skymodel.py:2451-2454; its tests pin the
+    table in tests/conftest.py:10-26).
+
+    Fixed-width columns, as in the IERS ``readme.finals2000A`` (1-based, inclusive): MJD 8-15, Bulletin A PM-x 19-27
+    and PM-y 38-46 (arcsec), UT1-UTC 59-68 (s); Bulletin B PM-x 135-144, PM-y 145-154, UT1-UTC 155-165 where present.
+    Like astropy, Bulletin B values are preferred where a row has them, rows without a UT1-UTC value are dropped,
+    values are interpolated linearly in MJD with the leap-second steps of UT1-UTC removed before and restored after the
+    interpolation, and instants outside the table raise.  No IERS file ships on this box, so the column layout is
+    restated from the IERS readme and checked on synthetic rows only (tests/test_host.py): parity unpinned.
+    """
+
+    def __init__(self, mjd, dut1, xp_arcsec, yp_arcsec):
+        order = np.argsort(np.asarray(mjd, dtype=np.float64))
+        self.mjd = np.asarray(mjd, dtype=np.float64)[order]
+        self.dut1 = np.asarray(dut1, dtype=np.float64)[order]
+        self.xp = np.asarray(xp_arcsec, dtype=np.float64)[order]
+        self.yp = np.asarray(yp_arcsec, dtype=np.float64)[order]
+        if self.mjd.size < 2:
+            raise ValueError("an IERS table needs at least two rows")
+
+    @staticmethod
+    def _field(line, first, last):
+        text = line[first - 1:last].strip()
+        return float(text) if text else None
+
+    @classmethod
+    def from_finals2000a(cls, path, prefer_bulletin_b=True):
+        mjd, dut1, xp, yp = [], [], [], []
+        with open(path) as fh:
+            for line in fh:
+                line = line.rstrip("\n")
+                if len(line) < 68:
+                    continue
+                m = cls._field(line, 8, 15)
+                ax, ay, au = cls._field(line, 19, 27), cls._field(line, 38, 46), cls._field(line, 59, 68)
+                bx = by = bu = None
+                if prefer_bulletin_b and len(line) >= 165:
+                    bx, by, bu = cls._field(line, 135, 144), cls._field(line, 145, 154), cls._field(line, 155, 165)
+                x, y, u = (bx, by, bu) if None not in (bx, by, bu) else (ax, ay, au)
+                if None in (m, x, y, u):
+                    continue
+                mjd.append(m); xp.append(x); yp.append(y); dut1.append(u)
+        if not mjd:
+            raise ValueError(f"no Earth-orientation rows found in {path}")
+        return cls(mjd, dut1, xp, yp)
+
+    def eop(self, jd1, jd2=0.0):
+        """(UT1-UTC [s], xp [rad], yp [rad]) at the UTC Julian date jd1 + jd2."""
+        mjd = (jd1 - 2400000.5) + jd2
+        if mjd < self.mjd[0] or mjd > self.mjd[-1]:
+            raise ValueError(f"MJD {mjd:.3f} is outside the IERS table ({self.mjd[0]:.1f} .. {self.mjd[-1]:.1f})")
+        i = int(np.clip(np.searchsorted(self.mjd, mjd, side="right") - 1, 0, self.mjd.size - 2))
+        w = (mjd - self.mjd[i]) / (self.mjd[i + 1] - self.mjd[i])
+        u0, u1 = self.dut1[i], self.dut1[i + 1]
+        # a leap second between the two rows shows as a step of about +1 s in UT1-UTC: take it out of the later row,
+        # interpolate, and put it back if the instant is past the step (which falls on the later row's midnight)
+        step = np.round(u1 - u0)
+        u = u0 + w * ((u1 - step) - u0)
+        if step != 0.0 and mjd >= np.floor(self.mjd[i + 1]):
+            u += step
+        arcsec = np.pi / 180.0 / 3600.0
+        x = self.xp[i] + w * (self.xp[i + 1] - self.xp[i])
+        y = self.yp[i] + w * (self.yp[i + 1] - self.yp[i])
+        return float(u), float(x * arcsec), float(y * arcsec)
 
 
 _ASTROPY_TYPES = None

@@ -279,3 +279,73 @@ def test_batched_contexts_equal_single_calls(librsk):
     mixed = times[:3] + [Time(2457083.5, 0.0, dut1=0.1)]
     assert np.array_equal(astrometry.astrom_contexts(mixed, loc)[3], astrometry.astrom_context(mixed[3], loc))
     assert astrometry.astrom_contexts([], loc).shape == (0, 31)
+
+
+def _finals_row(mjd, pmx, pmy, dut1, bull_b=None):
+    """One line of finals2000A in the column layout of the IERS readme (1-based: MJD 8-15, PM-x 19-27, PM-y 38-46,
+    UT1-UTC 59-68; Bulletin B 135-144, 145-154, 155-165)."""
+    line = [" "] * 188
+    def put(first, last, text):
+        width = last - first + 1
+        line[first - 1:last] = list(text.rjust(width)[-width:])
+    put(1, 6, "150301")
+    put(8, 15, f"{mjd:.2f}")
+    put(17, 17, "I")
+    put(19, 27, f"{pmx:.6f}")
+    put(28, 36, f"{0.00004:.6f}")
+    put(38, 46, f"{pmy:.6f}")
+    put(47, 55, f"{0.00005:.6f}")
+    put(58, 58, "I")
+    put(59, 68, f"{dut1:.7f}")
+    put(69, 78, f"{0.00001:.7f}")
+    if bull_b is not None:
+        put(135, 144, f"{bull_b[0]:.6f}")
+        put(145, 154, f"{bull_b[1]:.6f}")
+        put(155, 165, f"{bull_b[2]:.7f}")
+    return "".join(line).rstrip()
+
+
+def test_iers_table(tmp_path):
+    """IERSTable: fixed-width parsing, Bulletin B preferred, linear interpolation, the leap second of 2015-07-01
+    (MJD 57204) in UT1-UTC, range errors, Time.from_utc(iers=...)."""
+    from pyradiosky_b200 import IERSTable, Time
+
+    rows = [
+        _finals_row(57082.0, 0.010000, 0.300000, -0.4800000, bull_b=(0.011000, 0.301000, -0.4801000)),
+        _finals_row(57083.0, 0.012000, 0.304000, -0.4812000, bull_b=(0.013000, 0.305000, -0.4813000)),
+        _finals_row(57084.0, 0.014000, 0.308000, -0.4824000),  # no Bulletin B yet: Bulletin A is used
+        _finals_row(57202.0, 0.100000, 0.400000, -0.6750000),
+        _finals_row(57203.0, 0.102000, 0.402000, -0.6760000),
+        _finals_row(57204.0, 0.104000, 0.404000, 0.3230000),   # after the leap second
+        _finals_row(57205.0, 0.106000, 0.406000, 0.3220000),
+        "150709 57212.00 P                                                        ",  # prediction row without values
+    ]
+    path = tmp_path / "finals2000A.test"
+    path.write_text("\n".join(rows) + "\n")
+    tab = IERSTable.from_finals2000a(str(path))
+    assert tab.mjd.size == 7
+    arcsec = np.pi / 180 / 3600
+    u, x, y = tab.eop(2400000.5, 57082.0)
+    assert (u, x, y) == (-0.4801, 0.011 * arcsec, 0.301 * arcsec)
+    u, x, y = tab.eop(2400000.5 + 57082.0, 0.25)
+    assert abs(u - (-0.4801 - 0.25 * 0.0012)) < 1e-12 and abs(x - 0.0115 * arcsec) < 1e-18
+    u, x, y = tab.eop(2400000.5 + 57083.0, 0.5)   # between a Bulletin B row and a Bulletin A row
+    assert abs(u - 0.5 * (-0.4813 - 0.4824)) < 1e-12 and abs(y - 0.5 * (0.305 + 0.308) * arcsec) < 1e-18
+    # across the leap second the interpolant follows UT1-UTC without the step until midnight
+    u, _, _ = tab.eop(2400000.5 + 57203.0, 0.75)
+    assert abs(u - (-0.6760 + 0.75 * (-0.6770 + 0.6760))) < 1e-12
+    u, _, _ = tab.eop(2400000.5 + 57204.0, 0.0)
+    assert u == 0.3230
+    u, _, _ = tab.eop(2400000.5 + 57204.0, 0.5)
+    assert abs(u - 0.3225) < 1e-12
+    with pytest.raises(ValueError, match="outside the IERS table"):
+        tab.eop(2400000.5 + 57300.0)
+    tab_a = IERSTable.from_finals2000a(str(path), prefer_bulletin_b=False)
+    assert tab_a.eop(2400000.5, 57082.0)[0] == -0.48
+    t = Time.from_utc("2015-03-01 06:00:00", iers=tab)
+    assert abs(t.dut1 - (-0.4801 - 0.25 * 0.0012)) < 1e-12 and abs(t.xp - 0.0115 * arcsec) < 1e-18
+    t2 = Time.from_utc("2015-03-01 06:00:00", iers=tab, dut1=0.1)
+    assert t2.dut1 == 0.1 and t2.xp == t.xp
+    (tmp_path / "empty").write_text("nothing here\n")
+    with pytest.raises(ValueError, match="no Earth-orientation rows"):
+        IERSTable.from_finals2000a(str(tmp_path / "empty"))
