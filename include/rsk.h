@@ -290,6 +290,17 @@ int rsk_concat_rows(const void* a /* [nrows][n_a] or NULL */, int64_t n_a, const
 int rsk_rotate_lonlat(const double* lon, const double* lat, int64_t n, const double* rot /* HOST [9] */,
                       double* lon_out, double* lat_out, void* stream);
 
+/* SkyModel.healpix_interp_transform (skymodel.py:1448-1538): the map at the pixel centres of a NEW frame, bilinearly
+ * interpolated (astropy_healpix.HEALPix.interpolate_bilinear_skycoord, :1507-1509) from a map given on pixels of the
+ * old frame.  rot_new_to_old: HOST [9] row-major rotation of unit vectors from the new frame to the old one.  The
+ * input rows hold n_in pixels: pixel p of the old map sits at column lookup[p] (DEVICE [12 nside^2], -1 = absent), or
+ * at p - hpx_first when lookup is NULL.  out [nrows][12 nside^2] in the map's own ordering; valid[j] = 1 when all
+ * four neighbours of new pixel j are present (the reference's masked-array result), else 0 and the row values are 0. */
+int rsk_healpix_interp(int64_t nside, int nested, const double* rot_new_to_old /* HOST [9] */,
+                       const int64_t* lookup /* DEVICE [12 nside^2] or NULL */, int64_t hpx_first, int64_t n_in,
+                       const double* in /* [nrows][n_in] */, int64_t nrows, double* out /* [nrows][12 nside^2] */,
+                       uint8_t* valid /* [12 nside^2] */, void* stream);
+
 /* SkyModel.calculate_rise_set_lsts (skymodel.py:3284-3329): rise = lon - acos(-tan(tel_lat) tan(lat)) - buffer,
  * set = lon + acos(...) + buffer, each wrapped once into [0, 2 pi]; NaN for components that never rise or never set. */
 int rsk_rise_set_lsts(const RskCoords* coords, int64_t n, double tel_lat, double horizon_buffer,

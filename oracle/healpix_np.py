@@ -156,3 +156,116 @@ def nside_to_pixel_area(nside):
     import math
 
     return 4 * math.pi / (12 * int(nside) * int(nside))
+
+
+def ring2nest(nside, pix):
+    """Ring-ordered pixel number -> nested (through the pixel centre, which both orderings share)."""
+    lon, lat = healpix_to_lonlat(nside, pix, nested=False)
+    return lonlat_to_healpix(nside, lon, lat, nested=True)
+
+
+def _ring_info(nside, ring):
+    """(first pixel, pixels in ring, colatitude, shifted) of ring 1 .. 4 nside - 1 (HEALPix get_ring_info2)."""
+    nside = int(nside)
+    npix = 12 * nside * nside
+    ncap = 2 * nside * (nside - 1)
+    north = np.where(ring > 2 * nside, 4 * nside - ring, ring)
+    cap = north < nside
+    tmp = (north * north).astype(np.float64) * (4.0 / npix)
+    theta_cap = np.arctan2(np.sqrt(tmp * (2.0 - tmp)), 1.0 - tmp)
+    theta_eq = np.arccos(np.clip((2 * nside - north).astype(np.float64) * (2.0 / (3.0 * nside)), -1.0, 1.0))
+    theta = np.where(cap, theta_cap, theta_eq)
+    ringpix = np.where(cap, 4 * north, 4 * nside)
+    shifted = np.where(cap, True, ((north - nside) & 1) == 0)
+    start = np.where(cap, 2 * north * (north - 1), ncap + (north - nside) * 4 * nside)
+    south = north != ring
+    theta = np.where(south, np.pi - theta, theta)
+    start = np.where(south, npix - start - ringpix, start)
+    return start, ringpix, theta, shifted
+
+
+def interp_weights(nside, lon, lat, nested=False):
+    """The four neighbours and bilinear weights of ``astropy_healpix.HEALPix.interpolate_bilinear_lonlat`` -- the
+    interpolation SkyModel.healpix_interp_transform relies on (skymodel.py:1507-1509).
+
+    astropy-healpix is not on this box; its interpolation (two pixels that bracket the longitude on each of the two
+    rings that bracket the latitude, linear in longitude along a ring and in latitude between rings, a fictitious
+    polar pixel equal to the mean of the four cap pixels inside the first / last ring) is the classic HEALPix
+    ``get_interpol`` scheme, restated here.  Returns (pix [4, n] int64, wgt [4, n]).  Pinned by the reference's own
+    golden pair gsm_galactic.skyh5 -> gsm_icrs.skyh5 (tests/test_skymodel.py:4423-4452) in tests/test_oracle.py.
+    """
+    nside = int(nside)
+    lon = np.mod(np.atleast_1d(np.asarray(lon, dtype=np.float64)), 2 * np.pi)
+    lat = np.atleast_1d(np.asarray(lat, dtype=np.float64))
+    theta = np.pi / 2 - lat
+    z = np.sin(lat)
+    az = np.abs(z)
+    ir_eq = np.floor(nside * (2.0 - 1.5 * z)).astype(np.int64)
+    ir_cap = np.floor(nside * np.sqrt(3.0 * (1.0 - az))).astype(np.int64)
+    ir1 = np.where(az <= 2.0 / 3.0, ir_eq, np.where(z > 0, ir_cap, 4 * nside - ir_cap - 1))  # ring above the point
+    ir2 = ir1 + 1
+    npix = 12 * nside * nside
+    pix = np.zeros((4, lon.size), dtype=np.int64)
+    wgt = np.zeros((4, lon.size))
+    thetas = []
+    for slot, ring in ((0, ir1), (2, ir2)):
+        ok = (ring > 0) & (ring < 4 * nside)
+        start, nr, th, shifted = _ring_info(nside, np.where(ok, ring, 1))
+        dphi = 2 * np.pi / nr
+        tmp = lon / dphi - 0.5 * shifted
+        i1 = np.where(tmp < 0, tmp - 1, tmp).astype(np.int64)
+        w1 = (lon - (i1 + 0.5 * shifted) * dphi) / dphi
+        i2 = i1 + 1
+        i1 = np.where(i1 < 0, i1 + nr, i1)
+        i2 = np.where(i2 >= nr, i2 - nr, i2)
+        pix[slot], pix[slot + 1] = start + i1, start + i2
+        wgt[slot], wgt[slot + 1] = 1.0 - w1, w1
+        thetas.append(th)
+    theta1, theta2 = thetas
+    northpole = ir1 == 0
+    southpole = ir2 == 4 * nside
+    mid = ~(northpole | southpole)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        wt_mid = (theta - theta1) / (theta2 - theta1)
+        wt_n = theta / theta2
+        wt_s = (theta - theta1) / (np.pi - theta1)
+    # between two rings
+    w = wgt.copy()
+    w[0], w[1] = wgt[0] * (1 - wt_mid), wgt[1] * (1 - wt_mid)
+    w[2], w[3] = wgt[2] * wt_mid, wgt[3] * wt_mid
+    # north of the first ring: the polar value is the mean of the four pixels of ring 1
+    fac = (1 - wt_n) * 0.25
+    wn = np.array([fac, fac, wgt[2] * wt_n + fac, wgt[3] * wt_n + fac])
+    pn = np.array([(pix[2] + 2) & 3, (pix[3] + 2) & 3, pix[2], pix[3]])
+    # south of the last ring
+    fac = wt_s * 0.25
+    ws = np.array([wgt[0] * (1 - wt_s) + fac, wgt[1] * (1 - wt_s) + fac, fac, fac])
+    ps = np.array([pix[0], pix[1], ((pix[0] + 2) & 3) + npix - 4, ((pix[1] + 2) & 3) + npix - 4])
+    out_w = np.where(mid, w, np.where(northpole, wn, ws))
+    out_p = np.where(mid, pix, np.where(northpole, pn, ps))
+    if nested:
+        out_p = ring2nest(nside, out_p.ravel()).reshape(out_p.shape)
+    return out_p, out_w
+
+
+def interp_transform(nside, nested, hpx_inds, values, rot_new_to_old, full_sky=False):
+    """SkyModel.healpix_interp_transform (skymodel.py:1448-1538) for one map row: ``values`` on pixels ``hpx_inds`` of
+    the old frame -> the map at the pixel centres of the new frame, ``rot_new_to_old`` being the rotation of unit vectors
+    from the new frame to the old one.  Returns (new_hpx_inds, new_values); a new pixel whose four neighbours are not
+    all present is dropped (masked-array arithmetic upstream), or kept as 0 when ``full_sky``."""
+    npix = 12 * int(nside) ** 2
+    lon, lat = healpix_to_lonlat(nside, np.arange(npix), nested=nested)
+    v = rot_new_to_old @ np.array([np.cos(lat) * np.cos(lon), np.cos(lat) * np.sin(lon), np.sin(lat)])
+    lon_o, lat_o = np.arctan2(v[1], v[0]), np.arctan2(v[2], np.hypot(v[0], v[1]))
+    pix, wgt = interp_weights(nside, lon_o, lat_o, nested=nested)
+    lookup = np.full(npix, -1, dtype=np.int64)
+    lookup[np.asarray(hpx_inds)] = np.arange(len(hpx_inds))
+    pos = lookup[pix]
+    valid = np.all(pos >= 0, axis=0)
+    vals = np.asarray(values, dtype=np.float64)
+    out = np.sum(wgt * vals[np.where(pos >= 0, pos, 0)], axis=0)
+    out = np.where(valid, out, 0.0)
+    if full_sky:
+        return np.arange(npix), out
+    keep = np.nonzero(valid)[0]
+    return keep, out[keep]

@@ -158,6 +158,11 @@ _SIGNATURES = {
          ctypes.c_void_p],
     ),
     "rsk_coherency_to_stokes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
+    "rsk_healpix_interp": (
+        ctypes.c_int,
+        [ctypes.c_int64, ctypes.c_int, c_double_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+         ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p],
+    ),
     "rsk_rise_set_lsts": (
         ctypes.c_int,
         [ctypes.POINTER(RskCoords), ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_void_p,

@@ -435,6 +435,145 @@ __global__ void __launch_bounds__(kThreads) k_coherency_to_stokes(const double2*
   __stcs(stokes + 3 * count + i, -(c01.y - c10.y));
 }
 
+// ---- HEALPix bilinear interpolation: SkyModel.healpix_interp_transform (skymodel.py:1448-1538) ----------------
+// HEALPix ring geometry (get_ring_info2): first pixel, pixels in the ring, colatitude, half-pixel shift
+__device__ __forceinline__ void hpx_ring_info(const int64_t nside, const int64_t ring, int64_t& start, int64_t& nr,
+                                              double& theta, bool& shifted) {
+  const int64_t npix = 12 * nside * nside, ncap = 2 * nside * (nside - 1);
+  const int64_t north = ring > 2 * nside ? 4 * nside - ring : ring;
+  if (north < nside) {
+    const double tmp = (double)(north * north) * (4.0 / (double)npix);
+    theta = atan2(sqrt(tmp * (2.0 - tmp)), 1.0 - tmp);
+    nr = 4 * north;
+    shifted = true;
+    start = 2 * north * (north - 1);
+  } else {
+    theta = acos(fmin(1.0, fmax(-1.0, (double)(2 * nside - north) * (2.0 / (3.0 * (double)nside)))));
+    nr = 4 * nside;
+    shifted = ((north - nside) & 1) == 0;
+    start = ncap + (north - nside) * nr;
+  }
+  if (north != ring) {
+    theta = RSK_DPI - theta;
+    start = npix - start - nr;
+  }
+}
+
+// The four neighbours (ring numbering) and bilinear weights of a direction: two pixels bracketing the longitude on each
+// of the two rings bracketing the latitude, linear along the ring and in colatitude between rings; inside the first
+// / last ring a fictitious polar pixel = mean of the four cap pixels (HEALPix get_interpol, what
+// astropy_healpix.interpolate_bilinear_lonlat evaluates).
+__device__ __forceinline__ void hpx_interp_weights(const int64_t nside, const double z, const double theta,
+                                                   const double phi, int64_t pix[4], double wgt[4]) {
+  const double az = fabs(z);
+  int64_t ir1;
+  if (az <= 2.0 / 3.0) {
+    ir1 = (int64_t)floor((double)nside * (2.0 - 1.5 * z));
+  } else {
+    const int64_t ir = (int64_t)floor((double)nside * sqrt(3.0 * (1.0 - az)));
+    ir1 = z > 0.0 ? ir : 4 * nside - ir - 1;
+  }
+  const int64_t ir2 = ir1 + 1, npix = 12 * nside * nside;
+  double theta1 = 0.0, theta2 = 0.0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int64_t ring = h == 0 ? ir1 : ir2;
+    if (ring > 0 && ring < 4 * nside) {
+      int64_t start, nr;
+      double th;
+      bool shifted;
+      hpx_ring_info(nside, ring, start, nr, th, shifted);
+      const double dphi = RSK_D2PI / (double)nr;
+      const double tmp = phi / dphi - (shifted ? 0.5 : 0.0);
+      int64_t i1 = tmp < 0.0 ? (int64_t)(tmp - 1.0) : (int64_t)tmp;
+      const double w1 = (phi - ((double)i1 + (shifted ? 0.5 : 0.0)) * dphi) / dphi;
+      int64_t i2 = i1 + 1;
+      if (i1 < 0) i1 += nr;
+      if (i2 >= nr) i2 -= nr;
+      pix[2 * h] = start + i1;
+      pix[2 * h + 1] = start + i2;
+      wgt[2 * h] = 1.0 - w1;
+      wgt[2 * h + 1] = w1;
+      if (h == 0) theta1 = th; else theta2 = th;
+    }
+  }
+  if (ir1 == 0) {  // north of the first ring
+    const double wt = theta / theta2, fac = (1.0 - wt) * 0.25;
+    wgt[2] = wgt[2] * wt + fac;
+    wgt[3] = wgt[3] * wt + fac;
+    wgt[0] = fac;
+    wgt[1] = fac;
+    pix[0] = (pix[2] + 2) & 3;
+    pix[1] = (pix[3] + 2) & 3;
+  } else if (ir2 == 4 * nside) {  // south of the last ring
+    const double wt = (theta - theta1) / (RSK_DPI - theta1), fac = wt * 0.25;
+    wgt[0] = wgt[0] * (1.0 - wt) + fac;
+    wgt[1] = wgt[1] * (1.0 - wt) + fac;
+    wgt[2] = fac;
+    wgt[3] = fac;
+    pix[2] = ((pix[0] + 2) & 3) + npix - 4;
+    pix[3] = ((pix[1] + 2) & 3) + npix - 4;
+  } else {
+    const double wt = (theta - theta1) / (theta2 - theta1);
+    wgt[0] *= 1.0 - wt;
+    wgt[1] *= 1.0 - wt;
+    wgt[2] *= wt;
+    wgt[3] *= wt;
+  }
+}
+
+// One thread per pixel of the NEW frame's map: centre -> old frame -> neighbours and weights once, then every map row.
+// valid[j] = 1 when all four neighbours exist in the (possibly partial) input; rows of invalid pixels are written as 0.
+__global__ void __launch_bounds__(kThreads) k_healpix_interp(const int64_t nside, const int nested, const Rot9 r,
+                                                             const int64_t* __restrict__ lookup, const int64_t first,
+                                                             const int64_t n_in, const double* __restrict__ in,
+                                                             const int64_t nrows, double* __restrict__ out,
+                                                             uint8_t* __restrict__ valid) {
+  const int64_t npix = 12 * nside * nside;
+  const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (j >= npix) return;
+  double z, st, phi, sp, cp;
+  rsk_hpx_center(nside, nested, j, z, st, phi);
+  rsk_sincos(phi, &sp, &cp);
+  const double px = st * cp, py = st * sp;
+  const double x = r.m[0] * px + r.m[1] * py + r.m[2] * z;
+  const double y = r.m[3] * px + r.m[4] * py + r.m[5] * z;
+  const double zo = r.m[6] * px + r.m[7] * py + r.m[8] * z;
+  const double rxy = sqrt(x * x + y * y);
+  double lon = atan2(y, x);
+  if (lon < 0.0) lon += RSK_D2PI;
+  const double lat = atan2(zo, rxy);
+  int64_t pix[4] = {0, 0, 0, 0};
+  double wgt[4] = {0.0, 0.0, 0.0, 0.0};
+  hpx_interp_weights(nside, sin(lat), RSK_HALFPI - lat, lon, pix, wgt);
+  int64_t pos[4];
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int64_t p = pix[k];
+    if (nested) {  // ring -> nested through the pixel centre both orderings share
+      double zc, sc, pc;
+      rsk_hpx_center(nside, 0, p, zc, sc, pc);
+      p = rsk_hpx_pixel(nside, 1, zc, sc, pc);
+    }
+    pos[k] = lookup ? __ldg(lookup + p) : p - first;
+    ok = ok && pos[k] >= 0 && pos[k] < n_in;
+  }
+  if (blockIdx.y == 0) valid[j] = ok ? 1 : 0;
+  for (int64_t row = blockIdx.y; row < nrows; row += gridDim.y) {
+    double v = 0.0;
+    if (ok) {
+      const double* src = in + row * n_in;
+      // products and sums rounded one by one, in neighbour order, as numpy's (values * weights).sum(axis=0)
+      v = __dmul_rn(wgt[0], __ldg(src + pos[0]));
+      v = __dadd_rn(v, __dmul_rn(wgt[1], __ldg(src + pos[1])));
+      v = __dadd_rn(v, __dmul_rn(wgt[2], __ldg(src + pos[2])));
+      v = __dadd_rn(v, __dmul_rn(wgt[3], __ldg(src + pos[3])));
+    }
+    out[row * npix + j] = v;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) k_rise_set(const CoordSrc cs, const int64_t n, const double tan_tel,
                                                        const double buff, double* __restrict__ rise,
                                                        double* __restrict__ set) {
@@ -1609,6 +1748,22 @@ int rsk_rotate_lonlat(const double* lon, const double* lat, int64_t n, const dou
   Rot9 r;
   for (int i = 0; i < 9; ++i) r.m[i] = rot[i];
   k_rotate_lonlat<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(lon, lat, n, r, lon_out, lat_out);
+  return launch_status();
+}
+
+int rsk_healpix_interp(int64_t nside, int nested, const double* rot_new_to_old, const int64_t* lookup, int64_t hpx_first,
+                       int64_t n_in, const double* in, int64_t nrows, double* out, uint8_t* valid, void* stream) {
+  if (nside <= 0 || nside > (1ll << 29)) return RSK_ERR_NSIDE;
+  if (nested && (nside & (nside - 1)) != 0) return RSK_ERR_NSIDE;
+  if (n_in < 0 || nrows < 0) return RSK_ERR_SIZE;
+  if (!rot_new_to_old || !valid || (nrows > 0 && (!in || !out))) return RSK_ERR_NULL;
+  const int64_t npix = 12 * nside * nside;
+  if ((npix + kThreads - 1) / kThreads > 0x7fffffffll) return RSK_ERR_SIZE;
+  Rot9 r;
+  for (int i = 0; i < 9; ++i) r.m[i] = rot_new_to_old[i];
+  const dim3 grid(blocks_for(npix), (unsigned)std::max<int64_t>(1, std::min<int64_t>(nrows, 64)));
+  k_healpix_interp<<<grid, kThreads, 0, (cudaStream_t)stream>>>(nside, nested, r, lookup, hpx_first, n_in, in, nrows, out,
+                                                                valid);
   return launch_status();
 }
 

@@ -713,6 +713,69 @@ class SkyModel:
         self._frame_to_icrs = new_m
         self._rot_key = None  # the cached polarisation-rotation coefficients were for the old frame's basis
 
+    def healpix_interp_transform(self, frame, full_sky=False, inplace=True, run_check=True, check_extra=True,
+                                 run_check_acceptability=True, equinox=2000.0):
+        """Transform a HEALPix map to a new frame and interpolate to new pixel centers (skymodel.py:1448-1538).
+
+        The pixel centres of the new frame's map are rotated into the old frame and the old map is interpolated
+        bilinearly there (rsk_healpix_interp: what ``astropy_healpix.HEALPix.interpolate_bilinear_skycoord`` does at
+        :1507-1509), for every frequency in one launch.  As upstream, only Stokes I is carried (polarised maps raise),
+        a new pixel is kept when all four of its neighbours exist in the old map, and ``full_sky=True`` returns all
+        12 nside^2 pixels (zeros where the interpolation had no support).  Frames: 'icrs', 'fk5' (``equinox``),
+        'galactic'.  Per-pixel extras that cannot follow the resampling (``stokes_error``, ``beam_amp``, names, extra
+        columns) and the time-dependent attributes are cleared."""
+        this = self if inplace else self.copy()
+        if this.component_type != "healpix":
+            raise ValueError("Healpix frame interpolation is not valid for point source catalogs.")
+        if bool((this.stokes[1:] != 0).any()):
+            raise NotImplementedError(
+                "Healpix map transformations are currently not implemented for "
+                "catalogs with polarization information."
+            )
+        frame = str(getattr(frame, "name", frame)).lower()
+        new_m = astrometry.frame_to_icrs_matrix(frame, float(equinox))
+        rot = np.ascontiguousarray(this._frame_to_icrs.T @ new_m)  # new frame -> old frame
+        npix = 12 * this.nside * this.nside
+        n_in = this.Ncomponents
+        lookup = None
+        if this.hpx_inds is not None:
+            lookup = torch.full((npix,), -1, dtype=torch.int64, device=this.device)
+            lookup[this.hpx_inds] = torch.arange(n_in, dtype=torch.int64, device=this.device)
+        out = torch.zeros((4, this.Nfreqs, npix), dtype=torch.float64, device=this.device)
+        valid = torch.empty(npix, dtype=torch.uint8, device=this.device)
+        this._call("rsk_healpix_interp", this.nside, 1 if this.hpx_order == "nested" else 0, _lib.host_array(rot.ravel()),
+                   _lib.ptr(lookup), this.hpx_first, n_in, _lib.ptr(this.stokes[0].contiguous()), this.Nfreqs,
+                   _lib.ptr(out[0]), _lib.ptr(valid))
+        had_fc = this.frame_coherency is not None
+        if full_sky:
+            this.hpx_inds, this.hpx_first, m = None, 0, npix
+            this.stokes = out
+        else:
+            idx, m = this._compact_mask(valid)
+            if m == npix:
+                this.hpx_inds, this.hpx_first = None, 0
+                this.stokes = out
+            else:
+                idx = idx[:m].contiguous()
+                this.hpx_inds, this.hpx_first = idx, 0
+                this.stokes = this._gather(out, idx, m)
+        this.Ncomponents = m
+        this.frame = frame
+        this.hpx_frame = frame
+        this.equinox = float(equinox)
+        this._frame_to_icrs = new_m
+        this.name = None
+        this.stokes_error = this.beam_amp = this.extended_model_group = this.extra_columns = None
+        this.clear_time_position_specific_params()
+        this._polarized_mask = torch.zeros(m, dtype=torch.uint8, device=this.device)
+        this._n_polarized = 0
+        for cache in ("_rot", "_subband_cache", "_nan_group_cache", "_nan_cache", "_staging", "_graph", "_rise_lst", "_set_lst"):
+            this.__dict__.pop(cache, None)
+        this.frame_coherency = None
+        if had_fc:
+            this.calc_frame_coherency()  # recalculate the coherency now that we are in the new frame (:1528-1530)
+        return None if inplace else this
+
     def _check_tel_location(self, telescope_location):
         # skymodel.py:2391-2411 (the lunarsky/MoonLocation branch is out of scope)
         if not astrometry.is_earth_location(telescope_location):

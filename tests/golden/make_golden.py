@@ -206,7 +206,7 @@ def make_known_answers():
 
 
 def copy_skyh5_fixtures():
-    """Two of the reference's own (small) SkyH5 test *data* fixtures, byte for byte (under names that say where
+    """Three of the reference's own (small) SkyH5 test *data* fixtures, byte for byte (under names that say where
     they come from): files written by h5py / libhdf5 that the product's HDF5 reader (include/rsk_io.h) must read
     without libhdf5 -- the only h5py-written bytes available in an image that has neither h5py nor libhdf5.
 
@@ -215,12 +215,16 @@ def copy_skyh5_fixtures():
       (docs/tutorial.rst:1288-1297, transcribed into ``skyh5_known_answers.json``).
     * ``old_skyh5_point_sources.skyh5`` (50 GLEAM sources x 20 subbands, ``ra``/``dec`` in degrees) -- read by
       tests/test_skymodel.py:4507-4522, which fixes the warnings and the subband -> full downgrade.
+    * ``gsm_galactic.skyh5`` (the same map in the galactic frame): ``healpix_interp_transform("icrs")`` of it must
+      equal ``gsm_icrs.skyh5`` (tests/test_skymodel.py:4423-4452) -- the golden pair that pins the bilinear
+      HEALPix interpolation and the galactic -> ICRS rotation.
     """
     import shutil
 
     src = "/root/reference/src/pyradiosky/data"
     for name, fixture in (("gsm_icrs.skyh5", "ref_fixture_gsm_icrs_nside8.skyh5"),
-                          ("old_skyh5_point_sources.skyh5", "ref_fixture_gleam50_old_header.skyh5")):
+                          ("old_skyh5_point_sources.skyh5", "ref_fixture_gleam50_old_header.skyh5"),
+                          ("gsm_galactic.skyh5", "ref_fixture_gsm_galactic_nside8.skyh5")):
         shutil.copyfile(os.path.join(src, name), os.path.join(HERE, fixture))
     ka = {
         "gsm_icrs": {

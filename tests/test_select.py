@@ -768,3 +768,127 @@ def test_equality_operator(rsk, site):
     assert hp_a == hp_b
     hp_c = rsk.SkyModel(nside=4, stokes=np.ones((4, 1, 192)), spectral_type="flat", hpx_frame="icrs", hpx_order="nested")
     assert hp_a != hp_c
+
+
+# ---------------------------------------------------------------------------------------------------
+# healpix_interp_transform (skymodel.py:1448-1538): bilinear HEALPix interpolation into a new frame
+# ---------------------------------------------------------------------------------------------------
+GSM_GAL = os.path.join(ROOT, "tests", "golden", "ref_fixture_gsm_galactic_nside8.skyh5")
+
+
+def test_oracle_interpolation_reproduces_reference_golden_pair():
+    """tests/test_skymodel.py:4423-4452: gsm_galactic.skyh5 transformed to ICRS must equal gsm_icrs.skyh5 (UVParameter
+    tolerance rtol 1e-5).  This pins oracle/healpix_np.interp_weights and the galactic -> ICRS rotation."""
+    g, i = h5_np.File(GSM_GAL), h5_np.File(GSM)
+    sg, si = np.array(g["/Data/stokes"].read(), float), np.array(i["/Data/stokes"].read(), float)
+    hg, hi = np.array(g["/Header/hpx_inds"].read()), np.array(i["/Header/hpx_inds"].read())
+    assert bytes(g["/Header/frame"].read()) == b"galactic" and bytes(i["/Header/frame"].read()) == b"icrs"
+    rot = E.frame_to_icrs("galactic").T  # icrs (new) -> galactic (old)
+    worst = 0.0
+    for f in range(sg.shape[1]):
+        inds, vals = hp.interp_transform(8, False, hg, sg[0, f], rot)
+        assert np.array_equal(inds, hi)
+        worst = max(worst, (np.abs(vals - si[0, f]) / np.abs(si[0, f])).max())
+    assert worst < 2e-6  # observed 9.7e-7; the reference's own comparison allows 1e-5
+
+
+def test_oracle_interpolation_weights_properties():
+    rng = np.random.default_rng(41)
+    for nside in (1, 2, 8, 64):
+        npix = 12 * nside * nside
+        lon = np.concatenate([rng.uniform(0, 2 * np.pi, 4000), [0.0, 1e-12, 2 * np.pi - 1e-12, 3.0, 3.0]])
+        lat = np.concatenate([np.arcsin(rng.uniform(-1, 1, 4000)), [0.0, 0.0, 0.0, np.pi / 2 - 1e-9, -np.pi / 2 + 1e-9]])
+        pix, wgt = hp.interp_weights(nside, lon, lat)
+        assert pix.min() >= 0 and pix.max() < npix
+        assert np.abs(wgt.sum(axis=0) - 1).max() < 1e-12 and wgt.min() > -1e-12 and wgt.max() < 1 + 1e-12
+        # a constant map is reproduced, and so is the map value at a pixel centre
+        assert np.abs((wgt * np.ones(npix)[pix]).sum(axis=0) - 1).max() < 1e-12
+        clon, clat = hp.healpix_to_lonlat(nside, np.arange(npix))
+        cp, cw = hp.interp_weights(nside, clon, clat)
+        vals = rng.normal(size=npix)
+        assert np.abs((cw * vals[cp]).sum(axis=0) - vals).max() < 1e-9
+        # nested numbering names the same four pixels
+        pn, wn = hp.interp_weights(nside, lon, lat, nested=True) if nside & (nside - 1) == 0 else (None, None)
+        if pn is not None:
+            assert np.array_equal(pn, hp.ring2nest(nside, pix.ravel()).reshape(pix.shape)) and np.array_equal(wn, wgt)
+        # continuity: a small step moves the interpolated value of a smooth map by a small amount
+        zmap = np.sin(clat) + 0.3 * np.cos(clon) * np.cos(clat)
+        v0 = (wgt * zmap[pix]).sum(axis=0)
+        p1, w1 = hp.interp_weights(nside, lon + 1e-7, lat)
+        assert np.abs((w1 * zmap[p1]).sum(axis=0) - v0).max() < 1e-5
+
+
+@pytest.mark.gpu
+def test_healpix_interp_transform_golden_pair(rsk):
+    """tests/test_skymodel.py:4423-4452 on the GPU: galactic GSM map -> ICRS equals the reference's ICRS file."""
+    import torch
+
+    gal = rsk.SkyModel.from_skyh5(GSM_GAL)
+    icrs = rsk.SkyModel.from_skyh5(GSM)
+    assert gal.frame == "galactic" and icrs.frame == "icrs" and gal.Ncomponents == 768
+    gal.calc_frame_coherency()
+    before = gal.copy()
+    new = gal.healpix_interp_transform("icrs", inplace=False)
+    assert gal == before and new != gal
+    assert new.frame == "icrs" and new.Ncomponents == 768 and new.frame_coherency is not None
+    rel = ((new.stokes[0] - icrs.stokes[0]).abs() / icrs.stokes[0].abs()).max()
+    assert float(rel) < 2e-6
+    new.history, new.filename = icrs.history, icrs.filename
+    new.frame_coherency = None
+    assert new == icrs  # the reference's assertion, to its own (rtol 1e-5) tolerance
+    gal.healpix_interp_transform("icrs")
+    assert torch.equal(gal.stokes, new.stokes)
+    # the oracle, value for value
+    g = h5_np.File(GSM_GAL)
+    sg = np.array(g["/Data/stokes"].read(), float)
+    rot = E.frame_to_icrs("galactic").T
+    for f in (0, 9):
+        _, vals = hp.interp_transform(8, False, np.arange(768), sg[0, f], rot)
+        assert np.abs(new.stokes[0, f].cpu().numpy() - vals).max() < 1e-9 * np.abs(vals).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", ["ring", "nested"])
+def test_healpix_interp_transform_partial_sky(rsk, order):
+    """Partial maps: pixels whose four neighbours are not all present drop out; full_sky keeps them as zeros
+    (tests/test_skymodel.py:4488-4503); ring and nested; errors (:4455-4485)."""
+    rng = np.random.default_rng(43)
+    nside, nf = 16, 3
+    npix = 12 * nside * nside
+    nested = order == "nested"
+    lon, lat = hp.healpix_to_lonlat(nside, np.arange(npix), nested=nested)
+    have = np.nonzero(lat > -0.3)[0]                      # a cap-and-belt map
+    have = have[rng.permutation(have.size)]               # in scrambled order
+    vals = 5.0 + np.sin(lat) + 0.3 * np.cos(lon) * np.cos(lat)
+    st = np.zeros((4, nf, have.size))
+    st[0] = vals[have][None, :] * np.array([1.0, 2.0, 3.0])[:, None]
+    sky = rsk.SkyModel(nside=nside, hpx_order=order, hpx_frame="icrs", hpx_inds=have, stokes=st, spectral_type="full",
+                       freq_array=np.array([1e8, 1.1e8, 1.2e8]), stokes_unit="K")
+    rot = E.frame_to_icrs("icrs").T @ E.frame_to_icrs("galactic")  # galactic (new) -> icrs (old)
+    want_inds, want0 = hp.interp_transform(nside, nested, have, st[0, 0], rot)
+    new = sky.healpix_interp_transform("galactic", inplace=False)
+    assert 0 < new.Ncomponents < npix
+    assert np.array_equal(new.hpx_inds.cpu().numpy(), want_inds)
+    got = new.stokes.cpu().numpy()
+    assert np.abs(got[0, 0] - want0).max() < 1e-12 and np.abs(got[0, 2] - 3 * want0).max() < 1e-11
+    assert not got[1:].any()
+    # a smooth map is interpolated to within the pixel scale of its true value at the new centres
+    glon, glat = (x.cpu().numpy() for x in new.get_lon_lat())
+    v = E.frame_to_icrs("galactic") @ E.s2c(glon, glat)
+    truth = 5.0 + v[2] + 0.3 * v[0]
+    assert np.abs(got[0, 0] - truth).max() < 5e-3
+    full = sky.healpix_interp_transform("galactic", full_sky=True, inplace=False)
+    assert full.Ncomponents == npix and full.hpx_inds is None
+    fs = full.stokes.cpu().numpy()[0, 0]
+    assert np.array_equal(np.nonzero(fs)[0], want_inds) and np.abs(fs[want_inds] - want0).max() < 1e-12
+    # errors
+    pt = rsk.SkyModel(ra=[0.1], dec=[0.2], stokes=np.ones((4, 1, 1)), spectral_type="flat")
+    with pytest.raises(ValueError, match="Healpix frame interpolation is not valid for point source catalogs."):
+        pt.healpix_interp_transform("galactic")
+    sky.stokes[1] = sky.stokes[0]
+    with pytest.raises(NotImplementedError, match="Healpix map transformations are currently not implemented for"):
+        sky.healpix_interp_transform("galactic")
+    from pyradiosky_b200 import _lib
+
+    assert _lib.load().rsk_healpix_interp(0, 0, None, None, 0, 0, None, 0, None, None, None) == -7
+    assert _lib.load().rsk_healpix_interp(8, 0, None, None, 0, 0, None, 0, None, None, None) == -1
