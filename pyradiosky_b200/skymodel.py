@@ -446,16 +446,205 @@ class SkyModel:
         self.__init__(**skyh5.read_skyh5_params(filename, self.device, skip_params=skip_params, nthreads=nthreads),
                       device=self.device)
 
+    # ------------------------------------------------------------------------------------------
+    # VOTable catalogues (skymodel.py:3779-4203): host-side parsing, arrays to the GPU through __init__
+    # ------------------------------------------------------------------------------------------
+    def read_votable_catalog(self, votable_file, table_name, id_column, lon_column, lat_column, flux_columns, frame,
+                             reference_frequency=None, freq_array=None, freq_edge_array=None, spectral_index_column=None,
+                             flux_error_columns=None, history="", run_check=True, check_extra=True,
+                             run_check_acceptability=True):
+        """Read a votable catalog file into this object (skymodel.py:3779-4025).
+
+        Same column matching (a column is named by a part of its name that matches exactly one column), spectral-type
+        rules, unit checks, warnings and errors as the reference; the file is parsed by ``pyradiosky_b200.votable``
+        (TABLEDATA serialisation, no astropy).  ``frame``: 'icrs', 'fk5' or 'galactic'; frequencies in Hz or
+        Quantity-like."""
+        from . import votable as vot
+        from .skyh5 import get_freq_edges_from_centers
+
+        tables = vot.parse(votable_file)
+        if any(t.ID is None for t in tables):
+            raise ValueError(f"File {votable_file} contains tables with no name or ID.")
+        try:
+            use = vot.get_matching_fields(table_name, [t.ID for t in tables])
+            table = [t for t in tables if t.ID == use][0]
+        except ValueError:
+            use = vot.get_matching_fields(table_name, [t.name for t in tables])
+            table = [t for t in tables if t.name == use][0]
+        cols = table.colnames
+        id_col = vot.get_matching_fields(id_column, cols)
+        lon_col = vot.get_matching_fields(lon_column, cols, exclude_start_pattern="_")
+        lat_col = vot.get_matching_fields(lat_column, cols, exclude_start_pattern="_")
+        if isinstance(flux_columns, str):
+            flux_columns = [flux_columns]
+        flux_cols = [vot.get_matching_fields(c, cols) for c in flux_columns]
+        freq_array = _to_hz_host(freq_array)
+        freq_edge_array = None if freq_edge_array is None else np.asarray(_to_hz_host(freq_edge_array)).reshape(2, -1)
+        if len(flux_columns) > 1 and freq_array is None and freq_edge_array is None:
+            raise ValueError(
+                "Frequency information must be provided with multiple flux columns. "
+                "Must provide either freq_edge_array or freq_array (if the "
+                "frequencies are evenly spaced), both can be provided."
+            )
+        if len(flux_columns) > 1:
+            if freq_edge_array is None:
+                try:
+                    freq_edge_array = get_freq_edges_from_centers(freq_array, atol=1.0)
+                    warnings.warn("freq_edge_array not set, calculating it from the freq_array.")
+                except ValueError as ve:
+                    raise ValueError("freq_edge_array must be provided for multiple flux columns if "
+                                     "freq_array is not regularly spaced.") from ve
+            elif freq_array is None:
+                warnings.warn("freq_array not set, calculating it from the freq_edge_array.")
+                freq_array = np.mean(freq_edge_array, axis=0)
+        n = len(table)
+        spectral_index = None
+        if reference_frequency is not None or len(flux_cols) == 1:
+            if reference_frequency is not None:
+                rf = reference_frequency.to_value("Hz") if hasattr(reference_frequency, "to_value") else reference_frequency
+                reference_frequency = np.full(n, float(np.asarray(rf).ravel()[0]))
+            if spectral_index_column is not None:
+                spectral_type = "spectral_index"
+                spectral_index = table.columns[vot.get_matching_fields(spectral_index_column, cols)]
+            else:
+                spectral_type = "flat"
+        else:
+            spectral_type = "subband"
+
+        def flux_unit(col):
+            return vot.FLUX_UNITS.get((table.units[col] or "").strip(), (None, None))
+
+        kinds = {flux_unit(c)[0] for c in flux_cols}
+        if len(kinds) != 1 or None in kinds:
+            raise ValueError("All flux columns must have compatible units and must be compatible "
+                             "with one of ['Jy', 'Jy/sr', 'K', 'K sr'].")
+        unit_use = kinds.pop()
+        stokes = np.zeros((4, len(flux_cols), n))
+        for k, c in enumerate(flux_cols):
+            stokes[0, k] = table.columns[c] * flux_unit(c)[1]
+        stokes_error = None
+        if flux_error_columns is not None:
+            if isinstance(flux_error_columns, str):
+                flux_error_columns = [flux_error_columns]
+            err_cols = [vot.get_matching_fields(c, cols) for c in flux_error_columns]
+            if any(flux_unit(c)[0] != unit_use for c in err_cols):
+                raise ValueError("All flux error columns must have units compatible with the units "
+                                 "of the flux columns.")
+            stokes_error = np.zeros((4, len(err_cols), n))
+            for k, c in enumerate(err_cols):
+                stokes_error[0, k] = table.columns[c] * flux_unit(c)[1]
+        angle = {}
+        for what, c in (("lon", lon_col), ("lat", lat_col)):
+            u = (table.units[c] or "deg").strip()
+            if u not in vot.ANGLE_UNITS:
+                raise ValueError(f"column {c} has unit {u!r}, which is not an angle")
+            angle[what] = table.columns[c] * vot.ANGLE_UNITS[u]
+        self.__init__(name=table.columns[id_col].astype(str), lon=np.mod(angle["lon"], 2 * np.pi), lat=angle["lat"],
+                      frame=str(getattr(frame, "name", frame)).lower(), stokes=stokes, stokes_unit=unit_use,
+                      spectral_type=spectral_type, freq_array=freq_array if spectral_type == "subband" else None,
+                      freq_edge_array=freq_edge_array if spectral_type == "subband" else None,
+                      reference_frequency=reference_frequency, spectral_index=spectral_index, stokes_error=stokes_error,
+                      history=history, filename=[os.path.basename(os.fspath(votable_file))],
+                      device=self.__dict__.get("device"))
+
     @classmethod
-    def from_file(cls, filename, filetype=None, **kwargs):
-        """``SkyModel.from_file`` (skymodel.py:4864-4868) for the formats this build reads: 'skyh5'."""
-        if filetype is None:
-            ext = os.path.splitext(os.fspath(filename))[1]
-            filetype = {".skyh5": "skyh5"}.get(ext)
-        if filetype != "skyh5":
-            raise ValueError("Only the 'skyh5' file type is supported by pyradiosky_b200; got "
-                             f"{filetype!r} for {filename}")
-        return cls.from_skyh5(filename, **kwargs)
+    def from_votable_catalog(cls, votable_file, *args, device=None, **kwargs):
+        """Create a new :class:`SkyModel` from a votable catalog (skymodel.py:4027-4031)."""
+        sm = cls.__new__(cls)
+        sm.device = device
+        sm.read_votable_catalog(votable_file, *args, **kwargs)
+        return sm
+
+    def read_gleam_catalog(self, gleam_file, spectral_type="subband", with_error=False, use_paper_freqs=False,
+                           run_check=True, check_extra=True, run_check_acceptability=True):
+        """Read the GLEAM votable catalog file into this object (skymodel.py:4033-4195; GLEAM EGC catalog, version 2).
+
+        ``spectral_type``: 'flat' (wide-band integrated flux, 200 MHz), 'spectral_index' (fitted flux at 200 MHz and
+        ``alpha``; NaN where the fit failed) or 'subband' (the 20 sub-band fluxes with the catalogue's band centres and
+        edges, or the 7.68 MHz-spaced ones with ``use_paper_freqs``); ``with_error`` adds the fitting errors as
+        ``stokes_error``."""
+        spec_type_list = ["flat", "spectral_index", "subband"]
+        if spectral_type not in spec_type_list:
+            raise ValueError(f"spectral_type {spectral_type} is not an allowed type. Allowed types are: {spec_type_list}")
+        freq_array = freq_edge_array = reference_frequency = spectral_index_column = None
+        if spectral_type == "flat":
+            flux_columns, flux_error_columns, reference_frequency = "Fintwide", "e_Fintwide", 200e6
+        elif spectral_type == "spectral_index":
+            flux_columns, flux_error_columns, reference_frequency = "Fintfit200", "e_Fintfit200", 200e6
+            spectral_index_column = "alpha"
+        else:
+            bands = ["076", "084", "092", "099", "107", "115", "122", "130", "143", "151", "158", "166", "174", "181",
+                     "189", "197", "204", "212", "220", "227"]
+            flux_columns = ["Fint" + b for b in bands]
+            flux_error_columns = ["e_Fint" + b for b in bands]
+            if use_paper_freqs:
+                # 24 fine channels of 1.28 MHz in each of 5 coarse bands, four sub-bands of six channels each (:4129-4139)
+                starts = np.array([57, 81, 109, 133, 157])
+                chans = np.arange(24)[np.newaxis, :] + starts[:, np.newaxis]
+                temp = np.reshape(chans, (5, 4, 6)) * 1.28 * 1e6
+                freq_array = np.reshape(np.mean(temp, axis=2), 20)
+                freq_lower = np.reshape(np.min(temp, axis=2), 20)
+                freq_upper = np.reshape(np.max(temp, axis=2), 20)
+            else:
+                freq_array = np.array([76, 84, 92, 99, 107, 115, 122, 130, 143, 151, 158, 166, 174, 181, 189, 197, 204,
+                                       212, 220, 227]) * 1e6
+                freq_lower = np.array([72, 80, 88, 95, 103, 111, 118, 126, 139, 147, 154, 162, 170, 177, 185, 193, 200,
+                                       208, 216, 223]) * 1e6
+                freq_upper = np.array([80, 88, 95, 103, 111, 118, 126, 134, 147, 154, 162, 170, 177, 185, 193, 200, 208,
+                                       216, 223, 231]) * 1e6
+            freq_edge_array = np.stack([freq_lower, freq_upper])
+        if not with_error:
+            flux_error_columns = None
+        self.read_votable_catalog(gleam_file, "GLEAM", "GLEAM", "RAJ2000", "DEJ2000", frame="fk5",
+                                  flux_columns=flux_columns, freq_array=freq_array, freq_edge_array=freq_edge_array,
+                                  reference_frequency=reference_frequency, spectral_index_column=spectral_index_column,
+                                  flux_error_columns=flux_error_columns)
+
+    @classmethod
+    def from_gleam_catalog(cls, gleam_file, device=None, **kwargs):
+        """Create a :class:`SkyModel` from a GLEAM catalog (skymodel.py:4197-4203)."""
+        sm = cls.__new__(cls)
+        sm.device = device
+        sm.read_gleam_catalog(gleam_file, **kwargs)
+        return sm
+
+    @classmethod
+    def from_file(cls, filename, filetype=None, spectral_type=None, with_error=False, use_paper_freqs=False,
+                  table_name=None, id_column=None, lon_column=None, lat_column=None, frame=None, flux_columns=None,
+                  reference_frequency=None, freq_array=None, freq_edge_array=None, spectral_index_column=None,
+                  flux_error_columns=None, history="", device=None, **kwargs):
+        """``SkyModel.from_file`` (skymodel.py:4629-4868) for the formats this build reads: 'skyh5', 'gleam', 'vot'."""
+        allowed_filetypes = ["skyh5", "gleam", "vot", "text", "fhd"]
+        name = os.fspath(filename)
+        if filetype is not None:
+            if filetype not in allowed_filetypes:
+                raise ValueError(f"Invalid filetype. Filetype options are: {allowed_filetypes}")
+        else:
+            ext = os.path.splitext(name)[1]
+            if ext == ".vot":
+                filetype = "gleam" if "gleam" in name.casefold() else "vot"
+            else:
+                filetype = {".skyh5": "skyh5", ".txt": "text", ".sav": "fhd"}.get(ext)
+            if filetype is None:
+                raise ValueError("Cannot determine the file type.")
+        if filetype == "skyh5":
+            return cls.from_skyh5(filename, device=device, **kwargs)
+        if filetype == "gleam":
+            return cls.from_gleam_catalog(filename, device=device, spectral_type=spectral_type or "subband",
+                                          with_error=with_error, use_paper_freqs=use_paper_freqs)
+        if filetype == "vot":
+            required = {"table_name": table_name, "id_column": id_column, "lon_column": lon_column,
+                        "lat_column": lat_column, "flux_columns": flux_columns, "frame": frame}
+            for key, val in required.items():
+                if val is None:
+                    raise ValueError(f"{key} is required when reading vot files.")
+            return cls.from_votable_catalog(filename, table_name, id_column, lon_column, lat_column, flux_columns, frame,
+                                            device=device, reference_frequency=reference_frequency,
+                                            freq_array=freq_array, freq_edge_array=freq_edge_array,
+                                            spectral_index_column=spectral_index_column,
+                                            flux_error_columns=flux_error_columns, history=history)
+        raise ValueError("Only the 'skyh5', 'gleam' and 'vot' file types are supported by pyradiosky_b200; got "
+                         f"{filetype!r} for {filename}")
 
     def write_skyh5(self, filename, clobber=False, data_compression=None, **_checks):
         """Write this object to a SkyH5 file (skymodel.py:4871-5029)."""

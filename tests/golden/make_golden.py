@@ -224,7 +224,12 @@ def copy_skyh5_fixtures():
     src = "/root/reference/src/pyradiosky/data"
     for name, fixture in (("gsm_icrs.skyh5", "ref_fixture_gsm_icrs_nside8.skyh5"),
                           ("old_skyh5_point_sources.skyh5", "ref_fixture_gleam50_old_header.skyh5"),
-                          ("gsm_galactic.skyh5", "ref_fixture_gsm_galactic_nside8.skyh5")):
+                          ("gsm_galactic.skyh5", "ref_fixture_gsm_galactic_nside8.skyh5"),
+                          # VOTable test data (TABLEDATA text): the 50-source GLEAM extract every GLEAM test of the
+                          # reference reads (tests/test_skymodel.py:2879-3077), its two-row file and its ID-less one
+                          ("gleam_50srcs.vot", "ref_fixture_gleam_50srcs.vot"),
+                          ("simple_test.vot", "ref_fixture_simple_test.vot"),
+                          ("single_source_old.vot", "ref_fixture_single_source_old.vot")):
         shutil.copyfile(os.path.join(src, name), os.path.join(HERE, fixture))
     ka = {
         "gsm_icrs": {
