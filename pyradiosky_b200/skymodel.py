@@ -335,7 +335,8 @@ class SkyModel:
 
     def __eq__(self, other):
         """Equality of every parameter, as UVBase.__eq__ gives the reference's object (arrays to the UVParameter default
-        tolerances rtol 1e-5 / atol 1e-8, angles to 1e-12 rad, NaNs equal to NaNs, histories up to white space)."""
+        tolerances rtol 1e-5 / atol 1e-8, angles to pyuvdata's 1 mas (RADIAN_TOL), NaNs equal to NaNs, histories up to
+        white space)."""
         if not isinstance(other, SkyModel):
             return False
         for attr in ("component_type", "spectral_type", "Ncomponents", "Nfreqs", "stokes_unit", "frame", "equinox", "nside",
@@ -396,7 +397,7 @@ class SkyModel:
                 if not torch.equal(x, y):
                     return False
             elif attr in angles or attr in ("lon", "lat"):
-                if not torch.allclose(x, y, rtol=0.0, atol=1e-12, equal_nan=True):
+                if not torch.allclose(x, y, rtol=0.0, atol=4.848136811095360e-09, equal_nan=True):
                     return False
             elif not torch.allclose(x, y, rtol=1e-5, atol=1e-8, equal_nan=True):
                 return False
@@ -608,12 +609,59 @@ class SkyModel:
         sm.read_gleam_catalog(gleam_file, **kwargs)
         return sm
 
+    # ------------------------------------------------------------------------------------------
+    # text catalogues (skymodel.py:4204-4413, :5031-5182)
+    # ------------------------------------------------------------------------------------------
+    def read_text_catalog(self, catalog_csv, run_check=True, check_extra=True, run_check_acceptability=True):
+        """Read a text file of sources into this object (skymodel.py:4204-4407): columns ``source_id``,
+        ``<lon>_<frame>``, ``<lat>_<frame>`` in degrees, then ``Flux [Jy]`` (+ ``Frequency`` [Hz], ``Spectral_Index``) or one
+        ``Flux_<f>_<unit>`` column per frequency, each optionally followed by its ``Flux_error`` column."""
+        from . import textcat
+
+        kw = textcat.read(catalog_csv)
+        self.__init__(**kw, filename=[os.path.basename(os.fspath(catalog_csv))], history="",
+                      device=self.__dict__.get("device"))
+
+    @classmethod
+    def from_text_catalog(cls, catalog_csv, device=None, **kwargs):
+        """Create a :class:`SkyModel` from a text catalog (skymodel.py:4409-4413)."""
+        sm = cls.__new__(cls)
+        sm.device = device
+        sm.read_text_catalog(catalog_csv, **kwargs)
+        return sm
+
+    def write_text_catalog(self, filename):
+        """Write out this object to a text file (skymodel.py:5031-5182).  Text files hold point sources in Jy without
+        subbands or extended-model groups; readable with :meth:`read_text_catalog`."""
+        from . import textcat
+
+        if self.component_type != "point":
+            raise ValueError("component_type must be 'point' to use this method.")
+        if self.stokes_unit != "Jy":
+            raise ValueError("Stokes units must be equivalent to Jy to use this method.")
+        if self.spectral_type == "subband":
+            raise ValueError(
+                "Text files do not support subband types, use write_skyh5. If you "
+                "really need to get this into a text file, you could convert this "
+                "to a 'full' spectral type (losing the frequency edge array "
+                "information)."
+            )
+        if self.extended_model_group is not None:
+            raise ValueError(
+                "Text files do not support catalogs with extended_model_group, "
+                "use write_skyh5. If you really need to get this into a text file, "
+                "you could remove the extended_model_group information."
+            )
+        if self.name is None:
+            raise ValueError("component names are required to write a text catalog.")
+        textcat.write(filename, self)
+
     @classmethod
     def from_file(cls, filename, filetype=None, spectral_type=None, with_error=False, use_paper_freqs=False,
                   table_name=None, id_column=None, lon_column=None, lat_column=None, frame=None, flux_columns=None,
                   reference_frequency=None, freq_array=None, freq_edge_array=None, spectral_index_column=None,
                   flux_error_columns=None, history="", device=None, **kwargs):
-        """``SkyModel.from_file`` (skymodel.py:4629-4868) for the formats this build reads: 'skyh5', 'gleam', 'vot'."""
+        """``SkyModel.from_file`` (skymodel.py:4629-4868) for the formats this build reads: 'skyh5', 'gleam', 'vot', 'text'."""
         allowed_filetypes = ["skyh5", "gleam", "vot", "text", "fhd"]
         name = os.fspath(filename)
         if filetype is not None:
@@ -643,7 +691,9 @@ class SkyModel:
                                             freq_array=freq_array, freq_edge_array=freq_edge_array,
                                             spectral_index_column=spectral_index_column,
                                             flux_error_columns=flux_error_columns, history=history)
-        raise ValueError("Only the 'skyh5', 'gleam' and 'vot' file types are supported by pyradiosky_b200; got "
+        if filetype == "text":
+            return cls.from_text_catalog(filename, device=device)
+        raise ValueError("Only the 'skyh5', 'gleam', 'vot' and 'text' file types are supported by pyradiosky_b200; got "
                          f"{filetype!r} for {filename}")
 
     def write_skyh5(self, filename, clobber=False, data_compression=None, **_checks):

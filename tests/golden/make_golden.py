@@ -229,7 +229,10 @@ def copy_skyh5_fixtures():
                           # reference reads (tests/test_skymodel.py:2879-3077), its two-row file and its ID-less one
                           ("gleam_50srcs.vot", "ref_fixture_gleam_50srcs.vot"),
                           ("simple_test.vot", "ref_fixture_simple_test.vot"),
-                          ("single_source_old.vot", "ref_fixture_single_source_old.vot")):
+                          ("single_source_old.vot", "ref_fixture_single_source_old.vot"),
+                          # text catalogues read by tests/test_skymodel.py:3214-3238 and :3436-3441
+                          ("pointsource_catalog.txt", "ref_fixture_pointsource_catalog.txt"),
+                          ("mock_hera_text_2458098.27471.txt", "ref_fixture_mock_hera_text.txt")):
         shutil.copyfile(os.path.join(src, name), os.path.join(HERE, fixture))
     ka = {
         "gsm_icrs": {

@@ -166,3 +166,141 @@ def test_read_votable_and_errors(rsk, tmp_path):
         reg2 = rsk.SkyModel.from_votable_catalog(GLEAM_VOT, "GLEAM", "GLEAM", "RAJ2000", "DEJ2000", ["Fint076", "Fint084"],
                                                  frame="fk5", freq_edge_array=np.array([[72e6, 80e6], [80e6, 88e6]]))
     assert np.array_equal(reg2.freq_array, [76e6, 84e6])
+
+
+# ---------------------------------------------------------------------------------------------------
+# text catalogues (skymodel.py:4204-4413, :5031-5182; tests/test_skymodel.py:3214-3470)
+# ---------------------------------------------------------------------------------------------------
+POINT_TXT = os.path.join(GOLDEN, "ref_fixture_pointsource_catalog.txt")
+MOCK_TXT = os.path.join(GOLDEN, "ref_fixture_mock_hera_text.txt")
+
+
+def test_text_reader_on_reference_files():
+    """tests/test_skymodel.py:3214-3238 and :3436-3441 (host side)."""
+    from pyradiosky_b200 import textcat
+
+    kw = textcat.read(POINT_TXT)
+    assert kw["frame"] == "fk5" and kw["equinox"] == 2000.0 and kw["spectral_type"] == "flat"
+    assert kw["name"].tolist() == ["src1", "src2", "src3"]
+    assert np.allclose(np.rad2deg(kw["lon"]), [1.0, 1.3, 1.35]) and np.allclose(np.rad2deg(kw["lat"]), [-30, -31, -32])
+    assert kw["stokes"][0, 0].tolist() == [0.5, 2.0, 5.0] and kw["reference_frequency"].tolist() == [1e6] * 3
+    mock = textcat.read(MOCK_TXT)
+    assert mock["name"].tolist() == ["src" + str(k) for k in range(mock["stokes"].shape[2])]
+    assert mock["reference_frequency"][0] == 150e6 and mock["stokes"][0, 0, 0] == 1.0
+
+
+def test_text_frame_columns_and_frequencies():
+    """skymodel.py:116-203 for the frames carried here; tests/test_skymodel.py:2832-2875."""
+    from pyradiosky_b200.textcat import frame_comp_cols, frame_desc_str, name2freq
+
+    assert frame_comp_cols(["source_id", "RA_J2000", "Dec_J2000", "Flux"]) == ("fk5", 2000.0, "RA_J2000", "Dec_J2000")
+    assert frame_comp_cols(["source_id", "ra_j2000", "de_j2000"])[2:] == ("ra_j2000", "de_j2000")
+    assert frame_comp_cols(["source_id", "ra_icrs", "dec_icrs"]) == ("icrs", 2000.0, "ra_icrs", "dec_icrs")
+    assert frame_comp_cols(["source_id", "l_galactic", "b_galactic"]) == ("galactic", 2000.0, "l_galactic", "b_galactic")
+    assert frame_comp_cols(["source_id", "ra_fk5_j2002.000", "dec_fk5_j2002.000"])[:2] == ("fk5", 2002.0)
+    assert frame_comp_cols(["source_id", "ra_b1950", "dec_b1950"])[0] == "fk4"
+    with pytest.raises(ValueError, match="frame not recognized from coordinate column"):
+        frame_comp_cols(["source_id", "ra_foo", "dec_foo"])
+    with pytest.raises(ValueError, match="Longitudinal and Latidudinal component columns not identified."):
+        frame_comp_cols(["source_id", "foo_icrs", "dec_icrs"])
+    with pytest.raises(ValueError, match="Latitudinal component column not identified."):
+        frame_comp_cols(["source_id", "ra_j2000", "foo_j2000x"])
+    assert frame_desc_str("fk5", 2000.0) == "j2000" and frame_desc_str("fk5", 2002.0) == "fk5_J2002.000"
+    assert frame_desc_str("icrs", 2000.0) == "icrs" and frame_desc_str("galactic", 2000.0) == "galactic"
+    with pytest.raises(ValueError, match="fk4 is not supported for writing text files."):
+        frame_desc_str("fk4", 1950.0)
+    assert name2freq("Flux_150_MHz") == 150e6 and name2freq("Flux_1.5_GHz") == 1.5e9
+    assert name2freq("Flux_200_kHz") == 200e3 and name2freq("Flux_76_Hz") == 76.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_error", [False, True])
+@pytest.mark.parametrize("spec_type", ["flat", "spectral_index", "full", "subband"])
+def test_text_catalog_loop(rsk, tmp_path, spec_type, with_error):
+    """tests/test_skymodel.py:3285-3337: write_text_catalog -> from_file gives the object back."""
+    sky = rsk.SkyModel.from_file(GLEAM_VOT, spectral_type="subband" if spec_type == "full" else spec_type,
+                                 with_error=with_error)
+    if spec_type in ("full", "subband"):
+        sky.select(non_nan="any")  # ('nan' cells round-trip through text, but NaN != NaN in the numpy reader's eyes)
+    if spec_type == "spectral_index":
+        sky.select(component_inds=np.nonzero(~np.isnan(sky.spectral_index.cpu().numpy()))[0])
+    if spec_type == "full":
+        sky.at_frequencies(sky.freq_array)
+        sky.freq_edge_array = None
+    sky.calculate_rise_set_lsts(-0.5361)
+    sky.frame_coherency = None
+    fname = str(tmp_path / "temp_cat.txt")
+    if spec_type == "subband":
+        with pytest.raises(ValueError, match="Text files do not support subband types, use write_skyh5."):
+            sky.write_text_catalog(fname)
+        return
+    sky.write_text_catalog(fname)
+    sky2 = rsk.SkyModel.from_file(fname)
+    assert sky2.spectral_type == spec_type and sky2.filename == ["temp_cat.txt"] and sky2.frame == "fk5"
+    sky2.filename, sky2.history = sky.filename, sky.history
+    assert sky2 == sky  # values written with 8 decimals: equal at the UVParameter tolerances
+    if spec_type == "flat":
+        # again with no reference_frequency field
+        ref = sky.reference_frequency
+        sky.reference_frequency = None
+        sky.write_text_catalog(fname)
+        sky2 = rsk.SkyModel.from_file(fname, run_check=False)
+        sky2.filename, sky2.history = sky.filename, sky.history
+        assert sky2 == sky and sky2.reference_frequency is None
+        # again with flat & freq_array, in other units too (:3340-3351)
+        for mult in (1.0, 1e-6, 1e-3, 1e3):
+            sky.freq_array = np.atleast_1d(np.unique(ref.cpu().numpy())) * mult
+            sky.write_text_catalog(fname)
+            sky2 = rsk.SkyModel.from_file(fname, filetype="text")
+            sky2.filename, sky2.history = sky.filename, sky.history
+            assert sky2 == sky, mult
+
+
+@pytest.mark.gpu
+def test_text_catalog_files_and_errors(rsk, tmp_path):
+    """tests/test_skymodel.py:3214-3238, :3354-3470."""
+    sky = rsk.SkyModel.from_file(POINT_TXT)
+    assert sky.filename == ["ref_fixture_pointsource_catalog.txt"] and sky.Ncomponents == 3 and sky.frame == "fk5"
+    assert np.allclose(np.rad2deg(sky.lon.cpu().numpy()), [1.0, 1.3, 1.35]) and sky.stokes[0, 0].tolist() == [0.5, 2.0, 5.0]
+    mock = rsk.SkyModel.from_file(MOCK_TXT)
+    assert mock.name.tolist() == ["src" + str(k) for k in range(mock.Ncomponents)]
+    fname = str(tmp_path / "temp_cat.txt")
+    hpx = rsk.SkyModel(nside=2, stokes=np.ones((4, 1, 48)), spectral_type="flat", hpx_frame="icrs")
+    with pytest.raises(ValueError, match="component_type must be 'point' to use this method."):
+        hpx.write_text_catalog(fname)
+    g = rsk.SkyModel.from_file(GLEAM_VOT, spectral_type="flat")
+    g.jansky_to_kelvin()
+    with pytest.raises(ValueError, match="Stokes units must be equivalent to Jy to use this method."):
+        g.write_text_catalog(fname)
+    g = rsk.SkyModel.from_gleam_catalog(GLEAM_VOT, spectral_type="flat")
+    g.extended_model_group = np.asarray(["foo"] * g.Ncomponents)
+    with pytest.raises(ValueError, match="Text files do not support catalogs with extended_model_group"):
+        g.write_text_catalog(fname)
+    # a frame the text format can name, a frame it cannot find, lost coordinate columns (:3393-3433)
+    for frame in ("icrs", "galactic"):
+        z = rsk.SkyModel(name=["zen_source"], ra=[1.1], dec=[-0.5], frame=frame, stokes=np.array([1.0, 0, 0, 0]).reshape(4, 1, 1),
+                         spectral_type="flat")
+        z.write_text_catalog(fname)
+        back = rsk.SkyModel.from_text_catalog(fname)
+        assert back.frame == frame and abs(float(back.lon[0]) - 1.1) < 1e-9 and abs(float(back.lat[0]) + 0.5) < 1e-9
+    z = rsk.SkyModel(name=["zen_source"], ra=[1.1], dec=[-0.5], frame="icrs", stokes=np.array([1.0, 0, 0, 0]).reshape(4, 1, 1),
+                     spectral_type="flat")
+    for old, new, msg in (("icrs", "foo", "frame not recognized from coordinate column"),
+                          ("ra_", "foo_", "Longitudinal and Latidudinal component columns not identified."),
+                          ("dec_", "foo_", "Longitudinal and Latidudinal component columns not identified.")):
+        z.write_text_catalog(fname)
+        text = open(fname).read().split("\n")
+        text[0] = text[0].replace(old, new)
+        open(fname, "w").write("\n".join(text))
+        with pytest.raises(ValueError, match=msg):
+            rsk.SkyModel.from_text_catalog(fname)
+    # flux / error column bookkeeping (:3452-3470)
+    e = rsk.SkyModel.from_file(GLEAM_VOT, with_error=True, run_check=False)
+    e.select(non_negative=True, non_nan="any")
+    e.at_frequencies(e.freq_array)
+    e.freq_edge_array = None
+    e.write_text_catalog(fname)
+    text = open(fname).read().replace("Flux_76_MHz [Jy]", "Frequency [Hz]")
+    open(fname, "w").write(text)
+    with pytest.raises(ValueError, match="Number of flux error fields does not match number of flux fields."):
+        rsk.SkyModel.from_file(fname)
