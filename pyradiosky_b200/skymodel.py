@@ -1023,6 +1023,40 @@ class SkyModel:
                 f"object. value was: {str(telescope_location)}"
             )
 
+    def add_extra_columns(self, *, names, values, dtype=None):
+        """Add one or more length Ncomponent attributes to the object (skymodel.py:1279-1355).  ``extra_columns`` is a
+        dict of 1-D host arrays here (a numpy recarray upstream); they follow select / concat and are stored in SkyH5."""
+        if isinstance(names, str):
+            names = [names]
+        if isinstance(values, np.ndarray):
+            values = [values]
+        if len(names) != len(values):
+            raise ValueError("Must provide the same number of names and values.")
+        if dtype is not None:
+            if isinstance(dtype, (list, tuple, np.ndarray)):
+                if len(dtype) != len(names):
+                    raise ValueError("If dtype is set, it must be the same length as `name`.")
+            else:
+                dtype = [dtype]
+        if self.extra_columns is not None:
+            for name in names:
+                if name in self.extra_columns:
+                    raise ValueError(f"{name} column already exists, use a different name.")
+        values = [np.asarray(v) for v in values]
+        for index, val in enumerate(values):
+            if val.shape != (self.Ncomponents,):
+                raise ValueError("value array(s) must be 1D, Ncomponents length array(s). "
+                                 f"The value array in index {index} is not the right shape.")
+        new = {name: (val if dtype is None else val.astype(dtype[k])) for k, (name, val) in enumerate(zip(names, values))}
+        self.extra_columns = {**(self.extra_columns or {}), **new}
+
+    def remove_extra_columns(self, names):
+        """Remove one or more length Ncomponent attributes from the object (skymodel.py:1357-1376)."""
+        if isinstance(names, str):
+            names = [names]
+        kept = {k: v for k, v in (self.extra_columns or {}).items() if k not in names}
+        self.extra_columns = kept or None
+
     def clear_time_position_specific_params(self):
         """Set time/position dependent attributes to None (skymodel.py:1385-ff)."""
         self.time = None

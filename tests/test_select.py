@@ -892,3 +892,31 @@ def test_healpix_interp_transform_partial_sky(rsk, order):
 
     assert _lib.load().rsk_healpix_interp(0, 0, None, None, 0, 0, None, 0, None, None, None) == -7
     assert _lib.load().rsk_healpix_interp(8, 0, None, None, 0, 0, None, 0, None, None, None) == -1
+
+
+@pytest.mark.gpu
+def test_extra_columns(rsk):
+    """skymodel.py:1279-1376 (tests/test_skymodel.py add / remove extra columns): they follow select and concat."""
+    sky = _full_model(rsk, "point", "flat")
+    n = sky.Ncomponents
+    sky.add_extra_columns(names="foo", values=np.arange(n, dtype=float))
+    sky.add_extra_columns(names=["bar", "gah"], values=[np.arange(n), np.array(["g" + str(k) for k in range(n)])],
+                          dtype=[int, str])
+    assert list(sky.extra_columns) == ["foo", "bar", "gah"] and sky.extra_columns["bar"].dtype.kind == "i"
+    with pytest.raises(ValueError, match="foo column already exists, use a different name."):
+        sky.add_extra_columns(names="foo", values=np.zeros(n))
+    with pytest.raises(ValueError, match="Must provide the same number of names and values."):
+        sky.add_extra_columns(names=["a", "b"], values=[np.zeros(n)])
+    with pytest.raises(ValueError, match="If dtype is set, it must be the same length as `name`."):
+        sky.add_extra_columns(names=["a"], values=[np.zeros(n)], dtype=[float, int])
+    with pytest.raises(ValueError, match="The value array in index 0 is not the right shape."):
+        sky.add_extra_columns(names="a", values=np.zeros(n + 1))
+    half = sky.select(component_inds=np.arange(0, n, 2), inplace=False)
+    assert half.extra_columns["gah"].tolist() == ["g" + str(k) for k in range(0, n, 2)]
+    rest = sky.select(component_inds=np.arange(1, n, 2), inplace=False)
+    both = half.concat(rest, inplace=False)
+    assert both.extra_columns["foo"].tolist() == list(range(0, n, 2)) + list(range(1, n, 2))
+    sky.remove_extra_columns(["bar", "gah"])
+    assert list(sky.extra_columns) == ["foo"]
+    sky.remove_extra_columns("foo")
+    assert sky.extra_columns is None
