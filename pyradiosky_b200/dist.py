@@ -54,6 +54,16 @@ def shard_kwargs(kwargs, world_size, rank):
     return out
 
 
+def shard_sky(sky, world_size, rank):
+    """This rank's contiguous block of an existing :class:`SkyModel` (e.g. one every rank loaded from the same SkyH5 or
+    GLEAM file): ``sky.select(component_inds=[lo, hi))`` on a copy, so every per-component array is cut on the GPU by
+    the row-gather kernel.  The blocks of all ranks, concatenated in rank order (``SkyModel.concat``), give the
+    original catalogue back.  An empty block (more ranks than components) raises, as ``select`` does upstream."""
+    lo, hi = shard_bounds(sky.Ncomponents, world_size, rank)
+    inds = torch.arange(lo, hi, dtype=torch.int64, device=sky.device)
+    return sky.select(component_inds=inds, inplace=False)
+
+
 def exchange_counts(n_local, device=None, group=None):
     """All-gather the per-rank above-horizon counts.
 

@@ -920,3 +920,25 @@ def test_extra_columns(rsk):
     assert list(sky.extra_columns) == ["foo"]
     sky.remove_extra_columns("foo")
     assert sky.extra_columns is None
+
+
+@pytest.mark.gpu
+def test_shard_sky_and_reassemble(rsk):
+    """dist.shard_sky: the per-rank blocks of a loaded catalogue, concatenated in rank order, are the catalogue."""
+    from pyradiosky_b200 import dist
+
+    for comp_type in ("point", "healpix"):
+        full = _full_model(rsk, comp_type)
+        world = 3
+        parts = [dist.shard_sky(full, world, r) for r in range(world)]
+        assert sum(p.Ncomponents for p in parts) == full.Ncomponents
+        assert [p.Ncomponents for p in parts] == [b - a for a, b in (dist.shard_bounds(full.Ncomponents, world, r) for r in range(world))]
+        whole = parts[0]
+        for p in parts[1:]:
+            whole = whole.concat(p, inplace=False)
+        whole.history = full.history
+        assert whole == full
+    one = dist.shard_sky(full, 1, 0)  # a single rank keeps everything (select removes nothing)
+    assert one == full and one is not full
+    with pytest.raises(ValueError, match="Select would result in an empty object."):
+        dist.shard_sky(full.select(component_inds=[0, 1], inplace=False), 4, 3)
