@@ -656,12 +656,30 @@ class SkyModel:
             raise ValueError("component names are required to write a text catalog.")
         textcat.write(filename, self)
 
+    def read_fhd_catalog(self, filename_sav, expand_extended=True, extra_columns=None, run_check=True, check_extra=True,
+                         run_check_acceptability=True):
+        """Read in an FHD style catalog file (IDL save file, skymodel.py:4415-4621).  ``expand_extended``: replace
+        extended sources by their components (names ``<id>_<k>``, ``extended_model_group`` = the parent's id);
+        ``extra_columns``: {catalogue column: attribute name} to carry along."""
+        from . import fhdcat
+
+        self.__init__(**fhdcat.read(filename_sav, expand_extended=expand_extended, extra_columns=extra_columns), history="",
+                      device=self.__dict__.get("device"))
+
+    @classmethod
+    def from_fhd_catalog(cls, filename_sav, device=None, **kwargs):
+        """Create a :class:`SkyModel` from an FHD catalog (skymodel.py:4623-4627)."""
+        sm = cls.__new__(cls)
+        sm.device = device
+        sm.read_fhd_catalog(filename_sav, **kwargs)
+        return sm
+
     @classmethod
     def from_file(cls, filename, filetype=None, spectral_type=None, with_error=False, use_paper_freqs=False,
                   table_name=None, id_column=None, lon_column=None, lat_column=None, frame=None, flux_columns=None,
                   reference_frequency=None, freq_array=None, freq_edge_array=None, spectral_index_column=None,
-                  flux_error_columns=None, history="", device=None, **kwargs):
-        """``SkyModel.from_file`` (skymodel.py:4629-4868) for the formats this build reads: 'skyh5', 'gleam', 'vot', 'text'."""
+                  flux_error_columns=None, history="", expand_extended=True, extra_columns=None, device=None, **kwargs):
+        """``SkyModel.from_file`` (skymodel.py:4629-4868) for every format of the reference: 'skyh5', 'gleam', 'vot', 'text', 'fhd'."""
         allowed_filetypes = ["skyh5", "gleam", "vot", "text", "fhd"]
         name = os.fspath(filename)
         if filetype is not None:
@@ -693,8 +711,7 @@ class SkyModel:
                                             flux_error_columns=flux_error_columns, history=history)
         if filetype == "text":
             return cls.from_text_catalog(filename, device=device)
-        raise ValueError("Only the 'skyh5', 'gleam', 'vot' and 'text' file types are supported by pyradiosky_b200; got "
-                         f"{filetype!r} for {filename}")
+        return cls.from_fhd_catalog(filename, device=device, expand_extended=expand_extended, extra_columns=extra_columns)
 
     def write_skyh5(self, filename, clobber=False, data_compression=None, **_checks):
         """Write this object to a SkyH5 file (skymodel.py:4871-5029)."""

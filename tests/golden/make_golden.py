@@ -232,7 +232,12 @@ def copy_skyh5_fixtures():
                           ("single_source_old.vot", "ref_fixture_single_source_old.vot"),
                           # text catalogues read by tests/test_skymodel.py:3214-3238 and :3436-3441
                           ("pointsource_catalog.txt", "ref_fixture_pointsource_catalog.txt"),
-                          ("mock_hera_text_2458098.27471.txt", "ref_fixture_mock_hera_text.txt")):
+                          ("mock_hera_text_2458098.27471.txt", "ref_fixture_mock_hera_text.txt"),
+                          # FHD IDL save files read by tests/test_skymodel.py:3079-3211 (the smaller four)
+                          ("extended_source_test.sav", "ref_fixture_extended_source_test.sav"),
+                          ("fhd_catalog_no_extend.sav", "ref_fixture_fhd_catalog_no_extend.sav"),
+                          ("fhd_catalog_bad.sav", "ref_fixture_fhd_catalog_bad.sav"),
+                          ("fhd_source_array.sav", "ref_fixture_fhd_source_array.sav")):
         shutil.copyfile(os.path.join(src, name), os.path.join(HERE, fixture))
     ka = {
         "gsm_icrs": {

@@ -304,3 +304,76 @@ def test_text_catalog_files_and_errors(rsk, tmp_path):
     open(fname, "w").write(text)
     with pytest.raises(ValueError, match="Number of flux error fields does not match number of flux fields."):
         rsk.SkyModel.from_file(fname)
+
+
+# ---------------------------------------------------------------------------------------------------
+# FHD catalogues (skymodel.py:4415-4627; tests/test_skymodel.py:3079-3211)
+# ---------------------------------------------------------------------------------------------------
+FHD = {k: os.path.join(GOLDEN, f"ref_fixture_{k}.sav") for k in ("extended_source_test", "fhd_catalog_no_extend",
+                                                                  "fhd_catalog_bad", "fhd_source_array")}
+
+
+def test_fhd_reader_host():
+    """Labels of expanded extended sources (tests/test_skymodel.py:3183-3195), component counts (:3104-3133), beam
+    amplitudes (:3136-3180), extra columns (:3088-3095), errors (:3198-3211)."""
+    import scipy.io
+
+    from pyradiosky_b200 import fhdcat
+
+    with pytest.warns(UserWarning, match="Source IDs are not unique. Defining unique IDs."):
+        kw = fhdcat.read(FHD["extended_source_test"], expand_extended=True)
+    assert kw["extended_model_group"].tolist() == ["0", "0", "0", "1", "1"]
+    assert kw["name"].tolist() == ["0_1", "0_2", "0_3", "1_1", "1_2"]
+    assert kw["spectral_type"] == "spectral_index" and kw["frame"] == "icrs" and np.all(kw["reference_frequency"] > 50e6)
+    for key, var in (("fhd_catalog_no_extend", "catalog"), ("fhd_source_array", "source_array")):
+        catalog = scipy.io.readsav(FHD[key])[var]
+        ext = [i for i in range(len(catalog)) if catalog["extend"][i] is not None]
+        import warnings
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            flat = fhdcat.read(FHD[key], expand_extended=False, extra_columns={"x": "image_x", "y": "image_y"})
+            full = fhdcat.read(FHD[key], expand_extended=True, extra_columns={"x": "image_x", "y": "image_y"})
+        assert flat["stokes"].shape == (4, 1, len(catalog)) and list(flat["extra_columns"]) == ["image_x", "image_y"]
+        assert flat["extended_model_group"] is None and flat["filename"] == [f"ref_fixture_{key}.sav"]
+        assert full["stokes"].shape[2] == len(catalog) - len(ext) + sum(len(catalog[e]["extend"]) for e in ext)
+        assert (full["extended_model_group"] is None) == (len(ext) == 0)
+        assert full["extra_columns"]["image_x"].shape == (full["stokes"].shape[2],)
+        assert np.array_equal(flat["stokes"][0, 0], [catalog[i]["flux"]["I"][0] for i in range(len(catalog))])
+        if "BEAM" in catalog.dtype.names:
+            beam = np.array([[catalog[i]["beam"]["XX"][0], catalog[i]["beam"]["YY"][0], abs(catalog[i]["beam"]["XY"][0]),
+                              abs(catalog[i]["beam"]["YX"][0])] for i in range(len(catalog))]).T
+            assert np.array_equal(flat["beam_amp"][:, 0, :], beam)
+            # components of an extended source sit where the source was, each with its own beam values
+            first = ext[0]
+            ncomp = len(catalog[first]["extend"])
+            assert full["name"][first:first + ncomp].tolist() == [f"{flat['name'][first]}_{k}" for k in range(1, ncomp + 1)]
+            assert np.array_equal(full["beam_amp"][:, 0, :first], beam[:, :first])
+        else:
+            assert flat["beam_amp"] is None
+    with pytest.raises(KeyError, match="does not contain a known catalog name. "):
+        fhdcat.read(FHD["fhd_catalog_bad"])
+    with pytest.warns(UserWarning), pytest.raises(KeyError, match="foo in extra_columns not available in catalog. Available extra_columns are:"):
+        fhdcat.read(FHD["extended_source_test"], extra_columns={"foo": "foo"})
+
+
+@pytest.mark.gpu
+@pytest.mark.filterwarnings("ignore:Source IDs are not unique")
+def test_fhd_catalog_on_gpu(rsk):
+    sky = rsk.SkyModel.from_file(FHD["fhd_source_array"], expand_extended=True, extra_columns={"x": "image_x"})
+    assert sky.spectral_type == "spectral_index" and sky.Ncomponents == 1055 and sky.beam_amp.shape == (4, 1, 1055)
+    assert sky.extended_model_group is not None and sky.extra_columns["image_x"].shape == (1055,)
+    assert sky.filename == ["ref_fixture_fhd_source_array.sav"]
+    flat = rsk.SkyModel.from_fhd_catalog(FHD["fhd_catalog_no_extend"], expand_extended=False)
+    assert flat.Ncomponents == 100 and flat.extended_model_group is None and flat.extra_columns is None
+    assert bool((flat.reference_frequency > 50e6).all())
+    # straight into the hot path
+    loc = rsk.EarthLocation.from_dms((-30, 43, 17.5), (21, 25, 41.9), 1073.0)
+    sky.update_positions(rsk.Time.from_utc("2015-03-01 00:00:00"), loc)
+    out = sky.coherency_calc(freqs=np.array([150e6, 180e6]))
+    assert out.shape == (2, 2, 2, int(sky.above_horizon.sum()))
+    # groups survive a select; a select that keeps no extended component drops the attribute (skymodel.py:3260-3265)
+    ext = np.nonzero(sky.extended_model_group != "")[0]
+    plain = np.nonzero(sky.extended_model_group == "")[0]
+    assert sky.select(component_inds=ext[:7], inplace=False).extended_model_group.tolist() == sky.extended_model_group[ext[:7]].tolist()
+    assert sky.select(component_inds=plain[:7], inplace=False).extended_model_group is None
