@@ -456,8 +456,11 @@ def test_skyh5_read_errors(tmp_path, skyh5):
     with pytest.warns(UserWarning, match="No frame available in this file, assuming 'icrs'"):
         sky3 = SkyModel.from_file(rewrite(hpath, drop=("/Header/hpx_frame",)))
     assert sky3.frame == "icrs"
-    with pytest.raises(ValueError, match="Only the 'skyh5' file type"):
-        SkyModel.from_file(str(tmp_path / "catalog.txt"))
+    # tests/test_skymodel.py:2910-2918
+    with pytest.raises(ValueError, match="Cannot determine the file type."):
+        SkyModel.from_file(str(tmp_path / "catalog.foo"))
+    with pytest.raises(ValueError, match="Invalid filetype. Filetype options are"):
+        SkyModel.from_file(hpath, filetype="foo")
 
 
 @pytest.mark.gpu
