@@ -333,6 +333,46 @@ class SkyModel:
         self._subband_cache = op
         return op
 
+    def check(self, check_extra=True, run_check_acceptability=True):
+        """Check that the parameters are set reasonably (skymodel.py:1184-1277): the SkyModel-specific consistency rules
+        and, with ``run_check_acceptability``, the reference's three warnings about NaN spectral indices, NaN Stokes
+        values and negative Stokes I.  (The generic UVBase shape / type validation is not reproduced: shapes are
+        enforced by the constructor here.)  Not called implicitly -- the hot path never pays for it."""
+        if self.freq_array is not None and self.reference_frequency is not None:
+            raise ValueError("Only one of freq_array and reference_frequency can be specified, not both.")
+        allowed_units = ("Jy", "K sr") if self.component_type == "point" else ("Jy / sr", "K")
+        if self.stokes_unit not in allowed_units:
+            raise ValueError(
+                f"For {self.component_type} component types, the stokes parameter must have a unit that can be "
+                f"converted to {allowed_units}. Currently units are {self.stokes_unit}"
+            )
+        for attr in ("stokes_error", "beam_amp"):
+            t = getattr(self, attr)
+            if check_extra and t is not None and tuple(t.shape) != tuple(self.stokes.shape):
+                raise ValueError(f"{attr} must have the shape of stokes, {tuple(self.stokes.shape)}; it is {tuple(t.shape)}")
+        if run_check_acceptability:
+            if self.spectral_type == "spectral_index" and bool(torch.isnan(self.spectral_index).any()):
+                warnings.warn(
+                    "Some spectral index values are NaNs. If this is a GLEAM-based "
+                    "sky model, consider using the 'subband' spectral type to"
+                    "avoid this error (GLEAM assigns NaN spectral indices for "
+                    "sources that are not well-fit by a power law, this can include "
+                    "bright sources)."
+                )
+            if bool(torch.isnan(self.stokes).any()):
+                warnings.warn(
+                    "Some Stokes values are NaNs. Use the select method with the"
+                    "'non_nan' parameter to remove sources with NaN values at "
+                    "any or all frequencies."
+                )
+            if bool((self.stokes[0] < 0).any()):
+                warnings.warn(
+                    "Some Stokes I values are negative. Use the select method "
+                    "with the 'non_negative' parameter to remove sources with "
+                    "negative Stokes I values."
+                )
+        return True
+
     def __eq__(self, other):
         """Equality of every parameter, as UVBase.__eq__ gives the reference's object (arrays to the UVParameter default
         tolerances rtol 1e-5 / atol 1e-8, angles to pyuvdata's 1 mas (RADIAN_TOL), NaNs equal to NaNs, histories up to

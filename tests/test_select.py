@@ -942,3 +942,31 @@ def test_shard_sky_and_reassemble(rsk):
     assert one == full and one is not full
     with pytest.raises(ValueError, match="Select would result in an empty object."):
         dist.shard_sky(full.select(component_inds=[0, 1], inplace=False), 4, 3)
+
+
+@pytest.mark.gpu
+def test_check_acceptability_warnings(rsk):
+    """skymodel.py:1184-1277; the warnings tests/test_skymodel.py:2174-2223 expects around the NaN / negative cuts."""
+    sky, *_ = _gleam_model(rsk)  # NaNs injected, GLEAM has negative fluxes
+    with pytest.warns(UserWarning) as rec:
+        assert sky.check()
+    msgs = [str(w.message) for w in rec]
+    assert any("Some Stokes values are NaNs." in m for m in msgs) and any("Some Stokes I values are negative" in m for m in msgs)
+    clean = sky.select(non_nan="any", non_negative=True, inplace=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        assert clean.check() and sky.check(run_check_acceptability=False)
+    only_nan = sky.select(non_negative=True, inplace=False)
+    with pytest.warns(UserWarning, match="Some Stokes values are NaNs.") as rec:
+        only_nan.check()
+    assert not any("negative" in str(w.message) for w in rec)
+    spi = _full_model(rsk, "point", "spectral_index")
+    spi.spectral_index[3] = float("nan")
+    with pytest.warns(UserWarning, match="Some spectral index values are NaNs."):
+        spi.check()
+    spi.freq_array = np.array([1e8])
+    with pytest.raises(ValueError, match="Only one of freq_array and reference_frequency can be specified, not both."):
+        spi.check()
+    hpx = rsk.SkyModel(nside=2, stokes=np.ones((4, 1, 48)), spectral_type="flat", hpx_frame="icrs", stokes_unit="Jy")
+    with pytest.raises(ValueError, match="For healpix component types, the stokes parameter must have a unit"):
+        hpx.check()
