@@ -333,6 +333,30 @@ class SkyModel:
         self._subband_cache = op
         return op
 
+    _FRAME_COMPONENT_NAMES = {"icrs": ("ra", "dec"), "fk5": ("ra", "dec"), "galactic": ("l", "b")}
+
+    def __getattr__(self, name):
+        """Handle references to frame coordinates, ``ra`` / ``dec`` or ``l`` / ``b`` depending on the frame
+        (skymodel.py:1065-1090): radians, CUDA tensors.  Other unknown names raise AttributeError as usual."""
+        if not name.startswith("_"):
+            frame = self.__dict__.get("frame")
+            comp_names = self._FRAME_COMPONENT_NAMES.get(frame, ())
+            if name in comp_names:
+                if self.__dict__.get("component_type") == "healpix":
+                    warnings.warn("It is more efficient to use the `get_lon_lat` method to get "
+                                  "longitudinal and latitudinal coordinates for HEALPix maps.")
+                    return self.get_lon_lat()[comp_names.index(name)]
+                return self.__dict__["lon" if comp_names.index(name) == 0 else "lat"]
+        raise AttributeError(f"'{type(self).__name__}' object has no attribute '{name}'")
+
+    @property
+    def ncomponent_length_params(self):
+        """Names of the parameters that have an Ncomponents-long axis and are set (skymodel.py:1267-1277)."""
+        names = ["name", "stokes", "lon", "lat", "hpx_inds", "spectral_index", "reference_frequency", "stokes_error",
+                 "beam_amp", "extended_model_group", "extra_columns", "alt_az", "pos_lmn", "above_horizon",
+                 "frame_coherency"]
+        return [n for n in names if self.__dict__.get(n) is not None]
+
     def check(self, check_extra=True, run_check_acceptability=True):
         """Check that the parameters are set reasonably (skymodel.py:1184-1277): the SkyModel-specific consistency rules
         and, with ``run_check_acceptability``, the reference's three warnings about NaN spectral indices, NaN Stokes

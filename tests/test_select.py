@@ -970,3 +970,30 @@ def test_check_acceptability_warnings(rsk):
     hpx = rsk.SkyModel(nside=2, stokes=np.ones((4, 1, 48)), spectral_type="flat", hpx_frame="icrs", stokes_unit="Jy")
     with pytest.raises(ValueError, match="For healpix component types, the stokes parameter must have a unit"):
         hpx.check()
+
+
+@pytest.mark.gpu
+def test_frame_coordinate_attributes(rsk):
+    """skymodel.py:1065-1090 / tests/test_skymodel.py:2575-2583: ``ra`` / ``dec`` or ``l`` / ``b`` follow the frame."""
+    import torch
+
+    sky, _ = _twenty(rsk, "flat", {}, frame="icrs")
+    assert torch.equal(sky.ra, sky.lon) and torch.equal(sky.dec, sky.lat)
+    with pytest.raises(AttributeError, match="'SkyModel' object has no attribute 'b'"):
+        sky.b  # noqa: B018
+    sky.transform_to("galactic")
+    assert torch.equal(sky.l, sky.lon) and torch.equal(sky.b, sky.lat)
+    with pytest.raises(AttributeError, match="'SkyModel' object has no attribute 'ra'"):
+        sky.ra  # noqa: B018
+    with pytest.raises(AttributeError):
+        sky.no_such_thing  # noqa: B018
+    hpx = rsk.SkyModel(nside=2, stokes=np.ones((4, 1, 48)), spectral_type="flat", hpx_frame="icrs")
+    with pytest.warns(UserWarning, match="It is more efficient to use the `get_lon_lat` method"):
+        ra = hpx.ra
+    assert torch.equal(ra, hpx.get_lon_lat()[0])
+    assert "stokes" in sky.ncomponent_length_params and "alt_az" not in sky.ncomponent_length_params
+    import copy as _c
+    import pickle
+
+    clone = _c.copy(sky)  # __getattr__ must not recurse on half-built objects
+    assert clone.frame == "galactic" and sky.copy() == sky
