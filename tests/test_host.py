@@ -349,3 +349,31 @@ def test_iers_table(tmp_path):
     (tmp_path / "empty").write_text("nothing here\n")
     with pytest.raises(ValueError, match="no Earth-orientation rows"):
         IERSTable.from_finals2000a(str(tmp_path / "empty"))
+
+
+def test_headers_compile_as_c_and_layouts_match_ctypes(tmp_path):
+    """include/rsk.h and include/rsk_io.h are plain C (what a cgo / JNI / ctypes binding would consume): a C program
+    that includes them reports every struct's size and field offsets, which must be what pyradiosky_b200._lib declares."""
+    import subprocess
+
+    from pyradiosky_b200 import _lib
+
+    structs = {"RskCoords": _lib.RskCoords, "RskSpectrum": _lib.RskSpectrum, "RskBeam": _lib.RskBeam,
+               "RskSelect": _lib.RskSelect, "RskH5Info": _lib.RskH5Info}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "rsk.h"', '#include "rsk_io.h"', "int main(void) {"]
+    for name, cls in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in cls._fields_:
+            lines.append(f'  printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)],
+                   check=True, capture_output=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert int(out[name]) == ctypes.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert int(out[f"{name}.{field}"]) == getattr(cls, field).offset, f"{name}.{field}"
