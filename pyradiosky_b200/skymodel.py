@@ -527,7 +527,16 @@ class SkyModel:
         from . import votable as vot
         from .skyh5 import get_freq_edges_from_centers
 
-        tables = vot.parse(votable_file)
+        if isinstance(flux_columns, str):
+            flux_columns = [flux_columns]
+        if isinstance(flux_error_columns, str):
+            flux_error_columns = [flux_error_columns]
+        wanted = [id_column, lon_column, lat_column, *flux_columns, *(flux_error_columns or [])]
+        if spectral_index_column is not None:
+            wanted.append(spectral_index_column)
+        wanted = [w.casefold() for w in wanted]
+        # only the columns that can match are kept while the file streams by (the full GLEAM table has ~300)
+        tables = vot.parse(votable_file, columns=lambda name: any(w in name.casefold() for w in wanted))
         if any(t.ID is None for t in tables):
             raise ValueError(f"File {votable_file} contains tables with no name or ID.")
         try:
@@ -540,8 +549,6 @@ class SkyModel:
         id_col = vot.get_matching_fields(id_column, cols)
         lon_col = vot.get_matching_fields(lon_column, cols, exclude_start_pattern="_")
         lat_col = vot.get_matching_fields(lat_column, cols, exclude_start_pattern="_")
-        if isinstance(flux_columns, str):
-            flux_columns = [flux_columns]
         flux_cols = [vot.get_matching_fields(c, cols) for c in flux_columns]
         freq_array = _to_hz_host(freq_array)
         freq_edge_array = None if freq_edge_array is None else np.asarray(_to_hz_host(freq_edge_array)).reshape(2, -1)
@@ -589,8 +596,6 @@ class SkyModel:
             stokes[0, k] = table.columns[c] * flux_unit(c)[1]
         stokes_error = None
         if flux_error_columns is not None:
-            if isinstance(flux_error_columns, str):
-                flux_error_columns = [flux_error_columns]
             err_cols = [vot.get_matching_fields(c, cols) for c in flux_error_columns]
             if any(flux_unit(c)[0] != unit_use for c in err_cols):
                 raise ValueError("All flux error columns must have units compatible with the units "

@@ -7,7 +7,10 @@ serialisations are refused.  Numeric columns come back as float64 (empty cells a
 ``char`` columns as numpy str arrays.  Host-side only; the arrays reach the GPU through the SkyModel constructor.
 """
 
+import mmap
+import re
 import xml.etree.ElementTree as ET
+from xml.sax.saxutils import unescape
 
 import numpy as np
 
@@ -29,40 +32,163 @@ class Table:
     def __len__(self):
         return len(next(iter(self.columns.values()))) if self.columns else 0
 
+    def column(self, name):
+        try:
+            return self.columns[name]
+        except KeyError:
+            raise KeyError(f"column {name} of table {self.ID} was not kept when the file was parsed") from None
 
-def parse(path):
-    """All tables of a VOTable file, in file order."""
-    root = ET.parse(path).getroot()
+
+_TABLE_OPEN = re.compile(rb"<TABLE\b[^>]*>")
+
+
+def _column_arrays(names, fields, null_of, keep, cells):
+    cols = {}
+    for slot, k in enumerate(keep):
+        f, raw = fields[k], cells[slot]
+        if f["datatype"] in _NUMERIC and f["arraysize"] in (None, "1"):
+            null = null_of.get(k)
+            null = null.encode() if isinstance(null, str) and raw and isinstance(raw[0], bytes) else null
+            empty, nan = (b"", b"nan") if raw and isinstance(raw[0], bytes) else ("", "nan")
+            cleaned = [nan if (c == empty or c == null) else c for c in (c.strip() for c in raw)]
+            cols[names[k]] = np.array(cleaned, dtype=np.float64) if cleaned else np.empty(0, dtype=np.float64)
+        else:
+            text = [(c.decode("utf-8") if isinstance(c, bytes) else c).strip() for c in raw]
+            cols[names[k]] = np.array([unescape(c) if "&" in c else c for c in text], dtype=str)
+    return cols
+
+
+def _parse_fast(path, columns):
+    """Regular-expression scan of the memory-mapped file: the per-table header (FIELDs) goes through ElementTree, the
+    TABLEDATA rows through ``bytes.split`` in 32 MB blocks, which is two orders of magnitude faster than an element
+    tree for the 1e8 cells of the full GLEAM table.  Returns None when the file uses something this scan does not cover (namespace
+    prefixes on the tags, CDATA or comments inside the data): the caller then streams it with iterparse."""
     tables = []
-    for tab in root.iter():
-        if _local(tab.tag) != "TABLE":
+    with open(path, "rb") as fh:
+        size = fh.seek(0, 2)
+        if size == 0:
+            return None
+        mm = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+    try:
+        if re.search(rb"<\w+:(?:TABLE|TR|TD|FIELD)\b", mm[: min(size, 1 << 20)]):
+            return None
+        pos = 0
+        while True:
+            m = _TABLE_OPEN.search(mm, pos)
+            if m is None:
+                break
+            close = mm.find(b"</TABLE", m.end())
+            close = size if close < 0 else close
+            data = mm.find(b"<DATA", m.end(), close)
+            head_end = data if data >= 0 else close
+            head = ET.fromstring(mm[m.start():head_end] + b"</TABLE>")
+            fields, names, null_of = [], [], {}
+            for f in head:
+                if _local(f.tag) != "FIELD":
+                    continue
+                null_of[len(names)] = next((v.get("null") for v in f if _local(v.tag) == "VALUES"), None)
+                names.append(f.get("name") or f.get("ID"))
+                fields.append({"datatype": f.get("datatype"), "arraysize": f.get("arraysize"), "unit": f.get("unit")})
+            keep = [k for k, n in enumerate(names) if columns is None or columns(n)]
+            cells = [[] for _ in keep]
+            if data >= 0:
+                td0 = mm.find(b"<TABLEDATA", data, close)
+                if td0 < 0:
+                    raise ValueError(f"only the TABLEDATA serialisation of VOTable is supported by this reader ({path})")
+                td1 = mm.find(b"</TABLEDATA", td0, close)
+                td1 = close if td1 < 0 else td1
+                if mm.find(b"<![CDATA[", td0, td1) >= 0 or mm.find(b"<!--", td0, td1) >= 0:
+                    return None
+                probe = mm[td0:min(td1, td0 + (1 << 20))]
+                if b"</TD " in probe or b"</TR " in probe or b"</TD\n" in probe or b"</TR\n" in probe:
+                    return None  # closing tags with white space inside: leave it to the XML parser
+                appenders = [c.append for c in cells]
+                carry, a, step = b"", td0, 32 << 20
+                while a < td1:
+                    b = min(td1, a + step)
+                    buf = carry + mm[a:b]
+                    a = b
+                    cut = buf.rfind(b"</TR>")
+                    if cut < 0:
+                        carry = buf
+                        continue
+                    carry = buf[cut + 5:]
+                    # bytes.split does the work (C speed): rows on </TR>, cells on </TD>, the cell text is what follows
+                    # the last '>' of its piece; only the kept columns are touched
+                    block = buf[:cut].replace(b"<TD/>", b"<TD></TD>").replace(b"<TD />", b"<TD></TD>")
+                    for row in block.split(b"</TR>"):
+                        parts = row.split(b"</TD>")
+                        ntd = len(parts) - 1
+                        for add, k in zip(appenders, keep):
+                            if k < ntd:
+                                piece = parts[k]
+                                add(piece[piece.rfind(b">") + 1:])
+                            else:
+                                add(b"")
+            units = {n: f["unit"] for n, f in zip(names, fields)}
+            tables.append(Table(head.get("ID"), head.get("name"), names, _column_arrays(names, fields, null_of, keep, cells),
+                                units))
+            pos = close + 1
+    finally:
+        mm.close()
+    return tables
+
+
+def parse(path, columns=None):
+    """All tables of a VOTable file, in file order.
+
+    ``columns``: optional predicate ``name -> bool`` choosing the columns to keep (all by default); the table's
+    ``colnames`` always lists every FIELD, so column matching sees the same names either way.  Large catalogues (the
+    full GLEAM release is 3e5 rows x 3e2 columns) are scanned with ``bytes.split`` over the memory-mapped file
+    (:func:`_parse_fast`); files that scan does not cover are streamed through ``iterparse`` with every row released as
+    soon as it has been read.  Either way memory is spent on the kept columns only."""
+    try:
+        fast = _parse_fast(path, columns)
+    except ET.ParseError:
+        fast = None
+    if fast is not None:
+        return fast
+    return _parse_stream(path, columns)
+
+
+def _parse_stream(path, columns=None):
+    tables = []
+    fields, names, keep, cells, null_of = [], [], [], [], {}
+    table_attr = None
+    for event, elem in ET.iterparse(path, events=("start", "end")):
+        tag = _local(elem.tag)
+        if event == "start":
+            if tag == "TABLE":
+                table_attr = (elem.get("ID"), elem.get("name"))
+                fields, names, keep, cells, null_of = [], [], [], [], {}
+            elif tag in ("BINARY", "BINARY2", "FITS"):
+                raise ValueError(f"only the TABLEDATA serialisation of VOTable is supported, {path} has {tag}")
             continue
-        fields = [f for f in tab if _local(f.tag) == "FIELD"]
-        names = [f.get("name") or f.get("ID") for f in fields]
-        data = next((d for d in tab if _local(d.tag) == "DATA"), None)
-        rows = []
-        if data is not None:
-            td = next((t for t in data if _local(t.tag) == "TABLEDATA"), None)
-            if td is None:
-                kinds = [_local(t.tag) for t in data]
-                raise ValueError(f"only the TABLEDATA serialisation of VOTable is supported, {path} has {kinds}")
-            for tr in td:
-                if _local(tr.tag) == "TR":
-                    rows.append([(c.text or "") for c in tr if _local(c.tag) == "TD"])
-        columns, units = {}, {}
-        for k, (f, name) in enumerate(zip(fields, names)):
-            cells = [r[k] if k < len(r) else "" for r in rows]
-            units[name] = f.get("unit")
-            if f.get("datatype") in _NUMERIC and f.get("arraysize") in (None, "1"):
-                null = next((v.get("null") for v in f if _local(v.tag) == "VALUES"), None)
-                vals = np.empty(len(cells), dtype=np.float64)
-                for i, c in enumerate(cells):
-                    c = c.strip()
-                    vals[i] = np.nan if (c == "" or c == null or c.lower() == "nan") else float(c)
-                columns[name] = vals
-            else:
-                columns[name] = np.array([c.strip() for c in cells], dtype=str)
-        tables.append(Table(tab.get("ID"), tab.get("name"), names, columns, units))
+        if tag == "FIELD" and table_attr is not None:
+            name = elem.get("name") or elem.get("ID")
+            fields.append({"datatype": elem.get("datatype"), "arraysize": elem.get("arraysize"), "unit": elem.get("unit")})
+            null_of[len(names)] = next((v.get("null") for v in elem if _local(v.tag) == "VALUES"), None)
+            names.append(name)
+        elif tag == "TABLEDATA":
+            pass
+        elif tag == "TR" and table_attr is not None:
+            if not keep:
+                keep = [k for k, n in enumerate(names) if columns is None or columns(n)]
+                cells = [[] for _ in keep]
+            tds = [c for c in elem if _local(c.tag) == "TD"]
+            ntd = len(tds)
+            for slot, k in enumerate(keep):
+                cells[slot].append((tds[k].text or "") if k < ntd else "")
+            elem.clear()
+        elif tag == "TABLE" and table_attr is not None:
+            if not keep:
+                keep = [k for k, n in enumerate(names) if columns is None or columns(n)]
+                cells = [[] for _ in keep]
+            units = {n: f["unit"] for n, f in zip(names, fields)}
+            cols = _column_arrays(names, fields, null_of, keep, cells)
+            tables.append(Table(table_attr[0], table_attr[1], names, cols, units))
+            table_attr = None
+            elem.clear()
     return tables
 
 

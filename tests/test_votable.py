@@ -377,3 +377,54 @@ def test_fhd_catalog_on_gpu(rsk):
     plain = np.nonzero(sky.extended_model_group == "")[0]
     assert sky.select(component_inds=ext[:7], inplace=False).extended_model_group.tolist() == sky.extended_model_group[ext[:7]].tolist()
     assert sky.select(component_inds=plain[:7], inplace=False).extended_model_group is None
+
+
+def test_votable_fast_scan_equals_xml_parser(tmp_path):
+    """The bytes.split scan of large tables (votable._parse_fast) against the ElementTree stream on the reference's
+    files and on a synthetic table with empty cells, self-closed cells, entities, a short row and a column filter; files
+    the scan does not cover fall back to the XML parser."""
+    from pyradiosky_b200 import votable as vot
+
+    def same(a, b):
+        assert a is not None and len(a) == len(b)
+        for ta, tb in zip(a, b):
+            assert (ta.ID, ta.name, ta.colnames, ta.units) == (tb.ID, tb.name, tb.colnames, tb.units)
+            assert list(ta.columns) == list(tb.columns)
+            for k in ta.columns:
+                x, y = ta.columns[k], tb.columns[k]
+                assert x.dtype == y.dtype, k
+                assert np.array_equal(x, y, equal_nan=True) if x.dtype.kind == "f" else np.array_equal(x, y), k
+
+    for path in (GLEAM_VOT, SIMPLE_VOT, OLD_VOT):
+        same(vot._parse_fast(path, None), vot._parse_stream(path, None))
+    head = ('<?xml version="1.0"?>\n<VOTABLE version="1.4" xmlns="http://www.ivoa.net/xml/VOTable/v1.4"><RESOURCE>'
+            '<TABLE ID="t1" name="first"><FIELD name="id" datatype="char" arraysize="*"/>'
+            '<FIELD name="x" datatype="double" unit="deg"><VALUES null="-99"/></FIELD>'
+            '<FIELD name="flux" datatype="float" unit="mJy"/><FIELD name="n" datatype="int"/><DATA><TABLEDATA>\n')
+    rows = ('<TR><TD>A &amp; B</TD><TD> 1.5 </TD><TD>2e3</TD><TD>7</TD></TR>\n'
+            '<TR><TD>c&lt;d</TD><TD>-99</TD><TD/><TD></TD></TR>\n'
+            '<TR><TD/><TD>nan</TD><TD>4</TD></TR>\n')
+    tail = '</TABLEDATA></DATA></TABLE><TABLE ID="t2" name="empty"><FIELD name="q" datatype="double"/></TABLE></RESOURCE></VOTABLE>\n'
+    p = tmp_path / "syn.vot"
+    p.write_text(head + rows * 3 + tail)
+    fast, slow = vot._parse_fast(str(p), None), vot._parse_stream(str(p), None)
+    same(fast, slow)
+    t1, t2 = vot.parse(str(p))
+    assert len(t1) == 9 and len(t2) == 0 and t2.colnames == ["q"]
+    assert t1.columns["id"][:3].tolist() == ["A & B", "c<d", ""]
+    assert t1.columns["x"][0] == 1.5 and np.isnan(t1.columns["x"][1]) and np.isnan(t1.columns["x"][2])
+    assert t1.columns["flux"][:3].tolist()[0] == 2000.0 and np.isnan(t1.columns["flux"][1]) and t1.columns["flux"][2] == 4.0
+    assert t1.columns["n"][0] == 7.0 and np.isnan(t1.columns["n"][1]) and np.isnan(t1.columns["n"][2])
+    (only,) = vot.parse(str(p), columns=lambda name: name in ("id", "flux"))[:1]
+    assert list(only.columns) == ["id", "flux"] and only.colnames == ["id", "x", "flux", "n"]
+    with pytest.raises(KeyError, match="was not kept"):
+        only.column("x")
+    # not covered by the scan: comments inside the data, namespace prefixes -> the XML parser reads them
+    p2 = tmp_path / "comment.vot"
+    p2.write_text(head + "<!-- a comment -->" + rows + tail)
+    assert vot._parse_fast(str(p2), None) is None and len(vot.parse(str(p2))[0]) == 3
+    p3 = tmp_path / "binary.vot"
+    p3.write_text(head.replace("<TABLEDATA>", "<BINARY><STREAM>AAAA</STREAM></BINARY>").rstrip("\n")
+                  + "</DATA></TABLE></RESOURCE></VOTABLE>")
+    with pytest.raises(ValueError, match="only the TABLEDATA serialisation"):
+        vot.parse(str(p3))
