@@ -993,7 +993,6 @@ def test_frame_coordinate_attributes(rsk):
     assert torch.equal(ra, hpx.get_lon_lat()[0])
     assert "stokes" in sky.ncomponent_length_params and "alt_az" not in sky.ncomponent_length_params
     import copy as _c
-    import pickle
 
     clone = _c.copy(sky)  # __getattr__ must not recurse on half-built objects
     assert clone.frame == "galactic" and sky.copy() == sky

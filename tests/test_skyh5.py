@@ -6,7 +6,6 @@ CPU tests cover the host reader/writer through the C ABI; ``-m gpu`` tests cover
 and ``SkyModel.from_skyh5`` / ``write_skyh5`` with the reference's warnings and error texts
 (tests/test_skymodel.py:3851-4220, :4507-4522)."""
 
-import ctypes
 import json
 import os
 import subprocess
@@ -468,7 +467,7 @@ def test_loaded_healpix_model_runs_the_hot_path():
     """File -> HBM -> update_positions -> coherency_calc, against the oracle on the same file contents."""
     import torch
 
-    from oracle import erfa_np, healpix_np, skymodel_np
+    from oracle import healpix_np, skymodel_np
     from pyradiosky_b200 import EarthLocation, SkyModel, Time
 
     sky = SkyModel.from_skyh5(GSM)

@@ -38,7 +38,7 @@ def main():
     import __graft_entry__ as entry
 
     entry.build()
-    from pyradiosky_b200 import EarthLocation, SkyModel, Time, _lib, utils
+    from pyradiosky_b200 import EarthLocation, SkyModel, Time, _lib
 
     peak = 6547.8
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
