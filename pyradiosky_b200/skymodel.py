@@ -782,6 +782,14 @@ class SkyModel:
             return cls.from_text_catalog(filename, device=device)
         return cls.from_fhd_catalog(filename, device=device, expand_extended=expand_extended, extra_columns=extra_columns)
 
+    def read(self, filename, **kwargs):
+        """Read a file of any supported type into this object (skymodel.py:4629-4862); same arguments as
+        :meth:`from_file`."""
+        kwargs.setdefault("device", self.__dict__.get("device"))
+        new = type(self).from_file(filename, **kwargs)
+        self.__dict__.clear()
+        self.__dict__.update(new.__dict__)
+
     def write_skyh5(self, filename, clobber=False, data_compression=None, **_checks):
         """Write this object to a SkyH5 file (skymodel.py:4871-5029)."""
         from . import skyh5
