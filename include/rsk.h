@@ -128,6 +128,20 @@ typedef struct RskSpectrum {
    * pivot inside the band works (it only keeps the logarithms small).  0 = the middle requested channel.
    * Callers that evaluate the frequency axis in slabs pass one pivot so every slab rounds identically. */
   double pivot_hz;
+  /* Optional component filter (NaN handling, skymodel.py:2245-2312, without a host round trip): when group_of is
+   * non-NULL a column is evaluated only if group_of[component] == group; every other column of the output is left
+   * untouched.  The caller first evaluates all columns with the catalogue's operator and then launches once per
+   * NaN-pattern group with that group's operator (chan_map form) and this filter -- nothing depends on which
+   * components are above the horizon, so the whole step can be queued (or captured in a CUDA graph) as is. */
+  const int32_t* group_of;      /* [n] or NULL */
+  int32_t group;
+  int32_t reserved;
+  /* FULL, optional: a component-major copy of the stored Stokes, [n][nf_in][4] (the four Stokes parameters of one
+   * (component, channel) in one 32-byte sector), made once per catalogue by rsk_stokes_component_major().  The
+   * coherency kernels read the rows of the above-horizon components from it: with the (4, nf, n) layout a horizon
+   * mask that is scattered over the catalogue order drags in nearly every sector of the below-horizon components
+   * as well (~1.9x the bytes at 50 % density); this layout reads exactly 32 bytes per evaluation for any mask. */
+  const double* stokes_cm;      /* [n][nf_in][4] or NULL */
 } RskSpectrum;
 
 /* Antenna response for rsk_apparent_coherency.  Jones matrices are [feed][basis] with
@@ -314,10 +328,18 @@ int rsk_rise_set_lsts(const RskCoords* coords, int64_t n, double tel_lat, double
 int rsk_compact_index(const uint8_t* above, int64_t n, int64_t* idx /* [n] */,
                       int64_t* n_above /* device [1] */, void* work, size_t work_bytes, void* stream);
 
-/* Per-component bit mask of stored channels at which all four Stokes parameters are non-NaN (bit j =
- * channel j; nf_in <= 64): the freq_inds_use of skymodel.py:2246-2248 for every component at once. */
+/* Per-component bit mask of stored channels at which all four Stokes parameters are non-NaN: the freq_inds_use of
+ * skymodel.py:2246-2248 for every component at once.  Channel j is bit (j % 64) of word j / 64;
+ * mask is [ceil(nf_in / 64)][n] (one word per component for up to 64 subbands). */
 int rsk_valid_channels(const double* stokes /* [4][nf_in][n] */, int64_t nf_in, int64_t n,
-                       uint64_t* mask /* [n] */, void* stream);
+                       uint64_t* mask /* [ceil(nf_in / 64)][n] */, void* stream);
+
+/* *out (DEVICE int64) = number of NaNs in a double array (RSK_COUNT_NAN_F64: the np.any(np.isnan(...)) tests of
+ * skymodel.py:2157 and :2196) or of non-zero bytes in a byte array (RSK_COUNT_NONZERO_U8: the size of
+ * SkyModel._polarized, the above-horizon count of a mask). */
+#define RSK_COUNT_NAN_F64 0
+#define RSK_COUNT_NONZERO_U8 1
+int rsk_count(const void* x, int64_t count, int kind, int64_t* out /* device [1] */, void* stream);
 
 /* SkyModel._polarized (skymodel.py:1037-1042): pol[c] = any over stored channels of (Q+U+V != 0). */
 int rsk_polarized_mask(const double* stokes /* [4][nf_in][n] */, int64_t nf_in, int64_t n,
@@ -394,6 +416,9 @@ int rsk_unpack_coherency_host(const double* packed /* HOST [4][nf][ld_packed] */
 int rsk_spline_coefficients(const double* stokes /* [4][nf_in][n] */, int64_t nf_in, int64_t n,
                             const double* cmat /* [nc][nf_in] */, int64_t nc,
                             double* bcoef /* [4][nc][n] */, void* stream);
+
+/* stokes [4][nf][n] -> out [n][nf][4] (see RskSpectrum.stokes_cm).  Time independent: run once per catalogue. */
+int rsk_stokes_component_major(const double* stokes, int64_t nf, int64_t n, double* out, void* stream);
 
 /* ---- K3 / K4: unfused API-parity kernels ------------------------------------------------------- */
 

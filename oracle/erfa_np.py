@@ -27,8 +27,8 @@ DJY = 365.25
 DJC = 36525.0
 DAYSEC = 86400.0
 SRS = 1.97412574336e-8
-AULT = 499.004782
 DAU = 149597870.7e3
+AULT = DAU / 299792458.0  # erfam.h: ERFA_AULT = ERFA_DAU / ERFA_CMPS (pinned by t_erfa_c's apcs check values)
 WGS84_A = 6378137.0
 WGS84_F = 1.0 / 298.257223563
 CELMIN = 1e-6

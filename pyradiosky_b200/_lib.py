@@ -57,6 +57,10 @@ class RskSpectrum(ctypes.Structure):
         ("chan_map", ctypes.c_void_p),
         ("nf_use", ctypes.c_int64),
         ("pivot_hz", ctypes.c_double),
+        ("group_of", ctypes.c_void_p),
+        ("group", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("stokes_cm", ctypes.c_void_p),
     ]
 
 
@@ -71,6 +75,7 @@ class RskBeam(ctypes.Structure):
 
 
 BEAM_JONES, BEAM_SHORT_DIPOLE, BEAM_UNIFORM = 0, 1, 2
+COUNT_NAN_F64, COUNT_NONZERO_U8 = 0, 1
 
 
 class RskSelect(ctypes.Structure):
@@ -173,6 +178,7 @@ _SIGNATURES = {
         [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
          ctypes.c_size_t, ctypes.c_void_p],
     ),
+    "rsk_count": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "rsk_polarized_mask": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p],
@@ -218,6 +224,10 @@ _SIGNATURES = {
          ctypes.c_void_p, ctypes.c_void_p],
     ),
     "rsk_valid_channels": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p],
+    ),
+    "rsk_stokes_component_major": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p],
     ),

@@ -68,7 +68,8 @@ struct Dataset {
   const uint8_t* compact = nullptr;
   uint64_t compact_size = 0;
   uint64_t addr = kUndef;  // contiguous data or chunk B-tree
-  int64_t chunk[8] = {0};
+  int64_t chunk[9] = {0};  // rank + 1 entries (the last is the element size), rank <= 8
+  int chunk_nd = 0;
   std::vector<Filter> filters;
   std::vector<ChunkRec> chunks;
   bool chunks_loaded = false;
@@ -462,8 +463,18 @@ struct RskH5File {
     }
     if (d.layout < 0 || !have_space || !have_type) fail(RSK_H5_ERR_TYPE, key + " is not a dataset");
     d.count = d.null_space ? 0 : 1;
-    for (int i = 0; i < d.rank; ++i) d.count *= d.dims[i];
+    for (int i = 0; i < d.rank; ++i) {
+      if (d.dims[i] < 0 || (d.dims[i] > 0 && d.count > (int64_t)(INT64_MAX / 16) / d.dims[i]))
+        fail(RSK_H5_ERR_FORMAT, "dataset extent overflows");
+      d.count *= d.dims[i];
+    }
     if (d.layout == 2) {
+      if (d.chunk_nd != d.rank + 1) fail(RSK_H5_ERR_FORMAT, "chunk rank differs from the dataspace rank");
+      int64_t cb = d.dt.size > 0 ? d.dt.size : 1;
+      for (int a = 0; a < d.rank; ++a) {
+        if (d.chunk[a] <= 0 || cb > ((int64_t)1 << 40) / d.chunk[a]) fail(RSK_H5_ERR_FORMAT, "bad chunk shape");
+        cb *= d.chunk[a];
+      }
       if (d.chunk[d.rank] != d.dt.size) fail(RSK_H5_ERR_FORMAT, "chunk element size differs from the datatype size");
     }
     return ds_cache[key] = std::move(d);
@@ -487,6 +498,7 @@ struct RskH5File {
         if (nd < 1 || nd > 9 || m.len < 11 + 4 * (size_t)nd) fail(RSK_H5_ERR_FORMAT, "bad chunked layout");
         d.addr = u64(p + 3);
         for (int i = 0; i < nd; ++i) d.chunk[i] = u32(p + 11 + 4 * i);
+        d.chunk_nd = nd;
       } else fail(RSK_H5_ERR_UNSUPPORTED, "layout class");
     } else if (ver == 1 || ver == 2) {
       if (m.len < 8) fail(RSK_H5_ERR_FORMAT, "short layout message");
@@ -499,6 +511,7 @@ struct RskH5File {
       }
       if (nd > 9 || m.len < q + 4 * (size_t)nd) fail(RSK_H5_ERR_FORMAT, "bad layout message");
       for (int i = 0; i < nd; ++i) d.chunk[i] = u32(p + q + 4 * i);
+      d.chunk_nd = nd;
       q += 4 * (size_t)nd;
       if (d.layout == 0) {
         d.compact_size = u32(p + q);

@@ -33,8 +33,8 @@ const double DJ00 = 2451545.0;
 const double DJY = 365.25;
 const double DJC = 36525.0;
 const double DAYSEC = 86400.0;
-const double AULT = 499.004782;
 const double DAU = 149597870.7e3;
+const double AULT = DAU / 299792458.0;  // erfam.h: ERFA_AULT = ERFA_DAU / ERFA_CMPS
 const double WGS84_A = 6378137.0;
 const double WGS84_F = 1.0 / 298.257223563;
 const double DEG = RSK_DPI / 180.0;

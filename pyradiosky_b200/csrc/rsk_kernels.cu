@@ -686,17 +686,39 @@ __global__ void __launch_bounds__(kThreads) k_valid_channels(const double* __res
                                                              const int64_t n, uint64_t* __restrict__ mask) {
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (i >= n) return;
-  uint64_t m = 0;
-  for (int f = 0; f < nf; ++f) {
-    bool ok = true;
+  for (int w = 0; w * 64 < nf; ++w) {  // one 64-channel word at a time
+    uint64_t m = 0;
+    const int fend = min(nf, (w + 1) * 64);
+    for (int f = w * 64; f < fend; ++f) {
+      bool ok = true;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      const double v = __ldg(stokes + ((int64_t)s * nf + f) * n + i);
-      ok = ok && (v == v);
+      for (int s = 0; s < 4; ++s) {
+        const double v = __ldg(stokes + ((int64_t)s * nf + f) * n + i);
+        ok = ok && (v == v);
+      }
+      if (ok) m |= 1ull << (f & 63);
     }
-    if (ok) m |= 1ull << f;
+    mask[(int64_t)w * n + i] = m;
   }
-  mask[i] = m;
+}
+
+// Number of NaNs in a double array (KIND 0) or of non-zero bytes in a byte array (KIND 1): the np.any(np.isnan(...))
+// tests of skymodel.py:2157, :2196 and the size of SkyModel._polarized, without a library reduction.
+template <int KIND>
+__global__ void __launch_bounds__(kThreads) k_count(const void* __restrict__ x, const int64_t count,
+                                                    unsigned long long* __restrict__ out) {
+  int c = 0;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < count; i += (int64_t)gridDim.x * kThreads) {
+    if (KIND == 0) {
+      const double v = __ldg(static_cast<const double*>(x) + i);
+      c += (v != v) ? 1 : 0;
+    } else {
+      c += __ldg(static_cast<const uint8_t*>(x) + i) != 0 ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
 }
 
 // SkyModel._polarized predicate, skymodel.py:1039-1041: any_f ((Q + U) + V != 0)
@@ -736,6 +758,9 @@ struct EvalParams {
   const double* pband;
   const int32_t* freq_map;
   const uint8_t* polarized;
+  const int32_t* group_of;  // optional filter: only components with group_of[c] == group are evaluated
+  int group;
+  const double2* stokes_cm;  // FULL: component-major copy [n][nf_in][4] (RskSpectrum.stokes_cm) or NULL
   // geometry (coherency epilogue only)
   CoordSrc cs;
   const double* alt_az;
@@ -965,6 +990,9 @@ k_eval(const __grid_constant__ EvalParams p) {
   if (kcol >= ncols) return;
   const int64_t col = p.cols ? __ldg(p.cols + kcol) : kcol;
   const int64_t src = p.idx ? __ldg(p.idx + col) : col;
+  // NaN-pattern launches (skymodel.py:2245-2312): this operator belongs to one group of components only.  (No
+  // barrier follows, and a thread only ever consumes shared memory it filled itself, so leaving here is safe.)
+  if (p.group_of && __ldg(p.group_of + src) != p.group) return;
 
   // per-component rotation coefficients (identity for unpolarised components, skymodel.py:2687-2688)
   RskRot rot;
@@ -1127,6 +1155,19 @@ k_eval(const __grid_constant__ EvalParams p) {
       for (int q = 0; q < 4; ++q) o[q] = fma(fma(fma(cf[3][q], u, cf[2][q]), u, cf[1][q]), u, cf[0][q]);
       emit<EPI>(p, f0 + k, col, o, jp);
     }
+  } else if (p.stokes_cm) {
+    // RSK_FULL from the component-major copy: this column's (I, Q, U, V) at one channel are one 32-byte sector, the
+    // channels of a component are consecutive sectors -- exactly 32 bytes read per evaluation whatever the horizon
+    // mask looks like (the gathered reads below fetch nearly every sector of a scattered mask's gaps too)
+    const double2* __restrict__ row = p.stokes_cm + (int64_t)src * p.nf_in * 2;
+#pragma unroll 4
+    for (int k = 0; k < nfc; ++k) {
+      const double2 iq = __ldcs(row + 2 * (int64_t)s_iv[k]);
+      const double2 uv = __ldcs(row + 2 * (int64_t)s_iv[k] + 1);
+      double o[4];
+      xform<EPI>(rot, iq.x, iq.y, uv.x, uv.y, o);
+      emit<EPI>(p, f0 + k, col, o, jp);
+    }
   } else {  // RSK_FULL: stored Stokes, skymodel.py:2165-2181 subset + utils.py:42-57
 #pragma unroll 4
     for (int k = 0; k < nfc; ++k) {
@@ -1138,6 +1179,31 @@ k_eval(const __grid_constant__ EvalParams p) {
       xform<EPI>(rot, y0, y1, y2, y3, o);
       emit<EPI>(p, f0 + k, col, o, jp);
     }
+  }
+}
+
+// stokes [4][nf][n] -> out [n][nf][4] through a shared-memory tile of kCmTile components x kCmTile channels:
+// reads are coalesced along the component axis, writes along the (channel, Stokes) axis of one component.
+constexpr int kCmTile = 32;
+__global__ void __launch_bounds__(kThreads) k_stokes_component_major(const double* __restrict__ stokes, const int64_t nf,
+                                                                     const int64_t n, double* __restrict__ out) {
+  constexpr int kRow = kCmTile * 4 + 1;  // odd stride (in doubles): the transposed accesses spread over the banks
+  __shared__ double tile[kCmTile * kRow];
+  const int64_t c0 = (int64_t)blockIdx.x * kCmTile, f0 = (int64_t)blockIdx.y * kCmTile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // load: row r = (s, f) of the tile, lanes along components
+  for (int r = warp; r < 4 * kCmTile; r += kThreads / 32) {
+    const int s = r / kCmTile, f = r - s * kCmTile;
+    const int64_t c = c0 + lane, ff = f0 + f;
+    if (c < n && ff < nf) tile[lane * kRow + f * 4 + s] = __ldcs(stokes + (s * nf + ff) * n + c);
+  }
+  __syncthreads();
+  // store: one component per warp trip, lanes along its kCmTile x 4 contiguous output doubles
+  const int64_t nff = min((int64_t)kCmTile, nf - f0);
+  for (int c = warp; c < kCmTile; c += kThreads / 32) {
+    if (c0 + c >= n) break;
+    double* dst = out + ((c0 + c) * nf + f0) * 4;
+    for (int e = lane; e < nff * 4; e += 32) __stcs(dst + e, tile[c * kRow + e]);
   }
 }
 
@@ -1513,6 +1579,9 @@ int fill_eval_params(const RskSpectrum* spec, const double* freqs, int64_t nf, i
   p->degree = spec->degree;
   p->freq_map = spec->freq_map;
   p->polarized = spec->polarized;
+  p->group_of = spec->group_of;
+  p->group = spec->group;
+  p->stokes_cm = spec->mode == RSK_FULL ? reinterpret_cast<const double2*>(spec->stokes_cm) : nullptr;
   p->pivot_hz = spec->pivot_hz;
   p->chan_map = spec->mode == RSK_SUBBAND ? spec->chan_map : nullptr;
   p->nf_use = (int)((spec->mode == RSK_SUBBAND && spec->chan_map) ? spec->nf_use : spec->nf_in);
@@ -1811,11 +1880,27 @@ int rsk_compact_index(const uint8_t* above, int64_t n, int64_t* idx, int64_t* n_
 }
 
 int rsk_valid_channels(const double* stokes, int64_t nf_in, int64_t n, uint64_t* mask, void* stream) {
-  if (n < 0 || nf_in < 0) return RSK_ERR_SIZE;
-  if (nf_in > 64) return RSK_ERR_UNSUPPORTED;
-  if (n == 0) return RSK_OK;
+  if (n < 0 || nf_in < 0 || nf_in > INT32_MAX) return RSK_ERR_SIZE;
+  if (n == 0 || nf_in == 0) return RSK_OK;
   if (!stokes || !mask) return RSK_ERR_NULL;
   k_valid_channels<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(stokes, (int)nf_in, n, mask);
+  return launch_status();
+}
+
+int rsk_count(const void* x, int64_t count, int kind, int64_t* out, void* stream) {
+  if (!out) return RSK_ERR_NULL;
+  if (count < 0) return RSK_ERR_SIZE;
+  if (kind != RSK_COUNT_NAN_F64 && kind != RSK_COUNT_NONZERO_U8) return RSK_ERR_MODE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const cudaError_t e = cudaMemsetAsync(out, 0, sizeof(int64_t), st);
+  if (e != cudaSuccess) return (int)e;
+  if (count == 0) return RSK_OK;
+  if (!x) return RSK_ERR_NULL;
+  const unsigned grid = (unsigned)std::min<int64_t>((count + kThreads - 1) / kThreads, 148 * 16);
+  if (kind == RSK_COUNT_NAN_F64)
+    k_count<0><<<grid, kThreads, 0, st>>>(x, count, reinterpret_cast<unsigned long long*>(out));
+  else
+    k_count<1><<<grid, kThreads, 0, st>>>(x, count, reinterpret_cast<unsigned long long*>(out));
   return launch_status();
 }
 
@@ -2023,6 +2108,16 @@ int rsk_at_frequencies(const RskSpectrum* spec, const double* freqs, int64_t nf,
   p.ld_out = spec->n;
   p.col0 = 0;
   return launch_eval<kEpiStokes>(p, spec->mode, (cudaStream_t)stream);
+}
+
+int rsk_stokes_component_major(const double* stokes, int64_t nf, int64_t n, double* out, void* stream) {
+  if (nf < 0 || n < 0) return RSK_ERR_SIZE;
+  if (nf == 0 || n == 0) return RSK_OK;
+  if (!stokes || !out) return RSK_ERR_NULL;
+  const int64_t gx = (n + kCmTile - 1) / kCmTile, gy = (nf + kCmTile - 1) / kCmTile;
+  if (gx > 0x7fffffffll || gy > 65535) return RSK_ERR_SIZE;
+  k_stokes_component_major<<<dim3((unsigned)gx, (unsigned)gy), kThreads, 0, (cudaStream_t)stream>>>(stokes, nf, n, out);
+  return launch_status();
 }
 
 int rsk_stokes_to_coherency(const double* stokes, int64_t nf, int64_t n, double* out, void* stream) {

@@ -517,12 +517,16 @@ def write_skyh5(sky, filename, clobber=False, data_compression=None):
         w.dataset("/Header/history", history)
         if sky.name is not None:
             w.dataset("/Header/name", np.asarray(sky.name).astype(str))
-        if sky.component_type == "healpix":
+        # every header parameter that is set is written (skymodel.py:4925-4956): a point object made by
+        # healpix_to_point keeps nside / hpx_order / hpx_inds
+        if sky.nside is not None:
             w.dataset("/Header/nside", np.int64(sky.nside))
+        if sky.hpx_order is not None:
             w.dataset("/Header/hpx_order", sky.hpx_order)
-            inds = sky.hpx_inds
-            if inds is None:
-                inds = np.arange(sky.hpx_first, sky.hpx_first + sky.Ncomponents, dtype=np.int64)
+        inds = sky.hpx_inds
+        if inds is None and sky.component_type == "healpix":  # implicit pixel range
+            inds = np.arange(sky.hpx_first, sky.hpx_first + sky.Ncomponents, dtype=np.int64)
+        if inds is not None:
             w.dataset("/Header/hpx_inds", _host(inds).astype(np.int64))
         if sky.freq_array is not None:
             w.dataset("/Header/freq_array", np.asarray(sky.freq_array, dtype=np.float64), unit="Hz")

@@ -165,9 +165,16 @@ class SkyModel:
             if self.lon.numel() != self.Ncomponents or self.lat.numel() != self.Ncomponents:
                 raise ValueError("coordinate arrays must have length Ncomponents")
             self.frame = str(frame).lower()
-            self.nside = None
+            # a point object made by healpix_to_point keeps its pixel description (skymodel.py:1716-1727), so that
+            # _point_to_healpix can undo the conversion -- also after a write / read round trip
+            self.nside = None if nside is None else int(nside)
+            self.hpx_order = None if hpx_order is None else str(hpx_order).lower()
             self.hpx_inds = None
-            self.hpx_order = None
+            if hpx_inds is not None:
+                if isinstance(hpx_inds, torch.Tensor):
+                    self.hpx_inds = hpx_inds.to(self.device, dtype=torch.int64).contiguous()
+                else:
+                    self.hpx_inds = torch.as_tensor(np.ascontiguousarray(hpx_inds, dtype=np.int64)).to(self.device)
             self.hpx_first = 0
         else:
             if nside is None:
@@ -221,7 +228,7 @@ class SkyModel:
         self._polarized_mask = torch.empty(self.Ncomponents, dtype=torch.uint8, device=self.device)
         self._call("rsk_polarized_mask", _lib.ptr(self.stokes), self.Nfreqs, self.Ncomponents,
                    _lib.ptr(self._polarized_mask))
-        self._n_polarized = int(self._polarized_mask.sum().item())
+        self._n_polarized = self._count(self._polarized_mask, _lib.COUNT_NONZERO_U8)
 
         self.freq_edge_array = None if freq_edge_array is None else np.asarray(_to_hz_host(freq_edge_array)).reshape(2, -1)
         self.history = history
@@ -250,6 +257,12 @@ class SkyModel:
         with torch.cuda.device(self.device):
             code = getattr(_lib.load(), fname)(*args, self._stream())
         _lib.check(fname, code)
+
+    def _count(self, tensor, kind):
+        """Number of NaNs (COUNT_NAN_F64) / non-zero bytes (COUNT_NONZERO_U8) of a device array (rsk_count)."""
+        out = torch.empty(1, dtype=torch.int64, device=self.device)
+        self._call("rsk_count", _lib.ptr(tensor), tensor.numel(), kind, _lib.ptr(out))
+        return int(out.item())
 
     @property
     def _polarized(self):
@@ -291,7 +304,15 @@ class SkyModel:
         if mode == _lib.SPECTRAL_INDEX:
             s.spectral_index = self.spectral_index.data_ptr()
             s.ref_freq = self.reference_frequency.data_ptr()
-        if mode == _lib.SUBBAND:
+        if mode == _lib.SUBBAND and spectral.is_step_kind(freq_interp_kind):
+            # channel-picking kinds ('nearest', 'previous', ...): a degree-0 dense operator, nothing to precompute
+            op = self._step_operator(freq_interp_kind)
+            keep.append(op)
+            s.degree = 0
+            s.breaks = op["breaks"].data_ptr()
+            s.nb = op["breaks"].numel() - 1
+            s.ppoly = op["ppoly"].data_ptr()
+        elif mode == _lib.SUBBAND:
             op = self._subband_operator(freq_interp_kind)
             keep.append(op)
             s.degree = op["degree"]
@@ -301,6 +322,11 @@ class SkyModel:
             s.nc = op["nc"]
             s.first = op["first"].data_ptr()
             s.pband = op["pband"].data_ptr()
+        if mode == _lib.FULL and polarized:
+            cm = self._stokes_component_major()
+            if cm is not None:
+                keep.append(cm)
+                s.stokes_cm = cm.data_ptr()
         if mode == _lib.FULL and freq_map is not None:
             fm = torch.as_tensor(np.ascontiguousarray(freq_map, dtype=np.int32)).to(self.device)
             keep.append(fm)
@@ -309,14 +335,47 @@ class SkyModel:
             s.polarized = self._polarized_mask.data_ptr()
         return s
 
+    def _stokes_component_major(self):
+        """Component-major copy [N][Nfreqs][4] of a stored ('full' / single-channel) Stokes cube for the coherency
+        kernels (RskSpectrum.stokes_cm): made once per catalogue, dropped when the Stokes values change.  None when
+        the copy would not fit comfortably in free HBM, for single-channel cubes whose (4, 1, N) rows are read once
+        anyway, or with RSK_FULL_CM=0."""
+        if os.environ.get("RSK_FULL_CM", "1") == "0" or self.Nfreqs < 2 or self.Ncomponents == 0:
+            return None
+        key = (self.stokes.data_ptr(), self.stokes._version, self.__dict__.get("_stokes_gen", 0), tuple(self.stokes.shape))
+        hit = self.__dict__.get("_cm_cache")
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        nbytes = self.stokes.numel() * 8
+        free, _ = torch.cuda.mem_get_info(self.device)
+        if hit is None and nbytes > 0.35 * free:
+            self._cm_cache = (key, None)
+            return None
+        self.__dict__.pop("_cm_cache", None)
+        cm = torch.empty((self.Ncomponents, self.Nfreqs, 4), dtype=torch.float64, device=self.device)
+        self._call("rsk_stokes_component_major", _lib.ptr(self.stokes), self.Nfreqs, self.Ncomponents, _lib.ptr(cm))
+        self._cm_cache = (key, cm)
+        return cm
+
+    def _step_operator(self, freq_interp_kind):
+        """Device copy of ``spectral.build_step_operator`` (depends on freq_array and kind only)."""
+        key = (str(freq_interp_kind), self.freq_array.tobytes())
+        op = self.__dict__.get("_step_cache")
+        if op is None or op["key"] != key:
+            _, breaks, ppoly = spectral.build_step_operator(self.freq_array, freq_interp_kind)
+            op = dict(key=key, breaks=torch.as_tensor(breaks).to(self.device),
+                      ppoly=torch.as_tensor(np.ascontiguousarray(ppoly)).to(self.device))
+            self._step_cache = op
+        return op
+
     def _subband_operator(self, freq_interp_kind):
         """Device-resident banded spline operator + the spline coefficients of every stored spectrum.
 
         Both are time independent, so they are built once per (stokes contents, freq_array, kind) and
         reused by every ``coherency_calc`` / ``at_frequencies`` call (the reference rebuilds its
         ``interp1d`` on every call, skymodel.py:2362-2368)."""
-        key = (self.stokes.data_ptr(), self.stokes._version, tuple(self.stokes.shape), str(freq_interp_kind),
-               self.freq_array.tobytes())
+        key = (self.stokes.data_ptr(), self.stokes._version, self.__dict__.get("_stokes_gen", 0),
+               tuple(self.stokes.shape), str(freq_interp_kind), self.freq_array.tobytes())
         op = self.__dict__.get("_subband_cache")
         if op is not None and op["key"] == key:
             return op
@@ -481,9 +540,11 @@ class SkyModel:
             elif isinstance(v, np.ndarray):
                 setattr(new, k, v.copy())
         new._freq_dev_cache = {}
-        new.__dict__.pop("_subband_cache", None)
-        new.__dict__.pop("_nan_group_cache", None)
-        new.__dict__.pop("_nan_cache", None)
+        for name in ("_subband_cache", "_nan_group_cache", "_nan_cache", "_cm_cache", "_staging", "_graph",
+                     "_copy_stream", "_timing_events"):
+            new.__dict__.pop(name, None)
+        if new.__dict__.get("_rot_key") is not None and new.alt_az is not None:
+            new._rot_key = (new.alt_az.data_ptr(), new.alt_az._version)  # the cloned coefficients go with the cloned alt_az
         return new
 
     # ------------------------------------------------------------------------------------------
@@ -803,8 +864,17 @@ class SkyModel:
         """astropy_healpix.nside_to_pixel_area(nside) in steradian."""
         return 4 * math.pi / (12 * int(nside) * int(nside))
 
+    def _stokes_changed(self):
+        """The Stokes values were modified in place by a librsk kernel (which torch's ``_version`` counter does not
+        see): drop everything derived from them -- spline coefficients, NaN-pattern groups, NaN flags."""
+        self._stokes_gen = self.__dict__.get("_stokes_gen", 0) + 1
+        for name in ("_subband_cache", "_nan_group_cache", "_nan_cache", "_cm_cache"):
+            self.__dict__.pop(name, None)
+
     def _scale(self, tensor, factor, divide):
         self._call("rsk_scale", _lib.ptr(tensor), tensor.numel(), ctypes.c_double(factor), 1 if divide else 0)
+        if tensor is self.stokes:
+            self._stokes_changed()
 
     def _unit_times_sr(self, unit, divide):
         table = {("K", False): "K sr", ("Jy / sr", False): "Jy", ("K sr", True): "K", ("Jy", True): "Jy / sr"}
@@ -834,7 +904,6 @@ class SkyModel:
             self.frame_coherency = self.frame_coherency * area
         inds = self.hpx_inds.cpu().numpy()
         self.name = np.array(["nside" + str(self.nside) + "_" + self.hpx_order + "_" + str(ind) for ind in inds])
-        self.clear_time_position_specific_params()
         if to_jy:
             self.kelvin_to_jansky()
 
@@ -856,7 +925,6 @@ class SkyModel:
         self.name = None
         self.lon = None
         self.lat = None
-        self.clear_time_position_specific_params()
         if to_k:
             self.jansky_to_kelvin()
 
@@ -1299,7 +1367,7 @@ class SkyModel:
         if self.extra_columns:
             self.extra_columns = {k: np.asarray(v)[host_idx] for k, v in self.extra_columns.items()}
         self.Ncomponents = m
-        self._n_polarized = int(self._polarized_mask.sum().item())
+        self._n_polarized = self._count(self._polarized_mask, _lib.COUNT_NONZERO_U8)
         self._rot_key = None  # the cached rotation coefficients belong to the old component list
         self.__dict__.pop("_rot", None)
         for cache in ("_subband_cache", "_nan_group_cache", "_nan_cache", "_staging", "_graph"):
@@ -1714,12 +1782,7 @@ class SkyModel:
         torch.Tensor, complex128, shape (2, 2, Nfreqs, N_above) -- component axis fastest, only
         components above the horizon, in catalogue order.
         """
-        groups = None
-        if freqs is not None:
-            groups = self._nan_groups(_to_hz_host(freqs), freq_interp_kind, nan_handling)
-            if groups and not sync:
-                raise ValueError("sync=False is not available for subband models with NaN Stokes values")
-        plan = self._plan_coherency(freqs, freq_interp_kind, need_count=sync)
+        plan = self._plan_coherency(freqs, freq_interp_kind, need_count=sync, nan_handling=nan_handling)
         nf, ncols = plan["nf"], plan["n_above"]
         if out is None:
             if pad:
@@ -1734,19 +1797,6 @@ class SkyModel:
         elif ld_out is None:
             ld_out = int(out.shape[-1])
         self._launch_coherency(plan, 0, nf, out, ld_out, col0)
-        for g in groups or ():
-            # columns (positions in the compacted order) whose component belongs to this NaN pattern
-            member = torch.zeros(self.Ncomponents, dtype=torch.bool, device=self.device)
-            member[g["comps"]] = True
-            src = plan["idx"][:ncols] if plan["idx"] is not None else torch.arange(ncols, device=self.device)
-            gcols = torch.nonzero(member[src], as_tuple=False).flatten()
-            if gcols.numel() == 0:
-                continue
-            gplan = dict(plan)
-            gplan["spec"] = self._group_spectrum(g, polarized=True)
-            gplan["cols"] = gcols
-            gplan["n_above"] = int(gcols.numel())
-            self._launch_coherency(gplan, 0, nf, out, ld_out, col0)
         if not sync:
             return out, plan["count"]
         if out.shape[-1] == ncols and col0 == 0:
@@ -1754,7 +1804,7 @@ class SkyModel:
         return out[..., col0:col0 + ncols]
 
     def apparent_coherency_calc(self, beam="short_dipole", jones=None, jones2=None, freqs=None,
-                                freq_interp_kind="cubic", pad=True):
+                                freq_interp_kind="cubic", pad=True, nan_handling="clip"):
         """Instrumental coherency ``J1 C J2^H`` of every above-horizon component (extension).
 
         What a simulator does with the result of :meth:`coherency_calc` -- the contraction
@@ -1776,9 +1826,7 @@ class SkyModel:
         -------
         torch.Tensor complex128 (2, 2, Nfreqs, N_above).
         """
-        if freqs is not None and self._nan_groups(_to_hz_host(freqs), freq_interp_kind, "clip"):
-            raise NotImplementedError("apparent_coherency_calc does not handle NaN subband spectra")
-        plan = self._plan_coherency(freqs, freq_interp_kind, need_count=True)
+        plan = self._plan_coherency(freqs, freq_interp_kind, need_count=True, nan_handling=nan_handling)
         nf, ncols = plan["nf"], plan["n_above"]
         b = _lib.RskBeam()
         if jones is not None:
@@ -1807,7 +1855,8 @@ class SkyModel:
         self._launch_coherency(plan, 0, nf, out, ld, 0)
         return out if ld == ncols else out[..., :ncols]
 
-    def visibility_calc(self, beam="short_dipole", jones=None, jones2=None, freqs=None, uvw=None):
+    def visibility_calc(self, beam="short_dipole", jones=None, jones2=None, freqs=None, uvw=None,
+                        freq_interp_kind="cubic", nan_handling="clip"):
         """Source-summed instrumental coherency (extension; the last step of SURVEY.md 8f N4):
 
             vis[b, a, d, f] = sum_s (J1 C J2^H)[a, d, f, s] * exp(2j pi (f / c) uvw[b] . pos_lmn[:, s])
@@ -1816,14 +1865,22 @@ class SkyModel:
         :meth:`coherency_calc`, the beam Jones matrices and ``pos_lmn``.  Nothing per-component is written to
         HBM.  ``uvw``: (Nbls, 3) baseline vectors in metres (array_like or CUDA tensor); ``None`` gives the
         zero-baseline sum.  ``beam`` / ``jones`` / ``jones2`` / ``freqs`` as :meth:`apparent_coherency_calc`.
-        Spectral types flat, spectral_index and full (call :meth:`at_frequencies` first for subband models).
+        Every spectral type (subband spectra are interpolated to ``freqs`` first, as ``at_frequencies`` does).
 
         Returns a complex128 CUDA tensor of shape (max(Nbls, 1), 2, 2, Nfreqs).
         """
         if self.spectral_type == "subband" and freqs is not None:
-            raise NotImplementedError("visibility_calc evaluates flat, spectral_index and full spectra; call "
-                                      "at_frequencies() first for subband models")
-        plan = self._plan_coherency(freqs, "cubic", need_count=True)
+            # the source-sum kernel evaluates flat, power-law and stored spectra; subband spectra (NaN patterns
+            # included) are first interpolated to the request (K3, 32 B per evaluation written and read back once)
+            fhost = _to_hz_host(freqs)
+            cube, _ = self._evaluate_stokes(fhost, freq_interp_kind, nan_handling)
+            plan = self._plan_coherency(None, freq_interp_kind, need_count=True)
+            spec = plan["spec"]
+            spec.stokes, spec.nf_in = cube.data_ptr(), int(cube.shape[1])
+            plan["keep"].append(cube)
+            plan["nf"], plan["fdev"] = fhost.size, self._freqs_dev(fhost)
+        else:
+            plan = self._plan_coherency(freqs, freq_interp_kind, need_count=True)
         nf, ncols = plan["nf"], plan["n_above"]
         b = _lib.RskBeam()
         if jones is not None:
@@ -1869,7 +1926,7 @@ class SkyModel:
                    ctypes.c_size_t(wbytes))
         return vis
 
-    def _plan_coherency(self, freqs, freq_interp_kind, need_count=True):
+    def _plan_coherency(self, freqs, freq_interp_kind, need_count=True, nan_handling="clip"):
         """Everything coherency_calc needs before the launch: horizon compaction, spectral description,
         R_avg.  With ``need_count`` one device->host read (the above-horizon count) is made, after all
         other host-side preparation so the GPU is idle for as short a time as possible."""
@@ -1895,6 +1952,13 @@ class SkyModel:
         spec = self._spectrum_struct(mode, keep, freq_interp_kind, fmap)
         if mode == _lib.SPECTRAL_INDEX:
             spec.pivot_hz = float(fhost[fhost.size // 2])  # one pivot for every slab of the request
+        # subband spectra with NaNs (skymodel.py:2196-2360): one more launch per NaN pattern, restricted to the
+        # pattern's components by a device-side filter -- no host round trip, so it also works with sync=False,
+        # coherency_calc_to_host and captured steps
+        gspecs = []
+        if freqs is not None and mode == _lib.SUBBAND:
+            groups = self._nan_groups(fhost, freq_interp_kind, nan_handling)
+            gspecs = [self._group_spectrum(g, polarized=True) for g in groups or ()]
         ravg = None
         altaz = None
         if spec.polarized:
@@ -1913,7 +1977,7 @@ class SkyModel:
             coords.rot = self._rot.data_ptr()  # still valid: alt_az untouched since update_positions
         self._last_n_above = n_above
         return dict(spec=spec, keep=keep, mode=mode, nf=nf, fdev=fdev, idx=idx, n_above=n_above, ravg=ravg,
-                    altaz=altaz, coords=coords, count=count, count_dev=count_dev)
+                    altaz=altaz, coords=coords, count=count, count_dev=count_dev, group_specs=gspecs)
 
     def _launch_coherency(self, plan, f0, f1, out, ld_out, col0, packed=False):
         """Launch K2 for request channels [f0, f1) into ``out`` (complex [2][2][f1-f0][ld_out])."""
@@ -1933,20 +1997,22 @@ class SkyModel:
         if events is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(torch.cuda.current_stream(self.device))
-        head = (ctypes.byref(spec), ctypes.byref(plan["coords"]), _lib.ptr(plan["altaz"]), plan["ravg"],
-                None if plan["idx"] is None else _lib.ptr(plan["idx"]), _lib.ptr(plan.get("cols")), plan["n_above"],
-                _lib.ptr(plan["count_dev"]), fptr, nf)
-        if plan.get("beam") is not None:
-            self._call("rsk_apparent_coherency", *head, ctypes.byref(plan["beam"]), _lib.ptr(out), ld_out, col0)
-        else:
-            self._call("rsk_coherency_packed" if packed else "rsk_coherency", *head, _lib.ptr(out), ld_out, col0)
+        for sp in (spec, *plan.get("group_specs", ())):
+            head = (ctypes.byref(sp), ctypes.byref(plan["coords"]), _lib.ptr(plan["altaz"]), plan["ravg"],
+                    None if plan["idx"] is None else _lib.ptr(plan["idx"]), _lib.ptr(plan.get("cols")), plan["n_above"],
+                    _lib.ptr(plan["count_dev"]), fptr, nf)
+            if plan.get("beam") is not None:
+                self._call("rsk_apparent_coherency", *head, ctypes.byref(plan["beam"]), _lib.ptr(out), ld_out, col0)
+            else:
+                self._call("rsk_coherency_packed" if packed else "rsk_coherency", *head, _lib.ptr(out), ld_out, col0)
+            self._launch_count = self.__dict__.get("_launch_count", 0) + 1
         if events is not None:
             ev1.record(torch.cuda.current_stream(self.device))
             events.append((ev0, ev1))
         spec.freq_map = saved_map
 
     def coherency_calc_to_host(self, freqs, host_out=None, slab=64, freq_interp_kind="cubic", packed=True,
-                               nthreads=None):
+                               nthreads=None, nan_handling="clip"):
         """``coherency_calc(freqs=...)`` delivered into HOST memory (extension).
 
         The frequency axis is processed in slabs: while the kernel fills one device slab, the previous
@@ -1973,9 +2039,7 @@ class SkyModel:
 
         Returns the (2, 2, Nfreqs, N_above) view of ``host_out``.
         """
-        if self.spectral_type == "subband" and self._has_nan("stokes"):
-            raise NotImplementedError("coherency_calc_to_host does not handle NaN subband spectra; use coherency_calc")
-        plan = self._plan_coherency(freqs, freq_interp_kind)
+        plan = self._plan_coherency(freqs, freq_interp_kind, nan_handling=nan_handling)
         nf, n_above = plan["nf"], plan["n_above"]
         need = 4 * nf * n_above
         if host_out is None:
@@ -2184,8 +2248,6 @@ class SkyModel:
             return None
         if nan_handling not in ("propagate", "interp", "clip"):
             raise ValueError("nan_handling must be one of ['propagate', 'interp', 'clip']")
-        if self.Nfreqs > 64:
-            raise NotImplementedError("NaN handling on the GPU path supports at most 64 subbands.")
         message = "Some Stokes values are NaNs."
         if nan_handling == "propagate":
             message += " All output Stokes values for sources with any NaN values will be NaN."
@@ -2193,22 +2255,29 @@ class SkyModel:
             message += " Interpolating using the non-NaN values only."
         message += " You can change the way NaNs are handled using the `nan_handling` keyword."
         warnings.warn(message)
-        key = (self.stokes.data_ptr(), self.stokes._version, tuple(self.stokes.shape), str(freq_interp_kind),
-               nan_handling, self.freq_array.tobytes())
+        key = (self.stokes.data_ptr(), self.stokes._version, self.__dict__.get("_stokes_gen", 0),
+               tuple(self.stokes.shape), str(freq_interp_kind), nan_handling, self.freq_array.tobytes())
         cache = self.__dict__.get("_nan_group_cache")
         if cache is None or cache["key"] != key:
-            mask = torch.empty(self.Ncomponents, dtype=torch.int64, device=self.device)
+            nwords = -(-self.Nfreqs // 64)
+            mask = torch.empty((nwords, self.Ncomponents), dtype=torch.int64, device=self.device)
             self._call("rsk_valid_channels", _lib.ptr(self.stokes), self.Nfreqs, self.Ncomponents, _lib.ptr(mask))
-            mask_h = mask.cpu().numpy().view(np.uint64)
-            full = np.uint64((1 << self.Nfreqs) - 1) if self.Nfreqs < 64 else np.uint64(0xFFFFFFFFFFFFFFFF)
-            bad = np.nonzero(mask_h != full)[0]
+            mask_h = mask.cpu().numpy().view(np.uint64)  # (nwords, N): once per catalogue, cached below
+            full = np.array([(1 << min(64, self.Nfreqs - 64 * w)) - 1 for w in range(nwords)], dtype=np.uint64)
+            bad = np.nonzero(np.any(mask_h != full[:, None], axis=0))[0]
+            patterns, inverse = np.unique(mask_h[:, bad].T, axis=0, return_inverse=True)
+            inverse = np.asarray(inverse).reshape(-1)
+            group_of = np.full(self.Ncomponents, -1, dtype=np.int32)  # component -> its NaN-pattern group
+            group_of[bad] = inverse.astype(np.int32)
+            group_of_dev = torch.as_tensor(group_of).to(self.device)
             groups = []
-            for pat in np.unique(mask_h[bad]):
-                comps = bad[mask_h[bad] == pat]
-                use = np.array([j for j in range(self.Nfreqs) if (int(pat) >> j) & 1], dtype=np.int64)
+            for gi, pat in enumerate(patterns):
+                comps = bad[inverse == gi]
+                use = np.array([j for j in range(self.Nfreqs) if (int(pat[j // 64]) >> (j % 64)) & 1], dtype=np.int64)
                 degree, breaks, ppoly, chan, fallback = spectral.build_nan_group_operator(
                     self.freq_array, use, freq_interp_kind, nan_handling)
                 groups.append(dict(
+                    index=gi, group_of=group_of_dev,
                     comps_host=comps, use=use, fallback=fallback and use.size > 0, degree=degree,
                     comps=torch.as_tensor(comps.astype(np.int64)).to(self.device),
                     breaks=torch.as_tensor(breaks).to(self.device),
@@ -2257,8 +2326,13 @@ class SkyModel:
         s.nb = group["breaks"].numel() - 1
         s.chan_map = group["chan"].data_ptr()
         s.nf_use = group["chan"].numel()
-        if polarized and self._n_polarized > 0:
-            s.polarized = self._polarized_mask.data_ptr()
+        if polarized:
+            # coherency launches run over the above-horizon columns: the kernel keeps this group's components
+            # (at_frequencies instead hands the kernel the group's component list)
+            s.group_of = group["group_of"].data_ptr()
+            s.group = group["index"]
+            if self._n_polarized > 0:
+                s.polarized = self._polarized_mask.data_ptr()
         return s
 
     def _has_nan(self, attr):
@@ -2266,11 +2340,11 @@ class SkyModel:
         (the reference re-scans on every call, skymodel.py:2157, :2196; here that would cost a
         reduction kernel and a host sync per time step)."""
         t = getattr(self, attr)
-        key = (t.data_ptr(), t._version, tuple(t.shape))
+        key = (t.data_ptr(), t._version, self.__dict__.get("_stokes_gen", 0), tuple(t.shape))
         cache = self.__dict__.setdefault("_nan_cache", {})
         hit = cache.get(attr)
         if hit is None or hit[0] != key:
-            hit = (key, bool(torch.isnan(t).any().item()))
+            hit = (key, self._count(t.contiguous(), _lib.COUNT_NAN_F64) > 0)
             cache[attr] = hit
         return hit[1]
 
@@ -2284,16 +2358,9 @@ class SkyModel:
             raise ValueError("Some requested frequencies are not present in the current SkyModel.")
         return np.nonzero(matches)[0]
 
-    def at_frequencies(self, freqs, inplace=True, freq_interp_kind="cubic", nan_handling="clip",
-                       run_check=True, check_extra=True, run_check_acceptability=True, atol=None):
-        """Evaluate the stokes array at the specified frequencies (skymodel.py:2084-2389).
-
-        full: subset of existing channels; subband: spline interpolation; spectral_index: power law;
-        flat: copy.  The object becomes ``spectral_type='full'``.  Returns the new object iff
-        ``inplace`` is False.
-        """
-        sky = self if inplace else self.copy()
-        fhost = _to_hz_host(freqs)
+    def _evaluate_stokes(self, fhost, freq_interp_kind="cubic", nan_handling="clip", atol=None):
+        """The (4, Nfreqs, Ncomponents) Stokes cube of ``at_frequencies`` (K3 ``rsk_at_frequencies``), NaN-pattern
+        groups included.  Returns ``(stokes, freq_map)``; ``freq_map`` is the channel subset of a 'full' model."""
         self._check_request(fhost, freq_interp_kind)
         groups = self._nan_groups(fhost, freq_interp_kind, nan_handling)
         mode = _lib.SPECTRAL_MODES[self.spectral_type]
@@ -2308,13 +2375,35 @@ class SkyModel:
             gs = self._group_spectrum(g, polarized=False)
             self._call("rsk_at_frequencies", ctypes.byref(gs), _lib.ptr(fdev), nf, _lib.ptr(g["comps"]),
                        g["comps"].numel(), _lib.ptr(new_stokes))
+        return new_stokes, fmap
+
+    def at_frequencies(self, freqs, inplace=True, freq_interp_kind="cubic", nan_handling="clip",
+                       run_check=True, check_extra=True, run_check_acceptability=True, atol=None):
+        """Evaluate the stokes array at the specified frequencies (skymodel.py:2084-2389).
+
+        full: subset of existing channels; subband: spline interpolation; spectral_index: power law;
+        flat: copy.  The object becomes ``spectral_type='full'``.  Returns the new object iff
+        ``inplace`` is False.
+        """
+        sky = self if inplace else self.copy()
+        fhost = _to_hz_host(freqs)
+        new_stokes, fmap = self._evaluate_stokes(fhost, freq_interp_kind, nan_handling, atol)
+        nf = int(new_stokes.shape[1])
+        was_subband = self.spectral_type == "subband"
         sky.stokes = new_stokes
+        sky._stokes_changed()
         sky.reference_frequency = None
         sky.Nfreqs = nf
-        sky.freq_array = fhost.copy() if fmap is None else self.freq_array[fmap].copy()
+        sky.freq_array = fhost.copy()  # the request itself, as upstream (:2375)
+        if fmap is not None and sky.freq_edge_array is not None:
+            sky.freq_edge_array = sky.freq_edge_array[:, fmap]  # :2179-2180
+        if was_subband and sky.freq_edge_array is not None:
+            sky.freq_edge_array = None  # :2376-2377
         sky.spectral_type = "full"
         if sky.frame_coherency is not None:
             sky.calc_frame_coherency()
+        if run_check:  # :2382-2385
+            sky.check(check_extra=check_extra, run_check_acceptability=run_check_acceptability)
         if not inplace:
             return sky
 
@@ -2335,6 +2424,7 @@ class SkyModel:
             )
         self._call("rsk_convert_units", _lib.ptr(self.stokes), self.Nfreqs, self.Ncomponents, _lib.ptr(fchan),
                    _lib.ptr(fcomp), 1 if to_jansky else 0)
+        self._stokes_changed()
         if self.stokes_error is not None:  # skymodel.py:1583-1584, :1630-1631
             self._call("rsk_convert_units", _lib.ptr(self.stokes_error), self.Nfreqs, self.Ncomponents, _lib.ptr(fchan),
                        _lib.ptr(fcomp), 1 if to_jansky else 0)
@@ -2368,8 +2458,6 @@ class StepGraph:
     """
 
     def __init__(self, sky, freqs=None, freq_interp_kind="cubic"):
-        if sky.spectral_type == "subband" and sky._has_nan("stokes"):
-            raise NotImplementedError("capture_step does not handle NaN subband spectra")
         self.sky = sky
         self.freqs = None if freqs is None else _to_hz_host(freqs)
         self.kind = freq_interp_kind

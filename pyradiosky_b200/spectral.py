@@ -14,10 +14,19 @@ import numpy as np
 import scipy.interpolate
 
 _SPLINE_ORDER = {"slinear": 1, "quadratic": 2, "cubic": 3}
+# interp1d kinds that pick one stored channel per request frequency (piecewise constant in f)
+STEP_KINDS = ("nearest", "nearest-up", "zero", "previous", "next")
+
+
+def is_step_kind(kind):
+    return (isinstance(kind, str) and kind in STEP_KINDS) or (
+        isinstance(kind, (int, np.integer)) and not isinstance(kind, bool) and int(kind) == 0)
 
 
 def interp_degree(kind):
     """Polynomial degree of ``interp1d(kind=...)`` or raise for kinds the kernel does not cover."""
+    if is_step_kind(kind):
+        return 0
     if isinstance(kind, (int, np.integer)):
         order = int(kind)
     elif kind == "linear":
@@ -26,12 +35,43 @@ def interp_degree(kind):
         order = _SPLINE_ORDER[kind]
     else:
         raise NotImplementedError(
-            f"freq_interp_kind={kind!r} is not supported on the GPU path; use 'linear', 'slinear', "
-            "'quadratic', 'cubic' or a spline order 1-3."
+            f"freq_interp_kind={kind!r} is not supported on the GPU path; use 'linear', 'nearest', 'nearest-up', "
+            "'zero', 'slinear', 'quadratic', 'cubic', 'previous', 'next' or a spline order 0-3."
         )
-    if order < 1 or order > 3:
-        raise NotImplementedError("Only spline orders 1, 2 and 3 are supported on the GPU path.")
+    if order < 0 or order > 3:
+        raise NotImplementedError("Only spline orders 0 to 3 are supported on the GPU path.")
     return order
+
+
+def build_step_operator(freq_array, kind):
+    """Piecewise-constant form of ``interp1d(freq_array, ., kind)`` for the channel-picking kinds ('nearest',
+    'nearest-up', 'zero', 'previous', 'next', order 0), in the layout of :func:`build_ppoly_operator` with degree 0.
+
+    Which side of a knot (or of a midpoint between knots) belongs to which channel differs between the kinds and
+    is decided by scipy itself: ``interp1d`` of an identity matrix is evaluated at every possible jump location
+    ``p`` and at the next double after it, so each returned interval ``[breaks[b], breaks[b+1])`` -- closed on the
+    left, as the kernel looks intervals up -- carries exactly scipy's choice, ties included."""
+    x = np.asarray(freq_array, dtype=np.float64)
+    n = x.size
+    order = np.argsort(x, kind="stable")
+    xs = x[order]
+    if np.any(np.diff(xs) <= 0):
+        raise ValueError("Expect x to not have duplicates")
+    big = 1e300
+    if n == 1:
+        raise ValueError("x and y arrays must have at least 2 entries")
+    kind_use = 0 if isinstance(kind, (int, np.integer)) else kind
+    finterp = scipy.interpolate.interp1d(xs, np.eye(n)[order], axis=0, kind=kind_use)
+    mids = 0.5 * (xs[1:] + xs[:-1])
+    jumps = np.unique(np.concatenate((xs, mids)))
+    cand = np.unique(np.concatenate((jumps, np.nextafter(jumps, np.inf))))
+    cand = cand[(cand >= xs[0]) & (cand <= xs[-1])]
+    vals = finterp(cand)  # (ncand, n): one-hot rows
+    keep = np.ones(cand.size, dtype=bool)
+    keep[1:] = np.any(vals[1:] != vals[:-1], axis=1)
+    breaks = np.concatenate((cand[keep], [big]))
+    ppoly = np.ascontiguousarray(vals[keep][:, None, :])
+    return 0, breaks, ppoly
 
 
 def build_ppoly_operator(freq_array, kind="cubic"):
@@ -41,6 +81,8 @@ def build_ppoly_operator(freq_array, kind="cubic"):
     (nb, degree+1, Nfreqs_in): on interval b, with u = (f - breaks[b]) / (breaks[b+1] - breaks[b]),
     ``value = sum_p u**p * (ppoly[b, p, :] @ y)`` for stored channel values ``y``.
     """
+    if is_step_kind(kind):
+        return build_step_operator(freq_array, kind)
     x = np.asarray(freq_array, dtype=np.float64)
     n = x.size
     degree = interp_degree(kind)

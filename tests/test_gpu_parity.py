@@ -907,8 +907,24 @@ def test_coherency_fused_with_nan_spectra(rsk, site):
     ok = np.isfinite(ref)
     scale = np.broadcast_to(np.nanmax(np.abs(st[0]), axis=0)[above][None, None, None, :], ref.shape)
     assert np.max(np.abs(got[ok] - ref[ok]) / scale[ok]) < 1e-12
-    with pytest.raises(ValueError, match="sync=False is not available"):
-        sky.coherency_calc(freqs=freqs, out=torch.empty((2, 2, 41, 1504), dtype=torch.complex128, device="cuda"), sync=False)
+    # the same through the paths that never read the above-horizon count back: queued (sync=False), delivered to the
+    # host in slabs (packed and plain), and replayed from a CUDA graph -- bit-equal to the synchronous call
+    want = torch.as_tensor(got)
+    buf = torch.full((2, 2, 41, 1504), complex(7, 7), dtype=torch.complex128, device="cuda")
+    out, cnt = sky.coherency_calc(freqs=freqs, out=buf, sync=False)
+    c = int(cnt.item())
+    assert c == got.shape[-1]
+    assert torch.equal(torch.view_as_real(out[..., :c]).cpu().nan_to_num(nan=-1.0), torch.view_as_real(want).nan_to_num(nan=-1.0))
+    assert bool((out[..., c:] == complex(7, 7)).all())  # columns past the count are untouched
+    for packed in (True, False):
+        host = torch.empty(4 * 41 * c, dtype=torch.complex128).pin_memory()
+        view = sky.coherency_calc_to_host(freqs, host, slab=16, packed=packed, nthreads=2)
+        torch.cuda.synchronize()
+        assert torch.equal(torch.view_as_real(view).nan_to_num(nan=-1.0), torch.view_as_real(want).nan_to_num(nan=-1.0))
+    graph = sky.copy().capture_step(freqs=freqs)
+    out, cnt = graph.run(time, loc)
+    assert int(cnt.item()) == c
+    assert torch.equal(torch.view_as_real(out[..., :c]).cpu().nan_to_num(nan=-1.0), torch.view_as_real(want).nan_to_num(nan=-1.0))
 
 
 def test_rotation_coefficients_from_k1(rsk, site):
@@ -1365,10 +1381,6 @@ def test_visibility_errors_and_empty(rsk, site):
     time, loc = site
     rng = np.random.default_rng(3)
     ra, dec = random_sky(rng, 200)
-    sub = rsk.SkyModel(ra=ra, dec=dec, stokes=polarized_stokes(rng, 200, 4), spectral_type="subband", freq_array=GLEAM_BANDS[:4])
-    sub.update_positions(time, loc)
-    with pytest.raises(NotImplementedError, match="at_frequencies"):
-        sub.visibility_calc(freqs=[90e6])
     sky = rsk.SkyModel(ra=ra, dec=dec, stokes=polarized_stokes(rng, 200), spectral_type="flat")
     with pytest.raises(ValueError, match="update_positions must be called"):
         sky.visibility_calc(beam="short_dipole")

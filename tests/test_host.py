@@ -34,7 +34,7 @@ def test_struct_layouts_match_header():
     from pyradiosky_b200 import _lib
 
     assert ctypes.sizeof(_lib.RskCoords) == 56
-    assert ctypes.sizeof(_lib.RskSpectrum) == 144
+    assert ctypes.sizeof(_lib.RskSpectrum) == 168
     assert _lib.ASTROM_LEN == 31 and _lib.CTX_LEN == 34
 
 
@@ -205,11 +205,32 @@ def test_ppoly_operator_matches_interp1d(kind):
     assert np.abs(spectral.evaluate_operator(degree, breaks, ppoly, y[perm], f) - ref).max() < 1e-13
 
 
+@pytest.mark.parametrize("kind", ["nearest", "nearest-up", "zero", "previous", "next", 0])
+def test_step_operator_matches_interp1d(kind):
+    """The channel-picking interp1d kinds (skymodel.py:2362-2368 passes any kind through): bit-equal to scipy at the
+    knots, at the midpoints between knots, one ulp either side of both, and at random frequencies."""
+    import scipy.interpolate
+
+    from pyradiosky_b200 import spectral
+
+    x = np.array([76, 84, 92, 99, 107, 115, 122, 130, 143, 151, 158, 166, 174, 181, 189, 197, 204, 212, 220, 227]) * 1e6
+    rng = np.random.default_rng(3)
+    y = rng.normal(size=(20, 5))
+    mids = 0.5 * (x[1:] + x[:-1])
+    f = np.concatenate([x, mids, np.nextafter(x[:-1], np.inf), np.nextafter(x[1:], 0), np.nextafter(mids, np.inf),
+                        np.nextafter(mids, 0), rng.uniform(x[0], x[-1], 3000)])
+    for xs, ys in ((x, y), (x[::-1].copy(), y[::-1].copy())):
+        degree, breaks, ppoly = spectral.build_ppoly_operator(xs, kind)
+        assert degree == 0 and ppoly.shape == (breaks.size - 1, 1, 20)
+        ref = scipy.interpolate.interp1d(xs, ys, axis=0, kind=kind)(f)
+        assert np.array_equal(spectral.evaluate_operator(degree, breaks, ppoly, ys, f), ref)
+
+
 def test_ppoly_operator_errors():
     from pyradiosky_b200 import spectral
 
     with pytest.raises(NotImplementedError):
-        spectral.build_ppoly_operator(np.linspace(1, 2, 10), "nearest")
+        spectral.build_ppoly_operator(np.linspace(1, 2, 10), "akima")
     with pytest.raises(NotImplementedError):
         spectral.build_ppoly_operator(np.linspace(1, 2, 10), 5)
     with pytest.raises(ValueError):

@@ -406,3 +406,124 @@ def test_lonlat_to_healpix_inverts_pixel_centres():
     ra, dec = hp.healpix_to_lonlat(32, np.array([25]))
     off = np.deg2rad(0.01)
     assert list(hp.lonlat_to_healpix(32, ra + np.array([-off, off]), dec + np.array([-off, off]))) == [25, 25]
+
+
+# ---------------------------------------------------------------------------------------------------
+# ERFA's own known-answer vectors (src/t_erfa_c.c): the anchor of the position chain outside this repo
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def erfa_kat():
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "erfa_check_values.json")) as fh:
+        return json.load(fh)
+
+
+def _astrom_from(star, obs=None):
+    """eraASTROM (31 doubles) from the star-independent part of one check record and the observer part of another."""
+    a = np.zeros(E.ASTROM_LEN)
+    a[E.I_PMT] = star["pmt"]
+    a[E.I_EB:E.I_EB + 3] = star["eb"]
+    a[E.I_EH:E.I_EH + 3] = star["eh"]
+    a[E.I_EM] = star["em"]
+    a[E.I_V:E.I_V + 3] = star["v"]
+    a[E.I_BM1] = star["bm1"]
+    a[E.I_BPN:E.I_BPN + 9] = np.asarray(star["bpn"]).ravel()
+    if obs is not None:
+        for key, slot in (("along", E.I_ALONG), ("xpl", E.I_XPL), ("ypl", E.I_YPL), ("sphi", E.I_SPHI), ("cphi", E.I_CPHI),
+                          ("diurab", E.I_DIURAB), ("eral", E.I_ERAL), ("refa", E.I_REFA), ("refb", E.I_REFB)):
+            a[slot] = obs[key]
+        a[E.I_PHI] = obs.get("phi", 0.0)
+    return a
+
+
+def test_erfa_check_values(erfa_kat):
+    """oracle/erfa_np.py against ERFA's published test vectors: eraAb, eraLd, eraAtciqz (on the eraApci13 context),
+    eraAtioq (on the eraApio13 context: refraction and diurnal aberration present), eraApcs, eraApco, eraPvtob,
+    eraGd2gc, eraC2ixys, eraEra00, eraSp00.  Tolerances are t_erfa_c.c's own (1e-12) or tighter."""
+    k = erfa_kat
+    ab = k["ab"]
+    got = E.ab(np.asarray(ab["pnat"])[:, None], ab["v"], ab["s"], ab["bm1"])[:, 0]
+    assert np.abs(got - ab["ppr"]).max() < 1e-15
+    ld = k["ld"]
+    got = E.ld(ld["bm"], np.asarray(ld["p"])[:, None], np.asarray(ld["q"])[:, None], ld["e"], ld["em"], ld["dlim"])[:, 0]
+    assert np.abs(got - ld["p1"]).max() < 1e-15
+    # apci13's context is internally consistent (orthogonal bpn, unit eh, bm1 = sqrt(1 - v^2)) ...
+    star = k["apci13"]
+    bpn = np.asarray(star["bpn"])
+    assert np.abs(bpn @ bpn.T - np.eye(3)).max() < 1e-15
+    assert abs(np.linalg.norm(star["eh"]) - 1.0) < 1e-15
+    assert abs(np.sqrt(1.0 - np.sum(np.square(star["v"]))) - star["bm1"]) < 1e-15
+    # ... and carries (2.71, 0.174) to ERFA's CIRS answer through light deflection, aberration and bpn
+    q = k["atciqz"]
+    ri, di = E.atciqz(np.array([q["rc"]]), np.array([q["dc"]]), _astrom_from(star))
+    assert abs(ri[0] - q["ri"]) < 1e-15 and abs(di[0] - q["di"]) < 1e-15
+    # CIRS -> observed with polar motion, diurnal aberration and A/B refraction
+    o = k["atioq"]
+    obs = np.zeros(E.ASTROM_LEN)
+    for key, slot in (("along", E.I_ALONG), ("xpl", E.I_XPL), ("ypl", E.I_YPL), ("sphi", E.I_SPHI), ("cphi", E.I_CPHI),
+                      ("diurab", E.I_DIURAB), ("eral", E.I_ERAL), ("refa", E.I_REFA), ("refb", E.I_REFB)):
+        obs[slot] = k["apio13"][key]
+    az, zd = E.atioq(np.array([o["ri"]]), np.array([o["di"]]), obs)
+    assert abs(az[0] - o["aob"]) < 1e-15 and abs(zd[0] - o["zob"]) < 1e-15
+    # the star-independent parameters themselves
+    c = k["apcs"]
+    a = E.apcs(*c["date"], np.asarray(c["pv"]), np.asarray(c["ebpv"]), np.asarray(c["ehp"]))
+    assert abs(a[E.I_PMT] - c["pmt"]) < 1e-11 and abs(a[E.I_EM] - c["em"]) < 1e-15 and abs(a[E.I_BM1] - c["bm1"]) < 1e-15
+    assert np.abs(a[E.I_EB:E.I_EB + 3] - c["eb"]).max() < 1e-15 and np.abs(a[E.I_EH:E.I_EH + 3] - c["eh"]).max() < 1e-15
+    assert np.abs(a[E.I_V:E.I_V + 3] - c["v"]).max() < 1e-19  # (with AULT = 499.004782 this is 3.3e-13)
+    c = k["apco"]
+    a = E.apco(*c["date"], np.asarray(k["apcs"]["ebpv"]), np.asarray(k["apcs"]["ehp"]), c["x"], c["y"], c["s"], c["theta"],
+               c["elong"], c["phi"], c["hm"], c["xp"], c["yp"], c["sp"], c["refa"], c["refb"])
+    want = _astrom_from(c, c)
+    want[E.I_PHI] = c["phi"]
+    assert np.abs(a - want).max() < 1e-15
+    c = k["pvtob"]
+    p, v = E.pvtob(c["elong"], c["phi"], c["hm"], c["xp"], c["yp"], c["sp"], c["theta"])
+    assert np.abs(p - c["p"]).max() < 1e-5 and np.abs(v - c["v"]).max() < 1e-9  # t_erfa_c: 1e-5 m, 1e-9 m/s
+    c = k["gd2gc_wgs84"]
+    assert np.abs(E.gd2gc_wgs84(c["elong"], c["phi"], c["height"]) - c["xyz"]).max() < 1e-7
+    c = k["c2ixys"]
+    assert np.abs(E.c2ixys(c["x"], c["y"], c["s"]) - c["rc2i"]).max() < 1e-15
+    assert abs(E.era00(*k["era00"]["date"]) - k["era00"]["era"]) < 1e-12
+    assert abs(E.sp00(*k["sp00"]["date"]) - k["sp00"]["sp"]) < 1e-24
+
+
+def test_apio13_observer_part_from_oracle_builder(erfa_kat):
+    """The Earth-rotation / site half of a context (eral, along, xpl, ypl, sphi, cphi) needs no series: eraApio13's
+    published values follow from era00, sp00 and the polar-motion composition the oracle's apco already uses."""
+    c = erfa_kat["apio13"]
+    utc1, utc2 = c["utc"]
+    tai = utc2 + E.tai_minus_utc(utc1 + utc2) / E.DAYSEC
+    tt = tai + 32.184 / E.DAYSEC
+    ut1 = utc2 + c["dut1"] / E.DAYSEC
+    sp = E.sp00(utc1, tt)
+    theta = E.era00(utc1, ut1)
+    dummy = np.array([[1.0, 0, 0], [0, 0.01, 0]])
+    a = E.apco(utc1, tt, dummy, np.array([1.0, 0, 0]), 0.0, 0.0, 0.0, theta, c["elong"], c["phi"], c["hm"], c["xp"],
+               c["yp"], sp, c["refa"], c["refb"])
+    for key, slot in (("along", E.I_ALONG), ("xpl", E.I_XPL), ("ypl", E.I_YPL), ("sphi", E.I_SPHI), ("cphi", E.I_CPHI),
+                      ("eral", E.I_ERAL)):
+        assert abs(a[slot] - c[key]) < 1e-12, key
+
+
+def test_aberration_and_deflection_magnitudes(hera):
+    """SURVEY Appendix A invariant (ii), independent of any recalled number: annual aberration displaces a source 90 deg
+    from the Earth's velocity by v/c ~ 20.5 arcsec towards the apex, and the Sun deflects light from a source 90 deg
+    away from it by 4.07 mas, radially away from the Sun."""
+    lon, lat, h, jd = hera
+    a = E.astrom_context(jd, 0.3, lon, lat, h)
+    v = a[E.I_V:E.I_V + 3]
+    vhat = v / np.linalg.norm(v)
+    perp = np.cross(vhat, [0.0, 0.0, 1.0]); perp /= np.linalg.norm(perp)
+    out = E.ab(perp[:, None], v, a[E.I_EM], a[E.I_BM1])[:, 0]
+    shift = np.arccos(np.clip(out @ perp, -1, 1))
+    assert abs(shift - np.linalg.norm(v)) < 1e-9 and 20.0 < np.rad2deg(shift) * 3600 < 21.0
+    assert out @ vhat > 0  # towards the apex
+    eh = a[E.I_EH:E.I_EH + 3]  # Sun -> observer
+    p = np.cross(eh, [0.0, 0.0, 1.0]); p /= np.linalg.norm(p)  # 90 deg from the Sun
+    d = E.ld(1.0, p[:, None], p[:, None], eh, a[E.I_EM], 1e-6)[:, 0]
+    defl = np.linalg.norm(d - p)
+    assert abs(np.rad2deg(defl) * 3600e3 - 4.07 / a[E.I_EM]) < 0.02  # 2 SRS / em at 90 deg = 4.07 mas at 1 au
+    assert (d - p) @ eh > 0  # away from the Sun (eh points from the Sun to the observer)
