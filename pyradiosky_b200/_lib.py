@@ -314,6 +314,15 @@ _SIGNATURES.update(_IO_SIGNATURES)
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
+# Kernel launches per entry point (for callers that report how many of the library's kernels they queued, e.g.
+# bench.py's ``gpu_launches``): every call that is not listed launches exactly one kernel, host helpers none.
+LAUNCHES_PER_CALL = {"rsk_compact_index": 3, "rsk_visibility": 2, "rsk_count": 1}
+LAUNCHES = [0]  # process-wide running total, advanced by SkyModel._call
+
+
+def count_launches(fname):
+    LAUNCHES[0] += LAUNCHES_PER_CALL.get(fname, 1)
+
 _lib = None
 
 

@@ -23,6 +23,7 @@ constexpr int kMaxFChunk = 256;     // frequencies staged in shared memory per b
 // per block, frequency chunk fastest in the grid, no residency cap.  RSK_K2_FCHUNK / RSK_K2_TILEFAST /
 // RSK_K2_SMEM override them for tuning runs.
 constexpr int kDefaultFChunk = 64;
+constexpr int kFullCmFChunk = 32;            // FULL mode reading the component-major copy (measured)
 constexpr int kSubbandFChunk = 256;          // longer chunks: the per-block staging cost is amortised (measured)
 constexpr int kMaxDynSmem = 200 * 1024;      // dynamic shared memory budget per block
 constexpr int kDefaultTileFast = 0;
@@ -986,6 +987,20 @@ k_eval(const __grid_constant__ EvalParams p) {
   }
   if (MODE != RSK_FLAT) __syncthreads();
 
+  // FULL with a component-major copy: which layout this block reads is decided per block from how densely its
+  // columns sit in the catalogue (measured on B200: the gathered (4, Nf, N) reads win above ~0.75 -- they are
+  // coalesced and nearly every fetched sector is used -- the per-component rows below it)
+  bool use_cm = false;
+  if (MODE == RSK_FULL && p.stokes_cm) {
+    use_cm = true;
+    if (p.idx && !p.cols) {
+      const int64_t k0 = tile * NT, k1 = min(k0 + NT, ncols) - 1;
+      const int64_t span = __ldg(p.idx + k1) - __ldg(p.idx + k0) + 1;
+      use_cm = 4 * (k1 - k0 + 1) < 3 * span;
+    } else if (!p.idx && !p.cols) {
+      use_cm = false;  // every component is a column: plain coalesced rows
+    }
+  }
   const int64_t kcol = tile * NT + threadIdx.x;
   if (kcol >= ncols) return;
   const int64_t col = p.cols ? __ldg(p.cols + kcol) : kcol;
@@ -1155,17 +1170,20 @@ k_eval(const __grid_constant__ EvalParams p) {
       for (int q = 0; q < 4; ++q) o[q] = fma(fma(fma(cf[3][q], u, cf[2][q]), u, cf[1][q]), u, cf[0][q]);
       emit<EPI>(p, f0 + k, col, o, jp);
     }
-  } else if (p.stokes_cm) {
+  } else if (use_cm) {
     // RSK_FULL from the component-major copy: this column's (I, Q, U, V) at one channel are one 32-byte sector, the
     // channels of a component are consecutive sectors -- exactly 32 bytes read per evaluation whatever the horizon
-    // mask looks like (the gathered reads below fetch nearly every sector of a scattered mask's gaps too)
-    const double2* __restrict__ row = p.stokes_cm + (int64_t)src * p.nf_in * 2;
+    // mask looks like (the gathered reads below fetch nearly every sector of a scattered mask's gaps too).  One
+    // 256-bit load per evaluation.
+    const double* __restrict__ row = reinterpret_cast<const double*>(p.stokes_cm) + (int64_t)src * p.nf_in * 4;
 #pragma unroll 4
     for (int k = 0; k < nfc; ++k) {
-      const double2 iq = __ldcs(row + 2 * (int64_t)s_iv[k]);
-      const double2 uv = __ldcs(row + 2 * (int64_t)s_iv[k] + 1);
+      double y0, y1, y2, y3;
+      asm("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];"
+          : "=d"(y0), "=d"(y1), "=d"(y2), "=d"(y3)
+          : "l"(row + 4 * (int64_t)s_iv[k]));
       double o[4];
-      xform<EPI>(rot, iq.x, iq.y, uv.x, uv.y, o);
+      xform<EPI>(rot, y0, y1, y2, y3, o);
       emit<EPI>(p, f0 + k, col, o, jp);
     }
   } else {  // RSK_FULL: stored Stokes, skymodel.py:2165-2181 subset + utils.py:42-57
@@ -1598,7 +1616,9 @@ int fill_eval_params(const RskSpectrum* spec, const double* freqs, int64_t nf, i
   const int64_t tiles = (ncols + nt - 1) / nt;
   // SUBBAND: stage each column's 4 * nf_in stored values in shared memory when they fit
   p->y_in_smem = (dense_subband && !spec->chan_map && 4 * spec->nf_in * nt * (int64_t)sizeof(double) <= kMaxDynSmem) ? 1 : 0;
-  int fchunk = tuning_int("RSK_K2_FCHUNK", dense_subband ? kSubbandFChunk : kDefaultFChunk);
+  // (stored Stokes read from the component-major copy: 32-frequency chunks measured best, 0.86 against 0.84 with 64
+  // and 0.81 with 128 of the 96 B/eval roofline, profiles/r02_full_path_fchunk_sweep.txt)
+  int fchunk = tuning_int("RSK_K2_FCHUNK", dense_subband ? kSubbandFChunk : (p->stokes_cm ? kFullCmFChunk : kDefaultFChunk));
   if (fchunk < 1) fchunk = 1;
   if (fchunk > kMaxFChunk) fchunk = kMaxFChunk;
   if (fchunk > nf) fchunk = (int)(nf > 0 ? nf : 1);

@@ -257,6 +257,7 @@ class SkyModel:
         with torch.cuda.device(self.device):
             code = getattr(_lib.load(), fname)(*args, self._stream())
         _lib.check(fname, code)
+        _lib.count_launches(fname)
 
     def _count(self, tensor, kind):
         """Number of NaNs (COUNT_NAN_F64) / non-zero bytes (COUNT_NONZERO_U8) of a device array (rsk_count)."""
@@ -1792,7 +1793,13 @@ class SkyModel:
                 ld_out = -(-ncols // gran) * gran
             else:
                 ld_out = ncols
-            out = torch.empty((2, 2, nf, max(ld_out, 0)), dtype=torch.complex128, device=self.device)
+            try:
+                out = torch.empty((2, 2, nf, max(ld_out, 0)), dtype=torch.complex128, device=self.device)
+            except torch.OutOfMemoryError:
+                # a result that takes more than half of HBM: the cached block of the previous time step (a slightly
+                # different size) must go back to the driver before this one fits
+                torch.cuda.empty_cache()
+                out = torch.empty((2, 2, nf, max(ld_out, 0)), dtype=torch.complex128, device=self.device)
             col0 = 0
         elif ld_out is None:
             ld_out = int(out.shape[-1])
@@ -2005,7 +2012,6 @@ class SkyModel:
                 self._call("rsk_apparent_coherency", *head, ctypes.byref(plan["beam"]), _lib.ptr(out), ld_out, col0)
             else:
                 self._call("rsk_coherency_packed" if packed else "rsk_coherency", *head, _lib.ptr(out), ld_out, col0)
-            self._launch_count = self.__dict__.get("_launch_count", 0) + 1
         if events is not None:
             ev1.record(torch.cuda.current_stream(self.device))
             events.append((ev0, ev1))

@@ -518,7 +518,7 @@ def test_at_frequencies_errors(rsk):
     with pytest.raises(ValueError, match="Some spectral index values are NaNs."):
         sky2.at_frequencies(sky.freq_array)
     with pytest.raises(NotImplementedError):
-        sky.at_frequencies(sky.freq_array, freq_interp_kind="nearest")
+        sky.at_frequencies(sky.freq_array, freq_interp_kind=5)
     sky.stokes[0, 0, 0] = float("nan")
     with pytest.raises(ValueError, match="nan_handling must be one of "):
         sky.at_frequencies(sky.freq_array, nan_handling="foo")

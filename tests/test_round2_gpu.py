@@ -170,6 +170,7 @@ def test_skyh5_roundtrip_keeps_healpix_description_of_point_objects(rsk, tmp_pat
     back = rsk.SkyModel.from_skyh5(path)
     assert back.component_type == "point" and back.nside == 4 and back.hpx_order == "nested"
     assert torch.equal(back.hpx_inds, torch.arange(192, device=back.hpx_inds.device))
+    back.filename = sky.filename  # (the reader records the file name, as upstream)
     assert back == sky
     back._point_to_healpix()
     assert back.component_type == "healpix" and back.stokes_unit == "K"
