@@ -62,7 +62,8 @@ WORKLOADS = {
     "c2": ("BASELINE configs[1]: GLEAM-like 300k point sources, full Stokes, power-law spectral index, "
            "1024 frequencies, fk5", 300_000, 1024, "spectral_index", "fk5"),
     "c3": ("BASELINE configs[2]: HEALPix nside=1024 ring map (12.6M pixels), full Stokes, power law, "
-           "256 frequencies, one launch per time step (no frequency chunking)", 12 * 1024 * 1024, 256, "spectral_index", "icrs"),
+           "256 frequencies, one launch per time step (no frequency chunking); N > 1: pixels dealt out in blocks of 4096",
+           12 * 1024 * 1024, 256, "spectral_index", "icrs"),
     "c4": ("BASELINE configs[3]: 1M polarized sources, 20 GLEAM subbands cubic-interpolated to 1024 channels",
            1_000_000, 1024, "subband", "icrs"),
     "n1m": ("north_star target: 1M polarized sources x 1024 frequencies, power law", 1_000_000, 1024,
@@ -542,8 +543,26 @@ def coherency_record(ctx, r, steps, kernel, unit=UNIT):
     }
 
 
+HPX_SHARD_BLOCK = 4096  # pixels per block of the block-cyclic HEALPix split
+
+
 def make_sky(ctx, workload, seed=2):
     _, n, nf, stype, frame = WORKLOADS[workload]
+    if workload == "c3" and ctx.world > 1:
+        # A ring-ordered map split into contiguous ranges is a split by latitude: at HERA the southern ranks would hold
+        # three times as many above-horizon pixels as the northern ones.  Deal the pixels out in blocks instead (rank r
+        # takes blocks r, r + N, ...): every rank sees every latitude.  hpx_inds names the pixels explicitly.
+        cat = synth_catalog(workload, seed)
+        blocks = np.arange(n // HPX_SHARD_BLOCK)
+        mine = blocks[blocks % ctx.world == ctx.rank]
+        pix = (mine[:, None] * HPX_SHARD_BLOCK + np.arange(HPX_SHARD_BLOCK)[None, :]).ravel()
+        for key in ("stokes", "spectral_index", "reference_frequency"):
+            cat[key] = np.ascontiguousarray(cat[key][..., pix])
+        cat["n"] = pix.size
+        kw = model_kwargs(cat)
+        kw.pop("hpx_first")
+        kw["hpx_inds"] = pix
+        return ctx.rsk.SkyModel(**kw, device=ctx.dev), cat
     lo, hi = shard_bounds(n, ctx.world, ctx.rank)
     cat = synth_catalog(workload, seed, lo, hi)
     sky = ctx.rsk.SkyModel(**model_kwargs(cat), device=ctx.dev)
@@ -930,7 +949,10 @@ def measure_gather(ctx, steps):
         return best
 
     try:
-        pg = PeerGather(len(freqs), total, device=ctx.dev)
+        # (a rank's launch is sized for all of its components -- the count stays on the device -- so the buffer needs
+        # room for the columns before it plus its whole block)
+        (nmax,), _ = ctx.reduce([sky.Ncomponents], [0.0])
+        pg = PeerGather(len(freqs), total + int(nmax), device=ctx.dev)
         ms_all = timed(lambda: pg.coherency_calc(sky, freqs=freqs))
         ms_one = timed(lambda: pg.coherency_calc(sky, freqs=freqs, dst=0))
         recv_all = nbytes * (ctx.world - 1) / ctx.world  # bytes each GPU receives from its peers

@@ -119,7 +119,8 @@ class PeerGather:
     """Gathered coherency array in symmetric memory, filled by the kernels themselves over NVLink.
 
     ``PeerGather(nfreqs, max_cols)`` allocates, once, a ``(2, 2, nfreqs, ld)`` complex128 buffer on every rank
-    (``ld`` = ``max_cols`` rounded up to 16 columns: 256-byte rows) with
+    (``ld`` = ``max_cols`` rounded up to 16 columns: 256-byte rows; ``max_cols`` must cover the gathered columns plus
+    the largest rank's component count, because every launch is sized for its rank's whole block) with
     ``torch.distributed._symmetric_memory`` and maps every peer's copy.  :meth:`coherency_calc` then runs, per
     time step: the 8-byte count exchange (column offsets), one ``rsk_coherency`` launch per destination whose
     ``out`` pointer is the *destination's* buffer and whose ``col0`` is this rank's offset, and a device-side
@@ -158,6 +159,10 @@ class PeerGather:
         counts, col0, total = exchange_counts(n_above, self.device, self.group)
         if total > self.ld:
             raise ValueError(f"gathered array needs {total} columns, the buffer has {self.ld}")
+        if col0 + sky.Ncomponents > self.ld:
+            # the launches below leave the count on the device, so each is sized for the rank's whole block
+            raise ValueError(f"PeerGather needs max_cols >= column offset + Ncomponents of every rank "
+                             f"({col0} + {sky.Ncomponents} > {self.ld}); allocate sum(N_above) + max(Ncomponents)")
         # all-gather: at step k rank i writes to rank (i + k) mod world, so every step is a permutation -- each GPU
         # receives from exactly one sender at a time instead of all ranks converging on the same destination
         targets = [(self.rank + k) % self.world for k in range(self.world)] if dst is None else [int(dst)]

@@ -694,10 +694,16 @@ def test_column_offsets_for_sharded_output(rsk, site):
 # ---------------------------------------------------------------------------------------------------
 # full-size properties (BASELINE configs 2 and 4): size-independent invariants + sampled oracle columns
 # ---------------------------------------------------------------------------------------------------
-def _check_invariants_and_samples(rsk, sky, lon, lat, st, kw, spectral_type, freqs, got, rng, nsample=400):
+def _check_invariants_and_samples(rsk, sky, lon, lat, st, kw, spectral_type, freqs, got, rng, nsample=400, frame="icrs"):
     above = sky.above_horizon.cpu().numpy()
     cols = np.nonzero(above)[0]
     assert got.shape == (2, 2, freqs.size, cols.size)
+    # positions of EVERY component against the oracle's own chain (not the GPU's alt_az fed back to the oracle)
+    m = None if frame == "icrs" else rsk.astrometry.frame_to_icrs_matrix(frame)
+    o_alt_az, o_lmn, o_above = S.update_positions(lon, lat, sky._astrom, m)
+    assert_altaz_close(sky.alt_az.cpu().numpy(), o_alt_az)
+    assert_mask_equal(above, o_above, o_alt_az[0])
+    assert np.abs(sky.pos_lmn.cpu().numpy() - o_lmn).max() < 1e-14
     # invariants on device, all columns: Hermitian, real diagonal, imag parts antisymmetric
     assert torch.equal(got[0, 1].real, got[1, 0].real) and torch.equal(got[0, 1].imag, -got[1, 0].imag)
     assert float(got[0, 0].imag.abs().max()) == 0.0 and float(got[1, 1].imag.abs().max()) == 0.0
@@ -706,7 +712,7 @@ def _check_invariants_and_samples(rsk, sky, lon, lat, st, kw, spectral_type, fre
     src = cols[pick]
     sub_kw = {k: (v[src] if k in ("reference_frequency", "spectral_index") else v) for k, v in kw.items()}
     full = oracle_eval(st[:, :, src], spectral_type, freqs, sub_kw)
-    alt_az = sky.alt_az.cpu().numpy()[:, src]
+    alt_az = o_alt_az[:, src]  # the oracle's positions
     ref = S.coherency_calc(full, lon[src], lat[src], alt_az, np.ones(nsample, bool),
                            S.calc_average_rotation_matrix(sky._astrom),
                            polarized=S.polarized_indices(st[:, :, src]), vectorized=True)
@@ -730,7 +736,7 @@ def test_config2_full_size_properties(rsk, site):
     freqs = np.linspace(100e6, 200e6, 1024)
     sky.update_positions(time, loc)
     got = sky.coherency_calc(freqs=freqs)
-    _check_invariants_and_samples(rsk, sky, lon, lat, st, kw, "spectral_index", freqs, got, rng)
+    _check_invariants_and_samples(rsk, sky, lon, lat, st, kw, "spectral_index", freqs, got, rng, frame="fk5")
     # idempotence: a second evaluation is bit-identical
     assert torch.equal(got, sky.coherency_calc(freqs=freqs))
 
@@ -746,6 +752,59 @@ def test_config4_subband_full_size_properties(rsk, site):
     sky.update_positions(time, loc)
     got = sky.coherency_calc(freqs=freqs)
     _check_invariants_and_samples(rsk, sky, lon, lat, st, kw, "subband", freqs, got, rng)
+
+
+def test_target_shape_1m_x_1024_properties(rsk, site):
+    """The north-star shape: 1M polarised components x 1024 frequencies, power law (33 GB of coherency), checked like
+    config 2: every position against the oracle's chain, invariants on all columns, 400 oracle columns."""
+    time, loc = site
+    rng = np.random.default_rng(8)
+    n = 1_000_000
+    sky, lon, lat, st, kw = make_model(rsk, rng, "spectral_index", n)
+    freqs = np.linspace(100e6, 200e6, 1024)
+    sky.update_positions(time, loc)
+    got = sky.coherency_calc(freqs=freqs)
+    _check_invariants_and_samples(rsk, sky, lon, lat, st, kw, "spectral_index", freqs, got, rng)
+    del got
+    torch.cuda.empty_cache()
+
+
+def test_config3_healpix_nside1024_coherency_samples(rsk, site):
+    """BASELINE config 3 at its real resolution: pixel-range chunks of the nside-1024 ring map (north cap, the equatorial
+    belt across the horizon, south cap), full Stokes power law x 256 frequencies, coherency of sampled pixels against
+    the oracle (its own pixel centres, its own positions)."""
+    time, loc = site
+    rng = np.random.default_rng(33)
+    nside, nf = 1024, 256
+    npix = 12 * nside * nside
+    freqs = np.linspace(100e6, 200e6, nf)
+    m = 1 << 18
+    for first in (0, npix // 2 - m // 2, 5 * npix // 8, npix - m):
+        st = polarized_stokes(rng, m)
+        st[1:, :, rng.uniform(size=m) < 0.3] = 0.0
+        alpha = np.clip(rng.normal(-0.8, 0.2, m), -2, 1)
+        f0 = np.full(m, 150e6)
+        sky = rsk.SkyModel(nside=nside, hpx_order="ring", hpx_first=first, stokes=st, spectral_type="spectral_index",
+                           spectral_index=alpha, reference_frequency=f0, stokes_unit="K")
+        sky.update_positions(time, loc)
+        got = sky.coherency_calc(freqs=freqs)
+        above = sky.above_horizon.cpu().numpy()
+        cols = np.nonzero(above)[0]
+        assert got.shape == (2, 2, nf, cols.size)
+        pix = first + np.arange(m)
+        lon, lat = hp.healpix_to_lonlat(nside, pix)
+        o_alt_az, _, o_above = S.update_positions(lon, lat, sky._astrom)
+        assert_altaz_close(sky.alt_az.cpu().numpy(), o_alt_az)
+        assert_mask_equal(above, o_above, o_alt_az[0])
+        if cols.size == 0:
+            continue
+        pick = np.sort(rng.choice(cols.size, min(200, cols.size), replace=False))
+        src = cols[pick]
+        full = S.at_frequencies(st[:, :, src], "spectral_index", freqs, reference_frequency=f0[src], spectral_index=alpha[src])
+        ref = S.coherency_calc(full, lon[src], lat[src], o_alt_az[:, src], np.ones(src.size, bool),
+                               S.calc_average_rotation_matrix(sky._astrom), polarized=S.polarized_indices(st[:, :, src]),
+                               vectorized=True)
+        assert_coherency_close(got[..., torch.as_tensor(pick, device="cuda")].cpu().numpy(), ref, full[0])
 
 
 def test_empty_and_tiny_models(rsk, site):
