@@ -952,14 +952,17 @@ def measure_gather(ctx, steps):
         # (a rank's launch is sized for all of its components -- the count stays on the device -- so the buffer needs
         # room for the columns before it plus its whole block)
         (nmax,), _ = ctx.reduce([sky.Ncomponents], [0.0])
-        pg = PeerGather(len(freqs), total + int(nmax), device=ctx.dev)
-        ms_all = timed(lambda: pg.coherency_calc(sky, freqs=freqs))
-        ms_one = timed(lambda: pg.coherency_calc(sky, freqs=freqs, dst=0))
+        pg = PeerGather(len(freqs), total + int(nmax), device=ctx.dev, streams=4)
         recv_all = nbytes * (ctx.world - 1) / ctx.world  # bytes each GPU receives from its peers
-        rec["peer_store_all_gather"] = {"ms": ms_all, "GBps_received_per_gpu": recv_all / (ms_all * 1e-3) / 1e9,
-                                        "frac_of_peer_copy": recv_all / (ms_all * 1e-3) / 1e9 / peak}
-        rec["peer_store_to_rank0"] = {"ms": ms_one, "GBps_received": recv_all / (ms_one * 1e-3) / 1e9,
-                                      "frac_of_peer_copy": recv_all / (ms_one * 1e-3) / 1e9 / peak}
+        for route, what in (("copy", "kernel writes its columns locally in 4 column slabs; copy engines push each finished "
+                                     "slab to the peers while the next slab is computed"),
+                            ("store", "one kernel launch per destination, the kernel's own stores travel over NVLink")):
+            ms_all = timed(lambda: pg.coherency_calc(sky, freqs=freqs, route=route))
+            ms_one = timed(lambda: pg.coherency_calc(sky, freqs=freqs, dst=0, route=route))
+            rec[f"peer_{route}_all_gather"] = {"ms": ms_all, "GBps_received_per_gpu": recv_all / (ms_all * 1e-3) / 1e9,
+                                               "frac_of_peer_copy": recv_all / (ms_all * 1e-3) / 1e9 / peak, "what": what}
+            rec[f"peer_{route}_to_rank0"] = {"ms": ms_one, "GBps_received": recv_all / (ms_one * 1e-3) / 1e9,
+                                             "frac_of_peer_copy": recv_all / (ms_one * 1e-3) / 1e9 / peak}
         del pg
     except Exception as exc:
         rec["peer_store_error"] = str(exc)[:300]

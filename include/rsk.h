@@ -403,6 +403,12 @@ int rsk_visibility(const RskSpectrum* spec, const RskCoords* coords, const doubl
                    double* vis /* complex [max(nbl,1)][2][2][nf] */, void* work, size_t work_bytes, void* stream);
 size_t rsk_visibility_workspace_bytes(int64_t ncols, int64_t nf, int64_t nbl);
 
+/* Pitched device-to-device copy of ``height`` rows of ``width_bytes`` (cudaMemcpy2DAsync): how a rank's column block of the
+ * gathered (2, 2, Nf, sum N_above) array travels to the same place of a peer GPU's array over NVLink (the optional
+ * assembly of north_star; dst may be peer-mapped memory).  Copy engines, asynchronous on ``stream``. */
+int rsk_copy_2d(void* dst, size_t dst_pitch_bytes, const void* src, size_t src_pitch_bytes, size_t width_bytes,
+                size_t height, void* stream);
+
 /* HOST: expand a packed slab (HOST pointer, e.g. pinned staging memory that a cudaMemcpyAsync has filled)
  * into rows [f0_out, f0_out + nf) of the reference-layout array out = complex [2][2][nf_out][ld_out] in host
  * memory, with nthreads threads.  Pure data movement (duplicate / negate), no arithmetic of the path. */

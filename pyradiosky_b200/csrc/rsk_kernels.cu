@@ -2130,6 +2130,16 @@ int rsk_at_frequencies(const RskSpectrum* spec, const double* freqs, int64_t nf,
   return launch_eval<kEpiStokes>(p, spec->mode, (cudaStream_t)stream);
 }
 
+int rsk_copy_2d(void* dst, size_t dst_pitch_bytes, const void* src, size_t src_pitch_bytes, size_t width_bytes,
+                size_t height, void* stream) {
+  if (width_bytes == 0 || height == 0) return RSK_OK;
+  if (!dst || !src) return RSK_ERR_NULL;
+  if (dst_pitch_bytes < width_bytes || src_pitch_bytes < width_bytes) return RSK_ERR_LD;
+  const cudaError_t e = cudaMemcpy2DAsync(dst, dst_pitch_bytes, src, src_pitch_bytes, width_bytes, height,
+                                          cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  return e == cudaSuccess ? RSK_OK : (int)e;
+}
+
 int rsk_stokes_component_major(const double* stokes, int64_t nf, int64_t n, double* out, void* stream) {
   if (nf < 0 || n < 0) return RSK_ERR_SIZE;
   if (nf == 0 || n == 0) return RSK_OK;

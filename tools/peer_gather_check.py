@@ -78,6 +78,11 @@ def main():
     pg.buf.zero_()
     ms_root, (view0, _) = timed(lambda: pg.coherency_calc(mine, freqs=freqs, dst=0))
     ok_root = bool(torch.equal(view0, ref)) if rank == 0 else True
+    # the kernels' own stores over NVLink (route="store") must give the same array
+    pg.buf.zero_()
+    ms_store, (view_s, _) = timed(lambda: pg.coherency_calc(mine, freqs=freqs, route="store"))
+    ok_all = ok_all and bool(torch.equal(view_s, ref))
+    res["peer_store_route_all_ranks_ms"] = ms_store
     # NCCL route: local result, all_gather of padded blocks, re-pack
     def nccl_route():
         local_out = mine.coherency_calc(freqs=freqs, pad=False)
