@@ -368,6 +368,28 @@ def k2_algorithmic_bytes(cat, n_above, stored_full=False):
     return 64 * nf * n_above + per_comp * n_above + 8 * nf
 
 
+def traffic_record(workload):
+    """``roofline.traffic``: dram__bytes_read + dram__bytes_write per launch of the dominant kernel from the committed
+    ``ncu --set full`` capture of this workload (profiles/k_eval_traffic.json) -- reported only while the kernel sources
+    are the ones the capture was taken with; otherwise null, never a stale constant."""
+    import hashlib
+
+    path = os.path.join(ROOT, "profiles", "k_eval_traffic.json")
+    try:
+        entry = json.load(open(path)).get(workload)
+        h = hashlib.sha1()
+        for f in ("rsk_kernels.cu", "rsk_device.cuh"):
+            h.update(open(os.path.join(ROOT, "pyradiosky_b200", "csrc", f), "rb").read())
+    except (OSError, ValueError):
+        entry = None
+    if not entry:
+        return {"traffic": None, "traffic_source": "no ncu capture committed for this workload"}
+    if entry.get("kernel_source_sha1") != h.hexdigest():
+        return {"traffic": None, "traffic_source": f"capture {entry.get('capture')} predates the current kernel sources"}
+    return {"traffic": entry["traffic_bytes"], "traffic_source": f"{entry.get('capture')}; kernel sources unchanged since "
+            f"(sha1 {h.hexdigest()[:12]}); per launch of one GPU holding the whole catalogue"}
+
+
 class Ctx:
     """Per-process state of the GPU arm."""
 
@@ -1072,9 +1094,10 @@ def run_gpu(args):
 
     if ctx.rank == 0:
         cfg = config_record(workload, ctx.world)
-        head["roofline"].update({"traffic": None, "peak_source": ctx.peak_src,
-                                 "traffic_note": "dram__bytes of this kernel from the committed ncu capture: "
-                                                 "profiles/ (see r02 summary); not re-measured in the bench run"})
+        tr = traffic_record(workload)
+        if ctx.world > 1 and tr["traffic"] is not None:  # a rank launches on 1/N of the catalogue
+            tr = {"traffic": tr["traffic"] / ctx.world, "traffic_source": tr["traffic_source"] + f", divided by {ctx.world} ranks"}
+        head["roofline"].update({"peak_source": ctx.peak_src, **tr})
         line = {
             "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": ctx.world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"],

@@ -19,7 +19,8 @@ namespace {
 
 constexpr int kThreads = 256;       // threads per block for the component-parallel kernels
 constexpr int kMaxFChunk = 256;     // frequencies staged in shared memory per block
-// K2 launch shape, from sweeps of the real kernel on B200 (profiles/r01_k2_tuning.md): 64 frequencies
+// K2 launch shape, from sweeps of the real kernel on B200 (profiles/r01_k2_launch_shape_sweep_c2.log,
+// r01_k2_launch_shape_sweep_unpolarized.log, r01_k2_register_cap_sweep.log): 64 frequencies
 // per block, frequency chunk fastest in the grid, no residency cap.  RSK_K2_FCHUNK / RSK_K2_TILEFAST /
 // RSK_K2_SMEM override them for tuning runs.
 constexpr int kDefaultFChunk = 64;

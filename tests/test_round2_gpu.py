@@ -289,3 +289,29 @@ def test_device_chain_reproduces_erfa_check_values(rsk, site):
         alt_az, _, _ = sky.positions_sweep([time, time], loc, astroms=np.stack([astrom, astrom]))
         got = alt_az.cpu().numpy()
         assert np.abs(got[:, 0, 0] - want_alt).max() < 1e-14 and np.abs(got[:, 1, 0] - want_az).max() < 1e-14
+
+
+def test_astropy_context_bytes_give_astropy_alt_az(rsk):
+    """With astropy present (not on the build / GPU image: skipped there) the reference's own call,
+    ``skycoord.transform_to(AltAz(obstime, location))`` (skymodel.py:2451-2454), and this package fed the real
+    ``eraASTROM`` of ``erfa_astrom.get().apco`` must agree to 1 uas -- the N2 row closed by astropy itself."""
+    astropy = pytest.importorskip("astropy")  # noqa: F841
+    import astropy.units as u
+    from astropy.coordinates import AltAz, EarthLocation, SkyCoord
+    from astropy.time import Time
+
+    rng = np.random.default_rng(14)
+    n = 5000
+    ra, dec = random_sky(rng, n)
+    loc = EarthLocation.from_geodetic(lon=21.428305555 * u.deg, lat=-30.72152777 * u.deg, height=1073.0 * u.m)
+    time = Time("2015-03-01 00:00:00", scale="utc", location=loc)
+    want = SkyCoord(ra=ra * u.rad, dec=dec * u.rad, frame="icrs").transform_to(AltAz(obstime=time, location=loc))
+    st = np.zeros((4, 1, n)); st[0] = 1.0
+    sky = rsk.SkyModel(ra=ra, dec=dec, stokes=st, spectral_type="flat")
+    sky.update_positions(time, loc)  # astropy objects: the context is astropy's own eraASTROM
+    got = sky.alt_az.cpu().numpy()
+    uas = np.pi / 180 / 3600 * 1e-6
+    assert np.abs(got[0] - want.alt.rad).max() < uas
+    d_az = np.abs(got[1] - want.az.rad)
+    assert (np.minimum(d_az, 2 * np.pi - d_az) * np.cos(want.alt.rad)).max() < uas
+    assert np.array_equal(sky.above_horizon.cpu().numpy(), want.alt.rad > 0)
