@@ -698,6 +698,14 @@ def run_sweep(ctx, steps, warmup):
                      "per": "GPU; 17 B per (source, time): alt, az, mask"},
         "host_context_build_ms": host_ctx_s * 1e3,
     }
+    # this kernel is bound by fp64 issue, not by HBM (profiles/r02_sweep_floor.md): 77 fp64-pipe instructions per
+    # evaluation in the SASS of the time loop, 2 dispatch cycles each on the 4 x 148 schedulers
+    sm_hz = 1.965e9
+    pipe_ms = (n * nt / 32.0) / (4 * 148) * 77 * 2 / sm_hz * 1e3
+    rec["fp64_pipe"] = {"fp64_instr_per_eval": 77, "pipe_floor_ms": pipe_ms, "frac_of_pipe_floor": pipe_ms / kmax,
+                        "hbm_frac_at_pipe_floor": n * nt * 17 / (pipe_ms * 1e-3) / 1e9 / ctx.peak,
+                        "note": "floor = fp64 instructions alone at 16 lanes per scheduler and 1965 MHz, per GPU; even at "
+                                "the floor the kernel would sit at 0.63 of the 17-byte HBM roofline"}
     if ctx.rank == 0:
         k = nt // 3
         ref_alt_az, _ = positions_cpu_baseline(lon[:2000], lat[:2000], astroms[k:k + 1])
@@ -974,10 +982,10 @@ def measure_gather(ctx, steps):
         # (a rank's launch is sized for all of its components -- the count stays on the device -- so the buffer needs
         # room for the columns before it plus its whole block)
         (nmax,), _ = ctx.reduce([sky.Ncomponents], [0.0])
-        pg = PeerGather(len(freqs), total + int(nmax), device=ctx.dev, streams=4)
+        pg = PeerGather(len(freqs), total + int(nmax), device=ctx.dev, streams=2)
         recv_all = nbytes * (ctx.world - 1) / ctx.world  # bytes each GPU receives from its peers
-        for route, what in (("copy", "kernel writes its columns locally in 4 column slabs; copy engines push each finished "
-                                     "slab to the peers while the next slab is computed"),
+        for route, what in (("copy", "kernel writes its columns locally in up to 4 column slabs (>= 32k columns each); copy "
+                                     "engines push each finished slab to the peers while the next slab is computed"),
                             ("store", "one kernel launch per destination, the kernel's own stores travel over NVLink")):
             ms_all = timed(lambda: pg.coherency_calc(sky, freqs=freqs, route=route))
             ms_one = timed(lambda: pg.coherency_calc(sky, freqs=freqs, dst=0, route=route))

@@ -213,7 +213,9 @@ class PeerGather:
         self.handle.barrier()  # nobody is still reading the previous step's array
         main = torch.cuda.current_stream(self.device)
         lib = _lib.load()
-        nslab = max(1, min(int(slabs), -(-n_above // 4096))) if n_above > 0 else 0
+        # slabs of at least 32k columns (0.5 MB rows): measured on 8 B200 (profiles/r02_gather_sweep_8gpu.txt), shorter
+        # rows cost more in copy-engine efficiency than the overlap with the next slab's kernel gains
+        nslab = max(1, min(int(slabs), n_above // 32768)) if n_above > 0 else 0
         per = -(-(-(-n_above // max(nslab, 1))) // 16) * 16 if nslab else 0  # whole 256-byte groups per slab
         esize = 16
         base = self.buf.data_ptr()
