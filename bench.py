@@ -896,15 +896,18 @@ def measure_e2e(ctx, workload, counts_hint, e2e_steps):
     dram_per_eval = wire + 96.0 * packed_share
     dram_ms = ev_step_rank * dram_per_eval / (ceil["host_dram_traffic_GBps_this_rank"] * 1e9) * 1e3
     ceil.update({"link_floor_ms_per_step": link_ms, "host_expand_floor_ms_per_step": host_ms,
-                 "host_dram_floor_ms_per_step": dram_ms, "host_dram_bytes_per_eval": dram_per_eval,
                  "frac_of_link_floor": link_ms / ms_step, "frac_of_host_floor": host_ms / ms_step if host_ms else None,
-                 "frac_of_host_dram_floor": dram_ms / ms_step,
-                 "frac_of_binding_floor": max(link_ms, host_ms, dram_ms) / ms_step,
-                 "note": "floors per rank: bytes over PCIe / D2H rate measured alone; 64 B per evaluation / expansion rate "
-                         "measured alone (packed and mixed routes); host DRAM bytes of the route / host DRAM traffic measured "
-                         "with copies and expansion running at once -- the copies and the expansion share the host memory "
-                         "system, so the last one binds on this host (alone, each of the two runs ~1.5-2x faster than beside "
-                         "the other); the step cannot be faster than the largest floor"})
+                 "frac_of_binding_floor": max(link_ms, host_ms) / ms_step,
+                 "host_dram_model": {"bytes_per_eval": dram_per_eval, "floor_ms_per_step": dram_ms,
+                                     "frac": dram_ms / ms_step,
+                                     "what": "estimate, not a bound: host DRAM bytes of the route (DMA writes + 32 B read and 64 B "
+                                             "written per expanded evaluation) over the DRAM traffic measured with copies and "
+                                             "expansion free-running side by side"},
+                 "note": "floors per rank, each measured with all ranks active at once: bytes over PCIe / concurrent D2H rate "
+                         "(on these hosts the ranks share one host bridge: the rate per GPU falls from 57 GB/s alone to 35 at "
+                         "2, 18 at 4 and 11-15 at 8 ranks); 64 B per evaluation / expansion rate (packed and mixed routes). "
+                         "The two share the host memory system (side by side each runs at 0.5-0.8 of its rate alone), which is "
+                         "why a packed step sits between the floors and their sum"})
     return {
         "value": evals / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * ctx.world,
         "d2h_bytes_per_step": d2h / e2e_steps, "steps": e2e_steps, "ms_per_step": ms_step,

@@ -339,6 +339,7 @@ int rsk_valid_channels(const double* stokes /* [4][nf_in][n] */, int64_t nf_in, 
  * SkyModel._polarized, the above-horizon count of a mask). */
 #define RSK_COUNT_NAN_F64 0
 #define RSK_COUNT_NONZERO_U8 1
+#define RSK_COUNT_NEGATIVE_F64 2 /* the negative-Stokes-I acceptability test of SkyModel.check (skymodel.py:1258-1264) */
 int rsk_count(const void* x, int64_t count, int kind, int64_t* out /* device [1] */, void* stream);
 
 /* SkyModel._polarized (skymodel.py:1037-1042): pol[c] = any over stored channels of (Q+U+V != 0). */

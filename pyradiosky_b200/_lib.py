@@ -75,7 +75,7 @@ class RskBeam(ctypes.Structure):
 
 
 BEAM_JONES, BEAM_SHORT_DIPOLE, BEAM_UNIFORM = 0, 1, 2
-COUNT_NAN_F64, COUNT_NONZERO_U8 = 0, 1
+COUNT_NAN_F64, COUNT_NONZERO_U8, COUNT_NEGATIVE_F64 = 0, 1, 2
 
 
 class RskSelect(ctypes.Structure):

@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(kThreads) k_valid_channels(const double* __res
   }
 }
 
-// Number of NaNs in a double array (KIND 0) or of non-zero bytes in a byte array (KIND 1): the np.any(np.isnan(...))
+// Number of NaNs (KIND 0) / negative values (KIND 2) in a double array or of non-zero bytes in a byte array (KIND 1): the np.any(np.isnan(...))
 // tests of skymodel.py:2157, :2196 and the size of SkyModel._polarized, without a library reduction.
 template <int KIND>
 __global__ void __launch_bounds__(kThreads) k_count(const void* __restrict__ x, const int64_t count,
@@ -714,6 +714,8 @@ __global__ void __launch_bounds__(kThreads) k_count(const void* __restrict__ x, 
     if (KIND == 0) {
       const double v = __ldg(static_cast<const double*>(x) + i);
       c += (v != v) ? 1 : 0;
+    } else if (KIND == 2) {
+      c += __ldg(static_cast<const double*>(x) + i) < 0.0 ? 1 : 0;
     } else {
       c += __ldg(static_cast<const uint8_t*>(x) + i) != 0 ? 1 : 0;
     }
@@ -1137,11 +1139,14 @@ k_eval(const __grid_constant__ EvalParams p) {
     const int64_t cstride = p.nc * p.n;
     const int dp1 = p.degree + 1;
     double cf[4][4];  // [power][output quantity]
-    int cur = -1;
-    for (int k = 0; k < nfc; ++k) {
-      const int iv = s_iv[k];
-      if (iv != cur) {  // uniform across the block
-        cur = iv;
+    // The chunk is walked in runs of channels that share a break interval (uniform across the block): the polynomial
+    // coefficients are set up once per run and the run itself is a branch-free loop the compiler can unroll, so the
+    // stores of several channels are in flight together.
+    for (int k0 = 0; k0 < nfc;) {
+      const int iv = s_iv[k0];
+      int k1 = k0 + 1;
+      while (k1 < nfc && s_iv[k1] == iv) ++k1;
+      {
         const double* cc = p.bcoef + (int64_t)__ldg(p.first + iv) * p.n + src;
         const double* pb = p.pband + (int64_t)iv * dp1 * dp1;
         double c[4][4];  // [m][stokes]
@@ -1165,11 +1170,15 @@ k_eval(const __grid_constant__ EvalParams p) {
           xform<EPI>(rot, acc[0], acc[1], acc[2], acc[3], cf[a]);
         }
       }
-      const double u = s_fa[k];
-      double o[4];
+#pragma unroll 4
+      for (int k = k0; k < k1; ++k) {
+        const double u = s_fa[k];
+        double o[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) o[q] = fma(fma(fma(cf[3][q], u, cf[2][q]), u, cf[1][q]), u, cf[0][q]);
-      emit<EPI>(p, f0 + k, col, o, jp);
+        for (int q = 0; q < 4; ++q) o[q] = fma(fma(fma(cf[3][q], u, cf[2][q]), u, cf[1][q]), u, cf[0][q]);
+        emit<EPI>(p, f0 + k, col, o, jp);
+      }
+      k0 = k1;
     }
   } else if (use_cm) {
     // RSK_FULL from the component-major copy: this column's (I, Q, U, V) at one channel are one 32-byte sector, the
@@ -1911,7 +1920,7 @@ int rsk_valid_channels(const double* stokes, int64_t nf_in, int64_t n, uint64_t*
 int rsk_count(const void* x, int64_t count, int kind, int64_t* out, void* stream) {
   if (!out) return RSK_ERR_NULL;
   if (count < 0) return RSK_ERR_SIZE;
-  if (kind != RSK_COUNT_NAN_F64 && kind != RSK_COUNT_NONZERO_U8) return RSK_ERR_MODE;
+  if (kind != RSK_COUNT_NAN_F64 && kind != RSK_COUNT_NONZERO_U8 && kind != RSK_COUNT_NEGATIVE_F64) return RSK_ERR_MODE;
   cudaStream_t st = (cudaStream_t)stream;
   const cudaError_t e = cudaMemsetAsync(out, 0, sizeof(int64_t), st);
   if (e != cudaSuccess) return (int)e;
@@ -1920,6 +1929,8 @@ int rsk_count(const void* x, int64_t count, int kind, int64_t* out, void* stream
   const unsigned grid = (unsigned)std::min<int64_t>((count + kThreads - 1) / kThreads, 148 * 16);
   if (kind == RSK_COUNT_NAN_F64)
     k_count<0><<<grid, kThreads, 0, st>>>(x, count, reinterpret_cast<unsigned long long*>(out));
+  else if (kind == RSK_COUNT_NEGATIVE_F64)
+    k_count<2><<<grid, kThreads, 0, st>>>(x, count, reinterpret_cast<unsigned long long*>(out));
   else
     k_count<1><<<grid, kThreads, 0, st>>>(x, count, reinterpret_cast<unsigned long long*>(out));
   return launch_status();

@@ -435,7 +435,7 @@ class SkyModel:
             if check_extra and t is not None and tuple(t.shape) != tuple(self.stokes.shape):
                 raise ValueError(f"{attr} must have the shape of stokes, {tuple(self.stokes.shape)}; it is {tuple(t.shape)}")
         if run_check_acceptability:
-            if self.spectral_type == "spectral_index" and bool(torch.isnan(self.spectral_index).any()):
+            if self.spectral_type == "spectral_index" and self._has_nan("spectral_index"):
                 warnings.warn(
                     "Some spectral index values are NaNs. If this is a GLEAM-based "
                     "sky model, consider using the 'subband' spectral type to"
@@ -443,13 +443,13 @@ class SkyModel:
                     "sources that are not well-fit by a power law, this can include "
                     "bright sources)."
                 )
-            if bool(torch.isnan(self.stokes).any()):
+            if self._has_nan("stokes"):
                 warnings.warn(
                     "Some Stokes values are NaNs. Use the select method with the"
                     "'non_nan' parameter to remove sources with NaN values at "
                     "any or all frequencies."
                 )
-            if bool((self.stokes[0] < 0).any()):
+            if self._count(self.stokes[0], _lib.COUNT_NEGATIVE_F64) > 0:
                 warnings.warn(
                     "Some Stokes I values are negative. Use the select method "
                     "with the 'non_negative' parameter to remove sources with "
