@@ -298,6 +298,12 @@ def test_sweep_equals_repeated_update(rsk, site):
     margin = np.abs(np.abs(tans) - 1) > 0.1
     assert np.array_equal(up.all(axis=0)[margin], (tans > 1)[margin])
     assert np.array_equal((~up).all(axis=0)[margin], (tans < -1)[margin])
+    # contexts packed and uploaded once, reused by later sweeps
+    ctx = sky.sweep_contexts(times, loc)
+    a3, l3, m3 = sky.positions_sweep(None, loc, contexts=ctx, want_lmn=True)
+    assert torch.equal(a3, alt_az) and torch.equal(l3, lmn) and torch.equal(m3, above)
+    with pytest.raises(ValueError, match="contexts must be"):
+        sky.positions_sweep(None, loc, contexts=ctx[:, :5])
     a2, _, m2 = sky.positions_sweep(times[:3], loc, want_lmn=False, want_mask=False)
     assert m2 is None and float((a2 - alt_az[:3]).abs().max()) < 1e-14
     # contexts with refraction / diurnal aberration mixed with plain ones (some time blocks folded, some not):

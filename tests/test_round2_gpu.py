@@ -315,3 +315,52 @@ def test_astropy_context_bytes_give_astropy_alt_az(rsk):
     d_az = np.abs(got[1] - want.az.rad)
     assert (np.minimum(d_az, 2 * np.pi - d_az) * np.cos(want.alt.rad)).max() < uas
     assert np.array_equal(sky.above_horizon.cpu().numpy(), want.alt.rad > 0)
+
+
+@pytest.mark.parametrize("spectral_type,frame", [("spectral_index", "fk5"), ("subband", "icrs"), ("flat", "icrs")])
+def test_position_overlap_is_bit_identical(rsk, site, spectral_type, frame):
+    """enable_position_overlap(): K1 + compaction of step k + 1 on a side stream beside K2 of step k, two buffer sets.
+    Every step's positions, mask and coherency equal the plain sequence bit for bit, also when the caller reads the
+    position arrays between the two calls and when a big kernel is still running on the caller's stream."""
+    time, loc = site
+    rng = np.random.default_rng(99)
+    n, nf = 60_000, 64
+    sky = make_model(rsk, rng, spectral_type, n, frame=frame)[0]
+    ref = sky.copy()
+    freqs = np.linspace(100e6, 160e6, nf)
+    sky.enable_position_overlap()
+    buf = torch.empty((2, 2, nf, -(-n // 16) * 16), dtype=torch.complex128, device="cuda")
+    outs, alts, masks, cnts = [], [], [], []
+    for k in range(7):
+        sky.update_positions(time + 0.013 * k, loc)
+        if k % 2:
+            alts.append(sky.alt_az.clone())  # a read on the caller's stream right after the update
+        else:
+            alts.append(None)
+        _, cnt = sky.coherency_calc(freqs=freqs, out=buf, sync=False)
+        if alts[-1] is None:
+            alts[-1] = sky.alt_az.clone()
+        masks.append(sky.above_horizon.clone())
+        outs.append(buf.clone())
+        cnts.append(cnt.clone())
+    torch.cuda.synchronize()
+    for k in range(7):
+        ref.update_positions(time + 0.013 * k, loc)
+        want = ref.coherency_calc(freqs=freqs, pad=False)
+        c = int(cnts[k].item())
+        assert c == want.shape[-1]
+        assert torch.equal(alts[k], ref.alt_az) and torch.equal(masks[k], ref.above_horizon)
+        assert torch.equal(outs[k][..., :c], want)
+    # the exactly-sized call and a copy of the model work as before
+    sky.update_positions(time + 0.5, loc)
+    ref.update_positions(time + 0.5, loc)
+    assert torch.equal(sky.coherency_calc(freqs=freqs, pad=False), ref.coherency_calc(freqs=freqs, pad=False))
+    other = sky.copy()
+    assert "_overlap" not in other.__dict__
+    other.update_positions(time + 0.6, loc)
+    ref.update_positions(time + 0.6, loc)
+    assert torch.equal(other.alt_az, ref.alt_az)
+    sky.enable_position_overlap(False)
+    sky.update_positions(time + 0.7, loc)
+    ref.update_positions(time + 0.7, loc)
+    assert torch.equal(sky.alt_az, ref.alt_az)
