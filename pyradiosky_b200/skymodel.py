@@ -295,7 +295,7 @@ class SkyModel:
             self._freq_dev_cache[key] = t
         return t
 
-    def _spectrum_struct(self, mode, keep, freq_interp_kind="cubic", freq_map=None, polarized=True):
+    def _spectrum_struct(self, mode, keep, freq_interp_kind="cubic", freq_map=None, polarized=True, want_cm=True):
         """RskSpectrum for the stored model; ``keep`` collects tensors that must outlive the call."""
         s = _lib.RskSpectrum()
         s.mode = mode
@@ -323,7 +323,7 @@ class SkyModel:
             s.nc = op["nc"]
             s.first = op["first"].data_ptr()
             s.pband = op["pband"].data_ptr()
-        if mode == _lib.FULL and polarized:
+        if mode == _lib.FULL and polarized and want_cm:
             cm = self._stokes_component_major()
             if cm is not None:
                 keep.append(cm)
@@ -1314,6 +1314,9 @@ class SkyModel:
     def _update_positions_overlapped(self, astrom):
         st = self._overlap
         n = self.Ncomponents
+        if st["sets"][0]["alt_az"].shape[1] != n or (st["sets"][0]["rot"] is None) != (self._n_polarized == 0):
+            self.enable_position_overlap()  # the component list changed (select / concat): new buffer sets
+            st = self._overlap
         main = torch.cuda.current_stream(self.device)
         side = st["side"]
         cur, other = st["sets"][st["k"] % 2], st["sets"][(st["k"] + 1) % 2]
@@ -1967,13 +1970,14 @@ class SkyModel:
             # included) are first interpolated to the request (K3, 32 B per evaluation written and read back once)
             fhost = _to_hz_host(freqs)
             cube, _ = self._evaluate_stokes(fhost, freq_interp_kind, nan_handling)
-            plan = self._plan_coherency(None, freq_interp_kind, need_count=True)
+            plan = self._plan_coherency(None, freq_interp_kind, need_count=True, want_cm=False)
             spec = plan["spec"]
             spec.stokes, spec.nf_in = cube.data_ptr(), int(cube.shape[1])
             plan["keep"].append(cube)
             plan["nf"], plan["fdev"] = fhost.size, self._freqs_dev(fhost)
         else:
-            plan = self._plan_coherency(freqs, freq_interp_kind, need_count=True)
+            # (the source-sum kernel reads the (4, Nf, N) cube itself: no component-major copy is made for it)
+            plan = self._plan_coherency(freqs, freq_interp_kind, need_count=True, want_cm=False)
         nf, ncols = plan["nf"], plan["n_above"]
         b = _lib.RskBeam()
         if jones is not None:
@@ -2019,7 +2023,7 @@ class SkyModel:
                    ctypes.c_size_t(wbytes))
         return vis
 
-    def _plan_coherency(self, freqs, freq_interp_kind, need_count=True, nan_handling="clip"):
+    def _plan_coherency(self, freqs, freq_interp_kind, need_count=True, nan_handling="clip", want_cm=True):
         """Everything coherency_calc needs before the launch: horizon compaction, spectral description,
         R_avg.  With ``need_count`` one device->host read (the above-horizon count) is made, after all
         other host-side preparation so the GPU is idle for as short a time as possible."""
@@ -2047,7 +2051,7 @@ class SkyModel:
             fmap = self._full_freq_map(fhost) if mode == _lib.FULL else None
             nf = fhost.size
             fdev = self._freqs_dev(fhost)
-        spec = self._spectrum_struct(mode, keep, freq_interp_kind, fmap)
+        spec = self._spectrum_struct(mode, keep, freq_interp_kind, fmap, want_cm=want_cm)
         if mode == _lib.SPECTRAL_INDEX:
             spec.pivot_hz = float(fhost[fhost.size // 2])  # one pivot for every slab of the request
         # subband spectra with NaNs (skymodel.py:2196-2360): one more launch per NaN pattern, restricted to the
