@@ -398,3 +398,45 @@ def test_headers_compile_as_c_and_layouts_match_ctypes(tmp_path):
         assert int(out[name]) == ctypes.sizeof(cls), name
         for field, _ in cls._fields_:
             assert int(out[f"{name}.{field}"]) == getattr(cls, field).offset, f"{name}.{field}"
+
+
+def test_bench_catalogue_is_the_same_for_every_rank_count():
+    """bench.py shards ONE catalogue (strong scaling): the blocks of 2, 4 and 8 ranks concatenate to the single-rank
+    catalogue, for point and subband workloads, and the GPU and reference arms describe the same config."""
+    import bench
+
+    for wl in ("c2", "c1"):
+        n = bench.WORKLOADS[wl][1]
+        whole = bench.synth_catalog(wl)
+        for world in (2, 4, 8):
+            parts = [bench.synth_catalog(wl, 2, *bench.shard_bounds(n, world, r)) for r in range(world)]
+            assert sum(p["n"] for p in parts) == n
+            for key in ("stokes", "lon", "lat"):
+                assert np.array_equal(np.concatenate([p[key] for p in parts], axis=-1), whole[key])
+    n = bench.WORKLOADS["c4"][1]
+    lo8, hi8 = bench.shard_bounds(n, 8, 5)
+    lo2, hi2 = bench.shard_bounds(n, 2, 1)
+    a, b = bench.synth_catalog("c4", 2, lo8, hi8), bench.synth_catalog("c4", 2, lo2, hi2)
+    assert a["stokes"].shape == (4, 20, n // 8)
+    assert np.array_equal(a["stokes"], b["stokes"][..., lo8 - lo2:hi8 - lo2])
+    assert np.array_equal(a["lon"], b["lon"][lo8 - lo2:hi8 - lo2])
+    cfg1, cfg8 = bench.config_record("n1m", 1), bench.config_record("n1m", 8)
+    assert set(cfg1) == set(cfg8) and cfg8["components_per_gpu"] == 125_000 and cfg1["components"] == 1_000_000
+    # roofline bytes: 64 B per evaluation dominate; the stored-cube path counts 96
+    cat = bench.synth_catalog("c2", 2, 0, 1000)
+    assert bench.k2_algorithmic_bytes(cat, 500) == 64 * 1024 * 500 + (8 + 1 + 24 + 32 + 16) * 500 + 8 * 1024
+    assert bench.k2_algorithmic_bytes(cat, 500, stored_full=True) == 96 * 1024 * 500 + 33 * 500
+
+
+def test_bench_traffic_record_is_never_stale(tmp_path, monkeypatch):
+    """roofline.traffic comes from the committed ncu capture only while the kernel sources hash to the capture's."""
+    import json
+
+    import bench
+
+    rec = bench.traffic_record("n1m")
+    assert set(rec) == {"traffic", "traffic_source"}
+    entry = json.load(open(os.path.join(bench.ROOT, "profiles", "k_eval_traffic.json")))["n1m"]
+    if rec["traffic"] is not None:
+        assert rec["traffic"] == entry["traffic_bytes"] and abs(rec["traffic"] / entry["algorithmic_bytes"] - 1) < 0.01
+    assert bench.traffic_record("c1")["traffic"] is None
