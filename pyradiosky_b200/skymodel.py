@@ -1171,7 +1171,8 @@ class SkyModel:
         this.clear_time_position_specific_params()
         this._polarized_mask = torch.zeros(m, dtype=torch.uint8, device=this.device)
         this._n_polarized = 0
-        for cache in ("_rot", "_subband_cache", "_nan_group_cache", "_nan_cache", "_staging", "_graph", "_rise_lst", "_set_lst"):
+        for cache in ("_rot", "_subband_cache", "_nan_group_cache", "_nan_cache", "_cm_cache", "_compacted", "_staging", "_graph",
+                      "_rise_lst", "_set_lst"):
             this.__dict__.pop(cache, None)
         this.frame_coherency = None
         if had_fc:
@@ -1460,7 +1461,7 @@ class SkyModel:
         self._n_polarized = self._count(self._polarized_mask, _lib.COUNT_NONZERO_U8)
         self._rot_key = None  # the cached rotation coefficients belong to the old component list
         self.__dict__.pop("_rot", None)
-        for cache in ("_subband_cache", "_nan_group_cache", "_nan_cache", "_staging", "_graph"):
+        for cache in ("_subband_cache", "_nan_group_cache", "_nan_cache", "_cm_cache", "_compacted", "_staging", "_graph"):
             self.__dict__.pop(cache, None)
         if self.frame_coherency is not None:
             self.calc_frame_coherency()
@@ -1736,8 +1737,8 @@ class SkyModel:
                                                other.above_horizon.view(torch.uint8), nb).view(torch.bool)
         this.Ncomponents = na + nb
         this._rot_key = None
-        for cache in ("_rot", "_subband_cache", "_nan_group_cache", "_nan_cache", "_staging", "_graph", "_rise_lst",
-                      "_set_lst"):
+        for cache in ("_rot", "_subband_cache", "_nan_group_cache", "_nan_cache", "_cm_cache", "_compacted", "_staging",
+                      "_graph", "_rise_lst", "_set_lst"):
             this.__dict__.pop(cache, None)
         if all(had_fc):
             this.calc_frame_coherency()
