@@ -924,9 +924,12 @@ __device__ __forceinline__ void emit(const EvalParams& p, int f, int64_t col, co
 
 // NT = threads (= columns) per block: 256, except 128 for SUBBAND so that two blocks, each holding its
 // columns' stored spectra in shared memory, fit on an SM and overlap set-up with streaming.
+#ifndef RSK_FULL_NT
+#define RSK_FULL_NT 256  // columns per block in FULL mode (tuning: -DRSK_FULL_NT=128)
+#endif
 template <int MODE>
 struct EvalThreads {
-  static constexpr int value = (MODE == RSK_SUBBAND) ? 128 : kThreads;
+  static constexpr int value = (MODE == RSK_SUBBAND) ? 128 : (MODE == RSK_FULL ? RSK_FULL_NT : kThreads);
 };
 
 // Minimum resident blocks per SM asked of ptxas per mode (register cap); overridable at build time for
@@ -1622,7 +1625,8 @@ int fill_eval_params(const RskSpectrum* spec, const double* freqs, int64_t nf, i
   p->ncols = ncols;
   // Frequency chunking (defaults measured on B200, see the constants at the top of this file).
   const bool dense_subband = spec->mode == RSK_SUBBAND && !spec->bcoef;
-  const int nt = dense_subband ? EvalThreads<RSK_SUBBAND>::value : kThreads;
+  const int nt = dense_subband ? EvalThreads<RSK_SUBBAND>::value
+                               : (spec->mode == RSK_FULL ? EvalThreads<RSK_FULL>::value : kThreads);
   const int64_t tiles = (ncols + nt - 1) / nt;
   // SUBBAND: stage each column's 4 * nf_in stored values in shared memory when they fit
   p->y_in_smem = (dense_subband && !spec->chan_map && 4 * spec->nf_in * nt * (int64_t)sizeof(double) <= kMaxDynSmem) ? 1 : 0;
