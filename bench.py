@@ -704,14 +704,15 @@ def run_sweep(ctx, steps, warmup):
                      "per": "GPU; 17 B per (source, time): alt, az, mask"},
         "host_context_build_ms": host_ctx_s * 1e3,
     }
-    # this kernel is bound by fp64 issue, not by HBM (profiles/r02_sweep_floor.md): 77 fp64-pipe instructions per
+    # this kernel is bound by fp64 issue, not by HBM (profiles/r02_sweep_floor.md): 67 fp64-pipe instructions per
     # evaluation in the SASS of the time loop, 2 dispatch cycles each on the 4 x 148 schedulers
     sm_hz = 1.965e9
-    pipe_ms = (n * nt / 32.0) / (4 * 148) * 77 * 2 / sm_hz * 1e3
-    rec["fp64_pipe"] = {"fp64_instr_per_eval": 77, "pipe_floor_ms": pipe_ms, "frac_of_pipe_floor": pipe_ms / kmax,
+    pipe_ms = (n * nt / 32.0) / (4 * 148) * 67 * 2 / sm_hz * 1e3
+    rec["fp64_pipe"] = {"fp64_instr_per_eval": 67, "pipe_floor_ms": pipe_ms, "frac_of_pipe_floor": pipe_ms / kmax,
                         "hbm_frac_at_pipe_floor": n * nt * 17 / (pipe_ms * 1e-3) / 1e9 / ctx.peak,
                         "note": "floor = fp64 instructions alone at 16 lanes per scheduler and 1965 MHz, per GPU; even at "
-                                "the floor the kernel would sit at 0.63 of the 17-byte HBM roofline"}
+                                "the floor the kernel would sit at 0.72 of the 17-byte HBM roofline (0.63 with the 77 instructions of the "
+                                "full-accuracy-margin routines of round 1)"}
     if ctx.rank == 0:
         k = nt // 3
         ref_alt_az, _ = positions_cpu_baseline(lon[:2000], lat[:2000], astroms[k:k + 1])

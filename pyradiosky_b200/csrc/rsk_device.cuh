@@ -93,6 +93,27 @@ __device__ const double2 kRskAzTab[80] = {
     {0x1.2d97c7f3321d2p+2, -0x0.0p+0}, {0x1.25a2594c87114p+2, -0x1.0000000000000p-3}, {0x1.1dea0cf69bdcbp+2, -0x1.0000000000000p-2}, {0x1.16a1aeb14d3e3p+2, -0x1.8000000000000p-2}, {0x1.0feb60edd061dp+2, -0x1.0000000000000p-1},
     {0x1.09d7b09b741fcp+2, -0x1.4000000000000p-1}, {0x1.0468a8ace4df6p+2, -0x1.8000000000000p-1}, {0x1.ff2cf0d083217p+1, -0x1.c000000000000p-1}, {0x1.f6a7a2955385ep+1, -0x1.0000000000000p+0},  // octant 7
     {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};
+// Sweep-grade tables (rsk_sweep_angles below): 1/16 spacing, so the reduced argument is below 1/32 and a degree-2
+// polynomial in u^2 reaches 3e-15 rad; generated by tools/gen_sweep_tables.py.
+__device__ const double2 kRskAtanTab16[32] = {
+    {0x0.0p+0, 0x0.0p+0}, {0x1.ff55bb72cfdeap-5, 0x1.0000000000000p-4}, {0x1.fd5ba9aac2f6ep-4, 0x1.0000000000000p-3}, {0x1.7b97b4bce5b02p-3, 0x1.8000000000000p-3}, {0x1.f5b75f92c80ddp-3, 0x1.0000000000000p-2}, {0x1.362773707ebccp-2, 0x1.4000000000000p-2}, {0x1.6f61941e4def1p-2, 0x1.8000000000000p-2}, {0x1.a64eec3cc23fdp-2, 0x1.c000000000000p-2}, {0x1.dac670561bb4fp-2, 0x1.0000000000000p-1}, {0x1.0657e94db30d0p-1, 0x1.2000000000000p-1}, {0x1.1e00babdefeb4p-1, 0x1.4000000000000p-1}, {0x1.345f01cce37bbp-1, 0x1.6000000000000p-1}, {0x1.4978fa3269ee1p-1, 0x1.8000000000000p-1}, {0x1.5d58987169b18p-1, 0x1.a000000000000p-1}, {0x1.700a7c5784634p-1, 0x1.c000000000000p-1}, {0x1.819d0b7158a4dp-1, 0x1.e000000000000p-1}, {0x1.921fb54442d18p-1, 0x1.0000000000000p+0},
+    {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};
+__device__ const double kRskCk16[32] = {
+    0x1.0000000000000p+0, 0x1.ff00bf608b827p-1, 0x1.fc0bd88a0f1d9p-1, 0x1.f73b05f60fd39p-1, 0x1.f0b6848d2af1cp-1, 0x1.e8b19984b1caep-1, 0x1.df6689b7e6350p-1, 0x1.d51292feca74cp-1, 0x1.c9f25c5bfedd9p-1, 0x1.be3f2617e31c0p-1, 0x1.b22cd56d87d7ep-1, 0x1.a5e8d2b5f03a5p-1, 0x1.999999999999ap-1, 0x1.8d5ed070ef27dp-1, 0x1.8151bb86fee1dp-1, 0x1.7585e681fe6f2p-1, 0x1.6a09e667f3bcdp-1,
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+__device__ const double2 kRskAzTab16[144] = {
+    {0x0.0p+0, 0x0.0p+0}, {0x1.ff55bb72cfdeap-5, 0x1.0000000000000p-4}, {0x1.fd5ba9aac2f6ep-4, 0x1.0000000000000p-3}, {0x1.7b97b4bce5b02p-3, 0x1.8000000000000p-3}, {0x1.f5b75f92c80ddp-3, 0x1.0000000000000p-2}, {0x1.362773707ebccp-2, 0x1.4000000000000p-2}, {0x1.6f61941e4def1p-2, 0x1.8000000000000p-2}, {0x1.a64eec3cc23fdp-2, 0x1.c000000000000p-2}, {0x1.dac670561bb4fp-2, 0x1.0000000000000p-1}, {0x1.0657e94db30d0p-1, 0x1.2000000000000p-1}, {0x1.1e00babdefeb4p-1, 0x1.4000000000000p-1}, {0x1.345f01cce37bbp-1, 0x1.6000000000000p-1}, {0x1.4978fa3269ee1p-1, 0x1.8000000000000p-1}, {0x1.5d58987169b18p-1, 0x1.a000000000000p-1}, {0x1.700a7c5784634p-1, 0x1.c000000000000p-1}, {0x1.819d0b7158a4dp-1, 0x1.e000000000000p-1}, {0x1.921fb54442d18p-1, 0x1.0000000000000p+0},  // octant 0
+    {0x1.921fb54442d18p+0, -0x0.0p+0}, {0x1.82250768ac529p+0, -0x1.0000000000000p-4}, {0x1.7249faa996a21p+0, -0x1.0000000000000p-3}, {0x1.62acbeaca61b8p+0, -0x1.8000000000000p-3}, {0x1.5368c951e9cfdp+0, -0x1.0000000000000p-2}, {0x1.4495d86823225p+0, -0x1.4000000000000p-2}, {0x1.3647503caf55cp+0, -0x1.8000000000000p-2}, {0x1.288bfa3512419p+0, -0x1.c000000000000p-2}, {0x1.1b6e192ebbe44p+0, -0x1.0000000000000p-1}, {0x1.0ef3c09d694b0p+0, -0x1.2000000000000p-1}, {0x1.031f57e54adbep+0, -0x1.4000000000000p-1}, {0x1.efe068bba2275p-1, -0x1.6000000000000p-1}, {0x1.dac670561bb4fp-1, -0x1.8000000000000p-1}, {0x1.c6e6d2171bf18p-1, -0x1.a000000000000p-1}, {0x1.b434ee31013fdp-1, -0x1.c000000000000p-1}, {0x1.a2a25f172cfe4p-1, -0x1.e000000000000p-1}, {0x1.921fb54442d18p-1, -0x1.0000000000000p+0},  // octant 1
+    {0x1.921fb54442d18p+1, -0x0.0p+0}, {0x1.8a225e5677921p+1, -0x1.0000000000000p-4}, {0x1.8234d7f6ecb9dp+1, -0x1.0000000000000p-3}, {0x1.7a6639f874768p+1, -0x1.8000000000000p-3}, {0x1.72c43f4b1650ap+1, -0x1.0000000000000p-2}, {0x1.6b5ac6d632f9fp+1, -0x1.4000000000000p-2}, {0x1.643382c07913ap+1, -0x1.8000000000000p-2}, {0x1.5d55d7bcaa899p+1, -0x1.c000000000000p-2}, {0x1.56c6e7397f5aep+1, -0x1.0000000000000p-1}, {0x1.5089baf0d60e4p+1, -0x1.2000000000000p-1}, {0x1.4a9f8694c6d6bp+1, -0x1.4000000000000p-1}, {0x1.4507f4d109f29p+1, -0x1.6000000000000p-1}, {0x1.3fc176b7a8560p+1, -0x1.8000000000000p-1}, {0x1.3ac98f27e8652p+1, -0x1.a000000000000p-1}, {0x1.361d162e61b8bp+1, -0x1.c000000000000p-1}, {0x1.31b87267eca85p+1, -0x1.e000000000000p-1}, {0x1.2d97c7f3321d2p+1, -0x1.0000000000000p+0},  // octant 2
+    {0x1.921fb54442d18p+0, 0x0.0p+0}, {0x1.a21a631fd9508p+0, 0x1.0000000000000p-4}, {0x1.b1f56fdeef00fp+0, 0x1.0000000000000p-3}, {0x1.c192abdbdf879p+0, 0x1.8000000000000p-3}, {0x1.d0d6a1369bd34p+0, 0x1.0000000000000p-2}, {0x1.dfa992206280bp+0, 0x1.4000000000000p-2}, {0x1.edf81a4bd64d4p+0, 0x1.8000000000000p-2}, {0x1.fbb3705373617p+0, 0x1.c000000000000p-2}, {0x1.0468a8ace4df6p+1, 0x1.0000000000000p-1}, {0x1.0aa5d4f58e2c0p+1, 0x1.2000000000000p-1}, {0x1.109009519d639p+1, 0x1.4000000000000p-1}, {0x1.16279b155a47bp+1, 0x1.6000000000000p-1}, {0x1.1b6e192ebbe44p+1, 0x1.8000000000000p-1}, {0x1.206600be7bd52p+1, 0x1.a000000000000p-1}, {0x1.251279b802819p+1, 0x1.c000000000000p-1}, {0x1.29771d7e7791fp+1, 0x1.e000000000000p-1}, {0x1.2d97c7f3321d2p+1, 0x1.0000000000000p+0},  // octant 3
+    {0x1.921fb54442d18p+2, -0x0.0p+0}, {0x1.8e2109cd5d31cp+2, -0x1.0000000000000p-4}, {0x1.8a2a469d97c5bp+2, -0x1.0000000000000p-3}, {0x1.8642f79e5ba40p+2, -0x1.8000000000000p-3}, {0x1.8271fa47ac911p+2, -0x1.0000000000000p-2}, {0x1.7ebd3e0d3ae5cp+2, -0x1.4000000000000p-2}, {0x1.7b299c025df29p+2, -0x1.8000000000000p-2}, {0x1.77bac68076ad8p+2, -0x1.c000000000000p-2}, {0x1.74734e3ee1163p+2, -0x1.0000000000000p-1}, {0x1.7154b81a8c6fep+2, -0x1.2000000000000p-1}, {0x1.6e5f9dec84d42p+2, -0x1.4000000000000p-1}, {0x1.6b93d50aa6621p+2, -0x1.6000000000000p-1}, {0x1.68f095fdf593cp+2, -0x1.8000000000000p-1}, {0x1.6674a236159b5p+2, -0x1.a000000000000p-1}, {0x1.641e65b952452p+2, -0x1.c000000000000p-1}, {0x1.61ec13d617bcfp+2, -0x1.e000000000000p-1}, {0x1.5fdbbe9bba775p+2, -0x1.0000000000000p+0},  // octant 4
+    {0x1.2d97c7f3321d2p+2, 0x0.0p+0}, {0x1.3196736a17bcep+2, 0x1.0000000000000p-4}, {0x1.358d3699dd290p+2, 0x1.0000000000000p-3}, {0x1.39748599194aap+2, 0x1.8000000000000p-3}, {0x1.3d4582efc85d9p+2, 0x1.0000000000000p-2}, {0x1.40fa3f2a3a08fp+2, 0x1.4000000000000p-2}, {0x1.448de13516fc1p+2, 0x1.8000000000000p-2}, {0x1.47fcb6b6fe412p+2, 0x1.c000000000000p-2}, {0x1.4b442ef893d87p+2, 0x1.0000000000000p-1}, {0x1.4e62c51ce87ecp+2, 0x1.2000000000000p-1}, {0x1.5157df4af01a9p+2, 0x1.4000000000000p-1}, {0x1.5423a82cce8cap+2, 0x1.6000000000000p-1}, {0x1.56c6e7397f5aep+2, 0x1.8000000000000p-1}, {0x1.5942db015f535p+2, 0x1.a000000000000p-1}, {0x1.5b99177e22a99p+2, 0x1.c000000000000p-1}, {0x1.5dcb69615d31cp+2, 0x1.e000000000000p-1}, {0x1.5fdbbe9bba775p+2, 0x1.0000000000000p+0},  // octant 5
+    {0x1.921fb54442d18p+1, 0x0.0p+0}, {0x1.9a1d0c320e110p+1, 0x1.0000000000000p-4}, {0x1.a20a929198e94p+1, 0x1.0000000000000p-3}, {0x1.a9d93090112c8p+1, 0x1.8000000000000p-3}, {0x1.b17b2b3d6f526p+1, 0x1.0000000000000p-2}, {0x1.b8e4a3b252a92p+1, 0x1.4000000000000p-2}, {0x1.c00be7c80c8f6p+1, 0x1.8000000000000p-2}, {0x1.c6e992cbdb198p+1, 0x1.c000000000000p-2}, {0x1.cd78834f06482p+1, 0x1.0000000000000p-1}, {0x1.d3b5af97af94cp+1, 0x1.2000000000000p-1}, {0x1.d99fe3f3becc5p+1, 0x1.4000000000000p-1}, {0x1.df3775b77bb07p+1, 0x1.6000000000000p-1}, {0x1.e47df3d0dd4d1p+1, 0x1.8000000000000p-1}, {0x1.e975db609d3dep+1, 0x1.a000000000000p-1}, {0x1.ee22545a23ea5p+1, 0x1.c000000000000p-1}, {0x1.f286f82098fabp+1, 0x1.e000000000000p-1}, {0x1.f6a7a2955385ep+1, 0x1.0000000000000p+0},  // octant 6
+    {0x1.2d97c7f3321d2p+2, -0x0.0p+0}, {0x1.29991c7c4c7d6p+2, -0x1.0000000000000p-4}, {0x1.25a2594c87114p+2, -0x1.0000000000000p-3}, {0x1.21bb0a4d4aefap+2, -0x1.8000000000000p-3}, {0x1.1dea0cf69bdcbp+2, -0x1.0000000000000p-2}, {0x1.1a3550bc2a315p+2, -0x1.4000000000000p-2}, {0x1.16a1aeb14d3e3p+2, -0x1.8000000000000p-2}, {0x1.1332d92f65f92p+2, -0x1.c000000000000p-2}, {0x1.0feb60edd061dp+2, -0x1.0000000000000p-1}, {0x1.0ccccac97bbb8p+2, -0x1.2000000000000p-1}, {0x1.09d7b09b741fcp+2, -0x1.4000000000000p-1}, {0x1.070be7b995adbp+2, -0x1.6000000000000p-1}, {0x1.0468a8ace4df6p+2, -0x1.8000000000000p-1}, {0x1.01ecb4e504e6fp+2, -0x1.a000000000000p-1}, {0x1.ff2cf0d083217p+1, -0x1.c000000000000p-1}, {0x1.fac84d0a0e111p+1, -0x1.e000000000000p-1}, {0x1.f6a7a2955385ep+1, -0x1.0000000000000p+0},  // octant 7
+    {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};
+// atan(u) = u + u s (q0 + q1 s + q2 s^2), |u| <= 1/32 + 2^-20: Taylor coefficients, truncation u^9 / 9 = 3.2e-15 rad;
+// sqrt(1 + s) = 1 + s (1/2 + s (-1/8 + s / 16)), s <= 9.8e-4: truncation 5 s^4 / 128 = 3.6e-14 relative
+__constant__ double kRskSweepQ[6] = {-1.0 / 3.0, 1.0 / 5.0, -1.0 / 7.0, 0.5, -0.125, 0.0625};
 // 64-bit literals the chain needs: operands straight from the constant bank (a literal in the code costs two
 // UMOV per use inside the sweep loop)
 __constant__ double kRskC[4] = {1e-6, 1e-300, RSK_HALFPI, RSK_DPI};
@@ -231,6 +252,62 @@ RSK_HD double rsk_azimuth(double y, double x) {
 #endif
 }
 
+// Azimuth (eraAnp(atan2(y, x)), 0 at the zenith) and altitude (atan2(z, sqrt(x^2 + y^2))) of a direction in one go,
+// for the LST-sweep kernel, which is bound by fp64 issue (profiles/r02_sweep_floor.md): 30 fp64 instructions instead of
+// the 43 of rsk_azimuth + rsk_sqrt + rsk_atan2_t, paid for with accuracy margin -- 1/16-spaced tables and a degree-2
+// polynomial (3e-15 rad), one quadratic Newton step on the reciprocal seeds (relative 2^-40 on |u| <= 1/32: 3e-14
+// rad), and sqrt(x^2 + y^2) taken from the azimuth's own reduction, rho = den cos(phi_k) sqrt(1 + u^2), instead of a
+// square root (4e-14 relative).  Total below 1e-13 rad = 0.02 micro-arcseconds against the 1 uas criterion.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void rsk_sweep_angles(double x, double y, double z, double& az_out, double& alt_out) {
+  const bool sw = fabs(y) > fabs(x);
+  const double mn = fabs(sw ? x : y);
+  double mx = fabs(sw ? y : x);
+  const float fmx = (float)mx;
+  float fr;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(fr) : "f"(fmx));
+  const int k = __float2int_rn(16.0f * ((float)mn * fr));  // <= 16 and 0 for NaN, as in rsk_atan2_t
+  int oct = (int)((unsigned)__double2hiint(y) >> 31) * 4 + (int)((unsigned)__double2hiint(x) >> 31) * 2 + (sw ? 1 : 0);
+  oct = fmx == 0.0f ? 0 : oct;  // the zenith itself: azimuth 0 whatever the signs of the zeros
+  const double2 tab = __ldg(&kRskAzTab16[oct * 17 + k]);
+  const double ck = __ldg(&kRskCk16[k]);
+  mx = __hiloint2double(max(__double2hiint(mx), 0x00100000), __double2loint(mx));  // finite quotient at the zenith
+  const double t = fabs(tab.y);
+  const double num = fma(-t, mx, mn);
+  const double den = fma(t, mn, mx);
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+  r = fma(r, fma(-den, r, 1.0), r);
+  const double u = num * r;
+  const double s = u * u;
+  const double p = fma(fma(kRskSweepQ[2], s, kRskSweepQ[1]), s, kRskSweepQ[0]);
+  const double w = fma(u * s, p, u);
+  const double ws = __hiloint2double(__double2hiint(w) ^ (__double2hiint(tab.y) & 0x80000000), __double2loint(w));
+  az_out = tab.x + ws;
+  // rho = |(x, y)| = den cos(phi_k) sqrt(1 + u^2)
+  const double rho = (den * ck) * fma(s, fma(fma(kRskSweepQ[5], s, kRskSweepQ[4]), s, kRskSweepQ[3]), 1.0);
+  // alt = atan2(z, rho), rho >= 0
+  const double az_ = fabs(z);
+  const bool sw2 = az_ > rho;
+  const double mn2 = sw2 ? rho : az_, mx2 = sw2 ? az_ : rho;
+  float fr2;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(fr2) : "f"((float)mx2));
+  const int k2 = __float2int_rn(16.0f * ((float)mn2 * fr2));
+  const double2 tab2 = __ldg(&kRskAtanTab16[k2]);
+  const double num2 = fma(-tab2.y, mx2, mn2);
+  const double den2 = fma(tab2.y, mn2, mx2);
+  double r2;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r2) : "d"(den2));
+  r2 = fma(r2, fma(-den2, r2, 1.0), r2);
+  const double u2 = num2 * r2;
+  const double s2 = u2 * u2;
+  const double p2 = fma(fma(kRskSweepQ[2], s2, kRskSweepQ[1]), s2, kRskSweepQ[0]);
+  double a = tab2.x + fma(u2 * s2, p2, u2);
+  a = sw2 ? kRskC[2] - a : a;
+  alt_out = copysign(a, z);
+}
+#endif
+
 // sin and cos of an angle of catalogue size (|x| <= 16: longitudes, latitudes, HEALPix azimuths): two-term
 // Cody-Waite reduction by pi/2 (exact for |k| <= 10) and the fdlibm kernel polynomials on [-pi/4, pi/4]
 // (< 1 ulp, checked against long double libm).  About a third of the issue slots of libdevice's sincos,
@@ -289,7 +366,9 @@ RSK_HD bool rsk_ctx_folded(const RskCtx& c) {
 // once per block, outside its time loop).
 // UNIT: (with FRAME_DONE) the caller's vector is of unit length to rounding, so p.p is taken as 1 in the light
 // deflection (a relative change of 1e-16 in a term below 3e-5 rad).
-template <bool WANT_LMN, bool FRAME_DONE = false, int FOLD = 0, bool UNIT = false>
+// SWEEP: (device, folded contexts, no direction cosines) alt / az from rsk_sweep_angles instead of the full-margin
+// routines -- the LST-sweep kernel only.
+template <bool WANT_LMN, bool FRAME_DONE = false, int FOLD = 0, bool UNIT = false, bool SWEEP = false>
 RSK_HD RskAltAz rsk_chain_t(const RskCtx& c, double px, double py, double pz, double pp_in = -1.0) {
   if (!FRAME_DONE && c.m_ident == 0.0) {
     const double x = c.m[0] * px + c.m[1] * py + c.m[2] * pz;
@@ -342,6 +421,13 @@ RSK_HD RskAltAz rsk_chain_t(const RskCtx& c, double px, double py, double pz, do
     const double xn = (-c.a1[0]) * ax - c.a1[1] * ay - c.a1[2] * az_;
     const double yaeo = c.a1[3] * ax + c.a1[4] * ay + c.a1[5] * az_;
     const double zaeo = c.a1[6] * ax + c.a1[7] * ay + c.a1[8] * az_;
+#if defined(__CUDA_ARCH__)
+    if (SWEEP && !WANT_LMN) {
+      rsk_sweep_angles(xn, yaeo, zaeo, o.az, o.alt);
+      o.l = o.m = o.n = 0.0;
+      return o;
+    }
+#endif
     o.az = rsk_azimuth(yaeo, xn);  // eraAtioq + eraAnp: [0, 2 pi], 0 at the zenith
     const double r2 = xn * xn + yaeo * yaeo;
     const double rxy = rsk_sqrt(r2);

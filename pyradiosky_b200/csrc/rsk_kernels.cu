@@ -128,7 +128,18 @@ __global__ void __launch_bounds__(kThreads) k_positions_ctxdev(const CoordSrc cs
 
 // minimum resident blocks per SM asked of ptxas for the sweep kernel (register cap); -DRSK_SWEEP_MINB=n to tune
 #ifndef RSK_SWEEP_MINB
-#define RSK_SWEEP_MINB 4  // 64 registers, 4 x 256 threads per SM: best of the measured caps (profiles/r01_sweep_tuning.log)
+#define RSK_SWEEP_MINB 3  // register cap: 3 blocks of 256 threads per SM measured best for the round-2 loop (6.38 ms against
+                          // 6.47 with 4 and 6.73 with 2 for 1M x 1000; round 1's longer loop preferred 4, profiles/r01_sweep_tuning.log)
+#endif
+
+// 1: the sweep's folded, no-lmn path takes alt / az from rsk_sweep_angles (30 instead of 43 fp64 instructions, below
+// 1e-13 rad); 0: the full-margin routines of the single-time kernel.  -DRSK_SWEEP_FAST=0 to compare.
+#ifndef RSK_SWEEP_UNROLL
+#define RSK_SWEEP_UNROLL 2  // time steps per trip of the sweep loop (1 and 4 measured slower, profiles/r02_summary.md)
+#endif
+constexpr int kSweepUnroll = RSK_SWEEP_UNROLL;
+#ifndef RSK_SWEEP_FAST
+#define RSK_SWEEP_FAST 1
 #endif
 
 // The time loop of the sweep kernel.  MASK: the horizon mask is wanted; with CPT == 1 threads past the end of the
@@ -137,12 +148,12 @@ template <int CPT, bool WANT_LMN, int FOLD, bool MASK>
 __device__ __forceinline__ void sweep_times(const RskCtx* s_ctx, const int ntc, const int64_t n, const int64_t* idx,
                                             const double* px, const double* py, const double* pz, double** pa,
                                             double** pl, uint8_t** pm) {
-#pragma unroll 2
+#pragma unroll kSweepUnroll
   for (int k = 0; k < ntc; ++k) {
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
       // (px, py, pz) is a product of sines and cosines, rotated by an orthogonal matrix at most: unit length
-      const RskAltAz o = rsk_chain_t<WANT_LMN, true, FOLD, true>(s_ctx[k], px[j], py[j], pz[j]);
+      const RskAltAz o = rsk_chain_t<WANT_LMN, true, FOLD, true, RSK_SWEEP_FAST != 0>(s_ctx[k], px[j], py[j], pz[j]);
       if (CPT == 1 || idx[j] < n) {
         __stcs(pa[j], o.alt);
         __stcs(pa[j] + n, o.az);

@@ -286,9 +286,11 @@ def test_device_chain_reproduces_erfa_check_values(rsk, site):
     for astrom, ra, dec, want_alt, want_az in ((a, q["rc"], q["dc"], q["di"], (np.pi - q["ri"]) % (2 * np.pi)),
                                                (b, o["ri"], o["di"], np.pi / 2 - o["zob"], o["aob"])):
         sky = rsk.SkyModel(ra=[ra], dec=[dec], stokes=st, spectral_type="flat")
-        alt_az, _, _ = sky.positions_sweep([time, time], loc, astroms=np.stack([astrom, astrom]))
-        got = alt_az.cpu().numpy()
-        assert np.abs(got[:, 0, 0] - want_alt).max() < 1e-14 and np.abs(got[:, 1, 0] - want_az).max() < 1e-14
+        for lmn in (True, False):  # False: the sweep-grade angle routine (below 1e-13 rad by construction)
+            alt_az, _, _ = sky.positions_sweep([time, time], loc, astroms=np.stack([astrom, astrom]), want_lmn=lmn)
+            got = alt_az.cpu().numpy()
+            tol = 1e-14 if lmn else 1e-13
+            assert np.abs(got[:, 0, 0] - want_alt).max() < tol and np.abs(got[:, 1, 0] - want_az).max() < tol
 
 
 def test_astropy_context_bytes_give_astropy_alt_az(rsk):
