@@ -207,9 +207,9 @@ class PeerGather:
         counts, col0, total = exchange_counts(n_above, self.device, self.group)
         if total > self.ld:
             raise ValueError(f"gathered array needs {total} columns, the buffer has {self.ld}")
+        # every rank computes its own columns into its own copy; the destinations other than itself get them by copy
         targets = [(self.rank + k) % self.world for k in range(1, self.world)] if dst is None else (
             [] if int(dst) == self.rank else [int(dst)])
-        compute_here = dst is None or int(dst) == self.rank or bool(targets)
         self.handle.barrier()  # nobody is still reading the previous step's array
         main = torch.cuda.current_stream(self.device)
         lib = _lib.load()
@@ -222,7 +222,7 @@ class PeerGather:
         k = 0
         for s in range(nslab):
             c0, c1 = s * per, min(n_above, (s + 1) * per)
-            if c0 >= c1 or not compute_here:
+            if c0 >= c1:
                 break
             sub = dict(plan)
             sub["idx"] = None if plan["idx"] is None else plan["idx"][c0:c1]

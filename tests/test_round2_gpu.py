@@ -1,6 +1,7 @@
 """GPU parity tests added in round 2: cache invalidation after in-place unit changes, ``at_frequencies``
 book-keeping, the channel-picking interpolation kinds, NaN handling beyond 64 subbands, subband ``visibility_calc``,
-SkyH5 round trips of point objects that came from HEALPix maps, the source-tiled 'full' coherency kernel."""
+SkyH5 round trips of point objects that came from HEALPix maps, the component-major stored-cube path, ERFA's check
+vectors through the position kernels, the overlap of positions with the previous step's coherency kernel."""
 
 import warnings
 
