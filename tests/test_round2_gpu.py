@@ -367,3 +367,56 @@ def test_position_overlap_is_bit_identical(rsk, site, spectral_type, frame):
     sky.update_positions(time + 0.7, loc)
     ref.update_positions(time + 0.7, loc)
     assert torch.equal(sky.alt_az, ref.alt_az)
+
+
+def test_position_overlap_survives_select_and_healpix(rsk, site):
+    """The overlap's buffer sets follow the component list (select) and work for HEALPix maps (pixel centres generated
+    in the kernel on the side stream)."""
+    time, loc = site
+    rng = np.random.default_rng(101)
+    sky = make_model(rsk, rng, "spectral_index", 9000)[0]
+    ref = sky.copy()
+    sky.enable_position_overlap()
+    freqs = np.linspace(1e8, 2e8, 5)
+    sky.update_positions(time, loc)
+    keep = torch.arange(0, 9000, 3, device="cuda")
+    sky.select(component_inds=keep)
+    ref.select(component_inds=keep)
+    for k in range(3):
+        sky.update_positions(time + 0.02 * (k + 1), loc)
+        ref.update_positions(time + 0.02 * (k + 1), loc)
+        assert sky.alt_az.shape == (2, 3000) and torch.equal(sky.alt_az, ref.alt_az)
+        assert torch.equal(sky.coherency_calc(freqs=freqs, pad=False), ref.coherency_calc(freqs=freqs, pad=False))
+    st = polarized_stokes(rng, 12 * 16 * 16)
+    hp_sky = rsk.SkyModel(nside=16, hpx_order="nested", stokes=st, spectral_type="flat", stokes_unit="K")
+    hp_ref = hp_sky.copy()
+    hp_sky.enable_position_overlap()
+    for k in range(3):
+        hp_sky.update_positions(time + 0.1 * k, loc)
+        hp_ref.update_positions(time + 0.1 * k, loc)
+        assert torch.equal(hp_sky.alt_az, hp_ref.alt_az) and torch.equal(hp_sky.above_horizon, hp_ref.above_horizon)
+        assert torch.equal(hp_sky.coherency_calc(pad=False), hp_ref.coherency_calc(pad=False))
+
+
+@pytest.mark.filterwarnings("ignore:Some Stokes values are NaNs")
+@pytest.mark.filterwarnings("ignore:invalid value encountered")
+@pytest.mark.filterwarnings("ignore:.*components had")
+def test_apparent_coherency_with_nan_spectra(rsk, site):
+    """apparent_coherency_calc on a NaN-bearing subband catalogue (round 1: NotImplementedError): J C J^H of what
+    coherency_calc gives, NaN columns included."""
+    time, loc = site
+    rng = np.random.default_rng(102)
+    sky, lon, lat, st, kw = make_model(rsk, rng, "subband", 2000)
+    st[2, 4:9, ::13] = np.nan
+    st[:, :, 7] = np.nan
+    sky = rsk.SkyModel(lon=lon, lat=lat, stokes=st, spectral_type="subband", freq_array=kw["freq_array"])
+    freqs = np.linspace(90e6, 200e6, 9)
+    sky.update_positions(time, loc)
+    coh = sky.coherency_calc(freqs=freqs, pad=False)
+    app = sky.apparent_coherency_calc(beam="uniform", freqs=freqs, pad=False)
+    # identity Jones: the same numbers wherever the whole 2x2 matrix is finite; a NaN in any entry of C spreads over
+    # all of J C J^H (0 * NaN = NaN in IEEE arithmetic), exactly as the einsum of tests/test_skymodel.py:1464-1466 does
+    bad = torch.isnan(torch.view_as_real(coh)).any(dim=-1).any(dim=0).any(dim=0)  # (Nf, N_above)
+    assert bool(bad.any()) and not bool(bad.all())
+    assert torch.equal(app[:, :, ~bad], coh[:, :, ~bad])
+    assert bool(torch.isnan(torch.view_as_real(app[:, :, bad])).any(dim=-1).all())
