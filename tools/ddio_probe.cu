@@ -14,12 +14,14 @@
 #include <cuda_runtime.h>
 #include <immintrin.h>
 
+static int g_wc = 0;  // staging in write-combined pinned memory, read with streaming loads
+
 static void expand(const double* in, double* out, size_t n) {  // n doubles in -> 2n doubles out
   size_t i = 0;
 #if defined(__AVX512F__)
   const __m512d zero = _mm512_setzero_pd();
   for (; i + 8 <= n; i += 8) {
-    const __m512d v = _mm512_loadu_pd(in + i);
+    const __m512d v = g_wc ? _mm512_castsi512_pd(_mm512_stream_load_si512((void*)(in + i))) : _mm512_loadu_pd(in + i);
     _mm512_stream_pd(out + 2 * i, _mm512_mask_expand_pd(zero, 0x55, v));
     _mm512_stream_pd(out + 2 * i + 8, _mm512_mask_expand_pd(zero, 0x55, _mm512_castpd256_pd512(_mm512_extractf64x4_pd(v, 1))));
   }
@@ -31,9 +33,9 @@ static void expand(const double* in, double* out, size_t n) {  // n doubles in -
 int main(int argc, char** argv) {
   const int T = argc > 1 ? atoi(argv[1]) : 12;
   const double secs = argc > 2 ? atof(argv[2]) : 0.6;
+  g_wc = argc > 3 ? atoi(argv[3]) : 0;
   const size_t out_bytes = 256ull << 20;  // per worker, wrapped
-  const size_t sizes[] = {128ull << 10, 256ull << 10, 512ull << 10, 1ull << 20, 2ull << 20, 4ull << 20,
-                          16ull << 20, 64ull << 20};
+  const size_t sizes[] = {1ull << 20, 4ull << 20, 16ull << 20, 64ull << 20};
   for (size_t S : sizes) {
     std::atomic<long long> copied{0};
     std::atomic<bool> stop{false};
@@ -46,12 +48,14 @@ int main(int argc, char** argv) {
         double *dev, *stage[2], *out;
         cudaMalloc(&dev, S);
         cudaMemset(dev, 1, S);
-        cudaHostAlloc(&stage[0], S, cudaHostAllocDefault);
-        cudaHostAlloc(&stage[1], S, cudaHostAllocDefault);
+        cudaHostAlloc(&stage[0], S, g_wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+        cudaHostAlloc(&stage[1], S, g_wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
         out = static_cast<double*>(aligned_alloc(4096, out_bytes));
         memset(out, 0, out_bytes);
-        memset(stage[0], 0, S);
-        memset(stage[1], 0, S);
+        if (!g_wc) {
+          memset(stage[0], 0, S);
+          memset(stage[1], 0, S);
+        }
         cudaEvent_t ev[2];
         cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
@@ -85,7 +89,7 @@ int main(int argc, char** argv) {
     stop = true;
     for (auto& th : pool) th.join();
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() + 0.15;
-    printf("threads %2d  slab %8zu KB  staging total %7.1f MB  D2H+expand %.1f GB/s in (%.1f GB/s out)\n", T, S >> 10,
+    printf("wc %d threads %2d  slab %8zu KB  staging total %7.1f MB  D2H+expand %.1f GB/s in (%.1f GB/s out)\n", g_wc, T, S >> 10,
            T * 2.0 * S / 1048576.0, copied.load() / dt / 1e9, 2.0 * copied.load() / dt / 1e9);
     fflush(stdout);
   }
