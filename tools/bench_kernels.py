@@ -113,7 +113,11 @@ def main():
     freqs = np.linspace(100e6, 200e6, nf)
     sky = SkyModel(lon=lon, lat=lat, frame="fk5", stokes=s1, spectral_type="spectral_index",
                    spectral_index=np.clip(rng.normal(-0.8, 0.2, n), -2, 1), reference_frequency=np.full(n, 200e6))
-    rec("k_eval<spectral_index,stokes> at_frequencies 300k x 1024", timeit(lambda: sky.at_frequencies(freqs, inplace=False)),
+    # run_check=False: the kernel alone (the reference's default run_check=True adds SkyModel.check: three scans of the new
+    # cube for NaNs / negative Stokes I, measured on the next line)
+    rec("at_frequencies 300k x 1024 with run_check (3 acceptability scans of the 9.8 GB cube, host syncs)",
+        timeit(lambda: sky.at_frequencies(freqs, inplace=False)), 32 * freqs.size * n, "32 B/eval written by K3; the scans read 9.8 + 2.5 GB more")
+    rec("k_eval<spectral_index,stokes> at_frequencies 300k x 1024", timeit(lambda: sky.at_frequencies(freqs, inplace=False, run_check=False)),
         32 * n * nf, "32 B/eval written")
     # N4: coherency_calc + Jones contraction fused (apparent coherency), analytic and caller-supplied beams
     sky.update_positions(t0, loc)
