@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSK_VERSION 100 /* 0.1.0 */
+#define RSK_VERSION 200 /* 0.2.0: RskSpectrum gained group_of / group / stokes_cm; rsk_count, rsk_copy_2d, rsk_stokes_component_major; rsk_valid_channels writes multi-word masks */
 
 /* Length of the astrometry context: exactly ERFA's eraASTROM / erfa.dt_eraASTROM, as doubles:
  * pmt, eb[3], eh[3], em, v[3], bm1, bpn[3][3] (row-major), along, phi, xpl, ypl, sphi, cphi, diurab,
