@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(librsk):
     assert declared == set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(librsk, name), name
-    assert librsk.rsk_version() == 100
+    assert librsk.rsk_version() == 200
     assert librsk.rsk_strerror(0) == b"success"
     assert b"pointer" in librsk.rsk_strerror(-1)
 
