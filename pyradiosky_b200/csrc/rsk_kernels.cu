@@ -25,6 +25,20 @@ constexpr int kMaxFChunk = 256;     // frequencies staged in shared memory per b
 // RSK_K2_SMEM override them for tuning runs.
 constexpr int kDefaultFChunk = 64;
 constexpr int kFullCmFChunk = 32;            // FULL mode reading the component-major copy (measured)
+#ifndef RSK_FULL_BATCH
+#define RSK_FULL_BATCH 8
+#endif
+// FULL mode: channels whose loads a thread issues together.  Measured on the stored (4, 1024, 300k) cube, component-major
+// reads: 1 / 2 / 4 / 8 / 16 -> 0.857 / 0.865 / 0.871 / 0.929 / 0.855 of the 96 B/eval roofline (8: 110 registers, two
+// blocks per SM; 16: 176 registers, one); a cp.async ring (0.63) and L2 prefetches of the chunk (0.84) are slower.
+constexpr int kFullBatch = RSK_FULL_BATCH;
+#ifndef RSK_CM_DENSITY8
+#define RSK_CM_DENSITY8 8  // blocks whose columns are at least this / 8 dense in the catalogue read the (4, Nf, N) cube
+#endif
+#ifndef RSK_FULL_BATCH_PLAIN
+#define RSK_FULL_BATCH_PLAIN 4
+#endif
+constexpr int kFullBatchPlain = RSK_FULL_BATCH_PLAIN;  // the same for the gathered (4, Nf, N) reads (four 8-byte loads per channel)
 constexpr int kSubbandFChunk = 256;          // longer chunks: the per-block staging cost is amortised (measured)
 constexpr int kMaxDynSmem = 200 * 1024;      // dynamic shared memory budget per block
 constexpr int kDefaultTileFast = 0;
@@ -951,11 +965,15 @@ struct EvalThreads {
 #ifndef RSK_MINB_BANDED
 #define RSK_MINB_BANDED 1
 #endif
+#ifndef RSK_MINB_FULL
+#define RSK_MINB_FULL 1
+#endif
 template <int MODE, int EPI>
 struct EvalMinBlocks {
   // the Jones epilogue needs ~140 registers: cap at 128 (two 256-thread blocks per SM), not at 80
   static constexpr int value = EPI == 2 ? (EvalThreads<MODE>::value == 256 ? 2 : 1)
-                               : (MODE == RSK_SPECTRAL_INDEX) ? RSK_MINB_SI : (MODE == 4 ? RSK_MINB_BANDED : 1);
+                               : (MODE == RSK_SPECTRAL_INDEX) ? RSK_MINB_SI
+                               : (MODE == 4 ? RSK_MINB_BANDED : (MODE == RSK_FULL ? RSK_MINB_FULL : 1));
 };
 
 template <int MODE, int EPI>
@@ -963,6 +981,8 @@ __global__ void __launch_bounds__(EvalThreads<MODE>::value, EvalMinBlocks<MODE, 
 k_eval(const __grid_constant__ EvalParams p) {
   constexpr int NT = EvalThreads<MODE>::value;
   constexpr bool COH = EPI != kEpiStokes;
+  constexpr int FB = EPI == kEpiApparent ? 2 : kFullBatch;  // (the Jones epilogue has no registers to spare)
+  constexpr int FBP = EPI == kEpiApparent ? 2 : kFullBatchPlain;
   extern __shared__ double s_dyn[];    // SUBBAND: [4 * nf_in][NT] stored Stokes of this block's columns
   __shared__ double s_fa[kMaxFChunk];  // SPECTRAL_INDEX: ln(f / pivot); SUBBAND: local coordinate u
   __shared__ int s_iv[kMaxFChunk];     // SUBBAND: break interval; FULL: stored channel
@@ -1005,15 +1025,17 @@ k_eval(const __grid_constant__ EvalParams p) {
   if (MODE != RSK_FLAT) __syncthreads();
 
   // FULL with a component-major copy: which layout this block reads is decided per block from how densely its
-  // columns sit in the catalogue (measured on B200: the gathered (4, Nf, N) reads win above ~0.75 -- they are
-  // coalesced and nearly every fetched sector is used -- the per-component rows below it)
+  // columns sit in the catalogue.  Measured on B200 with the batched loads below: the component-major rows win at every
+  // density below 1 (0.77 / 0.91 / 0.93 / 0.94 / 0.945 of the 96 B/eval roofline at 0.05 / 0.25 / 0.5 / 0.75 / 0.95
+  // against 0.21 / 0.48 / 0.69 / 0.83 / 0.90 for the gathered (4, Nf, N) reads); a block whose columns are contiguous
+  // in the catalogue reads the cube's rows (0.949, the same).
   bool use_cm = false;
   if (MODE == RSK_FULL && p.stokes_cm) {
     use_cm = true;
     if (p.idx && !p.cols) {
       const int64_t k0 = tile * NT, k1 = min(k0 + NT, ncols) - 1;
       const int64_t span = __ldg(p.idx + k1) - __ldg(p.idx + k0) + 1;
-      use_cm = 4 * (k1 - k0 + 1) < 3 * span;
+      use_cm = 8 * (k1 - k0 + 1) < RSK_CM_DENSITY8 * span;
     } else if (!p.idx && !p.cols) {
       use_cm = false;  // every component is a column: plain coalesced rows
     }
@@ -1200,8 +1222,25 @@ k_eval(const __grid_constant__ EvalParams p) {
     // mask looks like (the gathered reads below fetch nearly every sector of a scattered mask's gaps too).  One
     // 256-bit load per evaluation.
     const double* __restrict__ row = reinterpret_cast<const double*>(p.stokes_cm) + (int64_t)src * p.nf_in * 4;
-#pragma unroll 4
-    for (int k = 0; k < nfc; ++k) {
+    // The output may alias nothing the kernel reads, but the compiler cannot know: left to itself it issues each
+    // load after the previous channel's stores and a thread has 32 bytes in flight (1024 threads x 32 B = 32 KB per
+    // SM, against ~35 KB that the HBM rate times its latency asks for).  So the loads are batched by hand.
+    int k = 0;
+    for (; k + FB <= nfc; k += FB) {
+      double y[FB][4];
+#pragma unroll
+      for (int u = 0; u < FB; ++u)
+        asm("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];"
+            : "=d"(y[u][0]), "=d"(y[u][1]), "=d"(y[u][2]), "=d"(y[u][3])
+            : "l"(row + 4 * (int64_t)s_iv[k + u]));
+#pragma unroll
+      for (int u = 0; u < FB; ++u) {
+        double o[4];
+        xform<EPI>(rot, y[u][0], y[u][1], y[u][2], y[u][3], o);
+        emit<EPI>(p, f0 + k + u, col, o, jp);
+      }
+    }
+    for (; k < nfc; ++k) {
       double y0, y1, y2, y3;
       asm("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];"
           : "=d"(y0), "=d"(y1), "=d"(y2), "=d"(y3)
@@ -1211,10 +1250,25 @@ k_eval(const __grid_constant__ EvalParams p) {
       emit<EPI>(p, f0 + k, col, o, jp);
     }
   } else {  // RSK_FULL: stored Stokes, skymodel.py:2165-2181 subset + utils.py:42-57
-#pragma unroll 4
-    for (int k = 0; k < nfc; ++k) {
-      // (a cp.async ring for these four 8-byte loads was measured and is slower: 0.93 -> 0.70 on the HEALPix
-      // 'full' map, 0.66 -> 0.53 on the randomly gathered catalogue; 16-byte copies are what that path is good at)
+    // (a cp.async ring for these four 8-byte loads was measured and is slower: 0.93 -> 0.70 on the HEALPix
+    // 'full' map, 0.66 -> 0.53 on the randomly gathered catalogue; 16-byte copies are what that path is good at)
+    int k = 0;
+    for (; k + FBP <= nfc; k += FBP) {  // loads batched by hand, as above
+      double y[FBP][4];
+#pragma unroll
+      for (int u = 0; u < FBP; ++u) {
+        const double* yp = p.stokes + (int64_t)s_iv[k + u] * p.n + src;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) y[u][q] = __ldcs(yp + q * sstride);
+      }
+#pragma unroll
+      for (int u = 0; u < FBP; ++u) {
+        double o[4];
+        xform<EPI>(rot, y[u][0], y[u][1], y[u][2], y[u][3], o);
+        emit<EPI>(p, f0 + k + u, col, o, jp);
+      }
+    }
+    for (; k < nfc; ++k) {
       const double* y = p.stokes + (int64_t)s_iv[k] * p.n + src;
       const double y0 = __ldcs(y), y1 = __ldcs(y + sstride), y2 = __ldcs(y + 2 * sstride), y3 = __ldcs(y + 3 * sstride);
       double o[4];

@@ -200,7 +200,7 @@ def test_copy_does_not_share_private_state(rsk, site):
 
 
 @pytest.mark.parametrize("density", [0.0, 0.07, 0.5, 0.93, 1.0])
-@pytest.mark.parametrize("n,nf", [(5003, 37), (256, 1), (70001, 8)])
+@pytest.mark.parametrize("n,nf", [(5003, 37), (256, 1), (70001, 8), (3001, 13)])
 def test_full_coherency_component_major_path(rsk, site, density, n, nf):
     """coherency_calc() on stored 'full' Stokes (the reference-shaped call, skymodel.py:2685, :2704-2710) reading the
     component-major copy of the cube (RskSpectrum.stokes_cm): equal, bit for bit, to the kernel that gathers from the
