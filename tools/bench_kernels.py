@@ -152,7 +152,7 @@ def main():
     buf = torch.empty((2, 2, nf, ld), dtype=torch.complex128, device="cuda")
     rec("k_eval<full,coherency> coherency_calc() on stored Stokes 300k x 1024",
         timeit(lambda: full.coherency_calc(out=buf, sync=False)), 96 * n_above * nf,
-        "96 B/eval algorithmic; reads are gathered through the horizon mask (~1.9x sector amplification at 50% density)")
+        "96 B/eval algorithmic; read from the component-major copy of the cube, 8 loads in flight per thread (the whole call: compaction launches + kernel)")
     del buf
     torch.cuda.empty_cache()
     rec("rsk_stokes_to_coherency 300k x 1024", timeit(lambda: full.calc_frame_coherency(store=False), reps=3), 96 * n * nf)
