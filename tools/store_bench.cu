@@ -73,6 +73,38 @@ __global__ void __launch_bounds__(256) k_pattern_v4(double2* out, int64_t n, int
   }
 }
 
+
+// the K2 pattern with a few reads mixed in: every `period` channels a thread fetches 16 doubles (coalesced rows of src,
+// fresh addresses, i.e. from DRAM) before it goes on storing -- what the banded subband kernel does at a change of break
+// interval (period ~54 on C4: 2.4 B read per 64 B written)
+__global__ void __launch_bounds__(256) k_pattern_reads(double2* out, const double* __restrict__ src, int64_t n, int nf, int fchunk,
+                                                       int nfchunks, int period) {
+  const int64_t tile = blockIdx.x / nfchunks;
+  const int chunk = blockIdx.x - tile * nfchunks;
+  const int f0 = chunk * fchunk;
+  const int nfc = min(fchunk, nf - f0);
+  const int64_t plane = (int64_t)nf * n;
+  const int64_t col = tile * 256 + threadIdx.x;
+  if (col >= n) return;
+  double a = -0.8 + 1e-6 * (double)(col & 1023);
+#pragma unroll 4
+  for (int k = 0; k < nfc; ++k) {
+    if (period > 0 && (f0 + k) % period == 0) {
+      const double* r = src + (int64_t)((f0 + k) / period) * 16 * n + col;
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc += __ldg(r + (int64_t)q * n);
+      a = -0.8 + 1e-9 * acc;
+    }
+    const double v = exp(a * (0.001 * (double)(f0 + k)));
+    double2* d = out + (int64_t)(f0 + k) * n + col;
+    st16<1>(d, v, 0.0);
+    st16<1>(d + plane, v, -v);
+    st16<1>(d + 2 * plane, v, v);
+    st16<1>(d + 3 * plane, v, 0.0);
+  }
+}
+
 // plane-major variant: block loops planes outermost (recompute), to see if fewer concurrent streams help
 template <int OP>
 __global__ void __launch_bounds__(256) k_plane_outer(double2* out, int64_t n, int nf, int fchunk, int nfchunks) {
@@ -128,6 +160,16 @@ int main(int argc, char** argv) {
   for (int blocks : {148 * 8, 148 * 16, 148 * 32}) {
     ms = timeit([&] { k_linear<<<blocks, 256>>>(out, total); });
     printf("linear store grid=%5d          : %7.3f ms  %7.1f GB/s\n", blocks, ms, bytes / ms / 1e6);
+  }
+  if (argc > 3 && argv[3][0] == 'r') {  // a few reads mixed into the write stream
+    for (int fc : {64}) for (int period : {0, 54, 27, 13, 4}) {
+      const int nfchunks = (nf + fc - 1) / fc; const int64_t tiles = (n + 255) / 256;
+      ms = timeit([&] { k_pattern_reads<<<(unsigned)(tiles * nfchunks), 256>>>(out, (const double*)src, n, nf, fc, nfchunks, period); });
+      const double rd = period > 0 ? 128.0 * ((nf + period - 1) / period) * n : 0.0;
+      printf("reads mixed in: period=%3d (%.2f B read per 64 B written) : %7.3f ms  write %7.1f GB/s  total %7.1f GB/s\n", period,
+             rd / (1.0 * nf * n), ms, 64.0 * nf * n / ms / 1e6, (64.0 * nf * n + rd) / ms / 1e6);
+    }
+    return 0;
   }
   if (argc > 3 && argv[3][0] == 'v') {  // 256-bit stores, two adjacent columns per thread
     for (int tf : {0, 1}) for (int fc : {16, 32, 64, 128}) for (int smem : {0, 72 * 1024, 112 * 1024}) {
